@@ -1,0 +1,213 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle (numpy) for the Remhos RK-stage hot path.
+
+End-to-end restatement of remhos() (remhos.cpp:210-1523) for the solver combinations on
+the hot path, used to pin the oracle against the reference's own known answers
+(autotest/out_baseline.dat, remhos_tests.cpp:38-107, README.md:221-259).
+
+ODE solvers restate MFEM's ForwardEuler / RK2Solver(1.0) / RK3SSPSolver / RK4Solver
+(remhos.cpp:488-492; formulas in SURVEY.md 3.2 / Appendix C-10).
+"""
+from dataclasses import dataclass
+import numpy as np
+from . import fe, mesh as meshmod, dg, problems
+from .solvers import Discretization
+
+
+@dataclass
+class Options:                       # defaults: remhos.cpp:216-244
+    mesh_file: str = 'default'
+    problem: int = 0
+    rs_levels: int = 2
+    order: int = 3
+    mesh_order: int = 2
+    ode_solver: int = 3
+    ho_type: int = 3
+    lo_type: int = 0
+    fct_type: int = 0
+    bounds_type: int = 0
+    t_final: float = 4.0
+    dt: float = 0.005
+    max_steps: int = -1
+    verify_bounds: bool = False
+
+
+class Run:
+    """Set-up phase of remhos() (remhos.cpp:438-1121)."""
+
+    def __init__(self, opt, mesh=None):
+        self.opt = opt
+        self.exec_mode = 0 if opt.problem < 10 else 1          # :438-440
+        m = meshmod.read_mesh(opt.mesh_file) if mesh is None else mesh
+        for _ in range(opt.rs_levels):
+            m = meshmod.refine_uniform(m)
+        self.bb_min, self.bb_max = meshmod.bounding_box(m)     # :457
+        m = meshmod.set_curvature(m, opt.mesh_order)           # :513
+        self.mesh = m
+        self.topo = meshmod.Topology(m)
+        dim = m.dim
+        self.space = sp = dg.Space(dim, opt.order, opt.mesh_order)
+        X0 = m.X.copy()
+        prob = opt.problem
+
+        def vel(pts):
+            shp = pts.shape
+            return problems.velocity(prob, pts.reshape(-1, dim), self.bb_min,
+                                     self.bb_max).reshape(shp)
+        self.vel = vel
+        dt = opt.dt
+        if dt < 0.0:                                           # CFL estimate, :538-553
+            gll = sp.gll
+            c = np.array([0.5])
+            Lc = fe.tensor_basis([fe.lagrange(gll, c)] * dim)
+            dLc = [fe.tensor_basis([fe.lagrange_deriv(gll, c) if a == b else fe.lagrange(gll, c)
+                                    for b in range(dim)]) for a in range(dim)]
+            J = sp.jacobians(X0, dLc)
+            det, _ = sp.det_adj(J)
+            length = np.abs(det[:, 0]) ** (1.0 / dim)          # Mesh::GetElementSize
+            xc = np.einsum('qn,eni->eqi', Lc, X0)
+            vc = vel(xc)[:, 0, :]
+            speed = np.sqrt((vc * vc).sum(axis=1) + 1e-14)
+            dt = float(np.min(0.25 * length / speed))
+        self.dt = dt
+        Vnodes = None
+        t_final = opt.t_final
+        if self.exec_mode == 1:                                # mesh velocity, :562-584
+            x = X0.copy()
+            v = vel(x)
+            t = 0.0
+            while t < t_final:
+                t += dt
+                x = x + min(dt, t_final - t) * v
+                v = vel(x)
+            Vnodes = x - X0
+            t_final = 1.0                                      # :1128-1134
+        self.t_final = t_final
+        infl = problems.inflow(prob, sp.dof_points(X0).reshape(-1, dim)).reshape(m.ne, sp.nd)
+        self.disc = Discretization(sp, self.topo, X0, self.exec_mode, vel_fun=vel,
+                                   Vnodes=Vnodes, inflow_vals=infl)
+        self.disc.assemble(0.0)
+        pts = sp.dof_points(X0)                                # ProjectCoefficient, :883
+        self.u = problems.u0(prob, pts.reshape(-1, dim), self.bb_min,
+                             self.bb_max).reshape(m.ne, sp.nd)
+        self.mass0 = float((self.disc.cur.ml * self.u).sum())
+        self.masses0 = self.disc.cur.ml.copy()
+        self.subcell_weights = None
+
+    # ---------------------------------------------------------------- stage operator
+    def mult(self, u, t, dt):
+        """LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult
+        (remhos_solvers.hpp:46-50; remhos.cpp:1596-1739, 1798-1916)."""
+        o, d = self.opt, self.disc
+        if self.exec_mode == 1:
+            d.assemble(t)
+        A = d.cur
+        if o.fct_type:
+            du_ho = d.ho_local_inverse(u)
+            du_lo = self.calc_lo(u, du_ho, dt)
+            umin, umax = d.bounds(u, o.bounds_type)
+            if o.verify_bounds:
+                self.check(u, dt, du_lo, umin, umax, 'LO')
+            if o.fct_type == 2:
+                du = d.fct_clip_scale(u, A.ml, du_ho, du_lo, umin, umax, dt)
+            elif o.fct_type == 1:
+                du = d.fct_flux_based(u, A.ml, du_ho, du_lo, umin, umax, dt)
+            else:
+                raise NotImplementedError('fct type %d' % o.fct_type)
+            if o.verify_bounds:
+                self.check(u, dt, du, umin, umax, 'FCT')
+            return du
+        if o.lo_type:
+            return self.calc_lo(u, None, dt)
+        return d.ho_local_inverse(u)
+
+    def calc_lo(self, u, du_ho, dt):
+        o, d = self.opt, self.disc
+        if o.lo_type == 5:
+            if du_ho is None:
+                du_ho = d.ho_local_inverse(u)
+            return d.lo_mass_based_avg(u, du_ho, dt)
+        if o.lo_type == 1:
+            return d.lo_discrete_upwind(u)
+        if o.lo_type == 3:
+            return d.lo_residual_distribution(u)
+        if o.lo_type == 4:
+            return d.lo_residual_distribution(u, self.get_subcell_weights())
+        raise NotImplementedError('lo type %d' % o.lo_type)
+
+    def get_subcell_weights(self):
+        from .subcell import subcell_weights
+        if self.exec_mode == 1 or self.subcell_weights is None:
+            self.subcell_weights = subcell_weights(self)
+        return self.subcell_weights
+
+    @staticmethod
+    def check(u, dt, du, umin, umax, info, tol=1e-12):         # check_violation, :1576-1594
+        un = u + dt * du
+        bad = (un + tol < umin) | (un > umax + tol)
+        if bad.any():
+            raise RuntimeError(info + ' bounds violation')
+
+    # ---------------------------------------------------------------- time stepping
+    def step(self, u, t, dt):
+        s = self.opt.ode_solver
+        f = self.mult
+        if s == 1:
+            k = f(u, t, dt)
+            return u + dt * k
+        if s == 2:                                             # RK2Solver(1.0)
+            k = f(u, t, dt)
+            x1 = u + 0.5 * dt * k
+            x = u + dt * k
+            k = f(x, t + dt, dt)
+            return x1 + 0.5 * dt * k
+        if s == 3:                                             # RK3SSPSolver
+            k = f(u, t, dt)
+            y = u + dt * k
+            k = f(y, t + dt, dt)
+            y = y + dt * k
+            y = 0.75 * u + 0.25 * y
+            k = f(y, t + dt / 2, dt)
+            y = y + dt * k
+            return (1. / 3) * u + (2. / 3) * y
+        if s == 4:
+            k1 = f(u, t, dt)
+            k2 = f(u + dt / 2 * k1, t + dt / 2, dt)
+            k3 = f(u + dt / 2 * k2, t + dt / 2, dt)
+            k4 = f(u + dt * k3, t + dt, dt)
+            return u + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        raise NotImplementedError('ode solver %d' % s)
+
+    def run(self, callback=None):
+        """Time loop (remhos.cpp:1146-1330) and final mass / max (:1382-1436)."""
+        o = self.opt
+        t, dt = 0.0, self.dt
+        u = self.u
+        ti = 0
+        done = False
+        while not done:
+            dt_real = min(dt, self.t_final - t)
+            u = self.step(u, t, dt_real)
+            t += dt_real
+            ti += 1
+            done = t >= self.t_final - 1e-8 * dt
+            if ti == o.max_steps:
+                done = True
+            if callback:
+                callback(ti, t, u)
+        self.u = u
+        self.t = t
+        self.steps = ti
+        if self.exec_mode == 1:
+            A = self.disc.assemble(t)
+            ml = A.ml
+        else:
+            ml = self.masses0
+        self.final_mass = float((ml * u).sum())
+        self.final_max = float(u.max())
+        return self.final_mass, self.final_max
+
+
+def run(**kw):
+    r = Run(Options(**kw))
+    r.run()
+    return r

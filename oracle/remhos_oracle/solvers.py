@@ -1,0 +1,280 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle (numpy) for the Remhos RK-stage hot path.
+
+The stage operator and its solver components, restated from the reference:
+  LocalInverseHOSolver::CalcHOSolution          remhos_ho.cpp:84-129 (FA-exact semantics)
+  DiscreteUpwind::CalcLOSolution                remhos_lo.cpp:43-100
+  MassBasedAvg::CalcLOSolution                  remhos_lo.cpp:247-324
+  ResidualDistribution::CalcLOSolution          remhos_lo.cpp:111-245
+  Assembly::LinearFluxLumping                   remhos_tools.cpp:876-913
+  DofInfo::ComputeElementsMinMax / ComputeBounds remhos_tools.cpp:497-523, 381-495
+  ClipScaleSolver::CalcFCTSolution              remhos_fct.cpp:449-541
+  FluxBasedFCT::CalcFCTSolution                 remhos_fct.cpp:155-181, 295-446
+  AdvectionOperator::MultUnlimited / LimitMult  remhos.cpp:1596-1739, 1798-1916
+All vectors are element-major [NE, nd] views of length-N arrays.
+"""
+import numpy as np
+from . import dg
+
+
+class Assembled:
+    """Everything that depends on the mesh position (re-assembled per stage in remap,
+    remhos.cpp:1598-1677)."""
+    pass
+
+
+class Discretization:
+    def __init__(self, space, topo, X0, exec_mode, vel_fun=None, Vnodes=None,
+                 inflow_vals=None, need_sparse=False):
+        """vel_fun(points[e,q,dim]) -> v for transport; Vnodes[e,ng,dim] nodal mesh velocity
+        for remap (VectorGridFunctionCoefficient v_mesh_coeff, remhos.cpp:561,655)."""
+        self.sp = space
+        self.topo = topo
+        self.X0 = X0
+        self.exec_mode = exec_mode
+        self.vel_fun = vel_fun
+        self.Vnodes = Vnodes
+        self.ne = X0.shape[0]
+        self.nd = space.nd
+        self.N = self.ne * self.nd
+        self.nbr = dg.nbr_dof_map(topo, space.p)                      # [NE, nf, nfd]
+        self.inflow = (np.zeros((self.ne, self.nd)) if inflow_vals is None else inflow_vals)
+        self.need_sparse = need_sparse
+        self.cur = None
+
+    # ------------------------------------------------------------------ assembly
+    def assemble(self, t=0.0):
+        sp = self.sp
+        A = Assembled()
+        if self.exec_mode == 1:
+            X = self.X0 + t * self.Vnodes
+            vq = np.einsum('qn,eni->eqi', sp.Lt, self.Vnodes)
+            alpha = 1.0
+
+            def vface(pts, f):
+                return np.einsum('qn,eni->eqi', sp.face[f]['L'], self.Vnodes)
+        else:
+            X = self.X0
+            vq = self.vel_fun(sp.quad_points(X))
+            alpha = -1.0
+
+            def vface(pts, f):
+                return self.vel_fun(pts)
+        A.X = X
+        A.M = sp.mass_matrices(X)
+        A.ml = A.M.sum(axis=2)                                        # lumped mass (row sums)
+        A.wdet = sp.quad_detw(X)
+        A.K = sp.conv_matrices(X, vq, alpha)
+        A.bdrInt = sp.face_flux_matrices(X, vface, remap=(self.exec_mode == 1))
+        self.cur = A
+        return A
+
+    # ------------------------------------------------------------------ helpers
+    def face_diffs(self, u, boundary_vals):
+        """xDiff[e,f,j] = u_nbr - u_own at the face DOFs (BdrDofs order).  boundary_vals:
+        None -> exterior state 0 (HO operator), else [NE,nd] exterior values (inflow_gf)."""
+        sp = self.sp
+        uf = u.reshape(-1)
+        own = u[:, sp.bd.T]                                           # [NE, nf, nfd]
+        nb = self.nbr
+        un = np.where(nb >= 0, uf[np.maximum(nb, 0)], 0.0)
+        if boundary_vals is not None:
+            un = np.where(nb >= 0, un, boundary_vals[:, sp.bd.T])
+        return un - own
+
+    def apply_K_HO(self, u):
+        """rhs = K_HO u: volume convection + upwinded face terms (transposed DG trace),
+        exterior state 0 on domain-boundary faces."""
+        A, sp = self.cur, self.sp
+        rhs = np.einsum('eij,ej->ei', A.K, u)
+        diff = self.face_diffs(u, None)
+        contrib = np.einsum('efij,efj->efi', A.bdrInt, diff)
+        for f in range(sp.nf):
+            np.add.at(rhs, (slice(None), sp.bd[:, f]), contrib[:, f, :])
+        return rhs
+
+    def ho_local_inverse(self, u):
+        rhs = self.apply_K_HO(u)
+        return np.linalg.solve(self.cur.M, rhs[:, :, None])[:, :, 0]
+
+    # ------------------------------------------------------------------ LO solvers
+    def lo_mass_based_avg(self, u, du_ho, dt):
+        A, sp = self.cur, self.sp
+        u_new = u + dt * du_ho
+        uq = np.einsum('qi,ei->eq', sp.Bt, u_new)
+        mass = (A.wdet * uq).sum(axis=1)
+        vol = A.wdet.sum(axis=1)
+        return ((mass / vol)[:, None] - u) / dt
+
+    def du_matrix(self, K):
+        """ComputeDiscreteUpwindMatrix on the element-block (volume-only) K
+        (remhos_lo.cpp:76-100)."""
+        Kt = np.swapaxes(K, 1, 2)
+        d = np.maximum(np.maximum(0.0, -K), -Kt)
+        D = K + d
+        idx = np.arange(K.shape[1])
+        dsum = d.sum(axis=2) - d[:, idx, idx]
+        D[:, idx, idx] = K[:, idx, idx] - dsum
+        return D
+
+    def lumped_face_terms(self, u):
+        """sum over faces of LinearFluxLumping with alpha = 0: y_i += (sum_j bdrInt_ij)
+        (u_nbr_i - u_own_i), inflow_gf as exterior state on the boundary."""
+        A, sp = self.cur, self.sp
+        y = np.zeros_like(u)
+        diff = self.face_diffs(u, self.inflow)
+        contrib = A.bdrInt.sum(axis=3) * diff
+        for f in range(sp.nf):
+            np.add.at(y, (slice(None), sp.bd[:, f]), contrib[:, f, :])
+        return y
+
+    def lo_discrete_upwind(self, u):
+        A = self.cur
+        D = self.du_matrix(A.K)
+        y = np.einsum('eij,ej->ei', D, u) + self.lumped_face_terms(u)
+        return y / A.ml
+
+    def lo_residual_distribution(self, u, subcell_weights=None):
+        """ResidualDistribution::CalcLOSolution (remhos_lo.cpp:111-245), gamma = 1.
+        subcell_weights[e, m, c] enables the subcell variant."""
+        A, sp = self.cur, self.sp
+        eps = 1e-15
+        nd = sp.nd
+        z = np.einsum('eij,ej->ei', A.K, u)
+        du = self.lumped_face_terms(u)
+        xmax = u.max(axis=1); xmin = u.min(axis=1); xsum = u.sum(axis=1)
+        rhoP = np.maximum(0.0, z).sum(axis=1)
+        rhoN = np.minimum(0.0, z).sum(axis=1)
+        sumWP = nd * xmax - xsum + eps
+        sumWN = nd * xmin - xsum - eps
+        wP = (xmax[:, None] - u) / sumWP[:, None]
+        wN = (xmin[:, None] - u) / sumWN[:, None]
+        if subcell_weights is not None:
+            gamma = 1.0
+            s2i = dg.sub2ind(sp.p, sp.dim)                           # [ns, nc]
+            us = u[:, s2i]                                           # [NE, ns, nc]
+            fluct = (subcell_weights * us).sum(axis=2)
+            smax = us.max(axis=2); smin = us.min(axis=2); ssum = us.sum(axis=2)
+            nc = s2i.shape[1]
+            swP = nc * smax - ssum + eps
+            swN = nc * smin - ssum - eps
+            fP = np.maximum(0.0, fluct); fN = np.minimum(0.0, fluct)
+            sfP = fP.sum(axis=1); sfN = fN.sum(axis=1)
+            nwP = np.zeros_like(u); nwN = np.zeros_like(u)
+            cP = fP[:, :, None] * ((smax[:, :, None] - us) / swP[:, :, None])
+            cN = fN[:, :, None] * ((smin[:, :, None] - us) / swN[:, :, None])
+            for m in range(s2i.shape[0]):
+                for c in range(nc):
+                    nwP[:, s2i[m, c]] += cP[:, m, c]
+                    nwN[:, s2i[m, c]] += cN[:, m, c]
+            aux = gamma / (rhoP + eps)
+            wP = wP * (1.0 - np.minimum(aux * sfP, 1.0))[:, None] \
+                + np.minimum(aux, 1.0 / (sfP + eps))[:, None] * nwP
+            aux = gamma / (rhoN - eps)
+            wN = wN * (1.0 - np.minimum(aux * sfN, 1.0))[:, None] \
+                + np.maximum(aux, 1.0 / (sfN - eps))[:, None] * nwN
+        return (du + wP * rhoP[:, None] + wN * rhoN[:, None]) / A.ml
+
+    # ------------------------------------------------------------------ bounds
+    def bounds(self, u, bounds_type):
+        sp, topo = self.sp, self.topo
+        xe_min = u.min(axis=1); xe_max = u.max(axis=1)
+        if bounds_type == 0:
+            emin = np.full(topo.n_ent, np.inf); emax = np.full(topo.n_ent, -np.inf)
+            np.minimum.at(emin, topo.lat, xe_min[:, None])
+            np.maximum.at(emax, topo.lat, xe_max[:, None])
+            lat = dg.dof_lattice(sp.p, sp.dim)
+            cls = np.where(lat == 0, 0, np.where(lat == sp.p, 2, 1))
+            t = sum(cls[:, a] * 3 ** a for a in range(sp.dim))       # [nd] macro position
+            ent = topo.lat[:, t]                                      # [NE, nd]
+            return emin[ent], emax[ent]
+        nb = topo.nbr_elem
+        mn = np.where(nb >= 0, xe_min[np.maximum(nb, 0)], np.inf).min(axis=1)
+        mx = np.where(nb >= 0, xe_max[np.maximum(nb, 0)], -np.inf).max(axis=1)
+        mn = np.minimum(mn, xe_min); mx = np.maximum(mx, xe_max)
+        return (np.repeat(mn[:, None], sp.nd, axis=1), np.repeat(mx[:, None], sp.nd, axis=1))
+
+    # ------------------------------------------------------------------ FCT
+    def fct_clip_scale(self, u, m, du_ho, du_lo, umin, umax, dt):
+        eps = 1.0e-15
+        u_new_lo = u + dt * du_lo
+        fmin = m / dt * (umin - u_new_lo)
+        fmax = m / dt * (umax - u_new_lo)
+        f = m * (du_ho - du_lo)
+        f = np.minimum(fmax, np.maximum(fmin, f))
+        # sequential sums in DOF order, as the reference loop
+        sumNeg = np.zeros(u.shape[0]); sumPos = np.zeros(u.shape[0])
+        for j in range(u.shape[1]):
+            sumNeg = sumNeg + np.minimum(f[:, j], 0.0)
+            sumPos = sumPos + np.maximum(f[:, j], 0.0)
+        new_mass = sumNeg + sumPos
+        with np.errstate(divide='ignore', invalid='ignore'):
+            fpos = np.minimum(0.0, f) - np.maximum(0.0, f) * sumNeg[:, None] / sumPos[:, None]
+            f = np.where((new_mass > eps)[:, None], fpos, f)
+            fneg = np.maximum(0.0, f) - np.minimum(0.0, f) * sumPos[:, None] / sumNeg[:, None]
+            f = np.where((new_mass < -eps)[:, None], fneg, f)
+        return du_lo + f / m
+
+    def build_sparse_K_HO(self):
+        """Upper-triangular coupling list of K_HO (volume blocks + face blocks) for the
+        flux-based FCT: arrays (I, J, kij, kji, same_elem, Mij)."""
+        A, sp = self.cur, self.sp
+        ne, nd = self.ne, self.nd
+        import scipy.sparse as sps
+        base = (np.arange(ne) * nd)[:, None, None]
+        ii = np.broadcast_to(base + np.arange(nd)[None, :, None], (ne, nd, nd))
+        jj = np.broadcast_to(base + np.arange(nd)[None, None, :], (ne, nd, nd))
+        rows = [ii.reshape(-1)]; cols = [jj.reshape(-1)]; vals = [A.K.reshape(-1)]
+        for f in range(sp.nf):
+            gi = (np.arange(ne) * nd)[:, None] + sp.bd[None, :, f]    # [NE, nfd] own globals
+            nb = self.nbr[:, f, :]
+            r = np.broadcast_to(gi[:, :, None], (ne, sp.nfd, sp.nfd))
+            c_own = np.broadcast_to(gi[:, None, :], (ne, sp.nfd, sp.nfd))
+            rows.append(r.reshape(-1)); cols.append(c_own.reshape(-1))
+            vals.append((-A.bdrInt[:, f]).reshape(-1))
+            has = nb[:, 0] >= 0
+            c_n = np.broadcast_to(nb[:, None, :], (ne, sp.nfd, sp.nfd))
+            rows.append(r[has].reshape(-1)); cols.append(c_n[has].reshape(-1))
+            vals.append(A.bdrInt[has, f].reshape(-1))
+        Ksp = sps.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                             shape=(self.N, self.N)).tocsr()
+        Ksp.sum_duplicates()
+        KT = Ksp.T.tocsr()
+        # union pattern (structurally symmetric already); take upper triangle
+        P = (abs(Ksp) + abs(KT)).tocoo()
+        mask = P.col > P.row
+        I = P.row[mask]; J = P.col[mask]
+        kij = np.asarray(Ksp[I, J]).reshape(-1)
+        kji = np.asarray(Ksp[J, I]).reshape(-1)
+        same = (I // nd) == (J // nd)
+        Mij = np.zeros(I.size)
+        Mij[same] = A.M[I[same] // nd, I[same] % nd, J[same] % nd]
+        return I, J, kij, kji, same, Mij
+
+    def fct_flux_based(self, u, m, du_ho, du_lo, umin, umax, dt, iter_cnt=1):
+        I, J, kij, kji, same, Mij = self.build_sparse_K_HO()
+        uf = u.reshape(-1); mf = m.reshape(-1); dho = du_ho.reshape(-1)
+        dij = np.maximum(np.maximum(0.0, -kij), -kji)
+        flux = dt * dij * (uf[I] - uf[J])
+        flux = flux + np.where(same, Mij * dt * (dho[I] - dho[J]), 0.0)
+        du_lo_fct = du_lo.reshape(-1).copy()
+        umn = umin.reshape(-1); umx = umax.reshape(-1)
+        du = du_lo_fct.copy()
+        for _ in range(iter_cnt):
+            gp = np.zeros(self.N); gm = np.zeros(self.N)
+            pos = flux >= 0.0
+            np.add.at(gp, I[pos], flux[pos]); np.add.at(gm, J[pos], -flux[pos])
+            np.add.at(gm, I[~pos], flux[~pos]); np.add.at(gp, J[~pos], -flux[~pos])
+            u_lo = uf + dt * du_lo_fct
+            max_pos = np.maximum((umx - u_lo) * mf, 0.0)
+            min_neg = np.minimum((umn - u_lo) * mf, 0.0)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                cp = np.where(gp > max_pos, max_pos / gp, 1.0)
+                cn = np.where(gm < min_neg, min_neg / gm, 1.0)
+            a = np.where(pos, np.minimum(cp[I], cn[J]), np.minimum(cn[I], cp[J]))
+            fa = flux * a
+            du = du_lo_fct.copy()
+            np.add.at(du, I, fa / mf[I] / dt)
+            np.add.at(du, J, -fa / mf[J] / dt)
+            flux = flux - fa
+            du_lo_fct = du.copy()
+        return du.reshape(u.shape)
