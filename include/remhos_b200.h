@@ -1,0 +1,176 @@
+/* remhos_b200 -- C ABI of the B200-native Remhos RK-stage hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The reference
+ * (CEED/Remhos) has no FFI layer; its boundary is the solver classes HOSolver / LOSolver /
+ * FCTSolver / AdvectionOperator.  Each entry point below names the reference
+ * method it replaces (file:line relative to the Remhos source tree).  The C++ classes in
+ * remhos_b200/host/ mirror those class names on top of this ABI; INTEGRATION.md shows the
+ * binding a Remhos maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on error; rmh_last_error() gives the text.
+ *   - all vectors are FP64, element-major: dof = k*nd + j, j lexicographic, x fastest
+ *     (remhos_fct.cpp:492, remhos_lo.cpp:153); index maps are int32.
+ *   - pointers named *_dev are CUDA device pointers on the context's device; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - no hidden device allocation after rmh_ctx_create().
+ *   - there is NO CPU fallback: without a CUDA device every rmh_ctx_* call fails.
+ */
+#ifndef REMHOS_B200_H
+#define REMHOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *rmh_last_error(void);
+int rmh_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host mesh module (CPU only; replaces what remhos.cpp:448-463,510-513 obtains from MFEM's
+ * Mesh: load, uniform refinement, SetCurvature, and the topology DofInfo needs).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rmh_mesh rmh_mesh;
+
+/* Mesh::LoadFromFile for "MFEM mesh v1.0" / "MFEM INLINE mesh v1.0", quads and hexes
+ * (remhos.cpp:448). */
+int rmh_mesh_load(const char *path, rmh_mesh **out);
+/* Cartesian n[0] x n[1] (x n[2]) mesh of [origin, origin+size]; periodic != 0 identifies
+ * opposite sides (the "-m default" generated mesh, remhos.cpp:451-455). */
+int rmh_mesh_cartesian(int dim, const int *n, const double *origin, const double *size,
+                       int periodic, rmh_mesh **out);
+int rmh_mesh_free(rmh_mesh *m);
+/* Mesh::UniformRefinement (remhos.cpp:449,463). */
+int rmh_mesh_refine(rmh_mesh *m, int levels);
+/* Mesh::SetCurvature(order, periodic) (remhos.cpp:513). */
+int rmh_mesh_set_curvature(rmh_mesh *m, int order);
+/* Mesh::GetBoundingBox (remhos.cpp:457). */
+int rmh_mesh_bounding_box(const rmh_mesh *m, double *bb_min, double *bb_max);
+int rmh_mesh_dim(const rmh_mesh *m);
+int rmh_mesh_ne(const rmh_mesh *m);
+int rmh_mesh_nv(const rmh_mesh *m);
+int rmh_mesh_geom_order(const rmh_mesh *m);
+/* element-wise nodal coordinates [ne][(g+1)^dim][dim], Gauss-Lobatto lattice, x fastest */
+const double *rmh_mesh_nodes(const rmh_mesh *m);
+/* element vertices [ne][2^dim], lexicographic corner order */
+const int64_t *rmh_mesh_elem_vertices(const rmh_mesh *m);
+/* Keep only the listed elements (used by the domain decomposition); ids are global. */
+int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *elem_ids, rmh_mesh **out);
+
+/* DofInfo integer maps (remhos_tools.cpp:356-379):
+ *   bdr_dofs [nfd][nf]      ExtractBdrDofs        (:1356-1431)   (row-major nfd x nf)
+ *   nbr_dof  [ne][nf][nfd]  FillNeighborDofs      (:525-676), -1 = domain boundary
+ *   sub2ind  [p^dim][2^dim] FillSubcell2CellDof   (:678-734)
+ *   lat      [ne][3^dim]    entity ids of the H1 space used by ComputeOverlapBounds (:432-495)
+ *   nbr_elem [ne][nf]       face-neighbour elements used by ComputeMatrixSparsityBounds
+ * Any output pointer may be NULL. */
+int rmh_mesh_dof_maps(const rmh_mesh *m, int order, int32_t *bdr_dofs, int32_t *nbr_dof,
+                      int32_t *sub2ind, int32_t *lat, int32_t *n_ent, int32_t *nbr_elem);
+
+/* ------------------------------------------------------------------------------------------
+ * Device context for the RK-stage path.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rmh_ctx rmh_ctx;
+
+typedef struct rmh_desc
+{
+   int32_t dim;          /* 2 or 3 */
+   int32_t order;        /* p: DG_FECollection(order, dim, Positive), remhos.cpp:588-590 */
+   int32_t mesh_order;   /* degree of the nodal geometry (remhos.cpp:222,513) */
+   int32_t exec_mode;    /* 0 transport, 1 remap (remhos.cpp:438-440) */
+   int32_t bounds_type;  /* 0 overlap, 1 matrix sparsity (remhos.cpp:228) */
+   int32_t device;       /* CUDA device ordinal */
+   int64_t ne;           /* owned elements */
+   int64_t ne_ghost;     /* ghost elements whose DOF blocks follow the owned ones (halo) */
+   const double *nodes;      /* host [ne][(mo+1)^dim][dim] element-wise nodal coordinates */
+   const double *vel_nodes;  /* host, same shape: remap mesh velocity v_gf (remhos.cpp:561),
+                                or transport velocity sampled at the nodes when
+                                vel_quad == NULL (exact for velocities of degree <= mo) */
+   const double *vel_quad;   /* host [ne][Q^dim][dim] transport velocity at the volume
+                                quadrature points (VectorFunctionCoefficient, remhos.cpp:537),
+                                may be NULL */
+   const double *vel_face;   /* host [ne][nf][Q^(dim-1)][dim] same at face quadrature points */
+   const int32_t *nbr_dof;   /* host [ne][nf][nfd]; ids >= ne*nd address ghost DOFs */
+   const int32_t *lat;       /* host [ne][3^dim] (bounds_type 0), ids < n_ent */
+   int32_t n_ent;
+   const int32_t *nbr_elem;  /* host [ne][nf] (bounds_type 1), -1 boundary, >= ne ghost */
+   const double *inflow;     /* host [ne*nd] inflow_gf (remhos.cpp:626-637) or NULL (= 0) */
+} rmh_desc;
+
+int rmh_ctx_create(const rmh_desc *desc, rmh_ctx **out);
+int rmh_ctx_destroy(rmh_ctx *ctx);
+int64_t rmh_ctx_ndofs(const rmh_ctx *ctx);   /* ne*nd (owned) */
+int rmh_ctx_nd(const rmh_ctx *ctx);
+int rmh_ctx_nq1d(const rmh_ctx *ctx);
+/* reference-element coordinates of the volume / face quadrature points, so a caller can
+ * evaluate its velocity coefficient there: q1d[Q] Gauss-Legendre points on [0,1] */
+int rmh_ctx_quad_points_1d(const rmh_ctx *ctx, double *q1d, double *w1d);
+
+/* Remap: move the mesh to x0 + t*v and rebuild all quadrature data, mass inverse data and
+ * the lumped mass (AdvectionOperator::MultUnlimited, remhos.cpp:1598-1677). No-op cost in
+ * transport mode. */
+int rmh_set_time(rmh_ctx *ctx, double t, void *stream);
+
+/* lumpedM (remhos.cpp:705-727; remap refresh :1625-1632) */
+int rmh_lumped_mass(rmh_ctx *ctx, double *m_dev, void *stream);
+
+/* K_HO.Mult(u, rhs) (remhos_ho.cpp:122): PA convection + transposed DG-trace face terms */
+int rmh_ho_mult(rmh_ctx *ctx, const double *u_dev, double *rhs_dev, void *stream);
+/* M_inv->Mult(rhs, du) (remhos_ho.cpp:126; exact-inverse semantics of :100-116) */
+int rmh_mass_inv(rmh_ctx *ctx, const double *rhs_dev, double *du_dev, void *stream);
+/* LocalInverseHOSolver::CalcHOSolution (remhos_ho.cpp:84-129) */
+int rmh_ho_local_inverse(rmh_ctx *ctx, const double *u_dev, double *du_dev, void *stream);
+
+/* MassBasedAvg::CalcLOSolution (remhos_lo.cpp:247-288) */
+int rmh_lo_mass_avg(rmh_ctx *ctx, double dt, const double *u_dev, const double *du_ho_dev,
+                    double *du_lo_dev, void *stream);
+/* DiscreteUpwind::CalcLOSolution (remhos_lo.cpp:43-74) */
+int rmh_lo_discrete_upwind(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
+/* ResidualDistribution / PAResidualDistribution::CalcLOSolution
+ * (remhos_lo.cpp:111-245, 967-1035) */
+int rmh_lo_res_dist(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
+
+/* DofInfo::ComputeElementsMinMax (remhos_tools.cpp:497-523) */
+int rmh_elem_min_max(rmh_ctx *ctx, const double *u_dev, double *xe_min_dev,
+                     double *xe_max_dev, void *stream);
+/* DofInfo::ComputeBounds (remhos_tools.hpp:156-170 -> remhos_tools.cpp:381-495) */
+int rmh_bounds(rmh_ctx *ctx, const double *xe_min_dev, const double *xe_max_dev,
+               double *xi_min_dev, double *xi_max_dev, void *stream);
+
+/* ClipScaleSolver::CalcFCTSolution (remhos_fct.cpp:449-541) */
+int rmh_fct_clip_scale(rmh_ctx *ctx, double dt, const double *u_dev, const double *m_dev,
+                       const double *du_ho_dev, const double *du_lo_dev,
+                       const double *xi_min_dev, const double *xi_max_dev, double *du_dev,
+                       void *stream);
+
+/* LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult for the configuration
+ * -ho 3 -lo {1,3,5} -fct 2 (remhos_solvers.hpp:46-50; remhos.cpp:1596-1739,1798-1916):
+ * k = F(u; dt), evaluated by the fused stage kernel.  lo_type follows remhos.cpp:76-77. */
+int rmh_stage(rmh_ctx *ctx, int lo_type, double dt, const double *u_dev, double *k_dev,
+              void *stream);
+/* One fused RK stage: out = a*x0 + b*(y + dt*F(y; dt)); also refreshes the per-element
+ * min/max of `out` kept in the context for the next stage's bounds. x0 may equal y. */
+int rmh_rk_stage(rmh_ctx *ctx, int lo_type, double dt, double a, double b,
+                 const double *x0_dev, const double *y_dev, double *out_dev, void *stream);
+/* ODESolver::Step for -s 1/2/3 (ForwardEuler, RK2Solver(1.0), RK3SSPSolver;
+ * remhos.cpp:488-490) built from rmh_rk_stage; u updated in place, t advanced. */
+int rmh_rk_step(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, double dt,
+                double *u_dev, void *stream);
+/* Same call with HOST state: H2D of u, one step, D2H of u (the end-to-end entry point). */
+int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, double dt,
+                     double *u_host);
+
+/* reductions over owned DOFs: op 0 = sum(a*b) (b may be NULL -> sum a), 1 = min(a), 2 = max(a)
+ * (remhos.cpp:1073-1076,1403-1415; GetMinMax remhos_tools.cpp:1433-1439); result on host */
+int rmh_reduce(rmh_ctx *ctx, int op, const double *a_dev, const double *b_dev, double *out,
+               void *stream);
+
+/* number of kernels this library has launched since the counter was last reset */
+int64_t rmh_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -89,6 +89,7 @@ class Run:
         pts = sp.dof_points(X0)                                # ProjectCoefficient, :883
         self.u = problems.u0(prob, pts.reshape(-1, dim), self.bb_min,
                              self.bb_max).reshape(m.ne, sp.nd)
+        self.u0_min, self.u0_max = float(self.u.min()), float(self.u.max())
         self.mass0 = float((self.disc.cur.ml * self.u).sum())
         self.masses0 = self.disc.cur.ml.copy()
         self.subcell_weights = None

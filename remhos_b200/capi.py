@@ -1,0 +1,265 @@
+"""ctypes binding of librmh_b200.so (the C ABI declared in include/remhos_b200.h).
+
+Thin marshalling only: numpy arrays for host data, raw device pointers (ints) for device
+vectors -- torch tensors are passed as tensor.data_ptr().  Raises RmhError with the library's
+message on any nonzero status.  There is no CPU fallback: importing works without a GPU (so
+the mesh module and symbol checks run anywhere) but every rmh_ctx_* call needs a CUDA device.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librmh_b200.so')
+
+
+class RmhError(RuntimeError):
+    pass
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ('dim', C.c_int32), ('order', C.c_int32), ('mesh_order', C.c_int32),
+        ('exec_mode', C.c_int32), ('bounds_type', C.c_int32), ('device', C.c_int32),
+        ('ne', C.c_int64), ('ne_ghost', C.c_int64),
+        ('nodes', C.c_void_p), ('vel_nodes', C.c_void_p), ('vel_quad', C.c_void_p),
+        ('vel_face', C.c_void_p), ('nbr_dof', C.c_void_p), ('lat', C.c_void_p),
+        ('n_ent', C.c_int32), ('nbr_elem', C.c_void_p), ('inflow', C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RmhError('librmh_b200.so is not built: run __graft_entry__.build() '
+                           '(make -C remhos_b200/csrc)')
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rmh_last_error.restype = C.c_char_p
+        _lib.rmh_mesh_nodes.restype = C.POINTER(C.c_double)
+        _lib.rmh_mesh_elem_vertices.restype = C.POINTER(C.c_int64)
+        _lib.rmh_ctx_ndofs.restype = C.c_int64
+        _lib.rmh_launch_count.restype = C.c_int64
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise RmhError(lib().rmh_last_error().decode())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(x):
+    """device pointer from an int / torch tensor / None"""
+    if x is None:
+        return C.c_void_p(0)
+    if hasattr(x, 'data_ptr'):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+class Mesh:
+    """Host mesh handle (rmh_mesh_*)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def load(cls, path):
+        h = C.c_void_p()
+        check(lib().rmh_mesh_load(path.encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def cartesian(cls, n, size, origin=None, periodic=False):
+        dim = len(n)
+        na = (C.c_int * dim)(*n)
+        sa = (C.c_double * dim)(*size)
+        oa = (C.c_double * dim)(*(origin if origin is not None else [0.0] * dim))
+        h = C.c_void_p()
+        check(lib().rmh_mesh_cartesian(dim, na, oa, sa, int(periodic), C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().rmh_mesh_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def refine(self, levels):
+        check(lib().rmh_mesh_refine(self.h, int(levels)))
+        return self
+
+    def set_curvature(self, order):
+        check(lib().rmh_mesh_set_curvature(self.h, int(order)))
+        return self
+
+    @property
+    def dim(self):
+        return lib().rmh_mesh_dim(self.h)
+
+    @property
+    def ne(self):
+        return lib().rmh_mesh_ne(self.h)
+
+    @property
+    def nv(self):
+        return lib().rmh_mesh_nv(self.h)
+
+    @property
+    def geom_order(self):
+        return lib().rmh_mesh_geom_order(self.h)
+
+    def bounding_box(self):
+        d = self.dim
+        lo = np.zeros(d); hi = np.zeros(d)
+        check(lib().rmh_mesh_bounding_box(self.h, _ptr(lo), _ptr(hi)))
+        return lo, hi
+
+    def nodes(self):
+        d, g = self.dim, self.geom_order
+        n = self.ne * (g + 1) ** d * d
+        p = lib().rmh_mesh_nodes(self.h)
+        return np.ctypeslib.as_array(p, shape=(n,)).reshape(self.ne, (g + 1) ** d, d).copy()
+
+    def elem_vertices(self):
+        d = self.dim
+        p = lib().rmh_mesh_elem_vertices(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.ne * 2 ** d,)).reshape(self.ne, 2 ** d).copy()
+
+    def extract(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        h = C.c_void_p()
+        check(lib().rmh_mesh_extract(self.h, C.c_int64(ids.size), _ptr(ids), C.byref(h)))
+        return Mesh(h)
+
+    def dof_maps(self, order):
+        d, ne, p = self.dim, self.ne, order
+        nf, nfd, nd = 2 * d, (p + 1) ** (d - 1), (p + 1) ** d
+        bd = np.zeros((nfd, nf), dtype=np.int32)
+        nbr = np.zeros((ne, nf, nfd), dtype=np.int32)
+        s2i = np.zeros((max(p, 1) ** d, 2 ** d), dtype=np.int32)
+        lat = np.zeros((ne, 3 ** d), dtype=np.int32)
+        n_ent = C.c_int32(0)
+        nbe = np.zeros((ne, nf), dtype=np.int32)
+        check(lib().rmh_mesh_dof_maps(self.h, int(p), _ptr(bd), _ptr(nbr), _ptr(s2i), _ptr(lat),
+                                      C.byref(n_ent), _ptr(nbe)))
+        return dict(bdr_dofs=bd, nbr_dof=nbr, sub2ind=s2i, lat=lat, n_ent=n_ent.value,
+                    nbr_elem=nbe, nd=nd)
+
+
+class Context:
+    """Device context (rmh_ctx_*): owns the stored quadrature data of one rank."""
+
+    def __init__(self, *, dim, order, mesh_order, exec_mode, bounds_type, nodes, nbr_dof,
+                 vel_nodes=None, vel_quad=None, vel_face=None, lat=None, n_ent=0,
+                 nbr_elem=None, inflow=None, ne_ghost=0, device=0):
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        self._keep = [f64(nodes), f64(vel_nodes), f64(vel_quad), f64(vel_face), i32(nbr_dof),
+                      i32(lat), i32(nbr_elem), f64(inflow)]
+        k = self._keep
+        d = Desc()
+        d.dim, d.order, d.mesh_order = dim, order, mesh_order
+        d.exec_mode, d.bounds_type, d.device = exec_mode, bounds_type, device
+        d.ne = k[0].shape[0]
+        d.ne_ghost = ne_ghost
+        d.nodes, d.vel_nodes, d.vel_quad, d.vel_face = _ptr(k[0]), _ptr(k[1]), _ptr(k[2]), _ptr(k[3])
+        d.nbr_dof, d.lat, d.n_ent, d.nbr_elem, d.inflow = _ptr(k[4]), _ptr(k[5]), n_ent, _ptr(k[6]), _ptr(k[7])
+        self.h = C.c_void_p()
+        check(lib().rmh_ctx_create(C.byref(d), C.byref(self.h)))
+        self._keep = None
+        self.ndofs = lib().rmh_ctx_ndofs(self.h)
+        self.nd = lib().rmh_ctx_nd(self.h)
+        self.ne = d.ne
+        self.nq1d = lib().rmh_ctx_nq1d(self.h)
+
+    def close(self):
+        if self.h:
+            lib().rmh_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def quad_points_1d(self):
+        x = np.zeros(self.nq1d); w = np.zeros(self.nq1d)
+        check(lib().rmh_ctx_quad_points_1d(self.h, _ptr(x), _ptr(w)))
+        return x, w
+
+    # each method mirrors one C entry point; `s` is a cudaStream_t as int (0 = default)
+    def set_time(self, t, s=0):
+        check(lib().rmh_set_time(self.h, C.c_double(t), C.c_void_p(s)))
+
+    def lumped_mass(self, m, s=0):
+        check(lib().rmh_lumped_mass(self.h, _dp(m), C.c_void_p(s)))
+
+    def ho_mult(self, u, rhs, s=0):
+        check(lib().rmh_ho_mult(self.h, _dp(u), _dp(rhs), C.c_void_p(s)))
+
+    def mass_inv(self, rhs, du, s=0):
+        check(lib().rmh_mass_inv(self.h, _dp(rhs), _dp(du), C.c_void_p(s)))
+
+    def ho_local_inverse(self, u, du, s=0):
+        check(lib().rmh_ho_local_inverse(self.h, _dp(u), _dp(du), C.c_void_p(s)))
+
+    def lo_mass_avg(self, dt, u, du_ho, du_lo, s=0):
+        check(lib().rmh_lo_mass_avg(self.h, C.c_double(dt), _dp(u), _dp(du_ho), _dp(du_lo),
+                                    C.c_void_p(s)))
+
+    def lo_discrete_upwind(self, u, du_lo, s=0):
+        check(lib().rmh_lo_discrete_upwind(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
+
+    def lo_res_dist(self, u, du_lo, s=0):
+        check(lib().rmh_lo_res_dist(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
+
+    def elem_min_max(self, u, xe_min, xe_max, s=0):
+        check(lib().rmh_elem_min_max(self.h, _dp(u), _dp(xe_min), _dp(xe_max), C.c_void_p(s)))
+
+    def bounds(self, xe_min, xe_max, xi_min, xi_max, s=0):
+        check(lib().rmh_bounds(self.h, _dp(xe_min), _dp(xe_max), _dp(xi_min), _dp(xi_max),
+                               C.c_void_p(s)))
+
+    def fct_clip_scale(self, dt, u, m, du_ho, du_lo, xi_min, xi_max, du, s=0):
+        check(lib().rmh_fct_clip_scale(self.h, C.c_double(dt), _dp(u), _dp(m), _dp(du_ho),
+                                       _dp(du_lo), _dp(xi_min), _dp(xi_max), _dp(du),
+                                       C.c_void_p(s)))
+
+    def stage(self, lo_type, dt, u, k, s=0):
+        check(lib().rmh_stage(self.h, int(lo_type), C.c_double(dt), _dp(u), _dp(k), C.c_void_p(s)))
+
+    def rk_stage(self, lo_type, dt, a, b, x0, y, out, s=0):
+        check(lib().rmh_rk_stage(self.h, int(lo_type), C.c_double(dt), C.c_double(a),
+                                 C.c_double(b), _dp(x0), _dp(y), _dp(out), C.c_void_p(s)))
+
+    def rk_step(self, ode_solver_type, lo_type, t, dt, u, s=0):
+        tt = C.c_double(t)
+        check(lib().rmh_rk_step(self.h, int(ode_solver_type), int(lo_type), C.byref(tt),
+                                C.c_double(dt), _dp(u), C.c_void_p(s)))
+        return tt.value
+
+    def rk_step_host(self, ode_solver_type, lo_type, t, dt, u_host):
+        tt = C.c_double(t)
+        check(lib().rmh_rk_step_host(self.h, int(ode_solver_type), int(lo_type), C.byref(tt),
+                                     C.c_double(dt), C.c_void_p(int(u_host))))
+        return tt.value
+
+    def reduce(self, op, a, b=None, s=0):
+        out = C.c_double(0.0)
+        check(lib().rmh_reduce(self.h, int(op), _dp(a), _dp(b), C.byref(out), C.c_void_p(s)))
+        return out.value
+
+
+def launch_count(reset=False):
+    return lib().rmh_launch_count(int(reset))

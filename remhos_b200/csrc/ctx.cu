@@ -1,0 +1,1159 @@
+// remhos_b200 device context, kernels' entry points and the C ABI of the RK-stage path.
+// See include/remhos_b200.h for the reference method each entry point replaces.
+#include "../../include/remhos_b200.h"
+#include "common.hpp"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace rmh;
+
+static std::atomic<int64_t> g_launches{0};
+
+#define CUDA_OK(call)                                                                  \
+   do {                                                                                \
+      cudaError_t err__ = (call);                                                      \
+      if (err__ != cudaSuccess)                                                        \
+      {                                                                                \
+         set_error(std::string(#call) + ": " + cudaGetErrorString(err__));             \
+         return 1;                                                                     \
+      }                                                                                \
+   } while (0)
+
+#define LAUNCH_OK()                                                                    \
+   do {                                                                                \
+      g_launches++;                                                                    \
+      cudaError_t err__ = cudaGetLastError();                                          \
+      if (err__ != cudaSuccess)                                                        \
+      {                                                                                \
+         set_error(std::string("kernel launch: ") + cudaGetErrorString(err__));        \
+         return 1;                                                                     \
+      }                                                                                \
+   } while (0)
+
+// ============================================================================ context
+struct rmh_ctx
+{
+   int dim, p, mo, exec_mode, bounds_type, device;
+   int D1, Q, ND, NQ, NF, NFD, NQF, NG1, NGN, N3;
+   int64_t ne, ne_ghost, N;
+   double t_cur;
+   // host tables
+   std::vector<double> hB, hG, hMinv, hw, hxq;
+   // device tables (generic kernels)
+   double *dB = nullptr, *dw = nullptr, *dL = nullptr, *ddL = nullptr, *dLs = nullptr,
+          *ddLs = nullptr;
+   // geometry inputs
+   double *X0 = nullptr, *V = nullptr, *velq = nullptr, *velf = nullptr;
+   // operator (PA) data
+   double *Dvol = nullptr, *detJw = nullptr, *Dface = nullptr, *ml = nullptr, *inflow = nullptr;
+   // face neighbours
+   int32_t *nbr_elem = nullptr;
+   uint8_t *nbr_pat = nullptr;
+   int16_t *pat = nullptr;
+   int npat = 0;
+   // bounds
+   int32_t *lat = nullptr, *ent_off = nullptr, *ent_el = nullptr, *bnbr = nullptr;
+   int32_t n_ent = 0;
+   double *ent_min = nullptr, *ent_max = nullptr, *xe_min = nullptr, *xe_max = nullptr;
+   bool xe_valid = false;
+   // halo
+   double *ughost = nullptr;
+   // scratch
+   double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *red = nullptr;
+   double *pin = nullptr;   // pinned host staging (e2e entry point)
+   double pcg_tol2 = 1e-28;
+   int pcg_maxit = 60;
+   std::vector<void *> allocs;
+};
+
+template <typename Tp>
+static int dev_alloc(rmh_ctx *c, Tp **p, size_t n)
+{
+   void *q = nullptr;
+   if (n == 0) { n = 1; }
+   cudaError_t e = cudaMalloc(&q, n * sizeof(Tp));
+   if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return 1; }
+   c->allocs.push_back(q);
+   *p = (Tp *)q;
+   return 0;
+}
+template <typename Tp>
+static int dev_upload(rmh_ctx *c, Tp **p, const Tp *h, size_t n)
+{
+   if (dev_alloc(c, p, n)) { return 1; }
+   CUDA_OK(cudaMemcpy(*p, h, n * sizeof(Tp), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+// ============================================================================ kernels
+struct GeomArgs
+{
+   int dim, Q, NG1, exec_mode;
+   int64_t ne;
+   double t;
+   const double *X0, *V, *velq, *velf, *L, *dL, *Ls, *dLs, *w;
+   double *Dvol, *detJw, *Dface;
+};
+
+template <int DIM>
+__device__ __forceinline__ void det_adj(const double (&J)[3][3], double &det, double (&adj)[3][3])
+{
+   if (DIM == 2)
+   {
+      det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      adj[0][0] = J[1][1]; adj[0][1] = -J[0][1];
+      adj[1][0] = -J[1][0]; adj[1][1] = J[0][0];
+   }
+   else
+   {
+      adj[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+      adj[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+      adj[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+      adj[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      adj[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+      adj[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+      adj[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      adj[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+      adj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      det = J[0][0] * adj[0][0] + J[0][1] * adj[1][0] + J[0][2] * adj[2][0];
+   }
+}
+
+// Jacobian (and optionally the interpolated nodal velocity) at a reference point given by its
+// per-axis 1-D basis rows l[a][.], dl[a][.]
+template <int DIM>
+__device__ __forceinline__ void eval_geom(const GeomArgs &g, int64_t e, const double *const *l,
+                                          const double *const *dl, double (&J)[3][3],
+                                          double (&v)[3], bool need_v)
+{
+   const int n1 = g.NG1;
+   int nn = 1;
+   for (int a = 0; a < DIM; a++) { nn *= n1; }
+   for (int i = 0; i < 3; i++) { v[i] = 0.0; for (int j = 0; j < 3; j++) { J[i][j] = 0.0; } }
+   const double *X = g.X0 + (size_t)e * nn * DIM;
+   const double *V = g.V ? g.V + (size_t)e * nn * DIM : nullptr;
+   for (int n = 0; n < nn; n++)
+   {
+      int idx[3] = {0, 0, 0}, m = n;
+      for (int a = 0; a < DIM; a++) { idx[a] = m % n1; m /= n1; }
+      double x[3];
+      for (int i = 0; i < DIM; i++)
+      {
+         x[i] = X[n * DIM + i];
+         if (g.exec_mode == 1) { x[i] += g.t * V[n * DIM + i]; }
+      }
+      double lv = 1.0;
+      for (int a = 0; a < DIM; a++) { lv *= l[a][idx[a]]; }
+      for (int j = 0; j < DIM; j++)
+      {
+         double d = 1.0;
+         for (int a = 0; a < DIM; a++) { d *= (a == j) ? dl[a][idx[a]] : l[a][idx[a]]; }
+         for (int i = 0; i < DIM; i++) { J[i][j] += d * x[i]; }
+      }
+      if (need_v) { for (int i = 0; i < DIM; i++) { v[i] += lv * V[n * DIM + i]; } }
+   }
+}
+
+template <int DIM>
+__global__ void k_geom_vol(GeomArgs g)
+{
+   const int Q = g.Q;
+   int NQ = 1;
+   for (int a = 0; a < DIM; a++) { NQ *= Q; }
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= g.ne * NQ) { return; }
+   const int64_t e = idx / NQ;
+   const int q = (int)(idx - e * NQ);
+   int qa[3] = {0, 0, 0}, m = q;
+   double w = 1.0;
+   const double *l[3], *dl[3];
+   for (int a = 0; a < DIM; a++)
+   {
+      qa[a] = m % Q; m /= Q;
+      w *= g.w[qa[a]];
+      l[a] = g.L + qa[a] * g.NG1;
+      dl[a] = g.dL + qa[a] * g.NG1;
+   }
+   double J[3][3], v[3], det, adj[3][3];
+   const bool nodal_v = (g.velq == nullptr);
+   eval_geom<DIM>(g, e, l, dl, J, v, nodal_v);
+   det_adj<DIM>(J, det, adj);
+   if (!nodal_v) { for (int i = 0; i < DIM; i++) { v[i] = g.velq[((size_t)e * NQ + q) * DIM + i]; } }
+   const double alpha = (g.exec_mode == 1) ? 1.0 : -1.0;   // remhos.cpp:648-657
+   for (int c = 0; c < DIM; c++)
+   {
+      double s = 0.0;
+      for (int j = 0; j < DIM; j++) { s += adj[c][j] * v[j]; }
+      g.Dvol[((size_t)e * DIM + c) * NQ + q] = alpha * w * s;
+   }
+   g.detJw[(size_t)e * NQ + q] = w * det;
+}
+
+template <int DIM>
+__global__ void k_geom_face(GeomArgs g)
+{
+   const int Q = g.Q, NF = 2 * DIM;
+   int NQF = 1;
+   for (int a = 0; a < DIM - 1; a++) { NQF *= Q; }
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= g.ne * NF * NQF) { return; }
+   const int64_t e = idx / (NF * NQF);
+   const int r = (int)(idx - e * NF * NQF), f = r / NQF, qf = r - f * NQF;
+   int axis, side;
+   face_axis_side(DIM, f, axis, side);
+   const double *l[3], *dl[3];
+   double w = 1.0;
+   int m = qf;
+   for (int a = 0; a < DIM; a++)
+   {
+      if (a == axis) { l[a] = g.Ls + side * g.NG1; dl[a] = g.dLs + side * g.NG1; }
+      else
+      {
+         const int q = m % Q; m /= Q;
+         w *= g.w[q];
+         l[a] = g.L + q * g.NG1; dl[a] = g.dL + q * g.NG1;
+      }
+   }
+   double J[3][3], v[3], det, adj[3][3];
+   const bool nodal_v = (g.velf == nullptr);
+   eval_geom<DIM>(g, e, l, dl, J, v, nodal_v);
+   det_adj<DIM>(J, det, adj);
+   if (!nodal_v) { for (int i = 0; i < DIM; i++) { v[i] = g.velf[(size_t)idx * DIM + i]; } }
+   const double sgn = side ? 1.0 : -1.0;
+   double vn = 0.0;
+   for (int i = 0; i < DIM; i++) { vn += v[i] * sgn * adj[axis][i]; }
+   // upwinded normal velocity (remhos_tools.cpp:833-845): transport min(0, v.n), remap -max(0, v.n)
+   const double vs = (g.exec_mode == 1) ? -fmax(0.0, vn) : fmin(0.0, vn);
+   g.Dface[idx] = w * vs;
+}
+
+// lumped mass m_i = sum_q B_qi detJw_q  (M_HO * 1, remhos.cpp:721-727)
+__global__ void k_lumped_mass(int dim, int D1, int Q, int64_t ne, const double *B,
+                              const double *detJw, double *ml)
+{
+   int ND = 1, NQ = 1;
+   for (int a = 0; a < dim; a++) { ND *= D1; NQ *= Q; }
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * ND) { return; }
+   const int64_t e = idx / ND;
+   const int i = (int)(idx - e * ND);
+   int ia[3] = {0, 0, 0}, m = i;
+   for (int a = 0; a < dim; a++) { ia[a] = m % D1; m /= D1; }
+   const double *d = detJw + (size_t)e * NQ;
+   double s = 0.0;
+   if (dim == 2)
+   {
+      for (int qy = 0; qy < Q; qy++)
+      {
+         double sx = 0.0;
+         for (int qx = 0; qx < Q; qx++) { sx += B[qx * D1 + ia[0]] * d[qy * Q + qx]; }
+         s += B[qy * D1 + ia[1]] * sx;
+      }
+   }
+   else
+   {
+      for (int qz = 0; qz < Q; qz++)
+      {
+         double sy = 0.0;
+         for (int qy = 0; qy < Q; qy++)
+         {
+            double sx = 0.0;
+            for (int qx = 0; qx < Q; qx++) { sx += B[qx * D1 + ia[0]] * d[(qz * Q + qy) * Q + qx]; }
+            sy += B[qy * D1 + ia[1]] * sx;
+         }
+         s += B[qz * D1 + ia[2]] * sy;
+      }
+   }
+   ml[idx] = s;
+}
+
+// ---------------------------------------------------------------- HO kernel (a) + (b)
+struct HoArgs
+{
+   int64_t ne;
+   const double *u;       // input: solution (mode has MULT) or rhs (mode == SOLVE only)
+   double *out;
+   const double *Dvol, *detJw, *Dface;
+   FaceNbr fn;
+   int mode;              // bit 0: apply K_HO, bit 1: apply M^-1
+   double tol2;
+   int maxit;
+};
+
+template <int DIM, int D1, int Q, int E>
+__global__ void __launch_bounds__(32 * E) k_ho(HoArgs a, const Tab<D1, Q> tab)
+{
+   using S = Smem<DIM, D1, Q, E>;
+   constexpr int T = 32 * E, ND = S::ND, NQ = S::NQ, NF = S::NF, NQF = S::NQF;
+   extern __shared__ double sm[];
+   const int64_t e0 = (int64_t)blockIdx.x * E;
+   const int ne = (int)min((int64_t)E, a.ne - e0);
+   double *U = sm + S::OFF_U, *R = sm + S::OFF_R, *X = sm + S::OFF_X;
+   for (int t = threadIdx.x; t < E * ND; t += T)
+   {
+      U[t] = (t < ne * ND) ? a.u[e0 * ND + t] : 0.0;
+   }
+   __syncthreads();
+   double *res = R;
+   if (a.mode & 1)
+   {
+      vol_apply<DIM, D1, Q, E>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
+      face_apply<DIM, D1, Q, E>(U, R, sm, a.u, a.Dface + (size_t)e0 * NF * NQF, a.fn, e0, ne, tab);
+   }
+   else
+   {
+      for (int t = threadIdx.x; t < E * ND; t += T) { R[t] = U[t]; }
+      __syncthreads();
+   }
+   if (a.mode & 2)
+   {
+      mass_solve<DIM, D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, ne, a.tol2, a.maxit, tab);
+      res = X;
+   }
+   for (int t = threadIdx.x; t < ne * ND; t += T) { a.out[e0 * ND + t] = res[t]; }
+}
+
+__device__ __forceinline__ int lattice_class(int dim, int D1, int i)
+{
+   int t = 0, mul = 1, m = i;
+   for (int a = 0; a < dim; a++)
+   {
+      const int l = m % D1; m /= D1;
+      const int c = (l == 0) ? 0 : ((l == D1 - 1) ? 2 : 1);
+      t += c * mul; mul *= 3;
+   }
+   return t;
+}
+
+// ---------------------------------------------------- fused RK-stage kernel (a)-(e)
+// One launch = HO advection action + element mass solve + MassBasedAvg LO + per-DOF bounds
+// gather + ClipScale + RK combination (+ element min/max of the output for the next stage).
+struct StageArgs
+{
+   HoArgs ho;                 // ho.u = stage input y; ho.out unused
+   const double *ml;          // lumped mass
+   const double *x0;          // RK base state (may alias ho.u)
+   double *out;               // out_mode 0: k = F(y); 1: a*x0 + b*(y + dt*k)
+   double a, b, dt;
+   int out_mode;
+   int bounds_type, dim_n3;
+   const int32_t *lat;        // [NE][3^dim]
+   const double *ent_min, *ent_max;
+   const int32_t *bnbr;       // [NE][NF] (bounds_type 1)
+   const double *xe_min, *xe_max;
+   double *xe_min_out, *xe_max_out;   // may be NULL
+};
+
+template <int DIM, int D1, int Q, int E>
+__global__ void __launch_bounds__(32 * E) k_stage(StageArgs a, const Tab<D1, Q> tab)
+{
+   using S = Smem<DIM, D1, Q, E>;
+   constexpr int T = 32 * E, ND = S::ND, NQ = S::NQ, NF = S::NF, NQF = S::NQF;
+   constexpr int NK = (ND + 31) / 32, N3 = ipow(3, DIM);
+   extern __shared__ double sm[];
+   const int64_t e0 = (int64_t)blockIdx.x * E;
+   const int ne = (int)min((int64_t)E, a.ho.ne - e0);
+   double *U = sm + S::OFF_U, *R = sm + S::OFF_R, *X = sm + S::OFF_X;
+   for (int t = threadIdx.x; t < E * ND; t += T) { U[t] = (t < ne * ND) ? a.ho.u[e0 * ND + t] : 0.0; }
+   __syncthreads();
+   vol_apply<DIM, D1, Q, E>(U, R, sm, a.ho.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
+   face_apply<DIM, D1, Q, E>(U, R, sm, a.ho.u, a.ho.Dface + (size_t)e0 * NF * NQF, a.ho.fn, e0, ne, tab);
+   mass_solve<DIM, D1, Q, E>(R, X, sm, a.ho.detJw + (size_t)e0 * NQ, ne, a.ho.tol2, a.ho.maxit, tab);
+   __syncthreads();
+   // ---- element-wise part: one warp per element
+   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   if (w >= ne) { return; }
+   const int64_t ge = e0 + w;
+   const double dt = a.dt;
+   double m[NK], u[NK], f[NK], lo[NK];
+   double s1 = 0.0, s0 = 0.0;
+#pragma unroll
+   for (int k = 0; k < NK; k++)
+   {
+      const int j = lane + 32 * k;
+      if (j < ND)
+      {
+         m[k] = a.ml[ge * ND + j];
+         u[k] = U[w * ND + j];
+         s1 += m[k] * (u[k] + dt * X[w * ND + j]);
+         s0 += m[k];
+      }
+   }
+   s1 = warp_sum(s1); s0 = warp_sum(s0);
+   const double ubar = s1 / s0;                        // MassBasedAvg, remhos_lo.cpp:278-285
+   double bmin = 0.0, bmax = 0.0;
+   if (a.bounds_type == 1)
+   {
+      bmin = a.xe_min[ge]; bmax = a.xe_max[ge];
+      for (int fc = 0; fc < NF; fc++)
+      {
+         const int nb = a.bnbr[ge * NF + fc];
+         if (nb >= 0) { bmin = fmin(bmin, a.xe_min[nb]); bmax = fmax(bmax, a.xe_max[nb]); }
+      }
+   }
+   double sumPos = 0.0, sumNeg = 0.0;
+#pragma unroll
+   for (int k = 0; k < NK; k++)
+   {
+      const int j = lane + 32 * k;
+      if (j < ND)
+      {
+         double umin = bmin, umax = bmax;
+         if (a.bounds_type == 0)
+         {
+            const int ent = a.lat[ge * N3 + lattice_class(DIM, D1, j)];
+            umin = a.ent_min[ent]; umax = a.ent_max[ent];
+         }
+         lo[k] = (ubar - u[k]) / dt;
+         const double u_new_lo = u[k] + dt * lo[k];
+         const double fmn = m[k] / dt * (umin - u_new_lo);
+         const double fmx = m[k] / dt * (umax - u_new_lo);
+         double fcl = m[k] * (X[w * ND + j] - lo[k]);
+         fcl = fmin(fmx, fmax(fmn, fcl));               // ClipScale, remhos_fct.cpp:490-515
+         f[k] = fcl;
+         sumNeg += fmin(fcl, 0.0);
+         sumPos += fmax(fcl, 0.0);
+      }
+   }
+   sumNeg = warp_sum(sumNeg); sumPos = warp_sum(sumPos);
+   const double new_mass = sumNeg + sumPos;
+   constexpr double eps = 1.0e-15;
+   double omin = INFINITY, omax = -INFINITY;
+#pragma unroll
+   for (int k = 0; k < NK; k++)
+   {
+      const int j = lane + 32 * k;
+      if (j < ND)
+      {
+         double fcl = f[k];
+         if (new_mass > eps) { fcl = fmin(0.0, fcl) - fmax(0.0, fcl) * sumNeg / sumPos; }
+         if (new_mass < -eps) { fcl = fmax(0.0, fcl) - fmin(0.0, fcl) * sumPos / sumNeg; }
+         const double du = lo[k] + fcl / m[k];
+         double o = du;
+         if (a.out_mode == 1) { o = a.a * a.x0[ge * ND + j] + a.b * (u[k] + dt * du); }
+         a.out[ge * ND + j] = o;
+         omin = fmin(omin, o); omax = fmax(omax, o);
+      }
+   }
+   if (a.xe_min_out)
+   {
+      omin = warp_min(omin); omax = warp_max(omax);
+      if (lane == 0) { a.xe_min_out[ge] = omin; a.xe_max_out[ge] = omax; }
+   }
+}
+
+// ------------------------------------------------------------- element-wise kernels
+// one warp per element; generic in nd
+
+// MassBasedAvg (remhos_lo.cpp:247-324): du_lo = (ubar - u)/dt, ubar = sum m (u + dt du_ho) / sum m
+__global__ void k_mass_avg(int64_t ne, int nd, double dt, const double *u, const double *du_ho,
+                           const double *ml, double *du_lo)
+{
+   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (e >= ne) { return; }
+   double s1 = 0.0, s0 = 0.0;
+   for (int j = lane; j < nd; j += 32)
+   {
+      const int64_t i = e * nd + j;
+      const double m = ml[i];
+      s1 += m * (u[i] + dt * du_ho[i]);
+      s0 += m;
+   }
+   s1 = warp_sum(s1); s0 = warp_sum(s0);
+   const double ubar = s1 / s0;
+   for (int j = lane; j < nd; j += 32)
+   {
+      const int64_t i = e * nd + j;
+      du_lo[i] = (ubar - u[i]) / dt;
+   }
+}
+
+// ComputeElementsMinMax (remhos_tools.cpp:497-523)
+__global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_min, double *xe_max)
+{
+   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (e >= ne) { return; }
+   double mn = INFINITY, mx = -INFINITY;
+   for (int j = lane; j < nd; j += 32)
+   {
+      const double v = u[e * nd + j];
+      mn = fmin(mn, v); mx = fmax(mx, v);
+   }
+   mn = warp_min(mn); mx = warp_max(mx);
+   if (lane == 0) { xe_min[e] = mn; xe_max[e] = mx; }
+}
+
+// entity min/max over the elements sharing the entity (CG-dof overlap, remhos_tools.cpp:449-458)
+__global__ void k_ent_min_max(int32_t n_ent, const int32_t *off, const int32_t *el,
+                              const double *xe_min, const double *xe_max, double *ent_min,
+                              double *ent_max)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n_ent) { return; }
+   double mn = INFINITY, mx = -INFINITY;
+   for (int k = off[i]; k < off[i + 1]; k++)
+   {
+      mn = fmin(mn, xe_min[el[k]]); mx = fmax(mx, xe_max[el[k]]);
+   }
+   ent_min[i] = mn; ent_max[i] = mx;
+}
+
+// per-DOF gather (remhos_tools.cpp:468-494)
+__global__ void k_bounds_overlap(int64_t ne, int dim, int D1, int nd, int n3, const int32_t *lat,
+                                 const double *ent_min, const double *ent_max, double *xi_min,
+                                 double *xi_max)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * nd) { return; }
+   const int64_t e = idx / nd;
+   const int i = (int)(idx - e * nd);
+   const int ent = lat[e * n3 + lattice_class(dim, D1, i)];
+   xi_min[idx] = ent_min[ent]; xi_max[idx] = ent_max[ent];
+}
+
+// ComputeMatrixSparsityBounds (remhos_tools.cpp:381-430)
+__global__ void k_bounds_sparsity(int64_t ne, int nf, int nd, const int32_t *nbr,
+                                  const double *xe_min, const double *xe_max, double *xi_min,
+                                  double *xi_max)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * nd) { return; }
+   const int64_t e = idx / nd;
+   double mn = xe_min[e], mx = xe_max[e];
+   for (int f = 0; f < nf; f++)
+   {
+      const int nb = nbr[e * nf + f];
+      if (nb >= 0) { mn = fmin(mn, xe_min[nb]); mx = fmax(mx, xe_max[nb]); }
+   }
+   xi_min[idx] = mn; xi_max[idx] = mx;
+}
+
+// ClipScaleSolver::CalcFCTSolution (remhos_fct.cpp:484-539)
+__global__ void k_clip_scale(int64_t ne, int nd, double dt, const double *u, const double *m,
+                             const double *du_ho, const double *du_lo, const double *umin,
+                             const double *umax, double *du)
+{
+   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (e >= ne) { return; }
+   constexpr int MAXK = 8;   // nd <= 256
+   double f[MAXK];
+   double sumPos = 0.0, sumNeg = 0.0;
+   int k = 0;
+   for (int j = lane; j < nd; j += 32, k++)
+   {
+      const int64_t i = e * nd + j;
+      const double mi = m[i], lo = du_lo[i];
+      const double u_new_lo = u[i] + dt * lo;
+      const double fmn = mi / dt * (umin[i] - u_new_lo);
+      const double fmx = mi / dt * (umax[i] - u_new_lo);
+      double fc = mi * (du_ho[i] - lo);
+      fc = fmin(fmx, fmax(fmn, fc));
+      f[k] = fc;
+      sumNeg += fmin(fc, 0.0);
+      sumPos += fmax(fc, 0.0);
+   }
+   sumNeg = warp_sum(sumNeg); sumPos = warp_sum(sumPos);
+   const double new_mass = sumNeg + sumPos;
+   constexpr double eps = 1.0e-15;
+   k = 0;
+   for (int j = lane; j < nd; j += 32, k++)
+   {
+      const int64_t i = e * nd + j;
+      double fc = f[k];
+      if (new_mass > eps) { fc = fmin(0.0, fc) - fmax(0.0, fc) * sumNeg / sumPos; }
+      if (new_mass < -eps) { fc = fmax(0.0, fc) - fmin(0.0, fc) * sumPos / sumNeg; }
+      du[i] = du_lo[i] + fc / m[i];
+   }
+}
+
+// out = a*x0 + b*(y + dt*k)
+__global__ void k_rk_combine(int64_t n, double a, double b, double dt, const double *x0,
+                             const double *y, const double *k, double *out)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { out[i] = a * x0[i] + b * (y[i] + dt * k[i]); }
+}
+
+// block-level reductions -> partial results, finished on the host (deterministic)
+__global__ void k_reduce(int64_t n, int op, const double *a, const double *b, double *part)
+{
+   __shared__ double sh[32];
+   double v = (op == 0) ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+        i += (int64_t)gridDim.x * blockDim.x)
+   {
+      if (op == 0) { v += b ? a[i] * b[i] : a[i]; }
+      else if (op == 1) { v = fmin(v, a[i]); }
+      else { v = fmax(v, a[i]); }
+   }
+   v = (op == 0) ? warp_sum(v) : (op == 1 ? warp_min(v) : warp_max(v));
+   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   if (lane == 0) { sh[w] = v; }
+   __syncthreads();
+   if (w == 0)
+   {
+      const int nw = blockDim.x >> 5;
+      v = (lane < nw) ? sh[lane] : ((op == 0) ? 0.0 : (op == 1 ? INFINITY : -INFINITY));
+      v = (op == 0) ? warp_sum(v) : (op == 1 ? warp_min(v) : warp_max(v));
+      if (lane == 0) { part[blockIdx.x] = v; }
+   }
+}
+
+// ============================================================================ dispatch
+template <int DIM, int D1, int Q, int E>
+static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
+{
+   using S = Smem<DIM, D1, Q, E>;
+   Tab<D1, Q> tab;
+   for (int q = 0; q < Q; q++)
+      for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
+   for (int i = 0; i < D1; i++)
+      for (int j = 0; j < D1; j++) { tab.Minv[i][j] = c->hMinv[i * D1 + j]; }
+   static bool attr_set = false;
+   if (!attr_set)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_ho<DIM, D1, Q, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)S::BYTES));
+      attr_set = true;
+   }
+   const int64_t nb = (a.ne + E - 1) / E;
+   k_ho<DIM, D1, Q, E><<<(unsigned)nb, 32 * E, S::BYTES, s>>>(a, tab);
+   LAUNCH_OK();
+   return 0;
+}
+
+template <int DIM, int D1, int Q>
+static int launch_ho(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
+{
+   constexpr size_t LIM = 110 * 1024;
+   if constexpr (Smem<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 8>(c, a, s); }
+   else if constexpr (Smem<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 4>(c, a, s); }
+   else if constexpr (Smem<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 2>(c, a, s); }
+   else { return launch_ho_E<DIM, D1, Q, 1>(c, a, s); }
+}
+
+#define RMH_DISPATCH(FN, c, ...)                                                          \
+   do {                                                                                   \
+      const int key__ = (c)->dim * 10000 + (c)->D1 * 100 + (c)->Q;                        \
+      switch (key__)                                                                      \
+      {                                                                                   \
+         case 20203: return FN<2, 2, 3>(c, __VA_ARGS__);                                  \
+         case 20304: return FN<2, 3, 4>(c, __VA_ARGS__);                                  \
+         case 20405: return FN<2, 4, 5>(c, __VA_ARGS__);                                  \
+         case 20506: return FN<2, 5, 6>(c, __VA_ARGS__);                                  \
+         case 30204: return FN<3, 2, 4>(c, __VA_ARGS__);                                  \
+         case 30305: return FN<3, 3, 5>(c, __VA_ARGS__);                                  \
+         case 30406: return FN<3, 4, 6>(c, __VA_ARGS__);                                  \
+         case 30507: return FN<3, 5, 7>(c, __VA_ARGS__);                                  \
+         default:                                                                         \
+            set_error("no kernel instantiated for (dim, order+1, nq1d) = (" +            \
+                      std::to_string((c)->dim) + "," + std::to_string((c)->D1) + "," +    \
+                      std::to_string((c)->Q) + ")");                                      \
+            return 1;                                                                     \
+      }                                                                                   \
+   } while (0)
+
+static int dispatch_ho(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
+{
+   RMH_DISPATCH(launch_ho, c, a, s);
+}
+
+template <int DIM, int D1, int Q, int E>
+static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
+{
+   using S = Smem<DIM, D1, Q, E>;
+   Tab<D1, Q> tab;
+   for (int q = 0; q < Q; q++)
+      for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
+   for (int i = 0; i < D1; i++)
+      for (int j = 0; j < D1; j++) { tab.Minv[i][j] = c->hMinv[i * D1 + j]; }
+   static bool attr_set = false;
+   if (!attr_set)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_stage<DIM, D1, Q, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)S::BYTES));
+      attr_set = true;
+   }
+   const int64_t nb = (a.ho.ne + E - 1) / E;
+   k_stage<DIM, D1, Q, E><<<(unsigned)nb, 32 * E, S::BYTES, s>>>(a, tab);
+   LAUNCH_OK();
+   return 0;
+}
+
+template <int DIM, int D1, int Q>
+static int launch_stage(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
+{
+   constexpr size_t LIM = 110 * 1024;
+   if constexpr (Smem<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 8>(c, a, s); }
+   else if constexpr (Smem<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 4>(c, a, s); }
+   else if constexpr (Smem<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 2>(c, a, s); }
+   else { return launch_stage_E<DIM, D1, Q, 1>(c, a, s); }
+}
+
+static int dispatch_stage(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
+{
+   RMH_DISPATCH(launch_stage, c, a, s);
+}
+
+static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
+{
+   GeomArgs g;
+   g.dim = c->dim; g.Q = c->Q; g.NG1 = c->NG1; g.exec_mode = c->exec_mode; g.ne = c->ne; g.t = t;
+   g.X0 = c->X0; g.V = c->V; g.velq = c->velq; g.velf = c->velf;
+   g.L = c->dL; g.dL = c->ddL; g.Ls = c->dLs; g.dLs = c->ddLs; g.w = c->dw;
+   g.Dvol = c->Dvol; g.detJw = c->detJw; g.Dface = c->Dface;
+   const int bs = 128;
+   const int64_t nv = c->ne * c->NQ, nfq = c->ne * c->NF * c->NQF;
+   if (c->dim == 2)
+   {
+      k_geom_vol<2><<<(unsigned)((nv + bs - 1) / bs), bs, 0, s>>>(g); LAUNCH_OK();
+      k_geom_face<2><<<(unsigned)((nfq + bs - 1) / bs), bs, 0, s>>>(g); LAUNCH_OK();
+   }
+   else
+   {
+      k_geom_vol<3><<<(unsigned)((nv + bs - 1) / bs), bs, 0, s>>>(g); LAUNCH_OK();
+      k_geom_face<3><<<(unsigned)((nfq + bs - 1) / bs), bs, 0, s>>>(g); LAUNCH_OK();
+   }
+   k_lumped_mass<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->dim, c->D1, c->Q, c->ne, c->dB,
+                                                                 c->detJw, c->ml);
+   LAUNCH_OK();
+   c->t_cur = t;
+   return 0;
+}
+
+// ============================================================================ C ABI
+extern "C" int64_t rmh_launch_count(int reset)
+{
+   const int64_t v = g_launches.load();
+   if (reset) { g_launches = 0; }
+   return v;
+}
+
+extern "C" int rmh_ctx_destroy(rmh_ctx *c)
+{
+   if (!c) { return 0; }
+   cudaSetDevice(c->device);
+   for (void *p : c->allocs) { cudaFree(p); }
+   if (c->pin) { cudaFreeHost(c->pin); }
+   delete c;
+   return 0;
+}
+
+extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
+{
+   if (!d || !out) { set_error("null argument"); return 1; }
+   if (d->dim != 2 && d->dim != 3) { set_error("dim must be 2 or 3"); return 1; }
+   if (d->order < 1) { set_error("order must be >= 1 (order 0 disables limiting, remhos.cpp:600-608)"); return 1; }
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+   {
+      set_error("no CUDA device: remhos_b200 has no CPU fallback");
+      return 1;
+   }
+   CUDA_OK(cudaSetDevice(d->device));
+   rmh_ctx *c = new rmh_ctx;
+   c->dim = d->dim; c->p = d->order; c->mo = d->mesh_order; c->exec_mode = d->exec_mode;
+   c->bounds_type = d->bounds_type; c->device = d->device;
+   c->D1 = c->p + 1;
+   c->Q = (2 * c->p + c->dim * c->mo - 1) / 2 + 1;
+   c->ND = ipow(c->D1, c->dim); c->NQ = ipow(c->Q, c->dim);
+   c->NF = 2 * c->dim; c->NFD = ipow(c->D1, c->dim - 1); c->NQF = ipow(c->Q, c->dim - 1);
+   c->NG1 = c->mo + 1; c->NGN = ipow(c->NG1, c->dim); c->N3 = ipow(3, c->dim);
+   c->ne = d->ne; c->ne_ghost = d->ne_ghost; c->N = c->ne * c->ND;
+   c->t_cur = 0.0;
+   auto fail = [&]() { rmh_ctx_destroy(c); return 1; };
+   if ((double)(c->ne + c->ne_ghost) * c->ND >= 2147483647.0)
+   { set_error("too many DOFs for int32 index maps"); return fail(); }
+   // ---- 1-D tables
+   gauss_legendre_01(c->Q, c->hxq, c->hw);
+   c->hB = bernstein(c->p, c->hxq);
+   c->hG = bernstein_deriv(c->p, c->hxq);
+   {
+      std::vector<double> M1((size_t)c->D1 * c->D1, 0.0);
+      for (int q = 0; q < c->Q; q++)
+         for (int i = 0; i < c->D1; i++)
+            for (int j = 0; j < c->D1; j++)
+            { M1[i * c->D1 + j] += c->hw[q] * c->hB[q * c->D1 + i] * c->hB[q * c->D1 + j]; }
+      c->hMinv = invert_small(M1, c->D1);
+   }
+   const std::vector<double> gll = gauss_lobatto_01(c->NG1);
+   const std::vector<double> L = lagrange(gll, c->hxq), dL = lagrange_deriv(gll, c->hxq);
+   const std::vector<double> ends = {0.0, 1.0};
+   const std::vector<double> Ls = lagrange(gll, ends), dLs = lagrange_deriv(gll, ends);
+   if (dev_upload(c, &c->dB, c->hB.data(), c->hB.size())) { return fail(); }
+   if (dev_upload(c, &c->dw, c->hw.data(), c->hw.size())) { return fail(); }
+   if (dev_upload(c, &c->dL, L.data(), L.size())) { return fail(); }
+   if (dev_upload(c, &c->ddL, dL.data(), dL.size())) { return fail(); }
+   if (dev_upload(c, &c->dLs, Ls.data(), Ls.size())) { return fail(); }
+   if (dev_upload(c, &c->ddLs, dLs.data(), dLs.size())) { return fail(); }
+   // ---- geometry / velocity inputs
+   const size_t nnod = (size_t)c->ne * c->NGN * c->dim;
+   if (!d->nodes) { set_error("desc.nodes is required"); return fail(); }
+   if (dev_upload(c, &c->X0, d->nodes, nnod)) { return fail(); }
+   if (d->vel_nodes) { if (dev_upload(c, &c->V, d->vel_nodes, nnod)) { return fail(); } }
+   if (c->exec_mode == 1 && !d->vel_nodes)
+   { set_error("remap mode needs desc.vel_nodes (mesh velocity)"); return fail(); }
+   if (c->exec_mode == 0)
+   {
+      if (d->vel_quad && d->vel_face)
+      {
+         if (dev_upload(c, &c->velq, d->vel_quad, (size_t)c->ne * c->NQ * c->dim)) { return fail(); }
+         if (dev_upload(c, &c->velf, d->vel_face, (size_t)c->ne * c->NF * c->NQF * c->dim)) { return fail(); }
+      }
+      else if (!d->vel_nodes)
+      { set_error("transport mode needs vel_quad+vel_face or vel_nodes"); return fail(); }
+   }
+   // ---- face neighbour map: compress NbrDof into (element, pattern)
+   if (!d->nbr_dof) { set_error("desc.nbr_dof is required"); return fail(); }
+   {
+      const int NF = c->NF, NFD = c->NFD, ND = c->ND;
+      std::vector<int> bd;
+      bdr_dofs(c->p, c->dim, bd);   // [NFD][NF] reference ordering
+      // natural face order j -> reference BdrDofs position
+      std::vector<int> nat2ref((size_t)NF * NFD);
+      for (int f = 0; f < NF; f++)
+      {
+         int axis, side;
+         face_axis(c->dim, f, axis, side);
+         for (int j = 0; j < NFD; j++)
+         {
+            int l[3] = {0, 0, 0}, m = j;
+            for (int a = 0; a < c->dim; a++)
+            {
+               if (a == axis) { l[a] = side * c->p; }
+               else { l[a] = m % c->D1; m /= c->D1; }
+            }
+            const int dof = l[0] + c->D1 * (l[1] + c->D1 * l[2]);
+            int pos = -1;
+            for (int r = 0; r < NFD; r++) { if (bd[r * NF + f] == dof) { pos = r; } }
+            nat2ref[f * NFD + j] = pos;
+         }
+      }
+      std::vector<int32_t> ne_h((size_t)c->ne * NF);
+      std::vector<uint8_t> pid_h((size_t)c->ne * NF, 0);
+      std::map<std::vector<int16_t>, int> pats;
+      std::vector<int16_t> patv, key(NFD);
+      for (int64_t e = 0; e < c->ne; e++)
+         for (int f = 0; f < NF; f++)
+         {
+            const int32_t *nd = &d->nbr_dof[((size_t)e * NF + f) * NFD];
+            if (nd[0] < 0) { ne_h[e * NF + f] = -1; continue; }
+            const int32_t nb = nd[0] / ND;
+            for (int j = 0; j < NFD; j++)
+            {
+               const int32_t g = nd[nat2ref[f * NFD + j]];
+               if (g < 0 || g / ND != nb)
+               { set_error("nbr_dof: face DOFs of one face must map into one neighbour element"); return fail(); }
+               key[j] = (int16_t)(g - nb * ND);
+            }
+            auto it = pats.find(key);
+            int id;
+            if (it == pats.end())
+            {
+               id = (int)pats.size();
+               if (id >= 255) { set_error("nbr_dof: too many distinct face patterns"); return fail(); }
+               pats[key] = id;
+               patv.insert(patv.end(), key.begin(), key.end());
+            }
+            else { id = it->second; }
+            ne_h[e * NF + f] = nb;
+            pid_h[e * NF + f] = (uint8_t)id;
+            if (nb >= c->ne + c->ne_ghost) { set_error("nbr_dof: neighbour beyond ghost range"); return fail(); }
+         }
+      c->npat = (int)pats.size();
+      if (patv.empty()) { patv.assign(NFD, 0); }
+      if (dev_upload(c, &c->nbr_elem, ne_h.data(), ne_h.size())) { return fail(); }
+      if (dev_upload(c, &c->nbr_pat, pid_h.data(), pid_h.size())) { return fail(); }
+      if (dev_upload(c, &c->pat, patv.data(), patv.size())) { return fail(); }
+   }
+   // ---- bounds structures
+   const int64_t ne_all = c->ne + c->ne_ghost;
+   if (dev_alloc(c, &c->xe_min, (size_t)ne_all)) { return fail(); }
+   if (dev_alloc(c, &c->xe_max, (size_t)ne_all)) { return fail(); }
+   if (c->bounds_type == 0)
+   {
+      if (!d->lat || d->n_ent <= 0) { set_error("bounds_type 0 needs desc.lat / n_ent"); return fail(); }
+      c->n_ent = d->n_ent;
+      const size_t nl = (size_t)c->ne * c->N3;
+      std::vector<int32_t> off((size_t)c->n_ent + 1, 0), el(nl);
+      for (size_t i = 0; i < nl; i++)
+      {
+         if (d->lat[i] < 0 || d->lat[i] >= c->n_ent) { set_error("lat id out of range"); return fail(); }
+         off[d->lat[i] + 1]++;
+      }
+      for (int i = 0; i < c->n_ent; i++) { off[i + 1] += off[i]; }
+      std::vector<int32_t> cur(off.begin(), off.end() - 1);
+      for (int64_t e = 0; e < c->ne; e++)
+         for (int t = 0; t < c->N3; t++) { el[cur[d->lat[e * c->N3 + t]]++] = (int32_t)e; }
+      if (dev_upload(c, &c->lat, d->lat, nl)) { return fail(); }
+      if (dev_upload(c, &c->ent_off, off.data(), off.size())) { return fail(); }
+      if (dev_upload(c, &c->ent_el, el.data(), el.size())) { return fail(); }
+      if (dev_alloc(c, &c->ent_min, (size_t)c->n_ent)) { return fail(); }
+      if (dev_alloc(c, &c->ent_max, (size_t)c->n_ent)) { return fail(); }
+   }
+   else
+   {
+      if (!d->nbr_elem) { set_error("bounds_type 1 needs desc.nbr_elem"); return fail(); }
+      if (dev_upload(c, &c->bnbr, d->nbr_elem, (size_t)c->ne * c->NF)) { return fail(); }
+   }
+   // ---- operator data + scratch
+   if (dev_alloc(c, &c->Dvol, (size_t)c->ne * c->dim * c->NQ)) { return fail(); }
+   if (dev_alloc(c, &c->detJw, (size_t)c->ne * c->NQ)) { return fail(); }
+   if (dev_alloc(c, &c->Dface, (size_t)c->ne * c->NF * c->NQF)) { return fail(); }
+   if (dev_alloc(c, &c->ml, (size_t)c->N)) { return fail(); }
+   if (dev_alloc(c, &c->w1, (size_t)c->N)) { return fail(); }
+   if (dev_alloc(c, &c->w2, (size_t)c->N)) { return fail(); }
+   if (dev_alloc(c, &c->w3, (size_t)c->N)) { return fail(); }
+   if (dev_alloc(c, &c->red, 4096)) { return fail(); }
+   if (c->ne_ghost > 0) { if (dev_alloc(c, &c->ughost, (size_t)c->ne_ghost * c->ND)) { return fail(); } }
+   if (d->inflow) { if (dev_upload(c, &c->inflow, d->inflow, (size_t)c->N)) { return fail(); } }
+   if (run_geom(c, 0.0, 0)) { return fail(); }
+   CUDA_OK(cudaDeviceSynchronize());
+   *out = c;
+   return 0;
+}
+
+extern "C" int64_t rmh_ctx_ndofs(const rmh_ctx *c) { return c->N; }
+extern "C" int rmh_ctx_nd(const rmh_ctx *c) { return c->ND; }
+extern "C" int rmh_ctx_nq1d(const rmh_ctx *c) { return c->Q; }
+extern "C" int rmh_ctx_quad_points_1d(const rmh_ctx *c, double *q1d, double *w1d)
+{
+   for (int q = 0; q < c->Q; q++) { if (q1d) { q1d[q] = c->hxq[q]; } if (w1d) { w1d[q] = c->hw[q]; } }
+   return 0;
+}
+
+extern "C" int rmh_set_time(rmh_ctx *c, double t, void *stream)
+{
+   if (c->exec_mode != 1) { c->t_cur = t; return 0; }
+   return run_geom(c, t, (cudaStream_t)stream);
+}
+
+extern "C" int rmh_lumped_mass(rmh_ctx *c, double *m_dev, void *stream)
+{
+   CUDA_OK(cudaMemcpyAsync(m_dev, c->ml, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+   return 0;
+}
+
+static HoArgs ho_args(rmh_ctx *c, const double *in, double *out, int mode)
+{
+   HoArgs a;
+   a.ne = c->ne; a.u = in; a.out = out;
+   a.Dvol = c->Dvol; a.detJw = c->detJw; a.Dface = c->Dface;
+   a.fn.nbr_elem = c->nbr_elem; a.fn.nbr_pat = c->nbr_pat; a.fn.pat = c->pat;
+   a.fn.ughost = c->ughost; a.fn.ne_owned = c->ne;
+   a.mode = mode; a.tol2 = c->pcg_tol2; a.maxit = c->pcg_maxit;
+   return a;
+}
+
+extern "C" int rmh_ho_mult(rmh_ctx *c, const double *u, double *rhs, void *stream)
+{
+   return dispatch_ho(c, ho_args(c, u, rhs, 1), (cudaStream_t)stream);
+}
+extern "C" int rmh_mass_inv(rmh_ctx *c, const double *rhs, double *du, void *stream)
+{
+   return dispatch_ho(c, ho_args(c, rhs, du, 2), (cudaStream_t)stream);
+}
+extern "C" int rmh_ho_local_inverse(rmh_ctx *c, const double *u, double *du, void *stream)
+{
+   return dispatch_ho(c, ho_args(c, u, du, 3), (cudaStream_t)stream);
+}
+
+extern "C" int rmh_lo_mass_avg(rmh_ctx *c, double dt, const double *u, const double *du_ho,
+                               double *du_lo, void *stream)
+{
+   const int bs = 256;
+   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
+   k_mass_avg<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, dt, u, du_ho, c->ml, du_lo);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_elem_min_max(rmh_ctx *c, const double *u, double *xe_min, double *xe_max,
+                                void *stream)
+{
+   const int bs = 256;
+   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
+   k_elem_min_max<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, u, xe_min, xe_max);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_bounds(rmh_ctx *c, const double *xe_min, const double *xe_max, double *xi_min,
+                          double *xi_max, void *stream)
+{
+   cudaStream_t s = (cudaStream_t)stream;
+   const int bs = 256;
+   if (c->bounds_type == 0)
+   {
+      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, c->ent_off, c->ent_el, xe_min,
+                                                            xe_max, c->ent_min, c->ent_max);
+      LAUNCH_OK();
+      k_bounds_overlap<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(
+         c->ne, c->dim, c->D1, c->ND, c->N3, c->lat, c->ent_min, c->ent_max, xi_min, xi_max);
+      LAUNCH_OK();
+   }
+   else
+   {
+      k_bounds_sparsity<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->ne, c->NF, c->ND, c->bnbr,
+                                                                        xe_min, xe_max, xi_min, xi_max);
+      LAUNCH_OK();
+   }
+   return 0;
+}
+
+extern "C" int rmh_fct_clip_scale(rmh_ctx *c, double dt, const double *u, const double *m,
+                                  const double *du_ho, const double *du_lo, const double *xi_min,
+                                  const double *xi_max, double *du, void *stream)
+{
+   if (c->ND > 256) { set_error("clip_scale: nd > 256 unsupported"); return 1; }
+   const int bs = 256;
+   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
+   k_clip_scale<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, dt, u, m, du_ho, du_lo,
+                                                               xi_min, xi_max, du);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_reduce(rmh_ctx *c, int op, const double *a, const double *b, double *out,
+                          void *stream)
+{
+   cudaStream_t s = (cudaStream_t)stream;
+   const int nb = 1024, bs = 256;
+   k_reduce<<<nb, bs, 0, s>>>(c->N, op, a, b, c->red);
+   LAUNCH_OK();
+   std::vector<double> part(nb);
+   CUDA_OK(cudaMemcpyAsync(part.data(), c->red, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+   CUDA_OK(cudaStreamSynchronize(s));
+   double v = (op == 0) ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
+   for (int i = 0; i < nb; i++)
+   {
+      if (op == 0) { v += part[i]; }
+      else if (op == 1) { v = std::min(v, part[i]); }
+      else { v = std::max(v, part[i]); }
+   }
+   *out = v;
+   return 0;
+}
+
+// ---------------------------------------------------------------- fused stage entry points
+// xe_valid: ctx->xe_min/xe_max already hold the element min/max of y
+static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a, double b,
+                      const double *x0, const double *y, double *out, bool xe_valid,
+                      bool write_xe, cudaStream_t s)
+{
+   if (lo_type != 5)
+   {
+      set_error("fused stage: only -lo 5 (MassBasedAvg) is fused; use the separate LO entry points");
+      return 1;
+   }
+   if (out == y) { set_error("stage: output must not alias the stage input"); return 1; }
+   const int bs = 256;
+   if (!xe_valid)
+   {
+      const int64_t nb = (c->ne * 32 + bs - 1) / bs;
+      k_elem_min_max<<<(unsigned)nb, bs, 0, s>>>(c->ne, c->ND, y, c->xe_min, c->xe_max);
+      LAUNCH_OK();
+   }
+   if (c->bounds_type == 0)
+   {
+      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, c->ent_off, c->ent_el, c->xe_min,
+                                                            c->xe_max, c->ent_min, c->ent_max);
+      LAUNCH_OK();
+   }
+   StageArgs sa;
+   sa.ho = ho_args(c, y, nullptr, 3);
+   sa.ml = c->ml; sa.x0 = x0; sa.out = out; sa.a = a; sa.b = b; sa.dt = dt; sa.out_mode = out_mode;
+   sa.bounds_type = c->bounds_type; sa.dim_n3 = c->N3; sa.lat = c->lat;
+   sa.ent_min = c->ent_min; sa.ent_max = c->ent_max; sa.bnbr = c->bnbr;
+   sa.xe_min = c->xe_min; sa.xe_max = c->xe_max;
+   // the next stage's element min/max must not overwrite the ones this launch still reads
+   // (bounds_type 1 reads neighbours' xe during the kernel) -> double buffer
+   sa.xe_min_out = nullptr; sa.xe_max_out = nullptr;
+   if (write_xe && c->bounds_type == 0) { sa.xe_min_out = c->xe_min; sa.xe_max_out = c->xe_max; }
+   return dispatch_stage(c, sa, s);
+}
+
+extern "C" int rmh_stage(rmh_ctx *c, int lo_type, double dt, const double *u, double *k, void *stream)
+{
+   return stage_impl(c, lo_type, dt, 0, 0.0, 0.0, u, u, k, false, false, (cudaStream_t)stream);
+}
+
+extern "C" int rmh_rk_stage(rmh_ctx *c, int lo_type, double dt, double a, double b,
+                            const double *x0, const double *y, double *out, void *stream)
+{
+   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, false, false, (cudaStream_t)stream);
+}
+
+extern "C" int rmh_rk_step(rmh_ctx *c, int ode, int lo_type, double *t, double dt, double *u,
+                           void *stream)
+{
+   cudaStream_t s = (cudaStream_t)stream;
+   const double t0 = *t;
+   // with overlap bounds the stage kernel leaves the element min/max of its output in the
+   // context, so only the first stage needs the stand-alone min/max pass
+   const bool chain = (c->bounds_type == 0);
+   if (ode == 1)          // ForwardEulerSolver
+   {
+      if (rmh_set_time(c, t0, stream)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, false, false, s)) { return 1; }
+      CUDA_OK(cudaMemcpyAsync(u, c->w1, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+   }
+   else if (ode == 2)     // RK2Solver(1.0): u_new = 1/2 u + 1/2 (y + dt F(y)), y = u + dt F(u)
+   {
+      if (rmh_set_time(c, t0, stream)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, false, chain, s)) { return 1; }
+      if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.5, 0.5, u, c->w1, u, chain, false, s)) { return 1; }
+   }
+   else if (ode == 3)     // RK3SSPSolver
+   {
+      if (rmh_set_time(c, t0, stream)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, false, chain, s)) { return 1; }
+      if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.75, 0.25, u, c->w1, c->w2, chain, chain, s)) { return 1; }
+      if (rmh_set_time(c, t0 + dt / 2, stream)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, chain, false, s)) { return 1; }
+   }
+   else
+   {
+      set_error("rmh_rk_step: ode solver type must be 1, 2 or 3 (use rmh_stage for general RK)");
+      return 1;
+   }
+   *t = t0 + dt;
+   return 0;
+}
+
+extern "C" int rmh_rk_step_host(rmh_ctx *c, int ode, int lo_type, double *t, double dt, double *u_host)
+{
+   // end-to-end entry point: state lives in host memory (as the reference's ODESolver vectors do,
+   // remhos.cpp:1680); H2D, one step, D2H.  u_host should be pinned for full PCIe bandwidth.
+   const size_t bytes = (size_t)c->N * sizeof(double);
+   CUDA_OK(cudaMemcpyAsync(c->w3, u_host, bytes, cudaMemcpyHostToDevice, 0));
+   if (rmh_rk_step(c, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }
+   CUDA_OK(cudaMemcpyAsync(u_host, c->w3, bytes, cudaMemcpyDeviceToHost, 0));
+   CUDA_OK(cudaStreamSynchronize(0));
+   return 0;
+}
+
+extern "C" int rmh_lo_discrete_upwind(rmh_ctx *, const double *, double *, void *)
+{
+   set_error("rmh_lo_discrete_upwind: not implemented yet");
+   return 1;
+}
+extern "C" int rmh_lo_res_dist(rmh_ctx *, const double *, double *, void *)
+{
+   set_error("rmh_lo_res_dist: not implemented yet");
+   return 1;
+}

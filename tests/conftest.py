@@ -1,0 +1,18 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+DATA = os.path.join(ROOT, 'tests', 'data')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: test needs a CUDA device (run with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def data_dir():
+    return DATA

@@ -1,0 +1,100 @@
+"""GPU parity tests of the fused RK-stage path (rmh_stage / rmh_rk_stage / rmh_rk_step /
+rmh_rk_step_host) against the CPU oracle, and of whole runs against the reference's own
+known answers (remhos_tests.cpp:38-107: final mass of `-ho 3 -lo 5 -fct 2` remap runs).
+
+Tolerance (north_star): final-solution L1/Linf and total mass within 1e-12 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import oracle_run, ctx_from_oracle, rel_err
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(-1), device='cuda')
+
+
+STAGE_CASES = [
+    ('periodic-square.mesh', dict(problem=5, rs_levels=2, order=3, dt=0.004), 0),
+    ('periodic-square.mesh', dict(problem=1, rs_levels=2, order=2, dt=0.004), 1),
+    ('inline-quad.mesh', dict(problem=14, rs_levels=1, order=3, dt=0.002, t_final=0.75), 0),
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=3, dt=0.01), 0),
+    ('periodic-cube.mesh', dict(problem=1, rs_levels=1, order=2, dt=0.01), 1),
+    ('cube01_hex.mesh', dict(problem=10, rs_levels=1, order=3, dt=0.02, t_final=0.7), 0),
+]
+
+
+@pytest.mark.parametrize('mesh,opt,bt', STAGE_CASES)
+def test_stage_matches_oracle(mesh, opt, bt):
+    run = oracle_run(mesh, ho_type=3, lo_type=5, fct_type=2, bounds_type=bt, **opt)
+    ctx = ctx_from_oracle(run)
+    rng = np.random.default_rng(7)
+    u = np.clip(run.u + 0.02 * rng.standard_normal(run.u.shape), 0.0, None)
+    t = 0.3 if run.exec_mode == 1 else 0.0
+    ref = run.mult(u, t, run.dt)
+    ctx.set_time(t)
+    k = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.stage(5, run.dt, dev(u), k)
+    assert rel_err(k.cpu().numpy().reshape(u.shape), ref) < 1e-10
+    # the limited update keeps u + dt*k inside the bounds (same verdict as the oracle's check)
+    umin, umax = run.disc.bounds(u, bt)
+    un = u + run.dt * k.cpu().numpy().reshape(u.shape)
+    assert (un + 1e-12 >= umin).all() and (un <= umax + 1e-12).all()
+    ctx.close()
+
+
+RUN_CASES = [
+    # (mesh, options, steps, reference final mass or None)
+    ('inline-quad.mesh', dict(problem=14, rs_levels=1, order=2, dt=-1.0, t_final=0.5), 5,
+     0.09711395400387984),                               # remhos_tests.cpp:40-44, 70-73
+    ('cube01_hex.mesh', dict(problem=10, rs_levels=1, order=2, dt=-1.0, t_final=0.5), 5,
+     0.11972857593296446),                               # remhos_tests.cpp:64-67
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=3, dt=0.01, t_final=1.0), 6, None),
+    ('periodic-square.mesh', dict(problem=5, rs_levels=3, order=3, dt=0.004, t_final=0.8), 10, None),
+]
+
+
+@pytest.mark.parametrize('mesh,opt,steps,ref_mass', RUN_CASES)
+@pytest.mark.parametrize('ode', [3, 2, 1])
+def test_rk_steps_match_oracle(mesh, opt, steps, ref_mass, ode):
+    run = oracle_run(mesh, ho_type=3, lo_type=5, fct_type=2, ode_solver=ode, max_steps=steps, **opt)
+    ctx = ctx_from_oracle(run)
+    u = dev(run.u)
+    t, dt = 0.0, run.dt
+    for _ in range(steps):
+        dt_real = min(dt, run.t_final - t)
+        t = ctx.rk_step(ode, 5, t, dt_real, u)
+    run.run()
+    ug = u.cpu().numpy().reshape(run.u.shape)
+    # final solution norms (lumped-mass weighted L1, and Linf) within 1e-12 relative
+    ml = run.disc.cur.ml if run.exec_mode == 1 else run.masses0
+    l1 = float((ml * np.abs(ug - run.u)).sum() / (ml * np.abs(run.u)).sum())
+    linf = float(np.abs(ug - run.u).max() / np.abs(run.u).max())
+    assert l1 < 1e-12 and linf < 1e-12, (l1, linf)
+    # total mass on the final mesh
+    ctx.set_time(t)
+    m = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.lumped_mass(m)
+    mass = ctx.reduce(0, u, m)
+    assert abs(mass - run.final_mass) < 1e-12 * abs(run.final_mass)
+    if ref_mass is not None and ode == 3:
+        assert abs(mass - ref_mass) < 1e-12 * abs(ref_mass)
+    # bound preservation verdict: global extrema do not grow (remhos.cpp:1219-1260)
+    assert ug.min() > run.u0_min - 1e-10 and ug.max() < run.u0_max + 1e-10
+    ctx.close()
+
+
+def test_rk_step_host_equals_device():
+    run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=0,
+                     rs_levels=1, order=3, dt=0.01)
+    ctx = ctx_from_oracle(run)
+    u = dev(run.u)
+    uh = torch.tensor(run.u.reshape(-1)).pin_memory()
+    t1 = ctx.rk_step(3, 5, 0.0, run.dt, u)
+    t2 = ctx.rk_step_host(3, 5, 0.0, run.dt, uh.data_ptr())
+    assert t1 == t2
+    assert torch.equal(u.cpu(), uh)
+    ctx.close()
