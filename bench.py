@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- DOF*RK-stage updates/s of the Remhos RK-stage path on B200 (BASELINE.json metric).
+
+Workload (config C2): 3D periodic cube [-1,1]^3, 3x3x3 coarse hexes refined
+`--rs` times (default 5 -> 884 736 elements), order 3 (56.6 M DOFs per GPU), mesh order 2,
+problem 0 (erfc bump, constant velocity), `-ho 3 -lo 5 -fct 2 -pa -s 3`: LocalInverse HO +
+MassBasedAvg LO + ClipScale FCT, RK3-SSP.  A "step" is one RK3 time step = 3 fused stage
+launches; value = DOFs * 3 * steps / time, summed over ranks (weak scaling: every rank owns a
+full cube of the same size).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints one JSON line (see the task contract): value (state resident in HBM), e2e (host state,
+H2D + D2H inside the timed region, through rmh_rk_step_host), roofline of the fused stage
+kernel, cpu_baseline (the CPU oracle timed on the host cores on a bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = 136.0          # algorithmic bytes per DOF*stage (five kernels)
+STAGES = 3             # RK3-SSP
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f:
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if sm:
+            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)),
+                   'reasons': sorted(reasons), 'samples': len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_baseline(order, seconds=12.0):
+    """The CPU oracle (numpy restatement of the reference path) on the same workload shrunk to
+    -rs 2, timed on this box's host cores."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from remhos_oracle import driver, mesh as om
+    m = om.cartesian_mesh([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+    rs = 2
+    run = driver.Run(driver.Options(problem=0, rs_levels=rs, order=order, ho_type=3, lo_type=5,
+                                    fct_type=2, dt=0.002, t_final=1e9), mesh=m)
+    n = run.u.size
+    u = run.u
+    u = run.step(u, 0.0, run.dt)            # warm-up
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        u = run.step(u, 0.0, run.dt)
+        steps += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    el = time.perf_counter() - t0
+    try:
+        import threadpoolctl
+        cores = max([p.get('num_threads', 1) for p in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        cores = 1
+    return {'value': n * STAGES * steps / el, 'unit': 'DOF*stage/s', 'cores': int(cores),
+            'kind': 'port',
+            'sample': 'numpy oracle, periodic cube -rs %d order %d (%d DOFs), %d RK3 steps in %.1f s'
+                      % (rs, order, n, steps, el)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--rs', type=int, default=5)
+    ap.add_argument('--order', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    workload = ('3D periodic-cube transport, order %d hex, -rs %d, -ho 3 -lo 5 -fct 2 -pa -s 3 '
+                '(problem 0)' % (a.order, a.rs))
+    metric = 'DOF*RK-stage updates/sec (3D hex, order 3, FCT)'
+
+    if a.impl == 'reference':
+        # the reference's MPI CPU build cannot be produced here (needs MFEM/hypre/METIS/MPI,
+        # SURVEY.md 8c): the reference arm times the CPU oracle port on the host cores
+        if rank != 0:
+            return
+        cb = cpu_baseline(a.order, seconds=max(5.0, 2.0 * a.steps))
+        line = {'impl': 'reference', 'metric': metric, 'value': cb['value'], 'unit': 'DOF*stage/s',
+                'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': None,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic', 'config': {'workload': workload, 'sample': cb['sample']},
+                'cpu_baseline': cb,
+                'e2e': {'value': cb['value'], 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import remhos_b200 as rb
+    from remhos_b200.setup_problem import Problem
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (remhos_b200 has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+    mesh.refine(a.rs)
+    h = 2.0 / (3 * 2 ** a.rs)
+    dt = 0.25 * h / a.order            # fixed dt = 0.25 h/|v| /p, |v| = 1
+    prob = Problem(mesh, problem=0, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
+                   device=local_rank)
+    ctx = prob.ctx
+    N = ctx.ndofs
+    u = torch.tensor(prob.u0, device='cuda')
+    m = torch.empty(N, dtype=torch.float64, device='cuda')
+    ctx.lumped_mass(m)
+    mass0 = ctx.reduce(0, u, m)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 0.0
+    for _ in range(a.warmup):
+        t = ctx.rk_step(3, 5, t, dt, u, stream)
+    barrier()
+    rb.launch_count(reset=True)
+    ctx.profile(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        t = ctx.rk_step(3, 5, t, dt, u, stream)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = rb.launch_count(reset=True)
+    kms, klaunch = ctx.profile(0)
+    mass1 = ctx.reduce(0, u, m)
+    umin, umax = ctx.reduce(1, u), ctx.reduce(2, u)
+
+    # end-to-end: state in pinned host memory, H2D + step + D2H every step
+    uh = u.cpu().pin_memory()
+    for _ in range(2):
+        ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(3, a.steps // 2)
+    for _ in range(e_steps):
+        ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
+    barrier()
+    e_ms = (time.perf_counter() - t0) * 1e3
+
+    tmax = torch.tensor([ms, e_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, e_ms = float(tmax[0]), float(tmax[1])
+    total_dofs = N * world
+    value = total_dofs * STAGES * a.steps / (ms * 1e-3)
+    e2e = total_dofs * STAGES * e_steps / (e_ms * 1e-3)
+    peak, which = read_peaks()
+    k_ms = kms / max(klaunch, 1)
+    achieved = B_ALG * N / (k_ms * 1e-3) / 1e9 if klaunch else None
+    line = {
+        'metric': metric, 'value': value, 'unit': 'DOF*stage/s', 'n_gpus': world,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': workload, 'dofs_per_gpu': N, 'elements_per_gpu': ctx.ne,
+                   'stages_per_step': STAGES, 'dt': dt,
+                   'l2': 'state vectors (453 MB each) and operator data (7.6 GB) exceed the 126 MB L2',
+                   'parallelism': 'dp%d' % world if world > 1 else 'single'},
+        'e2e': {'value': e2e, 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 8 * N,
+                'd2h_bytes_per_step': 8 * N, 'steps': e_steps},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'kernel': 'k_stage<3,%d,%d>' % (a.order + 1, a.order + 3),
+                     'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
+                     'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                     'alg_bytes_per_dof_stage': B_ALG, 'kernel_ms': k_ms,
+                     'kernel_share_of_step': (kms / ms) if klaunch else None},
+        'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0), 'u_min': umin, 'u_max': umax},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(a.order)
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

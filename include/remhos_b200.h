@@ -69,6 +69,24 @@ int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *elem_ids, rmh_
 int rmh_mesh_dof_maps(const rmh_mesh *m, int order, int32_t *bdr_dofs, int32_t *nbr_dof,
                       int32_t *sub2ind, int32_t *lat, int32_t *n_ent, int32_t *nbr_elem);
 
+/* Problem definitions and driver set-up (host): velocity_function (remhos.cpp:2001-2120),
+ * u0_function (:2201-2355), inflow_function (:2363-2381); x is [n][dim]. */
+int rmh_velocity(int problem, int dim, int64_t n, const double *x, const double *bb_min,
+                 const double *bb_max, double *v);
+int rmh_u0(int problem, int dim, int64_t n, const double *x, const double *bb_min,
+           const double *bb_max, double *u);
+int rmh_inflow(int problem, int dim, int64_t n, const double *x, double *u);
+/* physical coordinates of the tensor lattice pts1d[npts]^dim of every element (face < 0), or of
+ * the lattice on local face `face`; out [ne][npts^d'][dim].  With pts = i/p this gives the
+ * points ProjectCoefficient samples on the positive basis (remhos.cpp:883). */
+int rmh_mesh_eval(const rmh_mesh *m, int npts, const double *pts1d, int face, double *out);
+/* CFL time step used for -dt < 0 (remhos.cpp:538-553) */
+int rmh_cfl_dt(const rmh_mesh *m, int problem, const double *bb_min, const double *bb_max,
+               double *dt);
+/* remap mesh velocity v_gf = x_final - x0 (remhos.cpp:562-584); v_nodes like rmh_mesh_nodes */
+int rmh_remap_mesh_velocity(const rmh_mesh *m, int problem, const double *bb_min,
+                            const double *bb_max, double dt, double t_final, double *v_nodes);
+
 /* ------------------------------------------------------------------------------------------
  * Device context for the RK-stage path.
  * ---------------------------------------------------------------------------------------- */
@@ -166,6 +184,10 @@ int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, 
  * (remhos.cpp:1073-1076,1403-1415; GetMinMax remhos_tools.cpp:1433-1439); result on host */
 int rmh_reduce(rmh_ctx *ctx, int op, const double *a_dev, const double *b_dev, double *out,
                void *stream);
+
+/* per-launch CUDA-event timing of the fused stage kernel: enable != 0 starts recording; every
+ * call returns and clears the accumulated kernel time [ms] and launch count */
+int rmh_profile(rmh_ctx *ctx, int enable, double *total_ms, int64_t *launches);
 
 /* number of kernels this library has launched since the counter was last reset */
 int64_t rmh_launch_count(int reset);

@@ -255,6 +255,11 @@ class Context:
                                      C.c_double(dt), C.c_void_p(int(u_host))))
         return tt.value
 
+    def profile(self, enable):
+        ms = C.c_double(0.0); n = C.c_int64(0)
+        check(lib().rmh_profile(self.h, int(enable), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def reduce(self, op, a, b=None, s=0):
         out = C.c_double(0.0)
         check(lib().rmh_reduce(self.h, int(op), _dp(a), _dp(b), C.byref(out), C.c_void_p(s)))

@@ -69,6 +69,10 @@ struct rmh_ctx
    // scratch
    double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *red = nullptr;
    double *pin = nullptr;   // pinned host staging (e2e entry point)
+   // optional per-launch timing of the fused stage kernel (bench.py roofline)
+   bool prof = false;
+   std::vector<cudaEvent_t> prof_ev;
+   size_t prof_used = 0;
    double pcg_tol2 = 1e-28;
    int pcg_maxit = 60;
    std::vector<void *> allocs;
@@ -745,6 +749,7 @@ extern "C" int rmh_ctx_destroy(rmh_ctx *c)
    if (!c) { return 0; }
    cudaSetDevice(c->device);
    for (void *p : c->allocs) { cudaFree(p); }
+   for (cudaEvent_t ev : c->prof_ev) { cudaEventDestroy(ev); }
    if (c->pin) { cudaFreeHost(c->pin); }
    delete c;
    return 0;
@@ -1082,7 +1087,43 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    // (bounds_type 1 reads neighbours' xe during the kernel) -> double buffer
    sa.xe_min_out = nullptr; sa.xe_max_out = nullptr;
    if (write_xe && c->bounds_type == 0) { sa.xe_min_out = c->xe_min; sa.xe_max_out = c->xe_max; }
+   if (c->prof)
+   {
+      if (c->prof_used + 2 > c->prof_ev.size())
+      {
+         for (int i = 0; i < 64; i++)
+         {
+            cudaEvent_t ev;
+            CUDA_OK(cudaEventCreate(&ev));
+            c->prof_ev.push_back(ev);
+         }
+      }
+      CUDA_OK(cudaEventRecord(c->prof_ev[c->prof_used], s));
+      const int rc = dispatch_stage(c, sa, s);
+      CUDA_OK(cudaEventRecord(c->prof_ev[c->prof_used + 1], s));
+      c->prof_used += 2;
+      return rc;
+   }
    return dispatch_stage(c, sa, s);
+}
+
+extern "C" int rmh_profile(rmh_ctx *c, int enable, double *total_ms, int64_t *launches)
+{
+   // enable: 1 start/continue recording, 0 stop; always reports (and clears) what was recorded
+   double tot = 0.0;
+   int64_t n = 0;
+   for (size_t i = 0; i + 1 < c->prof_used; i += 2)
+   {
+      CUDA_OK(cudaEventSynchronize(c->prof_ev[i + 1]));
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
+      tot += ms; n++;
+   }
+   c->prof_used = 0;
+   c->prof = enable != 0;
+   if (total_ms) { *total_ms = tot; }
+   if (launches) { *launches = n; }
+   return 0;
 }
 
 extern "C" int rmh_stage(rmh_ctx *c, int lo_type, double dt, const double *u, double *k, void *stream)
