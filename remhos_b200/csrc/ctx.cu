@@ -3,6 +3,7 @@
 #include "../../include/remhos_b200.h"
 #include "common.hpp"
 #include "kernels.cuh"
+#include "stage3d.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -236,7 +237,13 @@ __global__ void k_geom_face(GeomArgs g)
    for (int i = 0; i < DIM; i++) { vn += v[i] * sgn * adj[axis][i]; }
    // upwinded normal velocity (remhos_tools.cpp:833-845): transport min(0, v.n), remap -max(0, v.n)
    const double vs = (g.exec_mode == 1) ? -fmax(0.0, vn) : fmin(0.0, vn);
-   g.Dface[idx] = w * vs;
+   if (DIM == 3)
+   {
+      // 3D layout [e][qb][f][qa] (coalesced for the (qa, f) thread mapping of stage3d.cuh)
+      const int qa = qf % Q, qb = qf / Q;
+      g.Dface[(size_t)e * NF * NQF + (size_t)qb * NF * Q + f * Q + qa] = w * vs;
+   }
+   else { g.Dface[idx] = w * vs; }
 }
 
 // lumped mass m_i = sum_q B_qi detJw_q  (M_HO * 1, remhos.cpp:721-727)
@@ -292,37 +299,88 @@ struct HoArgs
    int maxit;
 };
 
+// block shape / shared-memory plan: 3D uses the (a,b)-mapped fast path of stage3d.cuh
 template <int DIM, int D1, int Q, int E>
-__global__ void __launch_bounds__(32 * E) k_ho(HoArgs a, const Tab<D1, Q> tab)
+struct KCfg
 {
-   using S = Smem<DIM, D1, Q, E>;
-   constexpr int T = 32 * E, ND = S::ND, NQ = S::NQ, NF = S::NF, NQF = S::NQF;
+   using S2 = Smem<DIM, D1, Q, E>;
+   using S3 = Smem3<D1, Q, E>;
+   static constexpr int T = (DIM == 3) ? S3::T : 32 * E;
+   static constexpr size_t BYTES = (DIM == 3) ? S3::BYTES : S2::BYTES;
+   static constexpr int OFF_U = (DIM == 3) ? S3::OFF_U : S2::OFF_U;
+   static constexpr int OFF_R = (DIM == 3) ? S3::OFF_R : S2::OFF_R;
+   static constexpr int OFF_X = (DIM == 3) ? S3::OFF_X : S2::OFF_X;
+};
+
+// (a) + (b) on the block's element batch: U (smem) -> R = K_HO u -> X = M^-1 R; returns result ptr
+template <int DIM, int D1, int Q, int E>
+__device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_t e0, int ne,
+                                             const Tab<D1, Q> &tab);
+
+template <int DIM, int D1, int Q, int E>
+__global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_ho(HoArgs a, const Tab<D1, Q> tab)
+{
+   using K = KCfg<DIM, D1, Q, E>;
+   constexpr int T = K::T, ND = ipow(D1, DIM);
    extern __shared__ double sm[];
    const int64_t e0 = (int64_t)blockIdx.x * E;
    const int ne = (int)min((int64_t)E, a.ne - e0);
-   double *U = sm + S::OFF_U, *R = sm + S::OFF_R, *X = sm + S::OFF_X;
-   for (int t = threadIdx.x; t < E * ND; t += T)
-   {
-      U[t] = (t < ne * ND) ? a.u[e0 * ND + t] : 0.0;
-   }
-   __syncthreads();
+   double *U = sm + K::OFF_U;
+   for (int t = threadIdx.x; t < E * ND; t += T) { U[t] = (t < ne * ND) ? a.u[e0 * ND + t] : 0.0; }
+   const double *res = ho_phases<DIM, D1, Q, E>(a, sm, e0, ne, tab);
+   for (int t = threadIdx.x; t < ne * ND; t += T) { a.out[e0 * ND + t] = res[t]; }
+}
+
+template <int DIM, int D1, int Q, int E>
+__device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_t e0, int ne,
+                                             const Tab<D1, Q> &tab)
+{
+   using K = KCfg<DIM, D1, Q, E>;
+   constexpr int T = K::T, ND = ipow(D1, DIM), NQ = ipow(Q, DIM), NF = 2 * DIM,
+                 NQF = ipow(Q, DIM - 1);
+   double *U = sm + K::OFF_U, *R = sm + K::OFF_R, *X = sm + K::OFF_X;
    double *res = R;
-   if (a.mode & 1)
+   if constexpr (DIM == 3)
    {
-      vol_apply<DIM, D1, Q, E>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
-      face_apply<DIM, D1, Q, E>(U, R, sm, a.u, a.Dface + (size_t)e0 * NF * NQF, a.fn, e0, ne, tab);
+      const Tid3<D1, Q, E> t;
+      if (a.mode & 1) { face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne, t); }
+      __syncthreads();
+      if (a.mode & 1)
+      {
+         face3_apply<D1, Q, E>(sm, a.Dface + (size_t)e0 * NF * NQF, ne, tab, t);
+         vol3_apply<D1, Q, E, true>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab, t);
+      }
+      else
+      {
+         for (int i = threadIdx.x; i < E * ND; i += T) { R[i] = U[i]; }
+         __syncthreads();
+      }
+      if (a.mode & 2)
+      {
+         mass3_solve<D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, ne, a.tol2, a.maxit, tab, t);
+         res = X;
+      }
    }
    else
    {
-      for (int t = threadIdx.x; t < E * ND; t += T) { R[t] = U[t]; }
       __syncthreads();
+      if (a.mode & 1)
+      {
+         vol_apply<DIM, D1, Q, E>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
+         face_apply<DIM, D1, Q, E>(U, R, sm, a.u, a.Dface + (size_t)e0 * NF * NQF, a.fn, e0, ne, tab);
+      }
+      else
+      {
+         for (int i = threadIdx.x; i < E * ND; i += T) { R[i] = U[i]; }
+         __syncthreads();
+      }
+      if (a.mode & 2)
+      {
+         mass_solve<DIM, D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, ne, a.tol2, a.maxit, tab);
+         res = X;
+      }
    }
-   if (a.mode & 2)
-   {
-      mass_solve<DIM, D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, ne, a.tol2, a.maxit, tab);
-      res = X;
-   }
-   for (int t = threadIdx.x; t < ne * ND; t += T) { a.out[e0 * ND + t] = res[t]; }
+   return res;
 }
 
 __device__ __forceinline__ int lattice_class(int dim, int D1, int i)
@@ -357,20 +415,19 @@ struct StageArgs
 };
 
 template <int DIM, int D1, int Q, int E>
-__global__ void __launch_bounds__(32 * E) k_stage(StageArgs a, const Tab<D1, Q> tab)
+__global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, const Tab<D1, Q> tab)
 {
-   using S = Smem<DIM, D1, Q, E>;
-   constexpr int T = 32 * E, ND = S::ND, NQ = S::NQ, NF = S::NF, NQF = S::NQF;
+   using K = KCfg<DIM, D1, Q, E>;
+   constexpr int T = K::T, ND = ipow(D1, DIM), NF = 2 * DIM;
    constexpr int NK = (ND + 31) / 32, N3 = ipow(3, DIM);
    extern __shared__ double sm[];
    const int64_t e0 = (int64_t)blockIdx.x * E;
    const int ne = (int)min((int64_t)E, a.ho.ne - e0);
-   double *U = sm + S::OFF_U, *R = sm + S::OFF_R, *X = sm + S::OFF_X;
+   double *U = sm + K::OFF_U;
    for (int t = threadIdx.x; t < E * ND; t += T) { U[t] = (t < ne * ND) ? a.ho.u[e0 * ND + t] : 0.0; }
-   __syncthreads();
-   vol_apply<DIM, D1, Q, E>(U, R, sm, a.ho.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
-   face_apply<DIM, D1, Q, E>(U, R, sm, a.ho.u, a.ho.Dface + (size_t)e0 * NF * NQF, a.ho.fn, e0, ne, tab);
-   mass_solve<DIM, D1, Q, E>(R, X, sm, a.ho.detJw + (size_t)e0 * NQ, ne, a.ho.tol2, a.ho.maxit, tab);
+   HoArgs ha = a.ho;
+   ha.mode = 3;
+   const double *X = ho_phases<DIM, D1, Q, E>(ha, sm, e0, ne, tab);
    __syncthreads();
    // ---- element-wise part: one warp per element
    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -618,7 +675,7 @@ __global__ void k_reduce(int64_t n, int op, const double *a, const double *b, do
 template <int DIM, int D1, int Q, int E>
 static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
 {
-   using S = Smem<DIM, D1, Q, E>;
+   using S = KCfg<DIM, D1, Q, E>;
    Tab<D1, Q> tab;
    for (int q = 0; q < Q; q++)
       for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
@@ -632,7 +689,7 @@ static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
       attr_set = true;
    }
    const int64_t nb = (a.ne + E - 1) / E;
-   k_ho<DIM, D1, Q, E><<<(unsigned)nb, 32 * E, S::BYTES, s>>>(a, tab);
+   k_ho<DIM, D1, Q, E><<<(unsigned)nb, S::T, S::BYTES, s>>>(a, tab);
    LAUNCH_OK();
    return 0;
 }
@@ -640,10 +697,10 @@ static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
 template <int DIM, int D1, int Q>
 static int launch_ho(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
 {
-   constexpr size_t LIM = 110 * 1024;
-   if constexpr (Smem<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 8>(c, a, s); }
-   else if constexpr (Smem<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 4>(c, a, s); }
-   else if constexpr (Smem<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 2>(c, a, s); }
+   constexpr size_t LIM = 72 * 1024;
+   if constexpr (KCfg<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 8>(c, a, s); }
+   else if constexpr (KCfg<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 4>(c, a, s); }
+   else if constexpr (KCfg<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 2>(c, a, s); }
    else { return launch_ho_E<DIM, D1, Q, 1>(c, a, s); }
 }
 
@@ -676,7 +733,7 @@ static int dispatch_ho(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
 template <int DIM, int D1, int Q, int E>
 static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
 {
-   using S = Smem<DIM, D1, Q, E>;
+   using S = KCfg<DIM, D1, Q, E>;
    Tab<D1, Q> tab;
    for (int q = 0; q < Q; q++)
       for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
@@ -690,7 +747,7 @@ static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
       attr_set = true;
    }
    const int64_t nb = (a.ho.ne + E - 1) / E;
-   k_stage<DIM, D1, Q, E><<<(unsigned)nb, 32 * E, S::BYTES, s>>>(a, tab);
+   k_stage<DIM, D1, Q, E><<<(unsigned)nb, S::T, S::BYTES, s>>>(a, tab);
    LAUNCH_OK();
    return 0;
 }
@@ -698,10 +755,10 @@ static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
 template <int DIM, int D1, int Q>
 static int launch_stage(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
 {
-   constexpr size_t LIM = 110 * 1024;
-   if constexpr (Smem<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 8>(c, a, s); }
-   else if constexpr (Smem<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 4>(c, a, s); }
-   else if constexpr (Smem<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 2>(c, a, s); }
+   constexpr size_t LIM = 72 * 1024;
+   if constexpr (KCfg<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 8>(c, a, s); }
+   else if constexpr (KCfg<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 4>(c, a, s); }
+   else if constexpr (KCfg<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 2>(c, a, s); }
    else { return launch_stage_E<DIM, D1, Q, 1>(c, a, s); }
 }
 
