@@ -310,6 +310,11 @@ struct KCfg
    static constexpr int OFF_U = (DIM == 3) ? S3::OFF_U : S2::OFF_U;
    static constexpr int OFF_R = (DIM == 3) ? S3::OFF_R : S2::OFF_R;
    static constexpr int OFF_X = (DIM == 3) ? S3::OFF_X : S2::OFF_X;
+   // resident blocks per SM the register allocation must allow (shared memory permitting)
+#ifndef RMH_MINB
+#define RMH_MINB 3
+#endif
+   static constexpr int MINB = (DIM == 3 && BYTES * RMH_MINB <= 200 * 1024) ? RMH_MINB : 1;
 };
 
 // (a) + (b) on the block's element batch: U (smem) -> R = K_HO u -> X = M^-1 R; returns result ptr
@@ -415,7 +420,7 @@ struct StageArgs
 };
 
 template <int DIM, int D1, int Q, int E>
-__global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, const Tab<D1, Q> tab)
+__global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T, KCfg<DIM, D1, Q, E>::MINB) k_stage(StageArgs a, const Tab<D1, Q> tab)
 {
    using K = KCfg<DIM, D1, Q, E>;
    constexpr int T = K::T, ND = ipow(D1, DIM), NF = 2 * DIM;
@@ -427,14 +432,45 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, c
    for (int t = threadIdx.x; t < E * ND; t += T) { U[t] = (t < ne * ND) ? a.ho.u[e0 * ND + t] : 0.0; }
    HoArgs ha = a.ho;
    ha.mode = 3;
+   // element-wise inputs of this warp's element: issued before the HO phases so that their
+   // HBM latency overlaps the contractions
+   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const bool mine = (w < ne);
+   const int64_t ge = e0 + (mine ? w : 0);
+   double m[NK], x0v[NK], bmn[NK], bmx[NK];
+#pragma unroll
+   for (int k = 0; k < NK; k++)
+   {
+      const int j = lane + 32 * k;
+      m[k] = 1.0; x0v[k] = 0.0; bmn[k] = 0.0; bmx[k] = 0.0;
+      if (mine && j < ND)
+      {
+         m[k] = a.ml[ge * ND + j];
+         if (a.out_mode == 1) { x0v[k] = a.x0[ge * ND + j]; }
+         if (a.bounds_type == 0)
+         {
+            const int ent = a.lat[ge * N3 + lattice_class(DIM, D1, j)];
+            bmn[k] = a.ent_min[ent]; bmx[k] = a.ent_max[ent];
+         }
+      }
+   }
+   if (mine && a.bounds_type == 1)
+   {
+      double bmin = a.xe_min[ge], bmax = a.xe_max[ge];
+      for (int fc = 0; fc < NF; fc++)
+      {
+         const int nb = a.bnbr[ge * NF + fc];
+         if (nb >= 0) { bmin = fmin(bmin, a.xe_min[nb]); bmax = fmax(bmax, a.xe_max[nb]); }
+      }
+#pragma unroll
+      for (int k = 0; k < NK; k++) { bmn[k] = bmin; bmx[k] = bmax; }
+   }
    const double *X = ho_phases<DIM, D1, Q, E>(ha, sm, e0, ne, tab);
    __syncthreads();
    // ---- element-wise part: one warp per element
-   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   if (w >= ne) { return; }
-   const int64_t ge = e0 + w;
+   if (!mine) { return; }
    const double dt = a.dt;
-   double m[NK], u[NK], f[NK], lo[NK];
+   double u[NK], f[NK], lo[NK];
    double s1 = 0.0, s0 = 0.0;
 #pragma unroll
    for (int k = 0; k < NK; k++)
@@ -442,24 +478,13 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, c
       const int j = lane + 32 * k;
       if (j < ND)
       {
-         m[k] = a.ml[ge * ND + j];
          u[k] = U[w * ND + j];
          s1 += m[k] * (u[k] + dt * X[w * ND + j]);
          s0 += m[k];
       }
    }
-   s1 = warp_sum(s1); s0 = warp_sum(s0);
+   warp_sum2(s1, s0);
    const double ubar = s1 / s0;                        // MassBasedAvg, remhos_lo.cpp:278-285
-   double bmin = 0.0, bmax = 0.0;
-   if (a.bounds_type == 1)
-   {
-      bmin = a.xe_min[ge]; bmax = a.xe_max[ge];
-      for (int fc = 0; fc < NF; fc++)
-      {
-         const int nb = a.bnbr[ge * NF + fc];
-         if (nb >= 0) { bmin = fmin(bmin, a.xe_min[nb]); bmax = fmax(bmax, a.xe_max[nb]); }
-      }
-   }
    double sumPos = 0.0, sumNeg = 0.0;
 #pragma unroll
    for (int k = 0; k < NK; k++)
@@ -467,12 +492,7 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, c
       const int j = lane + 32 * k;
       if (j < ND)
       {
-         double umin = bmin, umax = bmax;
-         if (a.bounds_type == 0)
-         {
-            const int ent = a.lat[ge * N3 + lattice_class(DIM, D1, j)];
-            umin = a.ent_min[ent]; umax = a.ent_max[ent];
-         }
+         const double umin = bmn[k], umax = bmx[k];
          lo[k] = (ubar - u[k]) / dt;
          const double u_new_lo = u[k] + dt * lo[k];
          const double fmn = m[k] / dt * (umin - u_new_lo);
@@ -484,7 +504,7 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, c
          sumPos += fmax(fcl, 0.0);
       }
    }
-   sumNeg = warp_sum(sumNeg); sumPos = warp_sum(sumPos);
+   warp_sum2(sumNeg, sumPos);
    const double new_mass = sumNeg + sumPos;
    constexpr double eps = 1.0e-15;
    double omin = INFINITY, omax = -INFINITY;
@@ -499,14 +519,14 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_stage(StageArgs a, c
          if (new_mass < -eps) { fcl = fmax(0.0, fcl) - fmin(0.0, fcl) * sumPos / sumNeg; }
          const double du = lo[k] + fcl / m[k];
          double o = du;
-         if (a.out_mode == 1) { o = a.a * a.x0[ge * ND + j] + a.b * (u[k] + dt * du); }
+         if (a.out_mode == 1) { o = a.a * x0v[k] + a.b * (u[k] + dt * du); }
          a.out[ge * ND + j] = o;
          omin = fmin(omin, o); omax = fmax(omax, o);
       }
    }
    if (a.xe_min_out)
    {
-      omin = warp_min(omin); omax = warp_max(omax);
+      warp_minmax(omin, omax);
       if (lane == 0) { a.xe_min_out[ge] = omin; a.xe_max_out[ge] = omax; }
    }
 }

@@ -406,6 +406,27 @@ __device__ __forceinline__ double warp_sum(double v)
    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
    return v;
 }
+// two independent sums in flight (halves the shuffle-latency chain)
+__device__ __forceinline__ void warp_sum2(double &a, double &b)
+{
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1)
+   {
+      const double ta = __shfl_xor_sync(0xffffffffu, a, o);
+      const double tb = __shfl_xor_sync(0xffffffffu, b, o);
+      a += ta; b += tb;
+   }
+}
+__device__ __forceinline__ void warp_minmax(double &mn, double &mx)
+{
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1)
+   {
+      const double ta = __shfl_xor_sync(0xffffffffu, mn, o);
+      const double tb = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = fmin(mn, ta); mx = fmax(mx, tb);
+   }
+}
 __device__ __forceinline__ double warp_min(double v)
 {
 #pragma unroll

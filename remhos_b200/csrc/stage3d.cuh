@@ -547,20 +547,20 @@ __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
    if (mine) { for (int j = lane; j < ND; j += 32) { Rv[w * ND + j] *= iscale; } }
    __syncthreads();
    kron3_apply<D1, Q, E>(Rv, Z, tab, t);
-   double rz = 0.0;
+   double rz = 0.0, rr0 = 0.0;
    if (mine)
    {
       for (int j = lane; j < ND; j += 32)
       {
-         const double z = Z[w * ND + j];
+         const double z = Z[w * ND + j], r = Rv[w * ND + j];
          P[w * ND + j] = z;
          X[w * ND + j] = 0.0;
-         rz += Rv[w * ND + j] * z;
+         rz += r * z;
+         rr0 += r * r;
       }
    }
-   rz = warp_sum(rz);
-   const double rz0 = rz;
-   bool active = nonzero && (rz0 > 0.0);
+   warp_sum2(rz, rr0);
+   bool active = nonzero && (rz > 0.0);
    __syncthreads();
    for (int it = 0; it < maxit; it++)
    {
@@ -570,20 +570,25 @@ __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
       if (mine) { for (int j = lane; j < ND; j += 32) { pap += P[w * ND + j] * Z[w * ND + j]; } }
       pap = warp_sum(pap);
       const double alpha = active ? rz / pap : 0.0;
+      double rr = 0.0;
       if (mine)
       {
          for (int j = lane; j < ND; j += 32)
          {
             X[w * ND + j] += alpha * P[w * ND + j];
-            Rv[w * ND + j] -= alpha * Z[w * ND + j];
+            const double r = Rv[w * ND + j] - alpha * Z[w * ND + j];
+            Rv[w * ND + j] = r;
+            rr += r * r;
          }
       }
-      __syncthreads();
+      rr = warp_sum(rr);
+      // converged when |r|_2 <= tol |r0|_2: skips the trailing preconditioner application
+      if (active && !(rr > tol2 * rr0)) { active = false; }
+      if (!__syncthreads_or(active)) { break; }
       kron3_apply<D1, Q, E>(Rv, Z, tab, t);
       double rzn = 0.0;
       if (mine) { for (int j = lane; j < ND; j += 32) { rzn += Rv[w * ND + j] * Z[w * ND + j]; } }
       rzn = warp_sum(rzn);
-      if (active && !(rzn > tol2 * rz0)) { active = false; }
       const double beta = active ? rzn / rz : 0.0;
       if (mine)
       {
