@@ -55,6 +55,7 @@ struct rmh_ctx
    double *X0 = nullptr, *V = nullptr, *velq = nullptr, *velf = nullptr;
    // operator (PA) data
    double *Dvol = nullptr, *detJw = nullptr, *Dface = nullptr, *ml = nullptr, *inflow = nullptr;
+   double *einv = nullptr;   // [ne] 1/volume for elements with constant Jacobian determinant, else 0
    // face neighbours
    int32_t *nbr_elem = nullptr;
    uint8_t *nbr_pat = nullptr;
@@ -246,6 +247,45 @@ __global__ void k_geom_face(GeomArgs g)
    else { g.Dface[idx] = w * vs; }
 }
 
+// per element: einv = 1/volume if det J is constant over the element (then M = vol * M_ref
+// exactly and the Kronecker inverse is the exact mass inverse), else 0
+__global__ void k_elem_affine(int dim, int Q, int ngn, int exec_mode, double t, int64_t ne,
+                              const double *w, const double *detJw, const double *X0,
+                              const double *V, double *einv)
+{
+   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (e >= ne) { return; }
+   int NQ = 1;
+   for (int a = 0; a < dim; a++) { NQ *= Q; }
+   const double *d = detJw + (size_t)e * NQ;
+   double vol = 0.0;
+   for (int q = lane; q < NQ; q += 32) { vol += d[q]; }
+   vol = warp_sum(vol);
+   double dev = 0.0;
+   for (int q = lane; q < NQ; q += 32)
+   {
+      double wq = 1.0;
+      int m = q;
+      for (int a = 0; a < dim; a++) { wq *= w[m % Q]; m /= Q; }
+      dev = fmax(dev, fabs(d[q] / wq - vol));
+   }
+   dev = warp_max(dev);
+   // the Jacobian is a difference of coordinates of size |x| over a distance h, so det J carries
+   // a relative round-off of ~eps*|x|/h: deviations below that are not geometry, they are noise
+   double xmax = 0.0;
+   for (int n = lane; n < ngn * dim; n += 32)
+   {
+      double x = X0[(size_t)e * ngn * dim + n];
+      if (exec_mode == 1) { x += t * V[(size_t)e * ngn * dim + n]; }
+      xmax = fmax(xmax, fabs(x));
+   }
+   xmax = warp_max(xmax);
+   const double h = pow(fabs(vol), 1.0 / dim);
+   const double tol = 100.0 * 2.220446049250313e-16 * fmax(1.0, xmax / h);
+   if (lane == 0) { einv[e] = (vol > 0.0 && dev <= tol * vol) ? 1.0 / vol : 0.0; }
+}
+
 // lumped mass m_i = sum_q B_qi detJw_q  (M_HO * 1, remhos.cpp:721-727)
 __global__ void k_lumped_mass(int dim, int D1, int Q, int64_t ne, const double *B,
                               const double *detJw, double *ml)
@@ -292,7 +332,7 @@ struct HoArgs
    int64_t ne;
    const double *u;       // input: solution (mode has MULT) or rhs (mode == SOLVE only)
    double *out;
-   const double *Dvol, *detJw, *Dface;
+   const double *Dvol, *detJw, *Dface, *einv;
    FaceNbr fn;
    int mode;              // bit 0: apply K_HO, bit 1: apply M^-1
    double tol2;
@@ -347,13 +387,12 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
    double *res = R;
    if constexpr (DIM == 3)
    {
-      const Tid3<D1, Q, E> t;
-      if (a.mode & 1) { face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne, t); }
+      if (a.mode & 1) { face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne); }
       __syncthreads();
       if (a.mode & 1)
       {
-         face3_apply<D1, Q, E>(sm, a.Dface + (size_t)e0 * NF * NQF, ne, tab, t);
-         vol3_apply<D1, Q, E, true>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab, t);
+         face3_apply<D1, Q, E>(sm, a.Dface + (size_t)e0 * NF * NQF, ne, tab);
+         vol3_apply<D1, Q, E, true>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
       }
       else
       {
@@ -362,7 +401,8 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
       }
       if (a.mode & 2)
       {
-         mass3_solve<D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, ne, a.tol2, a.maxit, tab, t);
+         mass3_solve<D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, a.einv + e0, ne, a.tol2,
+                               a.maxit, tab);
          res = X;
       }
    }
@@ -809,6 +849,9 @@ static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
    k_lumped_mass<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->dim, c->D1, c->Q, c->ne, c->dB,
                                                                  c->detJw, c->ml);
    LAUNCH_OK();
+   k_elem_affine<<<(unsigned)((c->ne * 32 + bs - 1) / bs), bs, 0, s>>>(
+      c->dim, c->Q, c->NGN, c->exec_mode, t, c->ne, c->dw, c->detJw, c->X0, c->V, c->einv);
+   LAUNCH_OK();
    c->t_cur = t;
    return 0;
 }
@@ -994,6 +1037,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    if (dev_alloc(c, &c->detJw, (size_t)c->ne * c->NQ)) { return fail(); }
    if (dev_alloc(c, &c->Dface, (size_t)c->ne * c->NF * c->NQF)) { return fail(); }
    if (dev_alloc(c, &c->ml, (size_t)c->N)) { return fail(); }
+   if (dev_alloc(c, &c->einv, (size_t)c->ne)) { return fail(); }
    if (dev_alloc(c, &c->w1, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->w2, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->w3, (size_t)c->N)) { return fail(); }
@@ -1032,7 +1076,7 @@ static HoArgs ho_args(rmh_ctx *c, const double *in, double *out, int mode)
 {
    HoArgs a;
    a.ne = c->ne; a.u = in; a.out = out;
-   a.Dvol = c->Dvol; a.detJw = c->detJw; a.Dface = c->Dface;
+   a.Dvol = c->Dvol; a.detJw = c->detJw; a.Dface = c->Dface; a.einv = c->einv;
    a.fn.nbr_elem = c->nbr_elem; a.fn.nbr_pat = c->nbr_pat; a.fn.pat = c->pat;
    a.fn.ughost = c->ughost; a.fn.ne_owned = c->ne;
    a.mode = mode; a.tol2 = c->pcg_tol2; a.maxit = c->pcg_maxit;

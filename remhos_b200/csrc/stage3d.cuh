@@ -1,19 +1,21 @@
 // 3D hexahedral fast path of the RK-stage kernels (sm_100a, FP64).
 //
-// Thread mapping: every element of the block's batch owns TPE = max(32, Q*Q) threads with fixed
-// coordinates (a, b) in [0,Q)^2 for the whole kernel.  Each sum-factorisation stage maps (a, b)
-// to the two tensor axes that are NOT contracted and keeps the contracted line in registers:
+// Every sum-factorisation stage is a flat list of independent "line tasks" (one contracted line
+// held in registers per task); tasks are dealt to threads in order, so the active threads of a
+// stage are the first ntasks ones (whole warps idle at the barrier instead of executing masked
+// instructions).  Shared-memory layouts always have the un-contracted fastest index mapped to
+// consecutive threads:
 //
-//   fwd-x  (a,b) = (y,z)     u[z][y][:]          -> Bx u, Gx u            [z][y][qx]
-//   fwd-y  (a,b) = (qx,z)    [z][:][qx]          -> BB, BG, GB            [z][qy][qx]
-//   z-fused(a,b) = (qx,qy)   [:][qy][qx]         -> grad at 6 qz points in registers,
-//                            x D (prefetched from HBM into registers), Bz^T -> [iz][qy][qx]
-//   bwd-y  (a,b) = (qx,iz)   [iz][:][qx]         -> [iz][iy][qx]
-//   bwd-x  (a,b) = (iy,iz)   [iz][iy][:]         -> rhs line (+ face contributions)
+//   fwd-x   (arr,e,z,y)      u[e][z][y][:]      -> BU | GU          [e][z][y][qx]
+//   fwd-y   (arr,e,z,qx)     [e][z][:][qx]      -> BB | BG | GB     [e][z][qy][qx]
+//   z-fused (e,qy,qx)        [e][:][qy][qx]     -> reference gradient at the Q points of the
+//                            column in registers, x D (prefetched from HBM into registers one
+//                            stage earlier), contracted back with Bz^T      -> [e][iz][qy][qx]
+//   bwd-y   (e,iz,qx)        [e][iz][:][qx]     -> [e][iz][iy][qx]
+//   bwd-x   (e,iz,iy)        [e][iz][iy][:]     -> rhs line + owner-computes face contributions
 //
-// so consecutive threads touch consecutive shared-memory words in every stage (a is always the
-// fastest index), no gradient array at the quadrature points is ever stored, and the stored
-// operator data is loaded with fully coalesced accesses one stage ahead of its use.
+// No array at the quadrature points is ever stored; the stored operator data is read with fully
+// coalesced loads.
 #ifndef RMH_STAGE3D_CUH
 #define RMH_STAGE3D_CUH
 
@@ -28,7 +30,7 @@ struct Smem3
    static constexpr int ND = D1 * D1 * D1, NQ = Q * Q * Q, QQ = Q * Q;
    static constexpr int NF = 6, NFD = D1 * D1, NQF = Q * Q;
    static constexpr int TPE = QQ > 32 ? QQ : 32;            // threads per element
-   static constexpr int T = ((TPE * E + 31) / 32) * 32;     // block size
+   static constexpr int T = ((TPE * E + 31) / 32) * 32;     // block size (>= 32*E and >= QQ*E)
    static constexpr int SZ_V = E * ND;
    static constexpr int SZ_C0 = 2 * E * D1 * D1 * Q, SZ_C1 = E * NF * D1 * Q;
    static constexpr int SZ_C = SZ_C0 > SZ_C1 ? SZ_C0 : SZ_C1;
@@ -47,41 +49,33 @@ struct Smem3
    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
 };
 
-// thread coordinates
-template <int D1, int Q, int E>
-struct Tid3
-{
-   int e, a, b, r;
-   bool ok;      // r < Q*Q and e < E
-   __device__ __forceinline__ Tid3()
-   {
-      using S = Smem3<D1, Q, E>;
-      e = threadIdx.x / S::TPE;
-      r = threadIdx.x - e * S::TPE;
-      b = r / Q;
-      a = r - b * Q;
-      ok = (r < S::QQ) && (e < E);
+// out[o] = sum_i M(o,i) x[i] with compile-time indexed coefficients
+#define RMH_LINE(NOUT, NIN, MAT, X, OUT)                                      \
+   _Pragma("unroll") for (int o_ = 0; o_ < (NOUT); o_++)                      \
+   {                                                                          \
+      double acc_ = 0.0;                                                      \
+      _Pragma("unroll") for (int i_ = 0; i_ < (NIN); i_++)                    \
+      { acc_ = fma(MAT(o_, i_), (X)[i_], acc_); }                             \
+      (OUT)[o_] = acc_;                                                       \
    }
-};
 
 // ---------------------------------------------------------------- face terms
 // gather own - neighbour face DOF differences (global loads; call first, use after a sync)
 template <int D1, int Q, int E>
 __device__ __forceinline__ void face3_gather(double *sm, const double *__restrict__ ug,
-                                             const FaceNbr &fn, int64_t e0, int ne,
-                                             const Tid3<D1, Q, E> &t)
+                                             const FaceNbr &fn, int64_t e0, int ne)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD;
+   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, T = S::T;
    double *FD = sm + S::OFF_F;
-   if (t.e >= E) { return; }
-   for (int idx = t.r; idx < NF * NFD; idx += S::TPE)
+   for (int id = threadIdx.x; id < E * NF * NFD; id += T)
    {
+      const int e = id / (NF * NFD), idx = id - e * (NF * NFD);
       const int f = idx / NFD, j = idx - f * NFD;
       double d = 0.0;
-      if (t.e < ne)
+      if (e < ne)
       {
-         const int64_t ge = e0 + t.e;
+         const int64_t ge = e0 + e;
          const double own = ug[ge * ND + face_dof<3, D1>(f, j)];
          const int64_t nb = fn.nbr_elem[ge * NF + f];
          double un = 0.0;
@@ -92,103 +86,73 @@ __device__ __forceinline__ void face3_gather(double *sm, const double *__restric
          }
          d = own - un;
       }
-      FD[t.e * NF * NFD + idx] = d;
+      FD[id] = d;
    }
 }
 
-// FD (differences) -> FD (face contributions to the rhs), Dface layout [e][qb][f][qa]
+// FD (differences) -> FD (face contributions to the rhs); Dface layout [e][qb][f][qa]
 template <int D1, int Q, int E>
 __device__ __forceinline__ void face3_apply(double *sm, const double *__restrict__ Dface, int ne,
-                                            const Tab<D1, Q> &tab, const Tid3<D1, Q, E> &t)
+                                            const Tab<D1, Q> &tab)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int NF = S::NF, NFD = S::NFD, QQ = S::QQ;
-   double *FD = sm + S::OFF_F + t.e * NF * NFD;
-   double *F1 = sm + S::OFF_C + t.e * NF * D1 * Q;
-   double *F1b = sm + S::OFF_B + t.e * NF * D1 * Q;
-   const bool live = t.ok && (t.e < ne);
-   // prefetch the face data of this thread's (qa = a) column: [qb][f][qa]
-   double df[(NF + Q - 1) / Q][Q];
-   if (live)
+   constexpr int NF = S::NF, QQ = S::QQ, T = S::T;
+   constexpr int NT2 = E * NF * Q;                 // fused-stage tasks (e, f, qa)
+   constexpr int K2 = (NT2 + T - 1) / T;
+   double *FD = sm + S::OFF_F, *F1 = sm + S::OFF_C, *F1b = sm + S::OFF_B;
+   auto mB = [&](int o, int i) { return tab.B[o][i]; };
+   auto mBt = [&](int o, int i) { return tab.B[i][o]; };
+   // prefetch the face data of this thread's fused-stage task(s)
+   double df[K2][Q];
+#pragma unroll
+   for (int k = 0; k < K2; k++)
    {
+      const int id = threadIdx.x + k * T;
+      const int e = id / (NF * Q), r = id - e * (NF * Q);
+      const bool live = (id < NT2) && (e < ne);
 #pragma unroll
-      for (int k = 0; k < (NF + Q - 1) / Q; k++)
-      {
-         const int f = t.b + k * Q;
-#pragma unroll
-         for (int qb = 0; qb < Q; qb++)
-         {
-            df[k][qb] = (f < NF) ? Dface[(size_t)t.e * NF * QQ + qb * NF * Q + f * Q + t.a] : 0.0;
-         }
-      }
+      for (int q = 0; q < Q; q++) { df[k][q] = live ? Dface[(size_t)e * NF * QQ + q * NF * Q + r] : 0.0; }
    }
-   // F1: (a, b) = (jb, f): contract ja -> qa
-   if (t.ok && t.a < D1)
+   // F1: tasks (e, f, jb): contract ja -> qa
+   for (int id = threadIdx.x; id < E * NF * D1; id += T)
    {
-      for (int f = t.b; f < NF; f += Q)
+      double x[D1], y[Q];
+#pragma unroll
+      for (int i = 0; i < D1; i++) { x[i] = FD[id * D1 + i]; }
+      RMH_LINE(Q, D1, mB, x, y)
+#pragma unroll
+      for (int q = 0; q < Q; q++) { F1[id * Q + q] = y[q]; }
+   }
+   __syncthreads();
+   // F2: tasks (e, f, qa): contract jb -> qb, scale by the face data, contract qb -> ib
+#pragma unroll
+   for (int k = 0; k < K2; k++)
+   {
+      const int id = threadIdx.x + k * T;
+      if (id < NT2)
       {
-         double x[D1];
+         const int ef = id / Q, qa = id - ef * Q;
+         double x[D1], y[Q], z[D1];
 #pragma unroll
-         for (int i = 0; i < D1; i++) { x[i] = FD[(f * D1 + t.a) * D1 + i]; }
+         for (int i = 0; i < D1; i++) { x[i] = F1[(ef * D1 + i) * Q + qa]; }
+         RMH_LINE(Q, D1, mB, x, y)
 #pragma unroll
-         for (int q = 0; q < Q; q++)
-         {
-            double acc = 0.0;
+         for (int q = 0; q < Q; q++) { y[q] *= df[k][q]; }
+         RMH_LINE(D1, Q, mBt, y, z)
 #pragma unroll
-            for (int i = 0; i < D1; i++) { acc = fma(tab.B[q][i], x[i], acc); }
-            F1[(f * D1 + t.a) * Q + q] = acc;
-         }
+         for (int i = 0; i < D1; i++) { F1b[(ef * D1 + i) * Q + qa] = z[i]; }
       }
    }
    __syncthreads();
-   // F2: (a, b) = (qa, f): contract jb -> qb, scale by the face data, contract qb -> ib
-   if (t.ok)
+   // F3: tasks (e, f, ib): contract qa -> ia
+   for (int id = threadIdx.x; id < E * NF * D1; id += T)
    {
+      double x[Q], y[D1];
 #pragma unroll
-      for (int k = 0; k < (NF + Q - 1) / Q; k++)
-      {
-         const int f = t.b + k * Q;
-         if (f < NF)
-         {
-            double x[D1];
+      for (int q = 0; q < Q; q++) { x[q] = F1b[id * Q + q]; }
+      RMH_LINE(D1, Q, mBt, x, y)
 #pragma unroll
-            for (int i = 0; i < D1; i++) { x[i] = F1[(f * D1 + i) * Q + t.a]; }
-            double y[D1];
-#pragma unroll
-            for (int i = 0; i < D1; i++) { y[i] = 0.0; }
-#pragma unroll
-            for (int q = 0; q < Q; q++)
-            {
-               double acc = 0.0;
-#pragma unroll
-               for (int i = 0; i < D1; i++) { acc = fma(tab.B[q][i], x[i], acc); }
-               acc *= live ? df[k][q] : 0.0;
-#pragma unroll
-               for (int i = 0; i < D1; i++) { y[i] = fma(tab.B[q][i], acc, y[i]); }
-            }
-#pragma unroll
-            for (int i = 0; i < D1; i++) { F1b[(f * D1 + i) * Q + t.a] = y[i]; }
-         }
-      }
-   }
-   __syncthreads();
-   // F3: (a, b) = (ib, f): contract qa -> ia
-   if (t.ok && t.a < D1)
-   {
-      for (int f = t.b; f < NF; f += Q)
-      {
-         double x[Q];
-#pragma unroll
-         for (int q = 0; q < Q; q++) { x[q] = F1b[(f * D1 + t.a) * Q + q]; }
-#pragma unroll
-         for (int i = 0; i < D1; i++)
-         {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < Q; q++) { acc = fma(tab.B[q][i], x[q], acc); }
-            FD[(f * D1 + t.a) * D1 + i] = acc;
-         }
-      }
+      for (int i = 0; i < D1; i++) { FD[id * D1 + i] = y[i]; }
    }
    __syncthreads();
 }
@@ -196,98 +160,80 @@ __device__ __forceinline__ void face3_apply(double *sm, const double *__restrict
 // ---------------------------------------------------------------- volume term (+ face combine)
 // R = B^T [D . grad U] + face contributions (FD).  Dvol [e][3][NQ].
 template <int D1, int Q, int E, bool WITH_FACES>
-__device__ __forceinline__ void vol3_apply(const double *Uall, double *Rall, double *sm,
+__device__ __forceinline__ void vol3_apply(const double *U, double *R, double *sm,
                                            const double *__restrict__ Dvol, int ne,
-                                           const Tab<D1, Q> &tab, const Tid3<D1, Q, E> &t)
+                                           const Tab<D1, Q> &tab)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int ND = S::ND, NQ = S::NQ, QQ = S::QQ, NF = S::NF, NFD = S::NFD;
-   const double *U = Uall + t.e * ND;
-   double *R = Rall + t.e * ND;
-   double *BU = sm + S::OFF_C + t.e * 2 * D1 * D1 * Q, *GU = BU + D1 * D1 * Q;
-   double *GB = sm + S::OFF_B + t.e * 3 * D1 * QQ, *BG = GB + D1 * QQ, *BB = BG + D1 * QQ;
-   const double *FC = sm + S::OFF_F + t.e * NF * NFD;
-   const bool live = t.ok && (t.e < ne);
-   // V1 fwd-x: (a, b) = (y, z)
-   if (t.ok && t.a < D1 && t.b < D1)
+   constexpr int NQ = S::NQ, QQ = S::QQ, NFD = S::NFD, NF = S::NF, T = S::T;
+   constexpr int NL = E * D1 * D1;                 // x-lines
+   constexpr int NY = E * D1 * Q;                  // y-lines
+   double *BU = sm + S::OFF_C, *GU = BU + NL * Q;
+   double *GB = sm + S::OFF_B;                     // [e][3][z][qy][qx]: GB, BG, BB per element
+   const double *FC = sm + S::OFF_F;
+   auto mB = [&](int o, int i) { return tab.B[o][i]; };
+   auto mG = [&](int o, int i) { return tab.G[o][i]; };
+   auto mBt = [&](int o, int i) { return tab.B[i][o]; };
+   // V1 fwd-x: tasks (arr, e, z, y)
+   for (int id = threadIdx.x; id < 2 * NL; id += T)
    {
-      double x[D1];
+      const int arr = id / NL, l = id - arr * NL;
+      double x[D1], y[Q];
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = U[(t.b * D1 + t.a) * D1 + i]; }
+      for (int i = 0; i < D1; i++) { x[i] = U[l * D1 + i]; }
+      if (arr == 0) { RMH_LINE(Q, D1, mB, x, y) }
+      else { RMH_LINE(Q, D1, mG, x, y) }
+      double *o = (arr == 0 ? BU : GU) + l * Q;
 #pragma unroll
-      for (int q = 0; q < Q; q++)
-      {
-         double vb = 0.0, vg = 0.0;
-#pragma unroll
-         for (int i = 0; i < D1; i++)
-         {
-            vb = fma(tab.B[q][i], x[i], vb);
-            vg = fma(tab.G[q][i], x[i], vg);
-         }
-         BU[(t.b * D1 + t.a) * Q + q] = vb;
-         GU[(t.b * D1 + t.a) * Q + q] = vg;
-      }
+      for (int q = 0; q < Q; q++) { o[q] = y[q]; }
    }
    // prefetch this thread's column of the stored operator data (used two stages later)
+   const int zid = threadIdx.x;                    // z-stage task (e, qy, qx); T >= E*QQ
+   const int ze = zid / QQ, zr = zid - ze * QQ;
+   const bool zon = zid < E * QQ;
    double d0[Q], d1[Q], d2[Q];
-   if (live)
    {
-      const double *dp = Dvol + (size_t)t.e * 3 * NQ + t.r;
+      const bool live = zon && (ze < ne);
+      const double *dp = Dvol + (size_t)ze * 3 * NQ + zr;
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
-         d0[q] = dp[q * QQ];
-         d1[q] = dp[NQ + q * QQ];
-         d2[q] = dp[2 * NQ + q * QQ];
-      }
-   }
-   else
-   {
-#pragma unroll
-      for (int q = 0; q < Q; q++) { d0[q] = 0.0; d1[q] = 0.0; d2[q] = 0.0; }
-   }
-   __syncthreads();
-   // V2 fwd-y: (a, b) = (qx, z)
-   if (t.ok && t.b < D1)
-   {
-      double x1[D1], x2[D1];
-#pragma unroll
-      for (int i = 0; i < D1; i++)
-      {
-         x1[i] = BU[(t.b * D1 + i) * Q + t.a];
-         x2[i] = GU[(t.b * D1 + i) * Q + t.a];
-      }
-#pragma unroll
-      for (int q = 0; q < Q; q++)
-      {
-         double bb = 0.0, bg = 0.0, gb = 0.0;
-#pragma unroll
-         for (int i = 0; i < D1; i++)
-         {
-            bb = fma(tab.B[q][i], x1[i], bb);
-            bg = fma(tab.G[q][i], x1[i], bg);
-            gb = fma(tab.B[q][i], x2[i], gb);
-         }
-         BB[t.b * QQ + q * Q + t.a] = bb;
-         BG[t.b * QQ + q * Q + t.a] = bg;
-         GB[t.b * QQ + q * Q + t.a] = gb;
+         d0[q] = live ? dp[q * QQ] : 0.0;
+         d1[q] = live ? dp[NQ + q * QQ] : 0.0;
+         d2[q] = live ? dp[2 * NQ + q * QQ] : 0.0;
       }
    }
    __syncthreads();
-   // V3 z-fused: (a, b) = (qx, qy): gradient at the qz points, x D, back-contract z
-   if (t.ok)
+   // V2 fwd-y: tasks (arr, e, z, qx); arr 0: GB = By Gx u, 1: BG = Gy Bx u, 2: BB = By Bx u
+   for (int id = threadIdx.x; id < 3 * NY; id += T)
    {
-      double gb[D1], bg[D1], bb[D1];
+      const int arr = id / NY, l = id - arr * NY;
+      const int ez = l / Q, qx = l - ez * Q;
+      const double *in = (arr == 0 ? GU : BU) + ez * D1 * Q + qx;
+      double x[D1], y[Q];
+#pragma unroll
+      for (int i = 0; i < D1; i++) { x[i] = in[i * Q]; }
+      if (arr == 1) { RMH_LINE(Q, D1, mG, x, y) }
+      else { RMH_LINE(Q, D1, mB, x, y) }
+      const int e = ez / D1, z = ez - e * D1;
+      double *o = GB + ((e * 3 + arr) * D1 + z) * QQ + qx;
+#pragma unroll
+      for (int q = 0; q < Q; q++) { o[q * Q] = y[q]; }
+   }
+   __syncthreads();
+   // V3 z-fused: task (e, qy, qx)
+   if (zon)
+   {
+      double *col = GB + ze * 3 * D1 * QQ + zr;
+      double gb[D1], bg[D1], bb[D1], tz[D1];
 #pragma unroll
       for (int i = 0; i < D1; i++)
       {
-         gb[i] = GB[i * QQ + t.r];
-         bg[i] = BG[i * QQ + t.r];
-         bb[i] = BB[i * QQ + t.r];
+         gb[i] = col[i * QQ];
+         bg[i] = col[(D1 + i) * QQ];
+         bb[i] = col[(2 * D1 + i) * QQ];
+         tz[i] = 0.0;
       }
-      double tz[D1];
-#pragma unroll
-      for (int i = 0; i < D1; i++) { tz[i] = 0.0; }
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
@@ -303,242 +249,223 @@ __device__ __forceinline__ void vol3_apply(const double *Uall, double *Rall, dou
 #pragma unroll
          for (int i = 0; i < D1; i++) { tz[i] = fma(tab.B[q][i], s, tz[i]); }
       }
-      // in place: this thread is the only one touching column r of GB
+      // in place: this task is the only one touching column zr of its element
 #pragma unroll
-      for (int i = 0; i < D1; i++) { GB[i * QQ + t.r] = tz[i]; }
+      for (int i = 0; i < D1; i++) { col[i * QQ] = tz[i]; }
    }
    __syncthreads();
-   // V4 bwd-y: (a, b) = (qx, iz)
-   double *S2 = BU;   // [iz][iy][qx]
-   if (t.ok && t.b < D1)
+   // V4 bwd-y: tasks (e, iz, qx): [e][iz][qy][qx] -> S2 [e][iz][iy][qx]
+   double *S2 = BU;
+   for (int id = threadIdx.x; id < NY; id += T)
    {
-      double x[Q];
+      const int eiz = id / Q, qx = id - eiz * Q;
+      const int e = eiz / D1, iz = eiz - e * D1;
+      const double *in = GB + (e * 3 * D1 + iz) * QQ + qx;
+      double x[Q], y[D1];
 #pragma unroll
-      for (int q = 0; q < Q; q++) { x[q] = GB[t.b * QQ + q * Q + t.a]; }
+      for (int q = 0; q < Q; q++) { x[q] = in[q * Q]; }
+      RMH_LINE(D1, Q, mBt, x, y)
 #pragma unroll
-      for (int i = 0; i < D1; i++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int q = 0; q < Q; q++) { acc = fma(tab.B[q][i], x[q], acc); }
-         S2[(t.b * D1 + i) * Q + t.a] = acc;
-      }
+      for (int i = 0; i < D1; i++) { S2[(eiz * D1 + i) * Q + qx] = y[i]; }
    }
    __syncthreads();
-   // V5 bwd-x + owner-computes face combine: (a, b) = (iy, iz)
-   if (t.ok && t.a < D1 && t.b < D1)
+   // V5 bwd-x + owner-computes face combine: tasks (e, iz, iy)
+   for (int id = threadIdx.x; id < NL; id += T)
    {
-      double x[Q];
+      double x[Q], rr[D1];
 #pragma unroll
-      for (int q = 0; q < Q; q++) { x[q] = S2[(t.b * D1 + t.a) * Q + q]; }
-      double rr[D1];
-#pragma unroll
-      for (int i = 0; i < D1; i++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int q = 0; q < Q; q++) { acc = fma(tab.B[q][i], x[q], acc); }
-         rr[i] = acc;
-      }
+      for (int q = 0; q < Q; q++) { x[q] = S2[id * Q + q]; }
+      RMH_LINE(D1, Q, mBt, x, rr)
       if (WITH_FACES)
       {
+         const int e = id / (D1 * D1), r = id - e * D1 * D1, b = r / D1, a = r - b * D1;
+         const double *fc = FC + e * NF * NFD;
          // faces: 0 z=0 (x,y)  1 y=0 (x,z)  2 x=p (y,z)  3 y=p (x,z)  4 x=0 (y,z)  5 z=p (x,y)
-         rr[0] += FC[4 * NFD + t.b * D1 + t.a];
-         rr[D1 - 1] += FC[2 * NFD + t.b * D1 + t.a];
-         if (t.a == 0)
+         rr[0] += fc[4 * NFD + b * D1 + a];
+         rr[D1 - 1] += fc[2 * NFD + b * D1 + a];
+         if (a == 0)
          {
 #pragma unroll
-            for (int i = 0; i < D1; i++) { rr[i] += FC[1 * NFD + t.b * D1 + i]; }
+            for (int i = 0; i < D1; i++) { rr[i] += fc[1 * NFD + b * D1 + i]; }
          }
-         if (t.a == D1 - 1)
+         if (a == D1 - 1)
          {
 #pragma unroll
-            for (int i = 0; i < D1; i++) { rr[i] += FC[3 * NFD + t.b * D1 + i]; }
+            for (int i = 0; i < D1; i++) { rr[i] += fc[3 * NFD + b * D1 + i]; }
          }
-         if (t.b == 0)
+         if (b == 0)
          {
 #pragma unroll
-            for (int i = 0; i < D1; i++) { rr[i] += FC[0 * NFD + t.a * D1 + i]; }
+            for (int i = 0; i < D1; i++) { rr[i] += fc[0 * NFD + a * D1 + i]; }
          }
-         if (t.b == D1 - 1)
+         if (b == D1 - 1)
          {
 #pragma unroll
-            for (int i = 0; i < D1; i++) { rr[i] += FC[5 * NFD + t.a * D1 + i]; }
+            for (int i = 0; i < D1; i++) { rr[i] += fc[5 * NFD + a * D1 + i]; }
          }
       }
 #pragma unroll
-      for (int i = 0; i < D1; i++) { R[(t.b * D1 + t.a) * D1 + i] = rr[i]; }
+      for (int i = 0; i < D1; i++) { R[id * D1 + i] = rr[i]; }
    }
    __syncthreads();
 }
 
 // ---------------------------------------------------------------- mass apply  Z = M P
 template <int D1, int Q, int E>
-__device__ __forceinline__ void mass3_apply(const double *Pall, double *Zall, double *sm,
+__device__ __forceinline__ void mass3_apply(const double *P, double *Z, double *sm,
                                             const double *__restrict__ detJw, int ne,
-                                            const Tab<D1, Q> &tab, const Tid3<D1, Q, E> &t)
+                                            const Tab<D1, Q> &tab)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int ND = S::ND, NQ = S::NQ, QQ = S::QQ;
-   const double *P = Pall + t.e * ND;
-   double *Z = Zall + t.e * ND;
-   double *C1 = sm + S::OFF_C + t.e * 2 * D1 * D1 * Q;      // [z][y][qx]
-   double *C2 = sm + S::OFF_B + t.e * 3 * D1 * QQ;          // [z][qy][qx]
-   const bool live = t.ok && (t.e < ne);
+   constexpr int NQ = S::NQ, QQ = S::QQ, T = S::T;
+   constexpr int NL = E * D1 * D1, NY = E * D1 * Q;
+   double *C1 = sm + S::OFF_C;                     // [e][z][y][qx]
+   double *C2 = sm + S::OFF_B;                     // [e][z][qy][qx]
+   auto mB = [&](int o, int i) { return tab.B[o][i]; };
+   auto mBt = [&](int o, int i) { return tab.B[i][o]; };
+   const int zid = threadIdx.x, ze = zid / QQ, zr = zid - ze * QQ;
+   const bool zon = zid < E * QQ;
    double dj[Q];
-#pragma unroll
-   for (int q = 0; q < Q; q++) { dj[q] = live ? detJw[(size_t)t.e * NQ + q * QQ + t.r] : 0.0; }
-   if (t.ok && t.a < D1 && t.b < D1)
    {
-      double x[D1];
+      const bool live = zon && (ze < ne);
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = P[(t.b * D1 + t.a) * D1 + i]; }
+      for (int q = 0; q < Q; q++) { dj[q] = live ? detJw[(size_t)ze * NQ + q * QQ + zr] : 0.0; }
+   }
+   for (int id = threadIdx.x; id < NL; id += T)
+   {
+      double x[D1], y[Q];
 #pragma unroll
-      for (int q = 0; q < Q; q++)
-      {
-         double acc = 0.0;
+      for (int i = 0; i < D1; i++) { x[i] = P[id * D1 + i]; }
+      RMH_LINE(Q, D1, mB, x, y)
 #pragma unroll
-         for (int i = 0; i < D1; i++) { acc = fma(tab.B[q][i], x[i], acc); }
-         C1[(t.b * D1 + t.a) * Q + q] = acc;
-      }
+      for (int q = 0; q < Q; q++) { C1[id * Q + q] = y[q]; }
    }
    __syncthreads();
-   if (t.ok && t.b < D1)
+   for (int id = threadIdx.x; id < NY; id += T)
    {
-      double x[D1];
+      const int ez = id / Q, qx = id - ez * Q;
+      double x[D1], y[Q];
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = C1[(t.b * D1 + i) * Q + t.a]; }
+      for (int i = 0; i < D1; i++) { x[i] = C1[(ez * D1 + i) * Q + qx]; }
+      RMH_LINE(Q, D1, mB, x, y)
 #pragma unroll
-      for (int q = 0; q < Q; q++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int i = 0; i < D1; i++) { acc = fma(tab.B[q][i], x[i], acc); }
-         C2[t.b * QQ + q * Q + t.a] = acc;
-      }
+      for (int q = 0; q < Q; q++) { C2[ez * QQ + q * Q + qx] = y[q]; }
    }
    __syncthreads();
-   if (t.ok)
+   if (zon)
    {
-      double x[D1], tz[D1];
+      double *col = C2 + ze * D1 * QQ + zr;
+      double x[D1], y[Q], tz[D1];
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = C2[i * QQ + t.r]; tz[i] = 0.0; }
+      for (int i = 0; i < D1; i++) { x[i] = col[i * QQ]; }
+      RMH_LINE(Q, D1, mB, x, y)
 #pragma unroll
-      for (int q = 0; q < Q; q++)
-      {
-         double acc = 0.0;
+      for (int q = 0; q < Q; q++) { y[q] *= dj[q]; }
+      RMH_LINE(D1, Q, mBt, y, tz)
 #pragma unroll
-         for (int i = 0; i < D1; i++) { acc = fma(tab.B[q][i], x[i], acc); }
-         acc *= dj[q];
-#pragma unroll
-         for (int i = 0; i < D1; i++) { tz[i] = fma(tab.B[q][i], acc, tz[i]); }
-      }
-#pragma unroll
-      for (int i = 0; i < D1; i++) { C2[i * QQ + t.r] = tz[i]; }
+      for (int i = 0; i < D1; i++) { col[i * QQ] = tz[i]; }
    }
    __syncthreads();
-   if (t.ok && t.b < D1)
+   for (int id = threadIdx.x; id < NY; id += T)
    {
-      double x[Q];
+      const int eiz = id / Q, qx = id - eiz * Q;
+      double x[Q], y[D1];
 #pragma unroll
-      for (int q = 0; q < Q; q++) { x[q] = C2[t.b * QQ + q * Q + t.a]; }
+      for (int q = 0; q < Q; q++) { x[q] = C2[eiz * QQ + q * Q + qx]; }
+      RMH_LINE(D1, Q, mBt, x, y)
 #pragma unroll
-      for (int i = 0; i < D1; i++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int q = 0; q < Q; q++) { acc = fma(tab.B[q][i], x[q], acc); }
-         C1[(t.b * D1 + i) * Q + t.a] = acc;
-      }
+      for (int i = 0; i < D1; i++) { C1[(eiz * D1 + i) * Q + qx] = y[i]; }
    }
    __syncthreads();
-   if (t.ok && t.a < D1 && t.b < D1)
+   for (int id = threadIdx.x; id < NL; id += T)
    {
-      double x[Q];
+      double x[Q], y[D1];
 #pragma unroll
-      for (int q = 0; q < Q; q++) { x[q] = C1[(t.b * D1 + t.a) * Q + q]; }
+      for (int q = 0; q < Q; q++) { x[q] = C1[id * Q + q]; }
+      RMH_LINE(D1, Q, mBt, x, y)
 #pragma unroll
-      for (int i = 0; i < D1; i++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int q = 0; q < Q; q++) { acc = fma(tab.B[q][i], x[q], acc); }
-         Z[(t.b * D1 + t.a) * D1 + i] = acc;
-      }
+      for (int i = 0; i < D1; i++) { Z[id * D1 + i] = y[i]; }
    }
    __syncthreads();
 }
 
-// Z = (Minv x Minv x Minv) R
+// Z = (Minv x Minv x Minv) R, optionally scaled per element by einv[e] (affine mass inverse)
 template <int D1, int Q, int E>
-__device__ __forceinline__ void kron3_apply(const double *Rall, double *Zall,
-                                            const Tab<D1, Q> &tab, const Tid3<D1, Q, E> &t)
+__device__ __forceinline__ void kron3_apply(const double *R, double *Z, const Tab<D1, Q> &tab,
+                                            const double *escale = nullptr)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int ND = S::ND;
-   const double *R = Rall + t.e * ND;
-   double *Z = Zall + t.e * ND;
-   const bool on = t.ok && t.a < D1 && t.b < D1;
-   if (on)   // x axis: (a, b) = (y, z)
+   constexpr int ND = S::ND, T = S::T, NL = E * D1 * D1;
+   auto mM = [&](int o, int i) { return tab.Minv[o][i]; };
+   for (int id = threadIdx.x; id < NL; id += T)     // x axis
    {
-      double x[D1];
+      double x[D1], y[D1];
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = R[(t.b * D1 + t.a) * D1 + i]; }
+      for (int i = 0; i < D1; i++) { x[i] = R[id * D1 + i]; }
+      RMH_LINE(D1, D1, mM, x, y)
 #pragma unroll
-      for (int o = 0; o < D1; o++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int i = 0; i < D1; i++) { acc = fma(tab.Minv[o][i], x[i], acc); }
-         Z[(t.b * D1 + t.a) * D1 + o] = acc;
-      }
+      for (int i = 0; i < D1; i++) { Z[id * D1 + i] = y[i]; }
    }
    __syncthreads();
-   if (on)   // y axis: (a, b) = (x, z), in place
+   for (int id = threadIdx.x; id < NL; id += T)     // y axis, tasks (e, z, x), in place
    {
-      double x[D1];
+      const int ez = id / D1, ix = id - ez * D1;
+      double *p = Z + ez * D1 * D1 + ix;
+      double x[D1], y[D1];
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = Z[(t.b * D1 + i) * D1 + t.a]; }
+      for (int i = 0; i < D1; i++) { x[i] = p[i * D1]; }
+      RMH_LINE(D1, D1, mM, x, y)
 #pragma unroll
-      for (int o = 0; o < D1; o++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int i = 0; i < D1; i++) { acc = fma(tab.Minv[o][i], x[i], acc); }
-         Z[(t.b * D1 + o) * D1 + t.a] = acc;
-      }
+      for (int i = 0; i < D1; i++) { p[i * D1] = y[i]; }
    }
    __syncthreads();
-   if (on)   // z axis: (a, b) = (x, y), in place
+   for (int id = threadIdx.x; id < NL; id += T)     // z axis, tasks (e, y, x), in place
    {
-      double x[D1];
+      const int e = id / (D1 * D1), r = id - e * D1 * D1;
+      double *p = Z + e * ND + r;
+      double x[D1], y[D1];
 #pragma unroll
-      for (int i = 0; i < D1; i++) { x[i] = Z[(i * D1 + t.b) * D1 + t.a]; }
+      for (int i = 0; i < D1; i++) { x[i] = p[i * D1 * D1]; }
+      RMH_LINE(D1, D1, mM, x, y)
+      const double sc = escale ? escale[e] : 1.0;
 #pragma unroll
-      for (int o = 0; o < D1; o++)
-      {
-         double acc = 0.0;
-#pragma unroll
-         for (int i = 0; i < D1; i++) { acc = fma(tab.Minv[o][i], x[i], acc); }
-         Z[(o * D1 + t.b) * D1 + t.a] = acc;
-      }
+      for (int i = 0; i < D1; i++) { p[i * D1 * D1] = y[i] * sc; }
    }
    __syncthreads();
 }
 
-// Element mass solve X = M^-1 R (see mass_solve in kernels.cuh); one warp per element for the
-// dot products, the (a,b) mapping for the operator applications.
+// Element mass solve X = M^-1 R.
+//  * affine batch (every element of the block has constant Jacobian): M = vol_e * M_ref exactly,
+//    so X = (Minv x Minv x Minv) R / vol_e -- one Kronecker application, no quadrature data read.
+//  * otherwise: CG preconditioned with that Kronecker inverse, iterated to round-off
+//    (exact-inverse semantics of remhos_ho.cpp:100-116 at the cost profile of the PA
+//    DGMassInverse of :79-80,126).   R is destroyed.
 template <int D1, int Q, int E>
 __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
-                                            const double *__restrict__ detJw, int ne, double tol2,
-                                            int maxit, const Tab<D1, Q> &tab,
-                                            const Tid3<D1, Q, E> &t)
+                                            const double *__restrict__ detJw,
+                                            const double *__restrict__ einv, int ne, double tol2,
+                                            int maxit, const Tab<D1, Q> &tab)
 {
    using S = Smem3<D1, Q, E>;
    constexpr int ND = S::ND;
    double *P = sm + S::OFF_P, *Z = sm + S::OFF_Z;
    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const bool mine = (w < E);          // this warp owns element w in the reductions
+   // einv[e] > 0 marks an affine element and holds 1/vol_e
+   double *esc = P;                    // E doubles of scratch (P is unused on the affine path)
+   bool aff = true;
+   if (threadIdx.x < E)
+   {
+      const double v = (threadIdx.x < ne) ? einv[threadIdx.x] : 1.0;
+      esc[threadIdx.x] = v;
+      aff = v > 0.0;
+   }
+   if (__syncthreads_and(aff))
+   {
+      kron3_apply<D1, Q, E>(Rv, X, tab, esc);
+      return;
+   }
+   __syncthreads();
    double scale = 0.0;
    if (mine) { for (int j = lane; j < ND; j += 32) { scale = fmax(scale, fabs(Rv[w * ND + j])); } }
    scale = warp_max(scale);
@@ -546,7 +473,7 @@ __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
    const double iscale = nonzero ? 1.0 / scale : 0.0;
    if (mine) { for (int j = lane; j < ND; j += 32) { Rv[w * ND + j] *= iscale; } }
    __syncthreads();
-   kron3_apply<D1, Q, E>(Rv, Z, tab, t);
+   kron3_apply<D1, Q, E>(Rv, Z, tab);
    double rz = 0.0, rr0 = 0.0;
    if (mine)
    {
@@ -565,7 +492,7 @@ __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
    for (int it = 0; it < maxit; it++)
    {
       if (!__syncthreads_or(active)) { break; }
-      mass3_apply<D1, Q, E>(P, Z, sm, detJw, ne, tab, t);
+      mass3_apply<D1, Q, E>(P, Z, sm, detJw, ne, tab);
       double pap = 0.0;
       if (mine) { for (int j = lane; j < ND; j += 32) { pap += P[w * ND + j] * Z[w * ND + j]; } }
       pap = warp_sum(pap);
@@ -585,7 +512,7 @@ __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
       // converged when |r|_2 <= tol |r0|_2: skips the trailing preconditioner application
       if (active && !(rr > tol2 * rr0)) { active = false; }
       if (!__syncthreads_or(active)) { break; }
-      kron3_apply<D1, Q, E>(Rv, Z, tab, t);
+      kron3_apply<D1, Q, E>(Rv, Z, tab);
       double rzn = 0.0;
       if (mine) { for (int j = lane; j < ND; j += 32) { rzn += Rv[w * ND + j] * Z[w * ND + j]; } }
       rzn = warp_sum(rzn);
