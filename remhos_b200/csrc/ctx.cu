@@ -66,6 +66,7 @@ struct rmh_ctx
    int32_t n_ent = 0;
    double *ent_min = nullptr, *ent_max = nullptr, *xe_min = nullptr, *xe_max = nullptr;
    bool xe_valid = false;
+   bool all_affine = false;   // every element has constant det J (transport meshes only)
    // halo
    double *ughost = nullptr;
    // scratch
@@ -352,13 +353,13 @@ struct KCfg
    static constexpr int OFF_X = (DIM == 3) ? S3::OFF_X : S2::OFF_X;
    // resident blocks per SM the register allocation must allow (shared memory permitting)
 #ifndef RMH_MINB
-#define RMH_MINB 3
+#define RMH_MINB 2
 #endif
    static constexpr int MINB = (DIM == 3 && BYTES * RMH_MINB <= 200 * 1024) ? RMH_MINB : 1;
 };
 
 // (a) + (b) on the block's element batch: U (smem) -> R = K_HO u -> X = M^-1 R; returns result ptr
-template <int DIM, int D1, int Q, int E>
+template <int DIM, int D1, int Q, int E, bool AFF = false>
 __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_t e0, int ne,
                                              const Tab<D1, Q> &tab);
 
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T) k_ho(HoArgs a, const T
    for (int t = threadIdx.x; t < ne * ND; t += T) { a.out[e0 * ND + t] = res[t]; }
 }
 
-template <int DIM, int D1, int Q, int E>
+template <int DIM, int D1, int Q, int E, bool AFF>
 __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_t e0, int ne,
                                              const Tab<D1, Q> &tab)
 {
@@ -387,23 +388,40 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
    double *res = R;
    if constexpr (DIM == 3)
    {
-      if (a.mode & 1) { face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne); }
-      __syncthreads();
-      if (a.mode & 1)
+      Pre3<D1, Q, E> pre;
+      if constexpr (AFF)
       {
-         face3_apply<D1, Q, E>(sm, a.Dface + (size_t)e0 * NF * NQF, ne, tab);
-         vol3_apply<D1, Q, E, true>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
+         // every element of the mesh has constant det J (checked on the host at set-up)
+         pre.load(a.Dvol + (size_t)e0 * DIM * NQ, a.Dface + (size_t)e0 * NF * NQF, ne);
+         face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne);
+         __syncthreads();
+         ho3_affine<D1, Q, E>(U, X, sm, pre, a.einv + e0, ne, tab);
+         res = X;
       }
       else
       {
-         for (int i = threadIdx.x; i < E * ND; i += T) { R[i] = U[i]; }
+         if (a.mode & 1)
+         {
+            pre.load(a.Dvol + (size_t)e0 * DIM * NQ, a.Dface + (size_t)e0 * NF * NQF, ne);
+            face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne);
+         }
          __syncthreads();
-      }
-      if (a.mode & 2)
-      {
-         mass3_solve<D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, a.einv + e0, ne, a.tol2,
-                               a.maxit, tab);
-         res = X;
+         if (a.mode & 1)
+         {
+            face3_apply<D1, Q, E>(sm, pre, tab);
+            vol3_apply<D1, Q, E, true>(U, R, sm, pre, tab);
+         }
+         else
+         {
+            for (int i = threadIdx.x; i < E * ND; i += T) { R[i] = U[i]; }
+            __syncthreads();
+         }
+         if (a.mode & 2)
+         {
+            mass3_solve<D1, Q, E>(R, X, sm, a.detJw + (size_t)e0 * NQ, a.einv + e0, ne, a.tol2,
+                                  a.maxit, tab);
+            res = X;
+         }
       }
    }
    else
@@ -459,7 +477,7 @@ struct StageArgs
    double *xe_min_out, *xe_max_out;   // may be NULL
 };
 
-template <int DIM, int D1, int Q, int E>
+template <int DIM, int D1, int Q, int E, bool AFF>
 __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T, KCfg<DIM, D1, Q, E>::MINB) k_stage(StageArgs a, const Tab<D1, Q> tab)
 {
    using K = KCfg<DIM, D1, Q, E>;
@@ -472,40 +490,50 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T, KCfg<DIM, D1, Q, E>::M
    for (int t = threadIdx.x; t < E * ND; t += T) { U[t] = (t < ne * ND) ? a.ho.u[e0 * ND + t] : 0.0; }
    HoArgs ha = a.ho;
    ha.mode = 3;
-   // element-wise inputs of this warp's element: issued before the HO phases so that their
-   // HBM latency overlaps the contractions
    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const bool mine = (w < ne);
    const int64_t ge = e0 + (mine ? w : 0);
    double m[NK], x0v[NK], bmn[NK], bmx[NK];
-#pragma unroll
-   for (int k = 0; k < NK; k++)
+   // element-wise inputs of this warp's element (lumped mass, RK base state, bounds)
+   auto load_ew = [&]()
    {
-      const int j = lane + 32 * k;
-      m[k] = 1.0; x0v[k] = 0.0; bmn[k] = 0.0; bmx[k] = 0.0;
-      if (mine && j < ND)
+#pragma unroll
+      for (int k = 0; k < NK; k++)
       {
-         m[k] = a.ml[ge * ND + j];
-         if (a.out_mode == 1) { x0v[k] = a.x0[ge * ND + j]; }
-         if (a.bounds_type == 0)
+         const int j = lane + 32 * k;
+         m[k] = 1.0; x0v[k] = 0.0; bmn[k] = 0.0; bmx[k] = 0.0;
+         if (mine && j < ND)
          {
-            const int ent = a.lat[ge * N3 + lattice_class(DIM, D1, j)];
-            bmn[k] = a.ent_min[ent]; bmx[k] = a.ent_max[ent];
+            m[k] = a.ml[ge * ND + j];
+            if (a.out_mode == 1 && a.a != 0.0) { x0v[k] = a.x0[ge * ND + j]; }
+            if (a.bounds_type == 0)
+            {
+               const int ent = a.lat[ge * N3 + lattice_class(DIM, D1, j)];
+               bmn[k] = a.ent_min[ent]; bmx[k] = a.ent_max[ent];
+            }
          }
       }
-   }
-   if (mine && a.bounds_type == 1)
-   {
-      double bmin = a.xe_min[ge], bmax = a.xe_max[ge];
-      for (int fc = 0; fc < NF; fc++)
+      if (mine && a.bounds_type == 1)
       {
-         const int nb = a.bnbr[ge * NF + fc];
-         if (nb >= 0) { bmin = fmin(bmin, a.xe_min[nb]); bmax = fmax(bmax, a.xe_max[nb]); }
-      }
+         double bmin = a.xe_min[ge], bmax = a.xe_max[ge];
+         for (int fc = 0; fc < NF; fc++)
+         {
+            const int nb = a.bnbr[ge * NF + fc];
+            if (nb >= 0) { bmin = fmin(bmin, a.xe_min[nb]); bmax = fmax(bmax, a.xe_max[nb]); }
+         }
 #pragma unroll
-      for (int k = 0; k < NK; k++) { bmn[k] = bmin; bmx[k] = bmax; }
-   }
-   const double *X = ho_phases<DIM, D1, Q, E>(ha, sm, e0, ne, tab);
+         for (int k = 0; k < NK; k++) { bmn[k] = bmin; bmx[k] = bmax; }
+      }
+   };
+#ifndef RMH_LATE_EW
+#define RMH_LATE_EW 1
+#endif
+   // general path: issue them before the HO phases so their HBM latency overlaps the
+   // contractions; affine path: register pressure is the tighter constraint, load afterwards
+   constexpr bool LATE = AFF && (RMH_LATE_EW != 0);
+   if (!LATE) { load_ew(); }
+   const double *X = ho_phases<DIM, D1, Q, E, AFF>(ha, sm, e0, ne, tab);
+   if (LATE) { load_ew(); }
    __syncthreads();
    // ---- element-wise part: one warp per element
    if (!mine) { return; }
@@ -741,6 +769,13 @@ static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
       for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
    for (int i = 0; i < D1; i++)
       for (int j = 0; j < D1; j++) { tab.Minv[i][j] = c->hMinv[i * D1 + j]; }
+   for (int i = 0; i < D1; i++)
+      for (int q = 0; q < Q; q++)
+      {
+         double v = 0.0;
+         for (int j = 0; j < D1; j++) { v += c->hMinv[i * D1 + j] * c->hB[q * D1 + j]; }
+         tab.C[i][q] = v;
+      }
    static bool attr_set = false;
    if (!attr_set)
    {
@@ -757,7 +792,7 @@ static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
 template <int DIM, int D1, int Q>
 static int launch_ho(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
 {
-   constexpr size_t LIM = 72 * 1024;
+   constexpr size_t LIM = 80 * 1024;
    if constexpr (KCfg<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 8>(c, a, s); }
    else if constexpr (KCfg<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 4>(c, a, s); }
    else if constexpr (KCfg<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_ho_E<DIM, D1, Q, 2>(c, a, s); }
@@ -790,8 +825,8 @@ static int dispatch_ho(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
    RMH_DISPATCH(launch_ho, c, a, s);
 }
 
-template <int DIM, int D1, int Q, int E>
-static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
+template <int DIM, int D1, int Q, int E, bool AFF>
+static int launch_stage_EA(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
 {
    using S = KCfg<DIM, D1, Q, E>;
    Tab<D1, Q> tab;
@@ -799,23 +834,40 @@ static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
       for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
    for (int i = 0; i < D1; i++)
       for (int j = 0; j < D1; j++) { tab.Minv[i][j] = c->hMinv[i * D1 + j]; }
+   for (int i = 0; i < D1; i++)
+      for (int q = 0; q < Q; q++)
+      {
+         double v = 0.0;
+         for (int j = 0; j < D1; j++) { v += c->hMinv[i * D1 + j] * c->hB[q * D1 + j]; }
+         tab.C[i][q] = v;
+      }
    static bool attr_set = false;
    if (!attr_set)
    {
-      CUDA_OK(cudaFuncSetAttribute(k_stage<DIM, D1, Q, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)S::BYTES));
+      CUDA_OK(cudaFuncSetAttribute(k_stage<DIM, D1, Q, E, AFF>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
       attr_set = true;
    }
    const int64_t nb = (a.ho.ne + E - 1) / E;
-   k_stage<DIM, D1, Q, E><<<(unsigned)nb, S::T, S::BYTES, s>>>(a, tab);
+   k_stage<DIM, D1, Q, E, AFF><<<(unsigned)nb, S::T, S::BYTES, s>>>(a, tab);
    LAUNCH_OK();
    return 0;
+}
+
+template <int DIM, int D1, int Q, int E>
+static int launch_stage_E(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
+{
+   if constexpr (DIM == 3)
+   {
+      if (c->all_affine) { return launch_stage_EA<DIM, D1, Q, E, true>(c, a, s); }
+   }
+   return launch_stage_EA<DIM, D1, Q, E, false>(c, a, s);
 }
 
 template <int DIM, int D1, int Q>
 static int launch_stage(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
 {
-   constexpr size_t LIM = 72 * 1024;
+   constexpr size_t LIM = 80 * 1024;
    if constexpr (KCfg<DIM, D1, Q, 8>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 8>(c, a, s); }
    else if constexpr (KCfg<DIM, D1, Q, 4>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 4>(c, a, s); }
    else if constexpr (KCfg<DIM, D1, Q, 2>::BYTES <= LIM) { return launch_stage_E<DIM, D1, Q, 2>(c, a, s); }
@@ -1046,6 +1098,13 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    if (d->inflow) { if (dev_upload(c, &c->inflow, d->inflow, (size_t)c->N)) { return fail(); } }
    if (run_geom(c, 0.0, 0)) { return fail(); }
    CUDA_OK(cudaDeviceSynchronize());
+   if (c->exec_mode == 0)
+   {
+      std::vector<double> ei((size_t)c->ne);
+      CUDA_OK(cudaMemcpy(ei.data(), c->einv, ei.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      c->all_affine = true;
+      for (double v : ei) { if (!(v > 0.0)) { c->all_affine = false; break; } }
+   }
    *out = c;
    return 0;
 }

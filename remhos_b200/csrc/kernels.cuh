@@ -26,6 +26,7 @@ struct Tab
    double B[Q][D1];      // Bernstein values at the Gauss-Legendre points
    double G[Q][D1];      // derivatives
    double Minv[D1][D1];  // inverse of the 1-D Bernstein mass matrix (Kronecker preconditioner)
+   double C[D1][Q];      // Minv * B^T: back-contraction with the mass inverse folded in
 };
 
 // local face -> fixed axis / side (quad: S E N W; hex: bottom south east north west top)

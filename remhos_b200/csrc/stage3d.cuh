@@ -45,7 +45,8 @@ struct Smem3
    static constexpr int OFF_C = OFF_Z + SZ_V;
    static constexpr int OFF_B = OFF_C + SZ_C;
    static constexpr int OFF_F = OFF_B + SZ_B;
-   static constexpr int TOTAL = OFF_F + SZ_F;
+   static constexpr int OFF_G = OFF_F + SZ_F;          // face stage buffer F1 (merged path)
+   static constexpr int TOTAL = OFF_G + SZ_C1;
    static constexpr size_t BYTES = (size_t)TOTAL * sizeof(double);
 };
 
@@ -58,6 +59,41 @@ struct Smem3
       { acc_ = fma(MAT(o_, i_), (X)[i_], acc_); }                             \
       (OUT)[o_] = acc_;                                                       \
    }
+
+// operator data of this thread's z-stage / fused-face-stage tasks, loaded into registers at the
+// very start of the kernel so that one HBM latency covers every operator stream of the block
+template <int D1, int Q, int E>
+struct Pre3
+{
+   using S = Smem3<D1, Q, E>;
+   static constexpr int K2 = (E * S::NF * Q + S::T - 1) / S::T;
+   double d0[Q], d1[Q], d2[Q];
+   double df[K2][Q];
+   __device__ __forceinline__ void load(const double *__restrict__ Dvol,
+                                        const double *__restrict__ Dface, int ne)
+   {
+      constexpr int NQ = S::NQ, QQ = S::QQ, NF = S::NF, T = S::T;
+      const int zid = threadIdx.x, ze = zid / QQ, zr = zid - ze * QQ;
+      const bool live = (zid < E * QQ) && (ze < ne);
+      const double *dp = Dvol + (size_t)ze * 3 * NQ + zr;
+#pragma unroll
+      for (int q = 0; q < Q; q++)
+      {
+         d0[q] = live ? dp[q * QQ] : 0.0;
+         d1[q] = live ? dp[NQ + q * QQ] : 0.0;
+         d2[q] = live ? dp[2 * NQ + q * QQ] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < K2; k++)
+      {
+         const int id = threadIdx.x + k * T;
+         const int e = id / (NF * Q), r = id - e * (NF * Q);
+         const bool lv = (id < E * NF * Q) && (e < ne);
+#pragma unroll
+         for (int q = 0; q < Q; q++) { df[k][q] = lv ? Dface[(size_t)e * NF * QQ + q * NF * Q + r] : 0.0; }
+      }
+   }
+};
 
 // ---------------------------------------------------------------- face terms
 // gather own - neighbour face DOF differences (global loads; call first, use after a sync)
@@ -92,27 +128,16 @@ __device__ __forceinline__ void face3_gather(double *sm, const double *__restric
 
 // FD (differences) -> FD (face contributions to the rhs); Dface layout [e][qb][f][qa]
 template <int D1, int Q, int E>
-__device__ __forceinline__ void face3_apply(double *sm, const double *__restrict__ Dface, int ne,
+__device__ __forceinline__ void face3_apply(double *sm, const Pre3<D1, Q, E> &pre,
                                             const Tab<D1, Q> &tab)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int NF = S::NF, QQ = S::QQ, T = S::T;
+   constexpr int NF = S::NF, T = S::T;
    constexpr int NT2 = E * NF * Q;                 // fused-stage tasks (e, f, qa)
    constexpr int K2 = (NT2 + T - 1) / T;
    double *FD = sm + S::OFF_F, *F1 = sm + S::OFF_C, *F1b = sm + S::OFF_B;
    auto mB = [&](int o, int i) { return tab.B[o][i]; };
    auto mBt = [&](int o, int i) { return tab.B[i][o]; };
-   // prefetch the face data of this thread's fused-stage task(s)
-   double df[K2][Q];
-#pragma unroll
-   for (int k = 0; k < K2; k++)
-   {
-      const int id = threadIdx.x + k * T;
-      const int e = id / (NF * Q), r = id - e * (NF * Q);
-      const bool live = (id < NT2) && (e < ne);
-#pragma unroll
-      for (int q = 0; q < Q; q++) { df[k][q] = live ? Dface[(size_t)e * NF * QQ + q * NF * Q + r] : 0.0; }
-   }
    // F1: tasks (e, f, jb): contract ja -> qa
    for (int id = threadIdx.x; id < E * NF * D1; id += T)
    {
@@ -137,7 +162,7 @@ __device__ __forceinline__ void face3_apply(double *sm, const double *__restrict
          for (int i = 0; i < D1; i++) { x[i] = F1[(ef * D1 + i) * Q + qa]; }
          RMH_LINE(Q, D1, mB, x, y)
 #pragma unroll
-         for (int q = 0; q < Q; q++) { y[q] *= df[k][q]; }
+         for (int q = 0; q < Q; q++) { y[q] *= pre.df[k][q]; }
          RMH_LINE(D1, Q, mBt, y, z)
 #pragma unroll
          for (int i = 0; i < D1; i++) { F1b[(ef * D1 + i) * Q + qa] = z[i]; }
@@ -161,11 +186,10 @@ __device__ __forceinline__ void face3_apply(double *sm, const double *__restrict
 // R = B^T [D . grad U] + face contributions (FD).  Dvol [e][3][NQ].
 template <int D1, int Q, int E, bool WITH_FACES>
 __device__ __forceinline__ void vol3_apply(const double *U, double *R, double *sm,
-                                           const double *__restrict__ Dvol, int ne,
-                                           const Tab<D1, Q> &tab)
+                                           const Pre3<D1, Q, E> &pre, const Tab<D1, Q> &tab)
 {
    using S = Smem3<D1, Q, E>;
-   constexpr int NQ = S::NQ, QQ = S::QQ, NFD = S::NFD, NF = S::NF, T = S::T;
+   constexpr int QQ = S::QQ, NFD = S::NFD, NF = S::NF, T = S::T;
    constexpr int NL = E * D1 * D1;                 // x-lines
    constexpr int NY = E * D1 * Q;                  // y-lines
    double *BU = sm + S::OFF_C, *GU = BU + NL * Q;
@@ -187,22 +211,9 @@ __device__ __forceinline__ void vol3_apply(const double *U, double *R, double *s
 #pragma unroll
       for (int q = 0; q < Q; q++) { o[q] = y[q]; }
    }
-   // prefetch this thread's column of the stored operator data (used two stages later)
    const int zid = threadIdx.x;                    // z-stage task (e, qy, qx); T >= E*QQ
    const int ze = zid / QQ, zr = zid - ze * QQ;
    const bool zon = zid < E * QQ;
-   double d0[Q], d1[Q], d2[Q];
-   {
-      const bool live = zon && (ze < ne);
-      const double *dp = Dvol + (size_t)ze * 3 * NQ + zr;
-#pragma unroll
-      for (int q = 0; q < Q; q++)
-      {
-         d0[q] = live ? dp[q * QQ] : 0.0;
-         d1[q] = live ? dp[NQ + q * QQ] : 0.0;
-         d2[q] = live ? dp[2 * NQ + q * QQ] : 0.0;
-      }
-   }
    __syncthreads();
    // V2 fwd-y: tasks (arr, e, z, qx); arr 0: GB = By Gx u, 1: BG = Gy Bx u, 2: BB = By Bx u
    for (int id = threadIdx.x; id < 3 * NY; id += T)
@@ -245,7 +256,7 @@ __device__ __forceinline__ void vol3_apply(const double *U, double *R, double *s
             g1 = fma(tab.B[q][i], bg[i], g1);
             g2 = fma(tab.G[q][i], bb[i], g2);
          }
-         const double s = d0[q] * g0 + d1[q] * g1 + d2[q] * g2;
+         const double s = pre.d0[q] * g0 + pre.d1[q] * g1 + pre.d2[q] * g2;
 #pragma unroll
          for (int i = 0; i < D1; i++) { tz[i] = fma(tab.B[q][i], s, tz[i]); }
       }
@@ -528,6 +539,182 @@ __device__ __forceinline__ void mass3_solve(double *Rv, double *X, double *sm,
       __syncthreads();
    }
    if (mine) { for (int j = lane; j < ND; j += 32) { X[w * ND + j] *= scale; } }
+   __syncthreads();
+}
+
+// ---------------------------------------------------------------- fused affine HO path
+// X = M^-1 K_HO u for a batch whose elements all have constant det J: the exact mass inverse is
+// einv[e] * (Minv x Minv x Minv), and because contractions along different axes commute it is
+// folded into the three back-contractions (C = Minv B^T replaces B^T) at zero cost; the face
+// contributions get the two tangential Minv factors the same way and the normal one when they
+// are combined into the lines.  Face and volume stages share barrier intervals:
+//   A: fwd-x | face fwd-a     B: fwd-y | face fused     C: z-fused | face back-a
+//   D: bwd-y                  E: bwd-x + face combine -> X
+template <int D1, int Q, int E>
+__device__ __forceinline__ void ho3_affine(const double *U, double *X, double *sm,
+                                           const Pre3<D1, Q, E> &pre,
+                                           const double *__restrict__ einv, int ne,
+                                           const Tab<D1, Q> &tab)
+{
+   using S = Smem3<D1, Q, E>;
+   constexpr int QQ = S::QQ, NFD = S::NFD, NF = S::NF, T = S::T;
+   constexpr int NL = E * D1 * D1, NY = E * D1 * Q, NT1 = E * NF * D1, NT2 = E * NF * Q;
+   constexpr int K2 = (NT2 + T - 1) / T;
+   double *BU = sm + S::OFF_C, *GU = BU + NL * Q;
+   double *GB = sm + S::OFF_B;
+   double *FD = sm + S::OFF_F, *F1 = sm + S::OFF_G;
+   auto mB = [&](int o, int i) { return tab.B[o][i]; };
+   auto mG = [&](int o, int i) { return tab.G[o][i]; };
+   auto mC = [&](int o, int i) { return tab.C[o][i]; };
+   // ---- A: fwd-x tasks (arr, e, z, y)  |  face tasks (e, f, jb): contract ja -> qa
+   for (int id = threadIdx.x; id < 2 * NL + NT1; id += T)
+   {
+      if (id < 2 * NL)
+      {
+         const int arr = id / NL, l = id - arr * NL;
+         double x[D1], y[Q];
+#pragma unroll
+         for (int i = 0; i < D1; i++) { x[i] = U[l * D1 + i]; }
+         if (arr == 0) { RMH_LINE(Q, D1, mB, x, y) }
+         else { RMH_LINE(Q, D1, mG, x, y) }
+         double *o = (arr == 0 ? BU : GU) + l * Q;
+#pragma unroll
+         for (int q = 0; q < Q; q++) { o[q] = y[q]; }
+      }
+      else
+      {
+         const int l = id - 2 * NL;
+         double x[D1], y[Q];
+#pragma unroll
+         for (int i = 0; i < D1; i++) { x[i] = FD[l * D1 + i]; }
+         RMH_LINE(Q, D1, mB, x, y)
+#pragma unroll
+         for (int q = 0; q < Q; q++) { F1[l * Q + q] = y[q]; }
+      }
+   }
+   __syncthreads();
+   // ---- B: fwd-y tasks (arr, e, z, qx)  |  face fused tasks (e, f, qa)
+   for (int id = threadIdx.x; id < 3 * NY; id += T)
+   {
+      const int arr = id / NY, l = id - arr * NY;
+      const int ez = l / Q, qx = l - ez * Q;
+      const double *in = (arr == 0 ? GU : BU) + ez * D1 * Q + qx;
+      double x[D1], y[Q];
+#pragma unroll
+      for (int i = 0; i < D1; i++) { x[i] = in[i * Q]; }
+      if (arr == 1) { RMH_LINE(Q, D1, mG, x, y) }
+      else { RMH_LINE(Q, D1, mB, x, y) }
+      const int e = ez / D1, z = ez - e * D1;
+      double *o = GB + ((e * 3 + arr) * D1 + z) * QQ + qx;
+#pragma unroll
+      for (int q = 0; q < Q; q++) { o[q * Q] = y[q]; }
+   }
+#pragma unroll
+   for (int k = 0; k < K2; k++)
+   {
+      const int id = threadIdx.x + k * T;
+      if (id < NT2)
+      {
+         const int ef = id / Q, qa = id - ef * Q;
+         double x[D1], y[Q], z[D1];
+#pragma unroll
+         for (int i = 0; i < D1; i++) { x[i] = F1[(ef * D1 + i) * Q + qa]; }
+         RMH_LINE(Q, D1, mB, x, y)
+#pragma unroll
+         for (int q = 0; q < Q; q++) { y[q] *= pre.df[k][q]; }
+         RMH_LINE(D1, Q, mC, y, z)
+         // in place: this task owns column (ef, :, qa)
+#pragma unroll
+         for (int i = 0; i < D1; i++) { F1[(ef * D1 + i) * Q + qa] = z[i]; }
+      }
+   }
+   __syncthreads();
+   // ---- C: z-fused task (e, qy, qx)  |  face tasks (e, f, ib): contract qa -> ia
+   {
+      const int zid = threadIdx.x, ze = zid / QQ, zr = zid - ze * QQ;
+      if (zid < E * QQ)
+      {
+         double *col = GB + ze * 3 * D1 * QQ + zr;
+         double gb[D1], bg[D1], bb[D1], tz[D1];
+#pragma unroll
+         for (int i = 0; i < D1; i++)
+         {
+            gb[i] = col[i * QQ];
+            bg[i] = col[(D1 + i) * QQ];
+            bb[i] = col[(2 * D1 + i) * QQ];
+            tz[i] = 0.0;
+         }
+#pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < D1; i++)
+            {
+               g0 = fma(tab.B[q][i], gb[i], g0);
+               g1 = fma(tab.B[q][i], bg[i], g1);
+               g2 = fma(tab.G[q][i], bb[i], g2);
+            }
+            const double s = pre.d0[q] * g0 + pre.d1[q] * g1 + pre.d2[q] * g2;
+#pragma unroll
+            for (int i = 0; i < D1; i++) { tz[i] = fma(tab.C[i][q], s, tz[i]); }
+         }
+#pragma unroll
+         for (int i = 0; i < D1; i++) { col[i * QQ] = tz[i]; }
+      }
+   }
+   for (int id = threadIdx.x; id < NT1; id += T)
+   {
+      double x[Q], y[D1];
+#pragma unroll
+      for (int q = 0; q < Q; q++) { x[q] = F1[id * Q + q]; }
+      RMH_LINE(D1, Q, mC, x, y)
+#pragma unroll
+      for (int i = 0; i < D1; i++) { FD[id * D1 + i] = y[i]; }
+   }
+   __syncthreads();
+   // ---- D: bwd-y tasks (e, iz, qx)
+   double *S2 = BU;
+   for (int id = threadIdx.x; id < NY; id += T)
+   {
+      const int eiz = id / Q, qx = id - eiz * Q;
+      const int e = eiz / D1, iz = eiz - e * D1;
+      const double *in = GB + (e * 3 * D1 + iz) * QQ + qx;
+      double x[Q], y[D1];
+#pragma unroll
+      for (int q = 0; q < Q; q++) { x[q] = in[q * Q]; }
+      RMH_LINE(D1, Q, mC, x, y)
+#pragma unroll
+      for (int i = 0; i < D1; i++) { S2[(eiz * D1 + i) * Q + qx] = y[i]; }
+   }
+   __syncthreads();
+   // ---- E: bwd-x tasks (e, iz, iy) + face contributions with the normal-direction Minv
+   for (int id = threadIdx.x; id < NL; id += T)
+   {
+      double x[Q], rr[D1];
+#pragma unroll
+      for (int q = 0; q < Q; q++) { x[q] = S2[id * Q + q]; }
+      RMH_LINE(D1, Q, mC, x, rr)
+      const int e = id / (D1 * D1), r = id - e * D1 * D1, b = r / D1, a = r - b * D1;
+      const double *fc = FD + e * NF * NFD;
+      // faces: 0 z=0 (x,y)  1 y=0 (x,z)  2 x=p (y,z)  3 y=p (x,z)  4 x=0 (y,z)  5 z=p (x,y)
+      const double fx0 = fc[4 * NFD + b * D1 + a], fx1 = fc[2 * NFD + b * D1 + a];
+      const double my0 = tab.Minv[a][0], my1 = tab.Minv[a][D1 - 1];
+      const double mz0 = tab.Minv[b][0], mz1 = tab.Minv[b][D1 - 1];
+      const double sc = (e < ne) ? einv[e] : 0.0;
+#pragma unroll
+      for (int i = 0; i < D1; i++)
+      {
+         double v = rr[i];
+         v = fma(tab.Minv[i][0], fx0, v);
+         v = fma(tab.Minv[i][D1 - 1], fx1, v);
+         v = fma(my0, fc[1 * NFD + b * D1 + i], v);
+         v = fma(my1, fc[3 * NFD + b * D1 + i], v);
+         v = fma(mz0, fc[0 * NFD + a * D1 + i], v);
+         v = fma(mz1, fc[5 * NFD + a * D1 + i], v);
+         X[id * D1 + i] = v * sc;
+      }
+   }
    __syncthreads();
 }
 
