@@ -166,18 +166,48 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
-    mesh.refine(a.rs)
     h = 2.0 / (3 * 2 ** a.rs)
     dt = 0.25 * h / a.order            # fixed dt = 0.25 h/|v| /p, |v| = 1
-    prob = Problem(mesh, problem=0, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
-                   device=local_rank)
-    ctx = prob.ctx
+    if world == 1:
+        mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+        mesh.refine(a.rs)
+        prob = Problem(mesh, problem=0, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
+                       device=local_rank)
+        ctx = prob.ctx
+
+        def step(t, u, stream):
+            return ctx.rk_step(3, 5, t, dt, u, stream)
+        pdims = [1, 1, 1]
+    else:
+        # weak scaling: every rank owns a (3*2^rs)^3 brick of a periodic box that grows with the
+        # rank count; recursive coordinate bisection of the global Cartesian mesh yields the bricks
+        from remhos_b200.dist import DistProblem
+        pdims = {2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}.get(world)
+        if pdims is None:
+            raise SystemExit('bench.py: --gpus must be 1, 2, 4 or 8')
+        nloc = 3 * 2 ** a.rs
+        mesh = rb.Mesh.cartesian([nloc * d for d in pdims], [2.0 * d for d in pdims],
+                                 origin=[-1.0 * d for d in pdims], periodic=True)
+        prob = DistProblem(mesh, rank, world, problem=0, order=a.order, mesh_order=2,
+                           bounds_type=0, dt=dt, device=local_rank)
+        del mesh
+        ctx = prob.ctx
+
+        def step(t, u, stream):
+            return prob.rk3_step(t, u, stream)
     N = ctx.ndofs
     u = torch.tensor(prob.u0, device='cuda')
     m = torch.empty(N, dtype=torch.float64, device='cuda')
     ctx.lumped_mass(m)
-    mass0 = ctx.reduce(0, u, m)
+
+    def gsum(v, op='sum'):
+        if world == 1:
+            return v
+        tt = torch.tensor([v], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op={'sum': dist.ReduceOp.SUM, 'min': dist.ReduceOp.MIN,
+                                'max': dist.ReduceOp.MAX}[op])
+        return float(tt[0])
+    mass0 = gsum(ctx.reduce(0, u, m))
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -187,7 +217,7 @@ def main():
 
     t = 0.0
     for _ in range(a.warmup):
-        t = ctx.rk_step(3, 5, t, dt, u, stream)
+        t = step(t, u, stream)
     barrier()
     rb.launch_count(reset=True)
     ctx.profile(1)
@@ -197,25 +227,34 @@ def main():
     barrier()
     ev0.record()
     for _ in range(a.steps):
-        t = ctx.rk_step(3, 5, t, dt, u, stream)
+        t = step(t, u, stream)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     launches = rb.launch_count(reset=True)
     kms, klaunch = ctx.profile(0)
-    mass1 = ctx.reduce(0, u, m)
-    umin, umax = ctx.reduce(1, u), ctx.reduce(2, u)
+    mass1 = gsum(ctx.reduce(0, u, m))
+    umin, umax = gsum(ctx.reduce(1, u), 'min'), gsum(ctx.reduce(2, u), 'max')
 
     # end-to-end: state in pinned host memory, H2D + step + D2H every step
     uh = u.cpu().pin_memory()
+
+    def step_host(t):
+        if world == 1:
+            return ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
+        u.copy_(uh, non_blocking=True)
+        t = step(t, u, stream)
+        uh.copy_(u, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return t
     for _ in range(2):
-        ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
+        step_host(t)
     barrier()
     t0 = time.perf_counter()
     e_steps = max(3, a.steps // 2)
     for _ in range(e_steps):
-        ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
+        step_host(t)
     barrier()
     e_ms = (time.perf_counter() - t0) * 1e3
 
@@ -237,7 +276,8 @@ def main():
         'config': {'workload': workload, 'dofs_per_gpu': N, 'elements_per_gpu': ctx.ne,
                    'stages_per_step': STAGES, 'dt': dt,
                    'l2': 'state vectors (453 MB each) and operator data (7.6 GB) exceed the 126 MB L2',
-                   'parallelism': 'dp%d' % world if world > 1 else 'single'},
+                   'parallelism': ('domain decomposition %dx%dx%d bricks, NCCL halo exchange per stage'
+                                   % tuple(pdims)) if world > 1 else 'single GPU'},
         'e2e': {'value': e2e, 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 8 * N,
                 'd2h_bytes_per_step': 8 * N, 'steps': e_steps},
         'gpu_launches': int(launches),

@@ -59,6 +59,22 @@ const int64_t *rmh_mesh_elem_vertices(const rmh_mesh *m);
 /* Keep only the listed elements (used by the domain decomposition); ids are global. */
 int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *elem_ids, rmh_mesh **out);
 
+/* Domain decomposition (replaces ParMesh's METIS / Cartesian partitioning, remhos.cpp:451-461):
+ * recursive coordinate bisection of the element centroids; part[ne] receives the owner rank. */
+int rmh_mesh_partition(const rmh_mesh *m, int nparts, int32_t *part);
+
+/* Halo plan of one rank (replaces the face-neighbour tables behind
+ * ParGridFunction::ExchangeFaceNbrData and the GroupCommunicator of DofInfo):
+ * owned elements, the ghost ring (elements of other ranks sharing a vertex with an owned one,
+ * ordered by owner then global id) and per peer the owned elements that peer needs. */
+typedef struct rmh_halo rmh_halo;
+int rmh_halo_create(const rmh_mesh *m, const int32_t *part, int rank, rmh_halo **out);
+int rmh_halo_free(rmh_halo *h);
+int rmh_halo_sizes(const rmh_halo *h, int64_t *n_owned, int64_t *n_ghost, int32_t *n_peers,
+                   int64_t *n_send);
+int rmh_halo_get(const rmh_halo *h, int64_t *owned, int64_t *ghost, int32_t *peers,
+                 int32_t *send_off, int32_t *recv_off, int32_t *send_local);
+
 /* DofInfo integer maps (remhos_tools.cpp:356-379):
  *   bdr_dofs [nfd][nf]      ExtractBdrDofs        (:1356-1431)   (row-major nfd x nf)
  *   nbr_dof  [ne][nf][nfd]  FillNeighborDofs      (:525-676), -1 = domain boundary
@@ -179,6 +195,22 @@ int rmh_rk_step(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, doubl
 /* Same call with HOST state: H2D of u, one step, D2H of u (the end-to-end entry point). */
 int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, double dt,
                      double *u_host);
+
+/* ---- multi-GPU: one context per rank; ghost elements follow the owned ones in every index map.
+ * These replace ParGridFunction::ExchangeFaceNbrData (remhos.cpp:1813; inside K.Mult) and the
+ * GroupCommunicator min/max reduction of DofInfo::ComputeOverlapBounds (remhos_tools.cpp:463-466):
+ * the caller moves the packed buffers with NCCL (torch.distributed) between pack and set. */
+/* element min/max of y into the context (needed before the first rmh_halo_pack of a step) */
+int rmh_stage_minmax(rmh_ctx *ctx, const double *y_dev, void *stream);
+/* send_u [n_send][nd] DOF blocks and send_mm [n_send][2] (min,max) of the listed owned elements */
+int rmh_halo_pack(rmh_ctx *ctx, const double *u_dev, const int32_t *send_local_dev, int64_t n_send,
+                  double *send_u_dev, double *send_mm_dev, void *stream);
+/* install received ghost data: ghost_u [ne_ghost][nd] (pointer kept), ghost_mm [ne_ghost][2] */
+int rmh_halo_set(rmh_ctx *ctx, const double *ghost_u_dev, const double *ghost_mm_dev, void *stream);
+/* rmh_rk_stage for a decomposed mesh: assumes the ghosts of y are installed; leaves the element
+ * min/max of `out` in the context (bounds_type 0) for the next pack */
+int rmh_rk_stage_dist(rmh_ctx *ctx, int lo_type, double dt, double a, double b,
+                      const double *x0_dev, const double *y_dev, double *out_dev, void *stream);
 
 /* reductions over owned DOFs: op 0 = sum(a*b) (b may be NULL -> sum a), 1 = min(a), 2 = max(a)
  * (remhos.cpp:1073-1076,1403-1415; GetMinMax remhos_tools.cpp:1433-1439); result on host */

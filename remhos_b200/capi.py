@@ -141,6 +141,14 @@ class Mesh:
         check(lib().rmh_mesh_extract(self.h, C.c_int64(ids.size), _ptr(ids), C.byref(h)))
         return Mesh(h)
 
+    def partition(self, nparts):
+        part = np.zeros(self.ne, dtype=np.int32)
+        check(lib().rmh_mesh_partition(self.h, int(nparts), _ptr(part)))
+        return part
+
+    def halo(self, part, rank):
+        return Halo(self, part, rank)
+
     def dof_maps(self, order):
         d, ne, p = self.dim, self.ne, order
         nf, nfd, nd = 2 * d, (p + 1) ** (d - 1), (p + 1) ** d
@@ -154,6 +162,28 @@ class Mesh:
                                       C.byref(n_ent), _ptr(nbe)))
         return dict(bdr_dofs=bd, nbr_dof=nbr, sub2ind=s2i, lat=lat, n_ent=n_ent.value,
                     nbr_elem=nbe, nd=nd)
+
+
+class Halo:
+    """Halo plan of one rank (rmh_halo_*): owned / ghost global element ids, peers, per-peer
+    send lists (local owned indices) and receive offsets into the ghost ordering."""
+
+    def __init__(self, mesh, part, rank):
+        part = np.ascontiguousarray(part, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().rmh_halo_create(mesh.h, _ptr(part), int(rank), C.byref(h)))
+        no, ng, ns = C.c_int64(), C.c_int64(), C.c_int64()
+        npeer = C.c_int32()
+        check(lib().rmh_halo_sizes(h, C.byref(no), C.byref(ng), C.byref(npeer), C.byref(ns)))
+        self.owned = np.zeros(no.value, dtype=np.int64)
+        self.ghost = np.zeros(ng.value, dtype=np.int64)
+        self.peers = np.zeros(npeer.value, dtype=np.int32)
+        self.send_off = np.zeros(npeer.value + 1, dtype=np.int32)
+        self.recv_off = np.zeros(npeer.value + 1, dtype=np.int32)
+        self.send_local = np.zeros(ns.value, dtype=np.int32)
+        check(lib().rmh_halo_get(h, _ptr(self.owned), _ptr(self.ghost), _ptr(self.peers),
+                                 _ptr(self.send_off), _ptr(self.recv_off), _ptr(self.send_local)))
+        lib().rmh_halo_free(h)
 
 
 class Context:
@@ -254,6 +284,20 @@ class Context:
         check(lib().rmh_rk_step_host(self.h, int(ode_solver_type), int(lo_type), C.byref(tt),
                                      C.c_double(dt), C.c_void_p(int(u_host))))
         return tt.value
+
+    def stage_minmax(self, y, s=0):
+        check(lib().rmh_stage_minmax(self.h, _dp(y), C.c_void_p(s)))
+
+    def halo_pack(self, u, send_local, n_send, send_u, send_mm, s=0):
+        check(lib().rmh_halo_pack(self.h, _dp(u), _dp(send_local), C.c_int64(n_send), _dp(send_u),
+                                  _dp(send_mm), C.c_void_p(s)))
+
+    def halo_set(self, ghost_u, ghost_mm, s=0):
+        check(lib().rmh_halo_set(self.h, _dp(ghost_u), _dp(ghost_mm), C.c_void_p(s)))
+
+    def rk_stage_dist(self, lo_type, dt, a, b, x0, y, out, s=0):
+        check(lib().rmh_rk_stage_dist(self.h, int(lo_type), C.c_double(dt), C.c_double(a),
+                                      C.c_double(b), _dp(x0), _dp(y), _dp(out), C.c_void_p(s)))
 
     def profile(self, enable):
         ms = C.c_double(0.0); n = C.c_int64(0)

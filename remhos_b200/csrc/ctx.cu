@@ -68,7 +68,7 @@ struct rmh_ctx
    bool xe_valid = false;
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    // halo
-   double *ughost = nullptr;
+   const double *ughost = nullptr;   // caller-owned ghost DOF blocks (rmh_halo_set)
    // scratch
    double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *red = nullptr;
    double *pin = nullptr;   // pinned host staging (e2e entry point)
@@ -726,6 +726,27 @@ __global__ void k_clip_scale(int64_t ne, int nd, double dt, const double *u, con
    }
 }
 
+// halo pack: DOF blocks and (min,max) of the elements the peers need (send_local = owned index)
+__global__ void k_halo_pack(int64_t n_send, int nd, const int32_t *send_local, const double *u,
+                            const double *xe_min, const double *xe_max, double *send_u,
+                            double *send_mm)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= n_send * nd) { return; }
+   const int64_t i = idx / nd;
+   const int j = (int)(idx - i * nd);
+   const int64_t e = send_local[i];
+   send_u[idx] = u[e * nd + j];
+   if (j == 0) { send_mm[2 * i] = xe_min[e]; send_mm[2 * i + 1] = xe_max[e]; }
+}
+
+__global__ void k_halo_set_mm(int64_t n_ghost, const double *ghost_mm, double *xe_min_g,
+                              double *xe_max_g)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n_ghost) { xe_min_g[i] = ghost_mm[2 * i]; xe_max_g[i] = ghost_mm[2 * i + 1]; }
+}
+
 // out = a*x0 + b*(y + dt*k)
 __global__ void k_rk_combine(int64_t n, double a, double b, double dt, const double *x0,
                              const double *y, const double *k, double *out)
@@ -1062,7 +1083,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    {
       if (!d->lat || d->n_ent <= 0) { set_error("bounds_type 0 needs desc.lat / n_ent"); return fail(); }
       c->n_ent = d->n_ent;
-      const size_t nl = (size_t)c->ne * c->N3;
+      const size_t nl = (size_t)(c->ne + c->ne_ghost) * c->N3;   // owned + ghost rows
       std::vector<int32_t> off((size_t)c->n_ent + 1, 0), el(nl);
       for (size_t i = 0; i < nl; i++)
       {
@@ -1071,7 +1092,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       }
       for (int i = 0; i < c->n_ent; i++) { off[i + 1] += off[i]; }
       std::vector<int32_t> cur(off.begin(), off.end() - 1);
-      for (int64_t e = 0; e < c->ne; e++)
+      for (int64_t e = 0; e < c->ne + c->ne_ghost; e++)
          for (int t = 0; t < c->N3; t++) { el[cur[d->lat[e * c->N3 + t]]++] = (int32_t)e; }
       if (dev_upload(c, &c->lat, d->lat, nl)) { return fail(); }
       if (dev_upload(c, &c->ent_off, off.data(), off.size())) { return fail(); }
@@ -1094,7 +1115,6 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    if (dev_alloc(c, &c->w2, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->w3, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->red, 4096)) { return fail(); }
-   if (c->ne_ghost > 0) { if (dev_alloc(c, &c->ughost, (size_t)c->ne_ghost * c->ND)) { return fail(); } }
    if (d->inflow) { if (dev_upload(c, &c->inflow, d->inflow, (size_t)c->N)) { return fail(); } }
    if (run_geom(c, 0.0, 0)) { return fail(); }
    CUDA_OK(cudaDeviceSynchronize());
@@ -1377,4 +1397,45 @@ extern "C" int rmh_lo_res_dist(rmh_ctx *, const double *, double *, void *)
 {
    set_error("rmh_lo_res_dist: not implemented yet");
    return 1;
+}
+
+// ---------------------------------------------------------------- halo (multi-GPU) entry points
+extern "C" int rmh_stage_minmax(rmh_ctx *c, const double *y, void *stream)
+{
+   const int bs = 256;
+   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
+   k_elem_min_max<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, y, c->xe_min, c->xe_max);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_halo_pack(rmh_ctx *c, const double *u, const int32_t *send_local, int64_t n_send,
+                             double *send_u, double *send_mm, void *stream)
+{
+   if (n_send == 0) { return 0; }
+   const int bs = 256;
+   const int64_t n = n_send * c->ND;
+   k_halo_pack<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+      n_send, c->ND, send_local, u, c->xe_min, c->xe_max, send_u, send_mm);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_halo_set(rmh_ctx *c, const double *ghost_u, const double *ghost_mm, void *stream)
+{
+   c->ughost = ghost_u;
+   if (c->ne_ghost == 0) { return 0; }
+   const int bs = 256;
+   k_halo_set_mm<<<(unsigned)((c->ne_ghost + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+      c->ne_ghost, ghost_mm, c->xe_min + c->ne, c->xe_max + c->ne);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_rk_stage_dist(rmh_ctx *c, int lo_type, double dt, double a, double b,
+                                 const double *x0, const double *y, double *out, void *stream)
+{
+   // element min/max of y (owned: in the context; ghost: installed by rmh_halo_set) are valid
+   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0,
+                     (cudaStream_t)stream);
 }

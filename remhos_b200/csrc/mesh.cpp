@@ -699,7 +699,150 @@ extern "C" int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *ids
       std::copy(&M.X[(size_t)ids[i] * npe * M.dim], &M.X[(size_t)ids[i] * npe * M.dim] + npe * M.dim,
                 &S.X[(size_t)i * npe * M.dim]);
    }
+   // compact the vertex ids (topology only depends on their identity)
+   {
+      std::vector<int64_t> v(S.ev);
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+      for (auto &x : S.ev) { x = std::lower_bound(v.begin(), v.end(), x) - v.begin(); }
+      S.nv = (int64_t)v.size();
+   }
    *out = r;
+   return 0;
+}
+
+// ------------------------------------------------------------------- domain decomposition
+// Recursive coordinate bisection of the element centroids into nparts (any count; splits are
+// proportional).  Replaces the METIS / Cartesian partitioning ParMesh does (remhos.cpp:451-461).
+static void rcb(const std::vector<double> &cen, int dim, std::vector<int64_t> &idx, int64_t lo,
+                int64_t hi, int p0, int np, int32_t *part)
+{
+   if (np == 1) { for (int64_t i = lo; i < hi; i++) { part[idx[i]] = p0; } return; }
+   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+   for (int64_t i = lo; i < hi; i++)
+      for (int a = 0; a < dim; a++)
+      {
+         mn[a] = std::min(mn[a], cen[idx[i] * dim + a]);
+         mx[a] = std::max(mx[a], cen[idx[i] * dim + a]);
+      }
+   int ax = 0;
+   for (int a = 1; a < dim; a++) { if (mx[a] - mn[a] > (mx[ax] - mn[ax]) * (1.0 + 1e-12)) { ax = a; } }
+   const int npl = np / 2;
+   const int64_t mid = lo + (hi - lo) * npl / np;
+   std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                    [&](int64_t a, int64_t b)
+                    {
+                       const double ca = cen[a * dim + ax], cb = cen[b * dim + ax];
+                       return ca < cb || (ca == cb && a < b);
+                    });
+   rcb(cen, dim, idx, lo, mid, p0, npl, part);
+   rcb(cen, dim, idx, mid, hi, p0 + npl, np - npl, part);
+}
+
+extern "C" int rmh_mesh_partition(const rmh_mesh *m, int nparts, int32_t *part)
+{
+   const Mesh &M = m->m;
+   if (nparts < 1) { set_error("partition: nparts < 1"); return 1; }
+   const int dim = M.dim, npe = M.npe();
+   std::vector<double> cen((size_t)M.ne * dim, 0.0);
+   for (int64_t e = 0; e < M.ne; e++)
+      for (int n = 0; n < npe; n++)
+         for (int a = 0; a < dim; a++) { cen[e * dim + a] += M.X[((size_t)e * npe + n) * dim + a] / npe; }
+   std::vector<int64_t> idx(M.ne);
+   for (int64_t e = 0; e < M.ne; e++) { idx[e] = e; }
+   rcb(cen, dim, idx, 0, M.ne, 0, nparts, part);
+   return 0;
+}
+
+// Halo plan of `rank`: owned elements (ascending global id), ghost ring = elements of other
+// ranks sharing at least a vertex with an owned element, ordered by (owner, global id), and per
+// peer the owned elements that are in the peer's ghost ring (ascending global id).  Vertex
+// adjacency is symmetric, so every rank derives matching send/receive lists without talking.
+struct rmh_halo
+{
+   std::vector<int64_t> owned, ghost, send;         // global element ids
+   std::vector<int32_t> ghost_owner, peers, send_off, recv_off;
+};
+
+extern "C" int rmh_halo_create(const rmh_mesh *m, const int32_t *part, int rank, rmh_halo **out)
+{
+   const Mesh &M = m->m;
+   const int nvx = M.nvert();
+   rmh_halo *h = new rmh_halo;
+   // vertex -> elements CSR
+   std::vector<int64_t> off((size_t)M.nv + 1, 0);
+   for (size_t i = 0; i < M.ev.size(); i++) { off[M.ev[i] + 1]++; }
+   for (int64_t v = 0; v < M.nv; v++) { off[v + 1] += off[v]; }
+   std::vector<int64_t> cur(off.begin(), off.end() - 1), v2e(M.ev.size());
+   for (int64_t e = 0; e < M.ne; e++)
+      for (int c = 0; c < nvx; c++) { v2e[cur[M.ev[e * nvx + c]]++] = e; }
+   std::vector<std::pair<int32_t, int64_t>> gh;      // (owner, ghost element)
+   std::vector<std::pair<int32_t, int64_t>> sd;      // (peer, owned element)
+   for (int64_t e = 0; e < M.ne; e++)
+   {
+      if (part[e] != rank) { continue; }
+      h->owned.push_back(e);
+      for (int c = 0; c < nvx; c++)
+      {
+         const int64_t v = M.ev[e * nvx + c];
+         for (int64_t k = off[v]; k < off[v + 1]; k++)
+         {
+            const int64_t e2 = v2e[k];
+            if (part[e2] != rank)
+            {
+               gh.emplace_back(part[e2], e2);
+               sd.emplace_back(part[e2], e);
+            }
+         }
+      }
+   }
+   std::sort(gh.begin(), gh.end());
+   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
+   std::sort(sd.begin(), sd.end());
+   sd.erase(std::unique(sd.begin(), sd.end()), sd.end());
+   for (auto &g : gh) { h->ghost.push_back(g.second); h->ghost_owner.push_back(g.first); }
+   for (auto &g : gh) { if (h->peers.empty() || h->peers.back() != g.first) { h->peers.push_back(g.first); } }
+   // peers from the send side must coincide (symmetry); build offsets per peer
+   h->send_off.assign(h->peers.size() + 1, 0);
+   h->recv_off.assign(h->peers.size() + 1, 0);
+   for (size_t p = 0; p < h->peers.size(); p++)
+   {
+      int64_t ns = 0, nr = 0;
+      for (auto &x : sd) { if (x.first == h->peers[p]) { ns++; } }
+      for (auto &x : gh) { if (x.first == h->peers[p]) { nr++; } }
+      h->send_off[p + 1] = h->send_off[p] + (int32_t)ns;
+      h->recv_off[p + 1] = h->recv_off[p] + (int32_t)nr;
+   }
+   if ((size_t)h->send_off.back() != sd.size())
+   { set_error("halo: asymmetric adjacency"); delete h; return 1; }
+   for (auto &x : sd) { h->send.push_back(x.second); }
+   *out = h;
+   return 0;
+}
+
+extern "C" int rmh_halo_free(rmh_halo *h) { delete h; return 0; }
+extern "C" int rmh_halo_sizes(const rmh_halo *h, int64_t *n_owned, int64_t *n_ghost, int32_t *n_peers,
+                              int64_t *n_send)
+{
+   *n_owned = (int64_t)h->owned.size(); *n_ghost = (int64_t)h->ghost.size();
+   *n_peers = (int32_t)h->peers.size(); *n_send = (int64_t)h->send.size();
+   return 0;
+}
+// owned / ghost: global element ids; send_local: LOCAL owned index (position in `owned`) of every
+// element to send, concatenated by peer; offsets have n_peers + 1 entries
+extern "C" int rmh_halo_get(const rmh_halo *h, int64_t *owned, int64_t *ghost, int32_t *peers,
+                            int32_t *send_off, int32_t *recv_off, int32_t *send_local)
+{
+   std::copy(h->owned.begin(), h->owned.end(), owned);
+   std::copy(h->ghost.begin(), h->ghost.end(), ghost);
+   std::copy(h->peers.begin(), h->peers.end(), peers);
+   std::copy(h->send_off.begin(), h->send_off.end(), send_off);
+   std::copy(h->recv_off.begin(), h->recv_off.end(), recv_off);
+   for (size_t i = 0; i < h->send.size(); i++)
+   {
+      send_local[i] = (int32_t)(std::lower_bound(h->owned.begin(), h->owned.end(), h->send[i]) -
+                                h->owned.begin());
+   }
    return 0;
 }
 

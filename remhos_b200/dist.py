@@ -1,0 +1,123 @@
+"""Domain-decomposed stepping: one process per GPU, torch.distributed (NCCL over NVLink) for the
+face-neighbour halo exchange that replaces ParGridFunction::ExchangeFaceNbrData and the shared-DOF
+min/max reduction of DofInfo.  Scalars (mass, min, max, dt) go through all_reduce.
+
+The exchange itself (`exchange`) only moves torch tensors, so the same code runs under gloo on
+CPU tensors in the tests.
+"""
+import ctypes as C
+import numpy as np
+
+from . import capi
+from .capi import lib, check, _ptr
+from .setup_problem import mesh_eval, velocity, u0 as eval_u0
+
+
+def exchange(dist, plan, send_bufs, recv_bufs, widths):
+    """Point-to-point exchange of per-peer contiguous slices.  send_bufs/recv_bufs: lists of 1-D
+    tensors laid out [n_elements * width]; plan gives peers and element offsets."""
+    if len(plan.peers) == 0:
+        return
+    ops = []
+    for k, peer in enumerate(plan.peers):
+        s0, s1 = int(plan.send_off[k]), int(plan.send_off[k + 1])
+        r0, r1 = int(plan.recv_off[k]), int(plan.recv_off[k + 1])
+        for sb, rb, w in zip(send_bufs, recv_bufs, widths):
+            ops.append(dist.P2POp(dist.isend, sb[s0 * w:s1 * w], int(peer)))
+            ops.append(dist.P2POp(dist.irecv, rb[r0 * w:r1 * w], int(peer)))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+class DistProblem:
+    """Set-up of one rank's share of a run (transport problems; same reference defaults as
+    setup_problem.Problem).  `mesh` is the GLOBAL mesh (geometry order 1 is enough), already
+    refined; every rank builds the same RCB partition and keeps only its part plus a ghost ring."""
+
+    def __init__(self, mesh, rank, world, problem=0, order=3, mesh_order=2, bounds_type=0,
+                 dt=0.005, device=0):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.order = order
+        self.bb_min, self.bb_max = mesh.bounding_box()
+        dim = mesh.dim
+        part = mesh.partition(world)
+        plan = mesh.halo(part, rank)
+        self.plan = plan
+        ids = np.concatenate([plan.owned, plan.ghost])
+        local = mesh.extract(ids)
+        local.set_curvature(mesh_order)
+        no, ng = plan.owned.size, plan.ghost.size
+        maps = local.dof_maps(order)
+        nodes = local.nodes()[:no]
+        if problem >= 10:
+            raise NotImplementedError('distributed remap set-up')
+        nodal_ok = (problem % 20) in (0, 1, 2, 4, 5, 6, 7)
+        if not nodal_ok:
+            raise NotImplementedError('distributed set-up samples the velocity at the nodes')
+        vel_nodes = velocity(problem, nodes, self.bb_min, self.bb_max)
+        own_mesh = local.extract(np.arange(no, dtype=np.int64))
+        lat_pts = np.arange(order + 1) / max(order, 1)
+        xdof = mesh_eval(own_mesh, lat_pts)
+        self.ctx = capi.Context(dim=dim, order=order, mesh_order=mesh_order, exec_mode=0,
+                                bounds_type=bounds_type, nodes=nodes,
+                                nbr_dof=maps['nbr_dof'][:no], lat=maps['lat'], n_ent=maps['n_ent'],
+                                nbr_elem=maps['nbr_elem'][:no], vel_nodes=vel_nodes,
+                                ne_ghost=ng, device=device)
+        self.u0 = eval_u0(problem, xdof, self.bb_min, self.bb_max)
+        self.dt = dt
+        self.bounds_type = bounds_type
+        self.nd = maps['nd']
+        self.n_owned, self.n_ghost = no, ng
+        dev = torch.device('cuda', device)
+        f64 = torch.float64
+        ns = plan.send_local.size
+        self.send_local = torch.tensor(plan.send_local, dtype=torch.int32, device=dev)
+        self.send_u = torch.empty(max(ns, 1) * self.nd, dtype=f64, device=dev)
+        self.send_mm = torch.empty(max(ns, 1) * 2, dtype=f64, device=dev)
+        self.ghost_u = torch.zeros(max(ng, 1) * self.nd, dtype=f64, device=dev)
+        self.ghost_mm = torch.zeros(max(ng, 1) * 2, dtype=f64, device=dev)
+        self.w1 = torch.empty(self.ctx.ndofs, dtype=f64, device=dev)
+        self.w2 = torch.empty(self.ctx.ndofs, dtype=f64, device=dev)
+        self.n_send = ns
+
+    def halo(self, y, stream=0):
+        """pack -> NCCL send/recv -> install the ghosts of y (element min/max of y must already be
+        in the context)."""
+        import torch.distributed as dist
+        self.ctx.halo_pack(y, self.send_local, self.n_send, self.send_u, self.send_mm, stream)
+        if self.world > 1:
+            exchange(dist, self.plan, [self.send_u, self.send_mm], [self.ghost_u, self.ghost_mm],
+                     [self.nd, 2])
+        self.ctx.halo_set(self.ghost_u, self.ghost_mm, stream)
+
+    def rk3_step(self, t, u, stream=0):
+        """RK3-SSP step (remhos.cpp:490) on the decomposed mesh: three fused stage launches, each
+        preceded by one halo exchange."""
+        ctx, dt = self.ctx, self.dt
+        chain = self.bounds_type == 0     # stage kernel leaves min/max of its output in the context
+        ctx.stage_minmax(u, stream)
+        self.halo(u, stream)
+        ctx.rk_stage_dist(5, dt, 0.0, 1.0, u, u, self.w1, stream)
+        if not chain:
+            ctx.stage_minmax(self.w1, stream)
+        self.halo(self.w1, stream)
+        ctx.rk_stage_dist(5, dt, 0.75, 0.25, u, self.w1, self.w2, stream)
+        if not chain:
+            ctx.stage_minmax(self.w2, stream)
+        self.halo(self.w2, stream)
+        ctx.rk_stage_dist(5, dt, 1.0 / 3.0, 2.0 / 3.0, u, self.w2, u, stream)
+        return t + dt
+
+    def allreduce(self, value, op='sum'):
+        import torch.distributed as dist
+        if self.world == 1:
+            return value
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.w1.device)
+        dist.all_reduce(t, op={'sum': dist.ReduceOp.SUM, 'min': dist.ReduceOp.MIN,
+                               'max': dist.ReduceOp.MAX}[op])
+        return float(t[0])
+
+    def close(self):
+        self.ctx.close()
