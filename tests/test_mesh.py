@@ -1,0 +1,92 @@
+"""Host mesh module (C++) against the oracle's mesh code: bit-exact integer maps
+(BdrDofs, NbrDof, Sub2Ind, neighbour elements, overlap-bounds entity partition) and nodes."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import DATA
+import remhos_b200 as rb
+from remhos_oracle import mesh as om, dg
+
+CASES = [('periodic-square.mesh', 2, 3), ('periodic-square.mesh', 1, 1), ('inline-quad.mesh', 2, 2),
+         ('inline-quad.mesh', 1, 4), ('cube01_hex.mesh', 1, 2), ('cube01_hex.mesh', 2, 3),
+         ('periodic-cube.mesh', 1, 3), ('periodic-cube.mesh', 0, 4), ('periodic-cube.mesh', 1, 1)]
+
+
+@pytest.mark.parametrize('mesh,rs,p', CASES)
+def test_index_maps_bit_exact(mesh, rs, p):
+    m = om.read_mesh(os.path.join(DATA, mesh))
+    for _ in range(rs):
+        m = om.refine_uniform(m)
+    m = om.set_curvature(m, 2)
+    topo = om.Topology(m)
+    pm = rb.Mesh.load(os.path.join(DATA, mesh)).refine(rs).set_curvature(2)
+    maps = pm.dof_maps(p)
+    assert pm.ne == m.ne and pm.dim == m.dim
+    assert np.abs(pm.nodes() - m.X).max() < 1e-15
+    assert np.array_equal(maps['bdr_dofs'], dg.bdr_dofs(p, m.dim))
+    assert np.array_equal(maps['nbr_dof'], dg.nbr_dof_map(topo, p))
+    assert np.array_equal(maps['nbr_elem'], topo.nbr_elem)
+    if p > 1:
+        assert np.array_equal(maps['sub2ind'], dg.sub2ind(p, m.dim))
+    # same partition of (element, lattice position) pairs into shared entities
+    a = maps['lat'].reshape(-1); b = topo.lat.reshape(-1)
+    pairs = np.unique(np.stack([a, b], 1), axis=0)
+    assert len(pairs) == len(np.unique(a)) == len(np.unique(b))
+    assert maps['n_ent'] >= a.max() + 1
+
+
+def test_nbr_dof_is_an_involution_and_matches_geometry():
+    """NbrDof(NbrDof) = identity on interior faces, and matched DOFs coincide physically."""
+    pm = rb.Mesh.load(os.path.join(DATA, 'cube01_hex.mesh')).refine(1).set_curvature(2)
+    p = 3
+    maps = pm.dof_maps(p)
+    from remhos_b200.setup_problem import mesh_eval
+    x = mesh_eval(pm, np.arange(p + 1) / p).reshape(-1, 3)
+    bd, nb = maps['bdr_dofs'], maps['nbr_dof']
+    nd = maps['nd']
+    ne, nf, nfd = nb.shape
+    own = (np.arange(ne)[:, None, None] * nd + bd.T[None, :, :])
+    inner = nb >= 0
+    assert np.abs(x[own[inner]] - x[nb[inner]]).max() < 1e-14
+    lut = -np.ones(ne * nd * nf, dtype=np.int64)
+    # map (global dof, face) -> neighbour dof, then apply twice
+    back = {}
+    for e in range(ne):
+        for f in range(nf):
+            for j in range(nfd):
+                if nb[e, f, j] >= 0:
+                    back[(own[e, f, j], nb[e, f, j] // nd)] = nb[e, f, j]
+    for (g, ne2), g2 in back.items():
+        assert back[(g2, g // nd)] == g
+
+
+def test_cartesian_generator_and_refinement_counts():
+    m = rb.Mesh.cartesian([3, 3, 3], [2.0] * 3, origin=[-1.0] * 3, periodic=True).refine(2)
+    assert m.ne == 27 * 64
+    lo, hi = m.bounding_box()
+    assert np.allclose(lo, -1) and np.allclose(hi, 1)
+    maps = m.dof_maps(2)
+    assert (maps['nbr_dof'] >= 0).all()          # periodic: no domain boundary
+    m2 = rb.Mesh.cartesian([4, 2], [1.0, 1.0])
+    maps2 = m2.dof_maps(1)
+    assert (maps2['nbr_elem'] < 0).sum() == 2 * (4 + 2)
+
+
+def test_problem_functions_match_oracle():
+    from remhos_oracle import problems
+    from remhos_b200.setup_problem import velocity, u0
+    rng = np.random.default_rng(3)
+    for dim in (2, 3):
+        x = rng.uniform(-1, 1, size=(500, dim))
+        lo, hi = -np.ones(dim), np.ones(dim)
+        for prob in (0, 1, 3, 4, 5, 6, 7, 10, 11, 14):
+            if prob == 11 and dim == 3:
+                continue
+            assert np.allclose(velocity(prob, x, lo, hi), problems.velocity(prob, x, lo, hi),
+                               rtol=0, atol=1e-15)
+        for prob in (0, 1, 2, 3, 4, 5, 6, 7):
+            if prob in (2, 3, 4) and dim == 3:
+                continue
+            assert np.allclose(u0(prob, x, lo, hi), problems.u0(prob, x, lo, hi), rtol=0, atol=2e-15)
