@@ -40,7 +40,9 @@ def read_peaks():
 
 
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+    """nvidia-smi sampled every 50 ms from before the warm-up to the end of the e2e loop; the
+    reported clocks are the samples whose timestamp falls inside [t0, t1] (the timed regions)."""
+    Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -52,12 +54,13 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
         if self.p is None:
             return out
@@ -68,22 +71,28 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, reasons = [], [], set()
+        sm, sm_all, smax, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in self.f:
             c = [x.strip() for x in line.split(',')]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); smax.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                clk, cmax = float(c[2]), float(c[3])
             except ValueError:
                 continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        if sm:
-            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)),
-                   'reasons': sorted(reasons), 'samples': len(sm)}
+            sm_all.append(clk); smax.append(cmax)
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                for n, v in zip(names, c[6:10]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+        if sm_all:
+            use = sm if sm else sm_all
+            out = {'sm_mhz': float(np.median(use)), 'sm_max_mhz': float(max(smax)),
+                   'reasons': sorted(reasons), 'samples': len(sm),
+                   'window': 'timed + e2e loops' if sm else 'whole run (no sample inside the timed window)'}
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -125,7 +134,7 @@ def cpu_baseline(order, seconds=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--rs', type=int, default=5)
@@ -215,14 +224,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     t = 0.0
     for _ in range(a.warmup):
         t = step(t, u, stream)
     barrier()
     rb.launch_count(reset=True)
     ctx.profile(1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_wall0 = time.time()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -231,7 +241,6 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
     launches = rb.launch_count(reset=True)
     kms, klaunch = ctx.profile(0)
     mass1 = gsum(ctx.reduce(0, u, m))
@@ -257,6 +266,7 @@ def main():
         step_host(t)
     barrier()
     e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop(t_wall0, time.time())
 
     tmax = torch.tensor([ms, e_ms], dtype=torch.float64, device='cuda')
     if world > 1:

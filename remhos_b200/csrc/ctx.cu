@@ -4,11 +4,13 @@
 #include "common.hpp"
 #include "kernels.cuh"
 #include "stage3d.cuh"
+#include "stage3p.cuh"
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -59,12 +61,16 @@ struct rmh_ctx
    // face neighbours
    int32_t *nbr_elem = nullptr;
    uint8_t *nbr_pat = nullptr;
+   int32_t *nbr_pat32 = nullptr;   // same ids, cp.async granularity (pipelined stage kernel)
    int16_t *pat = nullptr;
    int npat = 0;
    // bounds
    int32_t *lat = nullptr, *ent_off = nullptr, *ent_el = nullptr, *bnbr = nullptr;
    int32_t n_ent = 0;
-   double *ent_min = nullptr, *ent_max = nullptr, *xe_min = nullptr, *xe_max = nullptr;
+   double *ent_mm = nullptr;   // [n_ent][2] (min, max) over the elements sharing the entity
+   double *xe_min = nullptr, *xe_max = nullptr;
+   int num_sms = 0;
+   bool pipelined = true;      // RMH_NO_PIPELINE=1 selects the one-batch-per-block stage kernel
    bool xe_valid = false;
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    // halo
@@ -471,7 +477,7 @@ struct StageArgs
    int out_mode;
    int bounds_type, dim_n3;
    const int32_t *lat;        // [NE][3^dim]
-   const double *ent_min, *ent_max;
+   const double *ent_mm;      // [n_ent][2]
    const int32_t *bnbr;       // [NE][NF] (bounds_type 1)
    const double *xe_min, *xe_max;
    double *xe_min_out, *xe_max_out;   // may be NULL
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(KCfg<DIM, D1, Q, E>::T, KCfg<DIM, D1, Q, E>::M
             if (a.bounds_type == 0)
             {
                const int ent = a.lat[ge * N3 + lattice_class(DIM, D1, j)];
-               bmn[k] = a.ent_min[ent]; bmx[k] = a.ent_max[ent];
+               bmn[k] = a.ent_mm[2 * ent]; bmx[k] = a.ent_mm[2 * ent + 1];
             }
          }
       }
@@ -644,8 +650,7 @@ __global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_m
 
 // entity min/max over the elements sharing the entity (CG-dof overlap, remhos_tools.cpp:449-458)
 __global__ void k_ent_min_max(int32_t n_ent, const int32_t *off, const int32_t *el,
-                              const double *xe_min, const double *xe_max, double *ent_min,
-                              double *ent_max)
+                              const double *xe_min, const double *xe_max, double *ent_mm)
 {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n_ent) { return; }
@@ -654,20 +659,19 @@ __global__ void k_ent_min_max(int32_t n_ent, const int32_t *off, const int32_t *
    {
       mn = fmin(mn, xe_min[el[k]]); mx = fmax(mx, xe_max[el[k]]);
    }
-   ent_min[i] = mn; ent_max[i] = mx;
+   ent_mm[2 * i] = mn; ent_mm[2 * i + 1] = mx;
 }
 
 // per-DOF gather (remhos_tools.cpp:468-494)
 __global__ void k_bounds_overlap(int64_t ne, int dim, int D1, int nd, int n3, const int32_t *lat,
-                                 const double *ent_min, const double *ent_max, double *xi_min,
-                                 double *xi_max)
+                                 const double *ent_mm, double *xi_min, double *xi_max)
 {
    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (idx >= ne * nd) { return; }
    const int64_t e = idx / nd;
    const int i = (int)(idx - e * nd);
    const int ent = lat[e * n3 + lattice_class(dim, D1, i)];
-   xi_min[idx] = ent_min[ent]; xi_max[idx] = ent_max[ent];
+   xi_min[idx] = ent_mm[2 * ent]; xi_max[idx] = ent_mm[2 * ent + 1];
 }
 
 // ComputeMatrixSparsityBounds (remhos_tools.cpp:381-430)
@@ -900,6 +904,75 @@ static int dispatch_stage(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
    RMH_DISPATCH(launch_stage, c, a, s);
 }
 
+// ---- persistent pipelined stage kernel (3D, every element affine): stage3p.cuh
+template <int D1, int Q>
+static Tab<D1, Q> make_tab(const rmh_ctx *c)
+{
+   Tab<D1, Q> tab;
+   for (int q = 0; q < Q; q++)
+      for (int i = 0; i < D1; i++) { tab.B[q][i] = c->hB[q * D1 + i]; tab.G[q][i] = c->hG[q * D1 + i]; }
+   for (int i = 0; i < D1; i++)
+      for (int j = 0; j < D1; j++) { tab.Minv[i][j] = c->hMinv[i * D1 + j]; }
+   for (int i = 0; i < D1; i++)
+      for (int q = 0; q < Q; q++)
+      {
+         double v = 0.0;
+         for (int j = 0; j < D1; j++) { v += c->hMinv[i * D1 + j] * c->hB[q * D1 + j]; }
+         tab.C[i][q] = v;
+      }
+   return tab;
+}
+
+template <int D1, int Q, int E>
+static int launch_stagep_E(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   using S = SmemP<D1, Q, E>;
+   constexpr int MINB0 = (int)((227 * 1024) / (S::BYTES + 1024));
+   constexpr int MINB = MINB0 < 1 ? 1 : (MINB0 > 3 ? 3 : MINB0);
+   static int blocks_per_sm = 0;
+   if (blocks_per_sm == 0)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_stage3p<D1, Q, E, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)S::BYTES));
+      int nb = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3p<D1, Q, E, MINB>, S::T, S::BYTES));
+      if (nb < 1) { set_error("k_stage3p does not fit on an SM"); return 1; }
+      blocks_per_sm = nb;
+   }
+   const int64_t nbatch = (a.ne + E - 1) / E;
+   const int64_t grid = std::min<int64_t>(nbatch, (int64_t)blocks_per_sm * c->num_sms);
+   k_stage3p<D1, Q, E, MINB><<<(unsigned)grid, S::T, S::BYTES, s>>>(a, make_tab<D1, Q>(c));
+   LAUNCH_OK();
+   return 0;
+}
+
+template <int DIM, int D1, int Q>
+static int launch_stagep(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   if constexpr (DIM == 3)
+   {
+      constexpr size_t LIM = 112 * 1024;
+      static int force_e = -1;
+      if (force_e < 0) { const char *ev = getenv("RMH_PIPE_E"); force_e = ev ? atoi(ev) : 0; }
+      // 4 elements per block: three resident blocks per SM at order 3 and no register spills
+      // (15 warps per SM leave 128 registers per thread); RMH_PIPE_E=8 selects the larger batch
+      if (force_e != 8) { return launch_stagep_E<D1, Q, 4>(c, a, s); }
+      if constexpr (SmemP<D1, Q, 8>::BYTES <= LIM) { return launch_stagep_E<D1, Q, 8>(c, a, s); }
+      else if constexpr (SmemP<D1, Q, 4>::BYTES <= LIM) { return launch_stagep_E<D1, Q, 4>(c, a, s); }
+      else { return launch_stagep_E<D1, Q, 2>(c, a, s); }
+   }
+   else
+   {
+      set_error("pipelined stage kernel is 3D only");
+      return 1;
+   }
+}
+
+static int dispatch_stagep(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   RMH_DISPATCH(launch_stagep, c, a, s);
+}
+
 static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
 {
    GeomArgs g;
@@ -970,6 +1043,13 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    c->NG1 = c->mo + 1; c->NGN = ipow(c->NG1, c->dim); c->N3 = ipow(3, c->dim);
    c->ne = d->ne; c->ne_ghost = d->ne_ghost; c->N = c->ne * c->ND;
    c->t_cur = 0.0;
+   {
+      cudaDeviceProp prop;
+      CUDA_OK(cudaGetDeviceProperties(&prop, d->device));
+      c->num_sms = prop.multiProcessorCount;
+      const char *np = getenv("RMH_NO_PIPELINE");
+      c->pipelined = !(np && np[0] == '1');
+   }
    auto fail = [&]() { rmh_ctx_destroy(c); return 1; };
    if ((double)(c->ne + c->ne_ghost) * c->ND >= 2147483647.0)
    { set_error("too many DOFs for int32 index maps"); return fail(); }
@@ -1073,6 +1153,10 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       if (patv.empty()) { patv.assign(NFD, 0); }
       if (dev_upload(c, &c->nbr_elem, ne_h.data(), ne_h.size())) { return fail(); }
       if (dev_upload(c, &c->nbr_pat, pid_h.data(), pid_h.size())) { return fail(); }
+      {
+         std::vector<int32_t> pid32(pid_h.begin(), pid_h.end());
+         if (dev_upload(c, &c->nbr_pat32, pid32.data(), pid32.size())) { return fail(); }
+      }
       if (dev_upload(c, &c->pat, patv.data(), patv.size())) { return fail(); }
    }
    // ---- bounds structures
@@ -1097,8 +1181,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       if (dev_upload(c, &c->lat, d->lat, nl)) { return fail(); }
       if (dev_upload(c, &c->ent_off, off.data(), off.size())) { return fail(); }
       if (dev_upload(c, &c->ent_el, el.data(), el.size())) { return fail(); }
-      if (dev_alloc(c, &c->ent_min, (size_t)c->n_ent)) { return fail(); }
-      if (dev_alloc(c, &c->ent_max, (size_t)c->n_ent)) { return fail(); }
+      if (dev_alloc(c, &c->ent_mm, 2 * (size_t)c->n_ent)) { return fail(); }
    }
    else
    {
@@ -1203,10 +1286,10 @@ extern "C" int rmh_bounds(rmh_ctx *c, const double *xe_min, const double *xe_max
    if (c->bounds_type == 0)
    {
       k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, c->ent_off, c->ent_el, xe_min,
-                                                            xe_max, c->ent_min, c->ent_max);
+                                                            xe_max, c->ent_mm);
       LAUNCH_OK();
       k_bounds_overlap<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(
-         c->ne, c->dim, c->D1, c->ND, c->N3, c->lat, c->ent_min, c->ent_max, xi_min, xi_max);
+         c->ne, c->dim, c->D1, c->ND, c->N3, c->lat, c->ent_mm, xi_min, xi_max);
       LAUNCH_OK();
    }
    else
@@ -1274,19 +1357,36 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    if (c->bounds_type == 0)
    {
       k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, c->ent_off, c->ent_el, c->xe_min,
-                                                            c->xe_max, c->ent_min, c->ent_max);
+                                                            c->xe_max, c->ent_mm);
       LAUNCH_OK();
    }
    StageArgs sa;
    sa.ho = ho_args(c, y, nullptr, 3);
    sa.ml = c->ml; sa.x0 = x0; sa.out = out; sa.a = a; sa.b = b; sa.dt = dt; sa.out_mode = out_mode;
    sa.bounds_type = c->bounds_type; sa.dim_n3 = c->N3; sa.lat = c->lat;
-   sa.ent_min = c->ent_min; sa.ent_max = c->ent_max; sa.bnbr = c->bnbr;
+   sa.ent_mm = c->ent_mm; sa.bnbr = c->bnbr;
    sa.xe_min = c->xe_min; sa.xe_max = c->xe_max;
    // the next stage's element min/max must not overwrite the ones this launch still reads
    // (bounds_type 1 reads neighbours' xe during the kernel) -> double buffer
    sa.xe_min_out = nullptr; sa.xe_max_out = nullptr;
    if (write_xe && c->bounds_type == 0) { sa.xe_min_out = c->xe_min; sa.xe_max_out = c->xe_max; }
+   // 3D meshes with constant-Jacobian elements: persistent pipelined kernel
+   const bool use_p = c->pipelined && c->dim == 3 && c->all_affine &&
+                      ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
+   StagePArgs pa;
+   if (use_p)
+   {
+      pa.ne = c->ne; pa.y = y; pa.x0 = x0; pa.out = out;
+      pa.Dvol = c->Dvol; pa.Dface = c->Dface; pa.einv = c->einv;
+      pa.fn = sa.ho.fn; pa.npat = c->npat; pa.nbr_pat32 = c->nbr_pat32;
+      pa.a = a; pa.b = b; pa.dt = dt; pa.out_mode = out_mode;
+      pa.has_x0 = (out_mode == 1 && a != 0.0) ? 1 : 0;
+      pa.bounds_type = c->bounds_type;
+      pa.bidx = (c->bounds_type == 0) ? c->lat : c->bnbr;
+      pa.ent_mm = c->ent_mm; pa.xe_min = c->xe_min; pa.xe_max = c->xe_max;
+      pa.xe_min_out = sa.xe_min_out; pa.xe_max_out = sa.xe_max_out;
+   }
+   auto run = [&]() { return use_p ? dispatch_stagep(c, pa, s) : dispatch_stage(c, sa, s); };
    if (c->prof)
    {
       if (c->prof_used + 2 > c->prof_ev.size())
@@ -1299,12 +1399,12 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
          }
       }
       CUDA_OK(cudaEventRecord(c->prof_ev[c->prof_used], s));
-      const int rc = dispatch_stage(c, sa, s);
+      const int rc = run();
       CUDA_OK(cudaEventRecord(c->prof_ev[c->prof_used + 1], s));
       c->prof_used += 2;
       return rc;
    }
-   return dispatch_stage(c, sa, s);
+   return run();
 }
 
 extern "C" int rmh_profile(rmh_ctx *c, int enable, double *total_ms, int64_t *launches)

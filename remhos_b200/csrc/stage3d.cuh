@@ -79,9 +79,9 @@ struct Pre3
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
-         d0[q] = live ? dp[q * QQ] : 0.0;
-         d1[q] = live ? dp[NQ + q * QQ] : 0.0;
-         d2[q] = live ? dp[2 * NQ + q * QQ] : 0.0;
+         d0[q] = live ? __ldcs(dp + q * QQ) : 0.0;
+         d1[q] = live ? __ldcs(dp + NQ + q * QQ) : 0.0;
+         d2[q] = live ? __ldcs(dp + 2 * NQ + q * QQ) : 0.0;
       }
 #pragma unroll
       for (int k = 0; k < K2; k++)
@@ -90,7 +90,7 @@ struct Pre3
          const int e = id / (NF * Q), r = id - e * (NF * Q);
          const bool lv = (id < E * NF * Q) && (e < ne);
 #pragma unroll
-         for (int q = 0; q < Q; q++) { df[k][q] = lv ? Dface[(size_t)e * NF * QQ + q * NF * Q + r] : 0.0; }
+         for (int q = 0; q < Q; q++) { df[k][q] = lv ? __ldcs(Dface + (size_t)e * NF * QQ + q * NF * Q + r) : 0.0; }
       }
    }
 };

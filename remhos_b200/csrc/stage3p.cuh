@@ -1,0 +1,554 @@
+// Persistent, software-pipelined RK-stage kernel for 3D hexahedral meshes whose elements all have
+// a constant Jacobian determinant (sm_100a, FP64).
+//
+// One block owns a static round-robin list of element batches (E elements each).  While batch b
+// is computed, every HBM stream of batch b+G except the stored quadrature data is already in
+// flight into the second shared-memory stage (cp.async, no registers held):
+//
+//   data stage   U   [E][ND]        stage input y of the batch            (16-byte cp.async)
+//                X0  [E][ND]        RK base state                         (16-byte cp.async)
+//                NB  [E][NF][NFD]   neighbour traces of y, gathered through the
+//                                   (neighbour element, orientation pattern) map (8-byte cp.async)
+//                BND [E][27][2]     (min,max) of the lattice entities / neighbours the per-DOF
+//                                   bounds are gathered from             (16/8-byte cp.async)
+//   index stage  neighbour element + pattern per face, bounds ids; loaded one batch further ahead
+//                so that the gather addresses of the data stage never wait on HBM.
+//
+// The stored quadrature data (3 Q^3 + 6 Q^2 doubles per element, the dominant HBM stream) goes
+// straight into registers at the top of the batch with streaming (evict-first) loads and is
+// consumed two barrier intervals later.
+//
+// The contraction phases are the ones of ho3_affine (stage3d.cuh): mass inverse folded into the
+// back-contractions, face and volume work sharing barrier intervals.
+#ifndef RMH_STAGE3P_CUH
+#define RMH_STAGE3P_CUH
+
+#include "stage3d.cuh"
+
+namespace rmh
+{
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *g)
+{
+   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *g)
+{
+   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *g)
+{
+   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int D1, int Q, int E>
+struct SmemP
+{
+   static constexpr int ND = D1 * D1 * D1, NQ = Q * Q * Q, QQ = Q * Q;
+   static constexpr int NF = 6, NFD = D1 * D1, N3 = 27;
+   static constexpr int TPE = QQ > 32 ? QQ : 32;            // threads per element
+   static constexpr int T = ((TPE * E + 31) / 32) * 32;     // block size (>= 32*E and >= QQ*E)
+   static constexpr int NL = E * D1 * D1, NY = E * D1 * Q, NT1 = E * NF * D1, NT2 = E * NF * Q;
+   // ---- one data stage (doubles)
+   static constexpr int P_U = 0;
+   static constexpr int P_X = P_U + E * ND;
+   static constexpr int P_N = P_X + E * ND;
+   static constexpr int P_B = P_N + E * NF * NFD;
+   static constexpr int P_E = P_B + E * N3 * 2;                  // 1/volume per element
+   static constexpr int PSZ = ((P_E + E) + 1) & ~1;
+   // ---- work arrays (doubles)
+   static constexpr int SZ_C0 = 2 * NL * Q;                       // BU | GU
+   static constexpr int SZ_C1 = NL * Q + E * NF * NFD;            // S2 | face results
+   static constexpr int SZ_C = SZ_C0 > SZ_C1 ? SZ_C0 : SZ_C1;
+   static constexpr int SZ_B = 3 * E * D1 * QQ;                   // GB | BG | BB per element
+   static constexpr int SZ_G0 = E * NF * D1 * Q;                  // F1
+   static constexpr int SZ_G = SZ_G0 > E * ND ? SZ_G0 : E * ND;   // ... later X
+   static constexpr int OFF_D = 0;                                // two data stages
+   static constexpr int OFF_C = OFF_D + 2 * PSZ;
+   static constexpr int OFF_B = OFF_C + SZ_C;
+   static constexpr int OFF_G = OFF_B + SZ_B;
+   static constexpr int NDBL = OFF_G + SZ_G;
+   // ---- ints behind the doubles: two index stages + the pattern table
+   static constexpr int I_NE = 0, I_NP = E * NF, I_BI = 2 * E * NF, ISZ = 2 * E * NF + E * N3;
+   static constexpr int PATMAX = 64;                              // patterns kept in shared memory
+   static constexpr int NINT = 2 * ISZ + (PATMAX * NFD + 1) / 2;
+   static constexpr size_t BYTES = (size_t)NDBL * 8 + (size_t)NINT * 4;
+};
+
+struct StagePArgs
+{
+   int64_t ne;                // owned elements
+   const double *y;           // stage input
+   const double *x0;          // RK base state (may alias y or out)
+   double *out;
+   const double *Dvol, *Dface, *einv;
+   FaceNbr fn;
+   int npat;
+   const int32_t *nbr_pat32;  // [NE][NF] pattern ids as int32 (cp.async granularity)
+   double a, b, dt;
+   int out_mode, has_x0;
+   int bounds_type;           // 0: bidx = lat [NE][27] -> ent_mm; 1: bidx = bnbr [NE][NF] -> xe_min/xe_max
+   const int32_t *bidx;
+   const double *ent_mm;      // [n_ent][2]
+   const double *xe_min, *xe_max;
+   double *xe_min_out, *xe_max_out;
+};
+
+template <int D1, int Q, int E>
+__device__ __forceinline__ void stagep_fetch_idx(const StagePArgs &a, int *ix, int64_t e0, int ne)
+{
+   using S = SmemP<D1, Q, E>;
+   constexpr int NF = S::NF, T = S::T, N3 = S::N3;
+   for (int id = threadIdx.x; id < E * NF; id += T)
+   {
+      if (id < ne * NF)
+      {
+         cp_async4(ix + S::I_NE + id, a.fn.nbr_elem + e0 * NF + id);
+         cp_async4(ix + S::I_NP + id, a.nbr_pat32 + e0 * NF + id);
+      }
+   }
+   if (a.bounds_type == 0)
+   {
+      for (int id = threadIdx.x; id < E * N3; id += T)
+      {
+         if (id < ne * N3) { cp_async4(ix + S::I_BI + id, a.bidx + e0 * N3 + id); }
+      }
+   }
+   else
+   {
+      for (int id = threadIdx.x; id < E * NF; id += T)
+      {
+         if (id < ne * NF) { cp_async4(ix + S::I_BI + id, a.bidx + e0 * NF + id); }
+      }
+   }
+}
+
+template <int D1, int Q, int E>
+__device__ __forceinline__ void stagep_fetch_data(const StagePArgs &a, double *dst, const int *ix,
+                                                  const int16_t *spat, int64_t e0, int ne)
+{
+   using S = SmemP<D1, Q, E>;
+   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, T = S::T, N3 = S::N3;
+   // contiguous DOF blocks, 16-byte chunks
+   {
+      const double *gu = a.y + e0 * ND, *gx = a.x0 + e0 * ND;
+      double *U = dst + S::P_U, *X = dst + S::P_X;
+      for (int c = threadIdx.x; c < E * ND / 2; c += T)
+      {
+         if (2 * c + 1 < ne * ND)
+         {
+            cp_async16(U + 2 * c, gu + 2 * c);
+            if (a.has_x0) { cp_async16(X + 2 * c, gx + 2 * c); }
+         }
+         else
+         {
+            // tail of a partial batch (ne*ND may be odd): element-wise
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+               const int i = 2 * c + h;
+               const bool in = i < ne * ND;
+               U[i] = in ? gu[i] : 0.0;
+               X[i] = (in && a.has_x0) ? gx[i] : 0.0;
+            }
+         }
+      }
+   }
+   // neighbour traces
+   {
+      double *NB = dst + S::P_N;
+      const int *NE_ = ix + S::I_NE, *NP_ = ix + S::I_NP;
+      for (int id = threadIdx.x; id < E * NF * NFD; id += T)
+      {
+         const int ef = id / NFD, j = id - ef * NFD;
+         const int nb = (ef < ne * NF) ? NE_[ef] : -1;
+         if (nb >= 0)
+         {
+            const int pid = NP_[ef];
+            const int loc = (pid < S::PATMAX) ? spat[pid * NFD + j] : a.fn.pat[pid * NFD + j];
+            const double *src = (nb < a.fn.ne_owned)
+                                   ? a.y + (int64_t)nb * ND + loc
+                                   : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * ND + loc;
+            cp_async8(NB + id, src);
+         }
+         else { NB[id] = 0.0; }
+      }
+   }
+   for (int e = threadIdx.x; e < E; e += T)
+   {
+      if (e < ne) { cp_async8(dst + S::P_E + e, a.einv + e0 + e); }
+      else { dst[S::P_E + e] = 0.0; }
+   }
+   // bounds sources
+   {
+      double *BD = dst + S::P_B;
+      const int *BI = ix + S::I_BI;
+      if (a.bounds_type == 0)
+      {
+         for (int id = threadIdx.x; id < E * N3; id += T)
+         {
+            if (id < ne * N3) { cp_async16(BD + 2 * id, a.ent_mm + 2 * (int64_t)BI[id]); }
+         }
+      }
+      else
+      {
+         // slot k < NF: face neighbour k, slot NF: the element itself
+         for (int id = threadIdx.x; id < E * (NF + 1); id += T)
+         {
+            const int e = id / (NF + 1), k = id - e * (NF + 1);
+            if (e < ne)
+            {
+               const int64_t src = (k == NF) ? (e0 + e) : (int64_t)BI[e * NF + k];
+               double *d = BD + 2 * (e * N3 + k);
+               if (src >= 0) { cp_async8(d, a.xe_min + src); cp_async8(d + 1, a.xe_max + src); }
+               else { d[0] = INFINITY; d[1] = -INFINITY; }
+            }
+         }
+      }
+   }
+}
+
+template <int D1, int Q, int E, int MINB>
+__global__ void __launch_bounds__(SmemP<D1, Q, E>::T, MINB)
+k_stage3p(StagePArgs a, const Tab<D1, Q> tab)
+{
+   using S = SmemP<D1, Q, E>;
+   using P3 = Smem3<D1, Q, E>;
+   constexpr int ND = S::ND, NQ = S::NQ, QQ = S::QQ, NF = S::NF, NFD = S::NFD, T = S::T, N3 = S::N3;
+   constexpr int NL = S::NL, NY = S::NY, NT1 = S::NT1, NT2 = S::NT2;
+   constexpr int K2 = (NT2 + T - 1) / T;
+   constexpr int NK = (ND + 31) / 32;
+   static_assert(P3::T == T, "block shapes of stage3d and stage3p must agree (Pre3)");
+   extern __shared__ double sm[];
+   int *ismem = reinterpret_cast<int *>(sm + S::NDBL);
+   int16_t *spat = reinterpret_cast<int16_t *>(ismem + 2 * S::ISZ);
+   const int64_t nbatch = (a.ne + E - 1) / E;
+   const int G = gridDim.x;
+   auto mB = [&](int o, int i) { return tab.B[o][i]; };
+   auto mG = [&](int o, int i) { return tab.G[o][i]; };
+   auto mC = [&](int o, int i) { return tab.C[o][i]; };
+   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const double inv_dt = 1.0 / a.dt;
+   // lattice class of this lane's DOFs (bounds_type 0)
+   int cls[NK];
+#pragma unroll
+   for (int k = 0; k < NK; k++)
+   {
+      int j = lane + 32 * k, t = 0, mul = 1;
+      if (j >= ND) { j = 0; }
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++)
+      {
+         const int l = j % D1; j /= D1;
+         t += ((l == 0) ? 0 : ((l == D1 - 1) ? 2 : 1)) * mul; mul *= 3;
+      }
+      cls[k] = t;
+   }
+   // ---- prologue: pattern table, indices of the first two batches, data of the first
+   {
+      const int np = a.npat < S::PATMAX ? a.npat : S::PATMAX;
+      for (int i = threadIdx.x; i < np * NFD; i += T) { spat[i] = a.fn.pat[i]; }
+   }
+   int64_t b = blockIdx.x;
+   if (b >= nbatch) { return; }
+   {
+      const int64_t e0 = b * E;
+      stagep_fetch_idx<D1, Q, E>(a, ismem, e0, (int)min((int64_t)E, a.ne - e0));
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
+      stagep_fetch_data<D1, Q, E>(a, sm + S::OFF_D, ismem, spat, e0, (int)min((int64_t)E, a.ne - e0));
+      const int64_t b1 = b + G;
+      if (b1 < nbatch)
+      {
+         const int64_t e1 = b1 * E;
+         stagep_fetch_idx<D1, Q, E>(a, ismem + S::ISZ, e1, (int)min((int64_t)E, a.ne - e1));
+      }
+      cp_async_commit();
+   }
+   for (int it = 0; b < nbatch; b += G, it++)
+   {
+      const int s = it & 1;
+      const int64_t e0 = b * E;
+      const int ne = (int)min((int64_t)E, a.ne - e0);
+      double *dat = sm + S::OFF_D + s * S::PSZ;
+      const double *U = dat + S::P_U, *NB = dat + S::P_N;
+      cp_async_wait_all();
+      __syncthreads();   // data(b), idx(b+G) landed; previous batch fully consumed
+      // ---- stored quadrature data of this batch -> registers (streaming)
+      Pre3<D1, Q, E> pre;
+      pre.load(a.Dvol + (size_t)e0 * 3 * NQ, a.Dface + (size_t)e0 * NF * QQ, ne);
+      // ---- prefetch: data(b+G) through idx(b+G); idx(b+2G)
+      {
+         const int64_t b1 = b + G, b2 = b + 2 * (int64_t)G;
+         if (b1 < nbatch)
+         {
+            const int64_t e1 = b1 * E;
+            stagep_fetch_data<D1, Q, E>(a, sm + S::OFF_D + (s ^ 1) * S::PSZ, ismem + (s ^ 1) * S::ISZ,
+                                        spat, e1, (int)min((int64_t)E, a.ne - e1));
+         }
+         if (b2 < nbatch)
+         {
+            const int64_t e2 = b2 * E;
+            stagep_fetch_idx<D1, Q, E>(a, ismem + s * S::ISZ, e2, (int)min((int64_t)E, a.ne - e2));
+         }
+         cp_async_commit();
+      }
+      double *BU = sm + S::OFF_C, *GU = BU + NL * Q;
+      double *GB = sm + S::OFF_B;
+      double *F1 = sm + S::OFF_G;
+      double *FD = sm + S::OFF_C + NL * Q;     // face results (phase C on; GU is dead by then)
+      double *X = sm + S::OFF_G;               // HO result (phase E; F1 is dead by then)
+      // ---- A: fwd-x tasks (arr, e, z, y)  |  face tasks (e, f, jb): contract ja -> qa
+      for (int id = threadIdx.x; id < 2 * NL + NT1; id += T)
+      {
+         if (id < 2 * NL)
+         {
+            const int arr = id / NL, l = id - arr * NL;
+            double x[D1], y[Q];
+#pragma unroll
+            for (int i = 0; i < D1; i++) { x[i] = U[l * D1 + i]; }
+            if (arr == 0) { RMH_LINE(Q, D1, mB, x, y) }
+            else { RMH_LINE(Q, D1, mG, x, y) }
+            double *o = (arr == 0 ? BU : GU) + l * Q;
+#pragma unroll
+            for (int q = 0; q < Q; q++) { o[q] = y[q]; }
+         }
+         else
+         {
+            const int l = id - 2 * NL;                       // (e, f, jb)
+            const int ef = l / D1, jb = l - ef * D1;
+            const int e = ef / NF, f = ef - e * NF;
+            // own trace: face f fixes `axis` at `side`; (ja, jb) run over the remaining axes
+            const int axis = (f == 0 || f == 5) ? 2 : ((f == 1 || f == 3) ? 1 : 0);
+            const int side = (f == 2 || f == 3 || f == 5) ? 1 : 0;
+            const int s1 = (axis == 0) ? D1 : 1;
+            const int s2 = (axis == 2) ? D1 : D1 * D1;
+            const int sa = (axis == 0) ? 1 : ((axis == 1) ? D1 : D1 * D1);
+            const double *own = U + e * ND + side * (D1 - 1) * sa + jb * s2;
+            double x[D1], y[Q];
+#pragma unroll
+            for (int i = 0; i < D1; i++) { x[i] = own[i * s1] - NB[l * D1 + i]; }
+            RMH_LINE(Q, D1, mB, x, y)
+#pragma unroll
+            for (int q = 0; q < Q; q++) { F1[l * Q + q] = y[q]; }
+         }
+      }
+      __syncthreads();
+      // ---- B: fwd-y tasks (arr, e, z, qx)  |  face fused tasks (e, f, qa)
+      for (int id = threadIdx.x; id < 3 * NY; id += T)
+      {
+         const int arr = id / NY, l = id - arr * NY;
+         const int ez = l / Q, qx = l - ez * Q;
+         const double *in = (arr == 0 ? GU : BU) + ez * D1 * Q + qx;
+         double x[D1], y[Q];
+#pragma unroll
+         for (int i = 0; i < D1; i++) { x[i] = in[i * Q]; }
+         if (arr == 1) { RMH_LINE(Q, D1, mG, x, y) }
+         else { RMH_LINE(Q, D1, mB, x, y) }
+         const int e = ez / D1, z = ez - e * D1;
+         double *o = GB + ((e * 3 + arr) * D1 + z) * QQ + qx;
+#pragma unroll
+         for (int q = 0; q < Q; q++) { o[q * Q] = y[q]; }
+      }
+#pragma unroll
+      for (int k = 0; k < K2; k++)
+      {
+         const int id = threadIdx.x + k * T;
+         if (id < NT2)
+         {
+            const int ef = id / Q, qa = id - ef * Q;
+            double x[D1], y[Q], z[D1];
+#pragma unroll
+            for (int i = 0; i < D1; i++) { x[i] = F1[(ef * D1 + i) * Q + qa]; }
+            RMH_LINE(Q, D1, mB, x, y)
+#pragma unroll
+            for (int q = 0; q < Q; q++) { y[q] *= pre.df[k][q]; }
+            RMH_LINE(D1, Q, mC, y, z)
+#pragma unroll
+            for (int i = 0; i < D1; i++) { F1[(ef * D1 + i) * Q + qa] = z[i]; }
+         }
+      }
+      __syncthreads();
+      // ---- C: z-fused task (e, qy, qx)  |  face tasks (e, f, ib): contract qa -> ia
+      {
+         const int zid = threadIdx.x, ze = zid / QQ, zr = zid - ze * QQ;
+         if (zid < E * QQ)
+         {
+            double *col = GB + ze * 3 * D1 * QQ + zr;
+            double gb[D1], bg[D1], bb[D1], tz[D1];
+#pragma unroll
+            for (int i = 0; i < D1; i++)
+            {
+               gb[i] = col[i * QQ];
+               bg[i] = col[(D1 + i) * QQ];
+               bb[i] = col[(2 * D1 + i) * QQ];
+               tz[i] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++)
+            {
+               double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+               for (int i = 0; i < D1; i++)
+               {
+                  g0 = fma(tab.B[q][i], gb[i], g0);
+                  g1 = fma(tab.B[q][i], bg[i], g1);
+                  g2 = fma(tab.G[q][i], bb[i], g2);
+               }
+               const double sv = pre.d0[q] * g0 + pre.d1[q] * g1 + pre.d2[q] * g2;
+#pragma unroll
+               for (int i = 0; i < D1; i++) { tz[i] = fma(tab.C[i][q], sv, tz[i]); }
+            }
+#pragma unroll
+            for (int i = 0; i < D1; i++) { col[i * QQ] = tz[i]; }
+         }
+      }
+      for (int id = threadIdx.x; id < NT1; id += T)
+      {
+         double x[Q], y[D1];
+#pragma unroll
+         for (int q = 0; q < Q; q++) { x[q] = F1[id * Q + q]; }
+         RMH_LINE(D1, Q, mC, x, y)
+#pragma unroll
+         for (int i = 0; i < D1; i++) { FD[id * D1 + i] = y[i]; }
+      }
+      __syncthreads();
+      // ---- D: bwd-y tasks (e, iz, qx)
+      double *S2 = BU;
+      for (int id = threadIdx.x; id < NY; id += T)
+      {
+         const int eiz = id / Q, qx = id - eiz * Q;
+         const int e = eiz / D1, iz = eiz - e * D1;
+         const double *in = GB + (e * 3 * D1 + iz) * QQ + qx;
+         double x[Q], y[D1];
+#pragma unroll
+         for (int q = 0; q < Q; q++) { x[q] = in[q * Q]; }
+         RMH_LINE(D1, Q, mC, x, y)
+#pragma unroll
+         for (int i = 0; i < D1; i++) { S2[(eiz * D1 + i) * Q + qx] = y[i]; }
+      }
+      __syncthreads();
+      // ---- E: bwd-x tasks (e, iz, iy) + face contributions with the normal-direction Minv
+      for (int id = threadIdx.x; id < NL; id += T)
+      {
+         double x[Q], rr[D1];
+#pragma unroll
+         for (int q = 0; q < Q; q++) { x[q] = S2[id * Q + q]; }
+         RMH_LINE(D1, Q, mC, x, rr)
+         const int e = id / (D1 * D1), r = id - e * D1 * D1, bb_ = r / D1, aa_ = r - bb_ * D1;
+         const double *fc = FD + e * NF * NFD;
+         // faces: 0 z=0 (x,y)  1 y=0 (x,z)  2 x=p (y,z)  3 y=p (x,z)  4 x=0 (y,z)  5 z=p (x,y)
+         const double fx0 = fc[4 * NFD + bb_ * D1 + aa_], fx1 = fc[2 * NFD + bb_ * D1 + aa_];
+         const double my0 = tab.Minv[aa_][0], my1 = tab.Minv[aa_][D1 - 1];
+         const double mz0 = tab.Minv[bb_][0], mz1 = tab.Minv[bb_][D1 - 1];
+         const double sc = dat[S::P_E + e];
+#pragma unroll
+         for (int i = 0; i < D1; i++)
+         {
+            double v = rr[i];
+            v = fma(tab.Minv[i][0], fx0, v);
+            v = fma(tab.Minv[i][D1 - 1], fx1, v);
+            v = fma(my0, fc[1 * NFD + bb_ * D1 + i], v);
+            v = fma(my1, fc[3 * NFD + bb_ * D1 + i], v);
+            v = fma(mz0, fc[0 * NFD + aa_ * D1 + i], v);
+            v = fma(mz1, fc[5 * NFD + aa_ * D1 + i], v);
+            X[id * D1 + i] = v * sc;
+         }
+      }
+      __syncthreads();
+      // ---- element-wise part: one warp per element (MassBasedAvg, bounds, ClipScale, RK).
+      // On an element with constant det J the Bernstein lumped mass is the same for every DOF,
+      // m = vol/ND (int B_i = 1/(p+1) per axis), so no lumped-mass stream is read here.
+      if (w < ne)
+      {
+         const int64_t ge = e0 + w;
+         const double *X0 = dat + S::P_X + w * ND;
+         const double *BD = dat + S::P_B + w * N3 * 2;
+         const double dt = a.dt;
+         const double inv_m = dat[S::P_E + w] * (double)ND, m = 1.0 / inv_m, mdt = m * inv_dt;
+         double u[NK], du_ho[NK], f[NK], lo[NK], bmn[NK], bmx[NK];
+         double bmin1 = INFINITY, bmax1 = -INFINITY;
+         if (a.bounds_type == 1)
+         {
+#pragma unroll
+            for (int k = 0; k <= NF; k++) { bmin1 = fmin(bmin1, BD[2 * k]); bmax1 = fmax(bmax1, BD[2 * k + 1]); }
+         }
+         double s1 = 0.0;
+#pragma unroll
+         for (int k = 0; k < NK; k++)
+         {
+            const int j = lane + 32 * k;
+            if (j < ND)
+            {
+               u[k] = U[w * ND + j];
+               du_ho[k] = X[w * ND + j];
+               if (a.bounds_type == 0) { bmn[k] = BD[2 * cls[k]]; bmx[k] = BD[2 * cls[k] + 1]; }
+               else { bmn[k] = bmin1; bmx[k] = bmax1; }
+               s1 += u[k] + dt * du_ho[k];
+            }
+         }
+         s1 = warp_sum(s1);
+         const double ubar = s1 * (1.0 / ND);                // MassBasedAvg, remhos_lo.cpp:278-285
+         double sumPos = 0.0, sumNeg = 0.0;
+#pragma unroll
+         for (int k = 0; k < NK; k++)
+         {
+            const int j = lane + 32 * k;
+            if (j < ND)
+            {
+               lo[k] = (ubar - u[k]) * inv_dt;
+               const double u_new_lo = u[k] + dt * lo[k];
+               const double fmn = mdt * (bmn[k] - u_new_lo);
+               const double fmx = mdt * (bmx[k] - u_new_lo);
+               double fcl = m * (du_ho[k] - lo[k]);
+               fcl = fmin(fmx, fmax(fmn, fcl));               // ClipScale, remhos_fct.cpp:490-515
+               f[k] = fcl;
+               sumNeg += fmin(fcl, 0.0);
+               sumPos += fmax(fcl, 0.0);
+            }
+         }
+         warp_sum2(sumNeg, sumPos);
+         const double new_mass = sumNeg + sumPos;
+         constexpr double eps = 1.0e-15;
+         // scale the positive (or negative) part so that the clipped fluxes sum to zero
+         const bool sp = new_mass > eps, sn = new_mass < -eps;
+         const double ratio = sp ? sumNeg / sumPos : (sn ? sumPos / sumNeg : 0.0);
+         double omin = INFINITY, omax = -INFINITY;
+#pragma unroll
+         for (int k = 0; k < NK; k++)
+         {
+            const int j = lane + 32 * k;
+            if (j < ND)
+            {
+               double fcl = f[k];
+               if (sp) { fcl = fmin(0.0, fcl) - fmax(0.0, fcl) * ratio; }
+               if (sn) { fcl = fmax(0.0, fcl) - fmin(0.0, fcl) * ratio; }
+               const double du = lo[k] + fcl * inv_m;
+               double o = du;
+               if (a.out_mode == 1)
+               {
+                  const double base = a.has_x0 ? a.a * X0[j] : 0.0;
+                  o = base + a.b * (u[k] + dt * du);
+               }
+               a.out[ge * ND + j] = o;
+               omin = fmin(omin, o); omax = fmax(omax, o);
+            }
+         }
+         if (a.xe_min_out)
+         {
+            warp_minmax(omin, omax);
+            if (lane == 0) { a.xe_min_out[ge] = omin; a.xe_max_out[ge] = omax; }
+         }
+      }
+   }
+}
+
+} // namespace rmh
+
+#endif
