@@ -5,6 +5,8 @@
 #include "kernels.cuh"
 #include "stage3d.cuh"
 #include "stage3p.cuh"
+#include "stage3t.cuh"
+#include "stage3w.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -71,6 +73,8 @@ struct rmh_ctx
    double *xe_min = nullptr, *xe_max = nullptr;
    int num_sms = 0;
    bool pipelined = true;      // RMH_NO_PIPELINE=1 selects the one-batch-per-block stage kernel
+   bool tensor = true;         // RMH_NO_TENSOR=1 selects the DFMA pipelined kernel
+   bool frag = false;          // Dvol/Dface stored in the fragment order of stage3t.cuh
    bool xe_valid = false;
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    // halo
@@ -110,6 +114,7 @@ static int dev_upload(rmh_ctx *c, Tp **p, const Tp *h, size_t n)
 struct GeomArgs
 {
    int dim, Q, NG1, exec_mode;
+   int frag;
    int64_t ne;
    double t;
    const double *X0, *V, *velq, *velf, *L, *dL, *Ls, *dLs, *w;
@@ -205,7 +210,14 @@ __global__ void k_geom_vol(GeomArgs g)
    {
       double s = 0.0;
       for (int j = 0; j < DIM; j++) { s += adj[c][j] * v[j]; }
-      g.Dvol[((size_t)e * DIM + c) * NQ + q] = alpha * w * s;
+      if (g.frag)
+      {
+         // [e][col = qy*Q+qx][qz (RQ)][3]
+         const int RQ = (Q + 1) & ~1, QQ = Q * Q;
+         const int col = q % QQ, qz = q / QQ;
+         g.Dvol[(size_t)e * QQ * RQ * 3 + ((size_t)col * RQ + qz) * 3 + c] = alpha * w * s;
+      }
+      else { g.Dvol[((size_t)e * DIM + c) * NQ + q] = alpha * w * s; }
    }
    g.detJw[(size_t)e * NQ + q] = w * det;
 }
@@ -249,7 +261,12 @@ __global__ void k_geom_face(GeomArgs g)
    {
       // 3D layout [e][qb][f][qa] (coalesced for the (qa, f) thread mapping of stage3d.cuh)
       const int qa = qf % Q, qb = qf / Q;
-      g.Dface[(size_t)e * NF * NQF + (size_t)qb * NF * Q + f * Q + qa] = w * vs;
+      if (g.frag)
+      {
+         const int RQ = (Q + 1) & ~1;     // [e][f][qa][qb (RQ)]
+         g.Dface[(size_t)e * NF * Q * RQ + ((size_t)f * Q + qa) * RQ + qb] = w * vs;
+      }
+      else { g.Dface[(size_t)e * NF * NQF + (size_t)qb * NF * Q + f * Q + qa] = w * vs; }
    }
    else { g.Dface[idx] = w * vs; }
 }
@@ -342,6 +359,7 @@ struct HoArgs
    const double *Dvol, *detJw, *Dface, *einv;
    FaceNbr fn;
    int mode;              // bit 0: apply K_HO, bit 1: apply M^-1
+   int frag;              // stored quadrature data in fragment order
    double tol2;
    int maxit;
 };
@@ -398,7 +416,7 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
       if constexpr (AFF)
       {
          // every element of the mesh has constant det J (checked on the host at set-up)
-         pre.load(a.Dvol + (size_t)e0 * DIM * NQ, a.Dface + (size_t)e0 * NF * NQF, ne);
+         pre.load(a.Dvol, a.Dface, e0, ne, a.frag != 0);
          face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne);
          __syncthreads();
          ho3_affine<D1, Q, E>(U, X, sm, pre, a.einv + e0, ne, tab);
@@ -408,7 +426,7 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
       {
          if (a.mode & 1)
          {
-            pre.load(a.Dvol + (size_t)e0 * DIM * NQ, a.Dface + (size_t)e0 * NF * NQF, ne);
+            pre.load(a.Dvol, a.Dface, e0, ne, a.frag != 0);
             face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne);
          }
          __syncthreads();
@@ -973,10 +991,109 @@ static int dispatch_stagep(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    RMH_DISPATCH(launch_stagep, c, a, s);
 }
 
+// ---- FP64 tensor-core variant (stage3t.cuh); needs the fragment-ordered operator data
+template <int D1, int Q, int E, int NW>
+static int launch_staget_E(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   using S = SmemT<D1, Q, E, NW>;
+   constexpr int MINB0 = (int)((227 * 1024) / (S::BYTES + 1024));
+   constexpr int MINB1 = MINB0 < 1 ? 1 : MINB0;
+   constexpr int MINB = (MINB1 * NW > 16) ? (16 / NW > 0 ? 16 / NW : 1) : MINB1;   // <= 16 warps/SM: 128 regs
+   static int blocks_per_sm = 0;
+   if (blocks_per_sm == 0)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_stage3t<D1, Q, E, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)S::BYTES));
+      int nb = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3t<D1, Q, E, NW, MINB>, S::T, S::BYTES));
+      if (nb < 1) { set_error("k_stage3t does not fit on an SM"); return 1; }
+      blocks_per_sm = nb;
+   }
+   const int64_t nbatch = (a.ne + E - 1) / E;
+   const int64_t grid = std::min<int64_t>(nbatch, (int64_t)blocks_per_sm * c->num_sms);
+   k_stage3t<D1, Q, E, NW, MINB><<<(unsigned)grid, S::T, S::BYTES, s>>>(a, make_tab<D1, Q>(c));
+   LAUNCH_OK();
+   return 0;
+}
+
+template <int DIM, int D1, int Q>
+static int launch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   if constexpr (DIM == 3 && D1 <= 4)
+   {
+      static int nw = -1;
+      if (nw < 0) { const char *ev = getenv("RMH_TENSOR_NW"); nw = ev ? atoi(ev) : 4; }
+      if (nw == 8) { return launch_staget_E<D1, Q, 4, 8>(c, a, s); }
+      if (nw == 6) { return launch_staget_E<D1, Q, 4, 6>(c, a, s); }
+      return launch_staget_E<D1, Q, 4, 4>(c, a, s);
+   }
+   else
+   {
+      set_error("tensor-core stage kernel: 3D, order <= 3 only");
+      return 1;
+   }
+}
+
+static int dispatch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   RMH_DISPATCH(launch_staget, c, a, s);
+}
+
+// ---- warp-per-element FP64 tensor-core kernel (stage3w.cuh)
+template <int D1, int Q, int NW>
+static int launch_stagew_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   using S = SmemW<D1, Q>;
+   constexpr size_t BYTES = S::bytes(NW);
+   constexpr int MINB0 = (int)((228 * 1024) / (BYTES + 1024));
+   constexpr int MINB1 = MINB0 < 1 ? 1 : MINB0;
+   constexpr int MINB = (MINB1 * NW > 20) ? (20 / NW > 0 ? 20 / NW : 1) : MINB1;   // <= 20 warps per SM
+   static int blocks_per_sm = 0;
+   if (blocks_per_sm == 0)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_stage3w<D1, Q, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)BYTES));
+      int nb = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3w<D1, Q, NW, MINB>, NW * 32, BYTES));
+      if (nb < 1) { set_error("k_stage3w does not fit on an SM"); return 1; }
+      blocks_per_sm = nb;
+   }
+   const int64_t nblk = (a.ne + NW - 1) / NW;
+   const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
+   k_stage3w<D1, Q, NW, MINB><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tab<D1, Q>(c));
+   LAUNCH_OK();
+   return 0;
+}
+
+template <int DIM, int D1, int Q>
+static int launch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   if constexpr (DIM == 3 && D1 <= 4)
+   {
+      static int nw = -1;
+      if (nw < 0) { const char *ev = getenv("RMH_W_NW"); nw = ev ? atoi(ev) : 5; }
+      if (nw == 4) { return launch_stagew_N<D1, Q, 4>(c, a, s); }
+      if (nw == 8) { return launch_stagew_N<D1, Q, 8>(c, a, s); }
+      if (nw == 10) { return launch_stagew_N<D1, Q, 10>(c, a, s); }
+      return launch_stagew_N<D1, Q, 5>(c, a, s);
+   }
+   else
+   {
+      set_error("tensor-core stage kernel: 3D, order <= 3 only");
+      return 1;
+   }
+}
+
+static int dispatch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   RMH_DISPATCH(launch_stagew, c, a, s);
+}
+
 static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
 {
    GeomArgs g;
    g.dim = c->dim; g.Q = c->Q; g.NG1 = c->NG1; g.exec_mode = c->exec_mode; g.ne = c->ne; g.t = t;
+   g.frag = c->frag ? 1 : 0;
    g.X0 = c->X0; g.V = c->V; g.velq = c->velq; g.velf = c->velf;
    g.L = c->dL; g.dL = c->ddL; g.Ls = c->dLs; g.dLs = c->ddLs; g.w = c->dw;
    g.Dvol = c->Dvol; g.detJw = c->detJw; g.Dface = c->Dface;
@@ -1049,6 +1166,8 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       c->num_sms = prop.multiProcessorCount;
       const char *np = getenv("RMH_NO_PIPELINE");
       c->pipelined = !(np && np[0] == '1');
+      const char *nt = getenv("RMH_NO_TENSOR");
+      c->tensor = !(nt && nt[0] == '1');
    }
    auto fail = [&]() { rmh_ctx_destroy(c); return 1; };
    if ((double)(c->ne + c->ne_ghost) * c->ND >= 2147483647.0)
@@ -1189,9 +1308,15 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       if (dev_upload(c, &c->bnbr, d->nbr_elem, (size_t)c->ne * c->NF)) { return fail(); }
    }
    // ---- operator data + scratch
-   if (dev_alloc(c, &c->Dvol, (size_t)c->ne * c->dim * c->NQ)) { return fail(); }
+   // 3D: room for the fragment-ordered layout (rows of Q padded to even length)
+   const size_t rq = (size_t)((c->Q + 1) & ~1);
+   const size_t n_dvol = (c->dim == 3) ? (size_t)c->ne * c->Q * c->Q * rq * 3 : (size_t)c->ne * c->dim * c->NQ;
+   const size_t n_dface = (c->dim == 3) ? (size_t)c->ne * c->NF * c->Q * rq : (size_t)c->ne * c->NF * c->NQF;
+   if (dev_alloc(c, &c->Dvol, n_dvol)) { return fail(); }
    if (dev_alloc(c, &c->detJw, (size_t)c->ne * c->NQ)) { return fail(); }
-   if (dev_alloc(c, &c->Dface, (size_t)c->ne * c->NF * c->NQF)) { return fail(); }
+   if (dev_alloc(c, &c->Dface, n_dface)) { return fail(); }
+   CUDA_OK(cudaMemset(c->Dvol, 0, n_dvol * sizeof(double)));
+   CUDA_OK(cudaMemset(c->Dface, 0, n_dface * sizeof(double)));
    if (dev_alloc(c, &c->ml, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->einv, (size_t)c->ne)) { return fail(); }
    if (dev_alloc(c, &c->w1, (size_t)c->N)) { return fail(); }
@@ -1207,6 +1332,16 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       CUDA_OK(cudaMemcpy(ei.data(), c->einv, ei.size() * sizeof(double), cudaMemcpyDeviceToHost));
       c->all_affine = true;
       for (double v : ei) { if (!(v > 0.0)) { c->all_affine = false; break; } }
+      // affine 3D meshes run the tensor-core stage kernel: store the quadrature data in its
+      // fragment order (every other 3D kernel reads it through the layout flag)
+      if (c->all_affine && c->dim == 3 && c->pipelined && c->tensor && c->D1 <= 4)
+      {
+         c->frag = true;
+         CUDA_OK(cudaMemset(c->Dvol, 0, n_dvol * sizeof(double)));
+         CUDA_OK(cudaMemset(c->Dface, 0, n_dface * sizeof(double)));
+         if (run_geom(c, 0.0, 0)) { return fail(); }
+         CUDA_OK(cudaDeviceSynchronize());
+      }
    }
    *out = c;
    return 0;
@@ -1241,7 +1376,7 @@ static HoArgs ho_args(rmh_ctx *c, const double *in, double *out, int mode)
    a.Dvol = c->Dvol; a.detJw = c->detJw; a.Dface = c->Dface; a.einv = c->einv;
    a.fn.nbr_elem = c->nbr_elem; a.fn.nbr_pat = c->nbr_pat; a.fn.pat = c->pat;
    a.fn.ughost = c->ughost; a.fn.ne_owned = c->ne;
-   a.mode = mode; a.tol2 = c->pcg_tol2; a.maxit = c->pcg_maxit;
+   a.mode = mode; a.tol2 = c->pcg_tol2; a.maxit = c->pcg_maxit; a.frag = c->frag ? 1 : 0;
    return a;
 }
 
@@ -1381,12 +1516,22 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       pa.fn = sa.ho.fn; pa.npat = c->npat; pa.nbr_pat32 = c->nbr_pat32;
       pa.a = a; pa.b = b; pa.dt = dt; pa.out_mode = out_mode;
       pa.has_x0 = (out_mode == 1 && a != 0.0) ? 1 : 0;
+      pa.frag = c->frag ? 1 : 0;
       pa.bounds_type = c->bounds_type;
       pa.bidx = (c->bounds_type == 0) ? c->lat : c->bnbr;
       pa.ent_mm = c->ent_mm; pa.xe_min = c->xe_min; pa.xe_max = c->xe_max;
       pa.xe_min_out = sa.xe_min_out; pa.xe_max_out = sa.xe_max_out;
    }
-   auto run = [&]() { return use_p ? dispatch_stagep(c, pa, s) : dispatch_stage(c, sa, s); };
+   auto run = [&]()
+   {
+      if (use_p && c->frag)
+      {
+         static int blk = -1;   // RMH_TENSOR_BLOCK=1: block-per-batch DMMA kernel (stage3t.cuh)
+         if (blk < 0) { const char *ev = getenv("RMH_TENSOR_BLOCK"); blk = (ev && ev[0] == '1') ? 1 : 0; }
+         return blk ? dispatch_staget(c, pa, s) : dispatch_stagew(c, pa, s);
+      }
+      return use_p ? dispatch_stagep(c, pa, s) : dispatch_stage(c, sa, s);
+   };
    if (c->prof)
    {
       if (c->prof_used + 2 > c->prof_ev.size())

@@ -69,20 +69,27 @@ struct Pre3
    static constexpr int K2 = (E * S::NF * Q + S::T - 1) / S::T;
    double d0[Q], d1[Q], d2[Q];
    double df[K2][Q];
+   // frag = false: Dvol [e][3][NQ], Dface [e][qb][f][qa];  frag = true: the fragment-ordered
+   // layout of stage3t.cuh, Dvol [e][col][qz (RQ)][3], Dface [e][f][qa][qb (RQ)]
    __device__ __forceinline__ void load(const double *__restrict__ Dvol,
-                                        const double *__restrict__ Dface, int ne)
+                                        const double *__restrict__ Dface, int64_t e0, int ne,
+                                        bool frag)
    {
-      constexpr int NQ = S::NQ, QQ = S::QQ, NF = S::NF, T = S::T;
+      constexpr int NQ = S::NQ, QQ = S::QQ, NF = S::NF, T = S::T, RQ = (Q + 1) & ~1;
       const int zid = threadIdx.x, ze = zid / QQ, zr = zid - ze * QQ;
       const bool live = (zid < E * QQ) && (ze < ne);
-      const double *dp = Dvol + (size_t)ze * 3 * NQ + zr;
+      const size_t es = frag ? (size_t)QQ * RQ * 3 : (size_t)3 * NQ;
+      const int sc = frag ? 1 : NQ, sq = frag ? 3 : QQ, scol = frag ? 3 * RQ : 1;
+      const double *dp = Dvol + (size_t)(e0 + ze) * es + (size_t)zr * scol;
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
-         d0[q] = live ? __ldcs(dp + q * QQ) : 0.0;
-         d1[q] = live ? __ldcs(dp + NQ + q * QQ) : 0.0;
-         d2[q] = live ? __ldcs(dp + 2 * NQ + q * QQ) : 0.0;
+         d0[q] = live ? __ldcs(dp + q * sq) : 0.0;
+         d1[q] = live ? __ldcs(dp + sc + q * sq) : 0.0;
+         d2[q] = live ? __ldcs(dp + 2 * sc + q * sq) : 0.0;
       }
+      const size_t esf = frag ? (size_t)NF * Q * RQ : (size_t)NF * QQ;
+      const int sqb = frag ? 1 : NF * Q, sr = frag ? RQ : 1;
 #pragma unroll
       for (int k = 0; k < K2; k++)
       {
@@ -90,7 +97,10 @@ struct Pre3
          const int e = id / (NF * Q), r = id - e * (NF * Q);
          const bool lv = (id < E * NF * Q) && (e < ne);
 #pragma unroll
-         for (int q = 0; q < Q; q++) { df[k][q] = lv ? __ldcs(Dface + (size_t)e * NF * QQ + q * NF * Q + r) : 0.0; }
+         for (int q = 0; q < Q; q++)
+         {
+            df[k][q] = lv ? __ldcs(Dface + (size_t)(e0 + e) * esf + (size_t)q * sqb + (size_t)r * sr) : 0.0;
+         }
       }
    }
 };

@@ -92,6 +92,7 @@ struct StagePArgs
    const int32_t *nbr_pat32;  // [NE][NF] pattern ids as int32 (cp.async granularity)
    double a, b, dt;
    int out_mode, has_x0;
+   int frag;                  // stored quadrature data in fragment order (stage3t.cuh)
    int bounds_type;           // 0: bidx = lat [NE][27] -> ent_mm; 1: bidx = bnbr [NE][NF] -> xe_min/xe_max
    const int32_t *bidx;
    const double *ent_mm;      // [n_ent][2]
@@ -282,7 +283,7 @@ k_stage3p(StagePArgs a, const Tab<D1, Q> tab)
       __syncthreads();   // data(b), idx(b+G) landed; previous batch fully consumed
       // ---- stored quadrature data of this batch -> registers (streaming)
       Pre3<D1, Q, E> pre;
-      pre.load(a.Dvol + (size_t)e0 * 3 * NQ, a.Dface + (size_t)e0 * NF * QQ, ne);
+      pre.load(a.Dvol, a.Dface, e0, ne, a.frag != 0);
       // ---- prefetch: data(b+G) through idx(b+G); idx(b+2G)
       {
          const int64_t b1 = b + G, b2 = b + 2 * (int64_t)G;
