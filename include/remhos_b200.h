@@ -13,7 +13,9 @@
  *     (remhos_fct.cpp:492, remhos_lo.cpp:153); index maps are int32.
  *   - pointers named *_dev are CUDA device pointers on the context's device; `stream` is a
  *     cudaStream_t passed as void* (NULL = legacy default stream).
- *   - no hidden device allocation after rmh_ctx_create().
+ *   - no hidden device allocation after rmh_ctx_create() on the fused path (rmh_stage, rmh_rk_*);
+ *     the matrix-based solvers allocate in rmh_fa_setup, the unfused rmh_mult / rmh_ode_step
+ *     allocate their work vectors on first use.
  *   - there is NO CPU fallback: without a CUDA device every rmh_ctx_* call fails.
  */
 #ifndef REMHOS_B200_H
@@ -160,10 +162,22 @@ int rmh_ho_local_inverse(rmh_ctx *ctx, const double *u_dev, double *du_dev, void
 /* MassBasedAvg::CalcLOSolution (remhos_lo.cpp:247-288) */
 int rmh_lo_mass_avg(rmh_ctx *ctx, double dt, const double *u_dev, const double *du_ho_dev,
                     double *du_lo_dev, void *stream);
-/* DiscreteUpwind::CalcLOSolution (remhos_lo.cpp:43-74) */
+/* Assemble the dense element matrices the matrix-based ("full assembly", remhos.cpp:1088)
+ * solvers need: convection blocks K (remhos.cpp:646-657,716-717), mass blocks M, face blocks
+ * bdrInt (Assembly::ComputeFluxTerms, remhos_tools.cpp:788-858) and the diagonal blocks of K_HO.
+ * In remap mode rmh_set_time re-assembles them afterwards (remhos.cpp:1614-1677). */
+int rmh_fa_setup(rmh_ctx *ctx, void *stream);
+/* copy assembled blocks to the host (what the reference reads through SparseMatrix::GetData /
+ * Assembly::bdrInt): which = 0 K [ne][nd][nd], 1 diagonal blocks of K_HO, 2 M [ne][nd][nd],
+ * 3 bdrInt [ne][nf][nfd][nfd], 4 its row sums [ne][nf][nfd]; face DOFs in natural order
+ * (remaining axes ascending) */
+int rmh_fa_get(rmh_ctx *ctx, int which, double *host_out);
+/* DiscreteUpwind::CalcLOSolution (remhos_lo.cpp:43-100) with ComputeDiscreteUpwindingMatrix
+ * (remhos_tools.cpp:1464-1487) and Assembly::LinearFluxLumping, alpha = 0 (:876-913).
+ * Needs rmh_fa_setup. */
 int rmh_lo_discrete_upwind(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
-/* ResidualDistribution / PAResidualDistribution::CalcLOSolution
- * (remhos_lo.cpp:111-245, 967-1035) */
+/* ResidualDistribution / PAResidualDistribution::CalcLOSolution without subcells
+ * (remhos_lo.cpp:111-245, 967-1035; -lo 2 / -lo 3): matrix-free */
 int rmh_lo_res_dist(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
 
 /* DofInfo::ComputeElementsMinMax (remhos_tools.cpp:497-523) */
@@ -178,6 +192,29 @@ int rmh_fct_clip_scale(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
                        const double *du_ho_dev, const double *du_lo_dev,
                        const double *xi_min_dev, const double *xi_max_dev, double *du_dev,
                        void *stream);
+
+/* FluxBasedFCT::CalcFCTSolution, one FCT iteration as the driver fixes it (remhos_fct.cpp:155-181,
+ * 295-446; remhos.cpp:1093).  Needs rmh_fa_setup; single-rank meshes only. */
+int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const double *m_dev,
+                       const double *du_ho_dev, const double *du_lo_dev,
+                       const double *xi_min_dev, const double *xi_max_dev, double *du_dev,
+                       void *stream);
+
+/* LimitedTimeDependentOperator::Mult (remhos_solvers.hpp:46-50) for any supported combination of
+ * -ho {0,3} -lo {0,1,3,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
+ * remhos.cpp:1598-1677): k = F(u; t, dt).  Orchestrates the separate kernels exactly as
+ * MultUnlimited / LimitMult do (remhos.cpp:1596-1739, 1798-1916); -ho 3 -lo 5 -fct 2 runs the
+ * fused stage kernel. */
+int rmh_mult(rmh_ctx *ctx, int ho_type, int lo_type, int fct_type, double t, double dt,
+             const double *u_dev, double *k_dev, void *stream);
+/* out = sum_i coef[i] * x[i], 1 <= n <= 9 (the vector updates of the explicit RK solvers) */
+int rmh_lincomb(rmh_ctx *ctx, int n, const double *coef, const double *const *x_dev,
+                double *out_dev, void *stream);
+/* ODESolver::Step for -s 1, 2, 3, 4, 6 (ForwardEuler, RK2Solver(1.0), RK3SSPSolver, RK4Solver,
+ * RK6Solver; remhos.cpp:488-492) over rmh_mult; returns 3 for an unknown type as remhos()
+ * does (remhos.cpp:499-500). */
+int rmh_ode_step(rmh_ctx *ctx, int ode_solver_type, int ho_type, int lo_type, int fct_type,
+                 double *t, double dt, double *u_dev, void *stream);
 
 /* LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult for the configuration
  * -ho 3 -lo {1,3,5} -fct 2 (remhos_solvers.hpp:46-50; remhos.cpp:1596-1739,1798-1916):

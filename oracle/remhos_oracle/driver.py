@@ -13,6 +13,31 @@ from . import fe, mesh as meshmod, dg, problems
 from .solvers import Discretization
 
 
+# MFEM RK6Solver tables (Verner's 8-stage, 6th-order method; remhos.cpp:492).  MFEM is not in the
+# reference tree, so the coefficients are restated and checked against the 6th-order conditions
+# in tests/test_oracle_golden.py (test_rk6_tableau).
+RK6_A = [
+    .6e-1,
+    .1923996296296296296296296296296296296296e-1, .7669337037037037037037037037037037037037e-1,
+    .35975e-1, 0., .107925,
+    1.318683415233148260919747276431735612861, 0., -5.042058063628562225427761634715637693344,
+    4.220674648395413964508014358283902080483,
+    -41.87259166432751461803757780644346812905, 0., 159.4325621631374917700365669070346830453,
+    -122.1192135650100309202516203389242140663, 5.531743066200053768252631238332999150076,
+    -54.43015693531650433250642051294142461271, 0., 207.0672513650184644273657173866509835987,
+    -158.6108137845899991828742424365058599469, 6.991816585950242321992597280791793907096,
+    -.1859723106220323397765171799549294623692e-1,
+    -54.66374178728197680241215648050386959351, 0., 207.9528062553893734515824816699834244238,
+    -159.2889574744995071508959805871426654216, 7.018743740796944434698170760964252490817,
+    -.1833878590504572306472782005141738268361e-1, -.5119484997882099077875432497245168395840e-3]
+RK6_B = [
+    .3438957868357036009278820124728322386520e-1, 0., 0.,
+    .2582624555633503404659558098586120858767, .4209371189673537150642551514069801967032,
+    4.405396469669310170148836816197095664891, -176.4831190242986576151740942499002125029,
+    172.3641334014150730294022582711902413315]
+RK6_C = [.6e-1, .9593333333333333333333333333333333333333e-1, .1439, .4973, .9725, .9995, 1.]
+
+
 @dataclass
 class Options:                       # defaults: remhos.cpp:216-244
     mesh_file: str = 'default'
@@ -176,6 +201,19 @@ class Run:
             k3 = f(u + dt / 2 * k2, t + dt / 2, dt)
             k4 = f(u + dt * k3, t + dt, dt)
             return u + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        if s == 6:                                             # RK6Solver (ExplicitRKSolver)
+            a, b, c = RK6_A, RK6_B, RK6_C
+            ks = [f(u, t, dt)]
+            for i in range(1, 8):
+                ai = a[i * (i - 1) // 2:i * (i + 1) // 2]
+                y = u.copy()
+                for j in range(i):
+                    y = y + dt * ai[j] * ks[j]
+                ks.append(f(y, t + c[i - 1] * dt, dt))
+            y = u.copy()
+            for j in range(8):
+                y = y + dt * b[j] * ks[j]
+            return y
         raise NotImplementedError('ode solver %d' % s)
 
     def run(self, callback=None):

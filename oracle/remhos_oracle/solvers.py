@@ -235,12 +235,14 @@ class Discretization:
             c_n = np.broadcast_to(nb[:, None, :], (ne, sp.nfd, sp.nfd))
             rows.append(r[has].reshape(-1)); cols.append(c_n[has].reshape(-1))
             vals.append(A.bdrInt[has, f].reshape(-1))
-        Ksp = sps.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
-                             shape=(self.N, self.N)).tocsr()
+        rows = np.concatenate(rows); cols = np.concatenate(cols)
+        Ksp = sps.coo_matrix((np.concatenate(vals), (rows, cols)), shape=(self.N, self.N)).tocsr()
         Ksp.sum_duplicates()
-        KT = Ksp.T.tocsr()
-        # union pattern (structurally symmetric already); take upper triangle
-        P = (abs(Ksp) + abs(KT)).tocoo()
+        # structural pattern of the assembled form (every in-element pair and every face
+        # coupling, whatever the values: MFEM keeps exact zeros in the CSR pattern); take the
+        # upper triangle
+        P = sps.coo_matrix((np.ones(rows.size), (rows, cols)), shape=(self.N, self.N)).tocsr()
+        P = (P + P.T).tocoo()
         mask = P.col > P.row
         I = P.row[mask]; J = P.col[mask]
         kij = np.asarray(Ksp[I, J]).reshape(-1)

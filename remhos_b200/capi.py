@@ -211,6 +211,7 @@ class Context:
         self.nd = lib().rmh_ctx_nd(self.h)
         self.ne = d.ne
         self.nq1d = lib().rmh_ctx_nq1d(self.h)
+        self.dim = dim
 
     def close(self):
         if self.h:
@@ -253,6 +254,41 @@ class Context:
 
     def lo_res_dist(self, u, du_lo, s=0):
         check(lib().rmh_lo_res_dist(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
+
+    def fa_setup(self, s=0):
+        check(lib().rmh_fa_setup(self.h, C.c_void_p(s)))
+
+    def fa_get(self, which):
+        nd, ne = self.nd, self.ne
+        dim = self.dim
+        nf = 2 * dim
+        nfd = round(nd ** ((dim - 1) / dim))
+        shape = {0: (ne, nd, nd), 1: (ne, nd, nd), 2: (ne, nd, nd), 3: (ne, nf, nfd, nfd),
+                 4: (ne, nf, nfd)}[which]
+        out = np.zeros(shape)
+        check(lib().rmh_fa_get(self.h, int(which), _ptr(out)))
+        return out
+
+    def fct_flux_based(self, dt, u, m, du_ho, du_lo, xi_min, xi_max, du, s=0):
+        check(lib().rmh_fct_flux_based(self.h, C.c_double(dt), _dp(u), _dp(m), _dp(du_ho),
+                                       _dp(du_lo), _dp(xi_min), _dp(xi_max), _dp(du),
+                                       C.c_void_p(s)))
+
+    def mult(self, ho_type, lo_type, fct_type, t, dt, u, k, s=0):
+        check(lib().rmh_mult(self.h, int(ho_type), int(lo_type), int(fct_type), C.c_double(t),
+                             C.c_double(dt), _dp(u), _dp(k), C.c_void_p(s)))
+
+    def ode_step(self, ode_solver_type, ho_type, lo_type, fct_type, t, dt, u, s=0):
+        tt = C.c_double(t)
+        check(lib().rmh_ode_step(self.h, int(ode_solver_type), int(ho_type), int(lo_type),
+                                 int(fct_type), C.byref(tt), C.c_double(dt), _dp(u), C.c_void_p(s)))
+        return tt.value
+
+    def lincomb(self, coef, xs, out, s=0):
+        n = len(coef)
+        ca = (C.c_double * n)(*coef)
+        xa = (C.c_void_p * n)(*[_dp(x).value for x in xs])
+        check(lib().rmh_lincomb(self.h, n, ca, xa, _dp(out), C.c_void_p(s)))
 
     def elem_min_max(self, u, xe_min, xe_max, s=0):
         check(lib().rmh_elem_min_max(self.h, _dp(u), _dp(xe_min), _dp(xe_max), C.c_void_p(s)))

@@ -7,6 +7,7 @@
 #include "stage3p.cuh"
 #include "stage3t.cuh"
 #include "stage3w.cuh"
+#include "fa.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -77,6 +78,15 @@ struct rmh_ctx
    bool frag = false;          // Dvol/Dface stored in the fragment order of stage3t.cuh
    bool xe_valid = false;
    bool all_affine = false;   // every element has constant det J (transport meshes only)
+   // matrix-based ("FA") solver data: lumped face matrices always; dense blocks after rmh_fa_setup
+   double *dG = nullptr, *BL = nullptr;
+   double *faK = nullptr, *faKH = nullptr, *faM = nullptr, *faBI = nullptr;
+   int16_t *pat_idx = nullptr;
+   uint8_t *pat_face = nullptr;
+   bool fa_on = false;
+   // work vectors of the unfused solver path (allocated on first use)
+   double *wk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   double *rk[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    // halo
    const double *ughost = nullptr;   // caller-owned ghost DOF blocks (rmh_halo_set)
    // scratch
@@ -358,7 +368,7 @@ struct HoArgs
    double *out;
    const double *Dvol, *detJw, *Dface, *einv;
    FaceNbr fn;
-   int mode;              // bit 0: apply K_HO, bit 1: apply M^-1
+   int mode;              // bit 0: apply K_HO, bit 1: apply M^-1, bit 2: volume terms only
    int frag;              // stored quadrature data in fragment order
    double tol2;
    int maxit;
@@ -427,10 +437,11 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
          if (a.mode & 1)
          {
             pre.load(a.Dvol, a.Dface, e0, ne, a.frag != 0);
-            face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne);
+            if (!(a.mode & 4)) { face3_gather<D1, Q, E>(sm, a.u, a.fn, e0, ne); }
          }
          __syncthreads();
-         if (a.mode & 1)
+         if ((a.mode & 1) && (a.mode & 4)) { vol3_apply<D1, Q, E, false>(U, R, sm, pre, tab); }
+         else if (a.mode & 1)
          {
             face3_apply<D1, Q, E>(sm, pre, tab);
             vol3_apply<D1, Q, E, true>(U, R, sm, pre, tab);
@@ -454,7 +465,10 @@ __device__ __forceinline__ double *ho_phases(const HoArgs &a, double *sm, int64_
       if (a.mode & 1)
       {
          vol_apply<DIM, D1, Q, E>(U, R, sm, a.Dvol + (size_t)e0 * DIM * NQ, ne, tab);
-         face_apply<DIM, D1, Q, E>(U, R, sm, a.u, a.Dface + (size_t)e0 * NF * NQF, a.fn, e0, ne, tab);
+         if (!(a.mode & 4))
+         {
+            face_apply<DIM, D1, Q, E>(U, R, sm, a.u, a.Dface + (size_t)e0 * NF * NQF, a.fn, e0, ne, tab);
+         }
       }
       else
       {
@@ -1089,6 +1103,15 @@ static int dispatch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    RMH_DISPATCH(launch_stagew, c, a, s);
 }
 
+static OpData op_data(const rmh_ctx *c)
+{
+   OpData o;
+   o.dim = c->dim; o.D1 = c->D1; o.Q = c->Q; o.frag = c->frag ? 1 : 0;
+   o.ND = c->ND; o.NQ = c->NQ; o.NF = c->NF; o.NFD = c->NFD; o.NQF = c->NQF;
+   o.Dvol = c->Dvol; o.Dface = c->Dface; o.detJw = c->detJw; o.B = c->dB; o.G = c->dG;
+   return o;
+}
+
 static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
 {
    GeomArgs g;
@@ -1115,6 +1138,18 @@ static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
    k_elem_affine<<<(unsigned)((c->ne * 32 + bs - 1) / bs), bs, 0, s>>>(
       c->dim, c->Q, c->NGN, c->exec_mode, t, c->ne, c->dw, c->detJw, c->X0, c->V, c->einv);
    LAUNCH_OK();
+   {
+      const OpData o = op_data(c);
+      const int64_t n = c->ne * c->NF * c->NFD;
+      k_face_lump<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(o, c->ne, c->BL);
+      LAUNCH_OK();
+      if (c->fa_on)
+      {
+         const size_t shb = (size_t)((c->dim + 1) * c->NQ + 2 * c->Q * c->D1) * sizeof(double);
+         k_fa_dense<<<(unsigned)c->ne, 256, shb, s>>>(o, c->ne, c->faK, c->faKH, c->faM, c->faBI);
+         LAUNCH_OK();
+      }
+   }
    c->t_cur = t;
    return 0;
 }
@@ -1189,6 +1224,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    const std::vector<double> ends = {0.0, 1.0};
    const std::vector<double> Ls = lagrange(gll, ends), dLs = lagrange_deriv(gll, ends);
    if (dev_upload(c, &c->dB, c->hB.data(), c->hB.size())) { return fail(); }
+   if (dev_upload(c, &c->dG, c->hG.data(), c->hG.size())) { return fail(); }
    if (dev_upload(c, &c->dw, c->hw.data(), c->hw.size())) { return fail(); }
    if (dev_upload(c, &c->dL, L.data(), L.size())) { return fail(); }
    if (dev_upload(c, &c->ddL, dL.data(), dL.size())) { return fail(); }
@@ -1277,6 +1313,42 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
          if (dev_upload(c, &c->nbr_pat32, pid32.data(), pid32.size())) { return fail(); }
       }
       if (dev_upload(c, &c->pat, patv.data(), patv.size())) { return fail(); }
+      // per pattern: the neighbour's local face and the natural index on it of every matched DOF
+      // (the reverse view the flux-based FCT needs for k_ji across a face)
+      const int np = (int)(patv.size() / NFD);
+      std::vector<uint8_t> pface(np, 0);
+      std::vector<int16_t> pidx(patv.size(), 0);
+      for (int id = 0; id < np; id++)
+      {
+         int found = -1;
+         for (int f2 = 0; f2 < NF && found < 0; f2++)
+         {
+            int axis, side;
+            face_axis(c->dim, f2, axis, side);
+            bool all = true;
+            for (int j = 0; j < NFD && all; j++)
+            {
+               int m = patv[(size_t)id * NFD + j], l[3] = {0, 0, 0};
+               for (int a = 0; a < c->dim; a++) { l[a] = m % c->D1; m /= c->D1; }
+               all = (l[axis] == side * c->p);
+            }
+            if (all) { found = f2; }
+         }
+         if (found < 0) { found = 0; }
+         pface[id] = (uint8_t)found;
+         int axis, side;
+         face_axis(c->dim, found, axis, side);
+         for (int j = 0; j < NFD; j++)
+         {
+            int m = patv[(size_t)id * NFD + j], l[3] = {0, 0, 0};
+            for (int a = 0; a < c->dim; a++) { l[a] = m % c->D1; m /= c->D1; }
+            int nat = 0, mul = 1;
+            for (int a = 0; a < c->dim; a++) { if (a != axis) { nat += l[a] * mul; mul *= c->D1; } }
+            pidx[(size_t)id * NFD + j] = (int16_t)nat;
+         }
+      }
+      if (dev_upload(c, &c->pat_face, pface.data(), pface.size())) { return fail(); }
+      if (dev_upload(c, &c->pat_idx, pidx.data(), pidx.size())) { return fail(); }
    }
    // ---- bounds structures
    const int64_t ne_all = c->ne + c->ne_ghost;
@@ -1319,6 +1391,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    CUDA_OK(cudaMemset(c->Dface, 0, n_dface * sizeof(double)));
    if (dev_alloc(c, &c->ml, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->einv, (size_t)c->ne)) { return fail(); }
+   if (dev_alloc(c, &c->BL, (size_t)c->ne * c->NF * c->NFD)) { return fail(); }
    if (dev_alloc(c, &c->w1, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->w2, (size_t)c->N)) { return fail(); }
    if (dev_alloc(c, &c->w3, (size_t)c->N)) { return fail(); }
@@ -1633,15 +1706,256 @@ extern "C" int rmh_rk_step_host(rmh_ctx *c, int ode, int lo_type, double *t, dou
    return 0;
 }
 
-extern "C" int rmh_lo_discrete_upwind(rmh_ctx *, const double *, double *, void *)
+// ---------------------------------------------------------------- matrix-based solver entry points
+static FaArgs fa_args(rmh_ctx *c)
 {
-   set_error("rmh_lo_discrete_upwind: not implemented yet");
+   FaArgs A;
+   A.ne = c->ne; A.dim = c->dim; A.D1 = c->D1; A.ND = c->ND; A.NF = c->NF; A.NFD = c->NFD;
+   A.fn.nbr_elem = c->nbr_elem; A.fn.nbr_pat = c->nbr_pat; A.fn.pat = c->pat;
+   A.fn.ughost = c->ughost; A.fn.ne_owned = c->ne;
+   A.pat_idx = c->pat_idx; A.pat_face = c->pat_face;
+   A.K = c->faK; A.KH = c->faKH; A.M = c->faM; A.BI = c->faBI; A.BL = c->BL; A.ml = c->ml;
+   A.inflow = c->inflow;
+   return A;
+}
+
+static int work_vec(rmh_ctx *c, double **slot)
+{
+   if (*slot) { return 0; }
+   return dev_alloc(c, slot, (size_t)c->N);
+}
+
+extern "C" int rmh_fa_setup(rmh_ctx *c, void *stream)
+{
+   if (c->fa_on) { return 0; }
+   const size_t nn = (size_t)c->ne * c->ND * c->ND;
+   if (dev_alloc(c, &c->faK, nn) || dev_alloc(c, &c->faKH, nn) || dev_alloc(c, &c->faM, nn) ||
+       dev_alloc(c, &c->faBI, (size_t)c->ne * c->NF * c->NFD * c->NFD)) { return 1; }
+   c->fa_on = true;
+   return run_geom(c, c->t_cur, (cudaStream_t)stream);
+}
+
+extern "C" int rmh_fa_get(rmh_ctx *c, int which, double *host_out)
+{
+   if (!c->fa_on && which != 4) { set_error("rmh_fa_get: call rmh_fa_setup first"); return 1; }
+   const size_t nn = (size_t)c->ne * c->ND * c->ND;
+   const double *src = nullptr;
+   size_t n = nn;
+   switch (which)
+   {
+      case 0: src = c->faK; break;
+      case 1: src = c->faKH; break;
+      case 2: src = c->faM; break;
+      case 3: src = c->faBI; n = (size_t)c->ne * c->NF * c->NFD * c->NFD; break;
+      case 4: src = c->BL; n = (size_t)c->ne * c->NF * c->NFD; break;
+      default: set_error("rmh_fa_get: which must be 0..4"); return 1;
+   }
+   CUDA_OK(cudaDeviceSynchronize());
+   CUDA_OK(cudaMemcpy(host_out, src, n * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+extern "C" int rmh_lo_discrete_upwind(rmh_ctx *c, const double *u, double *du_lo, void *stream)
+{
+   if (!c->fa_on) { set_error("rmh_lo_discrete_upwind: call rmh_fa_setup first (assembled K)"); return 1; }
+   const int bs = std::min(256, ((c->ND + 31) / 32) * 32);
+   k_lo_du<<<(unsigned)c->ne, bs, c->ND * sizeof(double), (cudaStream_t)stream>>>(fa_args(c), u, du_lo);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_lo_res_dist(rmh_ctx *c, const double *u, double *du_lo, void *stream)
+{
+   // z = K u with the volume-only convection operator (sum-factorised), then the element-local
+   // redistribution
+   if (work_vec(c, &c->wk[0])) { return 1; }
+   if (dispatch_ho(c, ho_args(c, u, c->wk[0], 1 | 4), (cudaStream_t)stream)) { return 1; }
+   const int bs = 256;
+   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
+   k_lo_rd<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(fa_args(c), u, c->wk[0], du_lo);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_fct_flux_based(rmh_ctx *c, double dt, const double *u, const double *m,
+                                  const double *du_ho, const double *du_lo, const double *xi_min,
+                                  const double *xi_max, double *du, void *stream)
+{
+   if (!c->fa_on) { set_error("rmh_fct_flux_based: call rmh_fa_setup first (assembled K_HO, M)"); return 1; }
+   if (c->ne_ghost > 0)
+   { set_error("rmh_fct_flux_based: decomposed meshes are not supported (needs ghost matrices)"); return 1; }
+   if (work_vec(c, &c->wk[1]) || work_vec(c, &c->wk[2])) { return 1; }
+   FaArgs A = fa_args(c);
+   A.ml = m;
+   cudaStream_t s = (cudaStream_t)stream;
+   const int bs = std::min(256, ((c->ND + 31) / 32) * 32);
+   const size_t shb = 2 * c->ND * sizeof(double);
+   k_flux_coeff<<<(unsigned)c->ne, bs, shb, s>>>(A, dt, u, du_ho, du_lo, xi_min, xi_max, c->wk[1], c->wk[2]);
+   LAUNCH_OK();
+   k_flux_apply<<<(unsigned)c->ne, bs, shb, s>>>(A, dt, u, du_ho, du_lo, c->wk[1], c->wk[2], du);
+   LAUNCH_OK();
+   return 0;
+}
+
+// LimitedTimeDependentOperator::Mult for any supported solver combination, from the separate
+// kernels (remhos.cpp:1596-1739 MultUnlimited, :1798-1916 LimitMult); the combination
+// -ho 3 -lo 5 -fct 2 goes to the fused stage kernel.
+extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t, double dt,
+                        const double *u, double *k, void *stream)
+{
+   cudaStream_t s = (cudaStream_t)stream;
+   if (ho_type != 0 && ho_type != 3)
+   { set_error("rmh_mult: HO solver must be 3 (LocalInverse) or 0"); return 1; }
+   if (lo_type < 0 || lo_type > 5 || lo_type == 4 || lo_type == 2)
+   { set_error("rmh_mult: LO solver must be 0, 1 (DiscreteUpwind), 3 (ResidualDistribution) or 5 (MassBasedAvg)"); return 1; }
+   if (fct_type < 0 || fct_type > 2) { set_error("rmh_mult: FCT solver must be 0, 1 (FluxBased) or 2 (ClipScale)"); return 1; }
+   if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
+   if (rmh_set_time(c, t, stream)) { return 1; }
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2)
+   { return stage_impl(c, 5, dt, 0, 0.0, 0.0, u, u, k, false, false, s); }
+   if (fct_type)
+   {
+      if (ho_type != 3 || lo_type == 0) { set_error("rmh_mult: FCT needs -ho 3 and an LO solver"); return 1; }
+      for (int i = 3; i < 7; i++) { if (work_vec(c, &c->wk[i])) { return 1; } }
+      double *du_ho = c->wk[3], *du_lo = c->wk[4], *xmn = c->wk[5], *xmx = c->wk[6];
+      if (rmh_ho_local_inverse(c, u, du_ho, stream)) { return 1; }
+      if (lo_type == 5) { if (rmh_lo_mass_avg(c, dt, u, du_ho, du_lo, stream)) { return 1; } }
+      else if (lo_type == 1) { if (rmh_lo_discrete_upwind(c, u, du_lo, stream)) { return 1; } }
+      else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
+      if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
+      if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
+      if (fct_type == 2) { return rmh_fct_clip_scale(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
+      return rmh_fct_flux_based(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream);
+   }
+   if (lo_type == 1) { return rmh_lo_discrete_upwind(c, u, k, stream); }
+   if (lo_type == 3) { return rmh_lo_res_dist(c, u, k, stream); }
+   if (lo_type == 5)
+   {
+      if (work_vec(c, &c->wk[3])) { return 1; }
+      if (rmh_ho_local_inverse(c, u, c->wk[3], stream)) { return 1; }
+      return rmh_lo_mass_avg(c, dt, u, c->wk[3], k, stream);
+   }
+   if (ho_type == 3) { return rmh_ho_local_inverse(c, u, k, stream); }
+   set_error("rmh_mult: no solver selected");
    return 1;
 }
-extern "C" int rmh_lo_res_dist(rmh_ctx *, const double *, double *, void *)
+
+static int lincomb(rmh_ctx *c, int n, const double *coef, const double *const *x, double *out,
+                   cudaStream_t s)
 {
-   set_error("rmh_lo_res_dist: not implemented yet");
-   return 1;
+   LinComb L;
+   L.n = 0;
+   for (int i = 0; i < n; i++)
+   {
+      if (coef[i] == 0.0) { continue; }
+      L.c[L.n] = coef[i]; L.x[L.n] = x[i]; L.n++;
+   }
+   const int bs = 256;
+   k_lincomb<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->N, L, out);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_lincomb(rmh_ctx *c, int n, const double *coef, const double *const *x_dev,
+                           double *out_dev, void *stream)
+{
+   if (n < 1 || n > 9) { set_error("rmh_lincomb: 1..9 terms"); return 1; }
+   return lincomb(c, n, coef, x_dev, out_dev, (cudaStream_t)stream);
+}
+
+// ODESolver::Step for -s 1/2/3/4/6 (remhos.cpp:488-492) over rmh_mult: explicit RK in Butcher
+// form.  Stage times t + c_i dt are pushed through rmh_set_time (remap); dt is the full step in
+// every stage, as the reference's operator keeps it (remhos.cpp:176-182).
+extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int fct_type, double *t,
+                            double dt, double *u, void *stream)
+{
+   cudaStream_t s = (cudaStream_t)stream;
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 && ode <= 3)
+   { return rmh_rk_step(c, ode, lo_type, t, dt, u, stream); }
+   const double t0 = *t;
+   const size_t bytes = (size_t)c->N * sizeof(double);
+   auto F = [&](const double *x, double tt, double *k) { return rmh_mult(c, ho_type, lo_type, fct_type, tt, dt, x, k, stream); };
+   for (int i = 0; i < 2; i++) { if (work_vec(c, &c->rk[i])) { return 1; } }
+   double *k0 = c->rk[0], *y = c->rk[1];
+   if (ode == 1)
+   {
+      if (F(u, t0, k0)) { return 1; }
+      const double cf[2] = {1.0, dt}; const double *xs[2] = {u, k0};
+      if (lincomb(c, 2, cf, xs, u, s)) { return 1; }
+   }
+   else if (ode == 2)       // RK2Solver(1.0): Heun
+   {
+      if (F(u, t0, k0)) { return 1; }
+      { const double cf[2] = {1.0, dt}; const double *xs[2] = {u, k0}; if (lincomb(c, 2, cf, xs, y, s)) { return 1; } }
+      { const double cf[2] = {1.0, 0.5 * dt}; const double *xs[2] = {u, k0}; if (lincomb(c, 2, cf, xs, u, s)) { return 1; } }
+      if (F(y, t0 + dt, k0)) { return 1; }
+      { const double cf[2] = {1.0, 0.5 * dt}; const double *xs[2] = {u, k0}; if (lincomb(c, 2, cf, xs, u, s)) { return 1; } }
+   }
+   else if (ode == 3)       // RK3SSPSolver
+   {
+      if (F(u, t0, k0)) { return 1; }
+      { const double cf[2] = {1.0, dt}; const double *xs[2] = {u, k0}; if (lincomb(c, 2, cf, xs, y, s)) { return 1; } }
+      if (F(y, t0 + dt, k0)) { return 1; }
+      { const double cf[3] = {0.75, 0.25, 0.25 * dt}; const double *xs[3] = {u, y, k0}; if (lincomb(c, 3, cf, xs, y, s)) { return 1; } }
+      if (F(y, t0 + dt / 2, k0)) { return 1; }
+      { const double cf[3] = {1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0 * dt}; const double *xs[3] = {u, y, k0}; if (lincomb(c, 3, cf, xs, u, s)) { return 1; } }
+   }
+   else if (ode == 4 || ode == 6)
+   {
+      // ExplicitRKSolver tables: classical RK4; RK6Solver = Verner's 8-stage 6th-order method
+      static const double a4[] = {0.5, 0.0, 0.5, 0.0, 0.0, 1.0};
+      static const double b4[] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+      static const double c4[] = {0.5, 0.5, 1.0};
+      static const double a6[] = {
+         .6e-1,
+         .1923996296296296296296296296296296296296e-1, .7669337037037037037037037037037037037037e-1,
+         .35975e-1, 0., .107925,
+         1.318683415233148260919747276431735612861, 0., -5.042058063628562225427761634715637693344,
+         4.220674648395413964508014358283902080483,
+         -41.87259166432751461803757780644346812905, 0., 159.4325621631374917700365669070346830453,
+         -122.1192135650100309202516203389242140663, 5.531743066200053768252631238332999150076,
+         -54.43015693531650433250642051294142461271, 0., 207.0672513650184644273657173866509835987,
+         -158.6108137845899991828742424365058599469, 6.991816585950242321992597280791793907096,
+         -.1859723106220323397765171799549294623692e-1,
+         -54.66374178728197680241215648050386959351, 0., 207.9528062553893734515824816699834244238,
+         -159.2889574744995071508959805871426654216, 7.018743740796944434698170760964252490817,
+         -.1833878590504572306472782005141738268361e-1, -.5119484997882099077875432497245168395840e-3};
+      static const double b6[] = {
+         .3438957868357036009278820124728322386520e-1, 0., 0.,
+         .2582624555633503404659558098586120858767, .4209371189673537150642551514069801967032,
+         4.405396469669310170148836816197095664891, -176.4831190242986576151740942499002125029,
+         172.3641334014150730294022582711902413315};
+      static const double c6[] = {.6e-1, .9593333333333333333333333333333333333333e-1, .1439, .4973,
+                                  .9725, .9995, 1.};
+      const int ns = (ode == 4) ? 4 : 8;
+      const double *a = (ode == 4) ? a4 : a6, *b = (ode == 4) ? b4 : b6, *cc = (ode == 4) ? c4 : c6;
+      for (int i = 0; i < ns + 1 && i < 9; i++) { if (work_vec(c, &c->rk[i])) { return 1; } }
+      // k_i in rk[0..ns-1]; y reuses wk[7]
+      if (work_vec(c, &c->wk[7])) { return 1; }
+      double *yy = c->wk[7];
+      if (F(u, t0, c->rk[0])) { return 1; }
+      for (int i = 1; i < ns; i++)
+      {
+         const double *ai = a + i * (i - 1) / 2;
+         double cf[9]; const double *xs[9];
+         cf[0] = 1.0; xs[0] = u;
+         for (int j = 0; j < i; j++) { cf[j + 1] = dt * ai[j]; xs[j + 1] = c->rk[j]; }
+         if (lincomb(c, i + 1, cf, xs, yy, s)) { return 1; }
+         if (F(yy, t0 + cc[i - 1] * dt, c->rk[i])) { return 1; }
+      }
+      double cf[9]; const double *xs[9];
+      cf[0] = 1.0; xs[0] = u;
+      for (int j = 0; j < ns; j++) { cf[j + 1] = dt * b[j]; xs[j + 1] = c->rk[j]; }
+      if (lincomb(c, ns + 1, cf, xs, u, s)) { return 1; }
+   }
+   else
+   {
+      set_error("rmh_ode_step: unknown ODE solver type (remhos.cpp:499-500 returns 3)");
+      return 3;
+   }
+   (void)bytes;
+   *t = t0 + dt;
+   return 0;
 }
 
 // ---------------------------------------------------------------- halo (multi-GPU) entry points

@@ -1,0 +1,391 @@
+// Matrix-based ("full assembly") solver kernels of the RK-stage path: the components the
+// reference runs from assembled element matrices (remhos.cpp:1088 -- FA only):
+//   DiscreteUpwind::CalcLOSolution              remhos_lo.cpp:43-100
+//   ResidualDistribution::CalcLOSolution        remhos_lo.cpp:111-245  (gamma-free variant, -lo 2/3)
+//   Assembly::LinearFluxLumping (alpha = 0)     remhos_tools.cpp:876-913
+//   FluxBasedFCT::CalcFCTSolution               remhos_fct.cpp:155-181, 295-446
+// Everything is generic in (dim, order): the element matrices are built from the same stored
+// quadrature data the sum-factorised kernels stream (Dvol, Dface, detJw), so transport and remap
+// share one code path.  These are the small-mesh paths; the fused stage kernels are the hot ones.
+#ifndef RMH_FA_CUH
+#define RMH_FA_CUH
+
+#include "kernels.cuh"
+
+namespace rmh
+{
+
+// read access to the stored quadrature data in either layout (see Pre3::load)
+struct OpData
+{
+   int dim, D1, Q, frag;
+   int ND, NQ, NF, NFD, NQF;
+   const double *Dvol, *Dface, *detJw;
+   const double *B, *G;          // device 1-D tables [Q][D1]
+   __device__ __forceinline__ double dvol(int64_t e, int c, int q) const
+   {
+      if (dim == 3 && frag)
+      {
+         const int RQ = (Q + 1) & ~1, QQ = Q * Q;
+         const int col = q % QQ, qz = q / QQ;
+         return Dvol[(size_t)e * QQ * RQ * 3 + ((size_t)col * RQ + qz) * 3 + c];
+      }
+      return Dvol[((size_t)e * dim + c) * NQ + q];
+   }
+   __device__ __forceinline__ double dface(int64_t e, int f, int qf) const
+   {
+      if (dim == 3)
+      {
+         const int qa = qf % Q, qb = qf / Q;
+         if (frag)
+         {
+            const int RQ = (Q + 1) & ~1;
+            return Dface[(size_t)e * NF * Q * RQ + ((size_t)f * Q + qa) * RQ + qb];
+         }
+         return Dface[(size_t)e * NF * NQF + (size_t)qb * NF * Q + f * Q + qa];
+      }
+      return Dface[((size_t)e * NF + f) * NQF + qf];
+   }
+};
+
+// lattice coordinates of local DOF i
+__device__ __forceinline__ void dof_lattice(int dim, int D1, int i, int (&l)[3])
+{
+   l[0] = l[1] = l[2] = 0;
+   for (int a = 0; a < dim; a++) { l[a] = i % D1; i /= D1; }
+}
+// natural face index of a DOF with lattice coordinates l on a face normal to `axis`
+__device__ __forceinline__ int face_nat_index(int dim, int D1, const int (&l)[3], int axis)
+{
+   int j = 0, mul = 1;
+   for (int b = 0; b < dim; b++)
+   {
+      if (b == axis) { continue; }
+      j += l[b] * mul; mul *= D1;
+   }
+   return j;
+}
+// local DOF of natural face DOF j on face f (runtime version of face_dof<>)
+__device__ __forceinline__ int face_dof_rt(int dim, int D1, int f, int j)
+{
+   int axis, side;
+   face_axis_side(dim, f, axis, side);
+   int l[3] = {0, 0, 0};
+   for (int a = 0; a < dim; a++)
+   {
+      if (a == axis) { l[a] = side * (D1 - 1); }
+      else { l[a] = j % D1; j /= D1; }
+   }
+   return l[0] + D1 * (l[1] + D1 * l[2]);
+}
+// value of the tensor face basis function a at face quadrature point qf
+__device__ __forceinline__ double face_phi(const OpData &o, int a, int qf)
+{
+   double v = 1.0;
+   for (int b = 0; b < o.dim - 1; b++)
+   {
+      v *= o.B[(qf % o.Q) * o.D1 + (a % o.D1)];
+      qf /= o.Q; a /= o.D1;
+   }
+   return v;
+}
+
+// BL[e][f][a] = sum_b bdrInt(a,b) = -sum_q Dface_q phi_a(q): the fully lumped face matrix of
+// LinearFluxLumping with alpha = 0 (remhos_tools.cpp:833-857, 897-910; partition of unity)
+__global__ void k_face_lump(OpData o, int64_t ne, double *BL)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * o.NF * o.NFD) { return; }
+   const int64_t e = idx / (o.NF * o.NFD);
+   const int r = (int)(idx - e * o.NF * o.NFD), f = r / o.NFD, a = r - f * o.NFD;
+   double s = 0.0;
+   for (int qf = 0; qf < o.NQF; qf++) { s += o.dface(e, f, qf) * face_phi(o, a, qf); }
+   BL[idx] = -s;
+}
+
+// Dense element matrices (one block per element):
+//   K  [e][i][j] = sum_q phi_i (D . grad phi_j)      ConvectionIntegrator block (remhos.cpp:646-657)
+//   M  [e][i][j] = sum_q detJw phi_i phi_j           MassIntegrator block
+//   BI [e][f][a][b] = -sum_q Dface phi_a phi_b       bdrInt (remhos_tools.cpp:788-858)
+//   KH = K - sum_f scatter(BI_f): the diagonal block of K_HO (volume + own-side face terms)
+__global__ void k_fa_dense(OpData o, int64_t ne, double *K, double *KH, double *M, double *BI)
+{
+   extern __shared__ double sh[];
+   const int64_t e = blockIdx.x;
+   const int ND = o.ND, NQ = o.NQ, dim = o.dim, D1 = o.D1, Q = o.Q;
+   double *dv = sh;                       // [dim][NQ]
+   double *dj = dv + dim * NQ;            // [NQ]
+   double *tB = dj + NQ, *tG = tB + Q * D1;
+   for (int t = threadIdx.x; t < dim * NQ; t += blockDim.x) { dv[t] = o.dvol(e, t / NQ, t % NQ); }
+   for (int t = threadIdx.x; t < NQ; t += blockDim.x) { dj[t] = o.detJw[(size_t)e * NQ + t]; }
+   for (int t = threadIdx.x; t < Q * D1; t += blockDim.x) { tB[t] = o.B[t]; tG[t] = o.G[t]; }
+   __syncthreads();
+   for (int ij = threadIdx.x; ij < ND * ND; ij += blockDim.x)
+   {
+      const int i = ij / ND, j = ij - i * ND;
+      int li[3], lj[3];
+      dof_lattice(dim, D1, i, li);
+      dof_lattice(dim, D1, j, lj);
+      double k = 0.0, m = 0.0;
+      for (int q = 0; q < NQ; q++)
+      {
+         int qa[3] = {0, 0, 0}, r = q;
+         for (int a = 0; a < dim; a++) { qa[a] = r % Q; r /= Q; }
+         double pi = 1.0, pj = 1.0;
+         for (int a = 0; a < dim; a++) { pi *= tB[qa[a] * D1 + li[a]]; pj *= tB[qa[a] * D1 + lj[a]]; }
+         double g = 0.0;
+         for (int c = 0; c < dim; c++)
+         {
+            double d = 1.0;
+            for (int a = 0; a < dim; a++) { d *= (a == c) ? tG[qa[a] * D1 + lj[a]] : tB[qa[a] * D1 + lj[a]]; }
+            g += dv[c * NQ + q] * d;
+         }
+         k += pi * g;
+         m += (pi * pj) * dj[q];
+      }
+      K[(size_t)e * ND * ND + ij] = k;
+      KH[(size_t)e * ND * ND + ij] = k;
+      M[(size_t)e * ND * ND + ij] = m;
+   }
+   const int NFD = o.NFD, NF = o.NF;
+   for (int t = threadIdx.x; t < NF * NFD * NFD; t += blockDim.x)
+   {
+      const int f = t / (NFD * NFD), r = t - f * NFD * NFD, a = r / NFD, b = r - a * NFD;
+      double s = 0.0;
+      for (int qf = 0; qf < o.NQF; qf++) { s += o.dface(e, f, qf) * (face_phi(o, a, qf) * face_phi(o, b, qf)); }
+      BI[(size_t)e * NF * NFD * NFD + t] = -s;
+   }
+   __syncthreads();
+   // own-side face blocks into KH (a DOF pair can share several faces: serial over faces)
+   for (int f = 0; f < NF; f++)
+   {
+      for (int t = threadIdx.x; t < NFD * NFD; t += blockDim.x)
+      {
+         const int a = t / NFD, b = t - a * NFD;
+         const int i = face_dof_rt(dim, D1, f, a), j = face_dof_rt(dim, D1, f, b);
+         KH[(size_t)e * ND * ND + i * ND + j] -= BI[((size_t)e * NF + f) * NFD * NFD + t];
+      }
+      __syncthreads();
+   }
+}
+
+struct FaArgs
+{
+   int64_t ne;
+   int dim, D1, ND, NF, NFD;
+   FaceNbr fn;
+   const int16_t *pat_idx;    // [npat][NFD] natural index, on the neighbour's face, of pat[id][j]
+   const uint8_t *pat_face;   // [npat] the neighbour's local face
+   const double *K, *KH, *M, *BI, *BL, *ml, *inflow;
+};
+
+// exterior state seen by face DOF (f, a) of element e: the neighbour's value, or `bval` on the
+// domain boundary
+__device__ __forceinline__ double nbr_value(const FaArgs &A, const double *u, int64_t e, int f,
+                                            int a, double bval, int64_t *gj = nullptr)
+{
+   const int64_t nb = A.fn.nbr_elem[e * A.NF + f];
+   if (nb < 0) { if (gj) { *gj = -1; } return bval; }
+   const int loc = A.fn.pat[(int)A.fn.nbr_pat[e * A.NF + f] * A.NFD + a];
+   if (gj) { *gj = nb * A.ND + loc; }
+   return (nb < A.fn.ne_owned) ? u[nb * A.ND + loc] : A.fn.ughost[(nb - A.fn.ne_owned) * A.ND + loc];
+}
+
+// sum over the faces containing DOF i of BL (u_nbr - u_own)   (LinearFluxLumping, alpha = 0)
+__device__ __forceinline__ double lumped_faces(const FaArgs &A, const double *u, int64_t e, int i,
+                                               double ui)
+{
+   int l[3];
+   dof_lattice(A.dim, A.D1, i, l);
+   const double infl = A.inflow ? A.inflow[e * A.ND + i] : 0.0;
+   double s = 0.0;
+   for (int ax = 0; ax < A.dim; ax++)
+   {
+      for (int side = 0; side < 2; side++)
+      {
+         if (l[ax] != side * (A.D1 - 1)) { continue; }
+         const int f = face_of(A.dim, ax, side);
+         const int a = face_nat_index(A.dim, A.D1, l, ax);
+         const double un = nbr_value(A, u, e, f, a, infl);
+         s += A.BL[(e * A.NF + f) * A.NFD + a] * (un - ui);
+      }
+   }
+   return s;
+}
+
+// DiscreteUpwind: du = (D u + lumped faces) / m with D = K + d, d_ij = max(0, -k_ij, -k_ji),
+// D_ii = K_ii - sum_{j != i} d_ij  (remhos_lo.cpp:43-100; remhos_tools.cpp:1464-1487)
+__global__ void k_lo_du(FaArgs A, const double *u, double *du)
+{
+   extern __shared__ double sh[];
+   const int64_t e = blockIdx.x;
+   const int ND = A.ND;
+   for (int t = threadIdx.x; t < ND; t += blockDim.x) { sh[t] = u[e * ND + t]; }
+   __syncthreads();
+   const double *Ke = A.K + (size_t)e * ND * ND;
+   for (int i = threadIdx.x; i < ND; i += blockDim.x)
+   {
+      const double ui = sh[i];
+      double s = 0.0;
+      for (int j = 0; j < ND; j++)
+      {
+         const double kij = Ke[i * ND + j];
+         s += kij * sh[j];
+         if (j != i)
+         {
+            const double dij = fmax(fmax(0.0, -kij), -Ke[j * ND + i]);
+            s += dij * (sh[j] - ui);
+         }
+      }
+      s += lumped_faces(A, u, e, i, ui);
+      du[e * ND + i] = s / A.ml[e * ND + i];
+   }
+}
+
+// ResidualDistribution without subcells (remhos_lo.cpp:111-245 with subcell_scheme = false):
+// z = K u given; du = (faces + w+ rho+ + w- rho-) / m.  One warp per element.
+__global__ void k_lo_rd(FaArgs A, const double *u, const double *z, double *du)
+{
+   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (e >= A.ne) { return; }
+   const int ND = A.ND;
+   double xmax = -INFINITY, xmin = INFINITY, xsum = 0.0, rhoP = 0.0, rhoN = 0.0;
+   for (int j = lane; j < ND; j += 32)
+   {
+      const double v = u[e * ND + j], zz = z[e * ND + j];
+      xmax = fmax(xmax, v); xmin = fmin(xmin, v); xsum += v;
+      rhoP += fmax(0.0, zz); rhoN += fmin(0.0, zz);
+   }
+   xmax = warp_max(xmax); xmin = warp_min(xmin);
+   xsum = warp_sum(xsum); rhoP = warp_sum(rhoP); rhoN = warp_sum(rhoN);
+   constexpr double eps = 1.0e-15;
+   const double sumWP = ND * xmax - xsum + eps, sumWN = ND * xmin - xsum - eps;
+   for (int j = lane; j < ND; j += 32)
+   {
+      const double ui = u[e * ND + j];
+      const double wP = (xmax - ui) / sumWP, wN = (xmin - ui) / sumWN;
+      const double s = lumped_faces(A, u, e, j, ui) + wP * rhoP + wN * rhoN;
+      du[e * ND + j] = s / A.ml[e * ND + j];
+   }
+}
+
+// ---- FluxBasedFCT (Zalesak), gather form: every DOF visits all its couplings of K_HO
+// (in-element via KH / M, across faces via BI of both sides); each flux is evaluated from both
+// ends with the same operands in the same order, so f_ji = -f_ij bit for bit.
+template <typename Visit>
+__device__ __forceinline__ void flux_visit(const FaArgs &A, const double *u, const double *du_ho,
+                                           double dt, int64_t e, int i, const double *ue,
+                                           const double *dhe, Visit visit)
+{
+   const int ND = A.ND, NFD = A.NFD, NF = A.NF;
+   const double *KHe = A.KH + (size_t)e * ND * ND, *Me = A.M + (size_t)e * ND * ND;
+   const double ui = ue[i], di = dhe[i];
+   for (int j = 0; j < ND; j++)
+   {
+      if (j == i) { continue; }
+      const double kij = KHe[i * ND + j], kji = KHe[j * ND + i];
+      const double dij = fmax(fmax(0.0, -kij), -kji);
+      // remhos_fct.cpp:313-318 + 334-338: dt d_ij (u_i - u_j) + dt M_ij (du_i - du_j)
+      const double f = dt * dij * (ui - ue[j]) + Me[i * ND + j] * dt * (di - dhe[j]);
+      visit(e * ND + j, f);
+   }
+   int l[3];
+   dof_lattice(A.dim, A.D1, i, l);
+   for (int ax = 0; ax < A.dim; ax++)
+   {
+      for (int side = 0; side < 2; side++)
+      {
+         if (l[ax] != side * (A.D1 - 1)) { continue; }
+         const int f = face_of(A.dim, ax, side);
+         const int64_t nb = A.fn.nbr_elem[e * NF + f];
+         if (nb < 0) { continue; }
+         const int a = face_nat_index(A.dim, A.D1, l, ax);
+         const int pid = A.fn.nbr_pat[e * NF + f];
+         const int f2 = A.pat_face[pid];
+         const int a2 = A.pat_idx[pid * NFD + a];
+         const double *BIe = A.BI + ((size_t)e * NF + f) * NFD * NFD;
+         const double *BIn = A.BI + ((size_t)nb * NF + f2) * NFD * NFD;
+         for (int b = 0; b < NFD; b++)
+         {
+            const int b2 = A.pat_idx[pid * NFD + b];
+            const int64_t gj = nb * ND + A.fn.pat[pid * NFD + b];
+            const double kij = BIe[a * NFD + b], kji = BIn[b2 * NFD + a2];
+            const double dij = fmax(fmax(0.0, -kij), -kji);
+            visit(gj, dt * dij * (ui - u[gj]));
+         }
+      }
+   }
+}
+
+// AddFluxesAtDofs + ComputeFluxCoefficients (remhos_fct.cpp:344-399): block per element
+__global__ void k_flux_coeff(FaArgs A, double dt, const double *u, const double *du_ho,
+                             const double *du_lo, const double *umin, const double *umax,
+                             double *cp, double *cn)
+{
+   extern __shared__ double sh[];
+   const int64_t e = blockIdx.x;
+   const int ND = A.ND;
+   double *ue = sh, *dhe = sh + ND;
+   for (int t = threadIdx.x; t < ND; t += blockDim.x) { ue[t] = u[e * ND + t]; dhe[t] = du_ho[e * ND + t]; }
+   __syncthreads();
+   for (int i = threadIdx.x; i < ND; i += blockDim.x)
+   {
+      double gp = 0.0, gm = 0.0;
+      flux_visit(A, u, du_ho, dt, e, i, ue, dhe, [&](int64_t, double f)
+      {
+         if (f >= 0.0) { gp += f; } else { gm += f; }
+      });
+      const int64_t g = e * ND + i;
+      const double m = A.ml[g];
+      const double u_lo = ue[i] + dt * du_lo[g];
+      const double max_pos = fmax((umax[g] - u_lo) * m, 0.0);
+      const double min_neg = fmin((umin[g] - u_lo) * m, 0.0);
+      cp[g] = (gp > max_pos) ? max_pos / gp : 1.0;
+      cn[g] = (gm < min_neg) ? min_neg / gm : 1.0;
+   }
+}
+
+// UpdateSolutionAndFlux (remhos_fct.cpp:401-446), single FCT iteration
+__global__ void k_flux_apply(FaArgs A, double dt, const double *u, const double *du_ho,
+                             const double *du_lo, const double *cp, const double *cn, double *du)
+{
+   extern __shared__ double sh[];
+   const int64_t e = blockIdx.x;
+   const int ND = A.ND;
+   double *ue = sh, *dhe = sh + ND;
+   for (int t = threadIdx.x; t < ND; t += blockDim.x) { ue[t] = u[e * ND + t]; dhe[t] = du_ho[e * ND + t]; }
+   __syncthreads();
+   for (int i = threadIdx.x; i < ND; i += blockDim.x)
+   {
+      const int64_t g = e * ND + i;
+      const double cpi = cp[g], cni = cn[g];
+      double s = 0.0;
+      flux_visit(A, u, du_ho, dt, e, i, ue, dhe, [&](int64_t gj, double f)
+      {
+         const double a = (f >= 0.0) ? fmin(cpi, cn[gj]) : fmin(cni, cp[gj]);
+         s += f * a;
+      });
+      du[g] = du_lo[g] + s / A.ml[g] / dt;
+   }
+}
+
+// out = sum_k c[k] * x[k]   (general explicit RK combinations; up to 9 terms)
+struct LinComb
+{
+   int n;
+   double c[9];
+   const double *x[9];
+};
+__global__ void k_lincomb(int64_t N, LinComb L, double *out)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= N) { return; }
+   double s = 0.0;
+   for (int k = 0; k < L.n; k++) { s += L.c[k] * L.x[k][i]; }
+   out[i] = s;
+}
+
+} // namespace rmh
+
+#endif

@@ -34,6 +34,8 @@ BASELINE = [
                                 lo_type=3, fct_type=2), 0.9607429525, 0.9202929163),     # :103-106
     ('periodic-square.mesh', dict(problem=5, rs_levels=3, dt=0.004, t_final=0.8, ho_type=3,
                                   lo_type=3, fct_type=2), 0.1623263888, 0.6374820899),   # :98-101
+    ('periodic-square.mesh', dict(problem=5, rs_levels=3, dt=0.004, t_final=0.8, ho_type=3,
+                                  lo_type=1, fct_type=1), 0.1623263888, 0.787875182),    # :172-175
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
                               lo_type=1, fct_type=1), 0.08479546845, 0.905654904),       # :152-155
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
@@ -42,7 +44,7 @@ BASELINE = [
 
 
 @pytest.mark.parametrize('mesh,opt,mass,umax', BASELINE,
-                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale',
+                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT',
                               'quad-remap-DU-fluxFCT', 'quad-remap-RD-clipscale'])
 def test_autotest_baseline(mesh, opt, mass, umax):
     r = run(mesh, **opt)
@@ -70,15 +72,6 @@ def test_remhos_tests_final_mass(mesh, opt, mass):
     assert abs(r.mass0 - r.final_mass) > 1e-10
 
 
-def test_known_unmatched_row_is_documented():
-    """autotest/out_baseline.dat:172-175 (periodic-square, -ho 3 -lo 1 -fct 1) is the one row tried
-    that the oracle does not reproduce (max 0.7879213622 vs 0.787875182); every component of that
-    combination is pinned by other rows.  Keep the discrepancy visible (DESIGN.md 'Oracle')."""
-    r = run('periodic-square.mesh', problem=5, rs_levels=3, dt=0.004, t_final=0.8, ho_type=3,
-            lo_type=1, fct_type=1, max_steps=30)
-    assert digits10(r.final_mass) == 0.1623263888
-
-
 @pytest.mark.skipif(not os.path.isdir(REF_DATA), reason='reference tree not mounted')
 @pytest.mark.parametrize('name', ['periodic-square', 'periodic-cube', 'cube01_hex', 'inline-quad'])
 def test_generated_meshes_equal_reference_meshes(name):
@@ -87,3 +80,31 @@ def test_generated_meshes_equal_reference_meshes(name):
     sa = sorted(map(tuple, a.X.reshape(a.ne, -1).tolist()))
     sb = sorted(map(tuple, b.X.reshape(b.ne, -1).tolist()))
     assert sa == sb
+
+
+def test_rk6_tableau():
+    """MFEM's RK6Solver coefficients are restated in the oracle (and in rmh_ode_step); check them
+    against the Runge-Kutta order conditions they must satisfy and the observed order."""
+    from remhos_oracle.driver import RK6_A, RK6_B, RK6_C
+    A = np.zeros((8, 8))
+    for i in range(1, 8):
+        A[i, :i] = RK6_A[i * (i - 1) // 2:i * (i + 1) // 2]
+    b = np.array(RK6_B); c = np.array([0.0] + RK6_C)
+    assert np.abs(A.sum(axis=1) - c).max() < 1e-12
+    for k in range(6):
+        assert abs(b @ c ** k - 1.0 / (k + 1)) < 1e-12
+    assert abs(b @ A @ c - 1.0 / 6) < 1e-11 and abs(b @ (c * (A @ c)) - 1.0 / 8) < 1e-11
+
+    def step(y, t, dt):
+        ks = []
+        for i in range(8):
+            yy = y + dt * sum(A[i, j] * ks[j] for j in range(i))
+            ks.append(yy * np.cos(t + c[i] * dt))
+        return y + dt * sum(b[j] * ks[j] for j in range(8))
+    errs = []
+    for n in (4, 8, 16):
+        y, t, dt = 1.0, 0.0, 2.0 / n
+        for _ in range(n):
+            y = step(y, t, dt); t += dt
+        errs.append(abs(y - np.exp(np.sin(2.0))))
+    assert np.log2(errs[0] / errs[1]) > 5.5 and np.log2(errs[1] / errs[2]) > 5.5
