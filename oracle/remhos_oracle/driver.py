@@ -35,6 +35,16 @@ RK6_B = [
     .2582624555633503404659558098586120858767, .4209371189673537150642551514069801967032,
     4.405396469669310170148836816197095664891, -176.4831190242986576151740942499002125029,
     172.3641334014150730294022582711902413315]
+# RKIDPSolver tables (remhos_solvers.cpp:252-279)
+IDP_TABLES = {
+    12: ([.5], [0., 1.], [.5]),
+    13: ([1. / 3., 0., 2. / 3.], [.25, 0., .75], [1. / 3., 2. / 3.]),
+    14: ([1. / 3., -1. / 3., 1., 1., -1., 1.], [1. / 8., 3. / 8., 3. / 8., 1. / 8.],
+         [1. / 3., 2. / 3., 1.]),
+    16: ([.25, 1. / 8., 1. / 8., 0., -.5, 1., 3. / 16., 0., 0., 9. / 16., -3. / 7., 2. / 7.,
+          12. / 7., -12. / 7., 8. / 7.], [7. / 90., 0., 32. / 90., 12. / 90., 32. / 90., 7. / 90.],
+         [.25, .25, .5, .75, 1.]),
+}
 RK6_C = [.6e-1, .9593333333333333333333333333333333333333e-1, .1439, .4973, .9725, .9995, 1.]
 
 
@@ -146,6 +156,91 @@ class Run:
             return self.calc_lo(u, None, dt)
         return d.ho_local_inverse(u)
 
+    def mult_unlimited(self, u, t, dt):
+        """AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739)."""
+        o, d = self.opt, self.disc
+        if self.exec_mode == 1:
+            d.assemble(t)
+        if o.fct_type:
+            return d.ho_local_inverse(u)
+        if o.lo_type:
+            return self.calc_lo(u, None, dt)
+        return d.ho_local_inverse(u)
+
+    def limit_mult(self, u, du_ho, dt):
+        """AdvectionOperator::LimitMult (remhos.cpp:1798-1916): du_ho is the (combined) HO rate."""
+        o, d = self.opt, self.disc
+        if not o.fct_type:
+            return du_ho
+        A = d.cur
+        du_lo = self.calc_lo(u, du_ho, dt)
+        umin, umax = d.bounds(u, o.bounds_type)
+        if o.fct_type == 2:
+            return d.fct_clip_scale(u, A.ml, du_ho, du_lo, umin, umax, dt)
+        return d.fct_flux_based(u, A.ml, du_ho, du_lo, umin, umax, dt)
+
+    def idp_step(self, u, t, dt):
+        """ForwardEulerIDPSolver / RKIDPSolver::Step with masks off (remhos_solvers.cpp:29-38,
+        40-95, 171-249; tables :252-279; remhos.cpp:502-507)."""
+        s = self.opt.ode_solver
+        if s == 11:
+            k = self.limit_mult(u, self.mult_unlimited(u, t, dt), dt)
+            return u + dt * k
+        a, b, c = IDP_TABLES[s]
+        ns = len(b)
+        # ConstructD
+        d = np.zeros(ns * (ns + 1) // 2)
+        an, ao, i_o, c_o = 0, 0, -1, 0.0           # offsets into `a` (an == -1: use b)
+        row = lambda off: (b if off < 0 else a[off:])
+        for i in range(ns):
+            c_n = c[i] if i < ns - 1 else 1.0
+            dc = c_n - c_o
+            di = i * (i + 1) // 2
+            for j in range(i):
+                a_oj = row(ao)[j] if j <= i_o else 0.0
+                m = (row(an)[j] - a_oj) / dc
+                if m == 0.0:
+                    d[di + j] = 0.0
+                    continue
+                dj = j * (j + 1) // 2
+                dij = m / d[dj + j]
+                for k in range(j):
+                    d[di + k] -= d[dj + k] * dij
+                d[di + j] = dij
+            d[di + i] = row(an)[i] / dc
+            c_next = c[i + 1] if i < ns - 2 else 1.0
+            if c_next > c_n:
+                i_o, c_o, ao = i, c_n, an
+            if i < ns - 2:
+                an += i + 1
+            else:
+                an = -1
+        # Step
+        x = u.copy()
+        ks = [None] * ns
+        c_o = 0.0
+        tcur = t
+        ks[0] = self.limit_mult(x, self.mult_unlimited(x, tcur, c[0] * dt), c[0] * dt)
+        c_next = c[1] if ns > 2 else 1.0
+        if c_next > c[0]:
+            x = x + c[0] * dt * ks[0]
+            tcur = t + c[0] * dt
+            c_o = c[0]
+        for i in range(1, ns):
+            c_n = c[i] if i < ns - 1 else 1.0
+            dct = (c_n - c_o) * dt
+            di = i * (i + 1) // 2
+            k = self.mult_unlimited(x, tcur, dct) * d[di + i]
+            for j in range(i):
+                k = k + d[di + j] * ks[j]
+            ks[i] = self.limit_mult(x, k, dct)
+            c_next = c[i + 1] if i < ns - 2 else 1.0
+            if i == ns - 1 or c_next > c_n:
+                tcur = t + c_n * dt
+                x = x + dct * ks[i]
+                c_o = c_n
+        return x
+
     def calc_lo(self, u, du_ho, dt):
         o, d = self.opt, self.disc
         if o.lo_type == 5:
@@ -177,6 +272,8 @@ class Run:
     def step(self, u, t, dt):
         s = self.opt.ode_solver
         f = self.mult
+        if s in (11, 12, 13, 14, 16):
+            return self.idp_step(u, t, dt)
         if s == 1:
             k = f(u, t, dt)
             return u + dt * k

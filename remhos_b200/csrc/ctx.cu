@@ -1797,36 +1797,31 @@ extern "C" int rmh_fct_flux_based(rmh_ctx *c, double dt, const double *u, const 
    return 0;
 }
 
-// LimitedTimeDependentOperator::Mult for any supported solver combination, from the separate
-// kernels (remhos.cpp:1596-1739 MultUnlimited, :1798-1916 LimitMult); the combination
-// -ho 3 -lo 5 -fct 2 goes to the fused stage kernel.
-extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t, double dt,
-                        const double *u, double *k, void *stream)
+static int check_combo(int ho_type, int lo_type, int fct_type)
 {
-   cudaStream_t s = (cudaStream_t)stream;
    if (ho_type != 0 && ho_type != 3)
-   { set_error("rmh_mult: HO solver must be 3 (LocalInverse) or 0"); return 1; }
+   { set_error("stage operator: HO solver must be 3 (LocalInverse) or 0"); return 1; }
    if (lo_type < 0 || lo_type > 5 || lo_type == 4 || lo_type == 2)
-   { set_error("rmh_mult: LO solver must be 0, 1 (DiscreteUpwind), 3 (ResidualDistribution) or 5 (MassBasedAvg)"); return 1; }
-   if (fct_type < 0 || fct_type > 2) { set_error("rmh_mult: FCT solver must be 0, 1 (FluxBased) or 2 (ClipScale)"); return 1; }
-   if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
+   { set_error("stage operator: LO solver must be 0, 1 (DiscreteUpwind), 3 (ResidualDistribution) or 5 (MassBasedAvg)"); return 1; }
+   if (fct_type < 0 || fct_type > 2)
+   { set_error("stage operator: FCT solver must be 0, 1 (FluxBased) or 2 (ClipScale)"); return 1; }
+   if (fct_type && (ho_type != 3 || lo_type == 0))
+   { set_error("FCT requires HO and LO solvers."); return 1; }        // remhos.cpp:1690
+   if (!fct_type && lo_type == 5 && ho_type != 3)
+   { set_error("Mass-Based LO solver requires a choice of a HO solver."); return 1; }   // remhos.cpp:991
+   if (!ho_type && !lo_type) { set_error("No solver was chosen."); return 1; }          // remhos.cpp:1711
+   return 0;
+}
+
+// AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739): remap re-assembly at time t, then the
+// HO rate when an FCT solver will limit it later, else the LO or HO rate.
+extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t,
+                                  double dt, const double *u, double *k, void *stream)
+{
+   if (check_combo(ho_type, lo_type, fct_type)) { return 1; }
+   if (k == u) { set_error("rmh_mult_unlimited: output must not alias the input"); return 1; }
    if (rmh_set_time(c, t, stream)) { return 1; }
-   if (ho_type == 3 && lo_type == 5 && fct_type == 2)
-   { return stage_impl(c, 5, dt, 0, 0.0, 0.0, u, u, k, false, false, s); }
-   if (fct_type)
-   {
-      if (ho_type != 3 || lo_type == 0) { set_error("rmh_mult: FCT needs -ho 3 and an LO solver"); return 1; }
-      for (int i = 3; i < 7; i++) { if (work_vec(c, &c->wk[i])) { return 1; } }
-      double *du_ho = c->wk[3], *du_lo = c->wk[4], *xmn = c->wk[5], *xmx = c->wk[6];
-      if (rmh_ho_local_inverse(c, u, du_ho, stream)) { return 1; }
-      if (lo_type == 5) { if (rmh_lo_mass_avg(c, dt, u, du_ho, du_lo, stream)) { return 1; } }
-      else if (lo_type == 1) { if (rmh_lo_discrete_upwind(c, u, du_lo, stream)) { return 1; } }
-      else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
-      if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
-      if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
-      if (fct_type == 2) { return rmh_fct_clip_scale(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
-      return rmh_fct_flux_based(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream);
-   }
+   if (fct_type) { return rmh_ho_local_inverse(c, u, k, stream); }
    if (lo_type == 1) { return rmh_lo_discrete_upwind(c, u, k, stream); }
    if (lo_type == 3) { return rmh_lo_res_dist(c, u, k, stream); }
    if (lo_type == 5)
@@ -1835,9 +1830,42 @@ extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, doub
       if (rmh_ho_local_inverse(c, u, c->wk[3], stream)) { return 1; }
       return rmh_lo_mass_avg(c, dt, u, c->wk[3], k, stream);
    }
-   if (ho_type == 3) { return rmh_ho_local_inverse(c, u, k, stream); }
-   set_error("rmh_mult: no solver selected");
-   return 1;
+   return rmh_ho_local_inverse(c, u, k, stream);
+}
+
+// AdvectionOperator::LimitMult (remhos.cpp:1798-1916): k holds the (possibly combined) HO rate
+// on entry and the limited rate on exit; a no-op without an FCT solver.
+extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u,
+                              double *k, void *stream)
+{
+   if (!fct_type) { return 0; }
+   if (check_combo(3, lo_type, fct_type)) { return 1; }
+   for (int i = 3; i < 7; i++) { if (work_vec(c, &c->wk[i])) { return 1; } }
+   double *du_ho = c->wk[3], *du_lo = c->wk[4], *xmn = c->wk[5], *xmx = c->wk[6];
+   CUDA_OK(cudaMemcpyAsync(du_ho, k, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+   if (lo_type == 5) { if (rmh_lo_mass_avg(c, dt, u, du_ho, du_lo, stream)) { return 1; } }
+   else if (lo_type == 1) { if (rmh_lo_discrete_upwind(c, u, du_lo, stream)) { return 1; } }
+   else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
+   if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
+   if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
+   if (fct_type == 2) { return rmh_fct_clip_scale(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
+   return rmh_fct_flux_based(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream);
+}
+
+// LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult (remhos_solvers.hpp:46-50);
+// the combination -ho 3 -lo 5 -fct 2 goes to the fused stage kernel.
+extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t, double dt,
+                        const double *u, double *k, void *stream)
+{
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2)
+   {
+      if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
+      if (rmh_set_time(c, t, stream)) { return 1; }
+      return stage_impl(c, 5, dt, 0, 0.0, 0.0, u, u, k, false, false, (cudaStream_t)stream);
+   }
+   if (rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t, dt, u, k, stream)) { return 1; }
+   return rmh_limit_mult(c, lo_type, fct_type, dt, u, k, stream);
 }
 
 static int lincomb(rmh_ctx *c, int n, const double *coef, const double *const *x, double *out,
@@ -1947,6 +1975,95 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
       cf[0] = 1.0; xs[0] = u;
       for (int j = 0; j < ns; j++) { cf[j + 1] = dt * b[j]; xs[j + 1] = c->rk[j]; }
       if (lincomb(c, ns + 1, cf, xs, u, s)) { return 1; }
+   }
+   else if (ode == 11)      // ForwardEulerIDPSolver (remhos_solvers.cpp:29-38)
+   {
+      if (rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t0, dt, u, k0, stream)) { return 1; }
+      if (rmh_limit_mult(c, lo_type, fct_type, dt, u, k0, stream)) { return 1; }
+      const double cf[2] = {1.0, dt}; const double *xs[2] = {u, k0};
+      if (lincomb(c, 2, cf, xs, u, s)) { return 1; }
+   }
+   else if (ode == 12 || ode == 13 || ode == 14 || ode == 16)
+   {
+      // RKIDPSolver::Step without masks (remhos_solvers.cpp:171-249; remhos.cpp:502-507 turns the
+      // masks off); tables :252-279
+      static const double a2[] = {.5}, b2[] = {0., 1.}, c2[] = {.5};
+      static const double a3[] = {1. / 3., 0., 2. / 3.}, b3[] = {.25, 0., .75}, c3[] = {1. / 3., 2. / 3.};
+      static const double a4i[] = {1. / 3., -1. / 3., 1., 1., -1., 1.};
+      static const double b4i[] = {1. / 8., 3. / 8., 3. / 8., 1. / 8.}, c4i[] = {1. / 3., 2. / 3., 1.};
+      static const double a6i[] = {.25, 1. / 8., 1. / 8., 0., -.5, 1., 3. / 16., 0., 0., 9. / 16.,
+                                   -3. / 7., 2. / 7., 12. / 7., -12. / 7., 8. / 7.};
+      static const double b6i[] = {7. / 90., 0., 32. / 90., 12. / 90., 32. / 90., 7. / 90.};
+      static const double c6i[] = {.25, .25, .5, .75, 1.};
+      const int ns = (ode == 12) ? 2 : (ode == 13) ? 3 : (ode == 14) ? 4 : 6;
+      const double *a = (ode == 12) ? a2 : (ode == 13) ? a3 : (ode == 14) ? a4i : a6i;
+      const double *b = (ode == 12) ? b2 : (ode == 13) ? b3 : (ode == 14) ? b4i : b6i;
+      const double *cc = (ode == 12) ? c2 : (ode == 13) ? c3 : (ode == 14) ? c4i : c6i;
+      // ConstructD (remhos_solvers.cpp:40-95)
+      double d[21] = {0};
+      {
+         const double *a_n = a, *a_o = a;
+         int i_o = -1;
+         double c_o = 0.;
+         for (int i = 0; i < ns; i++)
+         {
+            const double c_n = (i < ns - 1) ? cc[i] : 1.;
+            const double dc = c_n - c_o;
+            double *di = d + i * (i + 1) / 2;
+            for (int j = 0; j < i; j++)
+            {
+               const double a_oj = (j <= i_o) ? a_o[j] : 0.;
+               const double m = (a_n[j] - a_oj) / dc;
+               if (m == 0.) { di[j] = 0.; continue; }
+               const double *dj = d + j * (j + 1) / 2;
+               const double dij = m / dj[j];
+               for (int k = 0; k < j; k++) { di[k] -= dj[k] * dij; }
+               di[j] = dij;
+            }
+            di[i] = a_n[i] / dc;
+            const double c_next = (i < ns - 2) ? cc[i + 1] : 1.;
+            if (c_next > c_n) { i_o = i; c_o = c_n; a_o = a_n; }
+            if (i < ns - 2) { a_n += i + 1; } else { a_n = b; }
+         }
+      }
+      for (int i = 0; i < ns; i++) { if (work_vec(c, &c->rk[i])) { return 1; } }
+      double c_o = 0.;
+      double tcur = t0;
+      if (rmh_mult_unlimited(c, ho_type, lo_type, fct_type, tcur, cc[0] * dt, u, c->rk[0], stream)) { return 1; }
+      if (rmh_limit_mult(c, lo_type, fct_type, cc[0] * dt, u, c->rk[0], stream)) { return 1; }
+      {
+         const double c_next = (ns > 2) ? cc[1] : 1.;
+         if (c_next > cc[0])
+         {
+            const double cf[2] = {1.0, cc[0] * dt}; const double *xs[2] = {u, c->rk[0]};
+            if (lincomb(c, 2, cf, xs, u, s)) { return 1; }
+            tcur = t0 + cc[0] * dt;
+            c_o = cc[0];
+         }
+      }
+      const double *d_i = d + 1;
+      for (int i = 1; i < ns; i++)
+      {
+         const double c_n = (i < ns - 1) ? cc[i] : 1.;
+         const double dc = c_n - c_o, dct = dc * dt;
+         if (rmh_mult_unlimited(c, ho_type, lo_type, fct_type, tcur, dct, u, c->rk[i], stream)) { return 1; }
+         {
+            double cf[9]; const double *xs[9];
+            cf[0] = d_i[i]; xs[0] = c->rk[i];
+            for (int j = 0; j < i; j++) { cf[j + 1] = d_i[j]; xs[j + 1] = c->rk[j]; }
+            if (lincomb(c, i + 1, cf, xs, c->rk[i], s)) { return 1; }
+         }
+         if (rmh_limit_mult(c, lo_type, fct_type, dct, u, c->rk[i], stream)) { return 1; }
+         const double c_next = (i < ns - 2) ? cc[i + 1] : 1.;
+         if (i == ns - 1 || c_next > c_n)
+         {
+            tcur = t0 + c_n * dt;
+            const double cf[2] = {1.0, dct}; const double *xs[2] = {u, c->rk[i]};
+            if (lincomb(c, 2, cf, xs, u, s)) { return 1; }
+            c_o = c_n;
+         }
+         d_i += i + 1;
+      }
    }
    else
    {
