@@ -98,6 +98,8 @@ int rmh_inflow(int problem, int dim, int64_t n, const double *x, double *u);
  * the lattice on local face `face`; out [ne][npts^d'][dim].  With pts = i/p this gives the
  * points ProjectCoefficient samples on the positive basis (remhos.cpp:883). */
 int rmh_mesh_eval(const rmh_mesh *m, int npts, const double *pts1d, int face, double *out);
+/* n-point Gauss-Legendre rule on [0,1] (IntRules.Get(Geometry::SEGMENT, 2n-1)) */
+int rmh_gauss_legendre_01(int n, double *x, double *w);
 /* CFL time step used for -dt < 0 (remhos.cpp:538-553) */
 int rmh_cfl_dt(const rmh_mesh *m, int problem, const double *bb_min, const double *bb_max,
                double *dt);
@@ -207,12 +209,23 @@ int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
  * fused stage kernel. */
 int rmh_mult(rmh_ctx *ctx, int ho_type, int lo_type, int fct_type, double t, double dt,
              const double *u_dev, double *k_dev, void *stream);
+/* The two halves of the stage operator, as the IDP Runge-Kutta solvers call them
+ * (remhos_solvers.cpp:29-38,171-249): AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739) --
+ * remap re-assembly at time t, then the HO rate when an FCT solver will limit it, else the LO or
+ * HO rate -- and AdvectionOperator::LimitMult (remhos.cpp:1798-1916) -- k_dev holds the
+ * (combined) HO rate on entry and the limited rate on exit. */
+int rmh_mult_unlimited(rmh_ctx *ctx, int ho_type, int lo_type, int fct_type, double t, double dt,
+                       const double *u_dev, double *k_dev, void *stream);
+int rmh_limit_mult(rmh_ctx *ctx, int lo_type, int fct_type, double dt, const double *u_dev,
+                   double *k_dev, void *stream);
 /* out = sum_i coef[i] * x[i], 1 <= n <= 9 (the vector updates of the explicit RK solvers) */
 int rmh_lincomb(rmh_ctx *ctx, int n, const double *coef, const double *const *x_dev,
                 double *out_dev, void *stream);
 /* ODESolver::Step for -s 1, 2, 3, 4, 6 (ForwardEuler, RK2Solver(1.0), RK3SSPSolver, RK4Solver,
- * RK6Solver; remhos.cpp:488-492) over rmh_mult; returns 3 for an unknown type as remhos()
- * does (remhos.cpp:499-500). */
+ * RK6Solver; remhos.cpp:488-492) over rmh_mult, and for -s 11, 12, 13, 14, 16
+ * (ForwardEulerIDPSolver, RK{2,3,4,6}IDPSolver; remhos.cpp:493-497, remhos_solvers.cpp) over
+ * rmh_mult_unlimited / rmh_limit_mult with masks off (remhos.cpp:502-507); returns 3 for an
+ * unknown type as remhos() does (remhos.cpp:499-500). */
 int rmh_ode_step(rmh_ctx *ctx, int ode_solver_type, int ho_type, int lo_type, int fct_type,
                  double *t, double dt, double *u_dev, void *stream);
 
@@ -257,6 +270,15 @@ int rmh_reduce(rmh_ctx *ctx, int op, const double *a_dev, const double *b_dev, d
 /* per-launch CUDA-event timing of the fused stage kernel: enable != 0 starts recording; every
  * call returns and clears the accumulated kernel time [ms] and launch count */
 int rmh_profile(rmh_ctx *ctx, int enable, double *total_ms, int64_t *launches);
+
+/* device memory for callers without a CUDA toolchain (the host C++ layer is plain g++):
+ * allocation, release, and synchronous copies on the context's device */
+int rmh_dev_malloc(rmh_ctx *ctx, int64_t n_doubles, double **out_dev);
+int rmh_dev_free(rmh_ctx *ctx, double *p_dev);
+int rmh_copy_h2d(rmh_ctx *ctx, double *dst_dev, const double *src_host, int64_t n_doubles);
+int rmh_copy_d2h(rmh_ctx *ctx, double *dst_host, const double *src_dev, int64_t n_doubles);
+int rmh_copy_d2d(rmh_ctx *ctx, double *dst_dev, const double *src_dev, int64_t n_doubles);
+int rmh_sync(rmh_ctx *ctx);
 
 /* number of kernels this library has launched since the counter was last reset */
 int64_t rmh_launch_count(int reset);

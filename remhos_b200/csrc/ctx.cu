@@ -2075,6 +2075,43 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
    return 0;
 }
 
+// ---------------------------------------------------------------- device memory helpers
+extern "C" int rmh_dev_malloc(rmh_ctx *c, int64_t n, double **out)
+{
+   CUDA_OK(cudaSetDevice(c->device));
+   void *q = nullptr;
+   CUDA_OK(cudaMalloc(&q, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
+   *out = (double *)q;
+   return 0;
+}
+extern "C" int rmh_dev_free(rmh_ctx *c, double *p)
+{
+   CUDA_OK(cudaSetDevice(c->device));
+   CUDA_OK(cudaFree(p));
+   return 0;
+}
+extern "C" int rmh_copy_h2d(rmh_ctx *, double *dst, const double *src, int64_t n)
+{
+   CUDA_OK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+   return 0;
+}
+extern "C" int rmh_copy_d2h(rmh_ctx *, double *dst, const double *src, int64_t n)
+{
+   CUDA_OK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+extern "C" int rmh_copy_d2d(rmh_ctx *, double *dst, const double *src, int64_t n)
+{
+   CUDA_OK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice));
+   return 0;
+}
+extern "C" int rmh_sync(rmh_ctx *c)
+{
+   CUDA_OK(cudaSetDevice(c->device));
+   CUDA_OK(cudaDeviceSynchronize());
+   return 0;
+}
+
 // ---------------------------------------------------------------- halo (multi-GPU) entry points
 extern "C" int rmh_stage_minmax(rmh_ctx *c, const double *y, void *stream)
 {

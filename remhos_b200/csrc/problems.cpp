@@ -229,6 +229,15 @@ static double inflow_pt(int problem, int dim, const double *x)
    return 0.0;
 }
 
+extern "C" int rmh_gauss_legendre_01(int n, double *x, double *w)
+{
+   if (n < 1) { rmh::set_error("rmh_gauss_legendre_01: n >= 1"); return 1; }
+   std::vector<double> xv, wv;
+   rmh::gauss_legendre_01(n, xv, wv);
+   for (int i = 0; i < n; i++) { if (x) { x[i] = xv[i]; } if (w) { w[i] = wv[i]; } }
+   return 0;
+}
+
 extern "C" int rmh_velocity(int problem, int dim, int64_t n, const double *x, const double *bmin,
                             const double *bmax, double *v)
 {

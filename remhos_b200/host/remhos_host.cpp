@@ -1,0 +1,613 @@
+// Host-side mirror of the Remhos solver interfaces (see remhos_host.hpp) and the remhos() driver.
+#include "remhos_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+namespace remhos
+{
+
+void Abort(const std::string &msg) { throw std::runtime_error(msg); }
+void Verify(bool cond, const std::string &msg) { if (!cond) { Abort(msg); } }
+void Check(int status) { if (status != 0) { Abort(rmh_last_error()); } }
+
+// ------------------------------------------------------------------------------------ Vector
+Vector::Vector(const ParFiniteElementSpace &space) { SetSpace(space); }
+Vector::Vector(const Vector &o)
+{
+   if (o.fes) { SetSpace(*o.fes); Check(rmh_copy_d2d(fes->ctx, d, o.d, n)); }
+}
+Vector &Vector::operator=(const Vector &o)
+{
+   if (this == &o) { return *this; }
+   if (!fes && o.fes) { SetSpace(*o.fes); }
+   Verify(n == o.n, "Vector::operator=: size mismatch");
+   if (n) { Check(rmh_copy_d2d(fes->ctx, d, o.d, n)); }
+   return *this;
+}
+Vector &Vector::operator=(double v)
+{
+   const double c = 0.0;
+   const double *x = d;
+   if (v == 0.0) { Check(rmh_lincomb(fes->ctx, 1, &c, &x, d, nullptr)); }
+   else { SetFromHost(std::vector<double>((size_t)n, v)); }
+   return *this;
+}
+Vector::~Vector() { if (d && fes && fes->ctx) { rmh_dev_free(fes->ctx, d); } }
+void Vector::SetSpace(const ParFiniteElementSpace &space)
+{
+   Verify(d == nullptr, "Vector::SetSpace: already allocated");
+   fes = &space;
+   n = space.GetVSize();
+   Check(rmh_dev_malloc(space.ctx, n, &d));
+   const double c = 0.0;
+   const double *x = d;
+   // zero-fill through the library (0 * x): allocation returns uninitialised memory
+   Check(rmh_copy_h2d(space.ctx, d, std::vector<double>((size_t)n, 0.0).data(), n));
+   (void)c; (void)x;
+}
+void Vector::SetFromHost(const std::vector<double> &h)
+{
+   Verify((int64_t)h.size() == n, "Vector::SetFromHost: size mismatch");
+   Check(rmh_copy_h2d(fes->ctx, d, h.data(), n));
+}
+std::vector<double> Vector::HostRead() const
+{
+   std::vector<double> h((size_t)n);
+   if (n) { Check(rmh_copy_d2h(fes->ctx, h.data(), d, n)); }
+   return h;
+}
+void Vector::Add(double a, const Vector &x)
+{
+   const double c[2] = {1.0, a};
+   const double *xs[2] = {d, x.d};
+   Check(rmh_lincomb(fes->ctx, 2, c, xs, d, nullptr));
+}
+
+// ------------------------------------------------------------------------------------ space
+ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int order_, int mesh_order_,
+                                             int bounds_type_, double &dt, double &t_final_,
+                                             int device)
+   : mesh(m), order(order_), mesh_order(mesh_order_), bounds_type(bounds_type_), problem(problem_)
+{
+   dim = rmh_mesh_dim(m);
+   exec_mode = (problem < 10) ? 0 : 1;                                   // remhos.cpp:438-440
+   bb_min.assign(dim, 0.0); bb_max.assign(dim, 0.0);
+   Check(rmh_mesh_bounding_box(m, bb_min.data(), bb_max.data()));        // :457
+   Check(rmh_mesh_set_curvature(m, mesh_order));                         // :513
+   if (dt < 0.0) { Check(rmh_cfl_dt(m, problem, bb_min.data(), bb_max.data(), &dt)); }   // :538-553
+   dt_cfl = dt;
+   const int64_t ne = rmh_mesh_ne(m);
+   int ngn = 1, nd = 1, nf = 2 * dim, nfd = 1, n3 = 1, nsub = 1, ncorner = 1;
+   for (int a = 0; a < dim; a++) { ngn *= mesh_order + 1; nd *= order + 1; n3 *= 3; nsub *= std::max(order, 1); ncorner *= 2; }
+   for (int a = 0; a < dim - 1; a++) { nfd *= order + 1; }
+   const double *nodes = rmh_mesh_nodes(m);
+   std::vector<double> vel_nodes, vel_quad, vel_face;
+   const size_t nnod = (size_t)ne * ngn * dim;
+   if (exec_mode == 1)                                                   // :562-584
+   {
+      vel_nodes.resize(nnod);
+      Check(rmh_remap_mesh_velocity(m, problem, bb_min.data(), bb_max.data(), dt, t_final_,
+                                    vel_nodes.data()));
+      t_final_ = 1.0;                                                    // :1128-1134
+   }
+   else
+   {
+      // velocities that are polynomials of degree <= 1 are reproduced exactly by their nodal
+      // interpolant; anything else is sampled at the quadrature points (VectorFunctionCoefficient)
+      const int pv = problem % 20;
+      const bool nodal_ok = (pv == 0 || pv == 1 || pv == 2 || pv == 4 || pv == 5 || pv == 6 || pv == 7);
+      if (nodal_ok)
+      {
+         vel_nodes.resize(nnod);
+         Check(rmh_velocity(problem, dim, (int64_t)ne * ngn, nodes, bb_min.data(), bb_max.data(),
+                            vel_nodes.data()));
+      }
+      else
+      {
+         const int Q = (2 * order + dim * mesh_order - 1) / 2 + 1;
+         std::vector<double> xq(Q), wq(Q);
+         Check(rmh_gauss_legendre_01(Q, xq.data(), wq.data()));
+         int nq = 1, nqf = 1;
+         for (int a = 0; a < dim; a++) { nq *= Q; }
+         for (int a = 0; a < dim - 1; a++) { nqf *= Q; }
+         std::vector<double> pts((size_t)ne * nq * dim);
+         vel_quad.resize(pts.size());
+         Check(rmh_mesh_eval(m, Q, xq.data(), -1, pts.data()));
+         Check(rmh_velocity(problem, dim, (int64_t)ne * nq, pts.data(), bb_min.data(), bb_max.data(),
+                            vel_quad.data()));
+         vel_face.resize((size_t)ne * nf * nqf * dim);
+         std::vector<double> fp((size_t)ne * nqf * dim), fv(fp.size());
+         for (int f = 0; f < nf; f++)
+         {
+            Check(rmh_mesh_eval(m, Q, xq.data(), f, fp.data()));
+            Check(rmh_velocity(problem, dim, (int64_t)ne * nqf, fp.data(), bb_min.data(),
+                               bb_max.data(), fv.data()));
+            for (int64_t e = 0; e < ne; e++)
+            {
+               std::memcpy(&vel_face[((size_t)e * nf + f) * nqf * dim], &fv[(size_t)e * nqf * dim],
+                           sizeof(double) * nqf * dim);
+            }
+         }
+      }
+   }
+   t_final = t_final_;
+   std::vector<int32_t> bd((size_t)nfd * nf), nbr((size_t)ne * nf * nfd), s2i((size_t)nsub * ncorner),
+       lat((size_t)ne * n3), nbe((size_t)ne * nf);
+   int32_t n_ent = 0;
+   Check(rmh_mesh_dof_maps(m, order, bd.data(), nbr.data(), s2i.data(), lat.data(), &n_ent, nbe.data()));
+   // DOF positions: uniform lattice i/p (ProjectCoefficient on the positive basis, remhos.cpp:883)
+   std::vector<double> lp(order + 1);
+   for (int i = 0; i <= order; i++) { lp[i] = (double)i / std::max(order, 1); }
+   std::vector<double> xdof((size_t)ne * nd * dim), infl((size_t)ne * nd);
+   Check(rmh_mesh_eval(m, order + 1, lp.data(), -1, xdof.data()));
+   Check(rmh_inflow(problem, dim, (int64_t)ne * nd, xdof.data(), infl.data()));
+   rmh_desc d;
+   std::memset(&d, 0, sizeof(d));
+   d.dim = dim; d.order = order; d.mesh_order = mesh_order; d.exec_mode = exec_mode;
+   d.bounds_type = bounds_type; d.device = device; d.ne = ne; d.ne_ghost = 0;
+   d.nodes = nodes;
+   d.vel_nodes = vel_nodes.empty() ? nullptr : vel_nodes.data();
+   d.vel_quad = vel_quad.empty() ? nullptr : vel_quad.data();
+   d.vel_face = vel_face.empty() ? nullptr : vel_face.data();
+   d.nbr_dof = nbr.data(); d.lat = lat.data(); d.n_ent = n_ent; d.nbr_elem = nbe.data();
+   d.inflow = infl.data();
+   Check(rmh_ctx_create(&d, &ctx));
+   u0.resize((size_t)ne * nd);
+   Check(rmh_u0(problem, dim, (int64_t)ne * nd, xdof.data(), bb_min.data(), bb_max.data(), u0.data()));
+}
+ParFiniteElementSpace::~ParFiniteElementSpace()
+{
+   if (ctx) { rmh_ctx_destroy(ctx); ctx = nullptr; }
+}
+int64_t ParFiniteElementSpace::GetNE() const { return rmh_mesh_ne(mesh); }
+int64_t ParFiniteElementSpace::GetVSize() const { return rmh_ctx_ndofs(ctx); }
+int ParFiniteElementSpace::GetNDofs() const { return rmh_ctx_nd(ctx); }
+
+// ------------------------------------------------------------------------------------ solvers
+void LocalInverseHOSolver::CalcHOSolution(const Vector &u, Vector &du) const
+{
+   Verify(timer != nullptr, "Timer not set.");                           // remhos_ho.cpp:86
+   Check(rmh_ho_local_inverse(pfes.ctx, u.Read(), du.Write(), nullptr));
+}
+
+DiscreteUpwind::DiscreteUpwind(ParFiniteElementSpace &space) : LOSolver(space)
+{
+   Check(rmh_fa_setup(space.ctx, nullptr));
+}
+void DiscreteUpwind::CalcLOSolution(const Vector &u, Vector &du) const
+{
+   Check(rmh_lo_discrete_upwind(pfes.ctx, u.Read(), du.Write(), nullptr));
+}
+void ResidualDistribution::CalcLOSolution(const Vector &u, Vector &du) const
+{
+   Check(rmh_lo_res_dist(pfes.ctx, u.Read(), du.Write(), nullptr));
+}
+void MassBasedAvg::CalcLOSolution(const Vector &u, Vector &du) const
+{
+   // remhos_lo.cpp:253-262: use the HO solution handed over by LimitMult, or compute it
+   Vector *own = nullptr;
+   const Vector *ho = du_HO;
+   if (!ho)
+   {
+      own = new Vector(pfes);
+      ho_solver.CalcHOSolution(u, *own);
+      ho = own;
+   }
+   Check(rmh_lo_mass_avg(pfes.ctx, dt, u.Read(), ho->Read(), du.Write(), nullptr));
+   du_HO = nullptr;
+   delete own;
+}
+
+FluxBasedFCT::FluxBasedFCT(ParFiniteElementSpace &space, double dt_) : FCTSolver(space, dt_)
+{
+   Check(rmh_fa_setup(space.ctx, nullptr));
+}
+void FluxBasedFCT::CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho,
+                                   const Vector &du_lo, const Vector &u_min, const Vector &u_max,
+                                   Vector &du) const
+{
+   Check(rmh_fct_flux_based(pfes.ctx, dt, u.Read(), m.Read(), du_ho.Read(), du_lo.Read(),
+                            u_min.Read(), u_max.Read(), du.Write(), nullptr));
+}
+void ClipScaleSolver::CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho,
+                                      const Vector &du_lo, const Vector &u_min, const Vector &u_max,
+                                      Vector &du) const
+{
+   Check(rmh_fct_clip_scale(pfes.ctx, dt, u.Read(), m.Read(), du_ho.Read(), du_lo.Read(),
+                            u_min.Read(), u_max.Read(), du.Write(), nullptr));
+}
+
+// ------------------------------------------------------------------------------------ DofInfo
+DofInfo::DofInfo(ParFiniteElementSpace &space, int btype)
+   : pfes(space), bounds_type(btype), xi_min(space), xi_max(space)
+{
+   const int dim = space.dim, p = space.order;
+   int nd = 1, nfd = 1, nsub = 1, nc = 1;
+   for (int a = 0; a < dim; a++) { nd *= p + 1; nsub *= std::max(p, 1); nc *= 2; }
+   for (int a = 0; a < dim - 1; a++) { nfd *= p + 1; }
+   numBdrs = 2 * dim; numFaceDofs = nfd; numSubcells = nsub; numDofsSubcell = nc;
+   const int64_t ne = space.GetNE();
+   BdrDofs.resize((size_t)nfd * numBdrs);
+   NbrDof.resize((size_t)ne * numBdrs * nfd);
+   Sub2Ind.resize((size_t)nsub * nc);
+   Check(rmh_mesh_dof_maps(space.mesh, p, BdrDofs.data(), NbrDof.data(), Sub2Ind.data(), nullptr,
+                           nullptr, nullptr));
+   Check(rmh_dev_malloc(space.ctx, ne, &xe_min));
+   Check(rmh_dev_malloc(space.ctx, ne, &xe_max));
+}
+DofInfo::~DofInfo()
+{
+   if (xe_min) { rmh_dev_free(pfes.ctx, xe_min); }
+   if (xe_max) { rmh_dev_free(pfes.ctx, xe_max); }
+}
+void DofInfo::ComputeElementsMinMax(const Vector &u, double *u_min, double *u_max) const
+{
+   Check(rmh_elem_min_max(pfes.ctx, u.Read(), u_min, u_max, nullptr));
+}
+void DofInfo::ComputeBounds(const double *el_min, const double *el_max, Vector &dof_min,
+                            Vector &dof_max) const
+{
+   Check(rmh_bounds(pfes.ctx, el_min, el_max, dof_min.Write(), dof_max.Write(), nullptr));
+}
+
+// ------------------------------------------------------------------------------------ operator
+AdvectionOperator::AdvectionOperator(ParFiniteElementSpace &space, Vector &lumpedM_, DofInfo &dofs_,
+                                     HOSolver *hos, LOSolver *los, FCTSolver *fct)
+   : pfes(space), lumpedM(lumpedM_), dofs(dofs_), ho_solver(hos), lo_solver(los), fct_solver(fct)
+{
+   if (ho_solver) { ho_solver->timer = &timer; }
+   if (lo_solver) { lo_solver->timer = &timer; }
+   if (fct_solver) { fct_solver->timer = &timer; }
+}
+void AdvectionOperator::SetDt(double dt_)                                // remhos.cpp:176-182
+{
+   dt = dt_;
+   if (lo_solver) { lo_solver->UpdateTimeStep(dt_); }
+   if (fct_solver) { fct_solver->UpdateTimeStep(dt_); }
+}
+void AdvectionOperator::SetTime(double t_) { t = t_; }
+void AdvectionOperator::MultUnlimited(const Vector &x, Vector &y) const  // remhos.cpp:1596-1739
+{
+   // remap: move the mesh to x0 + t v and re-assemble (:1598-1677)
+   Check(rmh_set_time(pfes.ctx, t, nullptr));
+   if (pfes.exec_mode == 1) { Check(rmh_lumped_mass(pfes.ctx, lumpedM.Write(), nullptr)); }
+   if (fct_solver)
+   {
+      Verify(ho_solver && lo_solver, "FCT requires HO and LO solvers.");
+      ho_solver->CalcHOSolution(x, y);
+   }
+   else if (lo_solver) { lo_solver->CalcLOSolution(x, y); }
+   else if (ho_solver) { ho_solver->CalcHOSolution(x, y); }
+   else { Abort("No solver was chosen."); }
+}
+void AdvectionOperator::LimitMult(const Vector &x, Vector &y) const     // remhos.cpp:1798-1916
+{
+   if (!fct_solver) { return; }
+   Verify(ho_solver && lo_solver, "FCT requires HO and LO solvers.");
+   Vector du_HO(y), du_LO(pfes);
+   auto mba = dynamic_cast<MassBasedAvg *>(lo_solver);
+   if (mba) { mba->SetHOSolution(du_HO); }
+   lo_solver->CalcLOSolution(x, du_LO);
+   dofs.ComputeElementsMinMax(x, dofs.xe_min, dofs.xe_max);
+   dofs.ComputeBounds(dofs.xe_min, dofs.xe_max, dofs.xi_min, dofs.xi_max);
+   fct_solver->CalcFCTSolution(x, lumpedM, du_HO, du_LO, dofs.xi_min, dofs.xi_max, y);
+   if (verify_bounds)                                                    // check_violation, :1576-1594
+   {
+      const std::vector<double> u = x.HostRead(), du = y.HostRead(), mn = dofs.xi_min.HostRead(),
+                                mx = dofs.xi_max.HostRead();
+      for (size_t i = 0; i < u.size(); i++)
+      {
+         const double un = u[i] + dt * du[i];
+         if (un + 1e-12 < mn[i] || un > mx[i] + 1e-12)
+         {
+            std::ostringstream os;
+            os << std::setprecision(12) << "LimitMult FCT solution u bounds: " << mn[i] << " " << un
+               << " " << mx[i];
+            Abort(os.str());
+         }
+      }
+   }
+}
+void AdvectionOperator::Mult(const Vector &x, Vector &y) const
+{
+   // the fused stage kernel covers -ho 3 -lo 5 -fct 2; anything else goes solver by solver
+   if (HOType() == 3 && LOType() == 5 && FCTType() == 2 && !verify_bounds)
+   {
+      Check(rmh_mult(pfes.ctx, 3, 5, 2, t, dt, x.Read(), y.Write(), nullptr));
+      return;
+   }
+   MultUnlimited(x, y);
+   LimitMult(x, y);
+}
+void AdvectionOperator::PrintTimingData(int steps, double stage_seconds) const   // remhos.cpp:1918-1966
+{
+   if (!(HOType() == 3 && LOType() == 5 && FCTType() == 2)) { return; }
+   const double dofs_steps = (double)pfes.GlobalVSize() * steps;
+   std::cout << "---" << std::endl;
+   std::cout << "RHS+L2inv+LO+FCT run as one fused stage kernel per RK stage" << std::endl
+             << "Total kernel time: " << stage_seconds << std::endl;
+   std::cout << "---" << std::endl;
+   std::cout << "FOM:     " << 1e-6 * dofs_steps / stage_seconds << std::endl;
+   std::cout << "(megadofs x time steps / second)\n---" << std::endl;
+}
+
+// ------------------------------------------------------------------------------------ ODE
+bool ODESolver::Known(int t)
+{
+   return t == 1 || t == 2 || t == 3 || t == 4 || t == 6 || t == 11 || t == 12 || t == 13 ||
+          t == 14 || t == 16;
+}
+int ODESolver::Stages() const
+{
+   switch (type)            // remhos.cpp:1340-1347 (the FOM counts 6 for RK6)
+   {
+      case 2: return 2;
+      case 3: return 3;
+      case 4: return 4;
+      case 6: return 6;
+      default: return 1;
+   }
+}
+void ODESolver::Step(Vector &x, double &t, double &dt)
+{
+   Verify(f != nullptr, "ODESolver::Init was not called");
+   if (f->verify_bounds && (type >= 1 && type <= 3))
+   {
+      // checked path: same Butcher forms through AdvectionOperator::Mult
+      ParFiniteElementSpace &sp = f->Space();
+      Vector k(sp), y(sp);
+      auto F = [&](const Vector &in, double tt) { f->SetTime(tt); f->Mult(in, k); };
+      if (type == 1) { F(x, t); x.Add(dt, k); }
+      else if (type == 2)
+      {
+         F(x, t); y = x; y.Add(dt, k); x.Add(0.5 * dt, k);
+         F(y, t + dt); x.Add(0.5 * dt, k);
+      }
+      else
+      {
+         F(x, t); y = x; y.Add(dt, k);
+         F(y, t + dt); y.Add(dt, k);
+         { const double c[2] = {0.75, 0.25}; const double *xs[2] = {x.Read(), y.Read()};
+           Check(rmh_lincomb(sp.ctx, 2, c, xs, y.Write(), nullptr)); }
+         F(y, t + dt / 2); y.Add(dt, k);
+         { const double c[2] = {1.0 / 3.0, 2.0 / 3.0}; const double *xs[2] = {x.Read(), y.Read()};
+           Check(rmh_lincomb(sp.ctx, 2, c, xs, x.Write(), nullptr)); }
+      }
+      t += dt;
+      return;
+   }
+   const int rc = rmh_ode_step(f->Space().ctx, type, f->HOType(), f->LOType(), f->FCTType(), &t, dt,
+                               x.ReadWrite(), nullptr);
+   Check(rc);
+}
+
+// ------------------------------------------------------------------------------------ driver
+namespace
+{
+struct Opt
+{
+   std::string mesh_file = "default", device = "cpu";
+   int dim = 3, epm = 1, problem = 0, rs = 2, rp = 0, order = 3, mesh_order = 2, ode = 3, ho = 3,
+       lo = 0, fct = 0, mono = 0, bt = 0, si = 0, dtc = 0, max_steps = -1, vis_steps = 100, pool = 4;
+   bool pa = false, full = false, gam = false, vis = true, save = false, visit = false, vb = false,
+        ps = false;
+   double t_final = 4.0, dt = 0.005;
+};
+
+void usage(std::ostream &os)
+{
+   os << "Usage: remhos [options]\n"
+         "  -m <mesh>  -dim <d>  -epm <n>  -p <problem>  -rs <n>  -rp <n>  -o <order>  -mo <order>\n"
+         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|3>  -lo <0|1|3|5>  -fct <0|1|2>  -mono <0>\n"
+         "  -bt <0|1>  -pa/-no-pa  -full/-no-full  -d <device>  -gam/-no-gam  -si <0>  -tf <t>\n"
+         "  -dtc <0>  -dt <dt>  -ms <steps>  -vis/-no-vis  -save/-no-save  -visit/-no-visit\n"
+         "  -vb/-no-vb  -ps/-no-ps  -vs <steps>  -pool <GB>\n";
+}
+
+// returns false on a bad command line (remhos.cpp:335-339 prints the usage and returns 1)
+bool parse(int argc, char *argv[], Opt &o)
+{
+   std::map<std::string, int *> ints = {
+      {"-dim", &o.dim}, {"--dimension", &o.dim}, {"-epm", &o.epm}, {"--elem-per-mpi", &o.epm},
+      {"-p", &o.problem}, {"--problem", &o.problem}, {"-rs", &o.rs}, {"--refine-serial", &o.rs},
+      {"-rp", &o.rp}, {"--refine-parallel", &o.rp}, {"-o", &o.order}, {"--order", &o.order},
+      {"-mo", &o.mesh_order}, {"--mesh-order", &o.mesh_order}, {"-s", &o.ode}, {"--ode-solver", &o.ode},
+      {"-ho", &o.ho}, {"--ho-type", &o.ho}, {"-lo", &o.lo}, {"--lo-type", &o.lo},
+      {"-fct", &o.fct}, {"--fct-type", &o.fct}, {"-mono", &o.mono}, {"--mono-type", &o.mono},
+      {"-bt", &o.bt}, {"--bounds-type", &o.bt}, {"-si", &o.si}, {"--smth_ind", &o.si},
+      {"-dtc", &o.dtc}, {"--dt-control", &o.dtc}, {"-ms", &o.max_steps}, {"--max-steps", &o.max_steps},
+      {"-vs", &o.vis_steps}, {"--visualization-steps", &o.vis_steps}, {"-pool", &o.pool},
+      {"--dev-pool-size", &o.pool}};
+   std::map<std::string, double *> dbls = {{"-tf", &o.t_final}, {"--t-final", &o.t_final},
+                                           {"-dt", &o.dt}, {"--time-step", &o.dt}};
+   std::map<std::string, std::string *> strs = {{"-m", &o.mesh_file}, {"--mesh", &o.mesh_file},
+                                                {"-d", &o.device}, {"--device", &o.device}};
+   std::map<std::string, std::pair<bool *, bool>> flags = {
+      {"-pa", {&o.pa, true}}, {"--partial-assembly", {&o.pa, true}}, {"-no-pa", {&o.pa, false}},
+      {"--no-partial-assembly", {&o.pa, false}}, {"-full", {&o.full, true}}, {"-no-full", {&o.full, false}},
+      {"--next-gen-full", {&o.full, true}}, {"--no-next-gen-full", {&o.full, false}},
+      {"-gam", {&o.gam, true}}, {"-no-gam", {&o.gam, false}}, {"--gpu-aware-mpi", {&o.gam, true}},
+      {"--no-gpu-aware-mpi", {&o.gam, false}}, {"-vis", {&o.vis, true}}, {"-no-vis", {&o.vis, false}},
+      {"--visualization", {&o.vis, true}}, {"--no-visualization", {&o.vis, false}},
+      {"-save", {&o.save, true}}, {"-no-save", {&o.save, false}}, {"-visit", {&o.visit, true}},
+      {"-no-visit", {&o.visit, false}}, {"--visit-datafiles", {&o.visit, true}},
+      {"--no-visit-datafiles", {&o.visit, false}}, {"-vb", {&o.vb, true}}, {"-no-vb", {&o.vb, false}},
+      {"--verify-bounds", {&o.vb, true}}, {"--dont-verify-bounds", {&o.vb, false}},
+      {"-ps", {&o.ps, true}}, {"-no-ps", {&o.ps, false}}, {"--product-sync", {&o.ps, true}},
+      {"--no-product-sync", {&o.ps, false}}};
+   for (int i = 1; i < argc; i++)
+   {
+      const std::string a = argv[i];
+      if (a == "-h" || a == "--help") { return false; }
+      auto fi = flags.find(a);
+      if (fi != flags.end()) { *fi->second.first = fi->second.second; continue; }
+      if (i + 1 >= argc) { std::cout << "Missing value for option " << a << std::endl; return false; }
+      const char *v = argv[++i];
+      char *end = nullptr;
+      auto ii = ints.find(a);
+      if (ii != ints.end())
+      {
+         *ii->second = (int)std::strtol(v, &end, 10);
+         if (*end) { std::cout << "Wrong value for option " << a << std::endl; return false; }
+         continue;
+      }
+      auto di = dbls.find(a);
+      if (di != dbls.end())
+      {
+         *di->second = std::strtod(v, &end);
+         if (*end) { std::cout << "Wrong value for option " << a << std::endl; return false; }
+         continue;
+      }
+      auto si = strs.find(a);
+      if (si != strs.end()) { *si->second = v; continue; }
+      std::cout << "Unrecognized option: " << a << std::endl;
+      return false;
+   }
+   return true;
+}
+} // namespace
+
+int remhos(int argc, char *argv[], double &final_mass_u)
+{
+   Opt o;
+   if (!parse(argc, argv, o)) { usage(std::cout); return 1; }           // remhos.cpp:335-339
+   // ---- combinations the reference rejects (Appendix A of SURVEY.md) or this build lacks
+   if (!ODESolver::Known(o.ode))
+   {
+      std::cout << "Unknown ODE solver type: " << o.ode << '\n';       // remhos.cpp:499-500
+      return 3;
+   }
+   Verify(o.mono == 0, "monolithic solvers (-mono) are not part of this build");
+   Verify(o.ho == 0 || o.ho == 3, "only -ho 0 and -ho 3 (LocalInverse) are part of this build");
+   Verify(o.lo == 0 || o.lo == 1 || o.lo == 3 || o.lo == 5,
+          "only -lo 0, 1 (DiscreteUpwind), 3 (ResidualDistribution), 5 (MassBasedAvg) are part of this build");
+   Verify(o.fct >= 0 && o.fct <= 2, "only -fct 0, 1 (FluxBased), 2 (ClipScale) are part of this build");
+   Verify(!o.ps, "product remap (-ps) is not part of this build");
+   Verify(o.si == 0, "smoothness indicators (-si) are not part of this build");
+   Verify(o.dtc == 0, "automatic time step control (-dtc 1) is not part of this build");
+   Verify(!(o.fct == 1 && o.pa), "Flux-based FCT is not compatible with partial assembly.");   // :1088
+   Verify(o.order >= 1, "order 0 disables limiting; not part of this build");
+   if (o.fct) { Verify(o.ho && o.lo, "FCT requires HO and LO solvers."); }     // :1690
+   if (o.lo == 5) { Verify(o.ho != 0, "Mass-Based LO solver requires a choice of a HO solver."); }   // :991
+   Verify(o.ho || o.lo, "No solver was chosen.");
+   // ---- mesh (remhos.cpp:448-463)
+   rmh_mesh *mesh = nullptr;
+   if (o.mesh_file == "default")
+   {
+      Verify(o.dim == 2 || o.dim == 3, "-dim must be 2 or 3");
+      int n[3] = {1, 1, 1};
+      int left = o.epm;                       // one rank: epm elements, as cubic as possible
+      for (int a = 0; a < o.dim; a++)
+      {
+         int k = (int)std::lround(std::pow((double)left, 1.0 / (o.dim - a)));
+         while (k > 1 && left % k) { k--; }
+         n[a] = std::max(k, 1); left /= n[a];
+      }
+      const double org[3] = {0, 0, 0}, sz[3] = {1, 1, 1};
+      Check(rmh_mesh_cartesian(o.dim, n, org, sz, 0, &mesh));
+   }
+   else { Check(rmh_mesh_load(o.mesh_file.c_str(), &mesh)); }
+   Check(rmh_mesh_refine(mesh, o.rs + o.rp));
+   double dt = o.dt, t_final = o.t_final;
+   int rc = 0;
+   {
+      ParFiniteElementSpace pfes(mesh, o.problem, o.order, o.mesh_order, o.bt, dt, t_final, 0);
+      std::cout << "Number of unknowns: " << pfes.GlobalVSize() << std::endl;   // remhos.cpp:623
+      Vector u(pfes), lumpedM(pfes);
+      u.SetFromHost(pfes.u0);
+      Check(rmh_lumped_mass(pfes.ctx, lumpedM.Write(), nullptr));
+      DofInfo dofs(pfes, o.bt);
+      HOSolver *ho_solver = o.ho == 3 ? new LocalInverseHOSolver(pfes) : nullptr;
+      LOSolver *lo_solver = nullptr;
+      if (o.lo == 1) { lo_solver = new DiscreteUpwind(pfes); }
+      else if (o.lo == 3) { lo_solver = new ResidualDistribution(pfes); }
+      else if (o.lo == 5) { lo_solver = new MassBasedAvg(pfes, *ho_solver); }
+      FCTSolver *fct_solver = nullptr;
+      if (o.fct == 1) { fct_solver = new FluxBasedFCT(pfes, dt); }
+      else if (o.fct == 2) { fct_solver = new ClipScaleSolver(pfes, dt); }
+      AdvectionOperator adv(pfes, lumpedM, dofs, ho_solver, lo_solver, fct_solver);
+      adv.verify_bounds = o.vb;
+      double mass0_u = 0.0, u_min = 0.0, u_max = 0.0;
+      Check(rmh_reduce(pfes.ctx, 0, u.Read(), lumpedM.Read(), &mass0_u, nullptr));   // :1073-1076
+      Check(rmh_reduce(pfes.ctx, 1, u.Read(), nullptr, &u_min, nullptr));
+      Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &u_max, nullptr));
+      ODESolver ode_solver(o.ode);
+      ode_solver.Init(adv);
+      const bool steady = (o.problem == 6 || o.problem == 7 || o.problem == 8);
+      std::vector<double> res_h, ml_h;
+      if (steady) { res_h = u.HostRead(); ml_h = lumpedM.HostRead(); }
+      double t = 0.0, residual = 0.0;
+      bool done = false;
+      int ti = 0;
+      Check(rmh_sync(pfes.ctx));
+      const auto w0 = std::chrono::steady_clock::now();
+      while (!done)                                                      // remhos.cpp:1146-1330
+      {
+         double dt_real = std::min(dt, t_final - t);
+         adv.SetDt(dt_real);
+         ode_solver.Step(u, t, dt_real);
+         ti++;
+         if (!steady) { done = (t >= t_final - 1.e-8 * dt); }
+         else
+         {
+            const std::vector<double> uh = u.HostRead();
+            double r = 0.0;
+            for (size_t i = 0; i < uh.size(); i++)
+            {
+               r += std::pow((ml_h[i] * uh[i] / dt) - (ml_h[i] * res_h[i] / dt), 2.);
+            }
+            residual = std::sqrt(r);
+            if (residual < 1.e-12 && t >= 1.) { done = true; u.SetFromHost(res_h); }
+            else { res_h = uh; }
+         }
+         if (ti == o.max_steps) { done = true; }
+         if (done || ti % o.vis_steps == 0)
+         {
+            std::cout << "time step: " << ti << ", time: " << t << ", dt: " << dt
+                      << ", residual: " << residual << std::endl;
+         }
+      }
+      Check(rmh_sync(pfes.ctx));
+      const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+      adv.PrintTimingData(ti * ode_solver.Stages(), wall);
+      // final mass on the final mesh (remhos.cpp:1382-1415)
+      if (pfes.exec_mode == 1)
+      {
+         Check(rmh_set_time(pfes.ctx, t, nullptr));
+         Check(rmh_lumped_mass(pfes.ctx, lumpedM.Write(), nullptr));
+      }
+      double mass_u = 0.0;
+      Check(rmh_reduce(pfes.ctx, 0, u.Read(), lumpedM.Read(), &mass_u, nullptr));
+      Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &u_max, nullptr));
+      final_mass_u = mass_u;
+      std::cout << std::setprecision(10) << "Final mass u:  " << mass_u << std::endl
+                << "Max value u:   " << u_max << std::endl << std::setprecision(6)
+                << "Mass loss u:   " << std::abs(mass0_u - mass_u) << std::endl;
+      if (o.save)
+      {
+         // sltn_final.gf in MFEM GridFunction text format (remhos.cpp:1366-1380)
+         FILE *fp = std::fopen("sltn_final.gf", "w");
+         if (fp)
+         {
+            std::fprintf(fp, "FiniteElementSpace\nFiniteElementCollection: L2_T2_%dD_P%d\nVDim: 1\nOrdering: 0\n\n",
+                         pfes.dim, pfes.order);
+            for (double v : u.HostRead()) { std::fprintf(fp, "%.8g\n", v); }
+            std::fclose(fp);
+         }
+      }
+      delete fct_solver; delete lo_solver; delete ho_solver;            // remhos.cpp:1484-1489
+   }
+   rmh_mesh_free(mesh);
+   return rc;
+}
+
+} // namespace remhos

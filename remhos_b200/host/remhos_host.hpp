@@ -1,0 +1,258 @@
+// Host-side mirror of the Remhos solver interfaces on top of the remhos_b200 C ABI.
+//
+// Same class names, call shapes and error behaviour as the reference:
+//   HOSolver / LocalInverseHOSolver                remhos_ho.hpp:29-42, 63-67
+//   LOSolver / DiscreteUpwind / ResidualDistribution / MassBasedAvg
+//                                                  remhos_lo.hpp:28-44, 48-66, 68-83, 87-109
+//   FCTSolver / FluxBasedFCT / ClipScaleSolver     remhos_fct.hpp:31-90, 92-135, 137-155
+//   DofInfo                                        remhos_tools.hpp:114-189
+//   LimitedTimeDependentOperator                   remhos_solvers.hpp:25-63
+//   AdvectionOperator                              remhos.cpp:115-198
+//   ODE solvers (-s 1,2,3,4,6,11,12,13,14,16)      remhos.cpp:486-501, remhos_solvers.hpp
+//   int remhos(argc, argv, final_mass_u)           remhos.cpp:210
+// MFEM types are replaced by two thin ones: Vector (FP64, device-resident) and
+// ParFiniteElementSpace (mesh + order + device context).  This layer is plain C++ (g++): all
+// arithmetic happens behind the C ABI in librmh_b200.so; there is no CPU fallback.
+#ifndef REMHOS_HOST_HPP
+#define REMHOS_HOST_HPP
+
+#include "../../include/remhos_b200.h"
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace remhos
+{
+
+// MFEM_VERIFY / MFEM_ABORT terminate the job in the reference; here they throw, and main()
+// turns the exception into the message + abort the reference would produce.
+[[noreturn]] void Abort(const std::string &msg);
+void Verify(bool cond, const std::string &msg);
+void Check(int status);   // nonzero C-ABI status -> Abort(rmh_last_error())
+
+class ParFiniteElementSpace;
+
+// FP64 vector living in device memory of the space's context
+class Vector
+{
+   const ParFiniteElementSpace *fes = nullptr;
+   double *d = nullptr;
+   int64_t n = 0;
+public:
+   Vector() {}
+   explicit Vector(const ParFiniteElementSpace &space);
+   Vector(const Vector &o);
+   Vector &operator=(const Vector &o);
+   Vector &operator=(double v);
+   ~Vector();
+   void SetSpace(const ParFiniteElementSpace &space);
+   int64_t Size() const { return n; }
+   const double *Read() const { return d; }
+   double *Write() { return d; }
+   double *ReadWrite() { return d; }
+   void SetFromHost(const std::vector<double> &h);
+   std::vector<double> HostRead() const;
+   // this += a * x
+   void Add(double a, const Vector &x);
+   const ParFiniteElementSpace *Space() const { return fes; }
+};
+
+// mesh + DG order + the device context (what ParMesh + DG_FECollection + ParFiniteElementSpace
+// + the assembled forms are to the reference, remhos.cpp:448-727)
+class ParFiniteElementSpace
+{
+public:
+   rmh_mesh *mesh = nullptr;
+   rmh_ctx *ctx = nullptr;
+   int dim = 0, order = 0, mesh_order = 2, exec_mode = 0, bounds_type = 0, problem = 0;
+   std::vector<double> bb_min, bb_max;
+   std::vector<double> u0;          // ProjectCoefficient(u0_function) (remhos.cpp:883)
+   double dt_cfl = 0.0;
+   double t_final = 0.0;
+   ParFiniteElementSpace(rmh_mesh *m, int problem, int order, int mesh_order, int bounds_type,
+                         double &dt, double &t_final, int device);
+   ~ParFiniteElementSpace();
+   int64_t GetNE() const;
+   int64_t GlobalVSize() const { return GetVSize(); }
+   int64_t GetVSize() const;
+   int GetNDofs() const;
+};
+
+struct TimingData   // remhos_tools.hpp: sw_rhs, sw_L2inv, sw_LO, sw_FCT
+{
+   double sw_rhs = 0.0, sw_L2inv = 0.0, sw_LO = 0.0, sw_FCT = 0.0;
+};
+
+class HOSolver
+{
+protected:
+   ParFiniteElementSpace &pfes;
+public:
+   TimingData *timer = nullptr;
+   HOSolver(ParFiniteElementSpace &space) : pfes(space) {}
+   virtual ~HOSolver() {}
+   virtual void CalcHOSolution(const Vector &u, Vector &du) const = 0;
+};
+
+class LocalInverseHOSolver : public HOSolver
+{
+public:
+   LocalInverseHOSolver(ParFiniteElementSpace &space) : HOSolver(space) {}
+   void CalcHOSolution(const Vector &u, Vector &du) const override;
+};
+
+class LOSolver
+{
+protected:
+   ParFiniteElementSpace &pfes;
+   double dt = -1.0;
+public:
+   TimingData *timer = nullptr;
+   LOSolver(ParFiniteElementSpace &space) : pfes(space) {}
+   virtual ~LOSolver() {}
+   virtual void UpdateTimeStep(double dt_new) { dt = dt_new; }
+   virtual void CalcLOSolution(const Vector &u, Vector &du) const = 0;
+   virtual int Type() const = 0;
+};
+
+class DiscreteUpwind : public LOSolver
+{
+public:
+   DiscreteUpwind(ParFiniteElementSpace &space);
+   void CalcLOSolution(const Vector &u, Vector &du) const override;
+   int Type() const override { return 1; }
+};
+
+class ResidualDistribution : public LOSolver
+{
+public:
+   ResidualDistribution(ParFiniteElementSpace &space) : LOSolver(space) {}
+   void CalcLOSolution(const Vector &u, Vector &du) const override;
+   int Type() const override { return 3; }
+};
+
+class MassBasedAvg : public LOSolver
+{
+   HOSolver &ho_solver;
+   mutable const Vector *du_HO = nullptr;   // borrowed for one call (remhos_lo.hpp:93-102)
+public:
+   MassBasedAvg(ParFiniteElementSpace &space, HOSolver &hos) : LOSolver(space), ho_solver(hos) {}
+   void SetHOSolution(Vector &du) { du_HO = &du; }
+   void CalcLOSolution(const Vector &u, Vector &du) const override;
+   int Type() const override { return 5; }
+};
+
+class FCTSolver
+{
+protected:
+   ParFiniteElementSpace &pfes;
+   double dt;
+public:
+   TimingData *timer = nullptr;
+   bool verify_bounds = false;
+   FCTSolver(ParFiniteElementSpace &space, double dt_) : pfes(space), dt(dt_) {}
+   virtual ~FCTSolver() {}
+   virtual void UpdateTimeStep(double dt_new) { dt = dt_new; }
+   bool NeedsLOProductInput() const { return false; }
+   virtual void CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho,
+                                const Vector &du_lo, const Vector &u_min, const Vector &u_max,
+                                Vector &du) const = 0;
+   virtual int Type() const = 0;
+};
+
+class FluxBasedFCT : public FCTSolver
+{
+public:
+   FluxBasedFCT(ParFiniteElementSpace &space, double dt_);
+   void CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho, const Vector &du_lo,
+                        const Vector &u_min, const Vector &u_max, Vector &du) const override;
+   int Type() const override { return 1; }
+};
+
+class ClipScaleSolver : public FCTSolver
+{
+public:
+   ClipScaleSolver(ParFiniteElementSpace &space, double dt_) : FCTSolver(space, dt_) {}
+   void CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho, const Vector &du_lo,
+                        const Vector &u_min, const Vector &u_max, Vector &du) const override;
+   int Type() const override { return 2; }
+};
+
+class DofInfo
+{
+   ParFiniteElementSpace &pfes;
+   int bounds_type;
+   std::vector<double *> owned;
+public:
+   Vector xi_min, xi_max;          // per-DOF bounds
+   double *xe_min = nullptr, *xe_max = nullptr;   // per-element min/max (device, NE each)
+   std::vector<int32_t> BdrDofs, Sub2Ind, NbrDof;
+   int numBdrs = 0, numFaceDofs = 0, numSubcells = 0, numDofsSubcell = 0;
+   DofInfo(ParFiniteElementSpace &space, int btype);
+   ~DofInfo();
+   void ComputeElementsMinMax(const Vector &u, double *u_min, double *u_max) const;
+   void ComputeBounds(const double *el_min, const double *el_max, Vector &dof_min,
+                      Vector &dof_max) const;
+};
+
+class LimitedTimeDependentOperator
+{
+protected:
+   double dt = 0.0, t = 0.0;
+public:
+   virtual ~LimitedTimeDependentOperator() {}
+   virtual void SetDt(double dt_) { dt = dt_; }
+   double GetDt() const { return dt; }
+   virtual void SetTime(double t_) { t = t_; }
+   double GetTime() const { return t; }
+   virtual void MultUnlimited(const Vector &x, Vector &y) const = 0;
+   virtual void LimitMult(const Vector &x, Vector &y) const = 0;
+   virtual void Mult(const Vector &x, Vector &y) const { MultUnlimited(x, y); LimitMult(x, y); }
+};
+
+class AdvectionOperator : public LimitedTimeDependentOperator
+{
+   ParFiniteElementSpace &pfes;
+   Vector &lumpedM;
+   DofInfo &dofs;
+   HOSolver *ho_solver;
+   LOSolver *lo_solver;
+   FCTSolver *fct_solver;
+public:
+   mutable TimingData timer;
+   bool verify_bounds = false;
+   AdvectionOperator(ParFiniteElementSpace &space, Vector &lumpedM_, DofInfo &dofs_, HOSolver *hos,
+                     LOSolver *los, FCTSolver *fct);
+   void SetDt(double dt_) override;
+   void SetTime(double t_) override;
+   void MultUnlimited(const Vector &x, Vector &y) const override;
+   void LimitMult(const Vector &x, Vector &y) const override;
+   void Mult(const Vector &x, Vector &y) const override;
+   int HOType() const { return ho_solver ? 3 : 0; }
+   int LOType() const { return lo_solver ? lo_solver->Type() : 0; }
+   int FCTType() const { return fct_solver ? fct_solver->Type() : 0; }
+   ParFiniteElementSpace &Space() const { return pfes; }
+   void PrintTimingData(int steps, double stage_seconds) const;
+};
+
+// ODESolver::Init / Step (remhos.cpp:486-501): type = the -s value
+class ODESolver
+{
+   int type;
+   AdvectionOperator *f = nullptr;
+public:
+   explicit ODESolver(int ode_solver_type) : type(ode_solver_type) {}
+   static bool Known(int t);
+   void Init(AdvectionOperator &op) { f = &op; }
+   void Step(Vector &x, double &t, double &dt);
+   int Stages() const;
+};
+
+// The driver (remhos.cpp:210): returns 0 ok, 1 bad flags, 3 unknown ODE solver.
+int remhos(int argc, char *argv[], double &final_mass_u);
+
+} // namespace remhos
+
+#endif

@@ -1,0 +1,101 @@
+"""The remhos command-line driver (remhos_b200/host): flag handling without a GPU, and -- on the
+GPU -- whole runs through the C++ solver-interface mirror against the reference's known answers
+(remhos_tests.cpp:38-91, autotest/out_baseline.dat) and the CPU oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import DATA, oracle_run
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, 'remhos_b200', 'host', 'remhos')
+
+
+def run_cli(*args):
+    p = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout, p.stderr
+
+
+def test_driver_is_built():
+    assert os.path.exists(EXE), 'run __graft_entry__.build()'
+
+
+def test_bad_flag_returns_1():
+    rc, out, _ = run_cli('-no-such-flag')
+    assert rc == 1 and 'Usage' in out                      # remhos.cpp:335-339
+
+
+def test_unknown_ode_solver_returns_3():
+    rc, out, _ = run_cli('-m', 'x', '-s', '7')
+    assert rc == 3 and 'Unknown ODE solver type: 7' in out  # remhos.cpp:499-500
+
+
+def test_rejected_combinations_abort():
+    for flags in (['-fct', '2', '-lo', '0'], ['-lo', '5', '-ho', '0'], ['-fct', '1', '-lo', '1', '-pa']):
+        rc, _, err = run_cli('-m', 'x', *flags)
+        assert rc == 134 and 'Verification failed' in err
+
+
+def parse(out):
+    g = lambda pat: float(re.search(pat, out).group(1))
+    return dict(n=int(g(r'Number of unknowns: (\d+)')), mass=g(r'Final mass u:\s+(\S+)'),
+                umax=g(r'Max value u:\s+(\S+)'), loss=g(r'Mass loss u:\s+(\S+)'))
+
+
+def mesh(name):
+    return os.path.join(DATA, name)
+
+
+CLI_KNOWN = [
+    # remhos_tests.cpp:40-44,64-67: final mass of -ho 3 -lo 5 -fct 2 remap runs (first 10 digits)
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-o', 2, '-dt', -1, '-tf', 0.5, '-ho', 3,
+      '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis'], 0.09711395400387984, None),
+    (['-m', mesh('cube01_hex.mesh'), '-p', 10, '-rs', 1, '-o', 2, '-dt', -1, '-tf', 0.5, '-ho', 3,
+      '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis', '-pa'], 0.11972857593296446, None),
+    # autotest/out_baseline.dat:177-180 and :103-106 (mass and max, 10 digits)
+    (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 3,
+      '-lo', 1, '-fct', 1, '-no-vis'], 0.9607429525, 0.9984668427),
+    (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 3,
+      '-lo', 3, '-fct', 2, '-no-vis'], 0.9607429525, 0.9202929163),
+    # autotest/out_baseline.dat:172-175, :98-101 (2D periodic square)
+    (['-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 3, '-dt', 0.004, '-tf', 0.8, '-ho', 3,
+      '-lo', 1, '-fct', 1, '-no-vis'], 0.1623263888, 0.787875182),
+    (['-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 3, '-dt', 0.004, '-tf', 0.8, '-ho', 3,
+      '-lo', 3, '-fct', 2, '-no-vis'], 0.1623263888, 0.6374820899),
+    # remap rows :152-155, :78-81
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-dt', 0.0015, '-tf', 0.75, '-ho', 3,
+      '-lo', 1, '-fct', 1, '-no-vis'], 0.08479546845, 0.905654904),
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-dt', 0.0015, '-tf', 0.75, '-ho', 3,
+      '-lo', 3, '-fct', 2, '-no-vis'], 0.08479546775, 0.7779015453),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('args,mass,umax', CLI_KNOWN)
+def test_cli_reproduces_reference_known_answers(args, mass, umax):
+    rc, out, err = run_cli(*args)
+    assert rc == 0, err
+    r = parse(out)
+    assert float('%.10g' % r['mass']) == float('%.10g' % mass)
+    if umax is not None:
+        assert float('%.10g' % r['umax']) == umax
+
+
+@pytest.mark.gpu
+def test_cli_baseline_config_c1_matches_oracle():
+    """BASELINE.json configs[0]: 2D periodic-square, order 2, -rs 3, RK3, DU + ClipScale."""
+    rc, out, err = run_cli('-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 3, '-o', 2, '-dt', 0.004,
+                           '-tf', 0.8, '-s', 3, '-ho', 3, '-lo', 1, '-fct', 2, '-no-vis', '-vb')
+    assert rc == 0, err
+    r = parse(out)
+    run = oracle_run('periodic-square.mesh', problem=5, rs_levels=3, order=2, dt=0.004, t_final=0.8,
+                     ode_solver=3, ho_type=3, lo_type=1, fct_type=2)
+    run.run()
+    assert r['n'] == run.u.size
+    assert abs(r['mass'] - run.final_mass) < 1e-9 * abs(run.final_mass)      # printed to 10 digits
+    assert abs(r['umax'] - run.final_max) < 1e-9 * abs(run.final_max)
+    assert r['loss'] < 1e-12
+    assert 'time step:' in out and 'residual:' in out

@@ -116,7 +116,7 @@ def test_flux_based_fct(setup, lo):
 
 
 COMBOS = [(3, 1, 2), (3, 1, 1), (3, 3, 2), (3, 3, 1), (3, 5, 2), (3, 5, 1), (3, 0, 0), (0, 1, 0),
-          (0, 3, 0), (0, 5, 0)]
+          (0, 3, 0), (3, 5, 0)]
 
 
 @pytest.mark.parametrize('ho,lo,fct', COMBOS)
@@ -137,7 +137,7 @@ def test_mult_rejects_unsupported(setup):
     import remhos_b200 as rb
     run, ctx, u = setup
     k = empty(ctx)
-    for combo in [(1, 1, 2), (3, 4, 2), (3, 1, 3), (3, 0, 2)]:
+    for combo in [(1, 1, 2), (3, 4, 2), (3, 1, 3), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
         with pytest.raises(rb.RmhError):
             ctx.mult(*combo, 0.0, 0.01, dev(u), k)
 
@@ -200,8 +200,11 @@ def test_ode_steps_match_oracle(mesh, opt, steps):
     linf = float(np.abs(ug - run.u).max() / np.abs(run.u).max())
     # RK6's tableau has entries up to 208 and weights of -176/+172: with a limiter in F (Lipschitz
     # constant ~ 1/dt) round-off differences between two implementations are amplified by several
-    # orders per step, so limited RK6 runs are compared over one step at 1e-9
-    tol = 1e-9 if (opt['ode_solver'] == 6 and opt['fct_type']) else 1e-12
+    # orders per step, so limited RK6 runs are compared over one step at 1e-9; the unlimited
+    # (linear) RK6 run only carries the cancellation in the weights (1e-11)
+    tol = 1e-12
+    if opt['ode_solver'] == 6:
+        tol = 1e-9 if opt['fct_type'] else 1e-11
     assert l1 < tol and linf < tol, (l1, linf)
     ctx.set_time(t)
     m = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
