@@ -45,7 +45,7 @@ class Problem:
     """mesh: a capi.Mesh already refined.  Mirrors the reference defaults (remhos.cpp:216-244)."""
 
     def __init__(self, mesh, problem=0, order=3, mesh_order=2, bounds_type=0, dt=0.005,
-                 t_final=4.0, device=0, velocity_samples='auto'):
+                 t_final=4.0, device=0, velocity_samples='auto', create_ctx=True):
         self.mesh = mesh
         self.problem = problem
         self.order = order
@@ -89,13 +89,16 @@ class Problem:
         xdof = mesh_eval(mesh, lat_pts)
         infl = np.zeros(xdof.shape[0] * xdof.shape[1])
         check(lib().rmh_inflow(int(problem), dim, C.c_int64(infl.size), _ptr(xdof), _ptr(infl)))
-        self.ctx = capi.Context(dim=dim, order=order, mesh_order=mesh_order,
-                                exec_mode=self.exec_mode, bounds_type=bounds_type, nodes=nodes,
-                                nbr_dof=maps['nbr_dof'], lat=maps['lat'], n_ent=maps['n_ent'],
-                                nbr_elem=maps['nbr_elem'], inflow=infl, device=device, **kw)
+        # the host-side inputs of the stage path (also what bench.py hands to the CPU port)
+        self.inputs = dict(dim=dim, order=order, mesh_order=mesh_order, exec_mode=self.exec_mode,
+                           bounds_type=bounds_type, nodes=nodes, nbr_dof=maps['nbr_dof'],
+                           lat=maps['lat'], n_ent=maps['n_ent'], nbr_elem=maps['nbr_elem'],
+                           inflow=infl, **kw)
+        self.ctx = capi.Context(device=device, **self.inputs) if create_ctx else None
         self.u0 = u0(problem, xdof, self.bb_min, self.bb_max)         # :883
         self.ne = mesh.ne
         self.nd = maps['nd']
 
     def close(self):
-        self.ctx.close()
+        if self.ctx is not None:
+            self.ctx.close()
