@@ -1054,14 +1054,14 @@ static int dispatch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 }
 
 // ---- warp-per-element FP64 tensor-core kernel (stage3w.cuh)
-template <int D1, int Q, int NW>
+// NW warps per block, MINB resident blocks per SM the register allocation must allow.  The kernel
+// is latency-bound: 16 warps per SM at 128 registers (operator-data loads hoisted two phases
+// ahead) beat 20 warps at 96 (profiles/r01/README.md).
+template <int D1, int Q, int NW, int MINB>
 static int launch_stagew_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    using S = SmemW<D1, Q>;
    constexpr size_t BYTES = S::bytes(NW);
-   constexpr int MINB0 = (int)((228 * 1024) / (BYTES + 1024));
-   constexpr int MINB1 = MINB0 < 1 ? 1 : MINB0;
-   constexpr int MINB = (MINB1 * NW > 20) ? (20 / NW > 0 ? 20 / NW : 1) : MINB1;   // <= 20 warps per SM
    static int blocks_per_sm = 0;
    if (blocks_per_sm == 0)
    {
@@ -1070,7 +1070,7 @@ static int launch_stagew_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
       int nb = 0;
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3w<D1, Q, NW, MINB>, NW * 32, BYTES));
       if (nb < 1) { set_error("k_stage3w does not fit on an SM"); return 1; }
-      blocks_per_sm = nb;
+      blocks_per_sm = std::min(nb, MINB);
    }
    const int64_t nblk = (a.ne + NW - 1) / NW;
    const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
@@ -1084,12 +1084,25 @@ static int launch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    if constexpr (DIM == 3 && D1 <= 4)
    {
-      static int nw = -1;
-      if (nw < 0) { const char *ev = getenv("RMH_W_NW"); nw = ev ? atoi(ev) : 5; }
-      if (nw == 4) { return launch_stagew_N<D1, Q, 4>(c, a, s); }
-      if (nw == 8) { return launch_stagew_N<D1, Q, 8>(c, a, s); }
-      if (nw == 10) { return launch_stagew_N<D1, Q, 10>(c, a, s); }
-      return launch_stagew_N<D1, Q, 5>(c, a, s);
+      static int cfg = -1;
+      if (cfg < 0)
+      {
+         const char *ev = getenv("RMH_W_NW"), *em = getenv("RMH_W_MINB");
+         const int nw = ev ? atoi(ev) : 8, mb = em ? atoi(em) : 0;
+         cfg = nw * 10 + mb;
+      }
+      switch (cfg)
+      {
+         case 44: case 40: return launch_stagew_N<D1, Q, 4, 4>(c, a, s);    // 16 warps, 128 regs
+         case 43: return launch_stagew_N<D1, Q, 4, 3>(c, a, s);             // 12 warps, 168 regs
+         case 54: return launch_stagew_N<D1, Q, 5, 4>(c, a, s);             // 20 warps,  96 regs
+         case 53: case 50: return launch_stagew_N<D1, Q, 5, 3>(c, a, s);    // 15 warps, 136 regs
+         case 62: case 60: return launch_stagew_N<D1, Q, 6, 2>(c, a, s);    // 12 warps, 168 regs
+         case 72: case 70: return launch_stagew_N<D1, Q, 7, 2>(c, a, s);    // 14 warps, 144 regs
+         case 102: case 100: return launch_stagew_N<D1, Q, 10, 2>(c, a, s); // 20 warps,  96 regs
+         case 101: return launch_stagew_N<D1, Q, 10, 1>(c, a, s);           // 10 warps, 200 regs
+         default: return launch_stagew_N<D1, Q, 8, 2>(c, a, s);             // 16 warps, 128 regs
+      }
    }
    else
    {

@@ -43,13 +43,43 @@ struct SmemW
    static constexpr int NT1 = NF * D1;             // face lines (f, jb)
    static constexpr int NT2 = NF * Q;              // face lines (f, qa)
    // z-plane stride: >= QQ and = 4 (mod 8) so that the four z-planes of a tile hit distinct banks
-   static constexpr int PZ = ((QQ + 3) / 8) * 8 + 4;
+   static constexpr int PZ = (D1 == 4 && Q == 6) ? QQ : ((QQ + 3) / 8) * 8 + 4;
    static constexpr int PA = D1 * PZ;
+   // ---- bank-conflict-free layouts (tools/bank_sim_w.py models every access below; 64-bit
+   // accesses are served per half-warp over 16 bank pairs).  NEWL: order 3 (D1 = 4, Q = 6).
+   //   U   (z,y,x)      z-plane stride 20, x ^= z: face traces of all six faces hit 16 distinct banks
+   //   BU  (row,qx)     rows 8..15 swap the two columns of a pair (stride-6 rows only span 8 banks)
+   //   G3  (arr,z,qy,qx) [arr][qy][qx][z] with the qx parity flipped for qy in {2,3}: 16-byte stores
+   //                    in fwd-y and the z-stage, conflict-free loads in the z-stage and bwd-y
+   //   S2  (iz,iy,qx)   [qx (stride 20)][iz][iy], lives in the dead G3 array 1
+   static constexpr bool NEWL = (D1 == 4 && Q == 6);
+   static constexpr int SZU = NEWL ? D1 * D1 + 4 : D1 * D1;
+   static constexpr int FS = D1 * RQ;
+   __device__ static __forceinline__ int posU(int z, int y, int x)
+   { return NEWL ? z * SZU + y * D1 + (x ^ z) : (z * D1 + y) * D1 + x; }
+   __device__ static __forceinline__ int posUj(int j)
+   { return NEWL ? posU(j / (D1 * D1), (j / D1) % D1, j % D1) : j; }
+   __device__ static __forceinline__ int posBU(int row, int qx)
+   { return NEWL ? row * RQ + (qx ^ ((row >> 3) & 1)) : row * RQ + qx; }
+   __device__ static __forceinline__ int posG3(int arr, int z, int qy, int qx)
+   {
+      return NEWL ? arr * PA + qy * (Q * D1) + ((D1 * qx + z) ^ (D1 * ((qy >> 1) & 1)))
+                  : arr * PA + z * PZ + qy * Q + qx;
+   }
+   __device__ static __forceinline__ int posS2(int iz, int iy, int qx)
+   { return NEWL ? (D1 * D1 + 4) * qx + D1 * iz + iy : (iz * D1 + iy) * RQ + qx; }
+   __device__ static __forceinline__ int posF1(int f, int j, int q) { return f * FS + j * RQ + q; }
+   // fwd-y / bwd-y line index -> (z, qx)
+   __device__ static __forceinline__ void lineB(int line, int &z, int &qx)
+   {
+      if (NEWL) { qx = line / D1; z = line - qx * D1; }
+      else { z = line / Q; qx = line - z * Q; }
+   }
    // ---- one data stage (doubles)
-   static constexpr int NDP = (ND + 1) & ~1;
+   static constexpr int NDP = NEWL ? ((D1 * SZU + 1) & ~1) : ((ND + 1) & ~1);
    static constexpr int P_U = 0;
    static constexpr int P_X = P_U + NDP;
-   static constexpr int P_N = P_X + NDP;
+   static constexpr int P_N = P_X + ((ND + 1) & ~1);
    static constexpr int P_B = P_N + ((NF * NFD + 1) & ~1);
    static constexpr int P_E = P_B + N3 * 2;
    static constexpr int PSZ = P_E + 2;
@@ -58,7 +88,7 @@ struct SmemW
    static constexpr int SZ_C1 = NL * RQ + NF * NFD;               // S2 | face results
    static constexpr int SZ_C = ((SZ_C0 > SZ_C1 ? SZ_C0 : SZ_C1) + 1) & ~1;
    static constexpr int SZ_B = 3 * PA;                            // GB | BG | BB, later T4
-   static constexpr int SZ_G0 = NT1 * RQ;                         // F1
+   static constexpr int SZ_G0 = NF * FS;                          // F1
    static constexpr int SZ_G = ((SZ_G0 > ND ? SZ_G0 : ND) + 1) & ~1;   // ... later X
    static constexpr int OFF_D = 0;
    static constexpr int OFF_C = OFF_D + 2 * PSZ;
@@ -69,7 +99,7 @@ struct SmemW
    static constexpr int WINT = 2 * ISZ;                           // ints per warp
    static constexpr int WBYTES = WDBL * 8 + WINT * 4;
    // shared by the block
-   static constexpr int PATMAX = 32;
+   static constexpr int PATMAX = 16;
    static constexpr int CBYTES = 16 * 8 + ((PATMAX * NFD * 2 + 15) & ~15);
    static constexpr int TA_V = (NL + 7) / 8, TA_F = (NT1 + 7) / 8;
    static constexpr int TB_V = (NY + 7) / 8, TB_F = (NT2 + 7) / 8;
@@ -101,7 +131,26 @@ __device__ __forceinline__ void stagew_fetch_data(const StagePArgs &a, double *d
    {
       const double *gu = a.y + e * ND, *gx = a.x0 + e * ND;
       double *U = dst + S::P_U, *X = dst + S::P_X;
-      if ((ND & 1) == 0)
+      if (S::NEWL)
+      {
+         // swizzled U: 8-byte granularity
+#pragma unroll
+         for (int c0 = 0; c0 < ND; c0 += 32)
+         {
+            const int c = c0 + lane;
+            if (c < ND) { cp_async8(U + S::posUj(c), gu + c); }
+         }
+         if (a.has_x0)
+         {
+#pragma unroll
+            for (int c0 = 0; c0 < ND / 2; c0 += 32)
+            {
+               const int c = c0 + lane;
+               if (c < ND / 2) { cp_async16(X + 2 * c, gx + 2 * c); }
+            }
+         }
+      }
+      else if ((ND & 1) == 0)
       {
 #pragma unroll
          for (int c0 = 0; c0 < ND / 2; c0 += 32)
@@ -276,7 +325,7 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
    double *G3 = wsm + S::OFF_B;
    double *F1 = wsm + S::OFF_G;
    double *FD = wsm + S::OFF_C + NL * RQ;   // face results (phase C on; GU is dead by then)
-   double *S2 = BU;                         // phase D on
+   double *S2 = S::NEWL ? wsm + S::OFF_B + PA : BU;   // phase D on (NEWL: the dead G3 array 1)
    double *X = wsm + S::OFF_G;              // HO result (phase E; F1 is dead by then)
    for (int it = 0; e < a.ne; e += GW, it++)
    {
@@ -298,6 +347,35 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       }
       const double *dvp = a.Dvol + (size_t)e * S::ES_V;
       const double *dfp = a.Dface + (size_t)e * S::ES_F;
+      // operator data is consumed two phases later: issue the loads now (registers) so their L2
+      // latency overlaps phases A and B -- all face tiles and the first z-stage tile; the other
+      // z-stage tiles are fetched one tile ahead
+      double dfv[S::TB_F][2];
+#pragma unroll
+      for (int t = 0; t < S::TB_F; t++)
+      {
+         const int line = t * 8 + g;
+         dfv[t][0] = 0.0; dfv[t][1] = 0.0;
+         if (line < NT2 && 2 * c < Q)
+         {
+            const double2 v = __ldcs(reinterpret_cast<const double2 *>(dfp + line * RQ + 2 * c));
+            dfv[t][0] = v.x; dfv[t][1] = v.y;
+         }
+      }
+      double dvn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      auto load_dv = [&](int t, double (&dv)[6])
+      {
+         const int col = t * 8 + g;
+#pragma unroll
+         for (int i = 0; i < 6; i++) { dv[i] = 0.0; }
+         if (col < NC && 2 * c < Q)
+         {
+            const double2 *p = reinterpret_cast<const double2 *>(dvp + (col * RQ + 2 * c) * 3);
+            const double2 v0 = __ldcs(p), v1 = __ldcs(p + 1), v2 = __ldcs(p + 2);
+            dv[0] = v0.x; dv[1] = v0.y; dv[2] = v1.x; dv[3] = v1.y; dv[4] = v2.x; dv[5] = v2.y;
+         }
+      };
+      load_dv(0, dvn);
       // ================= A: fwd-x (rows = lines (z,y), k = ix) | face fwd-a (rows = (f,jb), k = ja)
 #pragma unroll
       for (int t = 0; t < S::TA_V; t++)
@@ -308,14 +386,15 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          for (int ks = 0; ks < KF; ks++)
          {
             const int k = ks * 4 + c;
-            const double x = (line < NL && k < D1) ? U[line * D1 + k] : 0.0;
+            const double x = (line < NL && k < D1) ? U[S::posU(line / D1, line % D1, k)] : 0.0;
             dmma884(bu0, bu1, x, fB[ks]);
             dmma884(gu0, gu1, x, fG[ks]);
          }
          if (line < NL && 2 * c < RQ)
          {
-            *reinterpret_cast<double2 *>(BU + line * RQ + 2 * c) = make_double2(bu0, bu1);
-            *reinterpret_cast<double2 *>(GU + line * RQ + 2 * c) = make_double2(gu0, gu1);
+            const bool sw = S::NEWL && ((line >> 3) & 1);     // posBU: rows 8..15 hold swapped pairs
+            *reinterpret_cast<double2 *>(BU + line * RQ + 2 * c) = sw ? make_double2(bu1, bu0) : make_double2(bu0, bu1);
+            *reinterpret_cast<double2 *>(GU + line * RQ + 2 * c) = sw ? make_double2(gu1, gu0) : make_double2(gu0, gu1);
          }
       }
 #pragma unroll
@@ -325,21 +404,22 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          const int f = line / D1, jb = line - f * D1;
          const int axis = (f == 0 || f == 5) ? 2 : ((f == 1 || f == 3) ? 1 : 0);
          const int side = (f == 2 || f == 3 || f == 5) ? 1 : 0;
-         const int s1 = (axis == 0) ? D1 : 1;
-         const int s2 = (axis == 2) ? D1 : D1 * D1;
-         const int sa = (axis == 0) ? 1 : ((axis == 1) ? D1 : D1 * D1);
-         const double *own = U + side * (D1 - 1) * sa + jb * s2;
+         const int fx = side * (D1 - 1);
          double f0 = 0.0, f1 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KF; ks++)
          {
             const int k = ks * 4 + c;
-            const double x = (line < NT1 && k < D1) ? own[k * s1] - NB[line * D1 + k] : 0.0;
+            // natural face parametrisation: (ja, jb) = the two remaining axes, ascending
+            const int ux = (axis == 0) ? fx : k;
+            const int uy = (axis == 1) ? fx : ((axis == 0) ? k : jb);
+            const int uz = (axis == 2) ? fx : jb;
+            const double x = (line < NT1 && k < D1) ? U[S::posU(uz, uy, ux)] - NB[line * D1 + k] : 0.0;
             dmma884(f0, f1, x, fB[ks]);
          }
          if (line < NT1 && 2 * c < RQ)
          {
-            *reinterpret_cast<double2 *>(F1 + line * RQ + 2 * c) = make_double2(f0, f1);
+            *reinterpret_cast<double2 *>(F1 + S::posF1(f, jb, 2 * c)) = make_double2(f0, f1);
          }
       }
       __syncwarp();
@@ -348,20 +428,35 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       for (int t = 0; t < S::TB_V; t++)
       {
          const int line = t * 8 + g;
-         const int z = line / Q, qx = line - z * Q;
+         int z, qx;
+         S::lineB(line, z, qx);
          double gb0 = 0.0, gb1 = 0.0, bg0 = 0.0, bg1 = 0.0, bb0 = 0.0, bb1 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KF; ks++)
          {
             const int k = ks * 4 + c;
             const bool on = (line < NY) && (k < D1);
-            const double xb = on ? BU[(z * D1 + k) * RQ + qx] : 0.0;
-            const double xg = on ? GU[(z * D1 + k) * RQ + qx] : 0.0;
+            const double xb = on ? BU[S::posBU(z * D1 + k, qx)] : 0.0;
+            const double xg = on ? GU[S::posBU(z * D1 + k, qx)] : 0.0;
             dmma884(gb0, gb1, fB[ks], xg);     // GB = By Gx u
             dmma884(bg0, bg1, fG[ks], xb);     // BG = Gy Bx u
             dmma884(bb0, bb1, fB[ks], xb);     // BB = By Bx u
          }
-         if (g < Q)
+         if (S::NEWL)
+         {
+            // lines 2c, 2c+1 of the tile = (qx, z), (qx, z+1): one 16-byte store per array
+            const int ls = t * 8 + 2 * c;
+            if (g < Q && ls < NY)
+            {
+               int zs, qxs;
+               S::lineB(ls, zs, qxs);
+               double *o = G3 + S::posG3(0, zs, g, qxs);
+               *reinterpret_cast<double2 *>(o) = make_double2(gb0, gb1);
+               *reinterpret_cast<double2 *>(o + PA) = make_double2(bg0, bg1);
+               *reinterpret_cast<double2 *>(o + 2 * PA) = make_double2(bb0, bb1);
+            }
+         }
+         else if (g < Q)
          {
 #pragma unroll
             for (int h = 0; h < 2; h++)
@@ -383,18 +478,13 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       {
          const int line = t * 8 + g;                        // (f, qa)
          const int f = line / Q, qa = line - f * Q;
-         double dfv0 = 0.0, dfv1 = 0.0;
-         if (line < NT2 && 2 * c < Q)
-         {
-            const double2 v = __ldcs(reinterpret_cast<const double2 *>(dfp + line * RQ + 2 * c));
-            dfv0 = v.x; dfv1 = v.y;
-         }
+         const double dfv0 = dfv[t][0], dfv1 = dfv[t][1];
          double y0 = 0.0, y1 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KF; ks++)
          {
             const int kk = ks * 4 + c;
-            const double x = (line < NT2 && kk < D1) ? F1[(f * D1 + kk) * RQ + qa] : 0.0;
+            const double x = (line < NT2 && kk < D1) ? F1[S::posF1(f, kk, qa)] : 0.0;
             dmma884(y0, y1, x, fB[ks]);                     // [line][qb = 2c, 2c+1]
          }
          y0 *= dfv0; y1 *= dfv1;
@@ -404,8 +494,8 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          __syncwarp();
          if (line < NT2)
          {
-            if (2 * c < D1) { F1[(f * D1 + 2 * c) * RQ + qa] = z0; }
-            if (2 * c + 1 < D1) { F1[(f * D1 + 2 * c + 1) * RQ + qa] = z1; }
+            if (2 * c < D1) { F1[S::posF1(f, 2 * c, qa)] = z0; }
+            if (2 * c + 1 < D1) { F1[S::posF1(f, 2 * c + 1, qa)] = z1; }
          }
       }
       __syncwarp();
@@ -414,22 +504,20 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       for (int t = 0; t < S::TC_V; t++)
       {
          const int col = t * 8 + g;
-         double dv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-         if (col < NC && 2 * c < Q)
-         {
-            const double2 *p = reinterpret_cast<const double2 *>(dvp + (col * RQ + 2 * c) * 3);
-            const double2 v0 = __ldcs(p), v1 = __ldcs(p + 1), v2 = __ldcs(p + 2);
-            dv[0] = v0.x; dv[1] = v0.y; dv[2] = v1.x; dv[3] = v1.y; dv[4] = v2.x; dv[5] = v2.y;
-         }
+         double dv[6];
+#pragma unroll
+         for (int i = 0; i < 6; i++) { dv[i] = dvn[i]; }
+         if (t + 1 < S::TC_V) { load_dv(t + 1, dvn); }
          double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0, g20 = 0.0, g21 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KF; ks++)
          {
             const int kk = ks * 4 + c;
             const bool on = (col < NC) && (kk < D1);
-            const double x0 = on ? G3[kk * PZ + col] : 0.0;
-            const double x1 = on ? G3[PA + kk * PZ + col] : 0.0;
-            const double x2 = on ? G3[2 * PA + kk * PZ + col] : 0.0;
+            const int po = S::posG3(0, kk, col / Q, col % Q);
+            const double x0 = on ? G3[po] : 0.0;
+            const double x1 = on ? G3[PA + po] : 0.0;
+            const double x2 = on ? G3[2 * PA + po] : 0.0;
             dmma884(g00, g01, x0, fB[ks]);                  // d/dx: Bz (By Gx u)
             dmma884(g10, g11, x1, fB[ks]);                  // d/dy: Bz (Gy Bx u)
             dmma884(g20, g21, x2, fG[ks]);                  // d/dz: Gz (By Bx u)
@@ -440,7 +528,14 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          dmma884(z0, z1, s0, cC1);                          // [column][iz = 2c, 2c+1]
          dmma884(z0, z1, s1, cC2);
          __syncwarp();
-         if (col < NC)
+         if (S::NEWL)
+         {
+            if (col < NC && 2 * c < D1)
+            {
+               *reinterpret_cast<double2 *>(G3 + S::posG3(0, 2 * c, col / Q, col % Q)) = make_double2(z0, z1);
+            }
+         }
+         else if (col < NC)
          {
             if (2 * c < D1) { G3[(2 * c) * PZ + col] = z0; }
             if (2 * c + 1 < D1) { G3[(2 * c + 1) * PZ + col] = z1; }
@@ -455,7 +550,7 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          for (int ks = 0; ks < KB; ks++)
          {
             const int kk = ks * 4 + c;
-            const double x = (line < NT1 && kk < Q) ? F1[line * RQ + kk] : 0.0;
+            const double x = (line < NT1 && kk < Q) ? F1[S::posF1(line / D1, line % D1, kk)] : 0.0;
             dmma884(y0, y1, x, bC[ks]);                     // [line][ia = 2c, 2c+1]
          }
          if (line < NT1)
@@ -470,13 +565,14 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       for (int t = 0; t < S::TB_V; t++)
       {
          const int line = t * 8 + g;
-         const int iz = line / Q, qx = line - iz * Q;
+         int iz, qx;
+         S::lineB(line, iz, qx);
          double y0 = 0.0, y1 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KB; ks++)
          {
             const int kk = ks * 4 + c;
-            const double x = (line < NY && kk < Q) ? G3[iz * PZ + kk * Q + qx] : 0.0;
+            const double x = (line < NY && kk < Q) ? G3[S::posG3(0, iz, kk, qx)] : 0.0;
             dmma884(y0, y1, bC[ks], x);                     // [iy = g][lines 2c, 2c+1]
          }
          if (g < D1)
@@ -487,8 +583,9 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
                const int ls = t * 8 + 2 * c + h;
                if (ls < NY)
                {
-                  const int izs = ls / Q, qxs = ls - izs * Q;
-                  S2[(izs * D1 + g) * RQ + qxs] = h ? y1 : y0;
+                  int izs, qxs;
+                  S::lineB(ls, izs, qxs);
+                  S2[S::posS2(izs, g, qxs)] = h ? y1 : y0;
                }
             }
          }
@@ -505,7 +602,7 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          for (int ks = 0; ks < KB; ks++)
          {
             const int kk = ks * 4 + c;
-            const double x = (line < NL && kk < Q) ? S2[line * RQ + kk] : 0.0;
+            const double x = (line < NL && kk < Q) ? S2[S::posS2(line / D1, line % D1, kk)] : 0.0;
             dmma884(r0, r1, x, bC[ks]);                     // [line][ix = 2c, 2c+1]
          }
          if (line < NL && i0 < D1)
@@ -558,7 +655,7 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
             const int j = lane + 32 * k;
             if (j < ND)
             {
-               u[k] = U[j];
+               u[k] = U[S::posUj(j)];
                du_ho[k] = X[j];
                if (a.bounds_type == 0) { bmn[k] = BD[2 * cls[k]]; bmx[k] = BD[2 * cls[k] + 1]; }
                else { bmn[k] = bmin1; bmx[k] = bmax1; }
