@@ -55,6 +55,20 @@ CLI_KNOWN = [
       '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis'], 0.09711395400387984, None),
     (['-m', mesh('cube01_hex.mesh'), '-p', 10, '-rs', 1, '-o', 2, '-dt', -1, '-tf', 0.5, '-ho', 3,
       '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis', '-pa'], 0.11972857593296446, None),
+    # remhos_tests.cpp #1, #2, #5, #7 (65536 / 102400 unknowns in 2D; 3D PA order 3 -rs 3)
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 4, '-o', 3, '-dt', -1, '-tf', 0.5, '-ho', 3,
+      '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis', '-vs', 1], 0.0930984399257905, None),
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 4, '-o', 4, '-dt', -1, '-tf', 0.5, '-ho', 3,
+      '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis', '-vs', 1], 0.09237630484178257, None),
+    (['-m', mesh('inline-quad.mesh'), '-pa', '-p', 14, '-rs', 4, '-o', 2, '-dt', -1, '-tf', 0.5,
+      '-ho', 3, '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis', '-vs', 1], 0.09185717760402806, None),
+    (['-m', mesh('cube01_hex.mesh'), '-pa', '-p', 10, '-rs', 3, '-o', 3, '-dt', -1, '-tf', 0.5,
+      '-ho', 3, '-lo', 5, '-fct', 2, '-ms', 1, '-no-vis', '-vs', 1], 0.11601536511552431, None),
+    # autotest/out_baseline.dat:167-170, :93-96: unstructured periodic hexagon
+    (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 3,
+      '-lo', 1, '-fct', 1, '-no-vis'], 0.3888354875, 0.9979069772),
+    (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 3,
+      '-lo', 3, '-fct', 2, '-no-vis'], 0.3888354875, 0.9755502191),
     # autotest/out_baseline.dat:177-180 and :103-106 (mass and max, 10 digits)
     (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 3,
       '-lo', 1, '-fct', 1, '-no-vis'], 0.9607429525, 0.9984668427),

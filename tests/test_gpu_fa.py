@@ -18,6 +18,7 @@ TOL = 1e-11
 CASES = [
     ('periodic-square.mesh', dict(problem=5, rs_levels=2, order=2)),
     ('periodic-square.mesh', dict(problem=1, rs_levels=1, order=3)),
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=1, order=2)),
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, order=2, dt=0.002, t_final=0.75)),
     ('inline-quad.mesh', dict(problem=4, rs_levels=1, order=1)),
     ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=2)),

@@ -21,6 +21,8 @@ STAGE_CASES = [
     ('periodic-square.mesh', dict(problem=5, rs_levels=2, order=3, dt=0.004), 0),
     ('periodic-square.mesh', dict(problem=1, rs_levels=2, order=2, dt=0.004), 1),
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, order=3, dt=0.002, t_final=0.75), 0),
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=1, order=3, dt=0.005), 0),
+    ('periodic-hexagon.mesh', dict(problem=1, rs_levels=1, order=2, dt=0.005), 1),
     ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=3, dt=0.01), 0),
     ('periodic-cube.mesh', dict(problem=1, rs_levels=1, order=2, dt=0.01), 1),
     ('cube01_hex.mesh', dict(problem=10, rs_levels=1, order=3, dt=0.02, t_final=0.7), 0),

@@ -36,6 +36,11 @@ BASELINE = [
                                   lo_type=3, fct_type=2), 0.1623263888, 0.6374820899),   # :98-101
     ('periodic-square.mesh', dict(problem=5, rs_levels=3, dt=0.004, t_final=0.8, ho_type=3,
                                   lo_type=1, fct_type=1), 0.1623263888, 0.787875182),    # :172-175
+    # unstructured periodic mesh (rotated neighbour orientations)
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=3,
+                                   lo_type=1, fct_type=1), 0.3888354875, 0.9979069772),  # :167-170
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=3,
+                                   lo_type=3, fct_type=2), 0.3888354875, 0.9755502191),  # :93-96
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
                               lo_type=1, fct_type=1), 0.08479546845, 0.905654904),       # :152-155
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
@@ -44,7 +49,7 @@ BASELINE = [
 
 
 @pytest.mark.parametrize('mesh,opt,mass,umax', BASELINE,
-                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT',
+                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT', 'hexagon-DU-fluxFCT', 'hexagon-RD-clipscale',
                               'quad-remap-DU-fluxFCT', 'quad-remap-RD-clipscale'])
 def test_autotest_baseline(mesh, opt, mass, umax):
     r = run(mesh, **opt)
@@ -73,7 +78,8 @@ def test_remhos_tests_final_mass(mesh, opt, mass):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_DATA), reason='reference tree not mounted')
-@pytest.mark.parametrize('name', ['periodic-square', 'periodic-cube', 'cube01_hex', 'inline-quad'])
+@pytest.mark.parametrize('name', ['periodic-square', 'periodic-cube', 'cube01_hex', 'inline-quad',
+                                  'periodic-hexagon'])
 def test_generated_meshes_equal_reference_meshes(name):
     a = om.read_mesh(os.path.join(DATA, name + '.mesh'))
     b = om.read_mesh(os.path.join(REF_DATA, name + '.mesh'))
