@@ -195,6 +195,17 @@ int rmh_fct_clip_scale(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
                        const double *xi_min_dev, const double *xi_max_dev, double *du_dev,
                        void *stream);
 
+/* Subcell residual distribution (-lo 4): ResidualDistribution::CalcLOSolution with
+ * subcell_scheme = true (remhos_lo.cpp:164-239) / PAResidualDistributionSubcell (:1040-1802).
+ * rmh_subcell_setup hands over what the driver builds on its low-order refined mesh
+ * (remhos.cpp:797-868): xlat [ne][nd][dim] = the lattice points i/p of every element at t = 0
+ * (the subcell vertices), and vel = velocity_function at the subcell centres [ne][p^dim][dim]
+ * (transport) or at the lattice points with zeros on the domain boundary [ne][nd][dim] (remap,
+ * v_sub_gf); the weights of Assembly::ComputeSubcellWeights (remhos_tools.cpp:860-874) are then
+ * (re)computed on the device whenever the mesh moves. */
+int rmh_subcell_setup(rmh_ctx *ctx, const double *xlat_host, const double *vel_host, void *stream);
+int rmh_lo_res_dist_subcell(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
+
 /* FluxBasedFCT::CalcFCTSolution, one FCT iteration as the driver fixes it (remhos_fct.cpp:155-181,
  * 295-446; remhos.cpp:1093).  Needs rmh_fa_setup; single-rank meshes only. */
 int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const double *m_dev,
@@ -203,7 +214,7 @@ int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
                        void *stream);
 
 /* LimitedTimeDependentOperator::Mult (remhos_solvers.hpp:46-50) for any supported combination of
- * -ho {0,3} -lo {0,1,3,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
+ * -ho {0,3} -lo {0,1,3,4,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
  * remhos.cpp:1598-1677): k = F(u; t, dt).  Orchestrates the separate kernels exactly as
  * MultUnlimited / LimitMult do (remhos.cpp:1596-1739, 1798-1916); -ho 3 -lo 5 -fct 2 runs the
  * fused stage kernel. */

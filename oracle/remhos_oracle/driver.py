@@ -134,6 +134,7 @@ class Run:
         """LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult
         (remhos_solvers.hpp:46-50; remhos.cpp:1596-1739, 1798-1916)."""
         o, d = self.opt, self.disc
+        self._t = t
         if self.exec_mode == 1:
             d.assemble(t)
         A = d.cur
@@ -159,6 +160,7 @@ class Run:
     def mult_unlimited(self, u, t, dt):
         """AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739)."""
         o, d = self.opt, self.disc
+        self._t = t
         if self.exec_mode == 1:
             d.assemble(t)
         if o.fct_type:
@@ -258,7 +260,7 @@ class Run:
     def get_subcell_weights(self):
         from .subcell import subcell_weights
         if self.exec_mode == 1 or self.subcell_weights is None:
-            self.subcell_weights = subcell_weights(self)
+            self.subcell_weights = subcell_weights(self, getattr(self, '_t', 0.0))
         return self.subcell_weights
 
     @staticmethod

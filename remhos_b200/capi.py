@@ -258,6 +258,14 @@ class Context:
     def fa_setup(self, s=0):
         check(lib().rmh_fa_setup(self.h, C.c_void_p(s)))
 
+    def subcell_setup(self, xlat, vel, s=0):
+        xlat = np.ascontiguousarray(xlat, dtype=np.float64)
+        vel = np.ascontiguousarray(vel, dtype=np.float64)
+        check(lib().rmh_subcell_setup(self.h, _ptr(xlat), _ptr(vel), C.c_void_p(s)))
+
+    def lo_res_dist_subcell(self, u, du_lo, s=0):
+        check(lib().rmh_lo_res_dist_subcell(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
+
     def fa_get(self, which):
         nd, ne = self.nd, self.ne
         dim = self.dim

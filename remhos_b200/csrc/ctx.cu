@@ -84,6 +84,9 @@ struct rmh_ctx
    int16_t *pat_idx = nullptr;
    uint8_t *pat_face = nullptr;
    bool fa_on = false;
+   // subcell residual distribution (-lo 4): lattice points, velocity samples, weights
+   double *sub_x = nullptr, *sub_v = nullptr, *sub_w = nullptr;
+   bool sub_on = false;
    // work vectors of the unfused solver path (allocated on first use)
    double *wk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    double *rk[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1156,6 +1159,15 @@ static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
       const int64_t n = c->ne * c->NF * c->NFD;
       k_face_lump<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(o, c->ne, c->BL);
       LAUNCH_OK();
+      if (c->sub_on)
+      {
+         int ns = 1;
+         for (int a = 0; a < c->dim; a++) { ns *= c->p; }
+         const int64_t nsub = c->ne * ns;
+         k_subcell_weights<<<(unsigned)((nsub + bs - 1) / bs), bs, 0, s>>>(
+            c->dim, c->p, c->exec_mode, t, c->ne, c->sub_x, c->sub_v, c->sub_w);
+         LAUNCH_OK();
+      }
       if (c->fa_on)
       {
          const size_t shb = (size_t)((c->dim + 1) * c->NQ + 2 * c->Q * c->D1) * sizeof(double);
@@ -1790,6 +1802,40 @@ extern "C" int rmh_lo_res_dist(rmh_ctx *c, const double *u, double *du_lo, void 
    return 0;
 }
 
+extern "C" int rmh_subcell_setup(rmh_ctx *c, const double *xlat_host, const double *vel_host,
+                                 void *stream)
+{
+   if (c->p < 2) { set_error("Subcell schemes require FE order > 1."); return 1; }   // remhos.cpp:613-616
+   int ns = 1, nc = 1;
+   for (int a = 0; a < c->dim; a++) { ns *= c->p; nc *= 2; }
+   const size_t nx = (size_t)c->ne * c->ND * c->dim;
+   const size_t nv = (c->exec_mode == 1) ? nx : (size_t)c->ne * ns * c->dim;
+   if (!c->sub_on)
+   {
+      if (dev_alloc(c, &c->sub_x, nx) || dev_alloc(c, &c->sub_v, nv) ||
+          dev_alloc(c, &c->sub_w, (size_t)c->ne * ns * nc)) { return 1; }
+   }
+   CUDA_OK(cudaMemcpy(c->sub_x, xlat_host, nx * sizeof(double), cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(c->sub_v, vel_host, nv * sizeof(double), cudaMemcpyHostToDevice));
+   c->sub_on = true;
+   return run_geom(c, c->t_cur, (cudaStream_t)stream);
+}
+
+extern "C" int rmh_lo_res_dist_subcell(rmh_ctx *c, const double *u, double *du_lo, void *stream)
+{
+   if (!c->sub_on) { set_error("rmh_lo_res_dist_subcell: call rmh_subcell_setup first"); return 1; }
+   if (work_vec(c, &c->wk[0])) { return 1; }
+   if (dispatch_ho(c, ho_args(c, u, c->wk[0], 1 | 4), (cudaStream_t)stream)) { return 1; }
+   int ns = 1;
+   for (int a = 0; a < c->dim; a++) { ns *= c->p; }
+   const int wpb = 4;
+   const int64_t nb = (c->ne + wpb - 1) / wpb;
+   k_lo_rd_sub<<<(unsigned)nb, wpb * 32, (size_t)wpb * ns * 6 * sizeof(double), (cudaStream_t)stream>>>(
+      fa_args(c), c->p, c->sub_w, u, c->wk[0], du_lo);
+   LAUNCH_OK();
+   return 0;
+}
+
 extern "C" int rmh_fct_flux_based(rmh_ctx *c, double dt, const double *u, const double *m,
                                   const double *du_ho, const double *du_lo, const double *xi_min,
                                   const double *xi_max, double *du, void *stream)
@@ -1814,8 +1860,8 @@ static int check_combo(int ho_type, int lo_type, int fct_type)
 {
    if (ho_type != 0 && ho_type != 3)
    { set_error("stage operator: HO solver must be 3 (LocalInverse) or 0"); return 1; }
-   if (lo_type < 0 || lo_type > 5 || lo_type == 4 || lo_type == 2)
-   { set_error("stage operator: LO solver must be 0, 1 (DiscreteUpwind), 3 (ResidualDistribution) or 5 (MassBasedAvg)"); return 1; }
+   if (lo_type < 0 || lo_type > 5 || lo_type == 2)
+   { set_error("stage operator: LO solver must be 0, 1 (DiscreteUpwind), 3 (ResidualDistribution), 4 (ResidualDistributionSubcell) or 5 (MassBasedAvg)"); return 1; }
    if (fct_type < 0 || fct_type > 2)
    { set_error("stage operator: FCT solver must be 0, 1 (FluxBased) or 2 (ClipScale)"); return 1; }
    if (fct_type && (ho_type != 3 || lo_type == 0))
@@ -1837,6 +1883,7 @@ extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_
    if (fct_type) { return rmh_ho_local_inverse(c, u, k, stream); }
    if (lo_type == 1) { return rmh_lo_discrete_upwind(c, u, k, stream); }
    if (lo_type == 3) { return rmh_lo_res_dist(c, u, k, stream); }
+   if (lo_type == 4) { return rmh_lo_res_dist_subcell(c, u, k, stream); }
    if (lo_type == 5)
    {
       if (work_vec(c, &c->wk[3])) { return 1; }
@@ -1859,6 +1906,7 @@ extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, 
                            (cudaStream_t)stream));
    if (lo_type == 5) { if (rmh_lo_mass_avg(c, dt, u, du_ho, du_lo, stream)) { return 1; } }
    else if (lo_type == 1) { if (rmh_lo_discrete_upwind(c, u, du_lo, stream)) { return 1; } }
+   else if (lo_type == 4) { if (rmh_lo_res_dist_subcell(c, u, du_lo, stream)) { return 1; } }
    else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
    if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
    if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }

@@ -270,6 +270,153 @@ __global__ void k_lo_rd(FaArgs A, const double *u, const double *z, double *du)
    }
 }
 
+// ---- subcell residual distribution (-lo 4)
+// SubcellWeights(k)(m, j) = alpha grad_ref(phi_j)(centre) . adj(J_sub) . v(centre) on the straight-
+// sided subcells spanned by the lattice points (Assembly::ComputeSubcellWeights,
+// remhos_tools.cpp:860-874, 1033-1076; set-up remhos.cpp:797-868).  xlat0 [ne][nd][dim] lattice
+// points at t = 0; transport: vel [ne][ns][dim] at the subcell centres, alpha = -1; remap: vel
+// [ne][nd][dim] at the lattice points (zero on the boundary), subcells move as x0 + t v, alpha = +1.
+__global__ void k_subcell_weights(int dim, int p, int exec_mode, double t, int64_t ne,
+                                  const double *xlat0, const double *vel, double *SW)
+{
+   int ns = 1, nc = 1, nd = 1;
+   for (int a = 0; a < dim; a++) { ns *= p; nc *= 2; nd *= p + 1; }
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * ns) { return; }
+   const int64_t e = idx / ns;
+   const int m = (int)(idx - e * ns);
+   int sc[3] = {0, 0, 0}, r = m;
+   for (int a = 0; a < dim; a++) { sc[a] = r % p; r /= p; }
+   double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, v[3] = {0, 0, 0};
+   const double gs = (dim == 2) ? 0.5 : 0.25;
+   for (int c = 0; c < nc; c++)
+   {
+      int loc = 0, mul = 1;
+      for (int a = 0; a < dim; a++) { loc += (sc[a] + ((c >> a) & 1)) * mul; mul *= p + 1; }
+      const double *x0 = xlat0 + ((size_t)e * nd + loc) * dim;
+      for (int i = 0; i < dim; i++)
+      {
+         double x = x0[i];
+         if (exec_mode == 1)
+         {
+            const double vv = vel[((size_t)e * nd + loc) * dim + i];
+            x += t * vv;
+            v[i] += vv / nc;
+         }
+         for (int j = 0; j < dim; j++) { J[i][j] += x * (((c >> j) & 1) ? gs : -gs); }
+      }
+   }
+   if (exec_mode != 1) { for (int i = 0; i < dim; i++) { v[i] = vel[((size_t)e * ns + m) * dim + i]; } }
+   double adj[3][3];
+   if (dim == 2)
+   {
+      adj[0][0] = J[1][1]; adj[0][1] = -J[0][1]; adj[1][0] = -J[1][0]; adj[1][1] = J[0][0];
+   }
+   else
+   {
+      adj[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+      adj[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+      adj[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+      adj[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      adj[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+      adj[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+      adj[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      adj[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+      adj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+   }
+   double av[3] = {0, 0, 0};
+   for (int i = 0; i < dim; i++) { for (int j = 0; j < dim; j++) { av[i] += adj[i][j] * v[j]; } }
+   const double alpha = (exec_mode == 1) ? 1.0 : -1.0;
+   for (int c = 0; c < nc; c++)
+   {
+      double w = 0.0;
+      for (int j = 0; j < dim; j++) { w += (((c >> j) & 1) ? gs : -gs) * av[j]; }
+      SW[((size_t)e * ns + m) * nc + c] = alpha * w;
+   }
+}
+
+// ResidualDistribution with the subcell fluctuation redistribution, gamma = 1
+// (remhos_lo.cpp:164-239).  One warp per element; per-subcell quantities are staged in shared
+// memory and gathered per DOF in ascending subcell order (the reference's summation order).
+__global__ void k_lo_rd_sub(FaArgs A, int p, const double *SW, const double *u, const double *z,
+                            double *du)
+{
+   extern __shared__ double sh[];
+   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+   int ns = 1, nc = 1;
+   for (int a = 0; a < A.dim; a++) { ns *= p; nc *= 2; }
+   double *sub = sh + (size_t)wib * ns * 6;      // fP, fN, xmax, xmin, swP, swN per subcell
+   if (e >= A.ne) { return; }
+   const int ND = A.ND, D1 = A.D1;
+   const double *ue = u + e * ND;
+   double xmax = -INFINITY, xmin = INFINITY, xsum = 0.0, rhoP = 0.0, rhoN = 0.0;
+   for (int j = lane; j < ND; j += 32)
+   {
+      const double v = ue[j], zz = z[e * ND + j];
+      xmax = fmax(xmax, v); xmin = fmin(xmin, v); xsum += v;
+      rhoP += fmax(0.0, zz); rhoN += fmin(0.0, zz);
+   }
+   xmax = warp_max(xmax); xmin = warp_min(xmin);
+   xsum = warp_sum(xsum); rhoP = warp_sum(rhoP); rhoN = warp_sum(rhoN);
+   constexpr double eps = 1.0e-15, gamma = 1.0;
+   double sfP = 0.0, sfN = 0.0;
+   for (int m = lane; m < ns; m += 32)
+   {
+      int sc[3] = {0, 0, 0}, r = m;
+      for (int a = 0; a < A.dim; a++) { sc[a] = r % p; r /= p; }
+      double fl = 0.0, smax = -INFINITY, smin = INFINITY, ssum = 0.0;
+      for (int c = 0; c < nc; c++)
+      {
+         int loc = 0, mul = 1;
+         for (int a = 0; a < A.dim; a++) { loc += (sc[a] + ((c >> a) & 1)) * mul; mul *= D1; }
+         const double v = ue[loc];
+         fl += SW[((size_t)e * ns + m) * nc + c] * v;
+         smax = fmax(smax, v); smin = fmin(smin, v); ssum += v;
+      }
+      const double fP = fmax(0.0, fl), fN = fmin(0.0, fl);
+      sub[m * 6 + 0] = fP; sub[m * 6 + 1] = fN; sub[m * 6 + 2] = smax; sub[m * 6 + 3] = smin;
+      sub[m * 6 + 4] = nc * smax - ssum + eps; sub[m * 6 + 5] = nc * smin - ssum - eps;
+      sfP += fP; sfN += fN;
+   }
+   sfP = warp_sum(sfP); sfN = warp_sum(sfN);
+   __syncwarp();
+   const double sumWP = ND * xmax - xsum + eps, sumWN = ND * xmin - xsum - eps;
+   for (int j = lane; j < ND; j += 32)
+   {
+      int l[3];
+      dof_lattice(A.dim, D1, j, l);
+      const double ui = ue[j];
+      // nodal weights: subcells containing this lattice point, ascending subcell index
+      double nwP = 0.0, nwN = 0.0;
+      for (int k = 0; k < nc; k++)
+      {
+         // k enumerates the offsets (dz, dy, dx) in {-1, 0}: ascending m means descending offset bits
+         int m = 0, mul = 1;
+         bool ok = true;
+         for (int a = 0; a < A.dim; a++)
+         {
+            const int off = ((k >> a) & 1) ? 0 : -1;
+            const int s = l[a] + off;
+            if (s < 0 || s >= p) { ok = false; }
+            m += s * mul; mul *= p;
+         }
+         if (!ok) { continue; }
+         nwP += sub[m * 6 + 0] * ((sub[m * 6 + 2] - ui) / sub[m * 6 + 4]);   // eq. (58)
+         nwN += sub[m * 6 + 1] * ((sub[m * 6 + 3] - ui) / sub[m * 6 + 5]);   // eq. (59)
+      }
+      double wP = (xmax - ui) / sumWP, wN = (xmin - ui) / sumWN;
+      double aux = gamma / (rhoP + eps);
+      wP *= 1.0 - fmin(aux * sfP, 1.0);
+      wP += fmin(aux, 1.0 / (sfP + eps)) * nwP;
+      aux = gamma / (rhoN - eps);
+      wN *= 1.0 - fmin(aux * sfN, 1.0);
+      wN += fmax(aux, 1.0 / (sfN - eps)) * nwN;
+      const double s = lumped_faces(A, u, e, j, ui) + wP * rhoP + wN * rhoN;
+      du[e * ND + j] = s / A.ml[e * ND + j];
+   }
+}
+
 // ---- FluxBasedFCT (Zalesak), gather form: every DOF visits all its couplings of K_HO
 // (in-element via KH / M, across faces via BI of both sides); each flux is evaluated from both
 // ends with the same operands in the same order, so f_ji = -f_ij bit for bit.

@@ -163,6 +163,9 @@ ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int orde
    Check(rmh_ctx_create(&d, &ctx));
    u0.resize((size_t)ne * nd);
    Check(rmh_u0(problem, dim, (int64_t)ne * nd, xdof.data(), bb_min.data(), bb_max.data(), u0.data()));
+   xlat = xdof;
+   bdr_dofs = bd;
+   nbr_elem = nbe;
 }
 ParFiniteElementSpace::~ParFiniteElementSpace()
 {
@@ -190,6 +193,60 @@ void DiscreteUpwind::CalcLOSolution(const Vector &u, Vector &du) const
 void ResidualDistribution::CalcLOSolution(const Vector &u, Vector &du) const
 {
    Check(rmh_lo_res_dist(pfes.ctx, u.Read(), du.Write(), nullptr));
+}
+ResidualDistributionSubcell::ResidualDistributionSubcell(ParFiniteElementSpace &space)
+   : LOSolver(space)
+{
+   Verify(space.order > 1, "Subcell schemes require FE order > 1.");     // remhos.cpp:613-616
+   const int dim = space.dim, p = space.order, nf = 2 * dim;
+   int nd = 1, ns = 1, nc = 1, nfd = 1;
+   for (int a = 0; a < dim; a++) { nd *= p + 1; ns *= p; nc *= 2; }
+   for (int a = 0; a < dim - 1; a++) { nfd *= p + 1; }
+   const int64_t ne = space.GetNE();
+   std::vector<double> vel;
+   if (space.exec_mode == 1)
+   {
+      // v_sub_gf: velocity_function at the subcell vertices, zero on the boundary (remhos.cpp:838-852)
+      vel.resize((size_t)ne * nd * dim);
+      Check(rmh_velocity(space.problem, dim, ne * nd, space.xlat.data(), space.bb_min.data(),
+                         space.bb_max.data(), vel.data()));
+      for (int64_t e = 0; e < ne; e++)
+         for (int f = 0; f < nf; f++)
+         {
+            if (space.nbr_elem[(size_t)e * nf + f] >= 0) { continue; }
+            for (int j = 0; j < nfd; j++)
+            {
+               const int loc = space.bdr_dofs[(size_t)j * nf + f];
+               for (int c = 0; c < dim; c++) { vel[((size_t)e * nd + loc) * dim + c] = 0.0; }
+            }
+         }
+   }
+   else
+   {
+      // velocity at the subcell centres (midpoint rule of MixedConvectionIntegrator)
+      std::vector<double> xc((size_t)ne * ns * dim, 0.0);
+      for (int64_t e = 0; e < ne; e++)
+         for (int m = 0; m < ns; m++)
+         {
+            int sc[3] = {0, 0, 0}, r = m;
+            for (int a = 0; a < dim; a++) { sc[a] = r % p; r /= p; }
+            for (int c = 0; c < nc; c++)
+            {
+               int loc = 0, mul = 1;
+               for (int a = 0; a < dim; a++) { loc += (sc[a] + ((c >> a) & 1)) * mul; mul *= p + 1; }
+               for (int i = 0; i < dim; i++)
+               { xc[((size_t)e * ns + m) * dim + i] += space.xlat[((size_t)e * nd + loc) * dim + i] / nc; }
+            }
+         }
+      vel.resize(xc.size());
+      Check(rmh_velocity(space.problem, dim, ne * ns, xc.data(), space.bb_min.data(),
+                         space.bb_max.data(), vel.data()));
+   }
+   Check(rmh_subcell_setup(space.ctx, space.xlat.data(), vel.data(), nullptr));
+}
+void ResidualDistributionSubcell::CalcLOSolution(const Vector &u, Vector &du) const
+{
+   Check(rmh_lo_res_dist_subcell(pfes.ctx, u.Read(), du.Write(), nullptr));
 }
 void MassBasedAvg::CalcLOSolution(const Vector &u, Vector &du) const
 {
@@ -407,7 +464,7 @@ void usage(std::ostream &os)
 {
    os << "Usage: remhos [options]\n"
          "  -m <mesh>  -dim <d>  -epm <n>  -p <problem>  -rs <n>  -rp <n>  -o <order>  -mo <order>\n"
-         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|3>  -lo <0|1|3|5>  -fct <0|1|2>  -mono <0>\n"
+         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|2|3>  -lo <0|1|3|4|5>  -fct <0|1|2>  -mono <0>\n"
          "  -bt <0|1>  -pa/-no-pa  -full/-no-full  -d <device>  -gam/-no-gam  -si <0>  -tf <t>\n"
          "  -dtc <0>  -dt <dt>  -ms <steps>  -vis/-no-vis  -save/-no-save  -visit/-no-visit\n"
          "  -vb/-no-vb  -ps/-no-ps  -vs <steps>  -pool <GB>\n";
@@ -487,9 +544,15 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       return 3;
    }
    Verify(o.mono == 0, "monolithic solvers (-mono) are not part of this build");
-   Verify(o.ho == 0 || o.ho == 3, "only -ho 0 and -ho 3 (LocalInverse) are part of this build");
-   Verify(o.lo == 0 || o.lo == 1 || o.lo == 3 || o.lo == 5,
-          "only -lo 0, 1 (DiscreteUpwind), 3 (ResidualDistribution), 5 (MassBasedAvg) are part of this build");
+   // -ho 2 (CGHOSolver, remhos_ho.cpp:30-70) solves the block-diagonal system M du = K u by PCG to
+   // a relative tolerance of 1e-12: on this path it is served by the exact element-local inverse
+   Verify(o.ho == 0 || o.ho == 2 || o.ho == 3,
+          "only -ho 0, -ho 2 (CG, served by the exact local inverse) and -ho 3 (LocalInverse) are part of this build");
+   if (o.ho == 2) { o.ho = 3; }
+   Verify(o.lo == 0 || o.lo == 1 || o.lo == 3 || o.lo == 4 || o.lo == 5,
+          "only -lo 0, 1 (DiscreteUpwind), 3 (ResidualDistribution), 4 (ResidualDistributionSubcell), "
+          "5 (MassBasedAvg) are part of this build");
+   if (o.lo == 4) { Verify(o.order > 1, "Subcell schemes require FE order > 1."); }
    Verify(o.fct >= 0 && o.fct <= 2, "only -fct 0, 1 (FluxBased), 2 (ClipScale) are part of this build");
    Verify(!o.ps, "product remap (-ps) is not part of this build");
    Verify(o.si == 0, "smoothness indicators (-si) are not part of this build");
@@ -530,6 +593,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       LOSolver *lo_solver = nullptr;
       if (o.lo == 1) { lo_solver = new DiscreteUpwind(pfes); }
       else if (o.lo == 3) { lo_solver = new ResidualDistribution(pfes); }
+      else if (o.lo == 4) { lo_solver = new ResidualDistributionSubcell(pfes); }
       else if (o.lo == 5) { lo_solver = new MassBasedAvg(pfes, *ho_solver); }
       FCTSolver *fct_solver = nullptr;
       if (o.fct == 1) { fct_solver = new FluxBasedFCT(pfes, dt); }

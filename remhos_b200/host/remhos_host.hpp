@@ -69,6 +69,8 @@ public:
    int dim = 0, order = 0, mesh_order = 2, exec_mode = 0, bounds_type = 0, problem = 0;
    std::vector<double> bb_min, bb_max;
    std::vector<double> u0;          // ProjectCoefficient(u0_function) (remhos.cpp:883)
+   std::vector<double> xlat;        // lattice points i/p of every element at t = 0 [ne][nd][dim]
+   std::vector<int32_t> bdr_dofs, nbr_elem;   // BdrDofs [nfd][nf]; face neighbours [ne][nf]
    double dt_cfl = 0.0;
    double t_final = 0.0;
    ParFiniteElementSpace(rmh_mesh *m, int problem, int order, int mesh_order, int bounds_type,
@@ -131,6 +133,16 @@ public:
    ResidualDistribution(ParFiniteElementSpace &space) : LOSolver(space) {}
    void CalcLOSolution(const Vector &u, Vector &du) const override;
    int Type() const override { return 3; }
+};
+
+// -lo 4: the subcell variant; the constructor builds the low-order refined mesh data
+// (remhos.cpp:797-868) and hands it to the device
+class ResidualDistributionSubcell : public LOSolver
+{
+public:
+   ResidualDistributionSubcell(ParFiniteElementSpace &space);
+   void CalcLOSolution(const Vector &u, Vector &du) const override;
+   int Type() const override { return 4; }
 };
 
 class MassBasedAvg : public LOSolver

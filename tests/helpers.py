@@ -33,3 +33,19 @@ def ctx_from_oracle(run, bounds_type=None, use_nodal_velocity=False):
 def rel_err(a, b):
     a = np.asarray(a); b = np.asarray(b)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def subcell_setup_from_oracle(run, ctx):
+    """Hand the oracle's low-order refined mesh data (lattice points, velocity samples) to the
+    context, as the driver does after building its subcell mesh (remhos.cpp:797-868)."""
+    from remhos_oracle import dg, subcell
+    sp = run.space
+    dim = sp.dim
+    xlat = sp.dof_points(run.disc.X0)
+    if run.exec_mode == 1:
+        vel = run.vel(xlat)
+        vel = np.where(subcell._boundary_lattice_mask(run)[:, :, None], 0.0, vel)
+    else:
+        s2i = dg.sub2ind(sp.p, dim)
+        vel = run.vel(xlat[:, s2i, :].mean(axis=2))
+    ctx.subcell_setup(xlat, vel)

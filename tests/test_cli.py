@@ -69,6 +69,19 @@ CLI_KNOWN = [
       '-lo', 1, '-fct', 1, '-no-vis'], 0.3888354875, 0.9979069772),
     (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 3,
       '-lo', 3, '-fct', 2, '-no-vis'], 0.3888354875, 0.9755502191),
+    # -lo 4 (subcell RD) rows: out_baseline.dat:41-69; -ho 2 ... -pa rows :76-100 run verbatim
+    (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 3,
+      '-lo', 4, '-fct', 2, '-no-vis'], 0.3888354875, 0.9850024108),
+    (['-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 3, '-dt', 0.004, '-tf', 0.8, '-ho', 3,
+      '-lo', 4, '-fct', 2, '-no-vis'], 0.1623263888, 0.7145371968),
+    (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 3,
+      '-lo', 4, '-fct', 2, '-no-vis'], 0.9607429525, 0.9334903111),
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-dt', 0.0015, '-tf', 0.75, '-ho', 3,
+      '-lo', 4, '-fct', 2, '-no-vis'], 0.0847954729, 0.7581364675),
+    (['-m', mesh('cube01_hex.mesh'), '-p', 10, '-rs', 1, '-o', 2, '-dt', 0.02, '-tf', 0.7, '-ho', 3,
+      '-lo', 4, '-fct', 2, '-no-vis'], 0.1197299801, 0.9997499683),
+    (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 2,
+      '-lo', 3, '-fct', 2, '-pa', '-no-vis'], 0.3888354875, 0.9755502191),
     # autotest/out_baseline.dat:177-180 and :103-106 (mass and max, 10 digits)
     (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 3,
       '-lo', 1, '-fct', 1, '-no-vis'], 0.9607429525, 0.9984668427),

@@ -8,7 +8,7 @@ Tolerances: single-kernel outputs 1e-11 of the field's max norm; whole runs 1e-1
 import numpy as np
 import pytest
 
-from helpers import oracle_run, ctx_from_oracle, rel_err
+from helpers import oracle_run, ctx_from_oracle, rel_err, subcell_setup_from_oracle
 
 torch = pytest.importorskip('torch')
 pytestmark = pytest.mark.gpu
@@ -78,6 +78,23 @@ def test_residual_distribution(setup):
     assert rel_err(host(out, u.shape), ref) < TOL
 
 
+def test_residual_distribution_subcell(setup):
+    run, ctx, u = setup
+    if run.space.p < 2:
+        import remhos_b200 as rb
+        with pytest.raises(rb.RmhError):
+            subcell_setup_from_oracle(run, ctx)          # remhos.cpp:613-616
+        return
+    subcell_setup_from_oracle(run, ctx)
+    at_time(run, ctx, 0.3)
+    run._t = 0.3 if run.exec_mode == 1 else 0.0
+    run.subcell_weights = None
+    ref = run.disc.lo_residual_distribution(u, run.get_subcell_weights())
+    out = empty(ctx)
+    ctx.lo_res_dist_subcell(dev(u), out)
+    assert rel_err(host(out, u.shape), ref) < TOL
+
+
 def test_lo_solutions_conserve_mass(setup):
     """sum_i m_i du_i of DU and RD equals the net lumped face flux; on periodic meshes with a
     divergence-free velocity it vanishes."""
@@ -138,7 +155,7 @@ def test_mult_rejects_unsupported(setup):
     import remhos_b200 as rb
     run, ctx, u = setup
     k = empty(ctx)
-    for combo in [(1, 1, 2), (3, 4, 2), (3, 1, 3), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
+    for combo in [(1, 1, 2), (3, 2, 2), (3, 1, 3), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
         with pytest.raises(rb.RmhError):
             ctx.mult(*combo, 0.0, 0.01, dev(u), k)
 
@@ -167,6 +184,15 @@ RUNS = [
                                   ho_type=3, lo_type=5, fct_type=2, ode_solver=6), 1),
     ('periodic-square.mesh', dict(problem=0, rs_levels=2, order=2, dt=0.004, t_final=0.8,
                                   ho_type=3, lo_type=0, fct_type=0, ode_solver=1), 10),
+    # subcell residual distribution (-lo 4), transport and remap
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=1, order=3, dt=0.005, t_final=2.5,
+                                   ho_type=3, lo_type=4, fct_type=2, ode_solver=3), 8),
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=2, dt=0.015, t_final=2.0,
+                                ho_type=3, lo_type=4, fct_type=2, ode_solver=3), 5),
+    ('inline-quad.mesh', dict(problem=14, rs_levels=1, order=3, dt=0.0015, t_final=0.75,
+                              ho_type=3, lo_type=4, fct_type=2, ode_solver=3), 8),
+    ('cube01_hex.mesh', dict(problem=10, rs_levels=1, order=2, dt=0.02, t_final=0.7,
+                             ho_type=3, lo_type=4, fct_type=1, ode_solver=2), 4),
     # IDP Runge-Kutta solvers (-s 11/12/13/14/16, remhos_solvers.cpp)
     ('periodic-square.mesh', dict(problem=5, rs_levels=2, order=2, dt=0.004, t_final=0.8,
                                   ho_type=3, lo_type=1, fct_type=2, ode_solver=11), 6),
@@ -189,6 +215,8 @@ def test_ode_steps_match_oracle(mesh, opt, steps):
     ctx = ctx_from_oracle(run)
     if opt['lo_type'] == 1 or opt['fct_type'] == 1:
         ctx.fa_setup()
+    if opt['lo_type'] == 4:
+        subcell_setup_from_oracle(run, ctx)
     u = dev(run.u)
     t, dt = 0.0, run.dt
     for _ in range(steps):

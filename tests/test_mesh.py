@@ -11,7 +11,8 @@ from remhos_oracle import mesh as om, dg
 
 CASES = [('periodic-square.mesh', 2, 3), ('periodic-square.mesh', 1, 1), ('inline-quad.mesh', 2, 2),
          ('inline-quad.mesh', 1, 4), ('cube01_hex.mesh', 1, 2), ('cube01_hex.mesh', 2, 3),
-         ('periodic-cube.mesh', 1, 3), ('periodic-cube.mesh', 0, 4), ('periodic-cube.mesh', 1, 1)]
+         ('periodic-cube.mesh', 1, 3), ('periodic-cube.mesh', 0, 4), ('periodic-cube.mesh', 1, 1),
+         ('periodic-hexagon.mesh', 2, 3), ('periodic-hexagon.mesh', 1, 2)]
 
 
 @pytest.mark.parametrize('mesh,rs,p', CASES)

@@ -41,6 +41,17 @@ BASELINE = [
                                    lo_type=1, fct_type=1), 0.3888354875, 0.9979069772),  # :167-170
     ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=3,
                                    lo_type=3, fct_type=2), 0.3888354875, 0.9755502191),  # :93-96
+    # subcell residual distribution (-lo 4): out_baseline.dat:56-69, :41-49
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=3,
+                                   lo_type=4, fct_type=2), 0.3888354875, 0.9850024108),
+    ('periodic-square.mesh', dict(problem=5, rs_levels=3, dt=0.004, t_final=0.8, ho_type=3,
+                                  lo_type=4, fct_type=2), 0.1623263888, 0.7145371968),
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=2, dt=0.015, t_final=2, ho_type=3,
+                                lo_type=4, fct_type=2), 0.9607429525, 0.9334903111),
+    ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
+                              lo_type=4, fct_type=2), 0.0847954729, 0.7581364675),
+    ('cube01_hex.mesh', dict(problem=10, rs_levels=1, order=2, dt=0.02, t_final=0.7, ho_type=3,
+                             lo_type=4, fct_type=2), 0.1197299801, 0.9997499683),
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
                               lo_type=1, fct_type=1), 0.08479546845, 0.905654904),       # :152-155
     ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=3,
@@ -49,7 +60,8 @@ BASELINE = [
 
 
 @pytest.mark.parametrize('mesh,opt,mass,umax', BASELINE,
-                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT', 'hexagon-DU-fluxFCT', 'hexagon-RD-clipscale',
+                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT', 'hexagon-DU-fluxFCT', 'hexagon-RD-clipscale', 'hexagon-RDsub', 'square-RDsub', 'cube-RDsub',
+                              'quad-remap-RDsub', 'hex-remap-RDsub',
                               'quad-remap-DU-fluxFCT', 'quad-remap-RD-clipscale'])
 def test_autotest_baseline(mesh, opt, mass, umax):
     r = run(mesh, **opt)
