@@ -178,6 +178,13 @@ int rmh_fa_get(rmh_ctx *ctx, int which, double *host_out);
  * (remhos_tools.cpp:1464-1487) and Assembly::LinearFluxLumping, alpha = 0 (:876-913).
  * Needs rmh_fa_setup. */
 int rmh_lo_discrete_upwind(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
+/* DiscreteUpwind on the preconditioned convection blocks M_L M^-1 K (-lo 2; remhos.cpp:749-771,
+ * PrecondConvectionIntegrator remhos_tools.cpp:975-1031).  Needs rmh_fa_setup. */
+int rmh_lo_discrete_upwind_prec(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
+/* NeumannHOSolver::CalcHOSolution (-ho 1; remhos_ho.cpp:136-187): rhs = k u + Galerkin face terms
+ * (LinearFluxLumping with alpha = 1, remhos_tools.cpp:876-913), then at most 20 Neumann sweeps
+ * du -= (M du - rhs)/m_L, stopped at |res|_2 <= 1e-4.  FA only: needs rmh_fa_setup. */
+int rmh_ho_neumann(rmh_ctx *ctx, const double *u_dev, double *du_dev, void *stream);
 /* ResidualDistribution / PAResidualDistribution::CalcLOSolution without subcells
  * (remhos_lo.cpp:111-245, 967-1035; -lo 2 / -lo 3): matrix-free */
 int rmh_lo_res_dist(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
@@ -214,7 +221,7 @@ int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
                        void *stream);
 
 /* LimitedTimeDependentOperator::Mult (remhos_solvers.hpp:46-50) for any supported combination of
- * -ho {0,3} -lo {0,1,3,4,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
+ * -ho {0,1,3} -lo {0,1,2,3,4,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
  * remhos.cpp:1598-1677): k = F(u; t, dt).  Orchestrates the separate kernels exactly as
  * MultUnlimited / LimitMult do (remhos.cpp:1596-1739, 1798-1916); -ho 3 -lo 5 -fct 2 runs the
  * fused stage kernel. */

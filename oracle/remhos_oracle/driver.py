@@ -139,7 +139,7 @@ class Run:
             d.assemble(t)
         A = d.cur
         if o.fct_type:
-            du_ho = d.ho_local_inverse(u)
+            du_ho = self.calc_ho(u)
             du_lo = self.calc_lo(u, du_ho, dt)
             umin, umax = d.bounds(u, o.bounds_type)
             if o.verify_bounds:
@@ -155,7 +155,12 @@ class Run:
             return du
         if o.lo_type:
             return self.calc_lo(u, None, dt)
-        return d.ho_local_inverse(u)
+        return self.calc_ho(u)
+
+    def calc_ho(self, u):
+        if self.opt.ho_type == 1:
+            return self.disc.ho_neumann(u)
+        return self.disc.ho_local_inverse(u)                  # -ho 3, and -ho 2 (CG to 1e-12)
 
     def mult_unlimited(self, u, t, dt):
         """AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739)."""
@@ -164,10 +169,10 @@ class Run:
         if self.exec_mode == 1:
             d.assemble(t)
         if o.fct_type:
-            return d.ho_local_inverse(u)
+            return self.calc_ho(u)
         if o.lo_type:
             return self.calc_lo(u, None, dt)
-        return d.ho_local_inverse(u)
+        return self.calc_ho(u)
 
     def limit_mult(self, u, du_ho, dt):
         """AdvectionOperator::LimitMult (remhos.cpp:1798-1916): du_ho is the (combined) HO rate."""
@@ -247,10 +252,12 @@ class Run:
         o, d = self.opt, self.disc
         if o.lo_type == 5:
             if du_ho is None:
-                du_ho = d.ho_local_inverse(u)
+                du_ho = self.calc_ho(u)
             return d.lo_mass_based_avg(u, du_ho, dt)
         if o.lo_type == 1:
             return d.lo_discrete_upwind(u)
+        if o.lo_type == 2:
+            return d.lo_discrete_upwind(u, prec=True)
         if o.lo_type == 3:
             return d.lo_residual_distribution(u)
         if o.lo_type == 4:

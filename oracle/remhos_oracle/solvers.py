@@ -127,9 +127,32 @@ class Discretization:
             np.add.at(y, (slice(None), sp.bd[:, f]), contrib[:, f, :])
         return y
 
-    def lo_discrete_upwind(self, u):
+    def ho_neumann(self, u):
+        """NeumannHOSolver::CalcHOSolution (remhos_ho.cpp:136-187): rhs = k u + Galerkin face terms
+        (LinearFluxLumping with alpha = 1, inflow exterior state), then the Neumann iteration
+        du <- du - (M du - rhs)/m_L, at most 20 sweeps, stop at |res|_2 <= 1e-4 (global norm)."""
+        A, sp = self.cur, self.sp
+        rhs = np.einsum('eij,ej->ei', A.K, u)
+        diff = self.face_diffs(u, self.inflow)
+        contrib = np.einsum('efij,efj->efi', A.bdrInt, diff)
+        for f in range(sp.nf):
+            np.add.at(rhs, (slice(None), sp.bd[:, f]), contrib[:, f, :])
+        du = np.zeros_like(u)
+        for _ in range(20):
+            res = np.einsum('eij,ej->ei', A.M, du) - rhs
+            if np.sqrt((res * res).sum()) <= 1.0e-4:
+                break
+            du = du - res / A.ml
+        return du
+
+    def precond_conv(self):
+        """PrecondConvectionIntegrator (remhos_tools.cpp:975-1031): M_L M^-1 K per element."""
         A = self.cur
-        D = self.du_matrix(A.K)
+        return A.ml[:, :, None] * np.linalg.solve(A.M, A.K)
+
+    def lo_discrete_upwind(self, u, prec=False):
+        A = self.cur
+        D = self.du_matrix(self.precond_conv() if prec else A.K)
         y = np.einsum('eij,ej->ei', D, u) + self.lumped_face_terms(u)
         return y / A.ml
 

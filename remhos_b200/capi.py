@@ -252,6 +252,12 @@ class Context:
     def lo_discrete_upwind(self, u, du_lo, s=0):
         check(lib().rmh_lo_discrete_upwind(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
 
+    def lo_discrete_upwind_prec(self, u, du_lo, s=0):
+        check(lib().rmh_lo_discrete_upwind_prec(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
+
+    def ho_neumann(self, u, du, s=0):
+        check(lib().rmh_ho_neumann(self.h, _dp(u), _dp(du), C.c_void_p(s)))
+
     def lo_res_dist(self, u, du_lo, s=0):
         check(lib().rmh_lo_res_dist(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
 

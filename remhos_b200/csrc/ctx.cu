@@ -81,6 +81,8 @@ struct rmh_ctx
    // matrix-based ("FA") solver data: lumped face matrices always; dense blocks after rmh_fa_setup
    double *dG = nullptr, *BL = nullptr;
    double *faK = nullptr, *faKH = nullptr, *faM = nullptr, *faBI = nullptr;
+   double *faKP = nullptr;     // M_L M^-1 K (PrecondConvectionIntegrator), valid at time kp_t
+   double kp_t = -1.0e300;
    int16_t *pat_idx = nullptr;
    uint8_t *pat_face = nullptr;
    bool fa_on = false;
@@ -1789,6 +1791,65 @@ extern "C" int rmh_lo_discrete_upwind(rmh_ctx *c, const double *u, double *du_lo
    return 0;
 }
 
+// PrecondConvectionIntegrator blocks M_L M^-1 K (remhos_tools.cpp:975-1031), column by column
+// through the exact element mass inverse; rebuilt when the mesh has moved
+static int build_precond_conv(rmh_ctx *c, cudaStream_t s)
+{
+   if (c->faKP && (c->exec_mode == 0 || c->kp_t == c->t_cur)) { return 0; }
+   const size_t nn = (size_t)c->ne * c->ND * c->ND;
+   if (!c->faKP) { if (dev_alloc(c, &c->faKP, nn)) { return 1; } }
+   if (work_vec(c, &c->wk[0]) || work_vec(c, &c->wk[1])) { return 1; }
+   const int bs = 256;
+   const unsigned nb = (unsigned)((c->N + bs - 1) / bs);
+   for (int j = 0; j < c->ND; j++)
+   {
+      k_col_get<<<nb, bs, 0, s>>>(c->ne, c->ND, j, c->faK, c->wk[0]);
+      LAUNCH_OK();
+      if (dispatch_ho(c, ho_args(c, c->wk[0], c->wk[1], 2), s)) { return 1; }
+      k_col_put<<<nb, bs, 0, s>>>(c->ne, c->ND, j, c->wk[1], c->ml, c->faKP);
+      LAUNCH_OK();
+   }
+   c->kp_t = c->t_cur;
+   return 0;
+}
+
+extern "C" int rmh_lo_discrete_upwind_prec(rmh_ctx *c, const double *u, double *du_lo, void *stream)
+{
+   if (!c->fa_on) { set_error("rmh_lo_discrete_upwind_prec: call rmh_fa_setup first (assembled K, M)"); return 1; }
+   if (build_precond_conv(c, (cudaStream_t)stream)) { return 1; }
+   FaArgs A = fa_args(c);
+   A.K = c->faKP;
+   const int bs = std::min(256, ((c->ND + 31) / 32) * 32);
+   k_lo_du<<<(unsigned)c->ne, bs, c->ND * sizeof(double), (cudaStream_t)stream>>>(A, u, du_lo);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_ho_neumann(rmh_ctx *c, const double *u, double *du, void *stream)
+{
+   if (!c->fa_on) { set_error("rmh_ho_neumann: call rmh_fa_setup first (the Neumann solver is FA only, remhos_ho.cpp:138-139)"); return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   if (work_vec(c, &c->wk[0]) || work_vec(c, &c->wk[1])) { return 1; }
+   double *rhs = c->wk[0], *res = c->wk[1];
+   if (dispatch_ho(c, ho_args(c, u, rhs, 1 | 4), s)) { return 1; }
+   const int bs = 256;
+   const unsigned nb = (unsigned)((c->N + bs - 1) / bs);
+   k_face_galerkin<<<nb, bs, 0, s>>>(fa_args(c), u, rhs);
+   LAUNCH_OK();
+   CUDA_OK(cudaMemsetAsync(du, 0, (size_t)c->N * sizeof(double), s));
+   for (int iter = 1; iter <= 20; iter++)
+   {
+      k_mass_residual<<<nb, bs, 0, s>>>(c->ne, c->ND, c->faM, du, rhs, res);
+      LAUNCH_OK();
+      double r2 = 0.0;
+      if (rmh_reduce(c, 0, res, res, &r2, stream)) { return 1; }
+      if (std::sqrt(r2) <= 1.0e-4) { return 0; }
+      k_neumann_update<<<nb, bs, 0, s>>>(c->N, res, c->ml, du);
+      LAUNCH_OK();
+   }
+   return 0;
+}
+
 extern "C" int rmh_lo_res_dist(rmh_ctx *c, const double *u, double *du_lo, void *stream)
 {
    // z = K u with the volume-only convection operator (sum-factorised), then the element-local
@@ -1858,15 +1919,15 @@ extern "C" int rmh_fct_flux_based(rmh_ctx *c, double dt, const double *u, const 
 
 static int check_combo(int ho_type, int lo_type, int fct_type)
 {
-   if (ho_type != 0 && ho_type != 3)
-   { set_error("stage operator: HO solver must be 3 (LocalInverse) or 0"); return 1; }
-   if (lo_type < 0 || lo_type > 5 || lo_type == 2)
-   { set_error("stage operator: LO solver must be 0, 1 (DiscreteUpwind), 3 (ResidualDistribution), 4 (ResidualDistributionSubcell) or 5 (MassBasedAvg)"); return 1; }
+   if (ho_type != 0 && ho_type != 1 && ho_type != 3)
+   { set_error("stage operator: HO solver must be 0, 1 (Neumann) or 3 (LocalInverse)"); return 1; }
+   if (lo_type < 0 || lo_type > 5)
+   { set_error("stage operator: LO solver must be 0 .. 5"); return 1; }
    if (fct_type < 0 || fct_type > 2)
    { set_error("stage operator: FCT solver must be 0, 1 (FluxBased) or 2 (ClipScale)"); return 1; }
-   if (fct_type && (ho_type != 3 || lo_type == 0))
+   if (fct_type && (ho_type == 0 || lo_type == 0))
    { set_error("FCT requires HO and LO solvers."); return 1; }        // remhos.cpp:1690
-   if (!fct_type && lo_type == 5 && ho_type != 3)
+   if (!fct_type && lo_type == 5 && ho_type == 0)
    { set_error("Mass-Based LO solver requires a choice of a HO solver."); return 1; }   // remhos.cpp:991
    if (!ho_type && !lo_type) { set_error("No solver was chosen."); return 1; }          // remhos.cpp:1711
    return 0;
@@ -1880,17 +1941,20 @@ extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_
    if (check_combo(ho_type, lo_type, fct_type)) { return 1; }
    if (k == u) { set_error("rmh_mult_unlimited: output must not alias the input"); return 1; }
    if (rmh_set_time(c, t, stream)) { return 1; }
-   if (fct_type) { return rmh_ho_local_inverse(c, u, k, stream); }
+   auto HO = [&](double *out)
+   { return ho_type == 1 ? rmh_ho_neumann(c, u, out, stream) : rmh_ho_local_inverse(c, u, out, stream); };
+   if (fct_type) { return HO(k); }
    if (lo_type == 1) { return rmh_lo_discrete_upwind(c, u, k, stream); }
+   if (lo_type == 2) { return rmh_lo_discrete_upwind_prec(c, u, k, stream); }
    if (lo_type == 3) { return rmh_lo_res_dist(c, u, k, stream); }
    if (lo_type == 4) { return rmh_lo_res_dist_subcell(c, u, k, stream); }
    if (lo_type == 5)
    {
       if (work_vec(c, &c->wk[3])) { return 1; }
-      if (rmh_ho_local_inverse(c, u, c->wk[3], stream)) { return 1; }
+      if (HO(c->wk[3])) { return 1; }
       return rmh_lo_mass_avg(c, dt, u, c->wk[3], k, stream);
    }
-   return rmh_ho_local_inverse(c, u, k, stream);
+   return HO(k);
 }
 
 // AdvectionOperator::LimitMult (remhos.cpp:1798-1916): k holds the (possibly combined) HO rate
@@ -1900,12 +1964,14 @@ extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, 
 {
    if (!fct_type) { return 0; }
    if (check_combo(3, lo_type, fct_type)) { return 1; }
+   if (k == u) { set_error("rmh_limit_mult: the rate must not alias the state"); return 1; }
    for (int i = 3; i < 7; i++) { if (work_vec(c, &c->wk[i])) { return 1; } }
    double *du_ho = c->wk[3], *du_lo = c->wk[4], *xmn = c->wk[5], *xmx = c->wk[6];
    CUDA_OK(cudaMemcpyAsync(du_ho, k, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));
    if (lo_type == 5) { if (rmh_lo_mass_avg(c, dt, u, du_ho, du_lo, stream)) { return 1; } }
    else if (lo_type == 1) { if (rmh_lo_discrete_upwind(c, u, du_lo, stream)) { return 1; } }
+   else if (lo_type == 2) { if (rmh_lo_discrete_upwind_prec(c, u, du_lo, stream)) { return 1; } }
    else if (lo_type == 4) { if (rmh_lo_res_dist_subcell(c, u, du_lo, stream)) { return 1; } }
    else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
    if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }

@@ -270,6 +270,73 @@ __global__ void k_lo_rd(FaArgs A, const double *u, const double *z, double *du)
    }
 }
 
+// ---- NeumannHOSolver pieces (remhos_ho.cpp:136-187)
+// rhs_i += sum over the faces containing i of sum_b bdrInt(a,b) (u_nbr(b) - u_own(b)):
+// LinearFluxLumping with alpha = 1 (the Galerkin face term), inflow exterior state
+__global__ void k_face_galerkin(FaArgs A, const double *u, double *rhs)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= A.ne * A.ND) { return; }
+   const int64_t e = idx / A.ND;
+   const int i = (int)(idx - e * A.ND);
+   int l[3];
+   dof_lattice(A.dim, A.D1, i, l);
+   double s = 0.0;
+   for (int ax = 0; ax < A.dim; ax++)
+   {
+      for (int side = 0; side < 2; side++)
+      {
+         if (l[ax] != side * (A.D1 - 1)) { continue; }
+         const int f = face_of(A.dim, ax, side);
+         const int a = face_nat_index(A.dim, A.D1, l, ax);
+         const double *BIe = A.BI + ((size_t)e * A.NF + f) * A.NFD * A.NFD + (size_t)a * A.NFD;
+         for (int b = 0; b < A.NFD; b++)
+         {
+            const int jb = face_dof_rt(A.dim, A.D1, f, b);
+            const double infl = A.inflow ? A.inflow[e * A.ND + jb] : 0.0;
+            const double un = nbr_value(A, u, e, f, b, infl);
+            s += BIe[b] * (un - u[e * A.ND + jb]);
+         }
+      }
+   }
+   rhs[idx] += s;
+}
+// res = M du - rhs with the dense element mass blocks
+__global__ void k_mass_residual(int64_t ne, int ND, const double *M, const double *du,
+                                const double *rhs, double *res)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * ND) { return; }
+   const int64_t e = idx / ND;
+   const int i = (int)(idx - e * ND);
+   const double *Me = M + (size_t)e * ND * ND + (size_t)i * ND, *de = du + e * ND;
+   double s = 0.0;
+   for (int j = 0; j < ND; j++) { s += Me[j] * de[j]; }
+   res[idx] = s - rhs[idx];
+}
+__global__ void k_neumann_update(int64_t n, const double *res, const double *ml, double *du)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { du[i] -= res[i] / ml[i]; }
+}
+// column j of the dense element blocks <-> a DOF vector (used to form M_L M^-1 K column-wise)
+__global__ void k_col_get(int64_t ne, int ND, int j, const double *K, double *v)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * ND) { return; }
+   const int64_t e = idx / ND;
+   const int i = (int)(idx - e * ND);
+   v[idx] = K[(size_t)e * ND * ND + (size_t)i * ND + j];
+}
+__global__ void k_col_put(int64_t ne, int ND, int j, const double *v, const double *ml, double *KP)
+{
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= ne * ND) { return; }
+   const int64_t e = idx / ND;
+   const int i = (int)(idx - e * ND);
+   KP[(size_t)e * ND * ND + (size_t)i * ND + j] = ml[idx] * v[idx];
+}
+
 // ---- subcell residual distribution (-lo 4)
 // SubcellWeights(k)(m, j) = alpha grad_ref(phi_j)(centre) . adj(J_sub) . v(centre) on the straight-
 // sided subcells spanned by the lattice points (Assembly::ComputeSubcellWeights,

@@ -182,13 +182,24 @@ void LocalInverseHOSolver::CalcHOSolution(const Vector &u, Vector &du) const
    Check(rmh_ho_local_inverse(pfes.ctx, u.Read(), du.Write(), nullptr));
 }
 
-DiscreteUpwind::DiscreteUpwind(ParFiniteElementSpace &space) : LOSolver(space)
+NeumannHOSolver::NeumannHOSolver(ParFiniteElementSpace &space) : HOSolver(space)
+{
+   Check(rmh_fa_setup(space.ctx, nullptr));
+}
+void NeumannHOSolver::CalcHOSolution(const Vector &u, Vector &du) const
+{
+   Check(rmh_ho_neumann(pfes.ctx, u.Read(), du.Write(), nullptr));
+}
+
+DiscreteUpwind::DiscreteUpwind(ParFiniteElementSpace &space, bool preconditioned)
+   : LOSolver(space), prec(preconditioned)
 {
    Check(rmh_fa_setup(space.ctx, nullptr));
 }
 void DiscreteUpwind::CalcLOSolution(const Vector &u, Vector &du) const
 {
-   Check(rmh_lo_discrete_upwind(pfes.ctx, u.Read(), du.Write(), nullptr));
+   if (prec) { Check(rmh_lo_discrete_upwind_prec(pfes.ctx, u.Read(), du.Write(), nullptr)); }
+   else { Check(rmh_lo_discrete_upwind(pfes.ctx, u.Read(), du.Write(), nullptr)); }
 }
 void ResidualDistribution::CalcLOSolution(const Vector &u, Vector &du) const
 {
@@ -464,7 +475,7 @@ void usage(std::ostream &os)
 {
    os << "Usage: remhos [options]\n"
          "  -m <mesh>  -dim <d>  -epm <n>  -p <problem>  -rs <n>  -rp <n>  -o <order>  -mo <order>\n"
-         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|2|3>  -lo <0|1|3|4|5>  -fct <0|1|2>  -mono <0>\n"
+         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|1|2|3>  -lo <0..5>  -fct <0|1|2>  -mono <0>\n"
          "  -bt <0|1>  -pa/-no-pa  -full/-no-full  -d <device>  -gam/-no-gam  -si <0>  -tf <t>\n"
          "  -dtc <0>  -dt <dt>  -ms <steps>  -vis/-no-vis  -save/-no-save  -visit/-no-visit\n"
          "  -vb/-no-vb  -ps/-no-ps  -vs <steps>  -pool <GB>\n";
@@ -546,12 +557,10 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    Verify(o.mono == 0, "monolithic solvers (-mono) are not part of this build");
    // -ho 2 (CGHOSolver, remhos_ho.cpp:30-70) solves the block-diagonal system M du = K u by PCG to
    // a relative tolerance of 1e-12: on this path it is served by the exact element-local inverse
-   Verify(o.ho == 0 || o.ho == 2 || o.ho == 3,
-          "only -ho 0, -ho 2 (CG, served by the exact local inverse) and -ho 3 (LocalInverse) are part of this build");
+   Verify(o.ho >= 0 && o.ho <= 3, "HO solver type must be 0 .. 3");
    if (o.ho == 2) { o.ho = 3; }
-   Verify(o.lo == 0 || o.lo == 1 || o.lo == 3 || o.lo == 4 || o.lo == 5,
-          "only -lo 0, 1 (DiscreteUpwind), 3 (ResidualDistribution), 4 (ResidualDistributionSubcell), "
-          "5 (MassBasedAvg) are part of this build");
+   Verify(!(o.ho == 1 && o.pa), "PA for DG is not supported for Neummann Solver.");   // remhos_ho.cpp:138-139
+   Verify(o.lo >= 0 && o.lo <= 5, "LO solver type must be 0 .. 5");
    if (o.lo == 4) { Verify(o.order > 1, "Subcell schemes require FE order > 1."); }
    Verify(o.fct >= 0 && o.fct <= 2, "only -fct 0, 1 (FluxBased), 2 (ClipScale) are part of this build");
    Verify(!o.ps, "product remap (-ps) is not part of this build");
@@ -589,9 +598,12 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       u.SetFromHost(pfes.u0);
       Check(rmh_lumped_mass(pfes.ctx, lumpedM.Write(), nullptr));
       DofInfo dofs(pfes, o.bt);
-      HOSolver *ho_solver = o.ho == 3 ? new LocalInverseHOSolver(pfes) : nullptr;
+      HOSolver *ho_solver = nullptr;
+      if (o.ho == 3) { ho_solver = new LocalInverseHOSolver(pfes); }
+      else if (o.ho == 1) { ho_solver = new NeumannHOSolver(pfes); }
       LOSolver *lo_solver = nullptr;
       if (o.lo == 1) { lo_solver = new DiscreteUpwind(pfes); }
+      else if (o.lo == 2) { lo_solver = new DiscreteUpwind(pfes, true); }
       else if (o.lo == 3) { lo_solver = new ResidualDistribution(pfes); }
       else if (o.lo == 4) { lo_solver = new ResidualDistributionSubcell(pfes); }
       else if (o.lo == 5) { lo_solver = new MassBasedAvg(pfes, *ho_solver); }

@@ -96,6 +96,7 @@ public:
    HOSolver(ParFiniteElementSpace &space) : pfes(space) {}
    virtual ~HOSolver() {}
    virtual void CalcHOSolution(const Vector &u, Vector &du) const = 0;
+   virtual int Type() const { return 3; }
 };
 
 class LocalInverseHOSolver : public HOSolver
@@ -103,6 +104,15 @@ class LocalInverseHOSolver : public HOSolver
 public:
    LocalInverseHOSolver(ParFiniteElementSpace &space) : HOSolver(space) {}
    void CalcHOSolution(const Vector &u, Vector &du) const override;
+};
+
+// -ho 1 (FA only)
+class NeumannHOSolver : public HOSolver
+{
+public:
+   NeumannHOSolver(ParFiniteElementSpace &space);
+   void CalcHOSolution(const Vector &u, Vector &du) const override;
+   int Type() const override { return 1; }
 };
 
 class LOSolver
@@ -121,10 +131,11 @@ public:
 
 class DiscreteUpwind : public LOSolver
 {
+   bool prec;      // -lo 2: upwinding of the preconditioned blocks M_L M^-1 K (remhos.cpp:749-771)
 public:
-   DiscreteUpwind(ParFiniteElementSpace &space);
+   DiscreteUpwind(ParFiniteElementSpace &space, bool preconditioned = false);
    void CalcLOSolution(const Vector &u, Vector &du) const override;
-   int Type() const override { return 1; }
+   int Type() const override { return prec ? 2 : 1; }
 };
 
 class ResidualDistribution : public LOSolver
@@ -242,7 +253,7 @@ public:
    void MultUnlimited(const Vector &x, Vector &y) const override;
    void LimitMult(const Vector &x, Vector &y) const override;
    void Mult(const Vector &x, Vector &y) const override;
-   int HOType() const { return ho_solver ? 3 : 0; }
+   int HOType() const { return ho_solver ? ho_solver->Type() : 0; }
    int LOType() const { return lo_solver ? lo_solver->Type() : 0; }
    int FCTType() const { return fct_solver ? fct_solver->Type() : 0; }
    ParFiniteElementSpace &Space() const { return pfes; }

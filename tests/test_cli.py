@@ -82,6 +82,17 @@ CLI_KNOWN = [
       '-lo', 4, '-fct', 2, '-no-vis'], 0.1197299801, 0.9997499683),
     (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 2,
       '-lo', 3, '-fct', 2, '-pa', '-no-vis'], 0.3888354875, 0.9755502191),
+    # -ho 1 -lo 2 -fct 2 (Neumann HO + preconditioned discrete upwinding): out_baseline.dat:4-32
+    (['-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-dt', 0.0015, '-tf', 0.75, '-ho', 1,
+      '-lo', 2, '-fct', 2, '-no-vis'], 0.08479546635, 0.8262759545),
+    (['-m', mesh('cube01_hex.mesh'), '-p', 10, '-rs', 1, '-o', 2, '-dt', 0.02, '-tf', 0.7, '-ho', 1,
+      '-lo', 2, '-fct', 2, '-no-vis'], 0.1197299711, 0.9998930413),
+    (['-m', mesh('periodic-hexagon.mesh'), '-p', 0, '-rs', 2, '-dt', 0.005, '-tf', 2.5, '-ho', 1,
+      '-lo', 2, '-fct', 2, '-no-vis'], 0.3888354875, 0.9854644631),
+    (['-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 3, '-dt', 0.004, '-tf', 0.8, '-ho', 1,
+      '-lo', 2, '-fct', 2, '-no-vis'], 0.1623263888, 0.7742737139),
+    (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 1,
+      '-lo', 2, '-fct', 2, '-no-vis'], 0.9607429525, 0.9724537077),
     # autotest/out_baseline.dat:177-180 and :103-106 (mass and max, 10 digits)
     (['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 1, '-o', 2, '-dt', 0.015, '-tf', 2, '-ho', 3,
       '-lo', 1, '-fct', 1, '-no-vis'], 0.9607429525, 0.9984668427),

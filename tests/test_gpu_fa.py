@@ -69,6 +69,24 @@ def test_discrete_upwind(setup):
     assert rel_err(host(out, u.shape), ref) < TOL
 
 
+def test_discrete_upwind_preconditioned(setup):
+    run, ctx, u = setup
+    at_time(run, ctx, 0.3)
+    ref = run.disc.lo_discrete_upwind(u, prec=True)
+    out = empty(ctx)
+    ctx.lo_discrete_upwind_prec(dev(u), out)
+    assert rel_err(host(out, u.shape), ref) < 1e-10
+
+
+def test_neumann_ho(setup):
+    run, ctx, u = setup
+    at_time(run, ctx, 0.3)
+    ref = run.disc.ho_neumann(u)
+    out = empty(ctx)
+    ctx.ho_neumann(dev(u), out)
+    assert rel_err(host(out, u.shape), ref) < TOL
+
+
 def test_residual_distribution(setup):
     run, ctx, u = setup
     at_time(run, ctx, 0.3)
@@ -133,7 +151,7 @@ def test_flux_based_fct(setup, lo):
     assert (un[ok] >= umin[ok] - 1e-11).all() and (un[ok] <= umax[ok] + 1e-11).all()
 
 
-COMBOS = [(3, 1, 2), (3, 1, 1), (3, 3, 2), (3, 3, 1), (3, 5, 2), (3, 5, 1), (3, 0, 0), (0, 1, 0),
+COMBOS = [(1, 2, 2), (1, 1, 1), (3, 2, 2), (1, 0, 0), (3, 1, 2), (3, 1, 1), (3, 3, 2), (3, 3, 1), (3, 5, 2), (3, 5, 1), (3, 0, 0), (0, 1, 0),
           (0, 3, 0), (3, 5, 0)]
 
 
@@ -155,7 +173,7 @@ def test_mult_rejects_unsupported(setup):
     import remhos_b200 as rb
     run, ctx, u = setup
     k = empty(ctx)
-    for combo in [(1, 1, 2), (3, 2, 2), (3, 1, 3), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
+    for combo in [(2, 1, 2), (3, 6, 2), (3, 1, 3), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
         with pytest.raises(rb.RmhError):
             ctx.mult(*combo, 0.0, 0.01, dev(u), k)
 

@@ -41,6 +41,13 @@ BASELINE = [
                                    lo_type=1, fct_type=1), 0.3888354875, 0.9979069772),  # :167-170
     ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=3,
                                    lo_type=3, fct_type=2), 0.3888354875, 0.9755502191),  # :93-96
+    # -ho 1 -lo 2 -fct 2 (Neumann HO + preconditioned discrete upwinding): out_baseline.dat:4-32
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=1,
+                                   lo_type=2, fct_type=2), 0.3888354875, 0.9854644631),
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=2, dt=0.015, t_final=2, ho_type=1,
+                                lo_type=2, fct_type=2), 0.9607429525, 0.9724537077),
+    ('inline-quad.mesh', dict(problem=14, rs_levels=1, dt=0.0015, t_final=0.75, ho_type=1,
+                              lo_type=2, fct_type=2), 0.08479546635, 0.8262759545),
     # subcell residual distribution (-lo 4): out_baseline.dat:56-69, :41-49
     ('periodic-hexagon.mesh', dict(problem=0, rs_levels=2, dt=0.005, t_final=2.5, ho_type=3,
                                    lo_type=4, fct_type=2), 0.3888354875, 0.9850024108),
@@ -60,7 +67,7 @@ BASELINE = [
 
 
 @pytest.mark.parametrize('mesh,opt,mass,umax', BASELINE,
-                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT', 'hexagon-DU-fluxFCT', 'hexagon-RD-clipscale', 'hexagon-RDsub', 'square-RDsub', 'cube-RDsub',
+                         ids=['cube-DU-fluxFCT', 'cube-RD-clipscale', 'square-RD-clipscale', 'square-DU-fluxFCT', 'hexagon-DU-fluxFCT', 'hexagon-RD-clipscale', 'hexagon-Neumann-DUprec', 'cube-Neumann-DUprec', 'quad-remap-Neumann-DUprec', 'hexagon-RDsub', 'square-RDsub', 'cube-RDsub',
                               'quad-remap-RDsub', 'hex-remap-RDsub',
                               'quad-remap-DU-fluxFCT', 'quad-remap-RD-clipscale'])
 def test_autotest_baseline(mesh, opt, mass, umax):
