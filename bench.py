@@ -302,9 +302,15 @@ def main():
                 'd2h_bytes_per_step': 8 * N, 'steps': e_steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'k_stage<3,%d,%d>' % (a.order + 1, a.order + 3),
+        'roofline': {'bound': 'hbm',
+                     'kernel': 'k_stage3w<%d,%d,%s> (FP64 DMMA, warp per element)'
+                               % (a.order + 1, a.order + 3, '8,2' if a.order <= 3 else '6,2'),
                      'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
-                     'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                     'frac': (achieved / peak) if achieved else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu
+                     # --set full capture of this workload (profiles/r01/ncu_stage_v9_hoisted_rs5.txt)
+                     'traffic': (7.000267e9 + 458.27968e6) if (a.order == 3 and a.rs == 5) else None,
+                     'traffic_unit': 'bytes per launch',
                      'alg_bytes_per_dof_stage': B_ALG, 'kernel_ms': k_ms,
                      'kernel_share_of_step': (kms / ms) if klaunch else None},
         'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0), 'u_min': umin, 'u_max': umax},

@@ -1048,7 +1048,7 @@ static int launch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    }
    else
    {
-      set_error("tensor-core stage kernel: 3D, order <= 3 only");
+      set_error("tensor-core stage kernel: 3D, order <= 4 only");
       return 1;
    }
 }
@@ -1087,13 +1087,14 @@ static int launch_stagew_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 template <int DIM, int D1, int Q>
 static int launch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
-   if constexpr (DIM == 3 && D1 <= 4)
+   if constexpr (DIM == 3 && D1 <= 5)
    {
       static int cfg = -1;
       if (cfg < 0)
       {
          const char *ev = getenv("RMH_W_NW"), *em = getenv("RMH_W_MINB");
-         const int nw = ev ? atoi(ev) : 8, mb = em ? atoi(em) : 0;
+         // order 4 needs 18.7 KB of shared memory per warp: 2 blocks x 6 warps (168 registers)
+         const int nw = ev ? atoi(ev) : (D1 >= 5 ? 6 : 8), mb = em ? atoi(em) : 0;
          cfg = nw * 10 + mb;
       }
       switch (cfg)
@@ -1111,7 +1112,7 @@ static int launch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    }
    else
    {
-      set_error("tensor-core stage kernel: 3D, order <= 3 only");
+      set_error("tensor-core stage kernel: 3D, order <= 4 only");
       return 1;
    }
 }
@@ -1434,7 +1435,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       for (double v : ei) { if (!(v > 0.0)) { c->all_affine = false; break; } }
       // affine 3D meshes run the tensor-core stage kernel: store the quadrature data in its
       // fragment order (every other 3D kernel reads it through the layout flag)
-      if (c->all_affine && c->dim == 3 && c->pipelined && c->tensor && c->D1 <= 4)
+      if (c->all_affine && c->dim == 3 && c->pipelined && c->tensor && c->D1 <= 5)
       {
          c->frag = true;
          CUDA_OK(cudaMemset(c->Dvol, 0, n_dvol * sizeof(double)));

@@ -25,6 +25,8 @@ STAGE_CASES = [
     ('periodic-hexagon.mesh', dict(problem=1, rs_levels=1, order=2, dt=0.005), 1),
     ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=3, dt=0.01), 0),
     ('periodic-cube.mesh', dict(problem=1, rs_levels=1, order=2, dt=0.01), 1),
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=4, dt=0.005), 0),
+    ('periodic-cube.mesh', dict(problem=1, rs_levels=0, order=1, dt=0.01), 0),
     ('cube01_hex.mesh', dict(problem=10, rs_levels=1, order=3, dt=0.02, t_final=0.7), 0),
 ]
 
@@ -40,7 +42,9 @@ def test_stage_matches_oracle(mesh, opt, bt):
     ctx.set_time(t)
     k = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
     ctx.stage(5, run.dt, dev(u), k)
-    assert rel_err(k.cpu().numpy().reshape(u.shape), ref) < 1e-10
+    # order 4: the Bernstein mass matrix has cond ~ 2e6, carried by both the oracle's dense LU
+    # and the Kronecker inverse
+    assert rel_err(k.cpu().numpy().reshape(u.shape), ref) < (1e-10 if run.space.p <= 3 else 1e-8)
     # the limited update keeps u + dt*k inside the bounds (same verdict as the oracle's check)
     umin, umax = run.disc.bounds(u, bt)
     un = u + run.dt * k.cpu().numpy().reshape(u.shape)
