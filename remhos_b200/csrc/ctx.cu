@@ -8,6 +8,7 @@
 #include "stage3t.cuh"
 #include "stage3w.cuh"
 #include "fa.cuh"
+#include "geom3.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1141,6 +1142,33 @@ static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
    g.Dvol = c->Dvol; g.detJw = c->detJw; g.Dface = c->Dface;
    const int bs = 128;
    const int64_t nv = c->ne * c->NQ, nfq = c->ne * c->NF * c->NQF;
+   static int use_g3 = -1;   // RMH_NO_GEOM3=1 selects the point-wise set-up kernels in 3D too
+   if (use_g3 < 0) { const char *ev = getenv("RMH_NO_GEOM3"); use_g3 = (ev && ev[0] == '1') ? 0 : 1; }
+   const bool g3 = (c->dim == 3) && use_g3 && c->NG1 == 3 &&
+                   (c->D1 * 100 + c->Q == 204 || c->D1 * 100 + c->Q == 305 || c->D1 * 100 + c->Q == 406 ||
+                    c->D1 * 100 + c->Q == 507);
+   if (g3)
+   {
+      Geom3Args a;
+      a.Q = c->Q; a.NG1 = c->NG1; a.D1 = c->D1; a.exec_mode = c->exec_mode; a.frag = c->frag ? 1 : 0;
+      a.ne = c->ne; a.t = t;
+      a.X0 = c->X0; a.V = c->V; a.velq = c->velq; a.velf = c->velf;
+      a.L = c->dL; a.dL = c->ddL; a.Ls = c->dLs; a.dLs = c->ddLs; a.w = c->dw; a.B = c->dB;
+      a.Dvol = c->Dvol; a.detJw = c->detJw; a.Dface = c->Dface; a.ml = c->ml; a.einv = c->einv; a.BL = c->BL;
+      const size_t shb = geom3_smem_doubles(c->Q, c->NG1, c->D1) * sizeof(double);
+      constexpr int GT = 128;
+      switch (c->D1 * 100 + c->Q)
+      {
+         case 204: k_geom3<3, 4, 2, GT><<<(unsigned)c->ne, GT, shb, s>>>(a); break;
+         case 305: k_geom3<3, 5, 3, GT><<<(unsigned)c->ne, GT, shb, s>>>(a); break;
+         case 406: k_geom3<3, 6, 4, GT><<<(unsigned)c->ne, GT, shb, s>>>(a); break;
+         case 507: k_geom3<3, 7, 5, GT><<<(unsigned)c->ne, GT, shb, s>>>(a); break;
+         default: set_error("k_geom3: no instantiation"); return 1;
+      }
+      LAUNCH_OK();
+   }
+   else
+   {
    if (c->dim == 2)
    {
       k_geom_vol<2><<<(unsigned)((nv + bs - 1) / bs), bs, 0, s>>>(g); LAUNCH_OK();
@@ -1157,11 +1185,15 @@ static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
    k_elem_affine<<<(unsigned)((c->ne * 32 + bs - 1) / bs), bs, 0, s>>>(
       c->dim, c->Q, c->NGN, c->exec_mode, t, c->ne, c->dw, c->detJw, c->X0, c->V, c->einv);
    LAUNCH_OK();
+   }
    {
       const OpData o = op_data(c);
       const int64_t n = c->ne * c->NF * c->NFD;
-      k_face_lump<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(o, c->ne, c->BL);
-      LAUNCH_OK();
+      if (!g3)
+      {
+         k_face_lump<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(o, c->ne, c->BL);
+         LAUNCH_OK();
+      }
       if (c->sub_on)
       {
          int ns = 1;
