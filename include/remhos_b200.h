@@ -142,6 +142,11 @@ int rmh_ctx_destroy(rmh_ctx *ctx);
 int64_t rmh_ctx_ndofs(const rmh_ctx *ctx);   /* ne*nd (owned) */
 int rmh_ctx_nd(const rmh_ctx *ctx);
 int rmh_ctx_nq1d(const rmh_ctx *ctx);
+/* which stage-kernel path this context takes (diagnostics, tests): bit 0 every element has a
+ * constant Jacobian, bit 1 stored quadrature data is in tensor-core fragment order, bit 2 the
+ * velocity is linear over every element (quadrature data rebuilt in-kernel from 12 doubles per
+ * element instead of streamed; set RMH_NO_LINEAR_OP=1 before rmh_ctx_create to disable) */
+int rmh_ctx_path_flags(const rmh_ctx *ctx);
 /* reference-element coordinates of the volume / face quadrature points, so a caller can
  * evaluate its velocity coefficient there: q1d[Q] Gauss-Legendre points on [0,1] */
 int rmh_ctx_quad_points_1d(const rmh_ctx *ctx, double *q1d, double *w1d);

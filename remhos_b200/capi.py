@@ -211,6 +211,7 @@ class Context:
         self.nd = lib().rmh_ctx_nd(self.h)
         self.ne = d.ne
         self.nq1d = lib().rmh_ctx_nq1d(self.h)
+        self.path_flags = lib().rmh_ctx_path_flags(self.h)
         self.dim = dim
 
     def close(self):

@@ -7,6 +7,7 @@
 #include "stage3p.cuh"
 #include "stage3t.cuh"
 #include "stage3w.cuh"
+#include "stage3c.cuh"
 #include "fa.cuh"
 #include "geom3.cuh"
 
@@ -79,6 +80,11 @@ struct rmh_ctx
    bool frag = false;          // Dvol/Dface stored in the fragment order of stage3t.cuh
    bool xe_valid = false;
    bool all_affine = false;   // every element has constant det J (transport meshes only)
+   bool op_lin = false;       // ... and adj(J) v is linear over every element: opc is valid
+   bool op_const = false;     // ... and constant over every element: opa is valid
+   double *opc = nullptr;     // [ne][12] (k_op_linear)
+   double *opa = nullptr;     // [ne][4]  (k_op_linear)
+   double *dxq = nullptr;     // device copy of the 1-D quadrature points
    // matrix-based ("FA") solver data: lumped face matrices always; dense blocks after rmh_fa_setup
    double *dG = nullptr, *BL = nullptr;
    double *faK = nullptr, *faKH = nullptr, *faM = nullptr, *faBI = nullptr;
@@ -324,6 +330,91 @@ __global__ void k_elem_affine(int dim, int Q, int ngn, int exec_mode, double t, 
    const double h = pow(fabs(vol), 1.0 / dim);
    const double tol = 100.0 * 2.220446049250313e-16 * fmax(1.0, xmax / h);
    if (lane == 0) { einv[e] = (vol > 0.0 && dev <= tol * vol) ? 1.0 / vol : 0.0; }
+}
+
+// Linear-operator detection for the tensor-core stage kernel (fragment-ordered 3D transport data).
+// One warp per element: least-squares fit (quadrature-weighted, so the basis 1, x-1/2, y-1/2, z-1/2
+// is orthogonal) of adj(J) v = W0 + W1 x + W2 y + W3 z in reference coordinates to the stored
+// Dvol = -w_q adj(J) v, then check that the fit reproduces every stored volume value and every
+// stored face value w min(0, +-(adj(J) v)_axis).  Tolerance: the stored data carries the round-off
+// of a Jacobian formed from coordinate differences, eps*|x|/h relative (see k_elem_affine).
+// opc[e][k*3 + c] = W_k[c]; nfail[0] counts the elements that do not fit.  Elements whose slopes
+// W1..W3 vanish to the same tolerance carry a constant coefficient a = W at the centroid:
+// opa[e] = (a_x, a_y, a_z, 1/vol); nfail[1] counts the elements that are not of that kind.
+__global__ void k_op_linear(int Q, int ngn, int64_t ne, const double *xq, const double *w,
+                            const double *Dvol, const double *Dface, const double *X0,
+                            const double *einv, double *opc, double *opa, unsigned int *nfail)
+{
+   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (e >= ne) { return; }
+   const int RQ = (Q + 1) & ~1, QQ = Q * Q;
+   const double *dv = Dvol + (size_t)e * QQ * RQ * 3;
+   const double *df = Dface + (size_t)e * 6 * Q * RQ;
+   double acc[12], s2 = 0.0;
+   for (int i = 0; i < 12; i++) { acc[i] = 0.0; }
+   for (int q = 0; q < Q; q++) { s2 += w[q] * (xq[q] - 0.5) * (xq[q] - 0.5); }
+   for (int q = lane; q < QQ * Q; q += 32)
+   {
+      const int qx = q % Q, qy = (q / Q) % Q, qz = q / QQ;
+      for (int c = 0; c < 3; c++)
+      {
+         // stored value = -w_q W_c(q): the quadrature weight is already on it
+         const double wv = -dv[((size_t)(qy * Q + qx) * RQ + qz) * 3 + c];
+         acc[c] += wv;
+         acc[3 + c] += wv * (xq[qx] - 0.5);
+         acc[6 + c] += wv * (xq[qy] - 0.5);
+         acc[9 + c] += wv * (xq[qz] - 0.5);
+      }
+   }
+   double cf[12];
+   for (int i = 0; i < 12; i++) { acc[i] = warp_sum(acc[i]); }
+   for (int c = 0; c < 3; c++)
+   {
+      cf[3 + c] = acc[3 + c] / s2; cf[6 + c] = acc[6 + c] / s2; cf[9 + c] = acc[9 + c] / s2;
+      cf[c] = acc[c] - 0.5 * (cf[3 + c] + cf[6 + c] + cf[9 + c]);
+   }
+   double scale = 0.0, dev = 0.0;
+   for (int q = lane; q < QQ * Q; q += 32)
+   {
+      const int qx = q % Q, qy = (q / Q) % Q, qz = q / QQ;
+      for (int c = 0; c < 3; c++)
+      {
+         const double v = -dv[((size_t)(qy * Q + qx) * RQ + qz) * 3 + c] / (w[qx] * w[qy] * w[qz]);
+         const double fit = cf[c] + cf[3 + c] * xq[qx] + cf[6 + c] * xq[qy] + cf[9 + c] * xq[qz];
+         scale = fmax(scale, fabs(v));
+         dev = fmax(dev, fabs(v - fit));
+      }
+   }
+   for (int i = lane; i < 6 * QQ; i += 32)
+   {
+      const int f = i / QQ, qa = i % Q, qb = (i / Q) % Q;
+      const int axis = (f == 0 || f == 5) ? 2 : ((f == 1 || f == 3) ? 1 : 0);
+      const int side = (f == 2 || f == 3 || f == 5) ? 1 : 0;
+      const int ia = (axis == 0) ? 1 : 0, ib = (axis == 2) ? 1 : 2;
+      double vn = cf[axis] + side * cf[3 * (1 + axis) + axis] + cf[3 * (1 + ia) + axis] * xq[qa] +
+                  cf[3 * (1 + ib) + axis] * xq[qb];
+      if (!side) { vn = -vn; }
+      const double stored = df[((size_t)f * Q + qa) * RQ + qb] / (w[qa] * w[qb]);
+      dev = fmax(dev, fabs(stored - fmin(0.0, vn)));
+   }
+   double xmax = 0.0;
+   for (int n = lane; n < ngn * 3; n += 32) { xmax = fmax(xmax, fabs(X0[(size_t)e * ngn * 3 + n])); }
+   scale = warp_max(scale);
+   dev = warp_max(dev);
+   xmax = warp_max(xmax);
+   const double h = cbrt(1.0 / einv[e]);
+   const double tol = 100.0 * 2.220446049250313e-16 * fmax(1.0, xmax / h);
+   if (lane < 12) { opc[e * 12 + lane] = cf[lane]; }
+   if (lane == 0)
+   {
+      const bool lin = (dev <= tol * scale);
+      double slope = 0.0;
+      for (int i = 3; i < 12; i++) { slope = fmax(slope, fabs(cf[i])); }
+      if (!lin) { atomicAdd(nfail, 1u); }
+      if (!(lin && slope <= tol * scale)) { atomicAdd(nfail + 1, 1u); }
+      opa[e * 4 + 0] = acc[0]; opa[e * 4 + 1] = acc[1]; opa[e * 4 + 2] = acc[2]; opa[e * 4 + 3] = einv[e];
+   }
 }
 
 // lumped mass m_i = sum_q B_qi detJw_q  (M_HO * 1, remhos.cpp:721-727)
@@ -958,6 +1049,7 @@ static Tab<D1, Q> make_tab(const rmh_ctx *c)
          for (int j = 0; j < D1; j++) { v += c->hMinv[i * D1 + j] * c->hB[q * D1 + j]; }
          tab.C[i][q] = v;
       }
+   for (int q = 0; q < Q; q++) { tab.xq[q] = c->hxq[q]; tab.wq[q] = c->hw[q]; }
    return tab;
 }
 
@@ -1063,26 +1155,39 @@ static int dispatch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 // NW warps per block, MINB resident blocks per SM the register allocation must allow.  The kernel
 // is latency-bound: 16 warps per SM at 128 registers (operator-data loads hoisted two phases
 // ahead) beat 20 warps at 96 (profiles/r01/README.md).
-template <int D1, int Q, int NW, int MINB>
-static int launch_stagew_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+template <int D1, int Q, int NW, int MINB, bool LIN>
+static int launch_stagew_L(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    using S = SmemW<D1, Q>;
    constexpr size_t BYTES = S::bytes(NW);
    static int blocks_per_sm = 0;
    if (blocks_per_sm == 0)
    {
-      CUDA_OK(cudaFuncSetAttribute(k_stage3w<D1, Q, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_OK(cudaFuncSetAttribute(k_stage3w<D1, Q, NW, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)BYTES));
       int nb = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3w<D1, Q, NW, MINB>, NW * 32, BYTES));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3w<D1, Q, NW, MINB, LIN>, NW * 32,
+                                                            BYTES));
       if (nb < 1) { set_error("k_stage3w does not fit on an SM"); return 1; }
       blocks_per_sm = std::min(nb, MINB);
+      if (getenv("RMH_VERBOSE"))
+      {
+         fprintf(stderr, "k_stage3w<%d,%d,%d,%d,%s>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, Q, NW, MINB,
+                 LIN ? "lin" : "stored", blocks_per_sm, nb, BYTES);
+      }
    }
    const int64_t nblk = (a.ne + NW - 1) / NW;
    const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
-   k_stage3w<D1, Q, NW, MINB><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tab<D1, Q>(c));
+   k_stage3w<D1, Q, NW, MINB, LIN><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tab<D1, Q>(c));
    LAUNCH_OK();
    return 0;
+}
+
+template <int D1, int Q, int NW, int MINB>
+static int launch_stagew_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   return a.opc ? launch_stagew_L<D1, Q, NW, MINB, true>(c, a, s)
+                : launch_stagew_L<D1, Q, NW, MINB, false>(c, a, s);
 }
 
 template <int DIM, int D1, int Q>
@@ -1121,6 +1226,85 @@ static int launch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 static int dispatch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    RMH_DISPATCH(launch_stagew, c, a, s);
+}
+
+// ---- constant-coefficient kernel (stage3c.cuh)
+template <int D1, int Q>
+static TabC<D1> make_tabc(const rmh_ctx *c)
+{
+   const Tab<D1, Q> t = make_tab<D1, Q>(c);
+   TabC<D1> o;
+   for (int i = 0; i < D1; i++)
+   {
+      for (int k = 0; k < D1; k++)
+      {
+         double v = 0.0;
+         for (int q = 0; q < Q; q++) { v += t.C[i][q] * t.wq[q] * t.G[q][k]; }
+         o.T[i][k] = v;
+      }
+      o.M0[i] = t.Minv[i][0]; o.Mp[i] = t.Minv[i][D1 - 1];
+   }
+   return o;
+}
+
+template <int D1, int Q, int NW, int MINB, int NST>
+static int launch_stagec_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   using S = SmemC<D1, NST>;
+   constexpr size_t BYTES = S::bytes(NW);
+   static int blocks_per_sm = 0;
+   if (blocks_per_sm == 0)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)BYTES));
+      int nb = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST>, NW * 32, BYTES));
+      if (nb < 1) { set_error("k_stage3c does not fit on an SM"); return 1; }
+      blocks_per_sm = std::min(nb, MINB);
+      if (getenv("RMH_VERBOSE"))
+      {
+         fprintf(stderr, "k_stage3c<%d,%d,%d,%d>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
+                 blocks_per_sm, nb, BYTES);
+      }
+   }
+   const int64_t nblk = (a.ne + NW - 1) / NW;
+   const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
+   k_stage3c<D1, NW, MINB, NST><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
+   LAUNCH_OK();
+   return 0;
+}
+
+template <int DIM, int D1, int Q>
+static int launch_stagec(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   if constexpr (DIM == 3 && D1 <= 5)
+   {
+      static int cfg = -1;
+      if (cfg < 0)
+      {
+         const char *ev = getenv("RMH_C_CFG");     // NW * 100 + MINB * 10 + NST
+         cfg = ev ? atoi(ev) : 0;
+      }
+      switch (cfg)
+      {
+         case 823: return launch_stagec_N<D1, Q, 8, 2, 3>(c, a, s);     // 16 warps, ring of 3
+         case 832: return launch_stagec_N<D1, Q, 8, 3, 2>(c, a, s);     // 24 warps, ring of 2
+         case 822: return launch_stagec_N<D1, Q, 8, 2, 2>(c, a, s);     // 16 warps, ring of 2
+         case 842: return launch_stagec_N<D1, Q, 8, 4, 2>(c, a, s);     // 32 warps, ring of 2
+         case 1024: return launch_stagec_N<D1, Q, 10, 2, 4>(c, a, s);   // 20 warps, ring of 4
+         default: return launch_stagec_N<D1, Q, 10, 2, 3>(c, a, s);     // 20 warps, ring of 3
+      }
+   }
+   else
+   {
+      set_error("constant-coefficient stage kernel: 3D, order <= 4 only");
+      return 1;
+   }
+}
+
+static int dispatch_stagec(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   RMH_DISPATCH(launch_stagec, c, a, s);
 }
 
 static OpData op_data(const rmh_ctx *c)
@@ -1474,6 +1658,35 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
          CUDA_OK(cudaMemset(c->Dface, 0, n_dface * sizeof(double)));
          if (run_geom(c, 0.0, 0)) { return fail(); }
          CUDA_OK(cudaDeviceSynchronize());
+         // velocity linear over every element (constant, rotation, ...): the stage kernel rebuilds
+         // the quadrature data from 12 doubles per element instead of streaming it
+         const char *nl = getenv("RMH_NO_LINEAR_OP");
+         if (!(nl && nl[0] == '1'))
+         {
+            unsigned int *nfail = nullptr;
+            if (dev_alloc(c, &c->opc, (size_t)c->ne * 12)) { return fail(); }
+            if (dev_alloc(c, &c->opa, (size_t)c->ne * 4)) { return fail(); }
+            if (dev_alloc(c, &nfail, 2)) { return fail(); }
+            if (dev_upload(c, &c->dxq, c->hxq.data(), c->hxq.size())) { return fail(); }
+            CUDA_OK(cudaMemset(nfail, 0, 2 * sizeof(unsigned int)));
+            const int bs = 128;
+            k_op_linear<<<(unsigned)((c->ne * 32 + bs - 1) / bs), bs>>>(
+               c->Q, c->NGN, c->ne, c->dxq, c->dw, c->Dvol, c->Dface, c->X0, c->einv, c->opc, c->opa, nfail);
+            LAUNCH_OK();
+            unsigned int nf[2] = {1, 1};
+            CUDA_OK(cudaMemcpy(nf, nfail, sizeof(nf), cudaMemcpyDeviceToHost));
+            // the rebuilt-data DMMA variant is correct but slower than streaming the stored data
+            // (the kernel is not HBM-bound, profiles/r01/README.md): opt-in with RMH_LINEAR_OP=1
+            const char *el = getenv("RMH_LINEAR_OP");
+            c->op_lin = (nf[0] == 0) && el && el[0] == '1';
+            const char *nc = getenv("RMH_NO_CONST_OP");
+            c->op_const = (nf[1] == 0) && !(nc && nc[0] == '1');
+            if (getenv("RMH_VERBOSE"))
+            {
+               fprintf(stderr, "k_op_linear: %u of %lld elements not linear, %u not constant\n", nf[0],
+                       (long long)c->ne, nf[1]);
+            }
+         }
       }
    }
    *out = c;
@@ -1483,6 +1696,8 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
 extern "C" int64_t rmh_ctx_ndofs(const rmh_ctx *c) { return c->N; }
 extern "C" int rmh_ctx_nd(const rmh_ctx *c) { return c->ND; }
 extern "C" int rmh_ctx_nq1d(const rmh_ctx *c) { return c->Q; }
+extern "C" int rmh_ctx_path_flags(const rmh_ctx *c)
+{ return (c->all_affine ? 1 : 0) | (c->frag ? 2 : 0) | (c->op_lin ? 4 : 0) | (c->op_const ? 8 : 0); }
 extern "C" int rmh_ctx_quad_points_1d(const rmh_ctx *c, double *q1d, double *w1d)
 {
    for (int q = 0; q < c->Q; q++) { if (q1d) { q1d[q] = c->hxq[q]; } if (w1d) { w1d[q] = c->hw[q]; } }
@@ -1646,6 +1861,8 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    {
       pa.ne = c->ne; pa.y = y; pa.x0 = x0; pa.out = out;
       pa.Dvol = c->Dvol; pa.Dface = c->Dface; pa.einv = c->einv;
+      pa.opc = c->op_lin ? c->opc : nullptr;
+      pa.opa = c->op_const ? c->opa : nullptr;
       pa.fn = sa.ho.fn; pa.npat = c->npat; pa.nbr_pat32 = c->nbr_pat32;
       pa.a = a; pa.b = b; pa.dt = dt; pa.out_mode = out_mode;
       pa.has_x0 = (out_mode == 1 && a != 0.0) ? 1 : 0;
@@ -1661,6 +1878,7 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       {
          static int blk = -1;   // RMH_TENSOR_BLOCK=1: block-per-batch DMMA kernel (stage3t.cuh)
          if (blk < 0) { const char *ev = getenv("RMH_TENSOR_BLOCK"); blk = (ev && ev[0] == '1') ? 1 : 0; }
+         if (pa.opa && !blk) { return dispatch_stagec(c, pa, s); }
          return blk ? dispatch_staget(c, pa, s) : dispatch_stagew(c, pa, s);
       }
       return use_p ? dispatch_stagep(c, pa, s) : dispatch_stage(c, sa, s);

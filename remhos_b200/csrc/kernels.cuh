@@ -27,6 +27,7 @@ struct Tab
    double G[Q][D1];      // derivatives
    double Minv[D1][D1];  // inverse of the 1-D Bernstein mass matrix (Kronecker preconditioner)
    double C[D1][Q];      // Minv * B^T: back-contraction with the mass inverse folded in
+   double xq[Q], wq[Q];  // Gauss-Legendre points / weights on [0,1]
 };
 
 // local face -> fixed axis / side (quad: S E N W; hex: bottom south east north west top)

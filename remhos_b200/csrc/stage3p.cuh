@@ -87,6 +87,8 @@ struct StagePArgs
    const double *x0;          // RK base state (may alias y or out)
    double *out;
    const double *Dvol, *Dface, *einv;
+   const double *opc;         // [NE][12] linear operator coefficients (k_op_linear) or null
+   const double *opa;         // [NE][4] (adj(J) v, 1/vol) of constant-coefficient elements or null
    FaceNbr fn;
    int npat;
    const int32_t *nbr_pat32;  // [NE][NF] pattern ids as int32 (cp.async granularity)

@@ -94,13 +94,16 @@ struct SmemW
    static constexpr int OFF_C = OFF_D + 2 * PSZ;
    static constexpr int OFF_B = OFF_C + SZ_C;
    static constexpr int OFF_G = OFF_B + SZ_B;
-   static constexpr int WDBL = OFF_G + SZ_G;                      // doubles per warp
+   static constexpr int OFF_O = OFF_G + SZ_G;                     // 12 operator coefficients (LIN)
+   static constexpr int WDBL = OFF_O + 12;                        // doubles per warp
    static constexpr int I_NE = 0, I_NP = NF, I_BI = 2 * NF, ISZ = (2 * NF + N3 + 1) & ~1;
    static constexpr int WINT = 2 * ISZ;                           // ints per warp
    static constexpr int WBYTES = WDBL * 8 + WINT * 4;
    // shared by the block
    static constexpr int PATMAX = 16;
-   static constexpr int CBYTES = 16 * 8 + ((PATMAX * NFD * 2 + 15) & ~15);
+   // block constants: Minv columns [0, 10), quadrature (point, weight) pairs [10, 26), patterns
+   static constexpr int C_XW = 10, C_PAT = 26;
+   static constexpr int CBYTES = C_PAT * 8 + ((PATMAX * NFD * 2 + 15) & ~15);
    static constexpr int TA_V = (NL + 7) / 8, TA_F = (NT1 + 7) / 8;
    static constexpr int TB_V = (NY + 7) / 8, TB_F = (NT2 + 7) / 8;
    static constexpr int TC_V = (NC + 7) / 8;
@@ -241,7 +244,19 @@ __device__ __forceinline__ void stagew_prefetch_op(const StagePArgs &a, int64_t 
    }
 }
 
-template <int D1, int Q, int NW, int MINB>
+// LIN: 12 coefficients of element e (see k_op_linear) -> the warp's single coefficient buffer
+template <int D1, int Q>
+__device__ __forceinline__ void stagew_fetch_opc(const StagePArgs &a, double *dst, int64_t e, int lane)
+{
+   if (lane < 6) { cp_async16(dst + 2 * lane, a.opc + e * 12 + 2 * lane); }
+}
+
+// LIN = true: every element's stored quadrature data is reproduced by a velocity that is linear
+// over the (affine) element, adj(J) v = W0 + W1 x + W2 y + W3 z on the reference cube (detected at
+// set-up by k_op_linear, ctx.cu).  The kernel then rebuilds Dvol / Dface at the quadrature points
+// from 12 doubles per element instead of streaming 3 Q^3 + 6 Q^2 stored values (108 of the 134
+// B/DOF the streamed variant moves at order 3).
+template <int D1, int Q, int NW, int MINB, bool LIN>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
 {
@@ -256,7 +271,8 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
    const int g = lane >> 2, c = lane & 3;
    // block-shared constants: Minv columns, pattern table
    double *MV = sm;
-   int16_t *spat = reinterpret_cast<int16_t *>(sm + 16);
+   const double2 *XW = reinterpret_cast<const double2 *>(sm + S::C_XW);
+   int16_t *spat = reinterpret_cast<int16_t *>(sm + S::C_PAT);
    double *wsm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm) + S::CBYTES) + (size_t)w * (S::WBYTES / 8);
    int *ismem = reinterpret_cast<int *>(wsm + S::WDBL);
    const double inv_dt = 1.0 / a.dt;
@@ -290,6 +306,17 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       MV[2 * threadIdx.x] = tab.Minv[threadIdx.x][0];
       MV[2 * threadIdx.x + 1] = tab.Minv[threadIdx.x][D1 - 1];
    }
+   if (threadIdx.x < 8)
+   {
+      const bool on = threadIdx.x < Q;
+      sm[S::C_XW + 2 * threadIdx.x] = on ? tab.xq[on ? threadIdx.x : 0] : 0.0;
+      sm[S::C_XW + 2 * threadIdx.x + 1] = on ? tab.wq[on ? threadIdx.x : 0] : 0.0;
+   }
+   // LIN: points / weights of this lane's two z (or qb) indices 2c, 2c+1 (weight 0 beyond Q);
+   // the convection sign alpha = -1 (transport, remhos.cpp:648-657) rides on the z weights
+   const bool zon0 = (2 * c < Q), zon1 = (2 * c + 1 < Q);
+   const double xz0 = zon0 ? tab.xq[zon0 ? 2 * c : 0] : 0.0, xz1 = zon1 ? tab.xq[zon1 ? 2 * c + 1 : 0] : 0.0;
+   const double wz0 = zon0 ? tab.wq[zon0 ? 2 * c : 0] : 0.0, wz1 = zon1 ? tab.wq[zon1 ? 2 * c + 1 : 0] : 0.0;
    {
       const int np = a.npat < S::PATMAX ? a.npat : S::PATMAX;
       for (int i = threadIdx.x; i < np * NFD; i += NW * 32) { spat[i] = a.fn.pat[i]; }
@@ -319,8 +346,10 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
    __syncwarp();
    stagew_fetch_data<D1, Q>(a, wsm + S::OFF_D, ismem, spat, e, lane);
    if (e + GW < a.ne) { stagew_fetch_idx<D1, Q>(a, ismem + S::ISZ, e + GW, lane); }
+   if (LIN) { stagew_fetch_opc<D1, Q>(a, wsm + S::OFF_O, e, lane); }
    cp_async_commit();
-   stagew_prefetch_op<D1, Q>(a, e, lane);
+   if (!LIN) { stagew_prefetch_op<D1, Q>(a, e, lane); }
+   const double *OPC = wsm + S::OFF_O;
    double *BU = wsm + S::OFF_C, *GU = BU + NL * RQ;
    double *G3 = wsm + S::OFF_B;
    double *F1 = wsm + S::OFF_G;
@@ -340,7 +369,7 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          {
             stagew_fetch_data<D1, Q>(a, wsm + S::OFF_D + (s ^ 1) * S::PSZ, ismem + (s ^ 1) * S::ISZ, spat,
                                      e1, lane);
-            stagew_prefetch_op<D1, Q>(a, e1, lane);
+            if (!LIN) { stagew_prefetch_op<D1, Q>(a, e1, lane); }
          }
          if (e2 < a.ne) { stagew_fetch_idx<D1, Q>(a, ismem + s * S::ISZ, e2, lane); }
          cp_async_commit();
@@ -350,9 +379,9 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       // operator data is consumed two phases later: issue the loads now (registers) so their L2
       // latency overlaps phases A and B -- all face tiles and the first z-stage tile; the other
       // z-stage tiles are fetched one tile ahead
-      double dfv[S::TB_F][2];
+      double dfv[LIN ? 1 : S::TB_F][2];
 #pragma unroll
-      for (int t = 0; t < S::TB_F; t++)
+      for (int t = 0; t < (LIN ? 0 : S::TB_F); t++)
       {
          const int line = t * 8 + g;
          dfv[t][0] = 0.0; dfv[t][1] = 0.0;
@@ -368,14 +397,14 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          const int col = t * 8 + g;
 #pragma unroll
          for (int i = 0; i < 6; i++) { dv[i] = 0.0; }
-         if (col < NC && 2 * c < Q)
+         if (!LIN && col < NC && 2 * c < Q)
          {
             const double2 *p = reinterpret_cast<const double2 *>(dvp + (col * RQ + 2 * c) * 3);
             const double2 v0 = __ldcs(p), v1 = __ldcs(p + 1), v2 = __ldcs(p + 2);
             dv[0] = v0.x; dv[1] = v0.y; dv[2] = v1.x; dv[3] = v1.y; dv[4] = v2.x; dv[5] = v2.y;
          }
       };
-      load_dv(0, dvn);
+      if (!LIN) { load_dv(0, dvn); }
       // ================= A: fwd-x (rows = lines (z,y), k = ix) | face fwd-a (rows = (f,jb), k = ja)
 #pragma unroll
       for (int t = 0; t < S::TA_V; t++)
@@ -478,7 +507,26 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       {
          const int line = t * 8 + g;                        // (f, qa)
          const int f = line / Q, qa = line - f * Q;
-         const double dfv0 = dfv[t][0], dfv1 = dfv[t][1];
+         double dfv0, dfv1;
+         if constexpr (LIN)
+         {
+            // w_qa w_qb min(0, v.n), v.n = +-(adj(J) v)_axis on the face (k_geom_face, ctx.cu)
+            const int fc_ = (line < NT2) ? f : 0;
+            const int axis = (fc_ == 0 || fc_ == 5) ? 2 : ((fc_ == 1 || fc_ == 3) ? 1 : 0);
+            const bool side = (fc_ == 2 || fc_ == 3 || fc_ == 5);
+            const int ia = (axis == 0) ? 1 : 0, ib = (axis == 2) ? 1 : 2;
+            const double2 ta = XW[(line < NT2) ? qa : 0];
+            double base = OPC[axis];
+            if (side) { base += OPC[3 * (1 + axis) + axis]; }
+            base = fma(OPC[3 * (1 + ia) + axis], ta.x, base);
+            const double cb = OPC[3 * (1 + ib) + axis];
+            double vn0 = fma(cb, xz0, base), vn1 = fma(cb, xz1, base);
+            if (!side) { vn0 = -vn0; vn1 = -vn1; }
+            const double wa = (line < NT2) ? ta.y : 0.0;
+            dfv0 = wa * wz0 * fmin(0.0, vn0);
+            dfv1 = wa * wz1 * fmin(0.0, vn1);
+         }
+         else { dfv0 = dfv[t][0]; dfv1 = dfv[t][1]; }
          double y0 = 0.0, y1 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KF; ks++)
@@ -505,9 +553,27 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
       {
          const int col = t * 8 + g;
          double dv[6];
+         if constexpr (LIN)
+         {
+            // alpha w_q (adj(J) v)_c at (qx, qy, qz = 2c | 2c+1), alpha = -1
+            const int cc_ = (col < NC) ? col : 0;
+            const double2 tx = XW[cc_ % Q], ty = XW[cc_ / Q];
+            const double wxy = (col < NC) ? -(tx.y * ty.y) : 0.0;
+            const double w0_ = wxy * wz0, w1_ = wxy * wz1;
 #pragma unroll
-         for (int i = 0; i < 6; i++) { dv[i] = dvn[i]; }
-         if (t + 1 < S::TC_V) { load_dv(t + 1, dvn); }
+            for (int i = 0; i < 3; i++)
+            {
+               const double A = fma(OPC[6 + i], ty.x, fma(OPC[3 + i], tx.x, OPC[i]));
+               dv[i] = w0_ * fma(OPC[9 + i], xz0, A);
+               dv[3 + i] = w1_ * fma(OPC[9 + i], xz1, A);
+            }
+         }
+         else
+         {
+#pragma unroll
+            for (int i = 0; i < 6; i++) { dv[i] = dvn[i]; }
+            if (t + 1 < S::TC_V) { load_dv(t + 1, dvn); }
+         }
          double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0, g20 = 0.0, g21 = 0.0;
 #pragma unroll
          for (int ks = 0; ks < KF; ks++)
@@ -560,6 +626,13 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
          }
       }
       __syncwarp();
+      if (LIN)
+      {
+         // the coefficient buffer is single: refill it for the next element now that phases B
+         // and C have consumed it (lands long before the next element's phase B)
+         if (e + GW < a.ne) { stagew_fetch_opc<D1, Q>(a, wsm + S::OFF_O, e + GW, lane); }
+         cp_async_commit();
+      }
       // ================= D: bwd-y (rows = iy, cols = lines (iz,qx), k = qy)
 #pragma unroll
       for (int t = 0; t < S::TB_V; t++)

@@ -104,3 +104,67 @@ def test_rk_step_host_equals_device():
     assert t1 == t2
     assert torch.equal(u.cpu(), uh)
     ctx.close()
+
+
+# Stage-kernel variants on affine 3D meshes (rmh_ctx_path_flags): bit 3 = velocity constant over
+# every element -> constant-coefficient kernel (stage3c.cuh, default when it applies); bit 2 =
+# velocity linear over every element -> DMMA kernel that rebuilds the quadrature data in-kernel
+# (opt-in, RMH_LINEAR_OP=1); otherwise the DMMA kernel streams the stored quadrature data.  All
+# variants must match the oracle and each other.
+@pytest.mark.parametrize('problem,order,bt,const,lin', [
+    (0, 3, 0, True, True), (0, 3, 1, True, True), (0, 4, 0, True, True), (0, 2, 0, True, True),
+    (0, 1, 1, True, True), (1, 3, 0, False, True), (1, 4, 0, False, True), (1, 1, 0, False, True),
+    (3, 3, 0, False, False), (3, 2, 1, False, False)])
+def test_stage_kernel_variants(problem, order, bt, const, lin, monkeypatch):
+    run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=problem,
+                     rs_levels=1, order=order, dt=0.005, bounds_type=bt)
+    rng = np.random.default_rng(11)
+    u = np.clip(run.u + 0.02 * rng.standard_normal(run.u.shape), 0.0, None)
+    ref = run.mult(u, 0.0, run.dt)
+    tol = 1e-10 if order <= 3 else 1e-8
+    out = []
+    for env, flags in [({}, 3 | (8 if const else 0)),
+                       ({'RMH_LINEAR_OP': '1', 'RMH_NO_CONST_OP': '1'}, 3 | (4 if lin else 0)),
+                       ({'RMH_NO_CONST_OP': '1'}, 3)]:
+        for k_ in ('RMH_LINEAR_OP', 'RMH_NO_CONST_OP'):
+            monkeypatch.delenv(k_, raising=False)
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        ctx = ctx_from_oracle(run)
+        assert ctx.path_flags == flags, (env, ctx.path_flags)
+        k = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+        ctx.stage(5, run.dt, dev(u), k)
+        out.append(k.cpu().numpy())
+        assert rel_err(out[-1].reshape(u.shape), ref) < tol, env
+        ctx.close()
+    assert rel_err(out[0], out[2]) < 1e-12 and rel_err(out[1], out[2]) < 1e-12
+
+
+def test_const_kernel_ring_depths(monkeypatch):
+    """every (warps, resident blocks, ring depth) configuration of k_stage3c gives the same RK3 step"""
+    run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=0,
+                     rs_levels=2, order=3, dt=0.005, max_steps=2)
+    res = []
+    for cfg in ('0', '823', '832', '822', '842', '1024'):
+        # the configuration is latched per process on first use: run each in a fresh interpreter
+        import subprocess, sys, os, json
+        code = ("import sys, os, numpy as np, torch; sys.path[:0] = [%r, %r, %r];"
+                "from helpers import oracle_run, ctx_from_oracle;"
+                "run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=0,"
+                " rs_levels=2, order=3, dt=0.005, max_steps=2);"
+                "ctx = ctx_from_oracle(run); assert ctx.path_flags == 11;"
+                "u = torch.tensor(run.u.reshape(-1), device='cuda'); t = 0.0\n"
+                "for _ in range(2): t = ctx.rk_step(3, 5, t, run.dt, u)\n"
+                "np.save(sys.argv[1], u.cpu().numpy())")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        code = code % (root, os.path.join(root, 'oracle'), os.path.join(root, 'tests'))
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            f = os.path.join(td, 'u.npy')
+            env = dict(os.environ, RMH_C_CFG=cfg)
+            subprocess.check_call([sys.executable, '-c', code, f], env=env)
+            res.append(np.load(f))
+    run.run()
+    for r in res:
+        assert np.array_equal(r, res[0])
+        assert rel_err(r.reshape(run.u.shape), run.u) < 1e-12
