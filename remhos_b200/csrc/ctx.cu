@@ -1287,12 +1287,12 @@ static int launch_stagec(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
       }
       switch (cfg)
       {
-         case 823: return launch_stagec_N<D1, Q, 8, 2, 3>(c, a, s);     // 16 warps, ring of 3
-         case 832: return launch_stagec_N<D1, Q, 8, 3, 2>(c, a, s);     // 24 warps, ring of 2
          case 822: return launch_stagec_N<D1, Q, 8, 2, 2>(c, a, s);     // 16 warps, ring of 2
-         case 842: return launch_stagec_N<D1, Q, 8, 4, 2>(c, a, s);     // 32 warps, ring of 2
-         case 1024: return launch_stagec_N<D1, Q, 10, 2, 4>(c, a, s);   // 20 warps, ring of 4
-         default: return launch_stagec_N<D1, Q, 10, 2, 3>(c, a, s);     // 20 warps, ring of 3
+         case 632: return launch_stagec_N<D1, Q, 6, 3, 2>(c, a, s);     // 18 warps, ring of 2
+         case 1213: return launch_stagec_N<D1, Q, 12, 1, 3>(c, a, s);   // 12 warps, ring of 3
+         case 2012: return launch_stagec_N<D1, Q, 20, 1, 2>(c, a, s);   // 20 warps (one block), ring of 2
+         case 1612: return launch_stagec_N<D1, Q, 16, 1, 2>(c, a, s);   // 16 warps (one block), ring of 2
+         default: return launch_stagec_N<D1, Q, 10, 2, 2>(c, a, s);     // 20 warps, ring of 2
       }
    }
    else

@@ -14,15 +14,23 @@
 // i.e. along every grid line of the element the update is one (D1 x (D1+2)) matrix applied to the
 // line's DOFs extended by the two neighbour trace values.  No quadrature-space intermediates, 18
 // instead of ~580 FMAs per DOF at order 3: what is left is a streaming kernel (y, x0, out, indices:
-// ~28 B/DOF of compulsory HBM traffic) whose element-wise tail (MassBasedAvg, bounds gather,
+// ~30 B/DOF of compulsory HBM traffic) whose element-wise tail (MassBasedAvg, bounds gather,
 // ClipScale, RK combination, element min/max of the output) is the one of stage3w.cuh.
 //
-// One warp owns one element at a time (static round-robin, persistent grid, no block barrier in
-// the loop).  Inputs arrive through an NST-deep cp.async ring per warp (DOF block in a padded
-// layout, RK base x0, neighbour traces gathered through (neighbour element, orientation pattern),
-// entity (min,max) pairs, (a, 1/vol)); gather indices run NST-1 elements further ahead.  A lane
-// owns one grid line per round (x- and y-lines share a round, half a warp each): D1+2 shared-memory
-// loads feed D1*(D1+2) FMAs, the coefficient matrix T comes from the constant bank.
+// Work split (v2; v1 spent 850 warp instructions per element, 72 % issue-slot utilisation):
+//   * a warp owns E = 32 / LG consecutive elements at a time (LG = D1^2 rounded up to a power of
+//     two: two elements at order 3), a lane owns one x-row of one element: the row's D1 DOFs stay
+//     in registers from the x-contraction to the final store (16-byte row loads / stores, x0 and
+//     out never touch shared memory, reductions run over LG lanes for E elements at once);
+//   * the y- and z-contractions run line-wise (lane = one y-line, then one z-line, all lanes busy)
+//     and hand their results to the row owners through two shared-memory arrays;
+//   * inputs arrive through an NST-deep cp.async ring per warp (DOF blocks in a padded layout,
+//     neighbour traces gathered through (neighbour element, orientation pattern), entity (min,max)
+//     pairs, (a, 1/vol)); gather indices run NST-1 groups further ahead; x0 rows are prefetched
+//     into registers one group ahead.  No block barrier in the loop.
+// Shared-memory layout at order 3 (tools/bank_sim_c.py): plane stride 18, element stride 72 doubles:
+// row (128-bit) and z-line accesses are conflict-free, y-lines use their own lane map (planes
+// {0,2} / {1,3} per half-warp) which makes them conflict-free too.
 #ifndef RMH_STAGE3C_CUH
 #define RMH_STAGE3C_CUH
 
@@ -42,21 +50,23 @@ template <int D1, int NST>
 struct SmemC
 {
    static constexpr int ND = D1 * D1 * D1, NF = 6, NFD = D1 * D1, N3 = 27, NL = D1 * D1;
-   // padded DOF block: row stride D1+1 makes the x-, y- and z-line accesses of a half-warp
-   // (64-bit words, 16 bank pairs) conflict-free at order 3 (z-lines: 2-way on 3 pairs)
-   static constexpr int RS = D1 + 1, SZ = D1 * RS, NDP = (D1 * SZ + 1) & ~1;
+   static constexpr int LG = NL <= 4 ? 4 : (NL <= 8 ? 8 : (NL <= 16 ? 16 : 32));   // lanes per element
+   static constexpr int E = 32 / LG;                                                // elements per warp
+   static constexpr bool V2 = (D1 % 2 == 0);                // rows move as 16-byte words
+   // padded DOF block
+   static constexpr int RS = D1, SZ = D1 * RS + (V2 ? 2 : 1), EL = (D1 * SZ + 1) & ~1;
+   static constexpr int NEL = NF * NFD + 4;                 // neighbour traces of one element (+pad)
+   static constexpr int BEL = N3 * 2;                       // (min,max) pairs of one element
    __device__ static __forceinline__ int posU(int z, int y, int x) { return z * SZ + y * RS + x; }
-   __device__ static __forceinline__ int posUj(int j) { return posU(j / NL, (j / D1) % D1, j % D1); }
    // one data stage (doubles)
    static constexpr int P_U = 0;
-   static constexpr int P_X = P_U + NDP;
-   static constexpr int P_N = P_X + ((ND + 1) & ~1);
-   static constexpr int P_B = P_N + ((NF * NFD + 1) & ~1);
-   static constexpr int P_A = P_B + N3 * 2;                 // a_x a_y a_z 1/vol
-   static constexpr int PSZ = P_A + 4;
-   static constexpr int OFF_X = NST * PSZ;                  // per-axis results [3][NDP]
-   static constexpr int WDBL = OFF_X + 3 * NDP;
-   static constexpr int I_NE = 0, I_NP = NF, I_BI = 2 * NF, ISZ = (2 * NF + N3 + 1) & ~1;
+   static constexpr int P_N = P_U + E * EL;
+   static constexpr int P_B = P_N + ((E * NEL + 1) & ~1);
+   static constexpr int P_A = P_B + E * BEL;                // a_x a_y a_z 1/vol per element
+   static constexpr int PSZ = P_A + E * 4;
+   static constexpr int OFF_X = NST * PSZ;                  // y- and z-line results [2][E * EL]
+   static constexpr int WDBL = OFF_X + 2 * E * EL;
+   static constexpr int I_NE = 0, I_NP = E * NF, I_BI = 2 * E * NF, ISZ = (2 * E * NF + E * N3 + 3) & ~3;
    static constexpr int WINT = NST * ISZ;
    static constexpr int WBYTES = ((WDBL * 8 + WINT * 4) + 15) & ~15;
    static constexpr int PATMAX = 16;
@@ -70,97 +80,118 @@ __device__ __forceinline__ void cp_async_wait_group()
    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// gather indices of the group's nv elements (consecutive elements: contiguous index blocks)
 template <int D1, int NST>
-__device__ __forceinline__ void stagec_fetch_idx(const StagePArgs &a, int *ix, int64_t e, int lane)
+__device__ __forceinline__ void stagec_fetch_idx(const StagePArgs &a, int *ix, int64_t e0, int nv, int lane)
 {
    using S = SmemC<D1, NST>;
-   constexpr int NF = S::NF, N3 = S::N3;
-   if (lane < NF)
+   constexpr int NF = S::NF, N3 = S::N3, E = S::E;
+#pragma unroll
+   for (int i0 = 0; i0 < E * NF; i0 += 32)
    {
-      cp_async4(ix + S::I_NE + lane, a.fn.nbr_elem + e * NF + lane);
-      cp_async4(ix + S::I_NP + lane, a.nbr_pat32 + e * NF + lane);
+      const int i = i0 + lane;
+      if (i < nv * NF)
+      {
+         cp_async4(ix + S::I_NE + i, a.fn.nbr_elem + e0 * NF + i);
+         cp_async4(ix + S::I_NP + i, a.nbr_pat32 + e0 * NF + i);
+      }
    }
    const int nb = (a.bounds_type == 0) ? N3 : NF;
-   if (lane < nb) { cp_async4(ix + S::I_BI + lane, a.bidx + e * nb + lane); }
+#pragma unroll
+   for (int i0 = 0; i0 < E * N3; i0 += 32)
+   {
+      const int i = i0 + lane;
+      if (i < nv * nb) { cp_async4(ix + S::I_BI + i, a.bidx + e0 * nb + i); }
+   }
 }
 
+// lane = (el, row): its own row of y; then the group's neighbour traces, bounds and coefficients
 template <int D1, int NST>
 __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *dst, const int *ix,
-                                                  const int16_t *spat, int64_t e, int lane)
+                                                  const int16_t *spat, int64_t e0, int nv, int lane,
+                                                  bool row_on, int row_src, int row_dst)
 {
    using S = SmemC<D1, NST>;
-   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, N3 = S::N3;
+   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, N3 = S::N3, E = S::E;
+   if (row_on)
    {
-      const double *gu = a.y + e * ND, *gx = a.x0 + e * ND;
-      double *U = dst + S::P_U, *X = dst + S::P_X;
-#pragma unroll
-      for (int c0 = 0; c0 < ND; c0 += 32)
+      const double *g = a.y + e0 * ND + row_src;
+      double *U = dst + S::P_U + row_dst;
+      if (S::V2)
       {
-         const int c = c0 + lane;
-         if (c < ND) { cp_async8(U + S::posUj(c), gu + c); }
+#pragma unroll
+         for (int i = 0; i < D1; i += 2) { cp_async16(U + i, g + i); }
       }
-      if (a.has_x0)
+      else
       {
-         if ((ND & 1) == 0)
-         {
 #pragma unroll
-            for (int c0 = 0; c0 < ND / 2; c0 += 32)
-            {
-               const int c = c0 + lane;
-               if (c < ND / 2) { cp_async16(X + 2 * c, gx + 2 * c); }
-            }
-         }
-         else
-         {
-#pragma unroll
-            for (int c0 = 0; c0 < ND; c0 += 32)
-            {
-               const int c = c0 + lane;
-               if (c < ND) { cp_async8(X + c, gx + c); }
-            }
-         }
+         for (int i = 0; i < D1; i++) { cp_async8(U + i, g + i); }
       }
    }
    {
       double *NB = dst + S::P_N;
       const int *NE_ = ix + S::I_NE, *NP_ = ix + S::I_NP;
 #pragma unroll
-      for (int i0 = 0; i0 < NF * NFD; i0 += 32)
+      for (int i0 = 0; i0 < E * NF * NFD; i0 += 32)
       {
          const int id = i0 + lane;
-         if (id < NF * NFD)
+         const int F = id / NFD, j = id - F * NFD;       // F = el * NF + f
+         if (F < nv * NF)
          {
-            const int f = id / NFD, j = id - f * NFD;
-            const int nb = NE_[f];
+            const int el = F / NF;
+            const int nb = NE_[F];
+            double *d = NB + F * NFD + el * (S::NEL - NF * NFD) + j;
             if (nb >= 0)
             {
-               const int pid = NP_[f];
+               const int pid = NP_[F];
                const int loc = (pid < S::PATMAX) ? spat[pid * NFD + j] : a.fn.pat[pid * NFD + j];
                const double *src = (nb < a.fn.ne_owned)
                                       ? a.y + (int64_t)nb * ND + loc
                                       : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * ND + loc;
-               cp_async8(NB + id, src);
+               cp_async8(d, src);
             }
-            else { NB[id] = 0.0; }
+            else { *d = 0.0; }
          }
       }
    }
-   if (lane < 2) { cp_async16(dst + S::P_A + 2 * lane, a.opa + e * 4 + 2 * lane); }
+   if (lane < 2 * nv) { cp_async16(dst + S::P_A + 2 * lane, a.opa + e0 * 4 + 2 * lane); }
    {
       double *BD = dst + S::P_B;
       const int *BI = ix + S::I_BI;
       if (a.bounds_type == 0)
       {
-         if (lane < N3) { cp_async16(BD + 2 * lane, a.ent_mm + 2 * (int64_t)BI[lane]); }
+#pragma unroll
+         for (int i0 = 0; i0 < E * N3; i0 += 32)
+         {
+            const int i = i0 + lane;
+            if (i < nv * N3) { cp_async16(BD + 2 * i, a.ent_mm + 2 * (int64_t)BI[i]); }
+         }
       }
-      else if (lane <= NF)
+      else
       {
-         const int64_t src = (lane == NF) ? e : (int64_t)BI[lane];
-         double *d = BD + 2 * lane;
-         if (src >= 0) { cp_async8(d, a.xe_min + src); cp_async8(d + 1, a.xe_max + src); }
-         else { d[0] = INFINITY; d[1] = -INFINITY; }
+#pragma unroll
+         for (int i0 = 0; i0 < E * (NF + 1); i0 += 32)
+         {
+            const int i = i0 + lane;
+            if (i < nv * (NF + 1))
+            {
+               const int el = i / (NF + 1), k = i - el * (NF + 1);
+               const int64_t src = (k == NF) ? e0 + el : (int64_t)BI[el * NF + k];
+               double *d = BD + el * S::BEL + 2 * k;
+               if (src >= 0) { cp_async8(d, a.xe_min + src); cp_async8(d + 1, a.xe_max + src); }
+               else { d[0] = INFINITY; d[1] = -INFINITY; }
+            }
+         }
       }
    }
+}
+
+template <int LG>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+   for (int o = LG / 2; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+   return v;
 }
 
 template <int D1, int NW, int MINB, int NST>
@@ -168,63 +199,53 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 k_stage3c(StagePArgs a, const TabC<D1> tab)
 {
    using S = SmemC<D1, NST>;
-   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, N3 = S::N3, NL = S::NL, NDP = S::NDP;
-   constexpr int NK = (ND + 31) / 32;
-   constexpr int NR = (3 * NL + 31) / 32;        // line rounds
+   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, NL = S::NL, LG = S::LG, E = S::E;
+   constexpr int RS = S::RS, SZ = S::SZ, EL = S::EL, NEL = S::NEL, BEL = S::BEL;
    static_assert(NST >= 2 && NST <= 4, "ring depth");
    extern __shared__ double sm[];
    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
    int16_t *spat = reinterpret_cast<int16_t *>(sm);
    double *wsm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm) + S::CBYTES) + (size_t)w * (S::WBYTES / 8);
    int *ismem = reinterpret_cast<int *>(wsm + S::WDBL);
-   const double inv_dt = 1.0 / a.dt;
+   const double inv_dt = 1.0 / a.dt, dt = a.dt;
    {
       const int np = a.npat < S::PATMAX ? a.npat : S::PATMAX;
       for (int i = threadIdx.x; i < np * NFD; i += NW * 32) { spat[i] = a.fn.pat[i]; }
    }
-   // lattice class of each of the lane's DOFs (which of the 27 entities its bound comes from)
-   int cls[NK];
-#pragma unroll
-   for (int k = 0; k < NK; k++)
+   // ---- lane roles
+   // row owner: element el, row r = iz * D1 + iy
+   const int el = lane / LG, r = lane - el * LG;
+   const bool lane_on = r < NL;
+   const int iy = lane_on ? r % D1 : 0, iz = lane_on ? r / D1 : 0;
+   const int row_src = el * ND + (iz * D1 + iy) * D1;               // in the group's y / x0 / out block
+   const int row_dst = el * EL + S::posU(iz, iy, 0);                // in the padded shared block
+   // y-line owner: element ely, line (x = ya, z = yb).  Order 3: planes {0,2} | {1,3} per half-warp
+   int ely = el, ya = iy, yb = iz;
+   if (D1 == 4)
    {
-      int j = lane + 32 * k, t = 0, mul = 1;
-      if (j >= ND) { j = 0; }
-#pragma unroll
-      for (int ax = 0; ax < 3; ax++)
-      {
-         const int l = j % D1; j /= D1;
-         t += ((l == 0) ? 0 : ((l == D1 - 1) ? 2 : 1)) * mul; mul *= 3;
-      }
-      cls[k] = t;
+      const int t = (lane >> 2) & 3;
+      ely = t >> 1; ya = lane & 3; yb = 2 * (t & 1) + (lane >> 4);
    }
-   // the lane's grid line in every round: axis, base offset and stride in the padded block,
-   // offsets of its two neighbour trace values
-   int l_axis[NR], l_base[NR], l_str[NR], l_nlo[NR], l_nhi[NR];
-#pragma unroll
-   for (int r = 0; r < NR; r++)
-   {
-      const int gl = r * 32 + lane;
-      const bool on = gl < 3 * NL;
-      const int axis = on ? gl / NL : 0, l = on ? gl - axis * NL : 0;
-      const int la = l % D1, lb = l / D1;
-      // axis 0: x-lines (y = la, z = lb), faces 4 | 2;  axis 1: y-lines (x = la, z = lb), faces 1 | 3;
-      // axis 2: z-lines (x = la, y = lb), faces 0 | 5.  Natural face index = la + D1 * lb in all three.
-      l_axis[r] = on ? axis : -1;
-      l_base[r] = (axis == 0) ? S::posU(lb, la, 0) : ((axis == 1) ? S::posU(lb, 0, la) : S::posU(0, lb, la));
-      l_str[r] = (axis == 0) ? 1 : ((axis == 1) ? S::RS : S::SZ);
-      const int flo = (axis == 0) ? 4 : ((axis == 1) ? 1 : 0), fhi = (axis == 0) ? 2 : ((axis == 1) ? 3 : 5);
-      l_nlo[r] = flo * NFD + l;
-      l_nhi[r] = fhi * NFD + l;
-   }
+   const int yl_base = ely * EL + S::posU(yb, 0, ya);               // + k * RS
+   const int yl_nb = ely * NEL + ya + D1 * yb;                      // + f * NFD, f = 1 | 3
+   // z-line owner: element el, line (x = iy, y = iz) in row-owner numbering
+   const int zl_base = el * EL + S::posU(0, iz, iy);                // + k * SZ
+   const int zl_nb = el * NEL + iy + D1 * iz;                       // + f * NFD, f = 0 | 5
+   // lattice class of the row (bounds): base + {0, 1, 2} for x = 0 | interior | p
+   const int cy = (iy == 0) ? 0 : ((iy == D1 - 1) ? 2 : 1), cz = (iz == 0) ? 0 : ((iz == D1 - 1) ? 2 : 1);
+   const int cbase = el * BEL + 2 * (3 * cy + 9 * cz);
    __syncthreads();     // the only block barrier: the pattern table is in place
+   const int64_t NG = (a.ne + E - 1) / E;                           // element groups
    const int64_t GW = (int64_t)gridDim.x * NW;
-   int64_t e = (int64_t)blockIdx.x * NW + w;
-   if (e >= a.ne) { return; }
-   // ---- prologue: indices of the first NST-1 elements, then their data and the next NST-1 index sets
+   int64_t gi = (int64_t)blockIdx.x * NW + w;
+   if (gi >= NG) { return; }
+   auto nvalid = [&](int64_t g) { const int64_t n = a.ne - g * E; return (int)(n < E ? n : E); };
+   // ---- prologue: indices of the first NST-1 groups, then their data and the next NST-1 index sets
 #pragma unroll
    for (int m = 0; m < NST - 1; m++)
    {
-      if (e + m * GW < a.ne) { stagec_fetch_idx<D1, NST>(a, ismem + (m % NST) * S::ISZ, e + m * GW, lane); }
+      const int64_t g = gi + m * GW;
+      if (g < NG) { stagec_fetch_idx<D1, NST>(a, ismem + (m % NST) * S::ISZ, g * E, nvalid(g), lane); }
    }
    cp_async_commit();
    cp_async_wait_all();
@@ -232,143 +253,268 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
 #pragma unroll
    for (int m = 0; m < NST - 1; m++)
    {
-      if (e + m * GW < a.ne)
+      const int64_t g = gi + m * GW;
+      if (g < NG)
       {
-         stagec_fetch_data<D1, NST>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, e + m * GW, lane);
+         const int nv = nvalid(g);
+         stagec_fetch_data<D1, NST>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, g * E, nv, lane,
+                                    lane_on && el < nv, row_src, row_dst);
       }
    }
    __syncwarp();
 #pragma unroll
    for (int m = NST - 1; m < 2 * (NST - 1); m++)
    {
-      if (e + m * GW < a.ne) { stagec_fetch_idx<D1, NST>(a, ismem + (m % NST) * S::ISZ, e + m * GW, lane); }
+      const int64_t g = gi + m * GW;
+      if (g < NG) { stagec_fetch_idx<D1, NST>(a, ismem + (m % NST) * S::ISZ, g * E, nvalid(g), lane); }
    }
    cp_async_commit();
 #pragma unroll
    for (int m = 0; m < NST - 2; m++) { cp_async_commit(); }    // keep the group count of the steady state
-   double *XO = wsm + S::OFF_X;
-   for (int it = 0; e < a.ne; e += GW, it++)
+   double *XY = wsm + S::OFF_X, *XZ = XY + E * EL;
+   // x0 row of the first group
+   double x0n[D1];
+#pragma unroll
+   for (int i = 0; i < D1; i++) { x0n[i] = 0.0; }
+   auto load_x0 = [&](int64_t g)
    {
-      const int s = it % NST;
-      double *dat = wsm + s * S::PSZ;
-      const double *U = dat + S::P_U, *NB = dat + S::P_N, *A = dat + S::P_A;
-      cp_async_wait_group<NST - 2>();
-      __syncwarp();      // data(e) and idx(e + (NST-1) GW) landed; the previous element is fully consumed
+      if (a.has_x0 && lane_on && el < nvalid(g))
       {
-         const int m1 = it + NST - 1, m2 = it + 2 * (NST - 1);
-         const int64_t e1 = e + (int64_t)(NST - 1) * GW, e2 = e + (int64_t)(2 * (NST - 1)) * GW;
-         if (e1 < a.ne)
+         const double *p = a.x0 + g * (E * ND) + row_src;
+         if (S::V2)
          {
-            stagec_fetch_data<D1, NST>(a, wsm + (m1 % NST) * S::PSZ, ismem + (m1 % NST) * S::ISZ, spat, e1, lane);
-         }
-         if (e2 < a.ne) { stagec_fetch_idx<D1, NST>(a, ismem + (m2 % NST) * S::ISZ, e2, lane); }
-         cp_async_commit();
-      }
-      // ================= grid lines: out = -a T u + Minv[:,0] vs_lo (u_0 - nbr_lo) + Minv[:,p] vs_hi (u_p - nbr_hi)
 #pragma unroll
-      for (int r = 0; r < NR; r++)
-      {
-         if (l_axis[r] >= 0)
-         {
-            const double ac = A[l_axis[r]];
-            double u[D1];
-#pragma unroll
-            for (int k = 0; k < D1; k++) { u[k] = U[l_base[r] + k * l_str[r]]; }
-            const double jl = fmin(0.0, -ac) * (u[0] - NB[l_nlo[r]]);
-            const double jh = fmin(0.0, ac) * (u[D1 - 1] - NB[l_nhi[r]]);
-            double *o = XO + l_axis[r] * NDP + l_base[r];
-#pragma unroll
-            for (int i = 0; i < D1; i++)
+            for (int i = 0; i < D1; i += 2)
             {
-               double sacc = 0.0;
-#pragma unroll
-               for (int k = 0; k < D1; k++) { sacc = fma(tab.T[i][k], u[k], sacc); }
-               o[i * l_str[r]] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -ac * sacc));
+               const double2 v = __ldcs(reinterpret_cast<const double2 *>(p + i));
+               x0n[i] = v.x; x0n[i + 1] = v.y;
             }
          }
-      }
-      __syncwarp();
-      // ================= element-wise tail (MassBasedAvg, bounds, ClipScale, RK); see stage3w.cuh
-      {
-         const double *X0 = dat + S::P_X;
-         const double *BD = dat + S::P_B;
-         const double dt = a.dt;
-         const double sc = A[3];
-         const double inv_m = sc * (double)ND, m = 1.0 / inv_m, mdt = m * inv_dt;
-         double u[NK], du_ho[NK], f[NK], lo[NK], bmn[NK], bmx[NK];
-         double bmin1 = INFINITY, bmax1 = -INFINITY;
-         if (a.bounds_type == 1)
+         else
          {
 #pragma unroll
-            for (int k = 0; k <= NF; k++) { bmin1 = fmin(bmin1, BD[2 * k]); bmax1 = fmax(bmax1, BD[2 * k + 1]); }
+            for (int i = 0; i < D1; i++) { x0n[i] = __ldcs(p + i); }
+         }
+      }
+   };
+   load_x0(gi);
+   int slot = 0;                 // it % NST
+   for (; gi < NG; gi += GW)
+   {
+      double *dat = wsm + slot * S::PSZ;
+      const double *U = dat + S::P_U, *NB = dat + S::P_N, *A = dat + S::P_A, *BD = dat + S::P_B;
+      const int nv = nvalid(gi);
+      const bool on = lane_on && el < nv;
+      cp_async_wait_group<NST - 2>();
+      __syncwarp();      // data(g) and idx(g + (NST-1) GW) landed; the previous group is fully consumed
+      double x0[D1];
+#pragma unroll
+      for (int i = 0; i < D1; i++) { x0[i] = x0n[i]; }
+      {
+         const int s1 = (slot == 0) ? NST - 1 : slot - 1;      // (it + NST - 1) % NST
+         const int s2 = (NST == 2) ? slot : ((slot >= 2) ? slot - 2 : slot + NST - 2);   // (it + 2 NST - 2) % NST
+         const int64_t g1 = gi + (int64_t)(NST - 1) * GW, g2 = gi + (int64_t)(2 * (NST - 1)) * GW;
+         if (g1 < NG)
+         {
+            const int nv1 = nvalid(g1);
+            stagec_fetch_data<D1, NST>(a, wsm + s1 * S::PSZ, ismem + s1 * S::ISZ, spat, g1 * E, nv1, lane,
+                                       lane_on && el < nv1, row_src, row_dst);
+         }
+         if (g2 < NG) { stagec_fetch_idx<D1, NST>(a, ismem + s2 * S::ISZ, g2 * E, nvalid(g2), lane); }
+         cp_async_commit();
+         if (gi + GW < NG) { load_x0(gi + GW); }
+      }
+      // ================= y-lines and z-lines -> XY, XZ (every lane owns one line of each kind)
+      //   out_i = sum_k c_k v_k - (Minv[i][0] vs_lo) nbr_lo - (Minv[i][p] vs_hi) nbr_hi,
+      //   c = -a T[i][:], c_0 += Minv[i][0] vs_lo, c_p += Minv[i][p] vs_hi
+      if (lane_on && ely < nv)
+      {
+         const double ay = A[ely * 4 + 1];
+         const double vlo = fmin(0.0, -ay), vhi = fmin(0.0, ay);
+         double v[D1];
+#pragma unroll
+         for (int k = 0; k < D1; k++) { v[k] = U[yl_base + k * RS]; }
+         const double jl = vlo * (v[0] - NB[yl_nb + 1 * NFD]), jh = vhi * (v[D1 - 1] - NB[yl_nb + 3 * NFD]);
+#pragma unroll
+         for (int i = 0; i < D1; i++)
+         {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < D1; k++) { sacc = fma(tab.T[i][k], v[k], sacc); }
+            XY[yl_base + i * RS] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -ay * sacc));
+         }
+      }
+      if (on)
+      {
+         const double az = A[el * 4 + 2];
+         const double vlo = fmin(0.0, -az), vhi = fmin(0.0, az);
+         double v[D1];
+#pragma unroll
+         for (int k = 0; k < D1; k++) { v[k] = U[zl_base + k * SZ]; }
+         const double jl = vlo * (v[0] - NB[zl_nb + 0 * NFD]), jh = vhi * (v[D1 - 1] - NB[zl_nb + 5 * NFD]);
+#pragma unroll
+         for (int i = 0; i < D1; i++)
+         {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < D1; k++) { sacc = fma(tab.T[i][k], v[k], sacc); }
+            XZ[zl_base + i * SZ] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -az * sacc));
+         }
+      }
+      // ================= x-row in registers
+      double u[D1], ho[D1];
+#pragma unroll
+      for (int i = 0; i < D1; i++) { u[i] = 0.0; ho[i] = 0.0; }
+      double sc = 0.0;
+      if (on)
+      {
+         if (S::V2)
+         {
+#pragma unroll
+            for (int i = 0; i < D1; i += 2)
+            {
+               const double2 t = *reinterpret_cast<const double2 *>(U + row_dst + i);
+               u[i] = t.x; u[i + 1] = t.y;
+            }
+         }
+         else
+         {
+#pragma unroll
+            for (int i = 0; i < D1; i++) { u[i] = U[row_dst + i]; }
+         }
+         const double ax = A[el * 4 + 0];
+         sc = A[el * 4 + 3];
+         const double vlo = fmin(0.0, -ax), vhi = fmin(0.0, ax);
+         const int xnb = el * NEL + iy + D1 * iz;
+         const double jl = vlo * (u[0] - NB[xnb + 4 * NFD]), jh = vhi * (u[D1 - 1] - NB[xnb + 2 * NFD]);
+#pragma unroll
+         for (int i = 0; i < D1; i++)
+         {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < D1; k++) { sacc = fma(tab.T[i][k], u[k], sacc); }
+            ho[i] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -ax * sacc));
+         }
+      }
+      __syncwarp();      // XY, XZ complete
+      // ================= element-wise tail on the row owner (MassBasedAvg, bounds, ClipScale, RK)
+      {
+         const double inv_m = sc * (double)ND, m = on ? 1.0 / inv_m : 0.0, mdt = m * inv_dt;
+         double bmn[3], bmx[3];
+         if (on)
+         {
+            if (S::V2)
+            {
+#pragma unroll
+               for (int i = 0; i < D1; i += 2)
+               {
+                  const double2 ty = *reinterpret_cast<const double2 *>(XY + row_dst + i);
+                  const double2 tz = *reinterpret_cast<const double2 *>(XZ + row_dst + i);
+                  ho[i] = (ho[i] + ty.x + tz.x) * sc; ho[i + 1] = (ho[i + 1] + ty.y + tz.y) * sc;
+               }
+            }
+            else
+            {
+#pragma unroll
+               for (int i = 0; i < D1; i++) { ho[i] = (ho[i] + XY[row_dst + i] + XZ[row_dst + i]) * sc; }
+            }
+            if (a.bounds_type == 0)
+            {
+#pragma unroll
+               for (int q = 0; q < 3; q++)
+               {
+                  const double2 t = *reinterpret_cast<const double2 *>(BD + cbase + 2 * q);
+                  bmn[q] = t.x; bmx[q] = t.y;
+               }
+            }
+            else
+            {
+               double bmin1 = INFINITY, bmax1 = -INFINITY;
+#pragma unroll
+               for (int k = 0; k <= NF; k++)
+               {
+                  bmin1 = fmin(bmin1, BD[el * BEL + 2 * k]); bmax1 = fmax(bmax1, BD[el * BEL + 2 * k + 1]);
+               }
+#pragma unroll
+               for (int q = 0; q < 3; q++) { bmn[q] = bmin1; bmx[q] = bmax1; }
+            }
+         }
+         else
+         {
+#pragma unroll
+            for (int q = 0; q < 3; q++) { bmn[q] = 0.0; bmx[q] = 0.0; }
          }
          double s1 = 0.0;
 #pragma unroll
-         for (int k = 0; k < NK; k++)
-         {
-            const int j = lane + 32 * k;
-            if (j < ND)
-            {
-               const int pj = S::posUj(j);
-               u[k] = U[pj];
-               du_ho[k] = (XO[pj] + XO[NDP + pj] + XO[2 * NDP + pj]) * sc;
-               if (a.bounds_type == 0) { bmn[k] = BD[2 * cls[k]]; bmx[k] = BD[2 * cls[k] + 1]; }
-               else { bmn[k] = bmin1; bmx[k] = bmax1; }
-               s1 += u[k] + dt * du_ho[k];
-            }
-         }
-         s1 = warp_sum(s1);
+         for (int i = 0; i < D1; i++) { s1 += u[i] + dt * ho[i]; }
+         s1 = group_sum<LG>(s1);
          const double ubar = s1 * (1.0 / ND);                // MassBasedAvg, remhos_lo.cpp:278-285
+         double lo[D1], fp[D1], fn[D1];
          double sumPos = 0.0, sumNeg = 0.0;
 #pragma unroll
-         for (int k = 0; k < NK; k++)
+         for (int i = 0; i < D1; i++)
          {
-            const int j = lane + 32 * k;
-            if (j < ND)
-            {
-               lo[k] = (ubar - u[k]) * inv_dt;
-               const double u_new_lo = u[k] + dt * lo[k];
-               const double fmn = mdt * (bmn[k] - u_new_lo);
-               const double fmx = mdt * (bmx[k] - u_new_lo);
-               double fcl = m * (du_ho[k] - lo[k]);
-               fcl = fmin(fmx, fmax(fmn, fcl));               // ClipScale, remhos_fct.cpp:490-515
-               f[k] = fcl;
-               sumNeg += fmin(fcl, 0.0);
-               sumPos += fmax(fcl, 0.0);
-            }
+            const int q = (i == 0) ? 0 : ((i == D1 - 1) ? 2 : 1);
+            lo[i] = (ubar - u[i]) * inv_dt;
+            const double u_new_lo = u[i] + dt * lo[i];
+            const double fmn = mdt * (bmn[q] - u_new_lo);
+            const double fmx = mdt * (bmx[q] - u_new_lo);
+            double fcl = m * (ho[i] - lo[i]);
+            fcl = fmin(fmx, fmax(fmn, fcl));               // ClipScale, remhos_fct.cpp:490-515
+            fp[i] = fmax(fcl, 0.0);
+            fn[i] = fcl - fp[i];                           // = fmin(fcl, 0), exactly
+            sumNeg += fn[i];
+            sumPos += fp[i];
          }
-         warp_sum2(sumNeg, sumPos);
+         sumNeg = group_sum<LG>(sumNeg);
+         sumPos = group_sum<LG>(sumPos);
          const double new_mass = sumNeg + sumPos;
          constexpr double eps = 1.0e-15;
          const bool sp = new_mass > eps, sn = new_mass < -eps;
-         const double ratio = sp ? sumNeg / sumPos : (sn ? sumPos / sumNeg : 0.0);
+         // positive excess: scale the positive fluxes by -sumNeg/sumPos; negative excess: the converse
+         const double cpos = sp ? -(sumNeg / sumPos) : 1.0, cneg = sn ? -(sumPos / sumNeg) : 1.0;
+         double o[D1];
          double omin = INFINITY, omax = -INFINITY;
 #pragma unroll
-         for (int k = 0; k < NK; k++)
+         for (int i = 0; i < D1; i++)
          {
-            const int j = lane + 32 * k;
-            if (j < ND)
+            const double fcl = fma(cneg, fn[i], cpos * fp[i]);      // one of fn, fp is zero: exact
+            const double du = lo[i] + fcl * inv_m;
+            double v = du;
+            if (a.out_mode == 1)
             {
-               double fcl = f[k];
-               if (sp) { fcl = fmin(0.0, fcl) - fmax(0.0, fcl) * ratio; }
-               if (sn) { fcl = fmax(0.0, fcl) - fmin(0.0, fcl) * ratio; }
-               const double du = lo[k] + fcl * inv_m;
-               double o = du;
-               if (a.out_mode == 1)
-               {
-                  const double base = a.has_x0 ? a.a * X0[j] : 0.0;
-                  o = base + a.b * (u[k] + dt * du);
-               }
-               a.out[e * ND + j] = o;
-               omin = fmin(omin, o); omax = fmax(omax, o);
+               const double base = a.has_x0 ? a.a * x0[i] : 0.0;
+               v = base + a.b * (u[i] + dt * du);
+            }
+            o[i] = v;
+            if (on) { omin = fmin(omin, v); omax = fmax(omax, v); }
+         }
+         if (on)
+         {
+            double *p = a.out + gi * (E * ND) + row_src;
+            if (S::V2)
+            {
+#pragma unroll
+               for (int i = 0; i < D1; i += 2) { *reinterpret_cast<double2 *>(p + i) = make_double2(o[i], o[i + 1]); }
+            }
+            else
+            {
+#pragma unroll
+               for (int i = 0; i < D1; i++) { p[i] = o[i]; }
             }
          }
          if (a.xe_min_out)
          {
-            warp_minmax(omin, omax);
-            if (lane == 0) { a.xe_min_out[e] = omin; a.xe_max_out[e] = omax; }
+#pragma unroll
+            for (int s = LG / 2; s > 0; s >>= 1)
+            {
+               omin = fmin(omin, __shfl_xor_sync(0xffffffffu, omin, s));
+               omax = fmax(omax, __shfl_xor_sync(0xffffffffu, omax, s));
+            }
+            if (r == 0 && el < nv) { a.xe_min_out[gi * E + el] = omin; a.xe_max_out[gi * E + el] = omax; }
          }
       }
+      slot = (slot + 1 == NST) ? 0 : slot + 1;
    }
 }
 
