@@ -150,12 +150,15 @@ def main():
     ap.add_argument('--rs', type=int, default=5)
     ap.add_argument('--order', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--problem', type=int, default=0,
+                    help='0: constant velocity (BASELINE config); 1: rotation (velocity linear in x: '
+                         'exercises the general FP64 tensor-core kernel)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     workload = ('3D periodic-cube transport, order %d hex, -rs %d, -ho 3 -lo 5 -fct 2 -pa -s 3 '
-                '(problem 0)' % (a.order, a.rs))
+                '(problem %d)' % (a.order, a.rs, a.problem))
     metric = 'DOF*RK-stage updates/sec (3D hex, order 3, FCT)'
 
     if a.impl == 'reference':
@@ -190,7 +193,7 @@ def main():
     if world == 1:
         mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
         mesh.refine(a.rs)
-        prob = Problem(mesh, problem=0, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
+        prob = Problem(mesh, problem=a.problem, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
                        device=local_rank)
         ctx = prob.ctx
 
@@ -207,7 +210,7 @@ def main():
         nloc = 3 * 2 ** a.rs
         mesh = rb.Mesh.cartesian([nloc * d for d in pdims], [2.0 * d for d in pdims],
                                  origin=[-1.0 * d for d in pdims], periodic=True)
-        prob = DistProblem(mesh, rank, world, problem=0, order=a.order, mesh_order=2,
+        prob = DistProblem(mesh, rank, world, problem=a.problem, order=a.order, mesh_order=2,
                            bounds_type=0, dt=dt, device=local_rank)
         del mesh
         ctx = prob.ctx
@@ -288,6 +291,20 @@ def main():
     peak, which = read_peaks()
     k_ms = kms / max(klaunch, 1)
     achieved = B_ALG * N / (k_ms * 1e-3) / 1e9 if klaunch else None
+    # which fused stage kernel ran (rmh_ctx_path_flags): bit 3 = constant-coefficient kernel
+    # (affine elements, element-wise constant velocity: stage3c.cuh), else the FP64 DMMA kernel
+    const_op = bool(ctx.path_flags & 8)
+    if const_op:
+        kname = 'k_stage3c<%d> (constant-coefficient line kernel, %d elements per warp)' % (
+            a.order + 1, {1: 8, 2: 2, 3: 2, 4: 1}.get(a.order, 1))
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+        # workload (profiles/r01/ncu_stage_v12_const_rs5.txt)
+        traffic = (1.254585e9 + 439.694080e6) if (a.order == 3 and a.rs == 5) else None
+    else:
+        kname = 'k_stage3w<%d,%d,%s> (FP64 DMMA, warp per element)' % (
+            a.order + 1, a.order + 3, '8,2' if a.order <= 3 else '6,2')
+        # profiles/r01/ncu_stage_v9_hoisted_rs5.txt
+        traffic = (7.000267e9 + 458.27968e6) if (a.order == 3 and a.rs == 5) else None
     line = {
         'metric': metric, 'value': value, 'unit': 'DOF*stage/s', 'n_gpus': world,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
@@ -295,7 +312,8 @@ def main():
         'data': 'synthetic',
         'config': {'workload': workload, 'dofs_per_gpu': N, 'elements_per_gpu': ctx.ne,
                    'stages_per_step': STAGES, 'dt': dt,
-                   'l2': 'state vectors (453 MB each) and operator data (7.6 GB) exceed the 126 MB L2',
+                   'l2': 'state vectors (453 MB each at -rs 5) exceed the 126 MB L2',
+                   'problem': a.problem,
                    'parallelism': ('domain decomposition %dx%dx%d bricks, NCCL halo exchange per stage'
                                    % tuple(pdims)) if world > 1 else 'single GPU'},
         'e2e': {'value': e2e, 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 8 * N,
@@ -303,14 +321,13 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'hbm',
-                     'kernel': 'k_stage3w<%d,%d,%s> (FP64 DMMA, warp per element)'
-                               % (a.order + 1, a.order + 3, '8,2' if a.order <= 3 else '6,2'),
+                     'kernel': kname,
                      'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu
-                     # --set full capture of this workload (profiles/r01/ncu_stage_v9_hoisted_rs5.txt)
-                     'traffic': (7.000267e9 + 458.27968e6) if (a.order == 3 and a.rs == 5) else None,
-                     'traffic_unit': 'bytes per launch',
+                     'traffic': traffic, 'traffic_unit': 'bytes per launch',
+                     # the fused kernel moves far less than the 136 B/DOF of five separate kernels:
+                     # its own DRAM traffic over its own time, as a fraction of the HBM peak
+                     'traffic_frac_of_peak': (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
                      'alg_bytes_per_dof_stage': B_ALG, 'kernel_ms': k_ms,
                      'kernel_share_of_step': (kms / ms) if klaunch else None},
         'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0), 'u_min': umin, 'u_max': umax},

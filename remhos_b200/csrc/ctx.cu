@@ -1247,31 +1247,39 @@ static TabC<D1> make_tabc(const rmh_ctx *c)
    return o;
 }
 
-template <int D1, int Q, int NW, int MINB, int NST>
-static int launch_stagec_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+template <int D1, int Q, int NW, int MINB, int NST, bool GH>
+static int launch_stagec_G(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    using S = SmemC<D1, NST>;
    constexpr size_t BYTES = S::bytes(NW);
    static int blocks_per_sm = 0;
    if (blocks_per_sm == 0)
    {
-      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST, GH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)BYTES));
       int nb = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST>, NW * 32, BYTES));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST, GH>, NW * 32, BYTES));
       if (nb < 1) { set_error("k_stage3c does not fit on an SM"); return 1; }
       blocks_per_sm = std::min(nb, MINB);
       if (getenv("RMH_VERBOSE"))
       {
-         fprintf(stderr, "k_stage3c<%d,%d,%d,%d>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
-                 blocks_per_sm, nb, BYTES);
+         fprintf(stderr, "k_stage3c<%d,%d,%d,%d,%s>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
+                 GH ? "ghosts" : "local", blocks_per_sm, nb, BYTES);
       }
    }
-   const int64_t nblk = (a.ne + NW - 1) / NW;
+   const int64_t ngrp = (a.ne + S::E - 1) / S::E;
+   const int64_t nblk = (ngrp + NW - 1) / NW;
    const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
-   k_stage3c<D1, NW, MINB, NST><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
+   k_stage3c<D1, NW, MINB, NST, GH><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
    LAUNCH_OK();
    return 0;
+}
+
+template <int D1, int Q, int NW, int MINB, int NST>
+static int launch_stagec_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
+{
+   return (c->ne_ghost > 0) ? launch_stagec_G<D1, Q, NW, MINB, NST, true>(c, a, s)
+                            : launch_stagec_G<D1, Q, NW, MINB, NST, false>(c, a, s);
 }
 
 template <int DIM, int D1, int Q>
@@ -1291,8 +1299,10 @@ static int launch_stagec(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
          case 632: return launch_stagec_N<D1, Q, 6, 3, 2>(c, a, s);     // 18 warps, ring of 2
          case 1213: return launch_stagec_N<D1, Q, 12, 1, 3>(c, a, s);   // 12 warps, ring of 3
          case 2012: return launch_stagec_N<D1, Q, 20, 1, 2>(c, a, s);   // 20 warps (one block), ring of 2
-         case 1612: return launch_stagec_N<D1, Q, 16, 1, 2>(c, a, s);   // 16 warps (one block), ring of 2
-         default: return launch_stagec_N<D1, Q, 10, 2, 2>(c, a, s);     // 20 warps, ring of 2
+         case 1022: return launch_stagec_N<D1, Q, 10, 2, 2>(c, a, s);   // 20 warps, ring of 2
+         default:                                                        // 16 warps (one block), ring of 2
+            if constexpr (SmemC<D1, 2>::bytes(16) <= 227 * 1024) { return launch_stagec_N<D1, Q, 16, 1, 2>(c, a, s); }
+            else { return launch_stagec_N<D1, Q, 8, 1, 2>(c, a, s); }   // order 1: eight elements per warp
       }
    }
    else
@@ -1878,7 +1888,8 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       {
          static int blk = -1;   // RMH_TENSOR_BLOCK=1: block-per-batch DMMA kernel (stage3t.cuh)
          if (blk < 0) { const char *ev = getenv("RMH_TENSOR_BLOCK"); blk = (ev && ev[0] == '1') ? 1 : 0; }
-         if (pa.opa && !blk) { return dispatch_stagec(c, pa, s); }
+         // (the constant-coefficient kernel keeps the whole orientation-pattern table in shared memory)
+         if (pa.opa && !blk && c->npat <= 16) { return dispatch_stagec(c, pa, s); }
          return blk ? dispatch_staget(c, pa, s) : dispatch_stagew(c, pa, s);
       }
       return use_p ? dispatch_stagep(c, pa, s) : dispatch_stage(c, sa, s);

@@ -79,84 +79,137 @@ __device__ __forceinline__ void cp_async_wait_group()
 {
    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// cp.async with 32-bit shared-window destinations (one generic->shared conversion per ring slot)
+__device__ __forceinline__ void cps16(unsigned s, const void *g)
+{
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cps8(unsigned s, const void *g)
+{
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cps4(unsigned s, const void *g)
+{
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(g) : "memory");
+}
+// 8-byte copy, or 8 bytes of zeros when nbytes == 0 (domain boundary: exterior state 0)
+__device__ __forceinline__ void cps8z(unsigned s, const void *g, unsigned nbytes)
+{
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(g), "r"(nbytes) : "memory");
+}
+// min / max without the NaN fix-up of fmin / fmax (3 instead of ~7 instructions on sm_100a; the
+// operands here are never NaN in a valid run, and a NaN still propagates into the output)
+__device__ __forceinline__ double dmin(double x, double y) { return x < y ? x : y; }
+__device__ __forceinline__ double dmax(double x, double y) { return x > y ? x : y; }
 
 // gather indices of the group's nv elements (consecutive elements: contiguous index blocks)
 template <int D1, int NST>
-__device__ __forceinline__ void stagec_fetch_idx(const StagePArgs &a, int *ix, int64_t e0, int nv, int lane)
+__device__ __forceinline__ void stagec_fetch_idx(const StagePArgs &a, unsigned six, int64_t e0, int nv, int lane)
 {
    using S = SmemC<D1, NST>;
    constexpr int NF = S::NF, N3 = S::N3, E = S::E;
-#pragma unroll
-   for (int i0 = 0; i0 < E * NF; i0 += 32)
+   const int nb = (a.bounds_type == 0) ? N3 : NF;
+   if (nv == E && ((E * nb) & 1) == 0)
    {
-      const int i = i0 + lane;
-      if (i < nv * NF)
+      // full group: 8-byte copies (E*NF and E*nb are even, so every block starts 8-byte aligned)
+      if (lane < E * NF / 2)
       {
-         cp_async4(ix + S::I_NE + i, a.fn.nbr_elem + e0 * NF + i);
-         cp_async4(ix + S::I_NP + i, a.nbr_pat32 + e0 * NF + i);
+         cps8(six + (S::I_NE + 2 * lane) * 4, a.fn.nbr_elem + e0 * NF + 2 * lane);
+         cps8(six + (S::I_NP + 2 * lane) * 4, a.nbr_pat32 + e0 * NF + 2 * lane);
+      }
+#pragma unroll
+      for (int i0 = 0; i0 < E * N3 / 2; i0 += 32)
+      {
+         const int i = i0 + lane;
+         if (i < E * nb / 2) { cps8(six + (S::I_BI + 2 * i) * 4, a.bidx + e0 * nb + 2 * i); }
       }
    }
-   const int nb = (a.bounds_type == 0) ? N3 : NF;
-#pragma unroll
-   for (int i0 = 0; i0 < E * N3; i0 += 32)
+   else
    {
-      const int i = i0 + lane;
-      if (i < nv * nb) { cp_async4(ix + S::I_BI + i, a.bidx + e0 * nb + i); }
+#pragma unroll
+      for (int i0 = 0; i0 < E * NF; i0 += 32)
+      {
+         const int i = i0 + lane;
+         if (i < nv * NF)
+         {
+            cps4(six + (S::I_NE + i) * 4, a.fn.nbr_elem + e0 * NF + i);
+            cps4(six + (S::I_NP + i) * 4, a.nbr_pat32 + e0 * NF + i);
+         }
+      }
+#pragma unroll
+      for (int i0 = 0; i0 < E * N3; i0 += 32)
+      {
+         const int i = i0 + lane;
+         if (i < nv * nb) { cps4(six + (S::I_BI + i) * 4, a.bidx + e0 * nb + i); }
+      }
    }
 }
 
-// lane = (el, row): its own row of y; then the group's neighbour traces, bounds and coefficients
-template <int D1, int NST>
+// lane = (el, row): its own row of y; then the group's neighbour traces, bounds and coefficients.
+// GH: some neighbours are ghost elements (multi-GPU), their DOF blocks live in a.fn.ughost.
+template <int D1, int NST, bool GH>
 __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *dst, const int *ix,
                                                   const int16_t *spat, int64_t e0, int nv, int lane,
                                                   bool row_on, int row_src, int row_dst)
 {
    using S = SmemC<D1, NST>;
    constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, N3 = S::N3, E = S::E;
-   if (row_on)
+   const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
+   if (S::V2)
    {
-      const double *g = a.y + e0 * ND + row_src;
-      double *U = dst + S::P_U + row_dst;
-      if (S::V2)
-      {
+      // 16-byte chunks in memory order: one instruction moves 512 contiguous bytes (4 cache lines;
+      // a lane copying its own row would touch every 32-byte sector twice, 14 instead of 4
+      // shared-memory wavefronts per instruction)
+      constexpr int CPR = D1 / 2;                       // chunks per row
+      const double *g = a.y + e0 * ND;
 #pragma unroll
-         for (int i = 0; i < D1; i += 2) { cp_async16(U + i, g + i); }
-      }
-      else
+      for (int c0 = 0; c0 < E * ND / 2; c0 += 32)
       {
-#pragma unroll
-         for (int i = 0; i < D1; i++) { cp_async8(U + i, g + i); }
+         const int ch = c0 + lane;
+         const int row = ch / CPR, h = ch - row * CPR;  // row = el * NL + (iz * D1 + iy)
+         const int el = row / S::NL, r = row - el * S::NL;
+         if (ch < nv * (ND / 2))
+         {
+            cps16(sd + (S::P_U + el * S::EL + (r / D1) * S::SZ + (r % D1) * S::RS + 2 * h) * 8, g + 2 * ch);
+         }
       }
    }
+   else if (row_on)
    {
-      double *NB = dst + S::P_N;
+      const double *g = a.y + e0 * ND + row_src;
+      const unsigned su = sd + (S::P_U + row_dst) * 8;
+#pragma unroll
+      for (int i = 0; i < D1; i++) { cps8(su + i * 8, g + i); }
+   }
+   {
       const int *NE_ = ix + S::I_NE, *NP_ = ix + S::I_NP;
+      // 32 % NFD == 0 (orders 1 and 3): face and face-DOF index of a lane differ by constants per slot
+      constexpr bool P2 = (32 % NFD == 0);
+      const int lq = lane / NFD, lj = lane % NFD;
 #pragma unroll
       for (int i0 = 0; i0 < E * NF * NFD; i0 += 32)
       {
-         const int id = i0 + lane;
-         const int F = id / NFD, j = id - F * NFD;       // F = el * NF + f
+         int F, j;
+         if (P2) { F = i0 / NFD + lq; j = lj; }
+         else { const int id = i0 + lane; F = id / NFD; j = id - F * NFD; }       // F = el * NF + f
          if (F < nv * NF)
          {
             const int el = F / NF;
             const int nb = NE_[F];
-            double *d = NB + F * NFD + el * (S::NEL - NF * NFD) + j;
-            if (nb >= 0)
+            const int pid = NP_[F];
+            const int loc = spat[pid * NFD + j];
+            const unsigned d = sd + (S::P_N + F * NFD + el * (S::NEL - NF * NFD) + j) * 8;
+            const double *src = a.y + (unsigned)((nb < 0 ? 0 : nb) * ND + loc);
+            if (GH)
             {
-               const int pid = NP_[F];
-               const int loc = (pid < S::PATMAX) ? spat[pid * NFD + j] : a.fn.pat[pid * NFD + j];
-               const double *src = (nb < a.fn.ne_owned)
-                                      ? a.y + (int64_t)nb * ND + loc
-                                      : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * ND + loc;
-               cp_async8(d, src);
+               if (nb >= a.fn.ne_owned) { src = a.fn.ughost + (unsigned)((nb - (int)a.fn.ne_owned) * ND + loc); }
             }
-            else { *d = 0.0; }
+            cps8z(d, src, nb < 0 ? 0u : 8u);
          }
       }
    }
-   if (lane < 2 * nv) { cp_async16(dst + S::P_A + 2 * lane, a.opa + e0 * 4 + 2 * lane); }
+   if (lane < 2 * nv) { cps16(sd + (S::P_A + 2 * lane) * 8, a.opa + e0 * 4 + 2 * lane); }
    {
-      double *BD = dst + S::P_B;
       const int *BI = ix + S::I_BI;
       if (a.bounds_type == 0)
       {
@@ -164,11 +217,12 @@ __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *d
          for (int i0 = 0; i0 < E * N3; i0 += 32)
          {
             const int i = i0 + lane;
-            if (i < nv * N3) { cp_async16(BD + 2 * i, a.ent_mm + 2 * (int64_t)BI[i]); }
+            if (i < nv * N3) { cps16(sd + (S::P_B + 2 * i) * 8, a.ent_mm + 2 * (int64_t)BI[i]); }
          }
       }
       else
       {
+         double *BD = dst + S::P_B;
 #pragma unroll
          for (int i0 = 0; i0 < E * (NF + 1); i0 += 32)
          {
@@ -194,7 +248,7 @@ __device__ __forceinline__ double group_sum(double v)
    return v;
 }
 
-template <int D1, int NW, int MINB, int NST>
+template <int D1, int NW, int MINB, int NST, bool GH>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_stage3c(StagePArgs a, const TabC<D1> tab)
 {
@@ -207,6 +261,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    int16_t *spat = reinterpret_cast<int16_t *>(sm);
    double *wsm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm) + S::CBYTES) + (size_t)w * (S::WBYTES / 8);
    int *ismem = reinterpret_cast<int *>(wsm + S::WDBL);
+   const unsigned six0 = (unsigned)__cvta_generic_to_shared(ismem);
    const double inv_dt = 1.0 / a.dt, dt = a.dt;
    {
       const int np = a.npat < S::PATMAX ? a.npat : S::PATMAX;
@@ -239,13 +294,14 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    const int64_t GW = (int64_t)gridDim.x * NW;
    int64_t gi = (int64_t)blockIdx.x * NW + w;
    if (gi >= NG) { return; }
-   auto nvalid = [&](int64_t g) { const int64_t n = a.ne - g * E; return (int)(n < E ? n : E); };
+   const int last_nv = (int)(a.ne - (NG - 1) * E);
+   auto nvalid = [&](int64_t g) { return (g + 1 == NG) ? last_nv : E; };
    // ---- prologue: indices of the first NST-1 groups, then their data and the next NST-1 index sets
 #pragma unroll
    for (int m = 0; m < NST - 1; m++)
    {
       const int64_t g = gi + m * GW;
-      if (g < NG) { stagec_fetch_idx<D1, NST>(a, ismem + (m % NST) * S::ISZ, g * E, nvalid(g), lane); }
+      if (g < NG) { stagec_fetch_idx<D1, NST>(a, six0 + (m % NST) * S::ISZ * 4, g * E, nvalid(g), lane); }
    }
    cp_async_commit();
    cp_async_wait_all();
@@ -257,7 +313,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
       if (g < NG)
       {
          const int nv = nvalid(g);
-         stagec_fetch_data<D1, NST>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, g * E, nv, lane,
+         stagec_fetch_data<D1, NST, GH>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, g * E, nv, lane,
                                     lane_on && el < nv, row_src, row_dst);
       }
    }
@@ -266,7 +322,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    for (int m = NST - 1; m < 2 * (NST - 1); m++)
    {
       const int64_t g = gi + m * GW;
-      if (g < NG) { stagec_fetch_idx<D1, NST>(a, ismem + (m % NST) * S::ISZ, g * E, nvalid(g), lane); }
+      if (g < NG) { stagec_fetch_idx<D1, NST>(a, six0 + (m % NST) * S::ISZ * 4, g * E, nvalid(g), lane); }
    }
    cp_async_commit();
 #pragma unroll
@@ -317,10 +373,10 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          if (g1 < NG)
          {
             const int nv1 = nvalid(g1);
-            stagec_fetch_data<D1, NST>(a, wsm + s1 * S::PSZ, ismem + s1 * S::ISZ, spat, g1 * E, nv1, lane,
+            stagec_fetch_data<D1, NST, GH>(a, wsm + s1 * S::PSZ, ismem + s1 * S::ISZ, spat, g1 * E, nv1, lane,
                                        lane_on && el < nv1, row_src, row_dst);
          }
-         if (g2 < NG) { stagec_fetch_idx<D1, NST>(a, ismem + s2 * S::ISZ, g2 * E, nvalid(g2), lane); }
+         if (g2 < NG) { stagec_fetch_idx<D1, NST>(a, six0 + s2 * S::ISZ * 4, g2 * E, nvalid(g2), lane); }
          cp_async_commit();
          if (gi + GW < NG) { load_x0(gi + GW); }
       }
@@ -330,7 +386,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
       if (lane_on && ely < nv)
       {
          const double ay = A[ely * 4 + 1];
-         const double vlo = fmin(0.0, -ay), vhi = fmin(0.0, ay);
+         const double vlo = dmin(0.0, -ay), vhi = dmin(0.0, ay);
          double v[D1];
 #pragma unroll
          for (int k = 0; k < D1; k++) { v[k] = U[yl_base + k * RS]; }
@@ -347,7 +403,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
       if (on)
       {
          const double az = A[el * 4 + 2];
-         const double vlo = fmin(0.0, -az), vhi = fmin(0.0, az);
+         const double vlo = dmin(0.0, -az), vhi = dmin(0.0, az);
          double v[D1];
 #pragma unroll
          for (int k = 0; k < D1; k++) { v[k] = U[zl_base + k * SZ]; }
@@ -384,7 +440,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          }
          const double ax = A[el * 4 + 0];
          sc = A[el * 4 + 3];
-         const double vlo = fmin(0.0, -ax), vhi = fmin(0.0, ax);
+         const double vlo = dmin(0.0, -ax), vhi = dmin(0.0, ax);
          const int xnb = el * NEL + iy + D1 * iz;
          const double jl = vlo * (u[0] - NB[xnb + 4 * NFD]), jh = vhi * (u[D1 - 1] - NB[xnb + 2 * NFD]);
 #pragma unroll
@@ -433,7 +489,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
 #pragma unroll
                for (int k = 0; k <= NF; k++)
                {
-                  bmin1 = fmin(bmin1, BD[el * BEL + 2 * k]); bmax1 = fmax(bmax1, BD[el * BEL + 2 * k + 1]);
+                  bmin1 = dmin(bmin1, BD[el * BEL + 2 * k]); bmax1 = dmax(bmax1, BD[el * BEL + 2 * k + 1]);
                }
 #pragma unroll
                for (int q = 0; q < 3; q++) { bmn[q] = bmin1; bmx[q] = bmax1; }
@@ -460,8 +516,8 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
             const double fmn = mdt * (bmn[q] - u_new_lo);
             const double fmx = mdt * (bmx[q] - u_new_lo);
             double fcl = m * (ho[i] - lo[i]);
-            fcl = fmin(fmx, fmax(fmn, fcl));               // ClipScale, remhos_fct.cpp:490-515
-            fp[i] = fmax(fcl, 0.0);
+            fcl = dmin(fmx, dmax(fmn, fcl));               // ClipScale, remhos_fct.cpp:490-515
+            fp[i] = dmax(fcl, 0.0);
             fn[i] = fcl - fp[i];                           // = fmin(fcl, 0), exactly
             sumNeg += fn[i];
             sumPos += fp[i];
@@ -472,7 +528,8 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          constexpr double eps = 1.0e-15;
          const bool sp = new_mass > eps, sn = new_mass < -eps;
          // positive excess: scale the positive fluxes by -sumNeg/sumPos; negative excess: the converse
-         const double cpos = sp ? -(sumNeg / sumPos) : 1.0, cneg = sn ? -(sumPos / sumNeg) : 1.0;
+         const double rat = (sp || sn) ? -((sp ? sumNeg : sumPos) / (sp ? sumPos : sumNeg)) : 1.0;
+         const double cpos = sp ? rat : 1.0, cneg = sn ? rat : 1.0;
          double o[D1];
          double omin = INFINITY, omax = -INFINITY;
 #pragma unroll
@@ -487,7 +544,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
                v = base + a.b * (u[i] + dt * du);
             }
             o[i] = v;
-            if (on) { omin = fmin(omin, v); omax = fmax(omax, v); }
+            if (on) { omin = dmin(omin, v); omax = dmax(omax, v); }
          }
          if (on)
          {
@@ -508,8 +565,8 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
 #pragma unroll
             for (int s = LG / 2; s > 0; s >>= 1)
             {
-               omin = fmin(omin, __shfl_xor_sync(0xffffffffu, omin, s));
-               omax = fmax(omax, __shfl_xor_sync(0xffffffffu, omax, s));
+               omin = dmin(omin, __shfl_xor_sync(0xffffffffu, omin, s));
+               omax = dmax(omax, __shfl_xor_sync(0xffffffffu, omax, s));
             }
             if (r == 0 && el < nv) { a.xe_min_out[gi * E + el] = omin; a.xe_max_out[gi * E + el] = omax; }
          }

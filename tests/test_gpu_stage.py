@@ -145,7 +145,7 @@ def test_const_kernel_ring_depths(monkeypatch):
     run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=0,
                      rs_levels=2, order=3, dt=0.005, max_steps=2)
     res = []
-    for cfg in ('0', '822', '632', '1213', '2012', '1612'):
+    for cfg in ('0', '822', '632', '1213', '2012', '1022'):
         # the configuration is latched per process on first use: run each in a fresh interpreter
         import subprocess, sys, os, json
         code = ("import sys, os, numpy as np, torch; sys.path[:0] = [%r, %r, %r];"

@@ -1,5 +1,5 @@
 python -m pytest tests/test_gpu_stage.py -x -q > gpurun_out/t2.log 2>&1; tail -15 gpurun_out/t2.log
-for cfg in 0 822 632 1213 2012 1612; do echo "== C_CFG=$cfg"; RMH_VERBOSE=1 RMH_C_CFG=$cfg python bench.py --steps 10 --no-cpu-baseline 2>&1 | python -c "
+for cfg in 0 822 632 1213 2012 1022; do echo "== C_CFG=$cfg"; RMH_VERBOSE=1 RMH_C_CFG=$cfg python bench.py --steps 10 --no-cpu-baseline 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
