@@ -147,6 +147,13 @@ int rmh_ctx_nq1d(const rmh_ctx *ctx);
  * velocity is linear over every element (quadrature data rebuilt in-kernel from 12 doubles per
  * element instead of streamed; set RMH_NO_LINEAR_OP=1 before rmh_ctx_create to disable) */
 int rmh_ctx_path_flags(const rmh_ctx *ctx);
+/* on != 0: the caller promises not to modify the state vector between consecutive rmh_rk_step()
+ * calls on the same device pointer (the reference's time loop does not, remhos.cpp:1146-1330).
+ * The element min/max the last RK stage computes for its output (ComputeElementsMinMax,
+ * remhos_tools.cpp:497-523, fused into the stage kernel) are then reused by the next step's first
+ * stage instead of being recomputed by a separate pass over the state.  Default off.  Any other
+ * entry point that is handed a state vector recomputes what it needs. */
+int rmh_ctx_trust_state(rmh_ctx *ctx, int on);
 /* reference-element coordinates of the volume / face quadrature points, so a caller can
  * evaluate its velocity coefficient there: q1d[Q] Gauss-Legendre points on [0,1] */
 int rmh_ctx_quad_points_1d(const rmh_ctx *ctx, double *q1d, double *w1d);

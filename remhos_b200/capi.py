@@ -225,6 +225,9 @@ class Context:
         except Exception:
             pass
 
+    def trust_state(self, on=True):
+        check(lib().rmh_ctx_trust_state(self.h, int(bool(on))))
+
     def quad_points_1d(self):
         x = np.zeros(self.nq1d); w = np.zeros(self.nq1d)
         check(lib().rmh_ctx_quad_points_1d(self.h, _ptr(x), _ptr(w)))

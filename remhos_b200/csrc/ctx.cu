@@ -82,6 +82,8 @@ struct rmh_ctx
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    bool op_lin = false;       // ... and adj(J) v is linear over every element: opc is valid
    bool op_const = false;     // ... and constant over every element: opa is valid
+   bool trust_state = false;  // rmh_ctx_trust_state: the caller leaves the state alone between steps
+   const double *xe_ptr = nullptr;   // state vector whose element min/max the context currently holds
    double *opc = nullptr;     // [ne][12] (k_op_linear)
    double *opa = nullptr;     // [ne][4]  (k_op_linear)
    double *dxq = nullptr;     // device copy of the 1-D quadrature points
@@ -777,6 +779,76 @@ __global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_m
    if (lane == 0) { xe_min[e] = mn; xe_max[e] = mx; }
 }
 
+// same, streaming variant for even nd and 16-byte aligned u: a warp owns EW consecutive elements
+// and issues all of its 16-byte loads before the first reduction (the one-element-per-warp form
+// keeps two 8-byte loads in flight per lane and reaches a third of the HBM bandwidth)
+template <int EW>
+__global__ void __launch_bounds__(256) k_elem_min_max_v(int64_t ne, int nd, const double *__restrict__ u,
+                                                        double *xe_min, double *xe_max)
+{
+   const int64_t e0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * EW;
+   const int lane = threadIdx.x & 31;
+   if (e0 >= ne) { return; }
+   const int nd2 = nd >> 1;                 // double2 words per element
+   double mn[EW], mx[EW];
+#pragma unroll
+   for (int k = 0; k < EW; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+   for (int j0 = 0; j0 < nd2; j0 += 32)
+   {
+      double2 v[EW];
+#pragma unroll
+      for (int k = 0; k < EW; k++)
+      {
+         const int j = j0 + lane;
+         v[k] = make_double2(INFINITY, -INFINITY);
+         if (j < nd2 && e0 + k < ne)
+         {
+            const double2 t = __ldcs(reinterpret_cast<const double2 *>(u + (e0 + k) * nd) + j);
+            v[k] = make_double2(t.x < t.y ? t.x : t.y, t.x < t.y ? t.y : t.x);
+         }
+      }
+#pragma unroll
+      for (int k = 0; k < EW; k++)
+      {
+         mn[k] = v[k].x < mn[k] ? v[k].x : mn[k];
+         mx[k] = v[k].y > mx[k] ? v[k].y : mx[k];
+      }
+   }
+#pragma unroll
+   for (int k = 0; k < EW; k++)
+   {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+         const double a = __shfl_xor_sync(0xffffffffu, mn[k], o), b = __shfl_xor_sync(0xffffffffu, mx[k], o);
+         mn[k] = a < mn[k] ? a : mn[k];
+         mx[k] = b > mx[k] ? b : mx[k];
+      }
+   }
+   if (lane < EW && e0 + lane < ne)
+   {
+      double a = mn[0], b = mx[0];
+#pragma unroll
+      for (int k = 1; k < EW; k++) { if (lane == k) { a = mn[k]; b = mx[k]; } }
+      xe_min[e0 + lane] = a; xe_max[e0 + lane] = b;
+   }
+}
+
+static void launch_elem_min_max(int64_t ne, int nd, const double *u, double *xe_min, double *xe_max, cudaStream_t s)
+{
+   const int bs = 256;
+   if ((nd & 1) == 0 && (((uintptr_t)u) & 15) == 0)
+   {
+      constexpr int EW = 4;
+      const int64_t nw = (ne + EW - 1) / EW;
+      k_elem_min_max_v<EW><<<(unsigned)((nw * 32 + bs - 1) / bs), bs, 0, s>>>(ne, nd, u, xe_min, xe_max);
+   }
+   else
+   {
+      k_elem_min_max<<<(unsigned)((ne * 32 + bs - 1) / bs), bs, 0, s>>>(ne, nd, u, xe_min, xe_max);
+   }
+}
+
 // entity min/max over the elements sharing the entity (CG-dof overlap, remhos_tools.cpp:449-458)
 __global__ void k_ent_min_max(int32_t n_ent, const int32_t *off, const int32_t *el,
                               const double *xe_min, const double *xe_max, double *ent_mm)
@@ -784,11 +856,24 @@ __global__ void k_ent_min_max(int32_t n_ent, const int32_t *off, const int32_t *
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n_ent) { return; }
    double mn = INFINITY, mx = -INFINITY;
-   for (int k = off[i]; k < off[i + 1]; k++)
+   const int k1 = off[i + 1];
+   // batches of four: all index loads, then all value loads, are in flight together
+   for (int k = off[i]; k < k1; k += 4)
    {
-      mn = fmin(mn, xe_min[el[k]]); mx = fmax(mx, xe_max[el[k]]);
+      int id[4];
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { id[q] = (k + q < k1) ? el[k + q] : -1; }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+      {
+         a[q] = (id[q] >= 0) ? xe_min[id[q]] : INFINITY;
+         b[q] = (id[q] >= 0) ? xe_max[id[q]] : -INFINITY;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) { mn = a[q] < mn ? a[q] : mn; mx = b[q] > mx ? b[q] : mx; }
    }
-   ent_mm[2 * i] = mn; ent_mm[2 * i + 1] = mx;
+   *reinterpret_cast<double2 *>(ent_mm + 2 * (size_t)i) = make_double2(mn, mx);
 }
 
 // per-DOF gather (remhos_tools.cpp:468-494)
@@ -1706,6 +1791,11 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
 extern "C" int64_t rmh_ctx_ndofs(const rmh_ctx *c) { return c->N; }
 extern "C" int rmh_ctx_nd(const rmh_ctx *c) { return c->ND; }
 extern "C" int rmh_ctx_nq1d(const rmh_ctx *c) { return c->Q; }
+extern "C" int rmh_ctx_trust_state(rmh_ctx *c, int on)
+{
+   c->trust_state = (on != 0); c->xe_ptr = nullptr;
+   return 0;
+}
 extern "C" int rmh_ctx_path_flags(const rmh_ctx *c)
 { return (c->all_affine ? 1 : 0) | (c->frag ? 2 : 0) | (c->op_lin ? 4 : 0) | (c->op_const ? 8 : 0); }
 extern "C" int rmh_ctx_quad_points_1d(const rmh_ctx *c, double *q1d, double *w1d)
@@ -1764,9 +1854,7 @@ extern "C" int rmh_lo_mass_avg(rmh_ctx *c, double dt, const double *u, const dou
 extern "C" int rmh_elem_min_max(rmh_ctx *c, const double *u, double *xe_min, double *xe_max,
                                 void *stream)
 {
-   const int bs = 256;
-   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
-   k_elem_min_max<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, u, xe_min, xe_max);
+   launch_elem_min_max(c->ne, c->ND, u, xe_min, xe_max, (cudaStream_t)stream);
    LAUNCH_OK();
    return 0;
 }
@@ -1840,11 +1928,11 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       return 1;
    }
    if (out == y) { set_error("stage: output must not alias the stage input"); return 1; }
+   c->xe_ptr = nullptr;     // the context's element min/max are about to change owner
    const int bs = 256;
    if (!xe_valid)
    {
-      const int64_t nb = (c->ne * 32 + bs - 1) / bs;
-      k_elem_min_max<<<(unsigned)nb, bs, 0, s>>>(c->ne, c->ND, y, c->xe_min, c->xe_max);
+      launch_elem_min_max(c->ne, c->ND, y, c->xe_min, c->xe_max, s);
       LAUNCH_OK();
    }
    if (c->bounds_type == 0)
@@ -1952,6 +2040,11 @@ extern "C" int rmh_rk_step(rmh_ctx *c, int ode, int lo_type, double *t, double d
    // with overlap bounds the stage kernel leaves the element min/max of its output in the
    // context, so only the first stage needs the stand-alone min/max pass
    const bool chain = (c->bounds_type == 0);
+   // rmh_ctx_trust_state: the last stage of the previous step left the element min/max of this
+   // very vector in the context
+   const bool have_xe = chain && c->trust_state && c->xe_ptr == u;
+   const bool keep_xe = chain && c->trust_state;
+   c->xe_ptr = nullptr;
    if (ode == 1)          // ForwardEulerSolver
    {
       if (rmh_set_time(c, t0, stream)) { return 1; }
@@ -1961,18 +2054,20 @@ extern "C" int rmh_rk_step(rmh_ctx *c, int ode, int lo_type, double *t, double d
    else if (ode == 2)     // RK2Solver(1.0): u_new = 1/2 u + 1/2 (y + dt F(y)), y = u + dt F(u)
    {
       if (rmh_set_time(c, t0, stream)) { return 1; }
-      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, false, chain, s)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, have_xe, chain, s)) { return 1; }
       if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
-      if (stage_impl(c, lo_type, dt, 1, 0.5, 0.5, u, c->w1, u, chain, false, s)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.5, 0.5, u, c->w1, u, chain, keep_xe, s)) { return 1; }
+      if (keep_xe) { c->xe_ptr = u; }
    }
    else if (ode == 3)     // RK3SSPSolver
    {
       if (rmh_set_time(c, t0, stream)) { return 1; }
-      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, false, chain, s)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 0.0, 1.0, u, u, c->w1, have_xe, chain, s)) { return 1; }
       if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
       if (stage_impl(c, lo_type, dt, 1, 0.75, 0.25, u, c->w1, c->w2, chain, chain, s)) { return 1; }
       if (rmh_set_time(c, t0 + dt / 2, stream)) { return 1; }
-      if (stage_impl(c, lo_type, dt, 1, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, chain, false, s)) { return 1; }
+      if (stage_impl(c, lo_type, dt, 1, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, chain, keep_xe, s)) { return 1; }
+      if (keep_xe) { c->xe_ptr = u; }
    }
    else
    {
@@ -1989,6 +2084,7 @@ extern "C" int rmh_rk_step_host(rmh_ctx *c, int ode, int lo_type, double *t, dou
    // remhos.cpp:1680); H2D, one step, D2H.  u_host should be pinned for full PCIe bandwidth.
    const size_t bytes = (size_t)c->N * sizeof(double);
    CUDA_OK(cudaMemcpyAsync(c->w3, u_host, bytes, cudaMemcpyHostToDevice, 0));
+   c->xe_ptr = nullptr;     // fresh state from the host
    if (rmh_rk_step(c, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }
    CUDA_OK(cudaMemcpyAsync(u_host, c->w3, bytes, cudaMemcpyDeviceToHost, 0));
    CUDA_OK(cudaStreamSynchronize(0));
@@ -2504,9 +2600,8 @@ extern "C" int rmh_sync(rmh_ctx *c)
 // ---------------------------------------------------------------- halo (multi-GPU) entry points
 extern "C" int rmh_stage_minmax(rmh_ctx *c, const double *y, void *stream)
 {
-   const int bs = 256;
-   const int64_t nb = (c->ne * 32 + bs - 1) / bs;
-   k_elem_min_max<<<(unsigned)nb, bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, y, c->xe_min, c->xe_max);
+   c->xe_ptr = nullptr;
+   launch_elem_min_max(c->ne, c->ND, y, c->xe_min, c->xe_max, (cudaStream_t)stream);
    LAUNCH_OK();
    return 0;
 }
