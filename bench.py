@@ -186,6 +186,9 @@ def main():
         raise SystemExit('bench.py: no CUDA device (remhos_b200 has no CPU fallback)')
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     h = 2.0 / (3 * 2 ** a.rs)
@@ -218,6 +221,7 @@ def main():
                            bounds_type=0, dt=dt, device=local_rank)
         del mesh
         ctx = prob.ctx
+        prob.trust_state = True      # as in the single-GPU loop: the state is not touched between steps
 
         def step(t, u, stream):
             return prob.rk3_step(t, u, stream)
@@ -270,6 +274,7 @@ def main():
         if world == 1:
             return ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
         u.copy_(uh, non_blocking=True)
+        prob._xe_for = None          # fresh state from the host: recompute its element min/max
         t = step(t, u, stream)
         uh.copy_(u, non_blocking=True)
         torch.cuda.current_stream().synchronize()
