@@ -87,6 +87,9 @@ int rmh_halo_get(const rmh_halo *h, int64_t *owned, int64_t *ghost, int32_t *pee
 int rmh_mesh_dof_maps(const rmh_mesh *m, int order, int32_t *bdr_dofs, int32_t *nbr_dof,
                       int32_t *sub2ind, int32_t *lat, int32_t *n_ent, int32_t *nbr_elem);
 
+/* Mesh::GetElementSize(e): |det J(centre)|^(1/dim) per element (remhos.cpp:544, remhos_mono.cpp:55) */
+int rmh_mesh_elem_sizes(const rmh_mesh *m, double *h_out);
+
 /* Problem definitions and driver set-up (host): velocity_function (remhos.cpp:2001-2120),
  * u0_function (:2201-2355), inflow_function (:2363-2381); x is [n][dim]. */
 int rmh_velocity(int problem, int dim, int64_t n, const double *x, const double *bb_min,
@@ -224,6 +227,16 @@ int rmh_fct_clip_scale(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
  * (re)computed on the device whenever the mesh moves. */
 int rmh_subcell_setup(rmh_ctx *ctx, const double *xlat_host, const double *vel_host, void *stream);
 int rmh_lo_res_dist_subcell(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
+
+/* MonolithicSolver (remhos_mono.hpp:28-65; set up at remhos.cpp:997-1011).  mono_type 1 =
+ * MonoRDSolver, 2 = with the subcell scheme (needs rmh_subcell_setup), 0 removes it.  mass_lim as at
+ * remhos.cpp:999.  scale_host[ne] = vmax / (2 sqrt(dim) h_e / order) (MonoRDSolver constructor,
+ * remhos_mono.cpp:40-57).  While a monolithic solver is set, rmh_mult / rmh_mult_unlimited /
+ * rmh_ode_step evaluate it instead of HO/LO/FCT (remhos.cpp:1687) and rmh_limit_mult is a no-op.
+ * No smoothness indicator (-si) yet.  Serial only, as in the reference (remhos_mono.cpp:283). */
+int rmh_mono_setup(rmh_ctx *ctx, int mono_type, int mass_lim, const double *scale_host, void *stream);
+/* MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356) */
+int rmh_mono_rd(rmh_ctx *ctx, const double *u_dev, double *du_dev, void *stream);
 
 /* FluxBasedFCT::CalcFCTSolution, one FCT iteration as the driver fixes it (remhos_fct.cpp:155-181,
  * 295-446; remhos.cpp:1093).  Needs rmh_fa_setup; single-rank meshes only. */

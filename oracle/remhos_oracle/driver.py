@@ -59,6 +59,7 @@ class Options:                       # defaults: remhos.cpp:216-244
     ho_type: int = 3
     lo_type: int = 0
     fct_type: int = 0
+    mono_type: int = 0            # 1: MonoRDSolver, 2: with subcells (remhos.cpp:285-289)
     bounds_type: int = 0
     t_final: float = 4.0
     dt: float = 0.005
@@ -128,8 +129,32 @@ class Run:
         self.mass0 = float((self.disc.cur.ml * self.u).sum())
         self.masses0 = self.disc.cur.ml.copy()
         self.subcell_weights = None
+        self.mono_scale = None
+        if opt.mono_type:
+            self.mono_scale = self._mono_scale()
 
     # ---------------------------------------------------------------- stage operator
+    def _mono_scale(self):
+        """MonoRDSolver constructor (remhos_mono.cpp:40-57): scale_e = vmax / (2 sqrt(dim) h_e / p),
+        vmax over the Gauss-Legendre rule of order OrderW + 2p + 2 max(OrderGrad, 0) [MFEM-K: for
+        tensor elements OrderW = dim*mo - 1, OrderGrad = mo*(dim-1) + p - 1], h_e = GetElementSize."""
+        sp, m = self.space, self.mesh
+        dim, p, mo = sp.dim, sp.p, sp.g
+        q_ord = (dim * mo - 1) + 2 * p + 2 * max(mo * (dim - 1) + p - 1, 0)
+        n = q_ord // 2 + 1
+        xq, _ = np.polynomial.legendre.leggauss(n)
+        xq = 0.5 * (xq + 1.0)
+        L = fe.tensor_basis([fe.lagrange(sp.gll, xq)] * dim)
+        pts = np.einsum('qn,eni->eqi', L, m.X)
+        v = self.vel(pts)
+        vmax = np.sqrt((v * v).sum(axis=2)).max(axis=1)
+        c = np.array([0.5])
+        dLc = [fe.tensor_basis([fe.lagrange_deriv(sp.gll, c) if a == b else fe.lagrange(sp.gll, c)
+                                for b in range(dim)]) for a in range(dim)]
+        det, _ = sp.det_adj(sp.jacobians(m.X, dLc))
+        h = np.abs(det[:, 0]) ** (1.0 / dim)
+        return vmax / (2.0 * (np.sqrt(dim) * h / p))
+
     def mult(self, u, t, dt):
         """LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult
         (remhos_solvers.hpp:46-50; remhos.cpp:1596-1739, 1798-1916)."""
@@ -138,6 +163,10 @@ class Run:
         if self.exec_mode == 1:
             d.assemble(t)
         A = d.cur
+        if o.mono_type:                                        # remhos.cpp:1687
+            sw = self.get_subcell_weights() if o.mono_type == 2 else None
+            mass_lim = o.problem not in (6, 7)                 # remhos.cpp:999
+            return d.mono_rd(u, o.bounds_type, self.mono_scale, sw, mass_lim)
         if o.fct_type:
             du_ho = self.calc_ho(u)
             du_lo = self.calc_lo(u, du_ho, dt)

@@ -197,6 +197,111 @@ class Discretization:
                 + np.maximum(aux, 1.0 / (sfN - eps))[:, None] * nwN
         return (du + wP * rhoP[:, None] + wN * rhoN[:, None]) / A.ml
 
+    # ------------------------------------------------------------------ monolithic solver
+    def nonlin_flux_lumping(self, u, alpha):
+        """sum over the faces (ascending) of Assembly::NonlinFluxLumping (remhos_tools.cpp:915-973):
+        the lumped face term plus the alpha-weighted anti-diffusive correction, rescaled per face so
+        that the corrections of one face sum to zero whenever both signs occur.
+        alpha: [NE, nd] (or None for alpha = 1).  Returns the increment y[NE, nd]."""
+        A, sp = self.cur, self.sp
+        eps = 1e-15
+        y = np.zeros_like(u)
+        diff = self.face_diffs(u, self.inflow)                        # [NE, nf, nfd]
+        for f in range(sp.nf):
+            B = A.bdrInt[:, f]                                        # [NE, nfd, nfd]
+            d = diff[:, f]
+            lump = np.zeros_like(d)
+            corr = np.zeros_like(d)
+            for j in range(sp.nfd):                                   # the reference's summation order
+                lump = lump + B[:, :, j] * d
+                corr = corr + B[:, :, j] * (d[:, j][:, None] - d)
+            if alpha is not None:
+                corr = corr * alpha[:, sp.bd[:, f]]
+            sP = np.maximum(0.0, corr).sum(axis=1)
+            sN = np.minimum(0.0, corr).sum(axis=1)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                cP = np.minimum(0.0, corr) - np.maximum(0.0, corr) * (sN / sP)[:, None]
+                cN = np.maximum(0.0, corr) - np.minimum(0.0, corr) * (sP / sN)[:, None]
+            tot = sP + sN
+            corr = np.where((tot > eps)[:, None], cP, np.where((tot < -eps)[:, None], cN, corr))
+            np.add.at(y, (slice(None), sp.bd[:, f]), lump + corr)
+        return y
+
+    def mono_rd(self, u, bounds_type, scale, subcell_weights=None, mass_lim=True):
+        """MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356) without a smoothness indicator:
+        convex-limited residual distribution (beta = gamma = 10) with the element-local fixed-point
+        mass correction (at most 101 sweeps, |res|_2 <= 1e-8).  scale[NE]: remhos_mono.cpp:40-57."""
+        A, sp = self.cur, self.sp
+        eps, beta, gamma, tol = 1e-15, 10.0, 10.0, 1e-8
+        nd = sp.nd
+        xi_min, xi_max = self.bounds(u, bounds_type)
+        xe_min = u.min(axis=1); xe_max = u.max(axis=1)
+        z = np.einsum('eij,ej->ei', A.K, u)
+        d = z.copy()
+        lo_gap = np.minimum(xi_max - u, u - xi_min)
+        alpha = np.minimum(1.0, beta * lo_gap / (np.maximum(xi_max - u, u - xi_min) + eps))
+        du = alpha * z
+        z = z - alpha * z
+        du = du + self.nonlin_flux_lumping(u, alpha)
+        d = d + self.nonlin_flux_lumping(u, None)
+        xsum = u.sum(axis=1)
+        rhoP = np.maximum(0.0, z).sum(axis=1)
+        rhoN = np.minimum(0.0, z).sum(axis=1)
+        sumWP = nd * xe_max - xsum + eps
+        sumWN = nd * xe_min - xsum - eps
+        wP = (xe_max[:, None] - u) / sumWP[:, None]
+        wN = (xe_min[:, None] - u) / sumWN[:, None]
+        if subcell_weights is not None:
+            s2i = dg.sub2ind(sp.p, sp.dim)
+            us = u[:, s2i]
+            fluct = (subcell_weights * us).sum(axis=2)
+            smax = us.max(axis=2); smin = us.min(axis=2); ssum = us.sum(axis=2)
+            nc = s2i.shape[1]
+            swP = nc * smax - ssum + eps
+            swN = nc * smin - ssum - eps
+            fP = np.maximum(0.0, fluct); fN = np.minimum(0.0, fluct)
+            sfP = fP.sum(axis=1); sfN = fN.sum(axis=1)
+            nwP = np.zeros_like(u); nwN = np.zeros_like(u)
+            cP = fP[:, :, None] * ((smax[:, :, None] - us) / swP[:, :, None])
+            cN = fN[:, :, None] * ((smin[:, :, None] - us) / swN[:, :, None])
+            for m in range(s2i.shape[0]):
+                for c in range(nc):
+                    nwP[:, s2i[m, c]] += cP[:, m, c]
+                    nwN[:, s2i[m, c]] += cN[:, m, c]
+            aux = gamma / (rhoP + eps)
+            wP = wP * (1.0 - np.minimum(aux * sfP, 1.0))[:, None] \
+                + np.minimum(aux, 1.0 / (sfP + eps))[:, None] * nwP
+            aux = gamma / (rhoN - eps)
+            wN = wN * (1.0 - np.minimum(aux * sfN, 1.0))[:, None] \
+                + np.maximum(aux, 1.0 / (sfN - eps))[:, None] * nwN
+        du = du + wP * rhoP[:, None] + wN * rhoN[:, None]
+        # time derivative and mass matrix: per-element fixed point (eq. 27-29)
+        m_it = np.zeros_like(u)
+        if mass_lim:
+            active = np.ones(u.shape[0], dtype=bool)
+            msum = A.M.sum(axis=2)
+            for it in range(101):
+                uDot = (du + m_it) / A.ml
+                uDotMin = uDot.min(axis=1)[:, None]; uDotMax = uDot.max(axis=1)[:, None]
+                m_new = msum * uDot - np.einsum('eij,ej->ei', A.M, uDot)   # sum_j M_ij (uDot_i - uDot_j)
+                diff = d - du
+                m_new = m_new + np.minimum(1.0, np.abs(m_new) / (np.abs(diff) + eps)) * diff
+                al = np.minimum(1.0, beta * scale[:, None] * lo_gap /
+                                (np.maximum(uDotMax - uDot, uDot - uDotMin) + eps))
+                m_new = m_new * al
+                MP = np.maximum(0.0, m_new).sum(axis=1); MN = np.minimum(0.0, m_new).sum(axis=1)
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    cP = np.minimum(0.0, m_new) - np.maximum(0.0, m_new) * (MN / MP)[:, None]
+                    cN = np.maximum(0.0, m_new) - np.minimum(0.0, m_new) * (MP / MN)[:, None]
+                tot = MP + MN
+                m_new = np.where((tot > eps)[:, None], cP, np.where((tot < -eps)[:, None], cN, m_new))
+                res = m_new + du - A.ml * uDot
+                m_it = np.where(active[:, None], m_new, m_it)
+                active = active & ~(np.sqrt((res * res).sum(axis=1)) <= tol)
+                if not active.any():
+                    break
+        return (du + m_it) / A.ml
+
     # ------------------------------------------------------------------ bounds
     def bounds(self, u, bounds_type):
         sp, topo = self.sp, self.topo

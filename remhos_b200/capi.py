@@ -276,6 +276,14 @@ class Context:
     def lo_res_dist_subcell(self, u, du_lo, s=0):
         check(lib().rmh_lo_res_dist_subcell(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
 
+    def mono_setup(self, mono_type, mass_lim, scale, s=0):
+        scale = np.ascontiguousarray(scale, dtype=np.float64) if scale is not None else None
+        check(lib().rmh_mono_setup(self.h, int(mono_type), int(bool(mass_lim)), _ptr(scale),
+                                   C.c_void_p(s)))
+
+    def mono_rd(self, u, du, s=0):
+        check(lib().rmh_mono_rd(self.h, _dp(u), _dp(du), C.c_void_p(s)))
+
     def fa_get(self, which):
         nd, ne = self.nd, self.ne
         dim = self.dim

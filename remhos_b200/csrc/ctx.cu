@@ -82,6 +82,9 @@ struct rmh_ctx
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    bool op_lin = false;       // ... and adj(J) v is linear over every element: opc is valid
    bool op_const = false;     // ... and constant over every element: opa is valid
+   int mono_type = 0;         // rmh_mono_setup: 1 MonoRDSolver, 2 with subcells; 0 none
+   int mono_mass_lim = 1;
+   double *mono_scale = nullptr;   // [ne] (remhos_mono.cpp:40-57)
    bool trust_state = false;  // rmh_ctx_trust_state: the caller leaves the state alone between steps
    const double *xe_ptr = nullptr;   // state vector whose element min/max the context currently holds
    double *opc = nullptr;     // [ne][12] (k_op_linear)
@@ -2255,6 +2258,56 @@ extern "C" int rmh_lo_res_dist_subcell(rmh_ctx *c, const double *u, double *du_l
    return 0;
 }
 
+// MonolithicSolver set-up (remhos.cpp:997-1011): the operator owns at most one monolithic solver,
+// which then takes precedence over HO/LO/FCT in rmh_mult / rmh_mult_unlimited (remhos.cpp:1687).
+extern "C" int rmh_mono_setup(rmh_ctx *c, int mono_type, int mass_lim, const double *scale_host,
+                              void *stream)
+{
+   if (mono_type < 0 || mono_type > 2) { set_error("rmh_mono_setup: mono type must be 0, 1 or 2"); return 1; }
+   if (mono_type == 0) { c->mono_type = 0; return 0; }
+   if (!scale_host) { set_error("rmh_mono_setup: scale (one value per element) is required"); return 1; }
+   if (mono_type == 2 && !c->sub_on)
+   { set_error("rmh_mono_setup: the subcell variant needs rmh_subcell_setup first"); return 1; }
+   if (c->ne_ghost > 0)
+   { set_error("rmh_mono_setup: decomposed meshes are not supported (serial only in the reference too, remhos_mono.cpp:283)"); return 1; }
+   if (c->ND > 256) { set_error("rmh_mono_setup: at most 256 DOFs per element"); return 1; }
+   if (rmh_fa_setup(c, stream)) { return 1; }
+   if (!c->mono_scale) { if (dev_alloc(c, &c->mono_scale, (size_t)c->ne)) { return 1; } }
+   CUDA_OK(cudaMemcpy(c->mono_scale, scale_host, (size_t)c->ne * sizeof(double), cudaMemcpyHostToDevice));
+   c->mono_type = mono_type; c->mono_mass_lim = mass_lim ? 1 : 0;
+   return 0;
+}
+
+// MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356)
+extern "C" int rmh_mono_rd(rmh_ctx *c, const double *u, double *du, void *stream)
+{
+   if (!c->mono_type) { set_error("rmh_mono_rd: call rmh_mono_setup first"); return 1; }
+   if (du == u) { set_error("rmh_mono_rd: output must not alias the input"); return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   if (work_vec(c, &c->wk[0]) || work_vec(c, &c->wk[5]) || work_vec(c, &c->wk[6])) { return 1; }
+   double *z = c->wk[0], *xmn = c->wk[5], *xmx = c->wk[6];
+   if (dispatch_ho(c, ho_args(c, u, z, 1 | 4), s)) { return 1; }
+   c->xe_ptr = nullptr;
+   if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
+   if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
+   int ns = 1;
+   for (int a = 0; a < c->dim; a++) { ns *= c->p; }
+   const int wpb = 2;
+   const size_t shb = (size_t)wpb * (8 * c->ND + 3 * c->NFD + ns * 6) * sizeof(double);
+   static bool attr = false;
+   if (!attr)
+   {
+      CUDA_OK(cudaFuncSetAttribute(k_mono_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+   }
+   if (shb > 96 * 1024) { set_error("rmh_mono_rd: element too large for the shared-memory scratch"); return 1; }
+   k_mono_rd<<<(unsigned)((c->ne + wpb - 1) / wpb), wpb * 32, shb, s>>>(
+      fa_args(c), c->p, c->mono_type == 2 ? 1 : 0, c->mono_mass_lim, c->sub_w, c->mono_scale, u, z, xmn,
+      xmx, du);
+   LAUNCH_OK();
+   return 0;
+}
+
 extern "C" int rmh_fct_flux_based(rmh_ctx *c, double dt, const double *u, const double *m,
                                   const double *du_ho, const double *du_lo, const double *xi_min,
                                   const double *xi_max, double *du, void *stream)
@@ -2296,6 +2349,11 @@ static int check_combo(int ho_type, int lo_type, int fct_type)
 extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t,
                                   double dt, const double *u, double *k, void *stream)
 {
+   if (c->mono_type)      // the monolithic solver takes precedence (remhos.cpp:1687)
+   {
+      if (rmh_set_time(c, t, stream)) { return 1; }
+      return rmh_mono_rd(c, u, k, stream);
+   }
    if (check_combo(ho_type, lo_type, fct_type)) { return 1; }
    if (k == u) { set_error("rmh_mult_unlimited: output must not alias the input"); return 1; }
    if (rmh_set_time(c, t, stream)) { return 1; }
@@ -2320,7 +2378,7 @@ extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_
 extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u,
                               double *k, void *stream)
 {
-   if (!fct_type) { return 0; }
+   if (!fct_type || c->mono_type) { return 0; }            // remhos.cpp:1803: no FCT solver, nothing to limit
    if (check_combo(3, lo_type, fct_type)) { return 1; }
    if (k == u) { set_error("rmh_limit_mult: the rate must not alias the state"); return 1; }
    for (int i = 3; i < 7; i++) { if (work_vec(c, &c->wk[i])) { return 1; } }
@@ -2343,6 +2401,7 @@ extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, 
 extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t, double dt,
                         const double *u, double *k, void *stream)
 {
+   if (c->mono_type) { return rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t, dt, u, k, stream); }
    if (ho_type == 3 && lo_type == 5 && fct_type == 2)
    {
       if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
@@ -2383,7 +2442,7 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
                             double dt, double *u, void *stream)
 {
    cudaStream_t s = (cudaStream_t)stream;
-   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 && ode <= 3)
+   if (!c->mono_type && ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 && ode <= 3)
    { return rmh_rk_step(c, ode, lo_type, t, dt, u, stream); }
    const double t0 = *t;
    const size_t bytes = (size_t)c->N * sizeof(double);

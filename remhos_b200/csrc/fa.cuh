@@ -484,6 +484,197 @@ __global__ void k_lo_rd_sub(FaArgs A, int p, const double *SW, const double *u, 
    }
 }
 
+// ---- MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356) without a smoothness indicator.
+// One warp per element, everything element-local in shared memory:
+//   alpha_j from the bound gaps (beta = 10), volume split du = alpha z, z <- (1 - alpha) z;
+//   faces in ascending order: Assembly::NonlinFluxLumping (remhos_tools.cpp:915-973) into du (alpha)
+//   and into d (alpha = 1);  residual distribution of the remaining z (subcell variant: gamma = 10);
+//   fixed-point mass correction (eq. 27-29; <= 101 sweeps, |res|_2 <= 1e-8) with the dense element
+//   mass block.  z = K u (volume-only) and the per-DOF bounds are inputs.
+__global__ void k_mono_rd(FaArgs A, int p, int subcell, int mass_lim, const double *SW,
+                          const double *scale, const double *u, const double *z,
+                          const double *xi_min, const double *xi_max, double *du_out)
+{
+   extern __shared__ double sh[];
+   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+   const int64_t e = (int64_t)blockIdx.x * wpb + wib;
+   int ns = 1, nc = 1;
+   for (int a = 0; a < A.dim; a++) { ns *= p; nc *= 2; }
+   const int ND = A.ND, NFD = A.NFD, NF = A.NF, D1 = A.D1;
+   const int per = 8 * ND + 3 * NFD + ns * 6;
+   double *U = sh + (size_t)wib * per, *DU = U + ND, *D = DU + ND, *ZR = D + ND, *AL = ZR + ND,
+          *MI = AL + ND, *UD = MI + ND, *GAP = UD + ND, *XD = GAP + ND, *C1 = XD + NFD, *C2 = C1 + NFD,
+          *sub = C2 + NFD;
+   if (e >= A.ne) { return; }
+   constexpr double eps = 1.0e-15, beta = 10.0, gamma = 10.0, tol = 1.0e-8;
+   // ---- bound gaps, alpha, volume split (remhos_mono.cpp:123-160)
+   double xmax = -INFINITY, xmin = INFINITY, xsum = 0.0;
+   for (int j = lane; j < ND; j += 32)
+   {
+      const double ui = u[e * ND + j], zz = z[e * ND + j];
+      const double up = xi_max[e * ND + j] - ui, dn = ui - xi_min[e * ND + j];
+      const double gap = fmin(up, dn);
+      const double al = fmin(1.0, beta * gap / (fmax(up, dn) + eps));
+      U[j] = ui; GAP[j] = gap; AL[j] = al; MI[j] = 0.0;
+      DU[j] = al * zz; ZR[j] = zz - al * zz; D[j] = zz;
+      xmax = fmax(xmax, ui); xmin = fmin(xmin, ui); xsum += ui;
+   }
+   xmax = warp_max(xmax); xmin = warp_min(xmin); xsum = warp_sum(xsum);
+   __syncwarp();
+   // ---- face contributions, faces in ascending order (remhos_mono.cpp:163-167)
+   for (int f = 0; f < NF; f++)
+   {
+      for (int a = lane; a < NFD; a += 32)
+      {
+         const int ja = face_dof_rt(A.dim, D1, f, a);
+         const double infl = A.inflow ? A.inflow[e * ND + ja] : 0.0;
+         XD[a] = nbr_value(A, u, e, f, a, infl) - U[ja];
+      }
+      __syncwarp();
+      double sP = 0.0, sN = 0.0, tP = 0.0, tN = 0.0;
+      for (int a = lane; a < NFD; a += 32)
+      {
+         const int ja = face_dof_rt(A.dim, D1, f, a);
+         const double *BIe = A.BI + (((size_t)e * NF + f) * NFD + a) * NFD;
+         double y1 = DU[ja], y2 = D[ja], corr = 0.0;
+         const double xa = XD[a];
+         for (int b = 0; b < NFD; b++)
+         {
+            y1 += BIe[b] * xa; y2 += BIe[b] * xa;
+            corr += BIe[b] * (XD[b] - xa);
+         }
+         DU[ja] = y1; D[ja] = y2;
+         const double c1 = corr * AL[ja];
+         C1[a] = c1; C2[a] = corr;
+         sP += fmax(0.0, c1); sN += fmin(0.0, c1);
+         tP += fmax(0.0, corr); tN += fmin(0.0, corr);
+      }
+      sP = warp_sum(sP); sN = warp_sum(sN); tP = warp_sum(tP); tN = warp_sum(tN);
+      for (int a = lane; a < NFD; a += 32)
+      {
+         const int ja = face_dof_rt(A.dim, D1, f, a);
+         double c1 = C1[a], c2 = C2[a];
+         if (sP + sN > eps) { c1 = fmin(0.0, c1) - fmax(0.0, c1) * sN / sP; }
+         else if (sP + sN < -eps) { c1 = fmax(0.0, c1) - fmin(0.0, c1) * sP / sN; }
+         if (tP + tN > eps) { c2 = fmin(0.0, c2) - fmax(0.0, c2) * tN / tP; }
+         else if (tP + tN < -eps) { c2 = fmax(0.0, c2) - fmin(0.0, c2) * tP / tN; }
+         DU[ja] += c1; D[ja] += c2;
+      }
+      __syncwarp();
+   }
+   // ---- element contributions (remhos_mono.cpp:169-262)
+   double rhoP = 0.0, rhoN = 0.0;
+   for (int j = lane; j < ND; j += 32) { rhoP += fmax(0.0, ZR[j]); rhoN += fmin(0.0, ZR[j]); }
+   rhoP = warp_sum(rhoP); rhoN = warp_sum(rhoN);
+   double sfP = 0.0, sfN = 0.0;
+   if (subcell)
+   {
+      for (int m = lane; m < ns; m += 32)
+      {
+         int sc[3] = {0, 0, 0}, r = m;
+         for (int a = 0; a < A.dim; a++) { sc[a] = r % p; r /= p; }
+         double fl = 0.0, smax = -INFINITY, smin = INFINITY, ssum = 0.0;
+         for (int c = 0; c < nc; c++)
+         {
+            int loc = 0, mul = 1;
+            for (int a = 0; a < A.dim; a++) { loc += (sc[a] + ((c >> a) & 1)) * mul; mul *= D1; }
+            const double v = U[loc];
+            fl += SW[((size_t)e * ns + m) * nc + c] * v;
+            smax = fmax(smax, v); smin = fmin(smin, v); ssum += v;
+         }
+         const double fP = fmax(0.0, fl), fN = fmin(0.0, fl);
+         sub[m * 6 + 0] = fP; sub[m * 6 + 1] = fN; sub[m * 6 + 2] = smax; sub[m * 6 + 3] = smin;
+         sub[m * 6 + 4] = nc * smax - ssum + eps; sub[m * 6 + 5] = nc * smin - ssum - eps;
+         sfP += fP; sfN += fN;
+      }
+      sfP = warp_sum(sfP); sfN = warp_sum(sfN);
+      __syncwarp();
+   }
+   const double sumWP = ND * xmax - xsum + eps, sumWN = ND * xmin - xsum - eps;
+   for (int j = lane; j < ND; j += 32)
+   {
+      const double ui = U[j];
+      double wP = (xmax - ui) / sumWP, wN = (xmin - ui) / sumWN;
+      if (subcell)
+      {
+         int l[3];
+         dof_lattice(A.dim, D1, j, l);
+         double nwP = 0.0, nwN = 0.0;
+         for (int k = 0; k < nc; k++)
+         {
+            int m = 0, mul = 1;
+            bool ok = true;
+            for (int a = 0; a < A.dim; a++)
+            {
+               const int off = ((k >> a) & 1) ? 0 : -1;
+               const int s_ = l[a] + off;
+               if (s_ < 0 || s_ >= p) { ok = false; }
+               m += s_ * mul; mul *= p;
+            }
+            if (!ok) { continue; }
+            nwP += sub[m * 6 + 0] * ((sub[m * 6 + 2] - ui) / sub[m * 6 + 4]);
+            nwN += sub[m * 6 + 1] * ((sub[m * 6 + 3] - ui) / sub[m * 6 + 5]);
+         }
+         double aux = gamma / (rhoP + eps);
+         wP *= 1.0 - fmin(aux * sfP, 1.0);
+         wP += fmin(aux, 1.0 / (sfP + eps)) * nwP;
+         aux = gamma / (rhoN - eps);
+         wN *= 1.0 - fmin(aux * sfN, 1.0);
+         wN += fmax(aux, 1.0 / (sfN - eps)) * nwN;
+      }
+      DU[j] += wP * rhoP + wN * rhoN;
+   }
+   __syncwarp();
+   // ---- time derivative and mass matrix: element-local fixed point (remhos_mono.cpp:264-346)
+   if (mass_lim)
+   {
+      const double sck = scale[e];
+      const double *Me = A.M + (size_t)e * ND * ND;
+      for (int it = 0; it <= 100; it++)
+      {
+         double udmin = INFINITY, udmax = -INFINITY;
+         for (int j = lane; j < ND; j += 32)
+         {
+            const double v = (DU[j] + MI[j]) / A.ml[e * ND + j];
+            UD[j] = v;
+            udmin = fmin(udmin, v); udmax = fmax(udmax, v);
+         }
+         udmin = warp_min(udmin); udmax = warp_max(udmax);
+         __syncwarp();
+         double mi[8];
+         double MP = 0.0, MN = 0.0;
+         int q = 0;
+         for (int i = lane; i < ND; i += 32, q++)
+         {
+            const double udi = UD[i];
+            double s = 0.0;
+            for (int j = ND - 1; j >= 0; j--) { s += Me[(size_t)i * ND + j] * (udi - UD[j]); }
+            const double diff = D[i] - DU[i];
+            s += fmin(1.0, fabs(s) / (fabs(diff) + eps)) * diff;
+            s *= fmin(1.0, beta * sck * GAP[i] / (fmax(udmax - udi, udi - udmin) + eps));
+            mi[q] = s;
+            MP += fmax(0.0, s); MN += fmin(0.0, s);
+         }
+         MP = warp_sum(MP); MN = warp_sum(MN);
+         double res2 = 0.0;
+         q = 0;
+         for (int i = lane; i < ND; i += 32, q++)
+         {
+            double s = mi[q];
+            if (MP + MN > eps) { s = fmin(0.0, s) - fmax(0.0, s) * MN / MP; }
+            else if (MP + MN < -eps) { s = fmax(0.0, s) - fmin(0.0, s) * MP / MN; }
+            const double r = s + DU[i] - A.ml[e * ND + i] * UD[i];
+            res2 += r * r;
+            MI[i] = s;
+         }
+         res2 = warp_sum(res2);
+         __syncwarp();
+         if (sqrt(res2) <= tol) { break; }
+      }
+   }
+   for (int j = lane; j < ND; j += 32) { du_out[e * ND + j] = (DU[j] + MI[j]) / A.ml[e * ND + j]; }
+}
+
 // ---- FluxBasedFCT (Zalesak), gather form: every DOF visits all its couplings of K_HO
 // (in-element via KH / M, across faces via BI of both sides); each flux is evaluated from both
 // ends with the same operands in the same order, so f_ji = -f_ij bit for bit.

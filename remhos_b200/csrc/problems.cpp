@@ -308,6 +308,47 @@ extern "C" int rmh_mesh_eval(const rmh_mesh *m, int npts, const double *pts1d, i
 }
 
 // CFL time step estimate (remhos.cpp:538-553): min_e 0.25 * |det J(center)|^(1/dim) / |v(center)|
+// Mesh::GetElementSize(e) (type 0): |det J at the element centre|^(1/dim), as used by the CFL
+// estimate (remhos.cpp:544) and by MonoRDSolver's scale (remhos_mono.cpp:55)
+extern "C" int rmh_mesh_elem_sizes(const rmh_mesh *m, double *h_out)
+{
+   const int dim = rmh_mesh_dim(m), g = rmh_mesh_geom_order(m), n1 = g + 1;
+   const int64_t ne = rmh_mesh_ne(m);
+   const double *X = rmh_mesh_nodes(m);
+   const std::vector<double> gll = gauss_lobatto_01(n1);
+   const std::vector<double> c = {0.5};
+   const std::vector<double> L = lagrange(gll, c), dL = lagrange_deriv(gll, c);
+   int nn = 1;
+   for (int a = 0; a < dim; a++) { nn *= n1; }
+#pragma omp parallel for
+   for (int64_t e = 0; e < ne; e++)
+   {
+      const double *Xe = X + (size_t)e * nn * dim;
+      double J[3][3] = {{0}};
+      for (int n = 0; n < nn; n++)
+      {
+         int idx[3] = {0, 0, 0}, mn = n;
+         for (int a = 0; a < dim; a++) { idx[a] = mn % n1; mn /= n1; }
+         for (int j = 0; j < dim; j++)
+         {
+            double d = 1.0;
+            for (int a = 0; a < dim; a++) { d *= (a == j) ? dL[idx[a]] : L[idx[a]]; }
+            for (int i = 0; i < dim; i++) { J[i][j] += d * Xe[n * dim + i]; }
+         }
+      }
+      double det;
+      if (dim == 2) { det = J[0][0] * J[1][1] - J[0][1] * J[1][0]; }
+      else
+      {
+         det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+               J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+               J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+      }
+      h_out[e] = pow(fabs(det), 1.0 / dim);
+   }
+   return 0;
+}
+
 extern "C" int rmh_cfl_dt(const rmh_mesh *m, int problem, const double *bmin, const double *bmax,
                           double *dt_out)
 {

@@ -208,6 +208,11 @@ void ResidualDistribution::CalcLOSolution(const Vector &u, Vector &du) const
 ResidualDistributionSubcell::ResidualDistributionSubcell(ParFiniteElementSpace &space)
    : LOSolver(space)
 {
+   SetupSubcells(space);
+}
+void SetupSubcells(ParFiniteElementSpace &space)
+{
+   if (space.subcells_ready) { return; }
    Verify(space.order > 1, "Subcell schemes require FE order > 1.");     // remhos.cpp:613-616
    const int dim = space.dim, p = space.order, nf = 2 * dim;
    int nd = 1, ns = 1, nc = 1, nfd = 1;
@@ -254,6 +259,48 @@ ResidualDistributionSubcell::ResidualDistributionSubcell(ParFiniteElementSpace &
                          space.bb_max.data(), vel.data()));
    }
    Check(rmh_subcell_setup(space.ctx, space.xlat.data(), vel.data(), nullptr));
+   space.subcells_ready = true;
+}
+
+// ---- monolithic solver (remhos_mono.cpp)
+MonoRDSolver::MonoRDSolver(ParFiniteElementSpace &space, bool subcell, bool timedep, bool masslim)
+   : MonolithicSolver(space), subcell_scheme(subcell), time_dep(timedep), mass_lim(masslim)
+{
+   // scale(e) = vmax / (2 sqrt(dim) h_e / order), vmax over the element quadrature rule of order
+   // OrderW + 2 p + 2 max(OrderGrad, 0) (remhos_mono.cpp:40-57); tensor elements: OrderW = dim mo - 1,
+   // OrderGrad = mo (dim - 1) + p - 1, Gauss-Legendre with order/2 + 1 points per direction
+   const int dim = space.dim, p = space.order, mo = space.mesh_order;
+   const int64_t ne = space.GetNE();
+   const int q_ord = (dim * mo - 1) + 2 * p + 2 * std::max(mo * (dim - 1) + p - 1, 0);
+   const int n = q_ord / 2 + 1;
+   std::vector<double> xq(n), wq(n);
+   Check(rmh_gauss_legendre_01(n, xq.data(), wq.data()));
+   int nq = 1;
+   for (int a = 0; a < dim; a++) { nq *= n; }
+   std::vector<double> pts((size_t)ne * nq * dim), vel(pts.size()), h((size_t)ne);
+   Check(rmh_mesh_eval(space.mesh, n, xq.data(), -1, pts.data()));
+   Check(rmh_velocity(space.problem, dim, ne * nq, pts.data(), space.bb_min.data(), space.bb_max.data(),
+                      vel.data()));
+   Check(rmh_mesh_elem_sizes(space.mesh, h.data()));
+   scale.resize((size_t)ne);
+   for (int64_t e = 0; e < ne; e++)
+   {
+      double vmax = 0.0;
+      for (int q = 0; q < nq; q++)
+      {
+         double v2 = 0.0;
+         for (int c = 0; c < dim; c++) { const double v = vel[((size_t)e * nq + q) * dim + c]; v2 += v * v; }
+         vmax = std::max(vmax, std::sqrt(v2));
+      }
+      scale[e] = vmax / (2. * (std::sqrt((double)dim) * h[e] / p));
+   }
+   if (subcell_scheme) { SetupSubcells(space); }
+   Check(rmh_mono_setup(space.ctx, subcell_scheme ? 2 : 1, mass_lim ? 1 : 0, scale.data(), nullptr));
+}
+MonoRDSolver::~MonoRDSolver() { rmh_mono_setup(pfes.ctx, 0, 0, nullptr, nullptr); }
+void MonoRDSolver::CalcSolution(const Vector &u, Vector &du) const
+{
+   Check(rmh_mono_rd(pfes.ctx, u.Read(), du.Write(), nullptr));
 }
 void ResidualDistributionSubcell::CalcLOSolution(const Vector &u, Vector &du) const
 {
@@ -329,8 +376,9 @@ void DofInfo::ComputeBounds(const double *el_min, const double *el_max, Vector &
 
 // ------------------------------------------------------------------------------------ operator
 AdvectionOperator::AdvectionOperator(ParFiniteElementSpace &space, Vector &lumpedM_, DofInfo &dofs_,
-                                     HOSolver *hos, LOSolver *los, FCTSolver *fct)
-   : pfes(space), lumpedM(lumpedM_), dofs(dofs_), ho_solver(hos), lo_solver(los), fct_solver(fct)
+                                     HOSolver *hos, LOSolver *los, FCTSolver *fct, MonolithicSolver *mos)
+   : pfes(space), lumpedM(lumpedM_), dofs(dofs_), ho_solver(hos), lo_solver(los), fct_solver(fct),
+     mono_solver(mos)
 {
    if (ho_solver) { ho_solver->timer = &timer; }
    if (lo_solver) { lo_solver->timer = &timer; }
@@ -348,7 +396,8 @@ void AdvectionOperator::MultUnlimited(const Vector &x, Vector &y) const  // remh
    // remap: move the mesh to x0 + t v and re-assemble (:1598-1677)
    Check(rmh_set_time(pfes.ctx, t, nullptr));
    if (pfes.exec_mode == 1) { Check(rmh_lumped_mass(pfes.ctx, lumpedM.Write(), nullptr)); }
-   if (fct_solver)
+   if (mono_solver) { mono_solver->CalcSolution(x, y); }                 // remhos.cpp:1687
+   else if (fct_solver)
    {
       Verify(ho_solver && lo_solver, "FCT requires HO and LO solvers.");
       ho_solver->CalcHOSolution(x, y);
@@ -359,7 +408,7 @@ void AdvectionOperator::MultUnlimited(const Vector &x, Vector &y) const  // remh
 }
 void AdvectionOperator::LimitMult(const Vector &x, Vector &y) const     // remhos.cpp:1798-1916
 {
-   if (!fct_solver) { return; }
+   if (!fct_solver || mono_solver) { return; }
    Verify(ho_solver && lo_solver, "FCT requires HO and LO solvers.");
    Vector du_HO(y), du_LO(pfes);
    auto mba = dynamic_cast<MassBasedAvg *>(lo_solver);
@@ -475,7 +524,7 @@ void usage(std::ostream &os)
 {
    os << "Usage: remhos [options]\n"
          "  -m <mesh>  -dim <d>  -epm <n>  -p <problem>  -rs <n>  -rp <n>  -o <order>  -mo <order>\n"
-         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|1|2|3>  -lo <0..5>  -fct <0|1|2>  -mono <0>\n"
+         "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|1|2|3>  -lo <0..5>  -fct <0|1|2>  -mono <0|1|2>\n"
          "  -bt <0|1>  -pa/-no-pa  -full/-no-full  -d <device>  -gam/-no-gam  -si <0>  -tf <t>\n"
          "  -dtc <0>  -dt <dt>  -ms <steps>  -vis/-no-vis  -save/-no-save  -visit/-no-visit\n"
          "  -vb/-no-vb  -ps/-no-ps  -vs <steps>  -pool <GB>\n";
@@ -554,7 +603,8 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       std::cout << "Unknown ODE solver type: " << o.ode << '\n';       // remhos.cpp:499-500
       return 3;
    }
-   Verify(o.mono == 0, "monolithic solvers (-mono) are not part of this build");
+   Verify(o.mono >= 0 && o.mono <= 2, "monolithic solver type must be 0, 1 (ResDistMono) or 2 (ResDistMonoSubcell)");
+   if (o.mono == 2) { Verify(o.order > 1, "Subcell schemes require FE order > 1."); }
    // -ho 2 (CGHOSolver, remhos_ho.cpp:30-70) solves the block-diagonal system M du = K u by PCG to
    // a relative tolerance of 1e-12: on this path it is served by the exact element-local inverse
    Verify(o.ho >= 0 && o.ho <= 3, "HO solver type must be 0 .. 3");
@@ -570,7 +620,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    Verify(o.order >= 1, "order 0 disables limiting; not part of this build");
    if (o.fct) { Verify(o.ho && o.lo, "FCT requires HO and LO solvers."); }     // :1690
    if (o.lo == 5) { Verify(o.ho != 0, "Mass-Based LO solver requires a choice of a HO solver."); }   // :991
-   Verify(o.ho || o.lo, "No solver was chosen.");
+   Verify(o.ho || o.lo || o.mono, "No solver was chosen.");
    // ---- mesh (remhos.cpp:448-463)
    rmh_mesh *mesh = nullptr;
    if (o.mesh_file == "default")
@@ -610,7 +660,11 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       FCTSolver *fct_solver = nullptr;
       if (o.fct == 1) { fct_solver = new FluxBasedFCT(pfes, dt); }
       else if (o.fct == 2) { fct_solver = new ClipScaleSolver(pfes, dt); }
-      AdvectionOperator adv(pfes, lumpedM, dofs, ho_solver, lo_solver, fct_solver);
+      // monolithic solver (remhos.cpp:997-1011)
+      MonolithicSolver *mono_solver = nullptr;
+      const bool mass_lim = (o.problem != 6 && o.problem != 7);
+      if (o.mono) { mono_solver = new MonoRDSolver(pfes, o.mono == 2, pfes.exec_mode == 1, mass_lim); }
+      AdvectionOperator adv(pfes, lumpedM, dofs, ho_solver, lo_solver, fct_solver, mono_solver);
       adv.verify_bounds = o.vb;
       double mass0_u = 0.0, u_min = 0.0, u_max = 0.0;
       Check(rmh_reduce(pfes.ctx, 0, u.Read(), lumpedM.Read(), &mass0_u, nullptr));   // :1073-1076
@@ -680,7 +734,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
             std::fclose(fp);
          }
       }
-      delete fct_solver; delete lo_solver; delete ho_solver;            // remhos.cpp:1484-1489
+      delete mono_solver; delete fct_solver; delete lo_solver; delete ho_solver;   // remhos.cpp:1484-1489
    }
    rmh_mesh_free(mesh);
    return rc;

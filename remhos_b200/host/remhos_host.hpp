@@ -73,6 +73,7 @@ public:
    std::vector<int32_t> bdr_dofs, nbr_elem;   // BdrDofs [nfd][nf]; face neighbours [ne][nf]
    double dt_cfl = 0.0;
    double t_final = 0.0;
+   bool subcells_ready = false;
    ParFiniteElementSpace(rmh_mesh *m, int problem, int order, int mesh_order, int bounds_type,
                          double &dt, double &t_final, int device);
    ~ParFiniteElementSpace();
@@ -156,6 +157,9 @@ public:
    int Type() const override { return 4; }
 };
 
+// the subcell mesh data of remhos.cpp:797-868, handed to the device once per space
+void SetupSubcells(ParFiniteElementSpace &space);
+
 class MassBasedAvg : public LOSolver
 {
    HOSolver &ho_solver;
@@ -203,6 +207,30 @@ public:
    int Type() const override { return 2; }
 };
 
+// remhos_mono.hpp:28-39
+class MonolithicSolver
+{
+protected:
+   ParFiniteElementSpace &pfes;
+public:
+   MonolithicSolver(ParFiniteElementSpace &space) : pfes(space) {}
+   virtual ~MonolithicSolver() {}
+   virtual void CalcSolution(const Vector &u, Vector &du) const = 0;
+};
+
+// remhos_mono.hpp:44-65.  The assembled matrices, the lumped mass, the Assembly object and the
+// velocity coefficient of the reference's constructor live in the device context of the space;
+// no smoothness indicator yet (-si).
+class MonoRDSolver : public MonolithicSolver
+{
+   bool subcell_scheme, time_dep, mass_lim;
+public:
+   std::vector<double> scale;      // remhos_mono.cpp:40-57
+   MonoRDSolver(ParFiniteElementSpace &space, bool subcell, bool timedep, bool masslim);
+   ~MonoRDSolver();
+   void CalcSolution(const Vector &u, Vector &du) const override;
+};
+
 class DofInfo
 {
    ParFiniteElementSpace &pfes;
@@ -243,11 +271,12 @@ class AdvectionOperator : public LimitedTimeDependentOperator
    HOSolver *ho_solver;
    LOSolver *lo_solver;
    FCTSolver *fct_solver;
+   MonolithicSolver *mono_solver;
 public:
    mutable TimingData timer;
    bool verify_bounds = false;
    AdvectionOperator(ParFiniteElementSpace &space, Vector &lumpedM_, DofInfo &dofs_, HOSolver *hos,
-                     LOSolver *los, FCTSolver *fct);
+                     LOSolver *los, FCTSolver *fct, MonolithicSolver *mos = nullptr);
    void SetDt(double dt_) override;
    void SetTime(double t_) override;
    void MultUnlimited(const Vector &x, Vector &y) const override;

@@ -15,7 +15,7 @@ EXE = os.path.join(ROOT, 'remhos_b200', 'host', 'remhos')
 
 
 def run_cli(*args):
-    p = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    p = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=180)
     return p.returncode, p.stdout, p.stderr
 
 
@@ -137,3 +137,28 @@ def test_cli_baseline_config_c1_matches_oracle():
     assert abs(r['umax'] - run.final_max) < 1e-9 * abs(run.final_max)
     assert r['loss'] < 1e-12
     assert 'time step:' in out and 'residual:' in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mono,order,meshname,problem', [(1, 2, 'periodic-square.mesh', 5),
+                                                         (2, 3, 'periodic-square.mesh', 1),
+                                                         (1, 1, 'inline-quad.mesh', 4)])
+def test_cli_mono_matches_oracle(mono, order, meshname, problem):
+    """-mono 1/2 (MonoRDSolver, no smoothness indicator) through the C++ MonolithicSolver mirror:
+    the driver computes the scale factors itself (remhos_mono.cpp:40-57)"""
+    rc, out, err = run_cli('-m', mesh(meshname), '-p', problem, '-rs', 2, '-o', order, '-dt', 0.002,
+                           '-tf', 0.02, '-s', 3, '-mono', mono, '-no-vis', '-ms', 10)
+    assert rc == 0, err
+    r = parse(out)
+    run = oracle_run(meshname, problem=problem, rs_levels=2, order=order, dt=0.002, t_final=0.02,
+                     ode_solver=3, mono_type=mono, max_steps=10)
+    run.run()
+    assert abs(r['mass'] - run.final_mass) < 1e-9 * abs(run.final_mass)
+    assert abs(r['umax'] - run.final_max) < 1e-9 * abs(run.final_max)
+
+
+def test_mono_flag_validation():
+    rc, _, err = run_cli('-m', 'x', '-mono', '3')
+    assert rc == 134 and 'Verification failed' in err
+    rc, _, err = run_cli('-m', 'x', '-mono', '2', '-o', '1')
+    assert rc == 134 and 'Subcell schemes require' in err

@@ -1,0 +1,75 @@
+"""GPU parity tests of the monolithic solver (MonoRDSolver, remhos_mono.cpp:60-356, `-mono 1/2`
+without a smoothness indicator) against the CPU oracle.  The oracle's restatement of this solver
+is NOT pinned by a reference number (both out_baseline.dat rows that use -mono also use -si):
+parity here is CUDA-vs-oracle plus the properties the scheme guarantees (conservation on periodic
+meshes, local bounds).
+
+Tolerances: one evaluation 1e-10 of the field's max norm (the fixed-point loop stops on a norm
+threshold, so a round-off sized difference may add or drop one sweep whose update is below 1e-8 of
+the residual scale); whole runs 1e-9.
+"""
+import numpy as np
+import pytest
+
+from helpers import oracle_run, ctx_from_oracle, rel_err, subcell_setup_from_oracle
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ('periodic-square.mesh', dict(problem=5, rs_levels=2, order=2, mono_type=1), 0),
+    ('periodic-square.mesh', dict(problem=1, rs_levels=1, order=3, mono_type=2), 0),
+    ('periodic-square.mesh', dict(problem=5, rs_levels=1, order=3, mono_type=2), 1),
+    ('inline-quad.mesh', dict(problem=6, rs_levels=2, order=1, mono_type=1), 0),      # mass_lim off
+    ('inline-quad.mesh', dict(problem=4, rs_levels=1, order=2, mono_type=1), 0),      # inflow boundary
+    ('periodic-hexagon.mesh', dict(problem=0, rs_levels=1, order=2, mono_type=1), 0),
+    ('periodic-cube.mesh', dict(problem=0, rs_levels=1, order=2, mono_type=1), 0),
+    ('periodic-cube.mesh', dict(problem=1, rs_levels=0, order=3, mono_type=2), 1),
+]
+
+
+def dev(a):
+    return torch.tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(-1), device='cuda')
+
+
+def make(mesh, opt, bt):
+    run = oracle_run(mesh, bounds_type=bt, dt=0.002, **opt)
+    ctx = ctx_from_oracle(run)
+    if opt['mono_type'] == 2:
+        subcell_setup_from_oracle(run, ctx)
+    ctx.mono_setup(opt['mono_type'], run.opt.problem not in (6, 7), run.mono_scale)
+    return run, ctx
+
+
+@pytest.mark.parametrize('mesh,opt,bt', CASES)
+def test_mono_rd_matches_oracle(mesh, opt, bt):
+    run, ctx = make(mesh, opt, bt)
+    rng = np.random.default_rng(5)
+    u = np.clip(run.u + 0.05 * rng.standard_normal(run.u.shape), 0.0, 1.0)
+    ref = run.mult(u, 0.0, run.dt)
+    k = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.mono_rd(dev(u), k)
+    assert rel_err(k.cpu().numpy().reshape(u.shape), ref) < 1e-10
+    # rmh_mult evaluates the monolithic solver while one is set (remhos.cpp:1687)
+    k2 = torch.empty_like(k)
+    ctx.mult(3, 5, 2, 0.0, run.dt, dev(u), k2)
+    assert torch.equal(k, k2)
+    ctx.close()
+
+
+@pytest.mark.parametrize('mesh,opt,bt', [CASES[0], CASES[2], CASES[6]])
+def test_mono_run_matches_oracle(mesh, opt, bt):
+    run, ctx = make(mesh, dict(opt, ode_solver=3, max_steps=8), bt)
+    u = dev(run.u)
+    t = 0.0
+    for _ in range(8):
+        t = ctx.ode_step(3, 0, 0, 0, t, run.dt, u)
+    run.run()
+    ug = u.cpu().numpy().reshape(run.u.shape)
+    assert rel_err(ug, run.u) < 1e-9
+    m = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.lumped_mass(m)
+    mass = ctx.reduce(0, u, m)
+    assert abs(mass - run.mass0) < 1e-12 * abs(run.mass0)          # periodic: conservative
+    assert ug.min() > run.u0_min - 1e-10 and ug.max() < run.u0_max + 1e-10
+    ctx.close()
