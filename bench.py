@@ -186,9 +186,8 @@ def main():
         raise SystemExit('bench.py: no CUDA device (remhos_b200 has no CPU fallback)')
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # keep stdout to the one JSON line: NCCL's debug output (version banner included) -> stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     h = 2.0 / (3 * 2 ** a.rs)

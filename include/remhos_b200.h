@@ -289,6 +289,17 @@ int rmh_rk_step(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, doubl
 int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, double dt,
                      double *u_host);
 
+/* Overlap of the halo exchange with interior work (replaces the blocking ExchangeFaceNbrData of
+ * remhos.cpp:1813 inside K.Mult): order the owned elements so that [0, n_interior) share no vertex
+ * with a ghost element, declare that with rmh_dist_split, then per stage
+ *   rmh_halo_pack -> (NCCL exchange on a side stream) || rmh_rk_stage_part(part 1)
+ *   -> rmh_halo_set -> rmh_rk_stage_part(part 2).
+ * Parts 1 + 2 equal one rmh_rk_stage_dist.  Needs overlap bounds (-bt 0) and the
+ * constant-coefficient stage kernel (rmh_ctx_path_flags bit 3). */
+int rmh_dist_split(rmh_ctx *ctx, int64_t n_interior);
+int rmh_rk_stage_part(rmh_ctx *ctx, int lo_type, double dt, double a, double b, const double *x0_dev,
+                      const double *y_dev, double *out_dev, int part, void *stream);
+
 /* ---- multi-GPU: one context per rank; ghost elements follow the owned ones in every index map.
  * These replace ParGridFunction::ExchangeFaceNbrData (remhos.cpp:1813; inside K.Mult) and the
  * GroupCommunicator min/max reduction of DofInfo::ComputeOverlapBounds (remhos_tools.cpp:463-466):

@@ -361,6 +361,14 @@ class Context:
         check(lib().rmh_rk_stage_dist(self.h, int(lo_type), C.c_double(dt), C.c_double(a),
                                       C.c_double(b), _dp(x0), _dp(y), _dp(out), C.c_void_p(s)))
 
+    def dist_split(self, n_interior):
+        check(lib().rmh_dist_split(self.h, C.c_int64(n_interior)))
+
+    def rk_stage_part(self, lo_type, dt, a, b, x0, y, out, part, s=0):
+        check(lib().rmh_rk_stage_part(self.h, int(lo_type), C.c_double(dt), C.c_double(a),
+                                      C.c_double(b), _dp(x0), _dp(y), _dp(out), int(part),
+                                      C.c_void_p(s)))
+
     def profile(self, enable):
         ms = C.c_double(0.0); n = C.c_int64(0)
         check(lib().rmh_profile(self.h, int(enable), C.byref(ms), C.byref(n)))

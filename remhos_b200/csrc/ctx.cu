@@ -82,6 +82,11 @@ struct rmh_ctx
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    bool op_lin = false;       // ... and adj(J) v is linear over every element: opc is valid
    bool op_const = false;     // ... and constant over every element: opa is valid
+   // decomposed meshes: entities that touch a ghost element come last in ent_list; owned elements
+   // [0, n_split) have no ghost dependence (rmh_dist_split)
+   int32_t *ent_list = nullptr;
+   int n_ent_int = 0;
+   int64_t n_split = -1;
    int mono_type = 0;         // rmh_mono_setup: 1 MonoRDSolver, 2 with subcells; 0 none
    int mono_mass_lim = 1;
    double *mono_scale = nullptr;   // [ne] (remhos_mono.cpp:40-57)
@@ -853,11 +858,12 @@ static void launch_elem_min_max(int64_t ne, int nd, const double *u, double *xe_
 }
 
 // entity min/max over the elements sharing the entity (CG-dof overlap, remhos_tools.cpp:449-458)
-__global__ void k_ent_min_max(int32_t n_ent, const int32_t *off, const int32_t *el,
+__global__ void k_ent_min_max(int32_t n_ent, const int32_t *list, const int32_t *off, const int32_t *el,
                               const double *xe_min, const double *xe_max, double *ent_mm)
 {
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= n_ent) { return; }
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= n_ent) { return; }
+   const int i = list ? list[t] : t;
    double mn = INFINITY, mx = -INFINITY;
    const int k1 = off[i + 1];
    // batches of four: all index loads, then all value loads, are in flight together
@@ -1355,7 +1361,7 @@ static int launch_stagec_G(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
                  GH ? "ghosts" : "local", blocks_per_sm, nb, BYTES);
       }
    }
-   const int64_t ngrp = (a.ne + S::E - 1) / S::E;
+   const int64_t ngrp = (a.ne + S::E - 1) / S::E - a.e_begin / S::E;
    const int64_t nblk = (ngrp + NW - 1) / NW;
    const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
    k_stage3c<D1, NW, MINB, NST, GH><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
@@ -1715,6 +1721,21 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       if (dev_upload(c, &c->ent_off, off.data(), off.size())) { return fail(); }
       if (dev_upload(c, &c->ent_el, el.data(), el.size())) { return fail(); }
       if (dev_alloc(c, &c->ent_mm, 2 * (size_t)c->n_ent)) { return fail(); }
+      if (c->ne_ghost > 0)
+      {
+         // entity ids, those without a ghost element first (interior / boundary passes of the
+         // overlapped multi-GPU stage)
+         std::vector<int32_t> list((size_t)c->n_ent);
+         int ni = 0, nb = c->n_ent;
+         for (int i = 0; i < c->n_ent; i++)
+         {
+            bool ghost = false;
+            for (int k = off[i]; k < off[i + 1]; k++) { if (el[k] >= c->ne) { ghost = true; break; } }
+            if (ghost) { list[--nb] = i; } else { list[ni++] = i; }
+         }
+         c->n_ent_int = ni;
+         if (dev_upload(c, &c->ent_list, list.data(), list.size())) { return fail(); }
+      }
    }
    else
    {
@@ -1778,7 +1799,8 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
             const char *el = getenv("RMH_LINEAR_OP");
             c->op_lin = (nf[0] == 0) && el && el[0] == '1';
             const char *nc = getenv("RMH_NO_CONST_OP");
-            c->op_const = (nf[1] == 0) && !(nc && nc[0] == '1');
+            // (the constant-coefficient kernel keeps the whole orientation-pattern table in shared memory)
+            c->op_const = (nf[1] == 0) && !(nc && nc[0] == '1') && c->npat <= 16;
             if (getenv("RMH_VERBOSE"))
             {
                fprintf(stderr, "k_op_linear: %u of %lld elements not linear, %u not constant\n", nf[0],
@@ -1869,7 +1891,7 @@ extern "C" int rmh_bounds(rmh_ctx *c, const double *xe_min, const double *xe_max
    const int bs = 256;
    if (c->bounds_type == 0)
    {
-      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, c->ent_off, c->ent_el, xe_min,
+      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, nullptr, c->ent_off, c->ent_el, xe_min,
                                                             xe_max, c->ent_mm);
       LAUNCH_OK();
       k_bounds_overlap<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(
@@ -1921,9 +1943,11 @@ extern "C" int rmh_reduce(rmh_ctx *c, int op, const double *a, const double *b, 
 
 // ---------------------------------------------------------------- fused stage entry points
 // xe_valid: ctx->xe_min/xe_max already hold the element min/max of y
+// part: 0 = the whole mesh; 1 = owned elements [0, n_split) and the entities without ghost elements;
+// 2 = the rest (needs the halo of y installed).  Parts 1 + 2 together equal part 0.
 static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a, double b,
                       const double *x0, const double *y, double *out, bool xe_valid,
-                      bool write_xe, cudaStream_t s)
+                      bool write_xe, cudaStream_t s, int part = 0)
 {
    if (lo_type != 5)
    {
@@ -1938,11 +1962,25 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       launch_elem_min_max(c->ne, c->ND, y, c->xe_min, c->xe_max, s);
       LAUNCH_OK();
    }
+   if (part != 0)
+   {
+      if (!(c->op_const && c->frag && c->bounds_type == 0 && c->n_split >= 0 && c->ent_list && xe_valid))
+      {
+         set_error("split stage: needs the constant-coefficient kernel, overlap bounds, a ghost layer, "
+                   "rmh_dist_split and valid element min/max");
+         return 1;
+      }
+   }
    if (c->bounds_type == 0)
    {
-      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, c->ent_off, c->ent_el, c->xe_min,
-                                                            c->xe_max, c->ent_mm);
-      LAUNCH_OK();
+      const int n0 = (part == 2) ? c->n_ent_int : 0, n1 = (part == 1) ? c->n_ent_int : c->n_ent;
+      if (n1 > n0)
+      {
+         k_ent_min_max<<<(n1 - n0 + bs - 1) / bs, bs, 0, s>>>(n1 - n0, part ? c->ent_list + n0 : nullptr,
+                                                              c->ent_off, c->ent_el, c->xe_min, c->xe_max,
+                                                              c->ent_mm);
+         LAUNCH_OK();
+      }
    }
    StageArgs sa;
    sa.ho = ho_args(c, y, nullptr, 3);
@@ -1957,10 +1995,13 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    // 3D meshes with constant-Jacobian elements: persistent pipelined kernel
    const bool use_p = c->pipelined && c->dim == 3 && c->all_affine &&
                       ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
+   if (part != 0 && !use_p) { set_error("split stage: state vectors must be 16-byte aligned"); return 1; }
    StagePArgs pa;
    if (use_p)
    {
-      pa.ne = c->ne; pa.y = y; pa.x0 = x0; pa.out = out;
+      pa.ne = (part == 1) ? c->n_split : c->ne; pa.y = y; pa.x0 = x0; pa.out = out;
+      pa.e_begin = (part == 2) ? c->n_split : 0;
+      if (pa.e_begin >= pa.ne) { return 0; }
       pa.Dvol = c->Dvol; pa.Dface = c->Dface; pa.einv = c->einv;
       pa.opc = c->op_lin ? c->opc : nullptr;
       pa.opa = c->op_const ? c->opa : nullptr;
@@ -2688,6 +2729,23 @@ extern "C" int rmh_halo_set(rmh_ctx *c, const double *ghost_u, const double *gho
    return 0;
 }
 
+// Overlapped multi-GPU stage.  rmh_dist_split: owned elements [0, n_interior) share no vertex with a
+// ghost element (the caller orders them first); rounded down to a multiple of the elements a warp
+// handles at once.  rmh_rk_stage_part(part 1) may run while the halo of y is still in flight,
+// part 2 after rmh_halo_set on the same stream.
+extern "C" int rmh_dist_split(rmh_ctx *c, int64_t n_interior)
+{
+   if (n_interior < 0 || n_interior > c->ne) { set_error("rmh_dist_split: out of range"); return 1; }
+   c->n_split = (n_interior / 8) * 8;
+   return 0;
+}
+extern "C" int rmh_rk_stage_part(rmh_ctx *c, int lo_type, double dt, double a, double b,
+                                 const double *x0, const double *y, double *out, int part, void *stream)
+{
+   if (part != 1 && part != 2) { set_error("rmh_rk_stage_part: part must be 1 (interior) or 2 (boundary)"); return 1; }
+   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0,
+                     (cudaStream_t)stream, part);
+}
 extern "C" int rmh_rk_stage_dist(rmh_ctx *c, int lo_type, double dt, double a, double b,
                                  const double *x0, const double *y, double *out, void *stream)
 {

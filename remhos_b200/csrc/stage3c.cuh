@@ -292,7 +292,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    __syncthreads();     // the only block barrier: the pattern table is in place
    const int64_t NG = (a.ne + E - 1) / E;                           // element groups
    const int64_t GW = (int64_t)gridDim.x * NW;
-   int64_t gi = (int64_t)blockIdx.x * NW + w;
+   int64_t gi = a.e_begin / E + (int64_t)blockIdx.x * NW + w;
    if (gi >= NG) { return; }
    const int last_nv = (int)(a.ne - (NG - 1) * E);
    auto nvalid = [&](int64_t g) { return (g + 1 == NG) ? last_nv : E; };

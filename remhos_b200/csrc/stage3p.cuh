@@ -82,7 +82,8 @@ struct SmemP
 
 struct StagePArgs
 {
-   int64_t ne;                // owned elements
+   int64_t ne;                // owned elements (end of the launch range)
+   int64_t e_begin = 0;       // first element of the launch range (k_stage3c only; multiple of 8)
    const double *y;           // stage input
    const double *x0;          // RK base state (may alias y or out)
    double *out;

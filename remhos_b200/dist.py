@@ -29,6 +29,21 @@ def exchange(dist, plan, send_bufs, recv_bufs, widths):
         req.wait()
 
 
+def interior_first(plan):
+    """Reorder the owned elements of a halo plan in place: those that some peer needs (= those
+    sharing a vertex with a ghost element -- the ghost ring is vertex adjacency, which is symmetric)
+    go last, so that the stage kernel can run on the leading elements while the halo is still in
+    flight.  Returns the number of leading (interior) elements."""
+    bnd = np.zeros(plan.owned.size, dtype=bool)
+    bnd[plan.send_local] = True
+    perm = np.concatenate([np.flatnonzero(~bnd), np.flatnonzero(bnd)])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    plan.owned = plan.owned[perm]
+    plan.send_local = inv[plan.send_local].astype(np.int32)
+    return int((~bnd).sum())
+
+
 class DistProblem:
     """Set-up of one rank's share of a run (transport problems; same reference defaults as
     setup_problem.Problem).  `mesh` is the GLOBAL mesh (geometry order 1 is enough), already
@@ -44,6 +59,7 @@ class DistProblem:
         dim = mesh.dim
         part = mesh.partition(world)
         plan = mesh.halo(part, rank)
+        self.n_interior = interior_first(plan)
         self.plan = plan
         ids = np.concatenate([plan.owned, plan.ghost])
         local = mesh.extract(ids)
@@ -81,6 +97,16 @@ class DistProblem:
         self.w1 = torch.empty(self.ctx.ndofs, dtype=f64, device=dev)
         self.w2 = torch.empty(self.ctx.ndofs, dtype=f64, device=dev)
         self.n_send = ns
+        # overlap of the exchange with the interior elements (rmh_rk_stage_part; constant-coefficient
+        # stage kernel and overlap bounds only).  Opt-in (RMH_OVERLAP=1): on 2 GPUs the second,
+        # small launch for the elements next to the ghost ring plus the NCCL kernels competing for
+        # SMs cost more (2.19 ms/step) than the ~60 us of exchange they hide (2.12 ms/step sequential)
+        import os
+        self.overlap = bool(world > 1 and ng > 0 and bounds_type == 0 and (self.ctx.path_flags & 8)
+                            and os.environ.get('RMH_OVERLAP', '0') == '1')
+        if self.overlap:
+            self.ctx.dist_split(self.n_interior)
+            self.cs = torch.cuda.Stream(device=dev)
 
     def halo(self, y, stream=0):
         """pack -> NCCL send/recv -> install the ghosts of y (element min/max of y must already be
@@ -92,6 +118,27 @@ class DistProblem:
                      [self.nd, 2])
         self.ctx.halo_set(self.ghost_u, self.ghost_mm, stream)
 
+    def stage(self, a, b, x0, y, out, stream=0):
+        """one RK stage out = a x0 + b (y + dt F(y)) on the decomposed mesh, halo of y included"""
+        ctx, dt = self.ctx, self.dt
+        if not self.overlap:
+            self.halo(y, stream)
+            ctx.rk_stage_dist(5, dt, a, b, x0, y, out, stream)
+            return
+        import torch.distributed as dist
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        ms = main.cuda_stream
+        ctx.halo_pack(y, self.send_local, self.n_send, self.send_u, self.send_mm, ms)
+        self.cs.wait_stream(main)
+        with torch.cuda.stream(self.cs):                # NCCL send/recv ordered behind the pack
+            exchange(dist, self.plan, [self.send_u, self.send_mm], [self.ghost_u, self.ghost_mm],
+                     [self.nd, 2])
+        ctx.rk_stage_part(5, dt, a, b, x0, y, out, 1, ms)     # interior elements: no ghost dependence
+        main.wait_stream(self.cs)
+        ctx.halo_set(self.ghost_u, self.ghost_mm, ms)
+        ctx.rk_stage_part(5, dt, a, b, x0, y, out, 2, ms)     # elements next to the ghost ring
+
     def rk3_step(self, t, u, stream=0):
         """RK3-SSP step (remhos.cpp:490) on the decomposed mesh: three fused stage launches, each
         preceded by one halo exchange."""
@@ -102,16 +149,13 @@ class DistProblem:
         if not (chain and getattr(self, 'trust_state', False) and getattr(self, '_xe_for', None) == u.data_ptr()):
             ctx.stage_minmax(u, stream)
         self._xe_for = None
-        self.halo(u, stream)
-        ctx.rk_stage_dist(5, dt, 0.0, 1.0, u, u, self.w1, stream)
+        self.stage(0.0, 1.0, u, u, self.w1, stream)
         if not chain:
             ctx.stage_minmax(self.w1, stream)
-        self.halo(self.w1, stream)
-        ctx.rk_stage_dist(5, dt, 0.75, 0.25, u, self.w1, self.w2, stream)
+        self.stage(0.75, 0.25, u, self.w1, self.w2, stream)
         if not chain:
             ctx.stage_minmax(self.w2, stream)
-        self.halo(self.w2, stream)
-        ctx.rk_stage_dist(5, dt, 1.0 / 3.0, 2.0 / 3.0, u, self.w2, u, stream)
+        self.stage(1.0 / 3.0, 2.0 / 3.0, u, self.w2, u, stream)
         if chain:
             self._xe_for = u.data_ptr()
         return t + dt

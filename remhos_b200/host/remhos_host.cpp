@@ -672,6 +672,9 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &u_max, nullptr));
       ODESolver ode_solver(o.ode);
       ode_solver.Init(adv);
+      // the time loop below only reads the state between steps: the element min/max the last RK
+      // stage leaves for its output are reused by the next step (fused RK1/2/3 path)
+      Check(rmh_ctx_trust_state(pfes.ctx, 1));
       const bool steady = (o.problem == 6 || o.problem == 7 || o.problem == 8);
       std::vector<double> res_h, ml_h;
       if (steady) { res_h = u.HostRead(); ml_h = lumpedM.HostRead(); }

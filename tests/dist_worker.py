@@ -40,6 +40,20 @@ def run_cpu(rank, world, port):
         nb = nb[nb >= 0]
         known = np.concatenate([plan.owned, plan.ghost])
         assert np.isin(nb, known).all()
+        # interior-first reordering (overlap of the exchange with interior work): the elements sent
+        # stay the same, and no leading element shares a lattice entity (vertex, edge, face) with an
+        # element of another rank
+        from remhos_b200.dist import interior_first
+        sent = plan.owned[plan.send_local].copy()
+        owned_set = set(plan.owned.tolist())
+        n_int = interior_first(plan)
+        assert np.array_equal(plan.owned[plan.send_local], sent)
+        assert set(plan.owned.tolist()) == owned_set and (plan.send_local >= n_int).all()
+        lat = maps['lat']
+        ent_foreign = np.zeros(maps['n_ent'], dtype=bool)
+        foreign = np.setdiff1d(np.arange(m.ne), plan.owned)
+        ent_foreign[lat[foreign].reshape(-1)] = True
+        assert not ent_foreign[lat[plan.owned[:n_int]]].any(), (rank, dim)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -55,8 +69,9 @@ def run_gpu():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     steps = 4
-    for bt in (0, 1):
-        for problem in (0, 1):
+    for bt, problem, overlap in ((0, 0, '0'), (0, 0, '1'), (0, 1, '0'), (1, 0, '0'), (1, 1, '0')):
+        os.environ['RMH_OVERLAP'] = overlap      # '1': exchange overlapped with the interior elements
+        if True:
             mesh = rb.Mesh.cartesian([3, 3, 3], [2.0] * 3, origin=[-1.0] * 3, periodic=True).refine(1)
             dp = DistProblem(mesh, rank, world, problem=problem, order=3, bounds_type=bt, dt=0.01,
                              device=local)
