@@ -60,6 +60,7 @@ class Options:                       # defaults: remhos.cpp:216-244
     lo_type: int = 0
     fct_type: int = 0
     mono_type: int = 0            # 1: MonoRDSolver, 2: with subcells (remhos.cpp:285-289)
+    si_type: int = 0              # smoothness indicator (remhos.cpp:302; order 1 only here)
     bounds_type: int = 0
     t_final: float = 4.0
     dt: float = 0.005
@@ -119,6 +120,18 @@ class Run:
             t_final = 1.0                                      # :1128-1134
         self.t_final = t_final
         infl = problems.inflow(prob, sp.dof_points(X0).reshape(-1, dim)).reshape(m.ne, sp.nd)
+        if prob == 7:
+            # "Convergence test: use high order projection" (remhos.cpp:628-635): interpolate the
+            # inflow function at the tensor Gauss-Legendre points (L2_FECollection's nodal basis),
+            # then take the Bernstein coefficients of that very polynomial (ProjectGridFunction
+            # between two bases of the same space) -- not the nodal samples at the lattice points
+            xg, _ = fe.gauss_legendre_01(sp.p + 1)
+            Lg = fe.tensor_basis([fe.lagrange(sp.gll, xg)] * dim)
+            pts = np.einsum('qn,eni->eqi', Lg, X0)
+            vals = problems.inflow(prob, pts.reshape(-1, dim)).reshape(m.ne, sp.nd)
+            Vinv = np.linalg.inv(fe.bernstein(sp.p, xg))               # [p+1 coeffs, p+1 points]
+            T = fe.tensor_basis([Vinv] * dim)
+            infl = vals @ T.T
         self.disc = Discretization(sp, self.topo, X0, self.exec_mode, vel_fun=vel,
                                    Vnodes=Vnodes, inflow_vals=infl)
         self.disc.assemble(0.0)
@@ -132,6 +145,10 @@ class Run:
         self.mono_scale = None
         if opt.mono_type:
             self.mono_scale = self._mono_scale()
+        self.si = None
+        if opt.si_type:
+            from .smoothness import SmoothnessIndicator
+            self.si = SmoothnessIndicator(self, opt.si_type)
 
     # ---------------------------------------------------------------- stage operator
     def _mono_scale(self):
@@ -166,7 +183,8 @@ class Run:
         if o.mono_type:                                        # remhos.cpp:1687
             sw = self.get_subcell_weights() if o.mono_type == 2 else None
             mass_lim = o.problem not in (6, 7)                 # remhos.cpp:999
-            return d.mono_rd(u, o.bounds_type, self.mono_scale, sw, mass_lim)
+            si_tmp = self.si.dof_values(u) if self.si is not None else None
+            return d.mono_rd(u, o.bounds_type, self.mono_scale, sw, mass_lim, si_tmp)
         if o.fct_type:
             du_ho = self.calc_ho(u)
             du_lo = self.calc_lo(u, du_ho, dt)
@@ -358,12 +376,23 @@ class Run:
         u = self.u
         ti = 0
         done = False
+        steady = o.problem in (6, 7, 8)                        # remhos.cpp:1146-1330
+        res = u.copy()
+        ml0 = self.disc.cur.ml
+        self.residual = 0.0
         while not done:
             dt_real = min(dt, self.t_final - t)
             u = self.step(u, t, dt_real)
             t += dt_real
             ti += 1
             done = t >= self.t_final - 1e-8 * dt
+            if steady:                                         # :1263-1290
+                self.residual = float(np.sqrt((((ml0 * u) / dt - (ml0 * res) / dt) ** 2).sum()))
+                if self.residual < 1e-12 and t >= 1.0:
+                    done = True
+                    u = res
+                else:
+                    res = u.copy()
             if ti == o.max_steps:
                 done = True
             if callback:

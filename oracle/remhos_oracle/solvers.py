@@ -227,8 +227,9 @@ class Discretization:
             np.add.at(y, (slice(None), sp.bd[:, f]), lump + corr)
         return y
 
-    def mono_rd(self, u, bounds_type, scale, subcell_weights=None, mass_lim=True):
-        """MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356) without a smoothness indicator:
+    def mono_rd(self, u, bounds_type, scale, subcell_weights=None, mass_lim=True, si_tmp=None):
+        """MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356); si_tmp[NE, nd] = the smoothness
+        indicator value at each DOF (1 on the domain boundary, remhos_mono.cpp:134-135) or None:
         convex-limited residual distribution (beta = gamma = 10) with the element-local fixed-point
         mass correction (at most 101 sweeps, |res|_2 <= 1e-8).  scale[NE]: remhos_mono.cpp:40-57."""
         A, sp = self.cur, self.sp
@@ -240,6 +241,14 @@ class Discretization:
         d = z.copy()
         lo_gap = np.minimum(xi_max - u, u - xi_min)
         alpha = np.minimum(1.0, beta * lo_gap / (np.maximum(xi_max - u, u - xi_min) + eps))
+        if si_tmp is not None:                                        # remhos_mono.cpp:132-153
+            tmp = si_tmp
+            bndN = np.maximum(0.0, tmp * (2.0 * u - xi_max) + (1.0 - tmp) * xi_min)
+            bndP = np.minimum(1.0, tmp * (2.0 * u - xi_min) + (1.0 - tmp) * xi_max)
+            aN = np.minimum(1.0, beta * (u - bndN) / (xi_max - u + eps))
+            aP = np.minimum(1.0, beta * (bndP - u) / (u - xi_min + eps))
+            ssum = xi_min + xi_max
+            alpha = np.where(ssum > 2.0 * u + eps, aN, np.where(ssum < 2.0 * u - eps, aP, alpha))
         du = alpha * z
         z = z - alpha * z
         du = du + self.nonlin_flux_lumping(u, alpha)
@@ -285,9 +294,15 @@ class Discretization:
                 uDotMin = uDot.min(axis=1)[:, None]; uDotMax = uDot.max(axis=1)[:, None]
                 m_new = msum * uDot - np.einsum('eij,ej->ei', A.M, uDot)   # sum_j M_ij (uDot_i - uDot_j)
                 diff = d - du
-                m_new = m_new + np.minimum(1.0, np.abs(m_new) / (np.abs(diff) + eps)) * diff
-                al = np.minimum(1.0, beta * scale[:, None] * lo_gap /
-                                (np.maximum(uDotMax - uDot, uDot - uDotMin) + eps))
+                ratio = np.abs(m_new) / (np.abs(diff) + eps)
+                if si_tmp is not None:
+                    ratio = np.maximum(si_tmp, ratio)
+                m_new = m_new + np.minimum(1.0, ratio) * diff
+                den = np.maximum(uDotMax - uDot, uDot - uDotMin) + eps
+                al = np.minimum(1.0, beta * scale[:, None] * lo_gap / den)
+                if si_tmp is not None:                                # remhos_mono.cpp:316-324
+                    aglob = np.minimum(1.0, beta * scale[:, None] * np.minimum(1.0 - u, u - 0.0) / den)
+                    al = np.minimum(np.maximum(si_tmp, al), aglob)
                 m_new = m_new * al
                 MP = np.maximum(0.0, m_new).sum(axis=1); MN = np.minimum(0.0, m_new).sum(axis=1)
                 with np.errstate(divide='ignore', invalid='ignore'):
