@@ -97,6 +97,9 @@ int rmh_velocity(int problem, int dim, int64_t n, const double *x, const double 
 int rmh_u0(int problem, int dim, int64_t n, const double *x, const double *bb_min,
            const double *bb_max, double *u);
 int rmh_inflow(int problem, int dim, int64_t n, const double *x, double *u);
+/* inflow_gf (remhos.cpp:625-636) in the order-p Bernstein space, [ne][(p+1)^dim]: lattice samples,
+ * or -- problem 7 -- the Bernstein form of the interpolant at the tensor Gauss-Legendre points */
+int rmh_inflow_project(const rmh_mesh *m, int problem, int order, double *infl_out);
 /* physical coordinates of the tensor lattice pts1d[npts]^dim of every element (face < 0), or of
  * the lattice on local face `face`; out [ne][npts^d'][dim].  With pts = i/p this gives the
  * points ProjectCoefficient samples on the positive basis (remhos.cpp:883). */
@@ -228,12 +231,20 @@ int rmh_fct_clip_scale(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
 int rmh_subcell_setup(rmh_ctx *ctx, const double *xlat_host, const double *vel_host, void *stream);
 int rmh_lo_res_dist_subcell(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
 
+/* SmoothnessIndicator (remhos_tools.hpp; remhos_tools.cpp:24-354; created at remhos.cpp:905-911):
+ * si_type 1 or 2 (-si), 0 removes it.  Built for order-1 spaces (the configuration of the
+ * reference's monolithic-solver known answers); while set, rmh_mono_rd uses it as
+ * remhos_mono.cpp:132-153,300-324 do.  rmh_si_values = ComputeSmoothnessIndicator followed by the
+ * DG2CG gather: one value per DG dof (1 on the domain boundary); out_dev may be NULL. */
+int rmh_si_setup(rmh_ctx *ctx, int si_type, void *stream);
+int rmh_si_values(rmh_ctx *ctx, const double *u_dev, double *out_dev, void *stream);
+
 /* MonolithicSolver (remhos_mono.hpp:28-65; set up at remhos.cpp:997-1011).  mono_type 1 =
  * MonoRDSolver, 2 = with the subcell scheme (needs rmh_subcell_setup), 0 removes it.  mass_lim as at
  * remhos.cpp:999.  scale_host[ne] = vmax / (2 sqrt(dim) h_e / order) (MonoRDSolver constructor,
  * remhos_mono.cpp:40-57).  While a monolithic solver is set, rmh_mult / rmh_mult_unlimited /
  * rmh_ode_step evaluate it instead of HO/LO/FCT (remhos.cpp:1687) and rmh_limit_mult is a no-op.
- * No smoothness indicator (-si) yet.  Serial only, as in the reference (remhos_mono.cpp:283). */
+ * Serial only, as in the reference (remhos_mono.cpp:283). */
 int rmh_mono_setup(rmh_ctx *ctx, int mono_type, int mass_lim, const double *scale_host, void *stream);
 /* MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356) */
 int rmh_mono_rd(rmh_ctx *ctx, const double *u_dev, double *du_dev, void *stream);

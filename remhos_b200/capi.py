@@ -281,6 +281,12 @@ class Context:
         check(lib().rmh_mono_setup(self.h, int(mono_type), int(bool(mass_lim)), _ptr(scale),
                                    C.c_void_p(s)))
 
+    def si_setup(self, si_type, s=0):
+        check(lib().rmh_si_setup(self.h, int(si_type), C.c_void_p(s)))
+
+    def si_values(self, u, out, s=0):
+        check(lib().rmh_si_values(self.h, _dp(u), _dp(out), C.c_void_p(s)))
+
     def mono_rd(self, u, du, s=0):
         check(lib().rmh_mono_rd(self.h, _dp(u), _dp(du), C.c_void_p(s)))
 

@@ -87,6 +87,13 @@ struct rmh_ctx
    int32_t *ent_list = nullptr;
    int n_ent_int = 0;
    int64_t n_split = -1;
+   // smoothness indicator (rmh_si_setup): H1 order-1 operators in CSR
+   int si_type = 0, si_n = 0;
+   double si_param = 0.0;
+   int32_t *si_MI = nullptr, *si_MJ = nullptr, *si_LI = nullptr, *si_LJ = nullptr, *si_XI = nullptr,
+           *si_XJ = nullptr, *si_d2c = nullptr;
+   double *si_MA = nullptr, *si_LA = nullptr, *si_XA = nullptr, *si_ml = nullptr, *si_y = nullptr,
+          *si_z = nullptr, *si_r = nullptr, *si_val = nullptr, *si_tmp = nullptr, *si_nrm = nullptr;
    int mono_type = 0;         // rmh_mono_setup: 1 MonoRDSolver, 2 with subcells; 0 none
    int mono_mass_lim = 1;
    double *mono_scale = nullptr;   // [ne] (remhos_mono.cpp:40-57)
@@ -2299,6 +2306,237 @@ extern "C" int rmh_lo_res_dist_subcell(rmh_ctx *c, const double *u, double *du_l
    return 0;
 }
 
+// ---- SmoothnessIndicator (remhos_tools.cpp:24-354) for order-1 spaces: the H1 space of positive
+// order-1 elements on the mesh itself (remhos.cpp:870) has one DOF per vertex.  Element matrices by
+// a 3-point Gauss rule on the multilinear map through the element corners (exact on parallelograms).
+namespace
+{
+struct Trip { int32_t r, c; double v; };
+void to_csr(int nrows, std::vector<Trip> &t, std::vector<int32_t> &I, std::vector<int32_t> &J,
+            std::vector<double> &A)
+{
+   std::sort(t.begin(), t.end(), [](const Trip &a, const Trip &b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+   I.assign((size_t)nrows + 1, 0); J.clear(); A.clear();
+   for (size_t k = 0; k < t.size(); k++)
+   {
+      if (k > 0 && t[k].r == t[k - 1].r && t[k].c == t[k - 1].c) { A.back() += t[k].v; continue; }
+      J.push_back(t[k].c); A.push_back(t[k].v); I[t[k].r + 1]++;
+   }
+   for (int i = 0; i < nrows; i++) { I[i + 1] += I[i]; }
+}
+// Q1 mass and (negative stiffness + boundary normal-derivative) matrices of one element
+void q1_element(int dim, const double *Xc, const bool *bnd, double *Me, double *Ke)
+{
+   const int nv = 1 << dim;
+   std::vector<double> xq, wq;
+   gauss_legendre_01(3, xq, wq);
+   for (int i = 0; i < nv * nv; i++) { Me[i] = 0.0; Ke[i] = 0.0; }
+   auto eval = [&](const double *xi, double *N, double (*G)[3], double &det, double (*Jinv)[3])
+   {
+      double dN[8][3], J[3][3] = {{0}};
+      for (int n = 0; n < nv; n++)
+      {
+         N[n] = 1.0;
+         for (int a = 0; a < dim; a++) { N[n] *= ((n >> a) & 1) ? xi[a] : 1.0 - xi[a]; }
+         for (int a = 0; a < dim; a++)
+         {
+            double d = 1.0;
+            for (int b = 0; b < dim; b++)
+            {
+               const int bit = (n >> b) & 1;
+               d *= (a == b) ? (bit ? 1.0 : -1.0) : (bit ? xi[b] : 1.0 - xi[b]);
+            }
+            dN[n][a] = d;
+            for (int i = 0; i < dim; i++) { J[i][a] += d * Xc[n * dim + i]; }
+         }
+      }
+      if (dim == 2)
+      {
+         det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+         Jinv[0][0] = J[1][1] / det; Jinv[0][1] = -J[0][1] / det;
+         Jinv[1][0] = -J[1][0] / det; Jinv[1][1] = J[0][0] / det;
+      }
+      else
+      {
+         double c[3][3];
+         c[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1]; c[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+         c[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1]; c[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+         c[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0]; c[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+         c[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0]; c[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+         c[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+         det = J[0][0] * c[0][0] + J[0][1] * c[1][0] + J[0][2] * c[2][0];
+         for (int a = 0; a < 3; a++) for (int i = 0; i < 3; i++) { Jinv[a][i] = c[a][i] / det; }
+      }
+      for (int n = 0; n < nv; n++)
+         for (int i = 0; i < dim; i++)
+         {
+            double g = 0.0;
+            for (int a = 0; a < dim; a++) { g += dN[n][a] * Jinv[a][i]; }
+            G[n][i] = g;
+         }
+   };
+   int nq = 1;
+   for (int a = 0; a < dim; a++) { nq *= 3; }
+   for (int q = 0; q < nq; q++)
+   {
+      double xi[3] = {0, 0, 0}, w = 1.0, N[8], G[8][3], det, Jinv[3][3];
+      int r = q;
+      for (int a = 0; a < dim; a++) { xi[a] = xq[r % 3]; w *= wq[r % 3]; r /= 3; }
+      eval(xi, N, G, det, Jinv);
+      w *= std::fabs(det);
+      for (int i = 0; i < nv; i++)
+         for (int j = 0; j < nv; j++)
+         {
+            double gg = 0.0;
+            for (int d = 0; d < dim; d++) { gg += G[i][d] * G[j][d]; }
+            Me[i * nv + j] += w * N[i] * N[j];
+            Ke[i * nv + j] -= w * gg;
+         }
+   }
+   for (int f = 0; f < 2 * dim; f++)
+   {
+      if (!bnd[f]) { continue; }
+      int axis, side;
+      face_axis(dim, f, axis, side);
+      int nqf = 1;
+      for (int a = 0; a < dim - 1; a++) { nqf *= 3; }
+      for (int q = 0; q < nqf; q++)
+      {
+         double xi[3] = {0, 0, 0}, w = 1.0, N[8], G[8][3], det, Jinv[3][3];
+         int r = q;
+         for (int a = 0; a < dim; a++)
+         {
+            if (a == axis) { xi[a] = side; }
+            else { xi[a] = xq[r % 3]; w *= wq[r % 3]; r /= 3; }
+         }
+         eval(xi, N, G, det, Jinv);
+         for (int j = 0; j < nv; j++)
+         {
+            double dn = 0.0;      // grad phi_j . (outward normal * surface element)
+            for (int i = 0; i < dim; i++) { dn += G[j][i] * (side ? 1.0 : -1.0) * det * Jinv[axis][i]; }
+            for (int i = 0; i < nv; i++) { Ke[i * nv + j] += w * N[i] * dn; }
+         }
+      }
+   }
+}
+} // namespace
+
+extern "C" int rmh_si_setup(rmh_ctx *c, int si_type, void *stream)
+{
+   if (si_type == 0) { c->si_type = 0; return 0; }
+   if (si_type != 1 && si_type != 2) { set_error("Bad smoothness indicator id!"); return 1; }   // remhos_tools.cpp:36
+   if (c->p != 1) { set_error("rmh_si_setup: the smoothness indicator is built for order 1 only"); return 1; }
+   if (!c->lat) { set_error("rmh_si_setup: needs the lattice entity map (bounds_type 0)"); return 1; }
+   if (c->ne_ghost > 0) { set_error("rmh_si_setup: decomposed meshes are not supported"); return 1; }
+   const int dim = c->dim, nv = 1 << dim, NF = c->NF, ND = c->ND;
+   const int64_t ne = c->ne;
+   std::vector<double> X((size_t)ne * c->NGN * dim);
+   std::vector<int32_t> lat((size_t)ne * c->N3), nbe((size_t)ne * NF);
+   CUDA_OK(cudaMemcpy(X.data(), c->X0, X.size() * sizeof(double), cudaMemcpyDeviceToHost));
+   CUDA_OK(cudaMemcpy(lat.data(), c->lat, lat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+   CUDA_OK(cudaMemcpy(nbe.data(), c->nbr_elem, nbe.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+   // corner j (bit a = coordinate a): geometry node and lattice entity position
+   int cnode[8], clat[8];
+   for (int j = 0; j < nv; j++)
+   {
+      int n = 0, t = 0;
+      for (int a = dim - 1; a >= 0; a--)
+      {
+         const int b = (j >> a) & 1;
+         n = n * c->NG1 + b * (c->NG1 - 1);
+         t = t * 3 + 2 * b;
+      }
+      cnode[j] = n; clat[j] = t;
+   }
+   // H1 dofs = the vertex entities that occur, compactly numbered in ascending entity id
+   std::vector<int32_t> ids;
+   ids.reserve((size_t)ne * nv);
+   for (int64_t e = 0; e < ne; e++) for (int j = 0; j < nv; j++) { ids.push_back(lat[e * c->N3 + clat[j]]); }
+   std::vector<int32_t> uniq(ids);
+   std::sort(uniq.begin(), uniq.end());
+   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+   const int N = (int)uniq.size();
+   std::vector<int32_t> cg(ids.size());
+   for (size_t i = 0; i < ids.size(); i++)
+   { cg[i] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), ids[i]) - uniq.begin()); }
+   std::vector<Trip> tm, tl, tx;
+   std::vector<int32_t> d2c((size_t)ne * ND);
+   std::vector<int> bd;
+   bdr_dofs(c->p, dim, bd);     // [NFD][NF]
+   for (int64_t e = 0; e < ne; e++)
+   {
+      double Xc[8 * 3], Me[64], Ke[64];
+      bool bnd[6];
+      for (int j = 0; j < nv; j++)
+         for (int i = 0; i < dim; i++) { Xc[j * dim + i] = X[((size_t)e * c->NGN + cnode[j]) * dim + i]; }
+      for (int f = 0; f < NF; f++) { bnd[f] = nbe[e * NF + f] < 0; }
+      q1_element(dim, Xc, bnd, Me, Ke);
+      for (int i = 0; i < nv; i++)
+      {
+         d2c[e * ND + i] = cg[e * nv + i];
+         for (int j = 0; j < nv; j++)
+         {
+            tm.push_back({cg[e * nv + i], cg[e * nv + j], Me[i * nv + j]});
+            tl.push_back({cg[e * nv + i], cg[e * nv + j], Ke[i * nv + j]});
+            tx.push_back({cg[e * nv + i], (int32_t)(e * ND + j), Me[i * nv + j]});
+         }
+      }
+      for (int f = 0; f < NF; f++)
+      {
+         if (!bnd[f]) { continue; }
+         for (int j = 0; j < c->NFD; j++) { d2c[e * ND + bd[j * NF + f]] = -1; }     // remhos_tools.cpp:94-105
+      }
+   }
+   std::vector<int32_t> MI, MJ, LI, LJ, XI, XJ;
+   std::vector<double> MA, LA, XA;
+   to_csr(N, tm, MI, MJ, MA); to_csr(N, tl, LI, LJ, LA); to_csr(N, tx, XI, XJ, XA);
+   std::vector<double> ml((size_t)N, 0.0);
+   for (int i = 0; i < N; i++) { for (int k = MI[i]; k < MI[i + 1]; k++) { ml[i] += MA[k]; } }   // LumpedIntegrator
+   if (dev_upload(c, &c->si_MI, MI.data(), MI.size()) || dev_upload(c, &c->si_MJ, MJ.data(), MJ.size()) ||
+       dev_upload(c, &c->si_MA, MA.data(), MA.size()) || dev_upload(c, &c->si_LI, LI.data(), LI.size()) ||
+       dev_upload(c, &c->si_LJ, LJ.data(), LJ.size()) || dev_upload(c, &c->si_LA, LA.data(), LA.size()) ||
+       dev_upload(c, &c->si_XI, XI.data(), XI.size()) || dev_upload(c, &c->si_XJ, XJ.data(), XJ.size()) ||
+       dev_upload(c, &c->si_XA, XA.data(), XA.size()) || dev_upload(c, &c->si_ml, ml.data(), ml.size()) ||
+       dev_upload(c, &c->si_d2c, d2c.data(), d2c.size())) { return 1; }
+   if (dev_alloc(c, &c->si_y, (size_t)N) || dev_alloc(c, &c->si_z, (size_t)N) || dev_alloc(c, &c->si_r, (size_t)N) ||
+       dev_alloc(c, &c->si_val, (size_t)N) || dev_alloc(c, &c->si_tmp, (size_t)c->N) ||
+       dev_alloc(c, &c->si_nrm, 1)) { return 1; }
+   c->si_n = N; c->si_type = si_type; c->si_param = (si_type == 1) ? 5.0 : 3.0;
+   (void)stream;
+   return 0;
+}
+
+// ComputeSmoothnessIndicator (remhos_tools.cpp:153-184) -> per DG dof: the indicator at the dof's
+// vertex, 1 on the domain boundary (the `tmp` of remhos_mono.cpp:134-135).  out may be null
+// (the values stay in the context for rmh_mono_rd).
+extern "C" int rmh_si_values(rmh_ctx *c, const double *u, double *out, void *stream)
+{
+   if (!c->si_type) { set_error("rmh_si_values: call rmh_si_setup first"); return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   const int N = c->si_n, bs = 128, nb = (N + bs - 1) / bs;
+   auto solve2 = [&](const double *rhs, double *y)      // ApproximateLaplacian: two sweeps from y = 0
+   {
+      cudaMemsetAsync(y, 0, (size_t)N * sizeof(double), s);
+      for (int it = 0; it < 2; it++)
+      {
+         k_csr_spmv<<<nb, bs, 0, s>>>(N, c->si_MI, c->si_MJ, c->si_MA, y, rhs, c->si_z);
+         k_sum_sq<<<1, 1024, 0, s>>>(N, c->si_z, c->si_nrm);
+         k_si_sweep<<<nb, bs, 0, s>>>(N, c->si_z, c->si_ml, c->si_nrm, y);
+      }
+   };
+   // u at the lattice points = u (ShapeEval is the identity for order 1), rhs = MassMixed u
+   k_csr_spmv<<<nb, bs, 0, s>>>(N, c->si_XI, c->si_XJ, c->si_XA, u, nullptr, c->si_r);
+   solve2(c->si_r, c->si_y);
+   k_csr_spmv<<<nb, bs, 0, s>>>(N, c->si_LI, c->si_LJ, c->si_LA, c->si_y, nullptr, c->si_r);
+   solve2(c->si_r, c->si_val);                          // g (reuses si_val as scratch ...)
+   CUDA_OK(cudaMemcpyAsync(c->si_y, c->si_val, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+   k_si_value<<<nb, bs, 0, s>>>(N, c->si_MI, c->si_MJ, c->si_y, c->si_type, c->si_param, c->si_val);
+   k_si_gather<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->N, c->si_d2c, c->si_val, c->si_tmp);
+   LAUNCH_OK();
+   if (out) { CUDA_OK(cudaMemcpyAsync(out, c->si_tmp, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
+   return 0;
+}
+
 // MonolithicSolver set-up (remhos.cpp:997-1011): the operator owns at most one monolithic solver,
 // which then takes precedence over HO/LO/FCT in rmh_mult / rmh_mult_unlimited (remhos.cpp:1687).
 extern "C" int rmh_mono_setup(rmh_ctx *c, int mono_type, int mass_lim, const double *scale_host,
@@ -2342,9 +2580,10 @@ extern "C" int rmh_mono_rd(rmh_ctx *c, const double *u, double *du, void *stream
       attr = true;
    }
    if (shb > 96 * 1024) { set_error("rmh_mono_rd: element too large for the shared-memory scratch"); return 1; }
+   if (c->si_type) { if (rmh_si_values(c, u, nullptr, stream)) { return 1; } }
    k_mono_rd<<<(unsigned)((c->ne + wpb - 1) / wpb), wpb * 32, shb, s>>>(
       fa_args(c), c->p, c->mono_type == 2 ? 1 : 0, c->mono_mass_lim, c->sub_w, c->mono_scale, u, z, xmn,
-      xmx, du);
+      xmx, c->si_type ? c->si_tmp : nullptr, du);
    LAUNCH_OK();
    return 0;
 }

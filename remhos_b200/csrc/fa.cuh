@@ -493,7 +493,8 @@ __global__ void k_lo_rd_sub(FaArgs A, int p, const double *SW, const double *u, 
 //   mass block.  z = K u (volume-only) and the per-DOF bounds are inputs.
 __global__ void k_mono_rd(FaArgs A, int p, int subcell, int mass_lim, const double *SW,
                           const double *scale, const double *u, const double *z,
-                          const double *xi_min, const double *xi_max, double *du_out)
+                          const double *xi_min, const double *xi_max, const double *si_tmp,
+                          double *du_out)
 {
    extern __shared__ double sh[];
    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -514,7 +515,15 @@ __global__ void k_mono_rd(FaArgs A, int p, int subcell, int mass_lim, const doub
       const double ui = u[e * ND + j], zz = z[e * ND + j];
       const double up = xi_max[e * ND + j] - ui, dn = ui - xi_min[e * ND + j];
       const double gap = fmin(up, dn);
-      const double al = fmin(1.0, beta * gap / (fmax(up, dn) + eps));
+      double al = fmin(1.0, beta * gap / (fmax(up, dn) + eps));
+      if (si_tmp)                                                // remhos_mono.cpp:132-153
+      {
+         const double tmp = si_tmp[e * ND + j], lo = xi_min[e * ND + j], hi = xi_max[e * ND + j];
+         const double bndN = fmax(0.0, tmp * (2.0 * ui - hi) + (1.0 - tmp) * lo);
+         const double bndP = fmin(1.0, tmp * (2.0 * ui - lo) + (1.0 - tmp) * hi);
+         if (lo + hi > 2.0 * ui + eps) { al = fmin(1.0, beta * (ui - bndN) / (hi - ui + eps)); }
+         else if (lo + hi < 2.0 * ui - eps) { al = fmin(1.0, beta * (bndP - ui) / (ui - lo + eps)); }
+      }
       U[j] = ui; GAP[j] = gap; AL[j] = al; MI[j] = 0.0;
       DU[j] = al * zz; ZR[j] = zz - al * zz; D[j] = zz;
       xmax = fmax(xmax, ui); xmin = fmin(xmin, ui); xsum += ui;
@@ -650,8 +659,16 @@ __global__ void k_mono_rd(FaArgs A, int p, int subcell, int mass_lim, const doub
             double s = 0.0;
             for (int j = ND - 1; j >= 0; j--) { s += Me[(size_t)i * ND + j] * (udi - UD[j]); }
             const double diff = D[i] - DU[i];
-            s += fmin(1.0, fabs(s) / (fabs(diff) + eps)) * diff;
-            s *= fmin(1.0, beta * sck * GAP[i] / (fmax(udmax - udi, udi - udmin) + eps));
+            const double tmp = si_tmp ? si_tmp[e * ND + i] : 0.0;
+            s += fmin(1.0, fmax(tmp, fabs(s) / (fabs(diff) + eps))) * diff;
+            const double den = fmax(udmax - udi, udi - udmin) + eps;
+            double al = fmin(1.0, beta * sck * GAP[i] / den);
+            if (si_tmp)                                          // remhos_mono.cpp:316-324
+            {
+               const double aglob = fmin(1.0, beta * sck * fmin(1.0 - U[i], U[i] - 0.0) / den);
+               al = fmin(fmax(tmp, al), aglob);
+            }
+            s *= al;
             mi[q] = s;
             MP += fmax(0.0, s); MN += fmin(0.0, s);
          }
@@ -673,6 +690,68 @@ __global__ void k_mono_rd(FaArgs A, int p, int subcell, int mass_lim, const doub
       }
    }
    for (int j = lane; j < ND; j += 32) { du_out[e * ND + j] = (DU[j] + MI[j]) / A.ml[e * ND + j]; }
+}
+
+// ---- SmoothnessIndicator (remhos_tools.cpp:24-354) on device: sparse H1 operators in CSR
+// y = A x - sub (sub may be null)
+__global__ void k_csr_spmv(int n, const int32_t *I, const int32_t *J, const double *A, const double *x,
+                           const double *sub, double *y)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   double s = 0.0;
+   for (int k = I[i]; k < I[i + 1]; k++) { s += A[k] * x[J[k]]; }
+   y[i] = sub ? s - sub[i] : s;
+}
+// out[0] = sum x_i^2 (one block; the H1 spaces of the meshes this runs on are small)
+__global__ void k_sum_sq(int n, const double *x, double *out)
+{
+   __shared__ double sh[32];
+   double s = 0.0;
+   for (int i = threadIdx.x; i < n; i += blockDim.x) { s += x[i] * x[i]; }
+   s = warp_sum(s);
+   if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = s; }
+   __syncthreads();
+   if (threadIdx.x < 32)
+   {
+      s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+      s = warp_sum(s);
+      if (threadIdx.x == 0) { out[0] = s; }
+   }
+}
+// one sweep of the truncated Neumann series (ApproximateLaplacian, :261-287): z = M y - rhs is
+// given; the reference leaves the loop when |z|_2 <= 1e-10
+__global__ void k_si_sweep(int n, const double *z, const double *ml, const double *nrm2, double *y)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   if (sqrt(nrm2[0]) <= 1.0e-10) { return; }
+   y[i] -= z[i] / ml[i];
+}
+// min / max of g over the sparsity pattern of the H1 mass matrix, then the indicator (:153-184)
+__global__ void k_si_value(int n, const int32_t *I, const int32_t *J, const double *g, int type,
+                           double param, double *si)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   double gmin = INFINITY, gmax = -INFINITY;
+   for (int k = I[i]; k < I[i + 1]; k++) { const double v = g[J[k]]; gmin = fmin(gmin, v); gmax = fmax(gmax, v); }
+   if (type == 1)
+   {
+      const double eps = 1.0e-50;
+      si[i] = 1.0 - pow((fabs(gmin - gmax) + eps) / (fabs(gmin) + fabs(gmax) + eps), param);
+   }
+   else
+   {
+      const double eps = 1.0e-15;
+      si[i] = fmin(1.0, param * fmax(0.0, gmin * gmax) / (fmax(gmin * gmin, gmax * gmax) + eps));
+   }
+}
+// per DG dof: the indicator at its H1 dof, 1 on the domain boundary (DG2CG < 0)
+__global__ void k_si_gather(int64_t n, const int32_t *d2c, const double *si, double *tmp)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { tmp[i] = (d2c[i] < 0) ? 1.0 : si[d2c[i]]; }
 }
 
 // ---- FluxBasedFCT (Zalesak), gather form: every DOF visits all its couplings of K_HO

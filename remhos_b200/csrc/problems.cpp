@@ -308,6 +308,49 @@ extern "C" int rmh_mesh_eval(const rmh_mesh *m, int npts, const double *pts1d, i
 }
 
 // CFL time step estimate (remhos.cpp:538-553): min_e 0.25 * |det J(center)|^(1/dim) / |v(center)|
+// inflow_gf (remhos.cpp:625-636): the inflow function in the order-p Bernstein DG space,
+// [ne][(p+1)^dim].  ProjectCoefficient on a positive basis samples at the lattice points i/p;
+// problem 7 ("Convergence test: use high order projection") interpolates at the tensor
+// Gauss-Legendre points instead and takes the Bernstein coefficients of that polynomial.
+extern "C" int rmh_inflow_project(const rmh_mesh *m, int problem, int order, double *infl_out)
+{
+   const int dim = rmh_mesh_dim(m), n1 = order + 1;
+   const int64_t ne = rmh_mesh_ne(m);
+   int nd = 1;
+   for (int a = 0; a < dim; a++) { nd *= n1; }
+   std::vector<double> pts1(n1), w1(n1);
+   const bool ho = (problem == 7);
+   if (ho) { gauss_legendre_01(n1, pts1, w1); }
+   else { for (int i = 0; i < n1; i++) { pts1[i] = order > 0 ? (double)i / order : 0.5; } }
+   std::vector<double> x((size_t)ne * nd * dim), v((size_t)ne * nd);
+   if (rmh_mesh_eval(m, n1, pts1.data(), -1, x.data())) { return 1; }
+   rmh_inflow(problem, dim, ne * nd, x.data(), v.data());
+   if (!ho) { std::copy(v.begin(), v.end(), infl_out); return 0; }
+   // coefficients = (Bernstein values at the Gauss points)^-1 applied along every axis
+   const std::vector<double> V = bernstein(order, pts1);          // [point][basis]
+   const std::vector<double> Vinv = invert_small(V, n1);          // [basis][point]
+#pragma omp parallel for
+   for (int64_t e = 0; e < ne; e++)
+   {
+      std::vector<double> a(v.begin() + e * nd, v.begin() + (e + 1) * nd), b(nd);
+      int stride = 1;
+      for (int ax = 0; ax < dim; ax++)
+      {
+         for (int i = 0; i < nd; i++)
+         {
+            const int k = (i / stride) % n1, base = i - k * stride;
+            double s = 0.0;
+            for (int g = 0; g < n1; g++) { s += Vinv[k * n1 + g] * a[base + g * stride]; }
+            b[i] = s;
+         }
+         a.swap(b);
+         stride *= n1;
+      }
+      std::copy(a.begin(), a.end(), infl_out + e * nd);
+   }
+   return 0;
+}
+
 // Mesh::GetElementSize(e) (type 0): |det J at the element centre|^(1/dim), as used by the CFL
 // estimate (remhos.cpp:544) and by MonoRDSolver's scale (remhos_mono.cpp:55)
 extern "C" int rmh_mesh_elem_sizes(const rmh_mesh *m, double *h_out)

@@ -149,7 +149,7 @@ ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int orde
    for (int i = 0; i <= order; i++) { lp[i] = (double)i / std::max(order, 1); }
    std::vector<double> xdof((size_t)ne * nd * dim), infl((size_t)ne * nd);
    Check(rmh_mesh_eval(m, order + 1, lp.data(), -1, xdof.data()));
-   Check(rmh_inflow(problem, dim, (int64_t)ne * nd, xdof.data(), infl.data()));
+   Check(rmh_inflow_project(m, problem, order, infl.data()));              // remhos.cpp:625-636
    rmh_desc d;
    std::memset(&d, 0, sizeof(d));
    d.dim = dim; d.order = order; d.mesh_order = mesh_order; d.exec_mode = exec_mode;
@@ -262,10 +262,25 @@ void SetupSubcells(ParFiniteElementSpace &space)
    space.subcells_ready = true;
 }
 
+// ---- smoothness indicator (remhos_tools.cpp:24-354)
+SmoothnessIndicator::SmoothnessIndicator(int type_id, ParFiniteElementSpace &pfes_DG)
+   : pfes(pfes_DG), type(type_id)
+{
+   Verify(type_id == 1 || type_id == 2, "Bad smoothness indicator id!");
+   Check(rmh_si_setup(pfes.ctx, type_id, nullptr));
+}
+SmoothnessIndicator::~SmoothnessIndicator() { rmh_si_setup(pfes.ctx, 0, nullptr); }
+void SmoothnessIndicator::ComputeSmoothnessIndicator(const Vector &u, Vector &si_vals_u) const
+{
+   Check(rmh_si_values(pfes.ctx, u.Read(), si_vals_u.Write(), nullptr));
+}
+
 // ---- monolithic solver (remhos_mono.cpp)
-MonoRDSolver::MonoRDSolver(ParFiniteElementSpace &space, bool subcell, bool timedep, bool masslim)
+MonoRDSolver::MonoRDSolver(ParFiniteElementSpace &space, SmoothnessIndicator *si, bool subcell,
+                           bool timedep, bool masslim)
    : MonolithicSolver(space), subcell_scheme(subcell), time_dep(timedep), mass_lim(masslim)
 {
+   (void)si;      // the indicator, if any, is already registered with the device context
    // scale(e) = vmax / (2 sqrt(dim) h_e / order), vmax over the element quadrature rule of order
    // OrderW + 2 p + 2 max(OrderGrad, 0) (remhos_mono.cpp:40-57); tensor elements: OrderW = dim mo - 1,
    // OrderGrad = mo (dim - 1) + p - 1, Gauss-Legendre with order/2 + 1 points per direction
@@ -614,7 +629,8 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    if (o.lo == 4) { Verify(o.order > 1, "Subcell schemes require FE order > 1."); }
    Verify(o.fct >= 0 && o.fct <= 2, "only -fct 0, 1 (FluxBased), 2 (ClipScale) are part of this build");
    Verify(!o.ps, "product remap (-ps) is not part of this build");
-   Verify(o.si == 0, "smoothness indicators (-si) are not part of this build");
+   Verify(o.si >= 0 && o.si <= 2, "Bad smoothness indicator id!");
+   if (o.si) { Verify(o.mono != 0 && o.order == 1, "smoothness indicators (-si) are built for -mono with -o 1 only"); }
    Verify(o.dtc == 0, "automatic time step control (-dtc 1) is not part of this build");
    Verify(!(o.fct == 1 && o.pa), "Flux-based FCT is not compatible with partial assembly.");   // :1088
    Verify(o.order >= 1, "order 0 disables limiting; not part of this build");
@@ -663,7 +679,10 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       // monolithic solver (remhos.cpp:997-1011)
       MonolithicSolver *mono_solver = nullptr;
       const bool mass_lim = (o.problem != 6 && o.problem != 7);
-      if (o.mono) { mono_solver = new MonoRDSolver(pfes, o.mono == 2, pfes.exec_mode == 1, mass_lim); }
+      SmoothnessIndicator *smth_indicator = nullptr;                     // remhos.cpp:905-911
+      if (o.si) { smth_indicator = new SmoothnessIndicator(o.si, pfes); }
+      if (o.mono)
+      { mono_solver = new MonoRDSolver(pfes, smth_indicator, o.mono == 2, pfes.exec_mode == 1, mass_lim); }
       AdvectionOperator adv(pfes, lumpedM, dofs, ho_solver, lo_solver, fct_solver, mono_solver);
       adv.verify_bounds = o.vb;
       double mass0_u = 0.0, u_min = 0.0, u_max = 0.0;
@@ -737,7 +756,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
             std::fclose(fp);
          }
       }
-      delete mono_solver; delete fct_solver; delete lo_solver; delete ho_solver;   // remhos.cpp:1484-1489
+      delete mono_solver; delete smth_indicator; delete fct_solver; delete lo_solver; delete ho_solver;   // remhos.cpp:1484-1489
    }
    rmh_mesh_free(mesh);
    return rc;

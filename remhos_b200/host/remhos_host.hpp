@@ -207,6 +207,19 @@ public:
    int Type() const override { return 2; }
 };
 
+// remhos_tools.hpp SmoothnessIndicator (remhos_tools.cpp:24-354; created at remhos.cpp:905-911).
+// Order-1 spaces only; the H1 operators live in the device context of the space.
+class SmoothnessIndicator
+{
+   ParFiniteElementSpace &pfes;
+   int type;
+public:
+   SmoothnessIndicator(int type_id, ParFiniteElementSpace &pfes_DG);
+   ~SmoothnessIndicator();
+   // one value per DG dof: the indicator at the dof's vertex, 1 on the domain boundary
+   void ComputeSmoothnessIndicator(const Vector &u, Vector &si_vals_u) const;
+};
+
 // remhos_mono.hpp:28-39
 class MonolithicSolver
 {
@@ -226,7 +239,8 @@ class MonoRDSolver : public MonolithicSolver
    bool subcell_scheme, time_dep, mass_lim;
 public:
    std::vector<double> scale;      // remhos_mono.cpp:40-57
-   MonoRDSolver(ParFiniteElementSpace &space, bool subcell, bool timedep, bool masslim);
+   MonoRDSolver(ParFiniteElementSpace &space, SmoothnessIndicator *si, bool subcell, bool timedep,
+                bool masslim);
    ~MonoRDSolver();
    void CalcSolution(const Vector &u, Vector &du) const override;
 };

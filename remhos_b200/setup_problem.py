@@ -88,7 +88,7 @@ class Problem:
         lat_pts = np.arange(order + 1) / max(order, 1)
         xdof = mesh_eval(mesh, lat_pts)
         infl = np.zeros(xdof.shape[0] * xdof.shape[1])
-        check(lib().rmh_inflow(int(problem), dim, C.c_int64(infl.size), _ptr(xdof), _ptr(infl)))
+        check(lib().rmh_inflow_project(mesh.h, int(problem), int(order), _ptr(infl)))   # remhos.cpp:625-636
         # the host-side inputs of the stage path (also what bench.py hands to the CPU port)
         self.inputs = dict(dim=dim, order=order, mesh_order=mesh_order, exec_mode=self.exec_mode,
                            bounds_type=bounds_type, nodes=nodes, nbr_dof=maps['nbr_dof'],

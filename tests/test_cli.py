@@ -162,3 +162,19 @@ def test_mono_flag_validation():
     assert rc == 134 and 'Verification failed' in err
     rc, _, err = run_cli('-m', 'x', '-mono', '2', '-o', '1')
     assert rc == 134 and 'Subcell schemes require' in err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('args,mass,umax', [
+    # autotest/out_baseline.dat:212-220 (= README.md runs 12, 13): the reference's known answers
+    # for the monolithic solver with smoothness indicator, steady-state stop
+    (['-m', mesh('inline-quad.mesh'), '-p', 7, '-rs', 3, '-o', 1, '-dt', 0.01, '-tf', 20, '-mono', 1,
+      '-si', 2, '-no-vis'], 0.1570667907, 0.9987771164),
+    (['-m', mesh('inline-quad.mesh'), '-p', 6, '-rs', 2, '-o', 1, '-dt', 0.01, '-tf', 20, '-mono', 1,
+      '-si', 1, '-no-vis'], 0.3182739921, 1.0)])
+def test_cli_mono_si_reproduces_reference_known_answers(args, mass, umax):
+    rc, out, err = run_cli(*args)
+    assert rc == 0, err
+    r = parse(out)
+    assert float('%.10g' % r['mass']) == mass
+    assert float('%.10g' % r['umax']) == umax

@@ -1,8 +1,9 @@
-"""GPU parity tests of the monolithic solver (MonoRDSolver, remhos_mono.cpp:60-356, `-mono 1/2`
-without a smoothness indicator) against the CPU oracle.  The oracle's restatement of this solver
-is NOT pinned by a reference number (both out_baseline.dat rows that use -mono also use -si):
-parity here is CUDA-vs-oracle plus the properties the scheme guarantees (conservation on periodic
-meshes, local bounds).
+"""GPU parity tests of the monolithic solver (MonoRDSolver, remhos_mono.cpp:60-356, `-mono 1/2`,
+with and without the smoothness indicator) against the CPU oracle, whose restatement is pinned on
+the reference's two known answers for -mono (tests/test_oracle_mono_golden.py; the GPU CLI
+reproduces them too, tests/test_cli.py).  Configurations no reference number covers (no -si,
+order > 1, subcells) are checked CUDA-vs-oracle plus the properties the scheme guarantees
+(conservation on periodic meshes, local bounds).
 
 Tolerances: one evaluation 1e-10 of the field's max norm (the fixed-point loop stops on a norm
 threshold, so a round-off sized difference may add or drop one sweep whose update is below 1e-8 of
@@ -72,4 +73,30 @@ def test_mono_run_matches_oracle(mesh, opt, bt):
     mass = ctx.reduce(0, u, m)
     assert abs(mass - run.mass0) < 1e-12 * abs(run.mass0)          # periodic: conservative
     assert ug.min() > run.u0_min - 1e-10 and ug.max() < run.u0_max + 1e-10
+    ctx.close()
+
+
+# ---- smoothness indicator (remhos_tools.cpp:24-354), order 1; the oracle's restatement is pinned on
+# both reference known answers for -mono (tests/test_oracle_mono_golden.py)
+SI_CASES = [('inline-quad.mesh', 6, 2, 1), ('inline-quad.mesh', 7, 2, 2), ('periodic-square.mesh', 5, 2, 1),
+            ('cube01_hex.mesh', 1, 1, 2)]
+
+
+@pytest.mark.parametrize('mesh,problem,rs,si', SI_CASES)
+def test_si_and_mono_with_si_match_oracle(mesh, problem, rs, si):
+    run = oracle_run(mesh, mono_type=1, si_type=si, problem=problem, rs_levels=rs, order=1, dt=0.002)
+    ctx = ctx_from_oracle(run)
+    ctx.mono_setup(1, run.opt.problem not in (6, 7), run.mono_scale)
+    ctx.si_setup(si)
+    rng = np.random.default_rng(9)
+    u = np.clip(run.u + 0.05 * rng.standard_normal(run.u.shape), 0.0, 1.0)
+    tmp = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.si_values(dev(u), tmp)
+    ref_si = run.si.dof_values(u)
+    # type 1 raises a ratio to the 5th power and type 2 divides two Laplacian-sized numbers:
+    # compare at 1e-9 absolute (values live in [0, 1])
+    assert np.abs(tmp.cpu().numpy().reshape(u.shape) - ref_si).max() < 1e-9
+    k = torch.empty_like(tmp)
+    ctx.mono_rd(dev(u), k)
+    assert rel_err(k.cpu().numpy().reshape(u.shape), run.mult(u, 0.0, run.dt)) < 1e-9
     ctx.close()

@@ -1,8 +1,7 @@
-"""CPU tests of the oracle's restatement of MonoRDSolver (remhos_mono.cpp:60-356, no smoothness
-indicator).  PARITY UNPINNED: the reference's only known answers for -mono (out_baseline.dat:212-220,
-README runs 12-13) also use -si, which is not built; what can be checked without the reference are
-the properties the scheme guarantees: conservation on periodic meshes, local bounds, consistency
-with the unlimited Galerkin operator when no limiting is active."""
+"""CPU tests of the oracle's restatement of MonoRDSolver (remhos_mono.cpp:60-356) in the
+configurations no reference number covers (no smoothness indicator, order > 1, subcells): the
+properties the scheme guarantees -- conservation on periodic meshes, local bounds, zero-sum rate.
+The pinned configurations are in tests/test_oracle_mono_golden.py."""
 import numpy as np
 import pytest
 
