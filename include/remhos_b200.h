@@ -249,6 +249,17 @@ int rmh_mono_setup(rmh_ctx *ctx, int mono_type, int mass_lim, const double *scal
 /* MonoRDSolver::CalcSolution (remhos_mono.cpp:60-356) */
 int rmh_mono_rd(rmh_ctx *ctx, const double *u_dev, double *du_dev, void *stream);
 
+/* ElementFCTProjection::CalcFCTSolution (remhos_fct.cpp:613-733; -fct 4); after rmh_fa_setup */
+int rmh_fct_project(rmh_ctx *ctx, double dt, const double *u_dev, const double *du_ho_dev,
+                    const double *du_lo_dev, const double *xi_min_dev, const double *xi_max_dev,
+                    double *du_dev, void *stream);
+/* Automatic time step control, -dtc 1 (remhos.cpp:312-316): with mode 1 every rmh_limit_mult runs
+ * AdvectionOperator::UpdateTimeStepEstimate (remhos.cpp:1968-1998) on the LO rate.  rmh_dt_ratio =
+ * GetTimeStepRatio (minimum of dt_estimate / dt since the last reset), reset != 0 =
+ * ResetTimeStepRatio; the caller repeats or grows the step as remhos.cpp:1178-1197 does. */
+int rmh_dt_control(rmh_ctx *ctx, int mode);
+int rmh_dt_ratio(rmh_ctx *ctx, int reset, double *ratio);
+
 /* FluxBasedFCT::CalcFCTSolution, one FCT iteration as the driver fixes it (remhos_fct.cpp:155-181,
  * 295-446; remhos.cpp:1093).  Needs rmh_fa_setup; single-rank meshes only. */
 int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const double *m_dev,

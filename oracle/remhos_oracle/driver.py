@@ -61,6 +61,7 @@ class Options:                       # defaults: remhos.cpp:216-244
     fct_type: int = 0
     mono_type: int = 0            # 1: MonoRDSolver, 2: with subcells (remhos.cpp:285-289)
     si_type: int = 0              # smoothness indicator (remhos.cpp:302; order 1 only here)
+    dt_control: int = 0           # -dtc 1: LO bounds error time step control (remhos.cpp:312-316)
     bounds_type: int = 0
     t_final: float = 4.0
     dt: float = 0.005
@@ -195,8 +196,12 @@ class Run:
                 du = d.fct_clip_scale(u, A.ml, du_ho, du_lo, umin, umax, dt)
             elif o.fct_type == 1:
                 du = d.fct_flux_based(u, A.ml, du_ho, du_lo, umin, umax, dt)
+            elif o.fct_type == 4:
+                du = d.fct_project(u, du_ho, du_lo, umin, umax, dt)
             else:
                 raise NotImplementedError('fct type %d' % o.fct_type)
+            if o.dt_control:                                   # remhos.cpp:1839-1842
+                self.update_dt_estimate(u, du_lo, umin, umax, dt)
             if o.verify_bounds:
                 self.check(u, dt, du, umin, umax, 'FCT')
             return du
@@ -208,6 +213,16 @@ class Run:
         if self.opt.ho_type == 1:
             return self.disc.ho_neumann(u)
         return self.disc.ho_local_inverse(u)                  # -ho 3, and -ho 2 (CG to 1e-12)
+
+    def update_dt_estimate(self, x, dx, x_min, x_max, dt_cur):
+        """AdvectionOperator::UpdateTimeStepEstimate (remhos.cpp:1968-1998)"""
+        eps = 1e-12
+        with np.errstate(divide='ignore', invalid='ignore'):
+            up = np.where(dx > eps, (x_max - x) / dx, np.inf)
+            dn = np.where(dx < -eps, (x_min - x) / dx, np.inf)
+        dt = float(min(up.min(), dn.min()))
+        self.dt_est = min(getattr(self, 'dt_est', np.inf), dt)
+        self.dt_ratio = min(getattr(self, 'dt_ratio', np.inf), dt / dt_cur if dt_cur != 0.0 else 0.0)
 
     def mult_unlimited(self, u, t, dt):
         """AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739)."""
@@ -380,11 +395,23 @@ class Run:
         res = u.copy()
         ml0 = self.disc.cur.ml
         self.residual = 0.0
+        self.repeats = 0
         while not done:
             dt_real = min(dt, self.t_final - t)
+            self.dt_est = np.inf; self.dt_ratio = np.inf       # ResetTimeStepRatio
+            u_old = u
             u = self.step(u, t, dt_real)
             t += dt_real
             ti += 1
+            if o.dt_control:                                   # remhos.cpp:1178-1197
+                if self.dt_ratio < 1.0:
+                    ti -= 1; t -= dt_real; u = u_old
+                    dt = 0.85 * dt
+                    self.repeats += 1
+                    assert dt >= 1e-12, 'The time step crashed!'
+                    continue
+                elif self.dt_ratio > 1.25:
+                    dt *= 1.02
             done = t >= self.t_final - 1e-8 * dt
             if steady:                                         # :1263-1290
                 self.residual = float(np.sqrt((((ml0 * u) / dt - (ml0 * res) / dt) ** 2).sum()))

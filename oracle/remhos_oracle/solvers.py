@@ -357,6 +357,33 @@ class Discretization:
             f = np.where((new_mass < -eps)[:, None], fneg, f)
         return du_lo + f / m
 
+    def fct_project(self, u, du_ho, du_lo, umin, umax, dt):
+        """ElementFCTProjection::CalcFCTSolution (remhos_fct.cpp:613-733): element-local Zalesak
+        limiter on the fluxes F_ij = M_ij (du_i - du_j) + (beta_j z_i - beta_i z_j), beta = M_L / sum M_L,
+        z = M du_HO - M_L du_LO, started from the LO rate."""
+        A = self.cur
+        M = A.M
+        ML = M.sum(axis=2)
+        rhs = np.einsum('eij,ej->ei', M, du_ho)
+        beta = ML / ML.sum(axis=1)[:, None]
+        z = rhs - ML * du_lo
+        F = M * (du_ho[:, :, None] - du_ho[:, None, :]) + \
+            (beta[:, None, :] * z[:, :, None] - beta[:, :, None] * z[:, None, :])
+        idx = np.arange(M.shape[1])
+        F[:, idx, idx] = 0.0
+        sp_ = np.maximum(0.0, F).sum(axis=2)
+        sm_ = np.minimum(0.0, F).sum(axis=2)
+        du_max = (umax - u) / dt
+        du_min = (umin - u) / dt
+        rp = np.maximum(ML * (du_max - du_lo), 0.0)
+        rm = np.minimum(ML * (du_min - du_lo), 0.0)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            gp = np.where(rp < sp_, rp / sp_, 1.0)
+            gm = np.where(rm > sm_, rm / sm_, 1.0)
+        a = np.where(F >= 0.0, np.minimum(gp[:, :, None], gm[:, None, :]),
+                     np.minimum(gm[:, :, None], gp[:, None, :]))
+        return du_lo + (a * F).sum(axis=2) / ML
+
     def build_sparse_K_HO(self):
         """Upper-triangular coupling list of K_HO (volume blocks + face blocks) for the
         flux-based FCT: arrays (I, J, kij, kji, same_elem, Mij)."""

@@ -276,6 +276,18 @@ class Context:
     def lo_res_dist_subcell(self, u, du_lo, s=0):
         check(lib().rmh_lo_res_dist_subcell(self.h, _dp(u), _dp(du_lo), C.c_void_p(s)))
 
+    def fct_project(self, dt, u, du_ho, du_lo, xmin, xmax, du, s=0):
+        check(lib().rmh_fct_project(self.h, C.c_double(dt), _dp(u), _dp(du_ho), _dp(du_lo), _dp(xmin),
+                                    _dp(xmax), _dp(du), C.c_void_p(s)))
+
+    def dt_control(self, mode):
+        check(lib().rmh_dt_control(self.h, int(mode)))
+
+    def dt_ratio(self, reset=False):
+        r = C.c_double(0.0)
+        check(lib().rmh_dt_ratio(self.h, int(bool(reset)), C.byref(r)))
+        return r.value
+
     def mono_setup(self, mono_type, mass_lim, scale, s=0):
         scale = np.ascontiguousarray(scale, dtype=np.float64) if scale is not None else None
         check(lib().rmh_mono_setup(self.h, int(mono_type), int(bool(mass_lim)), _ptr(scale),

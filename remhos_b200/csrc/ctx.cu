@@ -74,6 +74,7 @@ struct rmh_ctx
    int32_t n_ent = 0;
    double *ent_mm = nullptr;   // [n_ent][2] (min, max) over the elements sharing the entity
    double *xe_min = nullptr, *xe_max = nullptr;
+   double2 *xe_mm = nullptr;  // interleaved copy for the entity pass
    int num_sms = 0;
    bool pipelined = true;      // RMH_NO_PIPELINE=1 selects the one-batch-per-block stage kernel
    bool tensor = true;         // RMH_NO_TENSOR=1 selects the DFMA pipelined kernel
@@ -94,6 +95,8 @@ struct rmh_ctx
            *si_XJ = nullptr, *si_d2c = nullptr;
    double *si_MA = nullptr, *si_LA = nullptr, *si_XA = nullptr, *si_ml = nullptr, *si_y = nullptr,
           *si_z = nullptr, *si_r = nullptr, *si_val = nullptr, *si_tmp = nullptr, *si_nrm = nullptr;
+   int dt_control = 0;        // rmh_dt_control: 1 = LO bounds error (remhos.cpp:312-316)
+   double *dt_ratio = nullptr;   // device scalar, min over the LimitMult calls since the last reset
    int mono_type = 0;         // rmh_mono_setup: 1 MonoRDSolver, 2 with subcells; 0 none
    int mono_mass_lim = 1;
    double *mono_scale = nullptr;   // [ne] (remhos_mono.cpp:40-57)
@@ -865,8 +868,15 @@ static void launch_elem_min_max(int64_t ne, int nd, const double *u, double *xe_
 }
 
 // entity min/max over the elements sharing the entity (CG-dof overlap, remhos_tools.cpp:449-458)
+// (min, max) pairs of the elements as one 16-byte word each: the entity pass below is bound by the
+// number of gathered words (l1tex 86 %, profiles/r01/ncu_ent_min_max_v12_rs5.txt), not by bytes
+__global__ void k_xe_interleave(int64_t n, const double *xe_min, const double *xe_max, double2 *xe_mm)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { xe_mm[i] = make_double2(xe_min[i], xe_max[i]); }
+}
 __global__ void k_ent_min_max(int32_t n_ent, const int32_t *list, const int32_t *off, const int32_t *el,
-                              const double *xe_min, const double *xe_max, double *ent_mm)
+                              const double2 *__restrict__ xe_mm, double *ent_mm)
 {
    const int t = blockIdx.x * blockDim.x + threadIdx.x;
    if (t >= n_ent) { return; }
@@ -877,17 +887,13 @@ __global__ void k_ent_min_max(int32_t n_ent, const int32_t *list, const int32_t 
    for (int k = off[i]; k < k1; k += 4)
    {
       int id[4];
-      double a[4], b[4];
+      double2 v[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) { id[q] = (k + q < k1) ? el[k + q] : -1; }
 #pragma unroll
-      for (int q = 0; q < 4; q++)
-      {
-         a[q] = (id[q] >= 0) ? xe_min[id[q]] : INFINITY;
-         b[q] = (id[q] >= 0) ? xe_max[id[q]] : -INFINITY;
-      }
+      for (int q = 0; q < 4; q++) { v[q] = (id[q] >= 0) ? xe_mm[id[q]] : make_double2(INFINITY, -INFINITY); }
 #pragma unroll
-      for (int q = 0; q < 4; q++) { mn = a[q] < mn ? a[q] : mn; mx = b[q] > mx ? b[q] : mx; }
+      for (int q = 0; q < 4; q++) { mn = v[q].x < mn ? v[q].x : mn; mx = v[q].y > mx ? v[q].y : mx; }
    }
    *reinterpret_cast<double2 *>(ent_mm + 2 * (size_t)i) = make_double2(mn, mx);
 }
@@ -1709,6 +1715,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    const int64_t ne_all = c->ne + c->ne_ghost;
    if (dev_alloc(c, &c->xe_min, (size_t)ne_all)) { return fail(); }
    if (dev_alloc(c, &c->xe_max, (size_t)ne_all)) { return fail(); }
+   if (dev_alloc(c, &c->xe_mm, (size_t)ne_all)) { return fail(); }
    if (c->bounds_type == 0)
    {
       if (!d->lat || d->n_ent <= 0) { set_error("bounds_type 0 needs desc.lat / n_ent"); return fail(); }
@@ -1898,8 +1905,10 @@ extern "C" int rmh_bounds(rmh_ctx *c, const double *xe_min, const double *xe_max
    const int bs = 256;
    if (c->bounds_type == 0)
    {
-      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, nullptr, c->ent_off, c->ent_el, xe_min,
-                                                            xe_max, c->ent_mm);
+      const int64_t na = c->ne + c->ne_ghost;
+      k_xe_interleave<<<(unsigned)((na + bs - 1) / bs), bs, 0, s>>>(na, xe_min, xe_max, c->xe_mm);
+      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, nullptr, c->ent_off, c->ent_el, c->xe_mm,
+                                                            c->ent_mm);
       LAUNCH_OK();
       k_bounds_overlap<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(
          c->ne, c->dim, c->D1, c->ND, c->N3, c->lat, c->ent_mm, xi_min, xi_max);
@@ -1983,9 +1992,15 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       const int n0 = (part == 2) ? c->n_ent_int : 0, n1 = (part == 1) ? c->n_ent_int : c->n_ent;
       if (n1 > n0)
       {
+         // part 1 interleaves the owned elements, part 2 the ghosts (installed by rmh_halo_set since)
+         const int64_t i0 = (part == 2) ? c->ne : 0, i1 = (part == 1) ? c->ne : c->ne + c->ne_ghost;
+         if (i1 > i0)
+         {
+            k_xe_interleave<<<(unsigned)((i1 - i0 + bs - 1) / bs), bs, 0, s>>>(i1 - i0, c->xe_min + i0,
+                                                                                c->xe_max + i0, c->xe_mm + i0);
+         }
          k_ent_min_max<<<(n1 - n0 + bs - 1) / bs, bs, 0, s>>>(n1 - n0, part ? c->ent_list + n0 : nullptr,
-                                                              c->ent_off, c->ent_el, c->xe_min, c->xe_max,
-                                                              c->ent_mm);
+                                                              c->ent_off, c->ent_el, c->xe_mm, c->ent_mm);
          LAUNCH_OK();
       }
    }
@@ -2537,6 +2552,49 @@ extern "C" int rmh_si_values(rmh_ctx *c, const double *u, double *out, void *str
    return 0;
 }
 
+// ElementFCTProjection::CalcFCTSolution (remhos_fct.cpp:613-733); dense element mass blocks
+extern "C" int rmh_fct_project(rmh_ctx *c, double dt, const double *u, const double *du_ho,
+                               const double *du_lo, const double *xi_min, const double *xi_max,
+                               double *du, void *stream)
+{
+   if (!c->fa_on) { set_error("rmh_fct_project: call rmh_fa_setup first (assembled element mass)"); return 1; }
+   const int wpb = 2;
+   const size_t shb = (size_t)wpb * 6 * c->ND * sizeof(double);
+   k_fct_project<<<(unsigned)((c->ne + wpb - 1) / wpb), wpb * 32, shb, (cudaStream_t)stream>>>(
+      fa_args(c), dt, u, du_ho, du_lo, xi_min, xi_max, du);
+   LAUNCH_OK();
+   return 0;
+}
+
+// automatic time step control (remhos.cpp:312-316, 1153-1154, 1178-1197).  mode 1: every
+// rmh_limit_mult lowers the ratio dt_estimate / dt (UpdateTimeStepEstimate on the LO rate).
+// rmh_dt_ratio returns the minimum since the last reset (GetTimeStepRatio) and, with reset != 0,
+// starts over (ResetTimeStepRatio); it synchronises the device.
+extern "C" int rmh_dt_control(rmh_ctx *c, int mode)
+{
+   if (mode != 0 && mode != 1) { set_error("rmh_dt_control: mode must be 0 (fixed) or 1 (LO bounds error)"); return 1; }
+   if (mode && !c->dt_ratio)
+   {
+      if (dev_alloc(c, &c->dt_ratio, 1)) { return 1; }
+      const double inf = INFINITY;
+      CUDA_OK(cudaMemcpy(c->dt_ratio, &inf, sizeof(double), cudaMemcpyHostToDevice));
+   }
+   c->dt_control = mode;
+   return 0;
+}
+extern "C" int rmh_dt_ratio(rmh_ctx *c, int reset, double *ratio)
+{
+   if (!c->dt_ratio) { set_error("rmh_dt_ratio: call rmh_dt_control first"); return 1; }
+   CUDA_OK(cudaDeviceSynchronize());
+   if (ratio) { CUDA_OK(cudaMemcpy(ratio, c->dt_ratio, sizeof(double), cudaMemcpyDeviceToHost)); }
+   if (reset)
+   {
+      const double inf = INFINITY;
+      CUDA_OK(cudaMemcpy(c->dt_ratio, &inf, sizeof(double), cudaMemcpyHostToDevice));
+   }
+   return 0;
+}
+
 // MonolithicSolver set-up (remhos.cpp:997-1011): the operator owns at most one monolithic solver,
 // which then takes precedence over HO/LO/FCT in rmh_mult / rmh_mult_unlimited (remhos.cpp:1687).
 extern "C" int rmh_mono_setup(rmh_ctx *c, int mono_type, int mass_lim, const double *scale_host,
@@ -2614,8 +2672,8 @@ static int check_combo(int ho_type, int lo_type, int fct_type)
    { set_error("stage operator: HO solver must be 0, 1 (Neumann) or 3 (LocalInverse)"); return 1; }
    if (lo_type < 0 || lo_type > 5)
    { set_error("stage operator: LO solver must be 0 .. 5"); return 1; }
-   if (fct_type < 0 || fct_type > 2)
-   { set_error("stage operator: FCT solver must be 0, 1 (FluxBased) or 2 (ClipScale)"); return 1; }
+   if (fct_type < 0 || fct_type > 4 || fct_type == 3)
+   { set_error("stage operator: FCT solver must be 0, 1 (FluxBased), 2 (ClipScale) or 4 (FCTProject)"); return 1; }
    if (fct_type && (ho_type == 0 || lo_type == 0))
    { set_error("FCT requires HO and LO solvers."); return 1; }        // remhos.cpp:1690
    if (!fct_type && lo_type == 5 && ho_type == 0)
@@ -2672,8 +2730,19 @@ extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, 
    else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
    if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
    if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
-   if (fct_type == 2) { return rmh_fct_clip_scale(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
-   return rmh_fct_flux_based(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream);
+   int rc;
+   if (fct_type == 2) { rc = rmh_fct_clip_scale(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
+   else if (fct_type == 4) { rc = rmh_fct_project(c, dt, u, du_ho, du_lo, xmn, xmx, k, stream); }
+   else { rc = rmh_fct_flux_based(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
+   if (rc) { return rc; }
+   if (c->dt_control)                                         // remhos.cpp:1839-1842
+   {
+      const int bs = 256;
+      k_dt_estimate<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(c->N, dt, u, du_lo, xmn,
+                                                                                       xmx, c->dt_ratio);
+      LAUNCH_OK();
+   }
+   return 0;
 }
 
 // LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult (remhos_solvers.hpp:46-50);

@@ -692,6 +692,94 @@ __global__ void k_mono_rd(FaArgs A, int p, int subcell, int mass_lim, const doub
    for (int j = lane; j < ND; j += 32) { du_out[e * ND + j] = (DU[j] + MI[j]) / A.ml[e * ND + j]; }
 }
 
+// ---- ElementFCTProjection::CalcFCTSolution (remhos_fct.cpp:613-733): element-local Zalesak
+// limiter on F_ij = M_ij (du_i - du_j) + (beta_j z_i - beta_i z_j), beta = M_L / sum M_L,
+// z = M du_HO - M_L du_LO, started from the LO rate.  One warp per element; the fluxes are
+// re-evaluated from both ends with identical operands, so F_ji = -F_ij bit for bit.
+__global__ void k_fct_project(FaArgs A, double dt, const double *u, const double *du_ho,
+                              const double *du_lo, const double *xi_min, const double *xi_max,
+                              double *du)
+{
+   extern __shared__ double sh[];
+   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+   const int64_t e = (int64_t)blockIdx.x * wpb + wib;
+   const int ND = A.ND;
+   double *DH = sh + (size_t)wib * 6 * ND, *Z = DH + ND, *BE = Z + ND, *ML = BE + ND, *GP = ML + ND, *GM = GP + ND;
+   if (e >= A.ne) { return; }
+   const double *Me = A.M + (size_t)e * ND * ND;
+   for (int j = lane; j < ND; j += 32) { DH[j] = du_ho[e * ND + j]; }
+   __syncwarp();
+   double mls = 0.0;
+   for (int i = lane; i < ND; i += 32)
+   {
+      double rhs = 0.0, ml = 0.0;
+      for (int j = 0; j < ND; j++) { rhs += Me[(size_t)i * ND + j] * DH[j]; ml += Me[(size_t)i * ND + j]; }
+      ML[i] = ml; Z[i] = rhs - ml * du_lo[e * ND + i];
+      mls += ml;
+   }
+   mls = warp_sum(mls);
+   __syncwarp();
+   for (int i = lane; i < ND; i += 32) { BE[i] = ML[i] / mls; }
+   __syncwarp();
+   auto flux = [&](int i, int j)
+   { return Me[(size_t)i * ND + j] * (DH[i] - DH[j]) + (BE[j] * Z[i] - BE[i] * Z[j]); };
+   for (int i = lane; i < ND; i += 32)
+   {
+      double sp = 0.0, sm = 0.0;
+      for (int j = 0; j < ND; j++)
+      {
+         if (j == i) { continue; }
+         const double f = flux(i, j);
+         sp += fmax(0.0, f); sm += fmin(0.0, f);
+      }
+      const double ui = u[e * ND + i], dlo = du_lo[e * ND + i];
+      const double rp = fmax(ML[i] * ((xi_max[e * ND + i] - ui) / dt - dlo), 0.0);
+      const double rm = fmin(ML[i] * ((xi_min[e * ND + i] - ui) / dt - dlo), 0.0);
+      GP[i] = (rp < sp) ? rp / sp : 1.0;
+      GM[i] = (rm > sm) ? rm / sm : 1.0;
+   }
+   __syncwarp();
+   for (int i = lane; i < ND; i += 32)
+   {
+      double acc = 0.0;
+      for (int j = 0; j < ND; j++)
+      {
+         if (j == i) { continue; }
+         const double f = flux(i, j);
+         const double a = (f >= 0.0) ? fmin(GP[i], GM[j]) : fmin(GM[i], GP[j]);
+         acc += a * f;
+      }
+      du[e * ND + i] = du_lo[e * ND + i] + acc / ML[i];
+   }
+}
+
+// AdvectionOperator::UpdateTimeStepEstimate (remhos.cpp:1968-1998): ratio <- min(ratio, dt_est / dt)
+__global__ void k_dt_estimate(int64_t n, double dt, const double *x, const double *dx,
+                              const double *x_min, const double *x_max, double *ratio)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   double r = INFINITY;
+   if (i < n)
+   {
+      const double d = dx[i];
+      if (d > 1e-12) { r = (x_max[i] - x[i]) / d; }
+      else if (d < -1e-12) { r = (x_min[i] - x[i]) / d; }
+   }
+   r = warp_min(r);
+   if ((threadIdx.x & 31) == 0 && r < INFINITY)
+   {
+      r = (dt != 0.0) ? r / dt : 0.0;
+      unsigned long long *p = reinterpret_cast<unsigned long long *>(ratio);
+      unsigned long long old = *p;
+      while (__longlong_as_double((long long)old) > r)
+      {
+         const unsigned long long prev = atomicCAS(p, old, (unsigned long long)__double_as_longlong(r));
+         if (prev == old) { break; }
+         old = prev;
+      }
+   }
+}
+
 // ---- SmoothnessIndicator (remhos_tools.cpp:24-354) on device: sparse H1 operators in CSR
 // y = A x - sub (sub may be null)
 __global__ void k_csr_spmv(int n, const int32_t *I, const int32_t *J, const double *A, const double *x,

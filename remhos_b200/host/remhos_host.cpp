@@ -348,6 +348,19 @@ void FluxBasedFCT::CalcFCTSolution(const Vector &u, const Vector &m, const Vecto
    Check(rmh_fct_flux_based(pfes.ctx, dt, u.Read(), m.Read(), du_ho.Read(), du_lo.Read(),
                             u_min.Read(), u_max.Read(), du.Write(), nullptr));
 }
+ElementFCTProjection::ElementFCTProjection(ParFiniteElementSpace &space, double dt_)
+   : FCTSolver(space, dt_)
+{
+   Check(rmh_fa_setup(space.ctx, nullptr));      // dense element mass blocks
+}
+void ElementFCTProjection::CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho,
+                                           const Vector &du_lo, const Vector &u_min,
+                                           const Vector &u_max, Vector &du) const
+{
+   (void)m;                                       // the solver lumps its own element mass (remhos_fct.cpp:650)
+   Check(rmh_fct_project(pfes.ctx, dt, u.Read(), du_ho.Read(), du_lo.Read(), u_min.Read(), u_max.Read(),
+                         du.Write(), nullptr));
+}
 void ClipScaleSolver::CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho,
                                       const Vector &du_lo, const Vector &u_min, const Vector &u_max,
                                       Vector &du) const
@@ -627,11 +640,14 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    Verify(!(o.ho == 1 && o.pa), "PA for DG is not supported for Neummann Solver.");   // remhos_ho.cpp:138-139
    Verify(o.lo >= 0 && o.lo <= 5, "LO solver type must be 0 .. 5");
    if (o.lo == 4) { Verify(o.order > 1, "Subcell schemes require FE order > 1."); }
-   Verify(o.fct >= 0 && o.fct <= 2, "only -fct 0, 1 (FluxBased), 2 (ClipScale) are part of this build");
+   Verify(o.fct >= 0 && o.fct <= 4 && o.fct != 3,
+          "only -fct 0, 1 (FluxBased), 2 (ClipScale), 4 (FCTProject) are part of this build");
+   Verify(!(o.fct == 4 && o.pa), "FCTProject needs the assembled element mass (no -pa).");
    Verify(!o.ps, "product remap (-ps) is not part of this build");
    Verify(o.si >= 0 && o.si <= 2, "Bad smoothness indicator id!");
    if (o.si) { Verify(o.mono != 0 && o.order == 1, "smoothness indicators (-si) are built for -mono with -o 1 only"); }
-   Verify(o.dtc == 0, "automatic time step control (-dtc 1) is not part of this build");
+   Verify(o.dtc == 0 || o.dtc == 1, "time step control must be 0 (fixed) or 1 (LO bounds error)");
+   if (o.dtc) { Verify(o.fct != 0 && !o.vb, "-dtc 1 needs an FCT solver (and no -vb) in this build"); }
    Verify(!(o.fct == 1 && o.pa), "Flux-based FCT is not compatible with partial assembly.");   // :1088
    Verify(o.order >= 1, "order 0 disables limiting; not part of this build");
    if (o.fct) { Verify(o.ho && o.lo, "FCT requires HO and LO solvers."); }     // :1690
@@ -676,6 +692,8 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       FCTSolver *fct_solver = nullptr;
       if (o.fct == 1) { fct_solver = new FluxBasedFCT(pfes, dt); }
       else if (o.fct == 2) { fct_solver = new ClipScaleSolver(pfes, dt); }
+      else if (o.fct == 4) { fct_solver = new ElementFCTProjection(pfes, dt); }
+      if (o.dtc) { Check(rmh_dt_control(pfes.ctx, 1)); }
       // monolithic solver (remhos.cpp:997-1011)
       MonolithicSolver *mono_solver = nullptr;
       const bool mass_lim = (o.problem != 6 && o.problem != 7);
@@ -706,8 +724,25 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       {
          double dt_real = std::min(dt, t_final - t);
          adv.SetDt(dt_real);
+         Vector *u_old = o.dtc ? new Vector(u) : nullptr;             // Sold = S (remhos.cpp:1173)
+         if (o.dtc) { Check(rmh_dt_ratio(pfes.ctx, 1, nullptr)); }    // ResetTimeStepRatio
          ode_solver.Step(u, t, dt_real);
          ti++;
+         if (o.dtc)                                                    // remhos.cpp:1178-1197
+         {
+            double dt_ratio = 0.0;
+            Check(rmh_dt_ratio(pfes.ctx, 0, &dt_ratio));
+            if (dt_ratio < 1.)
+            {
+               std::cout << "Repeat / decrease dt: " << dt_real << " --> " << 0.85 * dt << std::endl;
+               ti--; t -= dt_real; u = *u_old; dt = 0.85 * dt;
+               delete u_old;
+               Verify(dt >= 1e-12, "The time step crashed!");
+               continue;
+            }
+            else if (dt_ratio > 1.25) { dt *= 1.02; }
+            delete u_old;
+         }
          if (!steady) { done = (t >= t_final - 1.e-8 * dt); }
          else
          {

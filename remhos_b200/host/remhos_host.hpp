@@ -245,6 +245,16 @@ public:
    void CalcSolution(const Vector &u, Vector &du) const override;
 };
 
+// remhos_fct.hpp:157-174
+class ElementFCTProjection : public FCTSolver
+{
+public:
+   ElementFCTProjection(ParFiniteElementSpace &space, double dt_);
+   void CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho, const Vector &du_lo,
+                        const Vector &u_min, const Vector &u_max, Vector &du) const override;
+   int Type() const override { return 4; }
+};
+
 class DofInfo
 {
    ParFiniteElementSpace &pfes;

@@ -178,3 +178,14 @@ def test_cli_mono_si_reproduces_reference_known_answers(args, mass, umax):
     r = parse(out)
     assert float('%.10g' % r['mass']) == mass
     assert float('%.10g' % r['umax']) == umax
+
+
+@pytest.mark.gpu
+def test_cli_fct_project_dtc_reproduces_reference_known_answer():
+    """autotest/out_baseline.dat:207-210 ("BLAST sharpening test"): -fct 4 -bt 1 -dtc 1"""
+    rc, out, err = run_cli('-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 3, '-dt', 0.01, '-tf', 0.8,
+                           '-ho', 3, '-lo', 5, '-fct', 4, '-bt', 1, '-dtc', 1, '-no-vis')
+    assert rc == 0, err
+    r = parse(out)
+    assert float('%.10g' % r['mass']) == 0.1623263888
+    assert float('%.10g' % r['umax']) == 0.2863317261

@@ -268,3 +268,44 @@ def test_ode_step_unknown_solver_returns_3():
     with pytest.raises(rb.RmhError):
         ctx.ode_step(5, 3, 0, 0, 0.0, 0.01, dev(run.u))
     ctx.close()
+
+
+# ---- ElementFCTProjection (-fct 4) and -dtc 1; the oracle is pinned on out_baseline.dat:207-210
+# (tests/test_oracle_fct_project_golden.py)
+def test_fct_project_matches_oracle(setup):
+    run, ctx, u = setup
+    at_time(run, ctx, 0.0)
+    d = run.disc
+    dt = run.dt
+    du_ho = d.ho_local_inverse(u)
+    du_lo = d.lo_mass_based_avg(u, du_ho, dt)
+    umin, umax = d.bounds(u, run.opt.bounds_type)
+    ref = d.fct_project(u, du_ho, du_lo, umin, umax, dt)
+    out = empty(ctx)
+    ctx.fct_project(dt, dev(u), dev(du_ho), dev(du_lo), dev(umin), dev(umax), out)
+    assert rel_err(host(out, u.shape), ref) < TOL
+    # conservative: sum_i M_L,i (du_i - du_lo_i) = 0 per element
+    ML = d.cur.M.sum(axis=2)
+    corr = (ML * (host(out, u.shape) - du_lo)).sum(axis=1)
+    assert np.abs(corr).max() < 1e-12 * np.abs(ML * du_lo).sum(axis=1).max()
+
+
+def test_dt_ratio_matches_oracle(setup):
+    run, ctx, u = setup
+    if run.exec_mode == 1:
+        pytest.skip('transport only')
+    run.opt.fct_type = 4; run.opt.lo_type = 5; run.opt.dt_control = 1
+    run.dt_ratio = np.inf; run.dt_est = np.inf
+    dt = run.dt
+    try:
+        ref = run.mult(u, 0.0, dt)
+        ctx.dt_control(1)
+        ctx.dt_ratio(reset=True)
+        k = empty(ctx)
+        ctx.mult(3, 5, 4, 0.0, dt, dev(u), k)
+        assert rel_err(host(k, u.shape), ref) < TOL
+        r = ctx.dt_ratio()
+        assert abs(r - run.dt_ratio) < 1e-9 * abs(run.dt_ratio)
+    finally:
+        ctx.dt_control(0)
+        run.opt.fct_type = 1; run.opt.lo_type = 1; run.opt.dt_control = 0

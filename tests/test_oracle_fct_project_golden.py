@@ -1,0 +1,13 @@
+"""The oracle's ElementFCTProjection (-fct 4) and automatic time step control (-dtc 1) against the
+reference's known answer autotest/out_baseline.dat:207-210 ("BLAST sharpening test"):
+  -m periodic-square.mesh -p 5 -rs 3 -dt 0.01 -tf 0.8 -ho 3 -lo 5 -fct 4 -bt 1 -dtc 1
+final mass and maximum to the 10 printed digits."""
+from helpers import oracle_run
+
+
+def test_fct_project_dtc_known_answer():
+    run = oracle_run('periodic-square.mesh', problem=5, rs_levels=3, order=3, dt=0.01, t_final=0.8,
+                     ode_solver=3, ho_type=3, lo_type=5, fct_type=4, bounds_type=1, dt_control=1)
+    run.run()
+    assert float('%.10g' % run.final_mass) == 0.1623263888
+    assert float('%.10g' % run.u.max()) == 0.2863317261
