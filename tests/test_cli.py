@@ -189,3 +189,14 @@ def test_cli_fct_project_dtc_reproduces_reference_known_answer():
     r = parse(out)
     assert float('%.10g' % r['mass']) == 0.1623263888
     assert float('%.10g' % r['umax']) == 0.2863317261
+
+
+@pytest.mark.gpu
+def test_cli_fct_project_dtc_remap_reproduces_reference_known_answer():
+    """autotest/out_baseline.dat:202-205 ("Pacman remap auto-dt"): remap, CFL dt, -fct 4 -bt 1 -dtc 1"""
+    rc, out, err = run_cli('-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-dt', -1, '-tf', 0.75,
+                           '-ho', 3, '-lo', 5, '-fct', 4, '-bt', 1, '-dtc', 1, '-no-vis')
+    assert rc == 0, err
+    r = parse(out)
+    assert float('%.10g' % r['mass']) == 0.08479612805
+    assert float('%.6g' % r['loss']) == 6.61247e-07
