@@ -307,7 +307,7 @@ def main():
             a.order + 1, {1: 8, 2: 2, 3: 2, 4: 1}.get(a.order, 1))
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
         # workload (profiles/r01/ncu_stage_v12_const_rs5.txt)
-        traffic = (1.254585e9 + 439.694080e6) if (a.order == 3 and a.rs == 5) else None
+        traffic = (1.255223e9 + 441.227776e6) if (a.order == 3 and a.rs == 5) else None
     else:
         kname = 'k_stage3w<%d,%d,%s> (FP64 DMMA, warp per element)' % (
             a.order + 1, a.order + 3, '8,2' if a.order <= 3 else '6,2')
@@ -336,6 +336,8 @@ def main():
                      # the fused kernel moves far less than the 136 B/DOF of five separate kernels:
                      # its own DRAM traffic over its own time, as a fraction of the HBM peak
                      'traffic_frac_of_peak': (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                     # the same against SURVEY.md 8d's fused lower bound (56 B/DOF*stage: the "stretch" figure)
+                     'frac_of_fused_lower_bound_56B': (56.0 * N / (k_ms * 1e-3) / 1e9 / peak) if klaunch else None,
                      'alg_bytes_per_dof_stage': B_ALG, 'kernel_ms': k_ms,
                      'kernel_share_of_step': (kms / ms) if klaunch else None},
         'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0), 'u_min': umin, 'u_max': umax},
