@@ -271,7 +271,7 @@ def test_ode_step_unknown_solver_returns_3():
 
 
 # ---- ElementFCTProjection (-fct 4) and -dtc 1; the oracle is pinned on out_baseline.dat:207-210
-# (tests/test_oracle_fct_project_golden.py)
+# (tests/test_oracle_mono_golden.py)
 def test_fct_project_matches_oracle(setup):
     run, ctx, u = setup
     at_time(run, ctx, 0.0)
