@@ -190,3 +190,32 @@ def test_trust_state_is_bit_identical(ode):
             ctx.stage(5, run.dt, u1, k)      # another vector passes through the context in between
     assert torch.equal(u1, u2)
     ctx.close()
+
+
+# k_stage3c edge cases: element counts that are not a multiple of the elements a warp handles at
+# once (27 elements: last group partial at every order), and domain-boundary faces (exterior state 0
+# through zero-fill copies) with both bounds types
+@pytest.mark.parametrize('mesh,rs,order,bt', [
+    ('periodic-cube.mesh', 0, 1, 0), ('periodic-cube.mesh', 0, 2, 0), ('periodic-cube.mesh', 0, 3, 1),
+    ('periodic-cube.mesh', 0, 4, 0), ('cube01_hex.mesh', 1, 3, 0), ('cube01_hex.mesh', 1, 2, 1),
+    ('cube01_hex.mesh', 0, 1, 0), ('cube01_hex.mesh', 2, 4, 0)])
+def test_const_kernel_edge_cases(mesh, rs, order, bt):
+    run = oracle_run(mesh, ho_type=3, lo_type=5, fct_type=2, problem=0, rs_levels=rs, order=order,
+                     dt=0.004, bounds_type=bt, max_steps=3)
+    ctx = ctx_from_oracle(run)
+    assert ctx.path_flags & 8, 'constant-coefficient kernel expected'
+    rng = np.random.default_rng(13)
+    u = np.clip(run.u + 0.02 * rng.standard_normal(run.u.shape), 0.0, None)
+    ref = run.mult(u, 0.0, run.dt)
+    k = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.stage(5, run.dt, dev(u), k)
+    assert rel_err(k.cpu().numpy().reshape(u.shape), ref) < (1e-10 if order <= 3 else 1e-8)
+    # a few RK3 steps, state carried across steps
+    ctx.trust_state(True)
+    ud = dev(run.u)
+    t = 0.0
+    for _ in range(3):
+        t = ctx.rk_step(3, 5, t, run.dt, ud)
+    run.run()
+    assert rel_err(ud.cpu().numpy().reshape(run.u.shape), run.u) < (1e-12 if order <= 3 else 1e-10)
+    ctx.close()
