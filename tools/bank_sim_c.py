@@ -41,6 +41,13 @@ def model(RS, SZ, EL, D1=4):
     res['row128'] = sum(wf128([el[L] * EL + b[L] * SZ + a[L] * RS + 2 * h for L in lanes]) for h in range(2))
     # y-lines: lane = (el, iz=b, ix=a): 64-bit at k
     res['yline64'] = sum(wf64([el[L] * EL + b[L] * SZ + k * RS + a[L] for L in lanes]) for k in range(D1))
+    # y-lines with the lane map of stage3c.cuh (order 3): half-warp h owns planes {h, h + 2} of both
+    # elements: ely = (lane >> 3) & 1, ya = lane & 3, yb = 2 * ((lane >> 2) & 1) + (lane >> 4)
+    ely = [(L >> 3) & 1 for L in lanes]
+    ya = [L & 3 for L in lanes]
+    yb = [2 * ((L >> 2) & 1) + (L >> 4) for L in lanes]
+    res['yline64_remapped'] = sum(wf64([ely[L] * EL + yb[L] * SZ + k * RS + ya[L] for L in lanes])
+                                  for k in range(D1))
     # z-lines: lane = (el, iy=b, ix=a)
     res['zline64'] = sum(wf64([el[L] * EL + k * SZ + b[L] * RS + a[L] for L in lanes]) for k in range(D1))
     return res
@@ -55,7 +62,7 @@ if __name__ == '__main__':
             SZ = 4 * RS + SZp
             EL = 4 * SZ + ELp
             r = model(RS, SZ, EL)
-            best.append((sum(r.values()), EL, RS, SZ, r))
+            best.append((r['row128'] + min(r['yline64'], r['yline64_remapped']) + r['zline64'], EL, RS, SZ, r))
         best.sort(key=lambda t: (t[0], t[1]))
         for t in best[:12]:
             print(t)
