@@ -96,11 +96,13 @@ def read_mesh(path):
     ne = int(toks[pos]); pos += 1
     nvert = 2 ** dim
     ev = np.empty((ne, nvert), dtype=np.int64)
+    ev_file = np.empty((ne, nvert), dtype=np.int64)          # MFEM's own vertex order
     for e in range(ne):
         geom = int(toks[pos + 1])
         if (dim, geom) not in ((2, 3), (3, 5)):
             raise ValueError('only quadrilateral / hexahedral meshes are supported')
         v = np.array([int(t) for t in toks[pos + 2: pos + 2 + nvert]])
+        ev_file[e] = v
         ev[e] = v[_MFEM2LEX[dim]]
         pos += 2 + nvert
     expect('boundary')
@@ -133,10 +135,40 @@ def read_mesh(path):
             assert data.size == nv * vdim
             coords = data.reshape(nv, vdim) if ordering == 1 else data.reshape(vdim, nv).T
             return Mesh(dim, ev, coords[ev], 1, nv)
+        if fec in ('Quadratic', 'H1_2D_P2') and dim == 2:
+            return Mesh(dim, ev, _quadratic_nodes(ev_file, nv, data, vdim, ordering), 2, nv)
         raise ValueError('unsupported nodal collection ' + fec)
     sdim = int(toks[pos]); pos += 1
     coords = np.array([float(t) for t in toks[pos: pos + nv * sdim]]).reshape(nv, sdim)
     return Mesh(dim, ev, coords[ev], 1, nv)
+
+
+def _quadratic_nodes(ev_file, nv, data, vdim, ordering):
+    """Element-wise 3 x 3 nodes of an H1 order-2 nodal field on quadrilaterals (legacy `Quadratic`
+    collection): global dofs are [vertices | edges | elements], edges numbered in the order of their
+    first appearance over the elements and their local edges (0,1), (1,2), (2,3), (3,0) -- MFEM's
+    vertex-to-vertex table [MFEM-K; validated by remhos_tests.cpp:88-91 through the star-q2 run]."""
+    ne = ev_file.shape[0]
+    edge_id = {}
+    el_edges = np.empty((ne, 4), dtype=np.int64)
+    for e in range(ne):
+        v = ev_file[e]
+        for j, (a, b) in enumerate(((0, 1), (1, 2), (2, 3), (3, 0))):
+            key = (min(v[a], v[b]), max(v[a], v[b]))
+            if key not in edge_id:
+                edge_id[key] = len(edge_id)
+            el_edges[e, j] = edge_id[key]
+    nedge = len(edge_id)
+    nd = nv + nedge + ne
+    assert data.size == nd * vdim, (data.size, nd, vdim)
+    vals = data.reshape(nd, vdim) if ordering == 1 else data.reshape(vdim, nd).T
+    X = np.empty((ne, 9, vdim))
+    v = ev_file
+    X[:, 0] = vals[v[:, 0]]; X[:, 2] = vals[v[:, 1]]; X[:, 8] = vals[v[:, 2]]; X[:, 6] = vals[v[:, 3]]
+    X[:, 1] = vals[nv + el_edges[:, 0]]; X[:, 5] = vals[nv + el_edges[:, 1]]
+    X[:, 7] = vals[nv + el_edges[:, 2]]; X[:, 3] = vals[nv + el_edges[:, 3]]
+    X[:, 4] = vals[nv + nedge + np.arange(ne)]
+    return X
 
 
 def _read_inline(path):

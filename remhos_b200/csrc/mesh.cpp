@@ -17,6 +17,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <map>
 #include <vector>
 
 namespace rmh
@@ -562,6 +563,7 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
    const int nvx = 1 << dim;
    m.dim = dim; m.ne = ne;
    m.ev.resize((size_t)ne * nvx);
+   std::vector<int64_t> ev_file((size_t)ne * nvx);        // the file's (MFEM's) vertex order
    for (int64_t e = 0; e < ne; e++)
    {
       const int geom = atoi(tk[pos + 1].c_str());
@@ -571,6 +573,7 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
       {
          const int src = (dim == 2) ? MFEM2LEX2[c] : MFEM2LEX3[c];
          m.ev[e * nvx + c] = atoll(tk[pos + 2 + src].c_str());
+         ev_file[e * nvx + c] = atoll(tk[pos + 2 + c].c_str());
       }
       pos += 2 + nvx;
    }
@@ -613,6 +616,42 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
                const size_t src = ordering == 1 ? i * dim + c : c * nd + i;
                m.X[i * dim + c] = atof(tk[pos + src].c_str());
             }
+         *out = r;
+         return 0;
+      }
+      if ((fec == "Quadratic" || fec == "H1_2D_P2") && dim == 2)
+      {
+         // H1 order-2 nodal field on quadrilaterals (legacy `Quadratic` collection): global dofs
+         // are [vertices | edges | elements]; edges are numbered in the order of their first
+         // appearance over the elements and their local edges (0,1), (1,2), (2,3), (3,0) -- MFEM's
+         // vertex-to-vertex table (validated by remhos_tests.cpp:88-91 through the star-q2 run)
+         std::map<std::pair<int64_t, int64_t>, int64_t> edge_id;
+         std::vector<int64_t> el_edges((size_t)ne * 4);
+         static const int EV[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};
+         for (int64_t e = 0; e < ne; e++)
+            for (int j = 0; j < 4; j++)
+            {
+               const int64_t a = ev_file[e * 4 + EV[j][0]], b = ev_file[e * 4 + EV[j][1]];
+               const std::pair<int64_t, int64_t> key(std::min(a, b), std::max(a, b));
+               auto it = edge_id.find(key);
+               if (it == edge_id.end()) { it = edge_id.emplace(key, (int64_t)edge_id.size()).first; }
+               el_edges[e * 4 + j] = it->second;
+            }
+         const int64_t nedge = (int64_t)edge_id.size(), ndof = nv + nedge + ne;
+         if (nvals != (size_t)ndof * dim) { return fail("wrong number of nodal values"); }
+         auto val = [&](int64_t i, int c)
+         { return atof(tk[pos + (ordering == 1 ? (size_t)i * dim + c : (size_t)c * ndof + i)].c_str()); };
+         m.g = 2;
+         m.X.resize((size_t)ne * 9 * dim);
+         for (int64_t e = 0; e < ne; e++)
+         {
+            const int64_t *v = &ev_file[e * 4], *ed = &el_edges[e * 4];
+            // lexicographic 3 x 3 nodes: corners, edge midpoints, centre
+            const int64_t dof[9] = {v[0], nv + ed[0], v[1], nv + ed[3], nv + nedge + e, nv + ed[1],
+                                    v[3], nv + ed[2], v[2]};
+            for (int n = 0; n < 9; n++)
+               for (int c = 0; c < dim; c++) { m.X[((size_t)e * 9 + n) * dim + c] = val(dof[n], c); }
+         }
          *out = r;
          return 0;
       }

@@ -200,3 +200,16 @@ def test_cli_fct_project_dtc_remap_reproduces_reference_known_answer():
     r = parse(out)
     assert float('%.10g' % r['mass']) == 0.08479612805
     assert float('%.6g' % r['loss']) == 6.61247e-07
+
+
+@pytest.mark.gpu
+def test_cli_star_q2_curved_mesh_known_answer(tmp_path):
+    """remhos_tests.cpp:88-91 (#8): curved Q2 `Quadratic` mesh (tests/golden/star_q2.json), PA remap"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from make_star_q2 import materialise
+    p = materialise(str(tmp_path / 'star-q2.mesh'))
+    rc, out, err = run_cli('-m', p, '-pa', '-p', 14, '-rs', 1, '-o', 3, '-dt', -1, '-tf', 0.5, '-ho', 3,
+                           '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis')
+    assert rc == 0, err
+    assert float('%.10g' % parse(out)['mass']) == float('%.10g' % 0.8069675186775516)

@@ -133,3 +133,36 @@ def test_rk6_tableau():
             y = step(y, t, dt); t += dt
         errs.append(abs(y - np.exp(np.sin(2.0))))
     assert np.log2(errs[0] / errs[1]) > 5.5 and np.log2(errs[1] / errs[2]) > 5.5
+
+
+def _star_q2(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from make_star_q2 import materialise
+    return materialise(str(tmp_path / 'star-q2.mesh'))
+
+
+def test_star_q2_curved_mesh_known_answer(tmp_path):
+    """remhos_tests.cpp:88-91 (#8): curved Q2 mesh given in the legacy `Quadratic` collection,
+    `-pa -p 14 -rs 1 -o 3 -dt -1.0 -tf 0.5 -ho 3 -lo 5 -fct 2 -ms 5` -> 0.8069675186775516 (the
+    reference's tolerance: 10 eps relative).  Input: tests/golden/star_q2.json."""
+    r = driver.Run(driver.Options(mesh_file=_star_q2(tmp_path), problem=14, rs_levels=1, order=3, dt=-1.0,
+                                  t_final=0.5, ode_solver=3, ho_type=3, lo_type=5, fct_type=2,
+                                  max_steps=5))
+    r.run()
+    assert abs(r.final_mass - 0.8069675186775516) < 10 * 2.220446049250313e-16 * 0.8069675186775516 * 2
+
+
+def test_star_q2_reader_matches_product_reader(tmp_path):
+    """the product's C++ mesh module reads, refines and curves the `Quadratic` mesh exactly as the
+    oracle does (no GPU needed)"""
+    import remhos_b200 as rb
+    p = _star_q2(tmp_path)
+    mo = om.read_mesh(p)
+    mc = rb.Mesh.load(p)
+    assert mc.geom_order == 2 and mc.ne == mo.ne == 20
+    assert np.array_equal(np.asarray(mc.nodes()).reshape(mo.X.shape), mo.X)
+    mo2 = om.set_curvature(om.refine_uniform(mo), 2)
+    mc.refine(1); mc.set_curvature(2)
+    assert np.abs(np.asarray(mc.nodes()).reshape(mo2.X.shape) - mo2.X).max() < 1e-14
+    assert np.array_equal(np.asarray(mc.elem_vertices()).reshape(mo2.ev.shape), mo2.ev)
