@@ -98,14 +98,15 @@ class DistProblem:
         self.w2 = torch.empty(self.ctx.ndofs, dtype=f64, device=dev)
         self.n_send = ns
         # overlap of the exchange with the interior elements (rmh_rk_stage_part; constant-coefficient
-        # stage kernel and overlap bounds only).  Default: on from 8 ranks (2x2x2 bricks exchange their
-        # whole surface: 2.39 vs 2.48 ms/step measured), off below: on 2 GPUs the second, small
+        # stage kernel and overlap bounds only).  Default: on from 4 ranks (8 ranks, 2x2x2 bricks
+        # exchanging their whole surface: 2.39 vs 2.48 ms/step measured; 4 ranks: 2.17 vs ~2.20),
+        # off on 2: there the second, small
         # launch for the elements next to the ghost ring plus the NCCL kernels competing for SMs
         # cost more (2.19 ms/step) than the ~60 us of exchange they hide (2.12 ms/step sequential).
         # RMH_OVERLAP=0/1 forces either form.
         import os
         self.overlap = bool(world > 1 and ng > 0 and bounds_type == 0 and (self.ctx.path_flags & 8)
-                            and os.environ.get('RMH_OVERLAP', '1' if world >= 8 else '0') == '1')
+                            and os.environ.get('RMH_OVERLAP', '1' if world >= 4 else '0') == '1')
         if self.overlap:
             self.ctx.dist_split(self.n_interior)
             self.cs = torch.cuda.Stream(device=dev)
