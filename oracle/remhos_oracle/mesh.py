@@ -137,6 +137,8 @@ def read_mesh(path):
             return Mesh(dim, ev, coords[ev], 1, nv)
         if fec in ('Quadratic', 'H1_2D_P2') and dim == 2:
             return Mesh(dim, ev, _quadratic_nodes(ev_file, nv, data, vdim, ordering), 2, nv)
+        if fec in ('Cubic', 'H1_2D_P3') and dim == 2:
+            return Mesh(dim, ev, _cubic_nodes(ev_file, nv, data, vdim, ordering), 3, nv)
         raise ValueError('unsupported nodal collection ' + fec)
     sdim = int(toks[pos]); pos += 1
     coords = np.array([float(t) for t in toks[pos: pos + nv * sdim]]).reshape(nv, sdim)
@@ -169,6 +171,51 @@ def _quadratic_nodes(ev_file, nv, data, vdim, ordering):
     X[:, 7] = vals[nv + el_edges[:, 2]]; X[:, 3] = vals[nv + el_edges[:, 3]]
     X[:, 4] = vals[nv + nedge + np.arange(ne)]
     return X
+
+
+def _cubic_nodes(ev_file, nv, data, vdim, ordering):
+    """Element-wise 4 x 4 Gauss-Lobatto nodes of an H1 order-3 nodal field on quadrilaterals given in
+    the legacy `Cubic` collection (equispaced nodes): global dofs are [vertices | 2 per edge | 4 per
+    element]; the two edge dofs run from the edge's lower-numbered vertex to the higher one, the
+    element dofs are (1/3,1/3), (2/3,1/3), (1/3,2/3), (2/3,2/3) [MFEM-K; checked geometrically on
+    data/star-q3.mesh: edge nodes ordered along their edges, positive Jacobians, interior nodes
+    closest to the transfinite interpolant, area equal to star-q2's to 1e-6]."""
+    from . import fe
+    ne = ev_file.shape[0]
+    edge_id = {}
+    el_edges = np.empty((ne, 4), dtype=np.int64)
+    el_fwd = np.empty((ne, 4), dtype=bool)
+    for e in range(ne):
+        v = ev_file[e]
+        for j, (a, b) in enumerate(((0, 1), (1, 2), (2, 3), (3, 0))):
+            key = (min(v[a], v[b]), max(v[a], v[b]))
+            if key not in edge_id:
+                edge_id[key] = len(edge_id)
+            el_edges[e, j] = edge_id[key]
+            el_fwd[e, j] = v[a] < v[b]
+    nedge = len(edge_id)
+    nd = nv + 2 * nedge + 4 * ne
+    assert data.size == nd * vdim, (data.size, nd, vdim)
+    vals = data.reshape(nd, vdim) if ordering == 1 else data.reshape(vdim, nd).T
+    X = np.empty((ne, 4, 4, vdim))                                   # [e][iy][ix]
+    v = ev_file
+    X[:, 0, 0] = vals[v[:, 0]]; X[:, 0, 3] = vals[v[:, 1]]
+    X[:, 3, 3] = vals[v[:, 2]]; X[:, 3, 0] = vals[v[:, 3]]
+
+    def edof(j, k):                                                  # k-th node along the local edge direction
+        g = np.where(el_fwd[:, j], k, 1 - k)
+        return vals[nv + 2 * el_edges[:, j] + g]
+    X[:, 0, 1] = edof(0, 0); X[:, 0, 2] = edof(0, 1)                 # v0 -> v1: +x at y = 0
+    X[:, 1, 3] = edof(1, 0); X[:, 2, 3] = edof(1, 1)                 # v1 -> v2: +y at x = 1
+    X[:, 3, 2] = edof(2, 0); X[:, 3, 1] = edof(2, 1)                 # v2 -> v3: -x at y = 1
+    X[:, 2, 0] = edof(3, 0); X[:, 1, 0] = edof(3, 1)                 # v3 -> v0: -y at x = 0
+    base = nv + 2 * nedge + 4 * np.arange(ne)
+    X[:, 1, 1] = vals[base]; X[:, 1, 2] = vals[base + 1]
+    X[:, 2, 1] = vals[base + 2]; X[:, 2, 2] = vals[base + 3]
+    # equispaced -> Gauss-Lobatto nodes of the same cubic map
+    T = fe.lagrange(np.array([0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0]), fe.gauss_lobatto_01(4))   # [gll][equi]
+    X = np.einsum('pj,qi,ejic->epqc', T, T, X)
+    return X.reshape(ne, 16, vdim)
 
 
 def _read_inline(path):

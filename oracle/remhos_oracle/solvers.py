@@ -219,7 +219,7 @@ class Discretization:
                 corr = corr * alpha[:, sp.bd[:, f]]
             sP = np.maximum(0.0, corr).sum(axis=1)
             sN = np.minimum(0.0, corr).sum(axis=1)
-            with np.errstate(divide='ignore', invalid='ignore'):
+            with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
                 cP = np.minimum(0.0, corr) - np.maximum(0.0, corr) * (sN / sP)[:, None]
                 cN = np.maximum(0.0, corr) - np.minimum(0.0, corr) * (sP / sN)[:, None]
             tot = sP + sN
@@ -305,7 +305,7 @@ class Discretization:
                     al = np.minimum(np.maximum(si_tmp, al), aglob)
                 m_new = m_new * al
                 MP = np.maximum(0.0, m_new).sum(axis=1); MN = np.minimum(0.0, m_new).sum(axis=1)
-                with np.errstate(divide='ignore', invalid='ignore'):
+                with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
                     cP = np.minimum(0.0, m_new) - np.maximum(0.0, m_new) * (MN / MP)[:, None]
                     cN = np.maximum(0.0, m_new) - np.minimum(0.0, m_new) * (MP / MN)[:, None]
                 tot = MP + MN

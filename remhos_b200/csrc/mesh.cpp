@@ -655,6 +655,70 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
          *out = r;
          return 0;
       }
+      if ((fec == "Cubic" || fec == "H1_2D_P3") && dim == 2)
+      {
+         // legacy `Cubic` collection (equispaced nodes): [vertices | 2 per edge | 4 per element]; the
+         // two edge dofs run from the edge's lower-numbered vertex to the higher one, the element
+         // dofs are (1/3,1/3), (2/3,1/3), (1/3,2/3), (2/3,2/3); stored as Gauss-Lobatto nodes of the
+         // same cubic map (see oracle/remhos_oracle/mesh.py:_cubic_nodes for how this was checked)
+         std::map<std::pair<int64_t, int64_t>, int64_t> edge_id;
+         std::vector<int64_t> el_edges((size_t)ne * 4);
+         std::vector<char> el_fwd((size_t)ne * 4);
+         static const int EV[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};
+         for (int64_t e = 0; e < ne; e++)
+            for (int j = 0; j < 4; j++)
+            {
+               const int64_t a = ev_file[e * 4 + EV[j][0]], b = ev_file[e * 4 + EV[j][1]];
+               const std::pair<int64_t, int64_t> key(std::min(a, b), std::max(a, b));
+               auto it = edge_id.find(key);
+               if (it == edge_id.end()) { it = edge_id.emplace(key, (int64_t)edge_id.size()).first; }
+               el_edges[e * 4 + j] = it->second;
+               el_fwd[e * 4 + j] = a < b;
+            }
+         const int64_t nedge = (int64_t)edge_id.size(), ndof = nv + 2 * nedge + 4 * ne;
+         if (nvals != (size_t)ndof * dim) { return fail("wrong number of nodal values"); }
+         auto val = [&](int64_t i, int c)
+         { return atof(tk[pos + (ordering == 1 ? (size_t)i * dim + c : (size_t)c * ndof + i)].c_str()); };
+         const std::vector<double> equi = {0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0};
+         const std::vector<double> T = lagrange(equi, gauss_lobatto_01(4));     // [gll point][equi node]
+         m.g = 3;
+         m.X.resize((size_t)ne * 16 * dim);
+         for (int64_t e = 0; e < ne; e++)
+         {
+            const int64_t *v = &ev_file[e * 4];
+            auto edof = [&](int j, int k)
+            { return nv + 2 * el_edges[e * 4 + j] + (el_fwd[e * 4 + j] ? k : 1 - k); };
+            const int64_t base = nv + 2 * nedge + 4 * e;
+            int64_t dof[4][4];                                    // [iy][ix]
+            dof[0][0] = v[0]; dof[0][3] = v[1]; dof[3][3] = v[2]; dof[3][0] = v[3];
+            dof[0][1] = edof(0, 0); dof[0][2] = edof(0, 1);
+            dof[1][3] = edof(1, 0); dof[2][3] = edof(1, 1);
+            dof[3][2] = edof(2, 0); dof[3][1] = edof(2, 1);
+            dof[2][0] = edof(3, 0); dof[1][0] = edof(3, 1);
+            dof[1][1] = base; dof[1][2] = base + 1; dof[2][1] = base + 2; dof[2][2] = base + 3;
+            for (int c = 0; c < dim; c++)
+            {
+               double E[4][4], tmp[4][4];
+               for (int iy = 0; iy < 4; iy++) for (int ix = 0; ix < 4; ix++) { E[iy][ix] = val(dof[iy][ix], c); }
+               for (int iy = 0; iy < 4; iy++)
+                  for (int q = 0; q < 4; q++)
+                  {
+                     double sacc = 0.0;
+                     for (int i = 0; i < 4; i++) { sacc += T[q * 4 + i] * E[iy][i]; }
+                     tmp[iy][q] = sacc;
+                  }
+               for (int p = 0; p < 4; p++)
+                  for (int q = 0; q < 4; q++)
+                  {
+                     double sacc = 0.0;
+                     for (int j = 0; j < 4; j++) { sacc += T[p * 4 + j] * tmp[j][q]; }
+                     m.X[((size_t)e * 16 + p * 4 + q) * dim + c] = sacc;
+                  }
+            }
+         }
+         *out = r;
+         return 0;
+      }
       if (fec == "Linear" || (fec.rfind("H1_", 0) == 0 && fec.size() >= 3 &&
                               fec.compare(fec.size() - 3, 3, "_P1") == 0))
       {

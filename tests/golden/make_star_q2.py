@@ -1,6 +1,7 @@
-"""Writes tests/golden/star_q2.json from the reference's data/star-q2.mesh (a curved Q2
-quadrilateral mesh, nodes in the legacy `Quadratic` collection): element vertex lists, boundary
-segments and the nodal values -- the input of the reference's known answer remhos_tests.cpp:88-91.
+"""Writes tests/golden/star_q2.json and star_q3.json from the reference's data/star-q2.mesh and
+data/star-q3.mesh (curved quadrilateral meshes, nodes in the legacy `Quadratic` / `Cubic`
+collections): element vertex lists, boundary segments and the nodal values.  star-q2 is the input
+of the reference's known answer remhos_tests.cpp:88-91, star-q3 the mesh of BASELINE config 5.
 The GPU box has no /root/reference; tests materialise the mesh file from this fixture with
 `materialise()` below (our own MFEM mesh v1.0 writer).
 
@@ -10,7 +11,7 @@ import json
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = '/root/reference/data/star-q2.mesh'
+SRC = {'star_q2.json': '/root/reference/data/star-q2.mesh', 'star_q3.json': '/root/reference/data/star-q3.mesh'}
 
 
 def parse(path):
@@ -31,10 +32,10 @@ def parse(path):
         bdr.append([int(t) for t in toks[pos:pos + 4]]); pos += 4
     assert toks[pos] == 'vertices'
     nv = int(toks[pos + 1]); pos += 2
-    assert toks[pos] == 'nodes' and toks[pos + 3] == 'Quadratic'
+    assert toks[pos] == 'nodes' and toks[pos + 3] in ('Quadratic', 'Cubic')
     assert toks[pos + 4:pos + 8] == ['VDim:', '2', 'Ordering:', '0']
     vals = toks[pos + 8:]
-    return dict(dimension=2, elements=elems, boundary=bdr, vertices=nv, collection='Quadratic',
+    return dict(dimension=2, elements=elems, boundary=bdr, vertices=nv, collection=toks[pos + 3],
                 vdim=2, ordering=0, nodes=vals)
 
 
@@ -55,6 +56,7 @@ def materialise(path, fixture=os.path.join(HERE, 'star_q2.json')):
 
 
 if __name__ == '__main__':
-    with open(os.path.join(HERE, 'star_q2.json'), 'w') as f:
-        json.dump(parse(SRC), f)
-    print('wrote star_q2.json')
+    for name, src in SRC.items():
+        with open(os.path.join(HERE, name), 'w') as f:
+            json.dump(parse(src), f)
+        print('wrote', name)

@@ -213,3 +213,25 @@ def test_cli_star_q2_curved_mesh_known_answer(tmp_path):
                            '-lo', 5, '-fct', 2, '-ms', 5, '-no-vis')
     assert rc == 0, err
     assert float('%.10g' % parse(out)['mass']) == float('%.10g' % 0.8069675186775516)
+
+
+@pytest.mark.gpu
+def test_cli_config5_star_q3_mono_subcell_matches_oracle(tmp_path):
+    """BASELINE config 5: monolithic subcell residual distribution (-mono 2) on the refined star-q3
+    mesh (curved, legacy `Cubic` nodes), solid-body rotation -p 4: CLI on the GPU vs the oracle, and
+    the bounds verdict (no reference number exists for this configuration)"""
+    import sys
+    from remhos_oracle import driver
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from make_star_q2 import materialise, HERE
+    p = materialise(str(tmp_path / 'star-q3.mesh'), os.path.join(HERE, 'star_q3.json'))
+    rc, out, err = run_cli('-m', p, '-p', 4, '-rs', 2, '-o', 2, '-dt', 0.002, '-tf', 0.1, '-mono', 2,
+                           '-ms', 10, '-no-vis')
+    assert rc == 0, err
+    r = parse(out)
+    run = driver.Run(driver.Options(mesh_file=p, problem=4, rs_levels=2, order=2, dt=0.002, t_final=0.1,
+                                    ode_solver=3, mono_type=2, max_steps=10))
+    run.run()
+    assert abs(r['mass'] - run.final_mass) < 1e-9 * abs(run.final_mass)
+    assert abs(r['umax'] - run.final_max) < 1e-9
+    assert run.u.min() > -1e-12 and r['umax'] < 1.0 + 1e-12

@@ -166,3 +166,38 @@ def test_star_q2_reader_matches_product_reader(tmp_path):
     mc.refine(1); mc.set_curvature(2)
     assert np.abs(np.asarray(mc.nodes()).reshape(mo2.X.shape) - mo2.X).max() < 1e-14
     assert np.array_equal(np.asarray(mc.elem_vertices()).reshape(mo2.ev.shape), mo2.ev)
+
+
+def test_star_q3_cubic_mesh_readers_agree_and_geometry_is_sane(tmp_path):
+    """data/star-q3.mesh (BASELINE config 5; legacy `Cubic` collection, tests/golden/star_q3.json):
+    the product's C++ mesh module and the oracle read, refine and re-curve it identically; the
+    node-ordering conventions are checked geometrically (positive Jacobians, area equal to the
+    star-q2 domain's to 1e-5) since no reference number exists on this mesh."""
+    import sys
+    import remhos_b200 as rb
+    from remhos_oracle import fe
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from make_star_q2 import materialise, HERE
+    p3 = materialise(str(tmp_path / 'star-q3.mesh'), os.path.join(HERE, 'star_q3.json'))
+    mo = om.read_mesh(p3)
+    mc = rb.Mesh.load(p3)
+    assert mo.gorder == 3 and mc.geom_order == 3
+    assert np.abs(np.asarray(mc.nodes()).reshape(mo.X.shape) - mo.X).max() < 1e-14
+    mo2 = om.set_curvature(om.refine_uniform(mo), 2)
+    mc.refine(1); mc.set_curvature(2)
+    assert np.abs(np.asarray(mc.nodes()).reshape(mo2.X.shape) - mo2.X).max() < 1e-14
+
+    def area_and_min_det(m):
+        gll = fe.gauss_lobatto_01(m.gorder + 1)
+        xq, wq = fe.gauss_legendre_01(6)
+        L, dL = fe.lagrange(gll, xq), fe.lagrange_deriv(gll, xq)
+        n1 = m.gorder + 1
+        Xe = m.X.reshape(m.ne, n1, n1, 2)
+        dx = np.einsum('qi,pj,ejic->epqc', dL, L, Xe)
+        dy = np.einsum('qi,pj,ejic->epqc', L, dL, Xe)
+        det = dx[..., 0] * dy[..., 1] - dx[..., 1] * dy[..., 0]
+        return float(np.einsum('p,q,epq->', wq, wq, det)), float(det.min())
+    a3, d3 = area_and_min_det(mo)
+    a2, d2 = area_and_min_det(om.read_mesh(_star_q2(tmp_path)))
+    assert d3 > 0.0 and d2 > 0.0
+    assert abs(a3 - a2) < 1e-5 * a2
