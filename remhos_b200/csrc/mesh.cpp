@@ -660,7 +660,7 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
          // legacy `Cubic` collection (equispaced nodes): [vertices | 2 per edge | 4 per element]; the
          // two edge dofs run from the edge's lower-numbered vertex to the higher one, the element
          // dofs are (1/3,1/3), (2/3,1/3), (1/3,2/3), (2/3,2/3); stored as Gauss-Lobatto nodes of the
-         // same cubic map (see oracle/remhos_oracle/mesh.py:_cubic_nodes for how this was checked)
+         // same cubic map (DESIGN.md section 3 says how these conventions were checked)
          std::map<std::pair<int64_t, int64_t>, int64_t> edge_id;
          std::vector<int64_t> el_edges((size_t)ne * 4);
          std::vector<char> el_fwd((size_t)ne * 4);
