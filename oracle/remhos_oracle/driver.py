@@ -62,6 +62,7 @@ class Options:                       # defaults: remhos.cpp:216-244
     mono_type: int = 0            # 1: MonoRDSolver, 2: with subcells (remhos.cpp:285-289)
     si_type: int = 0              # smoothness indicator (remhos.cpp:302; order 1 only here)
     dt_control: int = 0           # -dtc 1: LO bounds error time step control (remhos.cpp:312-316)
+    product_sync: bool = False    # -ps: remap the product field us along with u (remhos.cpp:886-903)
     bounds_type: int = 0
     t_final: float = 4.0
     dt: float = 0.005
@@ -142,6 +143,14 @@ class Run:
         self.u0_min, self.u0_max = float(self.u.min()), float(self.u.max())
         self.mass0 = float((self.disc.cur.ml * self.u).sum())
         self.masses0 = self.disc.cur.ml.copy()
+        self.us = None
+        if opt.product_sync:                                   # remhos.cpp:886-903
+            assert self.exec_mode == 1, 'Products are processed only in remap mode.'
+            el, _ = Discretization.bool_indicators(self.u)
+            P = pts.reshape(-1, dim)
+            s0 = (2.0 + np.sin(2 * np.pi * P[:, 0]) * np.sin(2 * np.pi * P[:, 1])).reshape(m.ne, sp.nd)
+            self.us = self.u * np.where(el[:, None], s0, 0.0)
+            self.mass0_us = float((self.disc.cur.ml * self.us).sum())
         self.subcell_weights = None
         self.mono_scale = None
         if opt.mono_type:
@@ -176,6 +185,8 @@ class Run:
     def mult(self, u, t, dt):
         """LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult
         (remhos_solvers.hpp:46-50; remhos.cpp:1596-1739, 1798-1916)."""
+        if u.ndim == 3:                                        # (u, us): product remap
+            return self.limit_mult(u, self.mult_unlimited(u, t, dt), dt)
         o, d = self.opt, self.disc
         self._t = t
         if self.exec_mode == 1:
@@ -225,7 +236,12 @@ class Run:
         self.dt_ratio = min(getattr(self, 'dt_ratio', np.inf), dt / dt_cur if dt_cur != 0.0 else 0.0)
 
     def mult_unlimited(self, u, t, dt):
-        """AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739)."""
+        """AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739).  A state of shape [2, NE, nd]
+        is (u, us): the product field is remapped with the same operator (remhos.cpp:1714-1738)."""
+        if u.ndim == 3:
+            ku = self.mult_unlimited(u[0], t, dt)
+            assert self.opt.fct_type, 'product remap is restated for the FCT path'
+            return np.stack([ku, self.calc_ho(u[1])])
         o, d = self.opt, self.disc
         self._t = t
         if self.exec_mode == 1:
@@ -239,6 +255,9 @@ class Run:
     def limit_mult(self, u, du_ho, dt):
         """AdvectionOperator::LimitMult (remhos.cpp:1798-1916): du_ho is the (combined) HO rate."""
         o, d = self.opt, self.disc
+        if u.ndim == 3:                                        # remhos.cpp:1848-1915
+            du = self.limit_mult(u[0], du_ho[0], dt)
+            return np.stack([du, self.limit_product(u[0], du, u[1], du_ho[1], dt)])
         if not o.fct_type:
             return du_ho
         A = d.cur
@@ -246,7 +265,30 @@ class Run:
         umin, umax = d.bounds(u, o.bounds_type)
         if o.fct_type == 2:
             return d.fct_clip_scale(u, A.ml, du_ho, du_lo, umin, umax, dt)
+        if o.fct_type == 4:
+            return d.fct_project(u, du_ho, du_lo, umin, umax, dt)
         return d.fct_flux_based(u, A.ml, du_ho, du_lo, umin, umax, dt)
+
+    def limit_product(self, u, du, us, d_us_ho, dt):
+        """second pass of LimitMult (remhos.cpp:1848-1915) + CalcFCTProduct of ClipScaleSolver /
+        ElementFCTProjection (remhos_fct.cpp:543-563, 735-758): bounds on s = us / u from the old
+        active dofs, compatible LO product, limiter on us, empty dofs zeroed"""
+        o, d = self.opt, self.disc
+        assert o.fct_type in (2, 4), 'product remap is restated for -fct 2 and -fct 4'
+        A = d.cur
+        s, s_el, s_dof = d.compute_ratio(us, u)
+        s_min, s_max = d.bounds(s, o.bounds_type, active_el=s_el, active_dof=s_dof)
+        u_new = u + dt * du
+        el_new, dof_new = d.bool_indicators(u_new)
+        d_lo, s_min, s_max = d.compatible_lo_product(us, A.ml, d_us_ho, s_min, s_max, u_new, el_new,
+                                                     dof_new, dt)
+        us_min, us_max = d.scale_product_bounds(s_min, s_max, u_new, el_new, dof_new)
+        if o.fct_type == 2:
+            d_us = d.fct_clip_scale(us, A.ml, d_us_ho, d_lo, us_min, us_max, dt)
+        else:
+            d_us = d.fct_project(us, d_us_ho, d_lo, us_min, us_max, dt)
+        # ZeroOutEmptyDofs (remhos_sync.cpp:96-114)
+        return np.where(~el_new[:, None] & ~dof_new, 0.0, d_us)
 
     def idp_step(self, u, t, dt):
         """ForwardEulerIDPSolver / RKIDPSolver::Step with masks off (remhos_solvers.cpp:29-38,
@@ -388,7 +430,7 @@ class Run:
         """Time loop (remhos.cpp:1146-1330) and final mass / max (:1382-1436)."""
         o = self.opt
         t, dt = 0.0, self.dt
-        u = self.u
+        u = self.u if self.us is None else np.stack([self.u, self.us])
         ti = 0
         done = False
         steady = o.problem in (6, 7, 8)                        # remhos.cpp:1146-1330
@@ -424,6 +466,8 @@ class Run:
                 done = True
             if callback:
                 callback(ti, t, u)
+        if self.us is not None:
+            u, self.us = u[0], u[1]
         self.u = u
         self.t = t
         self.steps = ti
@@ -433,6 +477,8 @@ class Run:
         else:
             ml = self.masses0
         self.final_mass = float((ml * u).sum())
+        if self.us is not None:
+            self.final_mass_us = float((ml * self.us).sum())
         self.final_max = float(u.max())
         return self.final_mass, self.final_max
 

@@ -318,9 +318,19 @@ class Discretization:
         return (du + m_it) / A.ml
 
     # ------------------------------------------------------------------ bounds
-    def bounds(self, u, bounds_type):
+    def bounds(self, u, bounds_type, active_el=None, active_dof=None):
+        """ComputeElementsMinMax + ComputeBounds (remhos_tools.cpp:381-523).  active_el / active_dof:
+        the masked variants used for the product field (inactive elements and dofs do not
+        contribute; dofs no active element touches get +-inf)"""
         sp, topo = self.sp, self.topo
-        xe_min = u.min(axis=1); xe_max = u.max(axis=1)
+        if active_dof is not None:
+            xe_min = np.where(active_dof, u, np.inf).min(axis=1)
+            xe_max = np.where(active_dof, u, -np.inf).max(axis=1)
+        else:
+            xe_min = u.min(axis=1); xe_max = u.max(axis=1)
+        if active_el is not None:
+            xe_min = np.where(active_el, xe_min, np.inf)
+            xe_max = np.where(active_el, xe_max, -np.inf)
         if bounds_type == 0:
             emin = np.full(topo.n_ent, np.inf); emax = np.full(topo.n_ent, -np.inf)
             np.minimum.at(emin, topo.lat, xe_min[:, None])
@@ -335,6 +345,57 @@ class Discretization:
         mx = np.where(nb >= 0, xe_max[np.maximum(nb, 0)], -np.inf).max(axis=1)
         mn = np.minimum(mn, xe_min); mx = np.maximum(mx, xe_max)
         return (np.repeat(mn[:, None], sp.nd, axis=1), np.repeat(mx[:, None], sp.nd, axis=1))
+
+    # ------------------------------------------------------------------ product fields (-ps)
+    @staticmethod
+    def bool_indicators(u, tol=1e-12):
+        """ComputeBoolIndicators (remhos_sync.cpp:24-47), EMPTY_ZONE_TOL = 1e-12"""
+        dofs = u > tol
+        return dofs.any(axis=1), dofs
+
+    @staticmethod
+    def compute_ratio(us, u):
+        """ComputeRatio (remhos_sync.cpp:50-94): s = us / u on active dofs, the average of those
+        ratios on the other dofs of an active element, 0 in inactive elements"""
+        el, dofs = Discretization.bool_indicators(u)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            r = np.where(dofs, us / u, 0.0)
+        n = dofs.sum(axis=1)
+        avg = np.where(n > 0, r.sum(axis=1) / np.maximum(n, 1), 0.0)
+        s = np.where(dofs, r, avg[:, None])
+        s = np.where(el[:, None], s, 0.0)
+        return s, el, dofs
+
+    def compatible_lo_product(self, us, m, d_us_ho, s_min, s_max, u_new, act_el, act_dof, dt):
+        """FCTSolver::CalcCompatibleLOProduct (remhos_fct.cpp:26-118); returns (d_us_LO, s_min, s_max)
+        with the bounds the reference adjusts in place"""
+        eps = 1e-12
+        s_min = s_min.copy(); s_max = s_max.copy()
+        mass_us = ((us + dt * d_us_ho) * m).sum(axis=1)
+        mass_u = (u_new * m).sum(axis=1)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            s_avg = mass_us / mass_u
+        smin = np.where(act_dof, s_min, np.inf).min(axis=1)
+        smax = np.where(act_dof, s_max, -np.inf).max(axis=1)
+        any_act = act_dof.any(axis=1)
+        with np.errstate(invalid='ignore'):
+            fix_lo = any_act & (s_avg < smin) & (mass_us + eps > smin * mass_u)
+            s_avg = np.where(fix_lo, smin, s_avg)
+            fix_hi = any_act & (s_avg > smax) & (mass_us - eps < smax * mass_u)
+            s_avg = np.where(fix_hi, smax, s_avg)
+        sa = s_avg[:, None]
+        upd = act_dof & act_el[:, None]
+        s_min = np.where(upd & (sa + eps < s_min), sa, s_min)
+        s_max = np.where(upd & (sa - eps > s_max), sa, s_max)
+        d_lo = np.where(act_el[:, None], (u_new * sa - us) / dt, 0.0)
+        return d_lo, s_min, s_max
+
+    @staticmethod
+    def scale_product_bounds(s_min, s_max, u_new, act_el, act_dof):
+        """FCTSolver::ScaleProductBounds (remhos_fct.cpp:120-153)"""
+        on = act_dof & act_el[:, None]
+        with np.errstate(invalid='ignore'):
+            return np.where(on, s_min * u_new, 0.0), np.where(on, s_max * u_new, 0.0)
 
     # ------------------------------------------------------------------ FCT
     def fct_clip_scale(self, u, m, du_ho, du_lo, umin, umax, dt):
