@@ -235,3 +235,17 @@ def test_cli_config5_star_q3_mono_subcell_matches_oracle(tmp_path):
     assert abs(r['mass'] - run.final_mass) < 1e-9 * abs(run.final_mass)
     assert abs(r['umax'] - run.final_max) < 1e-9
     assert run.u.min() > -1e-12 and r['umax'] < 1.0 + 1e-12
+
+
+def test_new_flag_combinations_validated():
+    """-si needs -mono and order 1 in this build; -fct 4 needs assembled matrices; -fct 3 is not built;
+    -dtc 1 needs an FCT solver"""
+    for flags, msg in ((['-si', '1'], 'smoothness indicators'),
+                       (['-si', '3', '-mono', '1', '-o', '1'], 'Bad smoothness indicator id!'),
+                       (['-mono', '1', '-si', '1', '-o', '2'], 'smoothness indicators'),
+                       (['-ho', '3', '-lo', '5', '-fct', '4', '-pa'], 'FCTProject needs the assembled'),
+                       (['-ho', '3', '-lo', '5', '-fct', '3'], 'only -fct 0, 1'),
+                       (['-ho', '3', '-dtc', '1'], '-dtc 1 needs an FCT solver'),
+                       (['-ho', '3', '-lo', '5', '-fct', '2', '-dtc', '2'], 'time step control must be')):
+        rc, _, err = run_cli('-m', 'x', *flags)
+        assert rc == 134 and msg in err, (flags, err)
