@@ -86,6 +86,12 @@ int rmh_halo_get(const rmh_halo *h, int64_t *owned, int64_t *ghost, int32_t *pee
  * Any output pointer may be NULL. */
 int rmh_mesh_dof_maps(const rmh_mesh *m, int order, int32_t *bdr_dofs, int32_t *nbr_dof,
                       int32_t *sub2ind, int32_t *lat, int32_t *n_ent, int32_t *nbr_elem);
+/* Neighbourhood lattice derived from `lat` (the [ne][3^dim] lattice-entity map above): nbr[e][d],
+ * d = sum (1 + d_a) 3^a, d_a in {-1,0,1}: the element across the face / edge / vertex in direction d
+ * (e itself for d = 0, -1 at the domain boundary).  *structured = 1 iff these neighbourhoods
+ * reproduce every entity's element set, i.e. the overlap bounds of ComputeOverlapBounds
+ * (remhos_tools.cpp:432-495) can be formed from 3^dim neighbour values without the entity table. */
+int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t *lat, int32_t *nbr, int *structured);
 
 /* Mesh::GetElementSize(e): |det J(centre)|^(1/dim) per element (remhos.cpp:544, remhos_mono.cpp:55) */
 int rmh_mesh_elem_sizes(const rmh_mesh *m, double *h_out);

@@ -149,6 +149,16 @@ class Mesh:
     def halo(self, part, rank):
         return Halo(self, part, rank)
 
+    def nbr_lattice(self, order=1):
+        """(nbr [ne, 3^dim], structured) of rmh_nbr_lattice on this mesh's lattice-entity map"""
+        maps = self.dof_maps(order)
+        lat = np.ascontiguousarray(maps['lat'], dtype=np.int32)
+        nbr = np.zeros_like(lat)
+        ok = C.c_int(0)
+        check(lib().rmh_nbr_lattice(self.dim, C.c_int64(lat.shape[0]), C.c_int32(maps['n_ent']), _ptr(lat),
+                                    _ptr(nbr), C.byref(ok)))
+        return nbr, bool(ok.value)
+
     def dof_maps(self, order):
         d, ne, p = self.dim, self.ne, order
         nf, nfd, nd = 2 * d, (p + 1) ** (d - 1), (p + 1) ** d

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <sstream>
 #include <string>
 #include <map>
@@ -747,6 +748,114 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
          for (int a = 0; a < dim; a++)
          { m.X[((size_t)e * nvx + c) * dim + a] = coords[m.ev[e * nvx + c] * dim + a]; }
    *out = r;
+   return 0;
+}
+
+// Neighbourhood lattice of every element, derived from the lattice-entity map `lat`
+// ([ne][3^dim] entity ids, as returned by rmh_mesh_dof_maps): nbr[e][d], d = sum (1 + d_a) 3^a with
+// d_a in {-1, 0, 1}, is the element reached from e by crossing the entity in direction d (a face,
+// an edge, a vertex), e itself for d = 0, -1 if there is none (domain boundary).
+// *structured = 1 iff, for every element and every one of its 3^dim entities, the set of elements
+// sharing the entity equals { nbr[e][d] : d_a in S(c_a) }, S(0) = {-1, 0}, S(1) = {0}, S(2) = {0, 1}
+// (c = the entity's position in the element).  Then the overlap bounds of
+// DofInfo::ComputeOverlapBounds (remhos_tools.cpp:432-495) -- min/max over the elements sharing a
+// lattice entity -- can be formed from the 3^dim neighbourhood values without the entity table.
+// Unstructured vertex valences (e.g. data/periodic-hexagon.mesh) give *structured = 0.
+extern "C" int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t *lat, int32_t *nbr,
+                               int *structured)
+{
+   if (dim != 2 && dim != 3) { set_error("rmh_nbr_lattice: dim must be 2 or 3"); return 1; }
+   int n3 = 1;
+   for (int a = 0; a < dim; a++) { n3 *= 3; }
+   // entity -> elements (CSR)
+   std::vector<int64_t> off((size_t)n_ent + 1, 0);
+   for (int64_t i = 0; i < ne * n3; i++)
+   {
+      if (lat[i] < 0 || lat[i] >= n_ent) { set_error("rmh_nbr_lattice: lat id out of range"); return 1; }
+      off[lat[i] + 1]++;
+   }
+   for (int32_t i = 0; i < n_ent; i++) { off[i + 1] += off[i]; }
+   std::vector<int32_t> el((size_t)ne * n3);
+   {
+      std::vector<int64_t> cur(off.begin(), off.end() - 1);
+      for (int64_t e = 0; e < ne; e++)
+         for (int t = 0; t < n3; t++) { el[cur[lat[e * n3 + t]]++] = (int32_t)e; }
+   }
+   auto members = [&](int64_t e, int t, std::vector<int32_t> &out)
+   {
+      out.clear();
+      const int32_t id = lat[e * n3 + t];
+      for (int64_t k = off[id]; k < off[id + 1]; k++) { out.push_back(el[k]); }
+      std::sort(out.begin(), out.end());
+      out.erase(std::unique(out.begin(), out.end()), out.end());
+   };
+   int ok = 1;
+   std::vector<int32_t> S, T;
+   // pass 1: neighbours, by increasing number of non-zero offset components
+   for (int64_t e = 0; e < ne; e++)
+   {
+      int32_t *nb = nbr + e * n3;
+      for (int t = 0; t < n3; t++) { nb[t] = -2; }
+      for (int nz = 0; nz <= dim; nz++)
+         for (int t = 0; t < n3; t++)
+         {
+            int c[3] = {1, 1, 1}, r = t, cnt = 0;
+            for (int a = 0; a < dim; a++) { c[a] = r % 3; r /= 3; cnt += (c[a] != 1); }
+            if (cnt != nz) { continue; }
+            if (nz == 0) { nb[t] = (int32_t)e; continue; }
+            // elements sharing the entity in direction d = c - 1, minus those reached by the proper
+            // sub-offsets (some components of d zeroed)
+            members(e, t, S);
+            T.clear();
+            for (int m = 0; m < (1 << dim); m++)
+            {
+               int tt = 0, mul = 1;
+               bool proper = false, valid = true;
+               for (int a = 0; a < dim; a++)
+               {
+                  int ca = c[a];
+                  if ((m >> a) & 1) { if (c[a] == 1) { valid = false; } ca = 1; proper = true; }
+                  tt += ca * mul; mul *= 3;
+               }
+               if (!valid || !proper) { continue; }
+               if (nb[tt] >= 0) { T.push_back(nb[tt]); }
+            }
+            std::sort(T.begin(), T.end());
+            T.erase(std::unique(T.begin(), T.end()), T.end());
+            std::vector<int32_t> rest;
+            std::set_difference(S.begin(), S.end(), T.begin(), T.end(), std::back_inserter(rest));
+            if (rest.empty()) { nb[t] = -1; }
+            else if (rest.size() == 1) { nb[t] = rest[0]; }
+            else { nb[t] = rest[0]; ok = 0; }
+         }
+   }
+   // pass 2: the neighbourhood must reproduce every entity's element set
+   for (int64_t e = 0; e < ne && ok; e++)
+   {
+      const int32_t *nb = nbr + e * n3;
+      for (int t = 0; t < n3 && ok; t++)
+      {
+         int c[3] = {1, 1, 1}, r = t;
+         for (int a = 0; a < dim; a++) { c[a] = r % 3; r /= 3; }
+         members(e, t, S);
+         T.clear();
+         for (int d = 0; d < n3; d++)
+         {
+            int q = d;
+            bool in = true;
+            for (int a = 0; a < dim; a++)
+            {
+               const int da = q % 3 - 1; q /= 3;
+               if (!((c[a] == 0 && da <= 0) || (c[a] == 1 && da == 0) || (c[a] == 2 && da >= 0))) { in = false; }
+            }
+            if (in && nb[d] >= 0) { T.push_back(nb[d]); }
+         }
+         std::sort(T.begin(), T.end());
+         T.erase(std::unique(T.begin(), T.end()), T.end());
+         if (T != S) { ok = 0; }
+      }
+   }
+   if (structured) { *structured = ok; }
    return 0;
 }
 

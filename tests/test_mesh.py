@@ -91,3 +91,48 @@ def test_problem_functions_match_oracle():
             if prob in (2, 3, 4) and dim == 3:
                 continue
             assert np.allclose(u0(prob, x, lo, hi), problems.u0(prob, x, lo, hi), rtol=0, atol=2e-15)
+
+
+def _brute_structured(lat, nbr, dim):
+    ne, n3 = lat.shape
+    ent = {}
+    for e in range(ne):
+        for t in range(n3):
+            ent.setdefault(int(lat[e, t]), set()).add(e)
+    for e in range(ne):
+        for t in range(n3):
+            c = [(t // 3 ** a) % 3 for a in range(dim)]
+            T = set()
+            for d in range(n3):
+                da = [(d // 3 ** a) % 3 - 1 for a in range(dim)]
+                if all((c[a] == 0 and da[a] <= 0) or (c[a] == 1 and da[a] == 0) or (c[a] == 2 and da[a] >= 0)
+                       for a in range(dim)) and nbr[e, d] >= 0:
+                    T.add(int(nbr[e, d]))
+            if T != ent[int(lat[e, t])]:
+                return False
+    return True
+
+
+@pytest.mark.parametrize('name,structured', [('cart3p', True), ('cart3', True), ('cart2p', True),
+                                             ('hexagon', False), ('cube01', True)])
+def test_nbr_lattice(name, structured):
+    """rmh_nbr_lattice: the 3^dim neighbourhood of every element derived from the lattice-entity map;
+    `structured` iff it reproduces every entity's element set (so overlap bounds can be formed from
+    neighbour values alone); face directions agree with the face-neighbour map"""
+    import remhos_b200 as rb
+    m = {'cart3p': lambda: rb.Mesh.cartesian([3, 3, 3], [2.] * 3, origin=[-1.] * 3, periodic=True).refine(1),
+         'cart3': lambda: rb.Mesh.cartesian([3, 2, 4], [1.] * 3, periodic=False),
+         'cart2p': lambda: rb.Mesh.cartesian([4, 5], [1.] * 2, periodic=True),
+         'hexagon': lambda: rb.Mesh.load(os.path.join(DATA, 'periodic-hexagon.mesh')).refine(1),
+         'cube01': lambda: rb.Mesh.load(os.path.join(DATA, 'cube01_hex.mesh')).refine(1)}[name]()
+    nbr, ok = m.nbr_lattice()
+    maps = m.dof_maps(1)
+    dim, n3 = m.dim, 3 ** m.dim
+    assert ok == structured
+    assert ok == _brute_structured(maps['lat'], nbr, dim)
+    assert (nbr[:, n3 // 2] == np.arange(nbr.shape[0])).all()
+    # faces: quad S E N W, hex bottom south east north west top -> (axis, side)
+    faces = {2: [(1, 0), (0, 1), (1, 1), (0, 0)], 3: [(2, 0), (1, 0), (0, 1), (1, 1), (0, 0), (2, 1)]}[dim]
+    for f, (axis, side) in enumerate(faces):
+        d = n3 // 2 + (1 if side else -1) * 3 ** axis
+        assert np.array_equal(nbr[:, d], maps['nbr_elem'][:, f]), f
