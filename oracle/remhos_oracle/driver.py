@@ -274,15 +274,20 @@ class Run:
         ElementFCTProjection (remhos_fct.cpp:543-563, 735-758): bounds on s = us / u from the old
         active dofs, compatible LO product, limiter on us, empty dofs zeroed"""
         o, d = self.opt, self.disc
-        assert o.fct_type in (2, 4), 'product remap is restated for -fct 2 and -fct 4'
+        assert o.fct_type in (1, 2, 4), 'product remap is restated for -fct 1, 2 and 4'
         A = d.cur
         s, s_el, s_dof = d.compute_ratio(us, u)
         s_min, s_max = d.bounds(s, o.bounds_type, active_el=s_el, active_dof=s_dof)
+        s_min0, s_max0 = s_min, s_max
         u_new = u + dt * du
         el_new, dof_new = d.bool_indicators(u_new)
         d_lo, s_min, s_max = d.compatible_lo_product(us, A.ml, d_us_ho, s_min, s_max, u_new, el_new,
                                                      dof_new, dt)
         us_min, us_max = d.scale_product_bounds(s_min, s_max, u_new, el_new, dof_new)
+        if o.fct_type == 1:        # NeedsLOProductInput (remhos.cpp:1865-1869)
+            d_us_lo = self.calc_lo(us, d_us_ho, dt)
+            return d.fct_flux_based_product(us, A.ml, d_us_ho, d_us_lo, s_min0, s_max0, u_new, el_new,
+                                            dof_new, dt)
         if o.fct_type == 2:
             d_us = d.fct_clip_scale(us, A.ml, d_us_ho, d_lo, us_min, us_max, dt)
         else:

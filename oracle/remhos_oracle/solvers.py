@@ -483,14 +483,18 @@ class Discretization:
         Mij[same] = A.M[I[same] // nd, I[same] % nd, J[same] % nd]
         return I, J, kij, kji, same, Mij
 
-    def fct_flux_based(self, u, m, du_ho, du_lo, umin, umax, dt, iter_cnt=1):
+    def _flux_matrix(self, u, du_ho, dt):
+        """FluxBasedFCT::ComputeFluxMatrix (remhos_fct.cpp:295-341) on the upper-triangular coupling
+        list: f_ij = dt d_ij (u_i - u_j) + dt M_ij (du_i - du_j)"""
         I, J, kij, kji, same, Mij = self.build_sparse_K_HO()
-        uf = u.reshape(-1); mf = m.reshape(-1); dho = du_ho.reshape(-1)
+        uf = u.reshape(-1); dho = du_ho.reshape(-1)
         dij = np.maximum(np.maximum(0.0, -kij), -kji)
         flux = dt * dij * (uf[I] - uf[J])
         flux = flux + np.where(same, Mij * dt * (dho[I] - dho[J]), 0.0)
-        du_lo_fct = du_lo.reshape(-1).copy()
-        umn = umin.reshape(-1); umx = umax.reshape(-1)
+        return I, J, same, flux
+
+    def _flux_iterate(self, I, J, flux, uf, mf, du_lo_fct, umn, umx, dt, iter_cnt, zero_mask=None):
+        """AddFluxesAtDofs / ComputeFluxCoefficients / UpdateSolutionAndFlux (remhos_fct.cpp:344-446)"""
         du = du_lo_fct.copy()
         for _ in range(iter_cnt):
             gp = np.zeros(self.N); gm = np.zeros(self.N)
@@ -509,5 +513,37 @@ class Discretization:
             np.add.at(du, I, fa / mf[I] / dt)
             np.add.at(du, J, -fa / mf[J] / dt)
             flux = flux - fa
+            if zero_mask is not None:
+                du = np.where(zero_mask, 0.0, du)                     # ZeroOutEmptyDofs
             du_lo_fct = du.copy()
+        return du
+
+    def fct_flux_based(self, u, m, du_ho, du_lo, umin, umax, dt, iter_cnt=1):
+        I, J, same, flux = self._flux_matrix(u, du_ho, dt)
+        du = self._flux_iterate(I, J, flux, u.reshape(-1), m.reshape(-1), du_lo.reshape(-1).copy(),
+                                umin.reshape(-1), umax.reshape(-1), dt, iter_cnt)
         return du.reshape(u.shape)
+
+    def fct_flux_based_product(self, us, m, d_us_ho, d_us_lo, s_min, s_max, u_new, act_el, act_dof, dt,
+                               iter_cnt=1):
+        """FluxBasedFCT::CalcFCTProduct (remhos_fct.cpp:183-294): the flux matrix of (us, d_us_HO),
+        plus the element-local fluxes that turn the LO product into the compatible one, limited
+        against the scaled bounds"""
+        nd = self.nd
+        I, J, same, flux = self._flux_matrix(us, d_us_ho, dt)
+        d_lo_c, s_min, s_max = self.compatible_lo_product(us, m, d_us_ho, s_min, s_max, u_new, act_el,
+                                                          act_dof, dt)
+        us_min, us_max = self.scale_product_bounds(s_min, s_max, u_new, act_el, act_dof)
+        flux_el = m * dt * (d_us_lo - d_lo_c)
+        beta = m * u_new
+        with np.errstate(divide='ignore', invalid='ignore'):
+            beta = beta / beta.sum(axis=1)[:, None]
+        e = I // nd
+        add = same & act_el[e]
+        i_loc, j_loc = I % nd, J % nd
+        fij = beta[e, j_loc] * flux_el[e, i_loc] - beta[e, i_loc] * flux_el[e, j_loc]
+        flux = flux + np.where(add, fij, 0.0)
+        zero = (~act_el[:, None] & ~act_dof).reshape(-1)
+        du = self._flux_iterate(I, J, flux, us.reshape(-1), m.reshape(-1), d_lo_c.reshape(-1).copy(),
+                                us_min.reshape(-1), us_max.reshape(-1), dt, iter_cnt, zero_mask=zero)
+        return du.reshape(us.shape)
