@@ -449,6 +449,8 @@ class Discretization:
         """Upper-triangular coupling list of K_HO (volume blocks + face blocks) for the
         flux-based FCT: arrays (I, J, kij, kji, same_elem, Mij)."""
         A, sp = self.cur, self.sp
+        if getattr(A, '_sparse_K_HO', None) is not None:          # same assembled operators: reuse
+            return A._sparse_K_HO
         ne, nd = self.ne, self.nd
         import scipy.sparse as sps
         base = (np.arange(ne) * nd)[:, None, None]
@@ -481,7 +483,8 @@ class Discretization:
         same = (I // nd) == (J // nd)
         Mij = np.zeros(I.size)
         Mij[same] = A.M[I[same] // nd, I[same] % nd, J[same] % nd]
-        return I, J, kij, kji, same, Mij
+        A._sparse_K_HO = (I, J, kij, kji, same, Mij)
+        return A._sparse_K_HO
 
     def _flux_matrix(self, u, du_ho, dt):
         """FluxBasedFCT::ComputeFluxMatrix (remhos_fct.cpp:295-341) on the upper-triangular coupling
