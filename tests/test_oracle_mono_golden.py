@@ -15,6 +15,8 @@ from helpers import oracle_run
 
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'known_answers.json')) as f:
     ROWS = json.load(f)['rows']
+if os.environ.get('RMH_SLOW_TESTS', '0') != '1':
+    ROWS = [r for r in ROWS if not r.get('slow')]
 
 
 @pytest.mark.parametrize('row', ROWS, ids=[r['name'] for r in ROWS])
