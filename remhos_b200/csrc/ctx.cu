@@ -2751,7 +2751,7 @@ extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, doub
                         const double *u, double *k, void *stream)
 {
    if (c->mono_type) { return rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t, dt, u, k, stream); }
-   if (ho_type == 3 && lo_type == 5 && fct_type == 2)
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control)
    {
       if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
       if (rmh_set_time(c, t, stream)) { return 1; }
@@ -2791,7 +2791,8 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
                             double dt, double *u, void *stream)
 {
    cudaStream_t s = (cudaStream_t)stream;
-   if (!c->mono_type && ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 && ode <= 3)
+   // (with automatic time step control the LO rate must be visible to the dt estimate: unfused path)
+   if (!c->mono_type && !c->dt_control && ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 && ode <= 3)
    { return rmh_rk_step(c, ode, lo_type, t, dt, u, stream); }
    const double t0 = *t;
    const size_t bytes = (size_t)c->N * sizeof(double);
