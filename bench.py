@@ -6,13 +6,16 @@ Workload (config C2): 3D periodic cube [-1,1]^3, 3x3x3 coarse
 problem 0 (erfc bump, constant velocity), `-ho 3 -lo 5 -fct 2 -pa -s 3`: LocalInverse HO +
 MassBasedAvg LO + ClipScale FCT, RK3-SSP.  A "step" is one RK3 time step = 3 fused stage
 launches; value = DOFs * 3 * steps / time, summed over ranks (weak scaling: every rank owns a
-full cube of the same size).
+(3*2^rs)^3 brick of a periodic box that grows with the rank count).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--order P] [--problem Q]
 
 Prints one JSON line (see the task contract): value (state resident in HBM), e2e (host state,
-H2D + D2H inside the timed region, through rmh_rk_step_host), roofline of the fused stage
-kernel, cpu_baseline (the CPU oracle timed on the host cores on a bounded sample).
+H2D + D2H inside the timed region, through rmh_rk_step_host / rmh_dist_rk_step_host), roofline of
+the fused stage kernel, cpu_baseline (the CPU oracle port timed on the host cores on a bounded
+sample), and -- N = 1 -- `extra`: the same metric on the general-velocity and remap paths.
+With N > 1 the line also carries check.dist_rel_err: decomposed vs single-GPU runs of a small
+global problem (orders 3 and 4, both bounds types), which must agree to 1e-12.
 """
 import argparse
 import json
@@ -27,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = 136.0          # algorithmic bytes per DOF*stage (five kernels)
+B_ALG = 136.0          # algorithmic bytes per DOF*stage of five UNFUSED kernels
 STAGES = 3             # RK3-SSP
 
 
@@ -37,6 +40,18 @@ def read_peaks():
             return float(json.load(f)['hbm_gbs']), 'measured'
     except Exception:
         return 6650.0, 'fallback'
+
+
+def read_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the stage kernel, from the ncu
+    --set full captures summarised in profiles/traffic.json (keyed by kernel|order|rs|problem);
+    None when no capture of this exact workload is committed."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            e = json.load(f).get(key)
+        return (float(e['dram_bytes']), e.get('source')) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -100,56 +115,175 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(order, seconds=12.0, rs=3):
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_port_run(order, rs, problem, steps, warmup, budget_s):
     """The C/OpenMP port of the stage path (oracle/c/remhos_stage.c: same algorithm as the
-    reference's `-ho 3 -lo 5 -fct 2 -pa -s 3` path, sum-factorised, all host threads) on the same
-    workload shrunk to -rs `rs`, timed on this box's host cores.  The reference's own MFEM/MPI
-    build cannot be produced in this image, so this is a port, not the reference."""
+    reference's `-ho 3 -lo 5 -fct 2 -pa -s 3` path, sum-factorised, all host threads) on the bench
+    workload at -rs `rs`, inputs built by the oracle's own mesh code (no product library is loaded
+    on this path).  The reference's own MFEM/MPI build cannot be produced in this image (SURVEY.md
+    8c), so this is a port, not the reference.  Times `steps` RK3 steps (fewer when `budget_s`
+    runs out first)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import remhos_b200 as rb
-    from remhos_b200.setup_problem import Problem
     from remhos_oracle.cport import Port
-    mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
-    mesh.refine(rs)
-    h = 2.0 / (3 * 2 ** rs)
+    cores = host_cores()
+    Port.set_threads(cores)           # launchers such as torchrun export OMP_NUM_THREADS=1
+    n = 3 * 2 ** rs
+    port, u0 = Port.periodic_cube(n, order, problem)
+    h = 2.0 / n
     dt = 0.25 * h / order
-    prob = Problem(mesh, problem=0, order=order, mesh_order=2, bounds_type=0, dt=dt,
-                   create_ctx=False)
-    i = prob.inputs
-    port = Port(order, 2, 0, i['nodes'], i['nbr_dof'], i['lat'], i['n_ent'],
-                vel_nodes=i.get('vel_nodes'), vel_quad=i.get('vel_quad'), vel_face=i.get('vel_face'))
-    u = np.ascontiguousarray(prob.u0, dtype=np.float64).copy()
-    n = u.size
+    u = np.ascontiguousarray(u0, dtype=np.float64).reshape(-1).copy()
+    ndof = u.size
     m = port.lumped_mass().reshape(-1)
     mass0 = float((m * u).sum())
-    port.rk3_step(0.0, dt, u)               # warm-up
     t0 = time.perf_counter()
-    steps = 0
-    while True:
+    for _ in range(max(1, warmup)):
         port.rk3_step(0.0, dt, u)
-        steps += 1
-        if time.perf_counter() - t0 > seconds:
+        if time.perf_counter() - t0 > 0.25 * budget_s:
+            break
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        port.rk3_step(0.0, dt, u)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
             break
     el = time.perf_counter() - t0
     drift = abs(float((m * u).sum()) - mass0) / abs(mass0)
-    cores = Port.threads()
+    threads = Port.threads()
     port.close()
-    return {'value': n * STAGES * steps / el, 'unit': 'DOF*stage/s', 'cores': int(cores),
-            'kind': 'port',
+    return {'value': ndof * STAGES * done / el, 'unit': 'DOF*stage/s', 'cores': int(threads),
+            'kind': 'port', 'steps_timed': done, 'ms_per_step': 1e3 * el / done,
             'sample': 'C/OpenMP port of the stage path (oracle/c), periodic cube -rs %d order %d '
                       '(%d DOFs), %d RK3 steps in %.1f s, %d threads, mass drift %.1e'
-                      % (rs, order, n, steps, el, cores, drift)}
+                      % (rs, order, ndof, done, el, threads, drift)}
+
+
+def dist_parity_check(rank, world, local_rank):
+    """Decomposed vs single-GPU: 2 RK3 steps of a small global problem (periodic 12^3 cube), orders 3
+    and 4, overlap (-bt 0) and sparsity (-bt 1) bounds; every rank's owned part is compared on rank 0
+    with the single-GPU run of the same global mesh.  Returns the worst relative error (max norm)."""
+    import torch
+    import torch.distributed as dist
+    import remhos_b200 as rb
+    from remhos_b200.dist import DistProblem
+    from remhos_b200.setup_problem import Problem
+    worst, cases = 0.0, []
+    for order, bt in ((3, 0), (3, 1), (4, 0), (4, 1)):
+        n = 12
+        dt = 0.25 * (2.0 / n) / order
+        mesh = rb.Mesh.cartesian([n, n, n], [2.0] * 3, origin=[-1.0] * 3, periodic=True)
+        dp = DistProblem(mesh, rank, world, problem=0, order=order, bounds_type=bt, dt=dt, device=local_rank)
+        dp.ctx.trust_state(True)
+        u = torch.tensor(dp.u0, device='cuda')
+        t = 0.0
+        for _ in range(2):
+            t = dp.rk3_step(t, u)
+        torch.cuda.synchronize()
+        mine = (dp.plan.owned.copy(), u.cpu().numpy().reshape(dp.n_owned, -1))
+        box = [None] * world
+        dist.all_gather_object(box, mine)
+        err = 0.0
+        if rank == 0:
+            mesh1 = rb.Mesh.cartesian([n, n, n], [2.0] * 3, origin=[-1.0] * 3, periodic=True)
+            p1 = Problem(mesh1, problem=0, order=order, bounds_type=bt, dt=dt, device=local_rank)
+            u1 = torch.tensor(p1.u0, device='cuda')
+            t1 = 0.0
+            for _ in range(2):
+                t1 = p1.ctx.rk_step(3, 5, t1, dt, u1)
+            ref = u1.cpu().numpy().reshape(mesh1.ne, -1)
+            seen = np.zeros(mesh1.ne, dtype=bool)
+            for ids, vals in box:
+                err = max(err, float(np.abs(vals - ref[ids]).max() / np.abs(ref).max()))
+                seen[ids] = True
+            assert seen.all()
+            p1.close()
+        dp.close()
+        cases.append({'order': order, 'bounds_type': bt, 'rel_err': err})
+        worst = max(worst, err)
+    return worst, cases
+
+
+def extra_runs(order, rs, local_rank, steps=20):
+    """The general paths, same metric, driver-visible: problem 1 (rotation: velocity varies inside an
+    element -> FP64 tensor-core kernel k_stage3w) on the bench mesh, and remap (problem 10 on the
+    refined unit cube: quadrature data rebuilt every stage, non-affine mass solve)."""
+    import torch
+    import remhos_b200 as rb
+    from remhos_b200.setup_problem import Problem
+    out = {}
+
+    def timed(ctx, u, dt, nst):
+        t = 0.0
+        for _ in range(2):
+            t = ctx.rk_step(3, 5, t, dt, u)
+        torch.cuda.synchronize()
+        ctx.profile(1)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nst):
+            t = ctx.rk_step(3, 5, t, dt, u)
+        e1.record()
+        torch.cuda.synchronize()
+        kms, kl = ctx.profile(0)
+        return e0.elapsed_time(e1), kms / max(kl, 1)
+    try:
+        mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+        mesh.refine(rs)
+        dt = 0.25 * (2.0 / (3 * 2 ** rs)) / order
+        prob = Problem(mesh, problem=1, order=order, mesh_order=2, bounds_type=0, dt=dt, device=local_rank)
+        prob.ctx.trust_state(True)
+        u = torch.tensor(prob.u0, device='cuda')
+        ms, kms = timed(prob.ctx, u, dt, steps)
+        n = prob.ctx.ndofs
+        tr, src = read_traffic('k_stage3w|o%d|rs%d|p1' % (order, rs))
+        peak, _ = read_peaks()
+        out['problem1_rotation'] = {
+            'workload': '3D periodic-cube transport, order %d, -rs %d, problem 1 (rotation)' % (order, rs),
+            'value': n * STAGES * steps / (ms * 1e-3), 'unit': 'DOF*stage/s', 'ms_per_step': ms / steps,
+            'steps': steps, 'kernel': 'k_stage3w (FP64 DMMA, stored quadrature data)', 'kernel_ms': kms,
+            'traffic': tr, 'frac': (tr / (kms * 1e-3) / 1e9 / peak) if tr else None, 'traffic_source': src}
+        prob.close()
+        del u, prob, mesh
+        torch.cuda.empty_cache()
+    except Exception as ex:                                    # the headline line must survive
+        out['problem1_rotation'] = {'error': repr(ex)[:300]}
+    try:
+        mesh = rb.Mesh.cartesian([2, 2, 2], [1.0, 1.0, 1.0])
+        mesh.refine(min(rs, 5))
+        prob = Problem(mesh, problem=10, order=order, mesh_order=2, bounds_type=0, dt=-1.0, t_final=0.5,
+                       device=local_rank)
+        u = torch.tensor(prob.u0, device='cuda')
+        nst = max(3, steps // 4)
+        ms, kms = timed(prob.ctx, u, prob.dt, nst)
+        n = prob.ctx.ndofs
+        out['remap'] = {
+            'workload': 'remap -p 10 (Taylor-Green mesh motion), unit cube -rs %d, order %d, operators '
+                        'rebuilt every stage' % (min(rs, 5), order),
+            'value': n * STAGES * nst / (ms * 1e-3), 'unit': 'DOF*stage/s', 'ms_per_step': ms / nst,
+            'steps': nst, 'dofs': n, 'stage_kernel_ms': kms}
+        prob.close()
+    except Exception as ex:
+        out['remap'] = {'error': repr(ex)[:300]}
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--rs', type=int, default=5)
     ap.add_argument('--order', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--no-dist-check', action='store_true')
     ap.add_argument('--problem', type=int, default=0,
                     help='0: constant velocity (BASELINE config); 1: rotation (velocity linear in x: '
                          'exercises the general FP64 tensor-core kernel)')
@@ -163,14 +297,17 @@ def main():
 
     if a.impl == 'reference':
         # the reference's MPI CPU build cannot be produced here (needs MFEM/hypre/METIS/MPI,
-        # SURVEY.md 8c): the reference arm times the CPU oracle port on the host cores
+        # SURVEY.md 8c): the reference arm times the CPU oracle port on the host cores, same -rs
+        # as the GPU arm, all host threads (set explicitly: torchrun exports OMP_NUM_THREADS=1)
         if rank != 0:
             return
-        cb = cpu_baseline(a.order, seconds=max(5.0, 2.0 * a.steps), rs=min(a.rs, 4))
+        cb = cpu_port_run(a.order, a.rs, a.problem, steps=a.steps, warmup=min(a.warmup, 2), budget_s=75.0)
         line = {'impl': 'reference', 'metric': metric, 'value': cb['value'], 'unit': 'DOF*stage/s',
-                'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': None,
+                'n_gpus': a.gpus, 'steps': cb['steps_timed'], 'warmup': a.warmup,
+                'ms_per_step': cb['ms_per_step'],
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-                'data': 'synthetic', 'config': {'workload': workload, 'sample': cb['sample']},
+                'data': 'synthetic', 'config': {'workload': workload, 'sample': cb['sample'],
+                                                'note': 'one host, %d threads, independent of --gpus' % cb['cores']},
                 'cpu_baseline': cb,
                 'e2e': {'value': cb['value'], 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}}
@@ -190,6 +327,10 @@ def main():
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
+    dist_err, dist_cases = None, None
+    if world > 1 and not a.no_dist_check:
+        dist_err, dist_cases = dist_parity_check(rank, world, local_rank)
+
     h = 2.0 / (3 * 2 ** a.rs)
     dt = 0.25 * h / a.order            # fixed dt = 0.25 h/|v| /p, |v| = 1
     if world == 1:
@@ -198,13 +339,12 @@ def main():
         prob = Problem(mesh, problem=a.problem, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
                        device=local_rank)
         ctx = prob.ctx
-        # the time loop below never touches the state between steps (neither does the reference's,
-        # remhos.cpp:1146-1330): the element min/max the last stage computes for its output are
-        # reused by the next step instead of a separate pass over the state
-        ctx.trust_state(True)
 
         def step(t, u, stream):
             return ctx.rk_step(3, 5, t, dt, u, stream)
+
+        def step_host(t, uh):
+            return ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
         pdims = [1, 1, 1]
     else:
         # weak scaling: every rank owns a (3*2^rs)^3 brick of a periodic box that grows with the
@@ -220,23 +360,24 @@ def main():
                            bounds_type=0, dt=dt, device=local_rank)
         del mesh
         ctx = prob.ctx
-        prob.trust_state = True      # as in the single-GPU loop: the state is not touched between steps
 
         def step(t, u, stream):
-            return prob.rk3_step(t, u, stream)
+            return prob.dist.rk_step(3, 5, t, dt, u, stream)
+
+        def step_host(t, uh):
+            return prob.dist.rk_step_host(3, 5, t, dt, uh.data_ptr())
+    # the time loop below never touches the state between steps (neither does the reference's,
+    # remhos.cpp:1146-1330): the element min/max the last stage computes for its output are
+    # reused by the next step instead of a separate pass over the state
+    ctx.trust_state(True)
     N = ctx.ndofs
     u = torch.tensor(prob.u0, device='cuda')
     m = torch.empty(N, dtype=torch.float64, device='cuda')
     ctx.lumped_mass(m)
 
-    def gsum(v, op='sum'):
-        if world == 1:
-            return v
-        tt = torch.tensor([v], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op={'sum': dist.ReduceOp.SUM, 'min': dist.ReduceOp.MIN,
-                                'max': dist.ReduceOp.MAX}[op])
-        return float(tt[0])
-    mass0 = gsum(ctx.reduce(0, u, m))
+    def gred(v, op='sum'):
+        return v if world == 1 else prob.allreduce(v, op)      # ncclAllReduce under the C ABI
+    mass0 = gred(ctx.reduce(0, u, m))
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -263,28 +404,18 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = rb.launch_count(reset=True)
     kms, klaunch = ctx.profile(0)
-    mass1 = gsum(ctx.reduce(0, u, m))
-    umin, umax = gsum(ctx.reduce(1, u), 'min'), gsum(ctx.reduce(2, u), 'max')
+    mass1 = gred(ctx.reduce(0, u, m))
+    umin, umax = gred(ctx.reduce(1, u), 'min'), gred(ctx.reduce(2, u), 'max')
 
     # end-to-end: state in pinned host memory, H2D + step + D2H every step
     uh = u.cpu().pin_memory()
-
-    def step_host(t):
-        if world == 1:
-            return ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
-        u.copy_(uh, non_blocking=True)
-        prob._xe_for = None          # fresh state from the host: recompute its element min/max
-        t = step(t, u, stream)
-        uh.copy_(u, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return t
     for _ in range(2):
-        step_host(t)
+        step_host(t, uh)
     barrier()
     t0 = time.perf_counter()
-    e_steps = max(3, a.steps // 2)
+    e_steps = max(3, min(a.steps // 2, 30))
     for _ in range(e_steps):
-        step_host(t)
+        step_host(t, uh)
     barrier()
     e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop(t_wall0, time.time())
@@ -298,21 +429,32 @@ def main():
     e2e = total_dofs * STAGES * e_steps / (e_ms * 1e-3)
     peak, which = read_peaks()
     k_ms = kms / max(klaunch, 1)
-    achieved = B_ALG * N / (k_ms * 1e-3) / 1e9 if klaunch else None
     # which fused stage kernel ran (rmh_ctx_path_flags): bit 3 = constant-coefficient kernel
-    # (affine elements, element-wise constant velocity: stage3c.cuh), else the FP64 DMMA kernel
-    const_op = bool(ctx.path_flags & 8)
-    if const_op:
-        kname = 'k_stage3c<%d> (constant-coefficient line kernel, %d elements per warp)' % (
-            a.order + 1, {1: 8, 2: 2, 3: 2, 4: 1}.get(a.order, 1))
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-        # workload (profiles/r01/ncu_stage_v12_const_rs5.txt)
-        traffic = (1.255223e9 + 441.227776e6) if (a.order == 3 and a.rs == 5) else None
+    # (affine elements, element-wise constant velocity: stage3c.cuh), bit 4 = with the overlap
+    # bounds formed in the kernel; else the FP64 DMMA kernel
+    flags = ctx.path_flags
+    if flags & 8:
+        kid = 'k_stage3c_fold' if flags & 16 else 'k_stage3c'
+        kname = 'k_stage3c<%d,...,%s,%s> (constant-coefficient line kernel, %d elements per warp)' % (
+            a.order + 1, 'ghosts' if world > 1 else 'local', 'fold' if flags & 16 else 'entities',
+            {1: 8, 2: 2, 3: 2, 4: 1}.get(a.order, 1))
     else:
-        kname = 'k_stage3w<%d,%d,%s> (FP64 DMMA, warp per element)' % (
-            a.order + 1, a.order + 3, '8,2' if a.order <= 3 else '6,2')
-        # profiles/r01/ncu_stage_v9_hoisted_rs5.txt
-        traffic = (7.000267e9 + 458.27968e6) if (a.order == 3 and a.rs == 5) else None
+        kid = 'k_stage3w'
+        kname = 'k_stage3w<%d,%d> (FP64 DMMA, warp per element)' % (a.order + 1, a.order + 3)
+    traffic, tsrc = read_traffic('%s|o%d|rs%d|p%d' % (kid, a.order, a.rs, a.problem))
+    roof = {'bound': 'hbm', 'kernel': kname, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
+            # the kernel's own DRAM traffic (ncu) over its own time (CUDA events, this run)
+            'traffic': traffic, 'traffic_unit': 'bytes per launch', 'traffic_source': tsrc,
+            'achieved': (traffic / (k_ms * 1e-3) / 1e9) if (traffic and klaunch) else None,
+            'frac': (traffic / (k_ms * 1e-3) / 1e9 / peak) if (traffic and klaunch) else None,
+            'traffic_bytes_per_dof': (traffic / N) if traffic else None,
+            # SURVEY.md 8d's algorithmic figure: 136 B/DOF*stage of five separate kernels -- what an
+            # unfused implementation at HBM speed would need; > 1 means faster than that bound
+            'alg_bytes_per_dof_stage': B_ALG,
+            'frac_vs_unfused_136B': (B_ALG * N / (k_ms * 1e-3) / 1e9 / peak) if klaunch else None,
+            'frac_of_fused_lower_bound_56B': (56.0 * N / (k_ms * 1e-3) / 1e9 / peak) if klaunch else None,
+            'kernel_ms': k_ms, 'kernel_launches': int(klaunch),
+            'kernel_share_of_step': (kms / ms) if klaunch else None}
     line = {
         'metric': metric, 'value': value, 'unit': 'DOF*stage/s', 'n_gpus': world,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps,
@@ -322,31 +464,35 @@ def main():
                    'stages_per_step': STAGES, 'dt': dt,
                    'l2': 'state vectors (453 MB each at -rs 5) exceed the 126 MB L2',
                    'problem': a.problem,
-                   'parallelism': ('domain decomposition %dx%dx%d bricks, NCCL halo exchange per stage'
+                   'parallelism': ('domain decomposition %dx%dx%d bricks; per stage one put kernel (face '
+                                   'traces + (min,max) pairs stored into the peers\' windows over NVLink) '
+                                   'and one stage kernel that waits for the halo before its shell elements'
                                    % tuple(pdims)) if world > 1 else 'single GPU'},
         'e2e': {'value': e2e, 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 8 * N,
                 'd2h_bytes_per_step': 8 * N, 'steps': e_steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'bound': 'hbm',
-                     'kernel': kname,
-                     'achieved': achieved, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
-                     'frac': (achieved / peak) if achieved else None,
-                     'traffic': traffic, 'traffic_unit': 'bytes per launch',
-                     # the fused kernel moves far less than the 136 B/DOF of five separate kernels:
-                     # its own DRAM traffic over its own time, as a fraction of the HBM peak
-                     'traffic_frac_of_peak': (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                     # the same against SURVEY.md 8d's fused lower bound (56 B/DOF*stage: the "stretch" figure)
-                     'frac_of_fused_lower_bound_56B': (56.0 * N / (k_ms * 1e-3) / 1e9 / peak) if klaunch else None,
-                     'alg_bytes_per_dof_stage': B_ALG, 'kernel_ms': k_ms,
-                     'kernel_share_of_step': (kms / ms) if klaunch else None},
+        'roofline': roof,
         'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0), 'u_min': umin, 'u_max': umax},
     }
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline(a.order)
+    if world > 1:
+        line['check']['dist_rel_err'] = dist_err
+        line['check']['dist_cases'] = dist_cases
+        if dist_err is not None and not (dist_err < 1e-12):
+            line['check']['dist_FAILED'] = True
+    if world == 1:
+        prob.close()
+        del u, m, prob
+        torch.cuda.empty_cache()
+        if not a.no_extras:
+            line['extra'] = extra_runs(a.order, a.rs, local_rank)
+        if rank == 0 and not a.no_cpu_baseline:
+            cb = cpu_port_run(a.order, min(a.rs, 4), a.problem, steps=10 ** 6, warmup=1, budget_s=12.0)
+            line['cpu_baseline'] = cb
+    else:
+        prob.close()
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -76,6 +76,9 @@ int rmh_halo_sizes(const rmh_halo *h, int64_t *n_owned, int64_t *n_ghost, int32_
                    int64_t *n_send);
 int rmh_halo_get(const rmh_halo *h, int64_t *owned, int64_t *ghost, int32_t *peers,
                  int32_t *send_off, int32_t *recv_off, int32_t *send_local);
+/* reorder the owned elements: those no peer needs (sharing no vertex with a ghost element) first, in
+ * their previous relative order; *n_interior receives their number.  Call before rmh_halo_get. */
+int rmh_halo_interior_first(rmh_halo *h, int64_t *n_interior);
 
 /* DofInfo integer maps (remhos_tools.cpp:356-379):
  *   bdr_dofs [nfd][nf]      ExtractBdrDofs        (:1356-1431)   (row-major nfd x nf)
@@ -142,7 +145,8 @@ typedef struct rmh_desc
                                 quadrature points (VectorFunctionCoefficient, remhos.cpp:537),
                                 may be NULL */
    const double *vel_face;   /* host [ne][nf][Q^(dim-1)][dim] same at face quadrature points */
-   const int32_t *nbr_dof;   /* host [ne][nf][nfd]; ids >= ne*nd address ghost DOFs */
+   const int32_t *nbr_dof;   /* host [ne][nf][nfd]; ids >= ne*nd address DOFs of ghost elements (only their
+                                face traces are ever exchanged: rmh_dplan_*) */
    const int32_t *lat;       /* host [ne][3^dim] (bounds_type 0), ids < n_ent */
    int32_t n_ent;
    const int32_t *nbr_elem;  /* host [ne][nf] (bounds_type 1), -1 boundary, >= ne ghost */
@@ -157,7 +161,9 @@ int rmh_ctx_nq1d(const rmh_ctx *ctx);
 /* which stage-kernel path this context takes (diagnostics, tests): bit 0 every element has a
  * constant Jacobian, bit 1 stored quadrature data is in tensor-core fragment order, bit 2 the
  * velocity is linear over every element (quadrature data rebuilt in-kernel from 12 doubles per
- * element instead of streamed; set RMH_NO_LINEAR_OP=1 before rmh_ctx_create to disable) */
+ * element instead of streamed; opt-in with RMH_LINEAR_OP=1), bit 3 the constant-coefficient stage kernel
+ * applies (affine elements, element-wise constant velocity), bit 4 the overlap bounds are formed inside
+ * that kernel from the 3x3x3 element neighbourhoods (structured vertex topology; RMH_NO_FOLD=1 disables) */
 int rmh_ctx_path_flags(const rmh_ctx *ctx);
 /* on != 0: the caller promises not to modify the state vector between consecutive rmh_rk_step()
  * calls on the same device pointer (the reference's time loop does not, remhos.cpp:1146-1330).
@@ -317,32 +323,64 @@ int rmh_rk_step(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, doubl
 int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, double dt,
                      double *u_host);
 
-/* Overlap of the halo exchange with interior work (replaces the blocking ExchangeFaceNbrData of
- * remhos.cpp:1813 inside K.Mult): order the owned elements so that [0, n_interior) share no vertex
- * with a ghost element, declare that with rmh_dist_split, then per stage
- *   rmh_halo_pack -> (NCCL exchange on a side stream) || rmh_rk_stage_part(part 1)
- *   -> rmh_halo_set -> rmh_rk_stage_part(part 2).
- * Parts 1 + 2 equal one rmh_rk_stage_dist.  Needs overlap bounds (-bt 0) and the
- * constant-coefficient stage kernel (rmh_ctx_path_flags bit 3). */
-int rmh_dist_split(rmh_ctx *ctx, int64_t n_interior);
-int rmh_rk_stage_part(rmh_ctx *ctx, int lo_type, double dt, double a, double b, const double *x0_dev,
-                      const double *y_dev, double *out_dev, int part, void *stream);
-
-/* ---- multi-GPU: one context per rank; ghost elements follow the owned ones in every index map.
- * These replace ParGridFunction::ExchangeFaceNbrData (remhos.cpp:1813; inside K.Mult) and the
- * GroupCommunicator min/max reduction of DofInfo::ComputeOverlapBounds (remhos_tools.cpp:463-466):
- * the caller moves the packed buffers with NCCL (torch.distributed) between pack and set. */
-/* element min/max of y into the context (needed before the first rmh_halo_pack of a step) */
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: the mesh decomposed over the GPUs of one node, one context per rank (one process per
+ * GPU, or several contexts in one process).  Replaces ParGridFunction::ExchangeFaceNbrData
+ * (remhos.cpp:1813; inside K.Mult), the GroupCommunicator min/max reduction of
+ * DofInfo::ComputeOverlapBounds (remhos_tools.cpp:463-466) and the MPI_Allreduce of mass / min / max /
+ * dt (remhos.cpp:538-553,1073-1076,1403-1415).
+ *
+ * Set-up per rank:
+ *   rmh_mesh_partition -> rmh_halo_create -> rmh_halo_interior_first -> rmh_mesh_extract(owned + ghost)
+ *   -> rmh_mesh_dof_maps -> rmh_ctx_create(ne = owned, ne_ghost = ghost ring)
+ *   -> rmh_dplan_create -> rmh_dist_create -> rmh_dist_export
+ *   -> [the caller all-gathers the blobs: any transport] -> rmh_dist_connect.
+ * Per stage the exchange is one kernel that stores face traces (nfd values per shared face, in the
+ * receiver's face order) and ring-element (min,max) pairs straight into the peers' windows over
+ * NVLink and publishes an epoch flag; the stage kernel runs interior elements first and waits for
+ * the flags before its first shell element.  On a decomposed context, step only through rmh_dist_*.
+ * ---------------------------------------------------------------------------------------- */
+/* element min/max of y into the context (needed before the first stage of a step when the state
+ * was modified from outside) */
 int rmh_stage_minmax(rmh_ctx *ctx, const double *y_dev, void *stream);
-/* send_u [n_send][nd] DOF blocks and send_mm [n_send][2] (min,max) of the listed owned elements */
-int rmh_halo_pack(rmh_ctx *ctx, const double *u_dev, const int32_t *send_local_dev, int64_t n_send,
-                  double *send_u_dev, double *send_mm_dev, void *stream);
-/* install received ghost data: ghost_u [ne_ghost][nd] (pointer kept), ghost_mm [ne_ghost][2] */
-int rmh_halo_set(rmh_ctx *ctx, const double *ghost_u_dev, const double *ghost_mm_dev, void *stream);
-/* rmh_rk_stage for a decomposed mesh: assumes the ghosts of y are installed; leaves the element
- * min/max of `out` in the context (bounds_type 0) for the next pack */
-int rmh_rk_stage_dist(rmh_ctx *ctx, int lo_type, double dt, double a, double b,
-                      const double *x0_dev, const double *y_dev, double *out_dev, void *stream);
+
+/* host-only exchange plan (dplan.cpp); nbr_dof = the owned rows [ne][nf][nfd] of rmh_mesh_dof_maps on
+ * the local (owned + ghost) mesh */
+typedef struct rmh_dplan rmh_dplan;
+int rmh_dplan_create(const rmh_halo *h, int rank, int world, int dim, int order, const int32_t *nbr_dof,
+                     rmh_dplan **out);
+int rmh_dplan_free(rmh_dplan *p);
+int64_t rmh_dplan_blob_bytes(const rmh_dplan *p);
+int rmh_dplan_export(const rmh_dplan *p, void *blob);
+/* blobs[r] = what rank r exported; fills this rank's send tables */
+int rmh_dplan_connect(rmh_dplan *p, int n_blobs, const void *const *blobs, const int64_t *sizes);
+int rmh_dplan_sizes(const rmh_dplan *p, int64_t *ne, int64_t *ne_ghost, int64_t *n_slots, int32_t *n_peers);
+/* per ghost-face slot (scan order over (element, face) with a ghost neighbour): the ghost element */
+int rmh_dplan_slot_ghosts(const rmh_dplan *p, int32_t *slot_ghost);
+int rmh_dplan_peer(const rmh_dplan *p, int k, int32_t *rank, int64_t *n_tr, int64_t *n_mm, int32_t *flag_slot);
+/* tr_src own DOF index -> tr_dst index in the peer's ghost trace array [n_slots][nfd];
+ * mm_src own element -> mm_dst index in the peer's (min,max) pair array [ne + ne_ghost] */
+int rmh_dplan_peer_tables(const rmh_dplan *p, int k, int32_t *tr_src, int32_t *tr_dst, int32_t *mm_src,
+                          int32_t *mm_dst);
+
+/* device layer.  n_interior: the leading owned elements that share no vertex with a ghost element
+ * (rmh_halo_interior_first).  The plan must outlive the rmh_dist. */
+typedef struct rmh_dist rmh_dist;
+int rmh_dist_create(rmh_ctx *ctx, rmh_dplan *plan, int rank, int world, int64_t n_interior, rmh_dist **out);
+int64_t rmh_dist_blob_bytes(const rmh_dist *d);
+/* blob = window handle (CUDA IPC) + NCCL id (rank 0) + the plan's requests */
+int rmh_dist_export(rmh_dist *d, void *blob);
+int rmh_dist_connect(rmh_dist *d, int n_blobs, const void *const *blobs, const int64_t *sizes);
+/* all ranks must have finished stepping (barrier) before any rank destroys its layer or context */
+int rmh_dist_destroy(rmh_dist *d);
+/* rmh_rk_stage / rmh_rk_step / rmh_rk_step_host on the decomposed mesh (-ho 3 -lo 5 -fct 2, transport) */
+int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0_dev,
+                      const double *y_dev, double *out_dev, void *stream);
+int rmh_dist_rk_step(rmh_dist *d, int ode_solver_type, int lo_type, double *t, double dt, double *u_dev,
+                     void *stream);
+int rmh_dist_rk_step_host(rmh_dist *d, int ode_solver_type, int lo_type, double *t, double dt, double *u_host);
+/* op 0 sum, 1 min, 2 max over the ranks, in place on n <= 16 host doubles (ncclAllReduce); collective */
+int rmh_dist_allreduce(rmh_dist *d, int op, double *vals, int n, void *stream);
 
 /* reductions over owned DOFs: op 0 = sum(a*b) (b may be NULL -> sum a), 1 = min(a), 2 = max(a)
  * (remhos.cpp:1073-1076,1403-1415; GetMinMax remhos_tools.cpp:1433-1439); result on host */

@@ -432,6 +432,16 @@ void roc_lumped_mass(const roc_t *c, double *m)
    memcpy(m, c->ml, sizeof(double) * (size_t)c->ne * c->D1 * c->D1 * c->D1);
 }
 
+/* n > 0: use n OpenMP threads from now on (launchers such as torchrun export OMP_NUM_THREADS=1) */
+void roc_set_threads(int n)
+{
+#ifdef _OPENMP
+   if (n > 0) { omp_set_num_threads(n); }
+#else
+   (void)n;
+#endif
+}
+
 int roc_threads(void)
 {
 #ifdef _OPENMP

@@ -72,6 +72,24 @@ class Port:
                                       axis=1)
         return cls(sp.p, sp.g, run.exec_mode, m.X, d.nbr, topo.lat, topo.n_ent, **kw)
 
+    @classmethod
+    def periodic_cube(cls, n, order, problem=0, mesh_order=2):
+        """The bench workload built with the oracle's own mesh code only (no product library):
+        periodic Cartesian n^3 hexes on [-1,1]^3 (the periodic-cube mesh of the reference refined
+        to n = 3 * 2^rs per direction), velocity of `problem` at the mesh nodes.
+        Returns (port, u0 [ne, nd])."""
+        from . import mesh as meshmod, dg, problems
+        m = meshmod.cartesian_mesh([n, n, n], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+        bb_min, bb_max = meshmod.bounding_box(m)
+        m = meshmod.set_curvature(m, mesh_order)
+        topo = meshmod.Topology(m)
+        sp = dg.Space(3, order, mesh_order)
+        nbr = dg.nbr_dof_map(topo, order)
+        vel = problems.velocity(problem, m.X.reshape(-1, 3), bb_min, bb_max).reshape(m.X.shape)
+        port = cls(order, mesh_order, 0, m.X, nbr, topo.lat, topo.n_ent, vel_nodes=vel)
+        u0 = problems.u0(problem, sp.dof_points(m.X).reshape(-1, 3), bb_min, bb_max).reshape(m.ne, sp.nd)
+        return port, u0
+
     def close(self):
         if self.h:
             lib().roc_destroy(self.h)
@@ -106,3 +124,8 @@ class Port:
     @staticmethod
     def threads():
         return lib().roc_threads()
+
+    @staticmethod
+    def set_threads(n):
+        """use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+        lib().roc_set_threads(int(n))

@@ -43,6 +43,8 @@ def lib():
         _lib.rmh_mesh_elem_vertices.restype = C.POINTER(C.c_int64)
         _lib.rmh_ctx_ndofs.restype = C.c_int64
         _lib.rmh_launch_count.restype = C.c_int64
+        _lib.rmh_dplan_blob_bytes.restype = C.c_int64
+        _lib.rmh_dist_blob_bytes.restype = C.c_int64
     return _lib
 
 
@@ -146,8 +148,8 @@ class Mesh:
         check(lib().rmh_mesh_partition(self.h, int(nparts), _ptr(part)))
         return part
 
-    def halo(self, part, rank):
-        return Halo(self, part, rank)
+    def halo(self, part, rank, interior_first=False):
+        return Halo(self, part, rank, interior_first)
 
     def nbr_lattice(self, order=1):
         """(nbr [ne, 3^dim], structured) of rmh_nbr_lattice on this mesh's lattice-entity map"""
@@ -176,12 +178,19 @@ class Mesh:
 
 class Halo:
     """Halo plan of one rank (rmh_halo_*): owned / ghost global element ids, peers, per-peer
-    send lists (local owned indices) and receive offsets into the ghost ordering."""
+    send lists (local owned indices) and receive offsets into the ghost ordering.
+    interior_first=True orders the owned elements interior first (rmh_halo_interior_first)."""
 
-    def __init__(self, mesh, part, rank):
+    def __init__(self, mesh, part, rank, interior_first=False):
         part = np.ascontiguousarray(part, dtype=np.int32)
         h = C.c_void_p()
         check(lib().rmh_halo_create(mesh.h, _ptr(part), int(rank), C.byref(h)))
+        self.h = h
+        self.n_interior = None
+        if interior_first:
+            ni = C.c_int64(0)
+            check(lib().rmh_halo_interior_first(h, C.byref(ni)))
+            self.n_interior = ni.value
         no, ng, ns = C.c_int64(), C.c_int64(), C.c_int64()
         npeer = C.c_int32()
         check(lib().rmh_halo_sizes(h, C.byref(no), C.byref(ng), C.byref(npeer), C.byref(ns)))
@@ -193,7 +202,125 @@ class Halo:
         self.send_local = np.zeros(ns.value, dtype=np.int32)
         check(lib().rmh_halo_get(h, _ptr(self.owned), _ptr(self.ghost), _ptr(self.peers),
                                  _ptr(self.send_off), _ptr(self.recv_off), _ptr(self.send_local)))
-        lib().rmh_halo_free(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().rmh_halo_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _blob_args(blobs):
+    n = len(blobs)
+    keep = [C.create_string_buffer(bytes(b), len(b)) for b in blobs]
+    ptrs = (C.c_void_p * n)(*[C.cast(k, C.c_void_p).value for k in keep])
+    sizes = (C.c_int64 * n)(*[len(b) for b in blobs])
+    return n, ptrs, sizes, keep
+
+
+class DPlan:
+    """Host-only exchange plan (rmh_dplan_*): ghost-face slots, requests, send tables."""
+
+    def __init__(self, halo, rank, world, dim, order, nbr_dof_owned):
+        self._nbr = np.ascontiguousarray(nbr_dof_owned, dtype=np.int32)
+        self.h = C.c_void_p()
+        check(lib().rmh_dplan_create(halo.h, int(rank), int(world), int(dim), int(order),
+                                     _ptr(self._nbr), C.byref(self.h)))
+        ne, ng, ns = C.c_int64(), C.c_int64(), C.c_int64()
+        npeer = C.c_int32()
+        check(lib().rmh_dplan_sizes(self.h, C.byref(ne), C.byref(ng), C.byref(ns), C.byref(npeer)))
+        self.ne, self.ne_ghost, self.n_slots, self.n_peers = ne.value, ng.value, ns.value, npeer.value
+
+    def export(self):
+        n = lib().rmh_dplan_blob_bytes(self.h)
+        buf = C.create_string_buffer(n)
+        check(lib().rmh_dplan_export(self.h, buf))
+        return buf.raw
+
+    def connect(self, blobs):
+        n, ptrs, sizes, keep = _blob_args(blobs)
+        check(lib().rmh_dplan_connect(self.h, n, ptrs, sizes))
+
+    def slot_ghosts(self):
+        out = np.zeros(self.n_slots, dtype=np.int32)
+        check(lib().rmh_dplan_slot_ghosts(self.h, _ptr(out)))
+        return out
+
+    def peer(self, k):
+        """(rank, flag_slot, tr_src, tr_dst, mm_src, mm_dst) of peer k (after connect)"""
+        r, fs = C.c_int32(), C.c_int32()
+        ntr, nmm = C.c_int64(), C.c_int64()
+        check(lib().rmh_dplan_peer(self.h, int(k), C.byref(r), C.byref(ntr), C.byref(nmm), C.byref(fs)))
+        a = [np.zeros(ntr.value, dtype=np.int32), np.zeros(ntr.value, dtype=np.int32),
+             np.zeros(nmm.value, dtype=np.int32), np.zeros(nmm.value, dtype=np.int32)]
+        check(lib().rmh_dplan_peer_tables(self.h, int(k), *[_ptr(x) for x in a]))
+        return (r.value, fs.value, *a)
+
+    def close(self):
+        if self.h:
+            lib().rmh_dplan_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Dist:
+    """Device layer of a decomposed run (rmh_dist_*)."""
+
+    def __init__(self, ctx, plan, rank, world, n_interior):
+        self.ctx, self.plan = ctx, plan
+        self.h = C.c_void_p()
+        check(lib().rmh_dist_create(ctx.h, plan.h, int(rank), int(world), C.c_int64(n_interior),
+                                    C.byref(self.h)))
+
+    def export(self):
+        n = lib().rmh_dist_blob_bytes(self.h)
+        buf = C.create_string_buffer(n)
+        check(lib().rmh_dist_export(self.h, buf))
+        return buf.raw
+
+    def connect(self, blobs):
+        n, ptrs, sizes, keep = _blob_args(blobs)
+        check(lib().rmh_dist_connect(self.h, n, ptrs, sizes))
+
+    def rk_stage(self, lo_type, dt, a, b, x0, y, out, s=0):
+        check(lib().rmh_dist_rk_stage(self.h, int(lo_type), C.c_double(dt), C.c_double(a), C.c_double(b),
+                                      _dp(x0), _dp(y), _dp(out), C.c_void_p(s)))
+
+    def rk_step(self, ode_solver_type, lo_type, t, dt, u, s=0):
+        tt = C.c_double(t)
+        check(lib().rmh_dist_rk_step(self.h, int(ode_solver_type), int(lo_type), C.byref(tt),
+                                     C.c_double(dt), _dp(u), C.c_void_p(s)))
+        return tt.value
+
+    def rk_step_host(self, ode_solver_type, lo_type, t, dt, u_host):
+        tt = C.c_double(t)
+        check(lib().rmh_dist_rk_step_host(self.h, int(ode_solver_type), int(lo_type), C.byref(tt),
+                                          C.c_double(dt), C.c_void_p(int(u_host))))
+        return tt.value
+
+    def allreduce(self, values, op='sum', s=0):
+        v = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).copy()
+        check(lib().rmh_dist_allreduce(self.h, {'sum': 0, 'min': 1, 'max': 2}[op], _ptr(v), int(v.size),
+                                       C.c_void_p(s)))
+        return v
+
+    def close(self):
+        if self.h:
+            lib().rmh_dist_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -377,25 +504,6 @@ class Context:
 
     def stage_minmax(self, y, s=0):
         check(lib().rmh_stage_minmax(self.h, _dp(y), C.c_void_p(s)))
-
-    def halo_pack(self, u, send_local, n_send, send_u, send_mm, s=0):
-        check(lib().rmh_halo_pack(self.h, _dp(u), _dp(send_local), C.c_int64(n_send), _dp(send_u),
-                                  _dp(send_mm), C.c_void_p(s)))
-
-    def halo_set(self, ghost_u, ghost_mm, s=0):
-        check(lib().rmh_halo_set(self.h, _dp(ghost_u), _dp(ghost_mm), C.c_void_p(s)))
-
-    def rk_stage_dist(self, lo_type, dt, a, b, x0, y, out, s=0):
-        check(lib().rmh_rk_stage_dist(self.h, int(lo_type), C.c_double(dt), C.c_double(a),
-                                      C.c_double(b), _dp(x0), _dp(y), _dp(out), C.c_void_p(s)))
-
-    def dist_split(self, n_interior):
-        check(lib().rmh_dist_split(self.h, C.c_int64(n_interior)))
-
-    def rk_stage_part(self, lo_type, dt, a, b, x0, y, out, part, s=0):
-        check(lib().rmh_rk_stage_part(self.h, int(lo_type), C.c_double(dt), C.c_double(a),
-                                      C.c_double(b), _dp(x0), _dp(y), _dp(out), int(part),
-                                      C.c_void_p(s)))
 
     def profile(self, enable):
         ms = C.c_double(0.0); n = C.c_int64(0)

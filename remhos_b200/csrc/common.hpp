@@ -2,6 +2,7 @@
 #ifndef RMH_COMMON_HPP
 #define RMH_COMMON_HPP
 
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -26,7 +27,25 @@ std::vector<double> invert_small(const std::vector<double> &A, int n);
 
 void face_axis(int dim, int f, int &axis, int &side);
 void bdr_dofs(int p, int dim, std::vector<int> &bd);
+// natural face order (remaining axes ascending, first fastest) -> row of BdrDofs: [nf][nfd]
+void nat2ref_table(int p, int dim, std::vector<int> &n2r);
+// rmh_nbr_lattice restricted to the first ne_rows elements (the owned ones of a decomposed mesh;
+// lat still lists owned + ghost rows, ne_all of them)
+int nbr_lattice_rows(int dim, int64_t ne_all, int64_t ne_rows, int32_t n_ent, const int32_t *lat,
+                     int32_t *nbr, int *structured);
 
 } // namespace rmh
+
+// Halo plan of one rank (rmh_halo_create): global element ids.  `owned` may be reordered by
+// rmh_halo_interior_first; owned_sorted / owned_pos locate a global id among the owned elements.
+struct rmh_halo
+{
+   std::vector<int64_t> owned, ghost, send;         // global element ids
+   std::vector<int32_t> ghost_owner, peers, send_off, recv_off;
+   std::vector<int64_t> owned_sorted;               // ascending global ids
+   std::vector<int32_t> owned_pos;                  // position in `owned` of owned_sorted[i]
+   int64_t n_interior = -1;
+   int32_t local_of(int64_t g) const;               // -1 if not owned
+};
 
 #endif

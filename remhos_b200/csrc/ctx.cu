@@ -5,7 +5,6 @@
 #include "kernels.cuh"
 #include "stage3d.cuh"
 #include "stage3p.cuh"
-#include "stage3t.cuh"
 #include "stage3w.cuh"
 #include "stage3c.cuh"
 #include "fa.cuh"
@@ -22,6 +21,9 @@
 #include <vector>
 
 using namespace rmh;
+
+#define RMH_MAX_PEERS 32      // epoch flags in a rank's window (one per peer)
+#define RMH_MAX_DEVICES 16
 
 static std::atomic<int64_t> g_launches{0};
 
@@ -78,15 +80,12 @@ struct rmh_ctx
    int num_sms = 0;
    bool pipelined = true;      // RMH_NO_PIPELINE=1 selects the one-batch-per-block stage kernel
    bool tensor = true;         // RMH_NO_TENSOR=1 selects the DFMA pipelined kernel
-   bool frag = false;          // Dvol/Dface stored in the fragment order of stage3t.cuh
+   bool frag = false;          // Dvol/Dface stored in the fragment order of stage3w.cuh
    bool xe_valid = false;
    bool all_affine = false;   // every element has constant det J (transport meshes only)
    bool op_lin = false;       // ... and adj(J) v is linear over every element: opc is valid
    bool op_const = false;     // ... and constant over every element: opa is valid
-   // decomposed meshes: entities that touch a ghost element come last in ent_list; owned elements
-   // [0, n_split) have no ghost dependence (rmh_dist_split)
-   int32_t *ent_list = nullptr;
-   int n_ent_int = 0;
+   // decomposed meshes: owned elements [0, n_split) share no vertex with a ghost element
    int64_t n_split = -1;
    // smoothness indicator (rmh_si_setup): H1 order-1 operators in CSR
    int si_type = 0, si_n = 0;
@@ -119,8 +118,25 @@ struct rmh_ctx
    // work vectors of the unfused solver path (allocated on first use)
    double *wk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    double *rk[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-   // halo
-   const double *ughost = nullptr;   // caller-owned ghost DOF blocks (rmh_halo_set)
+   // halo (multi-GPU, dist.cuh).  Faces with a ghost neighbour get one slot each: nbr_elem = ne + slot,
+   // the neighbour's face trace (this element's natural face order) is ughost[slot][NFD].
+   const double *ughost = nullptr;
+   int64_t n_gslots = 0;
+   std::vector<int32_t> gs_ghost, gs_pid;   // per slot: ghost element (0 .. ne_ghost-1), pattern id
+   std::vector<int16_t> pat_h;              // host copy of the pattern table [npat][NFD]
+   // k_stage3c<FOLD>: 3^dim neighbourhood of every owned element (rmh_nbr_lattice; boundary -> the
+   // sentinel pair); element (min,max) pairs ping-pong between xe_mm2[0|1], each [ne + ne_ghost + 1]
+   int32_t *nb27 = nullptr;
+   bool fold = false;
+   double2 *xe_mm2[2] = {nullptr, nullptr};
+   unsigned long long epoch = 0;   // stage counter: stage k reads pairs / ghost traces [k & 1], writes pairs [(k+1) & 1]
+   // the window peers write into (one allocation = one IPC handle):
+   // flags[RMH_MAX_PEERS] | xe_mm2[0] | xe_mm2[1] | gtr[0] | gtr[1]
+   void *win = nullptr;
+   size_t win_bytes = 0, win_off_mm[2] = {0, 0}, win_off_tr[2] = {0, 0};
+   unsigned long long *flags = nullptr;
+   double *gtr[2] = {nullptr, nullptr};
+   struct rmh_dist *dist = nullptr;
    // scratch
    double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *red = nullptr;
    double *pin = nullptr;   // pinned host staging (e2e entry point)
@@ -132,6 +148,10 @@ struct rmh_ctx
    int pcg_maxit = 60;
    std::vector<void *> allocs;
 };
+
+namespace rmh { struct StagePArgs; }
+// multi-GPU hook (dist.cuh): flags / epoch / shell range of the in-kernel halo wait
+static void dist_stage_args(rmh_ctx *c, rmh::StagePArgs &pa, bool in_kernel_wait);
 
 template <typename Tp>
 static int dev_alloc(rmh_ctx *c, Tp **p, size_t n)
@@ -782,7 +802,8 @@ __global__ void k_mass_avg(int64_t ne, int nd, double dt, const double *u, const
 }
 
 // ComputeElementsMinMax (remhos_tools.cpp:497-523)
-__global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_min, double *xe_max)
+__global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_min, double *xe_max,
+                               double2 *xe_mm = nullptr)
 {
    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    const int lane = threadIdx.x & 31;
@@ -794,7 +815,11 @@ __global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_m
       mn = fmin(mn, v); mx = fmax(mx, v);
    }
    mn = warp_min(mn); mx = warp_max(mx);
-   if (lane == 0) { xe_min[e] = mn; xe_max[e] = mx; }
+   if (lane == 0)
+   {
+      if (xe_mm) { xe_mm[e] = make_double2(mn, mx); }
+      else { xe_min[e] = mn; xe_max[e] = mx; }
+   }
 }
 
 // same, streaming variant for even nd and 16-byte aligned u: a warp owns EW consecutive elements
@@ -802,7 +827,7 @@ __global__ void k_elem_min_max(int64_t ne, int nd, const double *u, double *xe_m
 // keeps two 8-byte loads in flight per lane and reaches a third of the HBM bandwidth)
 template <int EW>
 __global__ void __launch_bounds__(256) k_elem_min_max_v(int64_t ne, int nd, const double *__restrict__ u,
-                                                        double *xe_min, double *xe_max)
+                                                        double *xe_min, double *xe_max, double2 *xe_mm)
 {
    const int64_t e0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * EW;
    const int lane = threadIdx.x & 31;
@@ -848,22 +873,25 @@ __global__ void __launch_bounds__(256) k_elem_min_max_v(int64_t ne, int nd, cons
       double a = mn[0], b = mx[0];
 #pragma unroll
       for (int k = 1; k < EW; k++) { if (lane == k) { a = mn[k]; b = mx[k]; } }
-      xe_min[e0 + lane] = a; xe_max[e0 + lane] = b;
+      if (xe_mm) { xe_mm[e0 + lane] = make_double2(a, b); }
+      else { xe_min[e0 + lane] = a; xe_max[e0 + lane] = b; }
    }
 }
 
-static void launch_elem_min_max(int64_t ne, int nd, const double *u, double *xe_min, double *xe_max, cudaStream_t s)
+// (min, max) of every element: into two arrays, or -- xe_mm != nullptr -- as one pair per element
+static void launch_elem_min_max(int64_t ne, int nd, const double *u, double *xe_min, double *xe_max, cudaStream_t s,
+                                double2 *xe_mm = nullptr)
 {
    const int bs = 256;
    if ((nd & 1) == 0 && (((uintptr_t)u) & 15) == 0)
    {
       constexpr int EW = 4;
       const int64_t nw = (ne + EW - 1) / EW;
-      k_elem_min_max_v<EW><<<(unsigned)((nw * 32 + bs - 1) / bs), bs, 0, s>>>(ne, nd, u, xe_min, xe_max);
+      k_elem_min_max_v<EW><<<(unsigned)((nw * 32 + bs - 1) / bs), bs, 0, s>>>(ne, nd, u, xe_min, xe_max, xe_mm);
    }
    else
    {
-      k_elem_min_max<<<(unsigned)((ne * 32 + bs - 1) / bs), bs, 0, s>>>(ne, nd, u, xe_min, xe_max);
+      k_elem_min_max<<<(unsigned)((ne * 32 + bs - 1) / bs), bs, 0, s>>>(ne, nd, u, xe_min, xe_max, xe_mm);
    }
 }
 
@@ -964,27 +992,6 @@ __global__ void k_clip_scale(int64_t ne, int nd, double dt, const double *u, con
       if (new_mass < -eps) { fc = fmax(0.0, fc) - fmin(0.0, fc) * sumPos / sumNeg; }
       du[i] = du_lo[i] + fc / m[i];
    }
-}
-
-// halo pack: DOF blocks and (min,max) of the elements the peers need (send_local = owned index)
-__global__ void k_halo_pack(int64_t n_send, int nd, const int32_t *send_local, const double *u,
-                            const double *xe_min, const double *xe_max, double *send_u,
-                            double *send_mm)
-{
-   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (idx >= n_send * nd) { return; }
-   const int64_t i = idx / nd;
-   const int j = (int)(idx - i * nd);
-   const int64_t e = send_local[i];
-   send_u[idx] = u[e * nd + j];
-   if (j == 0) { send_mm[2 * i] = xe_min[e]; send_mm[2 * i + 1] = xe_max[e]; }
-}
-
-__global__ void k_halo_set_mm(int64_t n_ghost, const double *ghost_mm, double *xe_min_g,
-                              double *xe_max_g)
-{
-   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n_ghost) { xe_min_g[i] = ghost_mm[2 * i]; xe_max_g[i] = ghost_mm[2 * i + 1]; }
 }
 
 // out = a*x0 + b*(y + dt*k)
@@ -1210,53 +1217,6 @@ static int dispatch_stagep(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    RMH_DISPATCH(launch_stagep, c, a, s);
 }
 
-// ---- FP64 tensor-core variant (stage3t.cuh); needs the fragment-ordered operator data
-template <int D1, int Q, int E, int NW>
-static int launch_staget_E(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
-{
-   using S = SmemT<D1, Q, E, NW>;
-   constexpr int MINB0 = (int)((227 * 1024) / (S::BYTES + 1024));
-   constexpr int MINB1 = MINB0 < 1 ? 1 : MINB0;
-   constexpr int MINB = (MINB1 * NW > 16) ? (16 / NW > 0 ? 16 / NW : 1) : MINB1;   // <= 16 warps/SM: 128 regs
-   static int blocks_per_sm = 0;
-   if (blocks_per_sm == 0)
-   {
-      CUDA_OK(cudaFuncSetAttribute(k_stage3t<D1, Q, E, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)S::BYTES));
-      int nb = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3t<D1, Q, E, NW, MINB>, S::T, S::BYTES));
-      if (nb < 1) { set_error("k_stage3t does not fit on an SM"); return 1; }
-      blocks_per_sm = nb;
-   }
-   const int64_t nbatch = (a.ne + E - 1) / E;
-   const int64_t grid = std::min<int64_t>(nbatch, (int64_t)blocks_per_sm * c->num_sms);
-   k_stage3t<D1, Q, E, NW, MINB><<<(unsigned)grid, S::T, S::BYTES, s>>>(a, make_tab<D1, Q>(c));
-   LAUNCH_OK();
-   return 0;
-}
-
-template <int DIM, int D1, int Q>
-static int launch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
-{
-   if constexpr (DIM == 3 && D1 <= 4)
-   {
-      static int nw = -1;
-      if (nw < 0) { const char *ev = getenv("RMH_TENSOR_NW"); nw = ev ? atoi(ev) : 4; }
-      if (nw == 8) { return launch_staget_E<D1, Q, 4, 8>(c, a, s); }
-      if (nw == 6) { return launch_staget_E<D1, Q, 4, 6>(c, a, s); }
-      return launch_staget_E<D1, Q, 4, 4>(c, a, s);
-   }
-   else
-   {
-      set_error("tensor-core stage kernel: 3D, order <= 4 only");
-      return 1;
-   }
-}
-
-static int dispatch_staget(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
-{
-   RMH_DISPATCH(launch_staget, c, a, s);
-}
 
 // ---- warp-per-element FP64 tensor-core kernel (stage3w.cuh)
 // NW warps per block, MINB resident blocks per SM the register allocation must allow.  The kernel
@@ -1354,30 +1314,31 @@ static TabC<D1> make_tabc(const rmh_ctx *c)
    return o;
 }
 
-template <int D1, int Q, int NW, int MINB, int NST, bool GH>
+template <int D1, int Q, int NW, int MINB, int NST, bool GH, bool FOLD>
 static int launch_stagec_G(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    using S = SmemC<D1, NST>;
    constexpr size_t BYTES = S::bytes(NW);
-   static int blocks_per_sm = 0;
-   if (blocks_per_sm == 0)
+   static int blocks_per_sm[RMH_MAX_DEVICES] = {0};     // function attributes are per device
+   int &bps = blocks_per_sm[c->device % RMH_MAX_DEVICES];
+   if (bps == 0)
    {
-      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST, GH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST, GH, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)BYTES));
       int nb = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST, GH>, NW * 32, BYTES));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST, GH, FOLD>, NW * 32, BYTES));
       if (nb < 1) { set_error("k_stage3c does not fit on an SM"); return 1; }
-      blocks_per_sm = std::min(nb, MINB);
+      bps = std::min(nb, MINB);
       if (getenv("RMH_VERBOSE"))
       {
-         fprintf(stderr, "k_stage3c<%d,%d,%d,%d,%s>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
-                 GH ? "ghosts" : "local", blocks_per_sm, nb, BYTES);
+         fprintf(stderr, "k_stage3c<%d,%d,%d,%d,%s,%s>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
+                 GH ? "ghosts" : "local", FOLD ? "fold" : "entities", bps, nb, BYTES);
       }
    }
    const int64_t ngrp = (a.ne + S::E - 1) / S::E - a.e_begin / S::E;
    const int64_t nblk = (ngrp + NW - 1) / NW;
-   const int64_t grid = std::min<int64_t>(nblk, (int64_t)blocks_per_sm * c->num_sms);
-   k_stage3c<D1, NW, MINB, NST, GH><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
+   const int64_t grid = std::min<int64_t>(nblk, (int64_t)bps * c->num_sms);
+   k_stage3c<D1, NW, MINB, NST, GH, FOLD><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
    LAUNCH_OK();
    return 0;
 }
@@ -1385,8 +1346,14 @@ static int launch_stagec_G(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 template <int D1, int Q, int NW, int MINB, int NST>
 static int launch_stagec_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
-   return (c->ne_ghost > 0) ? launch_stagec_G<D1, Q, NW, MINB, NST, true>(c, a, s)
-                            : launch_stagec_G<D1, Q, NW, MINB, NST, false>(c, a, s);
+   const bool fold = (a.xe_mm_out != nullptr);
+   if (c->ne_ghost > 0)
+   {
+      return fold ? launch_stagec_G<D1, Q, NW, MINB, NST, true, true>(c, a, s)
+                  : launch_stagec_G<D1, Q, NW, MINB, NST, true, false>(c, a, s);
+   }
+   return fold ? launch_stagec_G<D1, Q, NW, MINB, NST, false, true>(c, a, s)
+               : launch_stagec_G<D1, Q, NW, MINB, NST, false, false>(c, a, s);
 }
 
 template <int DIM, int D1, int Q>
@@ -1402,11 +1369,7 @@ static int launch_stagec(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
       }
       switch (cfg)
       {
-         case 822: return launch_stagec_N<D1, Q, 8, 2, 2>(c, a, s);     // 16 warps, ring of 2
-         case 632: return launch_stagec_N<D1, Q, 6, 3, 2>(c, a, s);     // 18 warps, ring of 2
-         case 1213: return launch_stagec_N<D1, Q, 12, 1, 3>(c, a, s);   // 12 warps, ring of 3
-         case 2012: return launch_stagec_N<D1, Q, 20, 1, 2>(c, a, s);   // 20 warps (one block), ring of 2
-         case 1022: return launch_stagec_N<D1, Q, 10, 2, 2>(c, a, s);   // 20 warps, ring of 2
+         case 822: return launch_stagec_N<D1, Q, 8, 2, 2>(c, a, s);     // 16 warps in two blocks, ring of 2
          default:                                                        // 16 warps (one block), ring of 2
             if constexpr (SmemC<D1, 2>::bytes(16) <= 227 * 1024) { return launch_stagec_N<D1, Q, 16, 1, 2>(c, a, s); }
             else { return launch_stagec_N<D1, Q, 8, 1, 2>(c, a, s); }   // order 1: eight elements per warp
@@ -1664,9 +1627,19 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
             ne_h[e * NF + f] = nb;
             pid_h[e * NF + f] = (uint8_t)id;
             if (nb >= c->ne + c->ne_ghost) { set_error("nbr_dof: neighbour beyond ghost range"); return fail(); }
+            if (nb >= c->ne)
+            {
+               // ghost neighbour: one trace slot per (element, face), in scan order
+               c->gs_ghost.push_back((int32_t)(nb - c->ne));
+               c->gs_pid.push_back(id);
+               if (c->ne + c->n_gslots >= 2147483647LL) { set_error("too many ghost faces"); return fail(); }
+               ne_h[e * NF + f] = (int32_t)(c->ne + c->n_gslots);
+               c->n_gslots++;
+            }
          }
       c->npat = (int)pats.size();
       if (patv.empty()) { patv.assign(NFD, 0); }
+      c->pat_h = patv;
       if (dev_upload(c, &c->nbr_elem, ne_h.data(), ne_h.size())) { return fail(); }
       if (dev_upload(c, &c->nbr_pat, pid_h.data(), pid_h.size())) { return fail(); }
       {
@@ -1716,6 +1689,26 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    if (dev_alloc(c, &c->xe_min, (size_t)ne_all)) { return fail(); }
    if (dev_alloc(c, &c->xe_max, (size_t)ne_all)) { return fail(); }
    if (dev_alloc(c, &c->xe_mm, (size_t)ne_all)) { return fail(); }
+   {
+      // window: epoch flags, the two (min,max) pair arrays (+1: sentinel), the two ghost trace arrays
+      auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+      size_t off = up(RMH_MAX_PEERS * sizeof(unsigned long long));
+      for (int k = 0; k < 2; k++) { c->win_off_mm[k] = off; off += up((size_t)(ne_all + 1) * sizeof(double2)); }
+      for (int k = 0; k < 2; k++) { c->win_off_tr[k] = off; off += up((size_t)std::max<int64_t>(c->n_gslots, 1) * c->NFD * sizeof(double)); }
+      c->win_bytes = off;
+      CUDA_OK(cudaMalloc(&c->win, off));
+      c->allocs.push_back(c->win);
+      CUDA_OK(cudaMemset(c->win, 0, off));
+      c->flags = (unsigned long long *)c->win;
+      const double2 sentinel = make_double2(INFINITY, -INFINITY);
+      for (int k = 0; k < 2; k++)
+      {
+         c->xe_mm2[k] = (double2 *)((char *)c->win + c->win_off_mm[k]);
+         c->gtr[k] = (double *)((char *)c->win + c->win_off_tr[k]);
+         CUDA_OK(cudaMemcpy(c->xe_mm2[k] + ne_all, &sentinel, sizeof(sentinel), cudaMemcpyHostToDevice));
+      }
+      c->ughost = c->gtr[0];
+   }
    if (c->bounds_type == 0)
    {
       if (!d->lat || d->n_ent <= 0) { set_error("bounds_type 0 needs desc.lat / n_ent"); return fail(); }
@@ -1735,21 +1728,6 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       if (dev_upload(c, &c->ent_off, off.data(), off.size())) { return fail(); }
       if (dev_upload(c, &c->ent_el, el.data(), el.size())) { return fail(); }
       if (dev_alloc(c, &c->ent_mm, 2 * (size_t)c->n_ent)) { return fail(); }
-      if (c->ne_ghost > 0)
-      {
-         // entity ids, those without a ghost element first (interior / boundary passes of the
-         // overlapped multi-GPU stage)
-         std::vector<int32_t> list((size_t)c->n_ent);
-         int ni = 0, nb = c->n_ent;
-         for (int i = 0; i < c->n_ent; i++)
-         {
-            bool ghost = false;
-            for (int k = off[i]; k < off[i + 1]; k++) { if (el[k] >= c->ne) { ghost = true; break; } }
-            if (ghost) { list[--nb] = i; } else { list[ni++] = i; }
-         }
-         c->n_ent_int = ni;
-         if (dev_upload(c, &c->ent_list, list.data(), list.size())) { return fail(); }
-      }
    }
    else
    {
@@ -1823,6 +1801,24 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
          }
       }
    }
+   // overlap bounds inside the constant-coefficient stage kernel: needs the 3x3x3 element
+   // neighbourhoods to reproduce every lattice entity's element set (structured vertex topology)
+   {
+      const char *nfold = getenv("RMH_NO_FOLD");
+      if (c->op_const && c->bounds_type == 0 && c->dim == 3 && !(nfold && nfold[0] == '1'))
+      {
+         std::vector<int32_t> nb((size_t)c->ne * c->N3);
+         int structured = 0;
+         if (nbr_lattice_rows(c->dim, ne_all, c->ne, c->n_ent, d->lat, nb.data(), &structured)) { return fail(); }
+         if (structured)
+         {
+            for (auto &v : nb) { if (v < 0) { v = (int32_t)ne_all; } }     // -> the (inf,-inf) sentinel pair
+            if (dev_upload(c, &c->nb27, nb.data(), nb.size())) { return fail(); }
+            c->fold = true;
+         }
+         if (getenv("RMH_VERBOSE")) { fprintf(stderr, "neighbourhood lattice: structured = %d\n", structured); }
+      }
+   }
    *out = c;
    return 0;
 }
@@ -1835,8 +1831,9 @@ extern "C" int rmh_ctx_trust_state(rmh_ctx *c, int on)
    c->trust_state = (on != 0); c->xe_ptr = nullptr;
    return 0;
 }
+// bit 4: overlap bounds formed inside the stage kernel (k_stage3c<FOLD>)
 extern "C" int rmh_ctx_path_flags(const rmh_ctx *c)
-{ return (c->all_affine ? 1 : 0) | (c->frag ? 2 : 0) | (c->op_lin ? 4 : 0) | (c->op_const ? 8 : 0); }
+{ return (c->all_affine ? 1 : 0) | (c->frag ? 2 : 0) | (c->op_lin ? 4 : 0) | (c->op_const ? 8 : 0) | (c->fold ? 16 : 0); }
 extern "C" int rmh_ctx_quad_points_1d(const rmh_ctx *c, double *q1d, double *w1d)
 {
    for (int q = 0; q < c->Q; q++) { if (q1d) { q1d[q] = c->hxq[q]; } if (w1d) { w1d[q] = c->hw[q]; } }
@@ -1893,6 +1890,7 @@ extern "C" int rmh_lo_mass_avg(rmh_ctx *c, double dt, const double *u, const dou
 extern "C" int rmh_elem_min_max(rmh_ctx *c, const double *u, double *xe_min, double *xe_max,
                                 void *stream)
 {
+   if (xe_min == c->xe_min || xe_max == c->xe_max) { c->xe_ptr = nullptr; }   // the cached min/max change owner
    launch_elem_min_max(c->ne, c->ND, u, xe_min, xe_max, (cudaStream_t)stream);
    LAUNCH_OK();
    return 0;
@@ -1958,12 +1956,24 @@ extern "C" int rmh_reduce(rmh_ctx *c, int op, const double *a, const double *b, 
 }
 
 // ---------------------------------------------------------------- fused stage entry points
-// xe_valid: ctx->xe_min/xe_max already hold the element min/max of y
-// part: 0 = the whole mesh; 1 = owned elements [0, n_split) and the entities without ghost elements;
-// 2 = the rest (needs the halo of y installed).  Parts 1 + 2 together equal part 0.
+// Element (min,max) of a stage input live in the context: as pairs in xe_mm2[(epoch + 1) & 1] when
+// the bounds are folded into the stage kernel (c->fold), else in xe_min / xe_max.
+static int stage_minmax(rmh_ctx *c, const double *y, cudaStream_t s)
+{
+   c->xe_ptr = nullptr;
+   if (c->fold) { launch_elem_min_max(c->ne, c->ND, y, nullptr, nullptr, s, c->xe_mm2[(c->epoch + 1) & 1]); }
+   else { launch_elem_min_max(c->ne, c->ND, y, c->xe_min, c->xe_max, s); }
+   LAUNCH_OK();
+   return 0;
+}
+
+// xe_valid: the context already holds the element min/max of y (and, on a decomposed mesh, the
+// peers' k_halo_put for stage epoch + 1 has been issued: dist.cuh).  Every call is one "stage
+// epoch": ghost traces and (min,max) pairs of parity epoch & 1 are read, pairs of the output are
+// written with the other parity.
 static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a, double b,
                       const double *x0, const double *y, double *out, bool xe_valid,
-                      bool write_xe, cudaStream_t s, int part = 0)
+                      bool write_xe, cudaStream_t s)
 {
    if (lo_type != 5)
    {
@@ -1973,36 +1983,23 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    if (out == y) { set_error("stage: output must not alias the stage input"); return 1; }
    c->xe_ptr = nullptr;     // the context's element min/max are about to change owner
    const int bs = 256;
-   if (!xe_valid)
+   if (!xe_valid) { if (stage_minmax(c, y, s)) { return 1; } }
+   c->epoch++;
+   const int par = (int)(c->epoch & 1);
+   c->ughost = c->gtr[par];
+   // 3D meshes with constant-Jacobian elements: persistent pipelined kernels
+   const bool use_p = c->pipelined && c->dim == 3 && c->all_affine &&
+                      ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
+   const bool use_c = use_p && c->frag && c->op_const && c->npat <= 16;
+   const bool fold = use_c && c->fold;
+   if (c->fold && !fold) { set_error("stage: state vectors must be 16-byte aligned"); return 1; }
+   if (c->bounds_type == 0 && !fold)
    {
-      launch_elem_min_max(c->ne, c->ND, y, c->xe_min, c->xe_max, s);
+      const int64_t na = c->ne + c->ne_ghost;
+      k_xe_interleave<<<(unsigned)((na + bs - 1) / bs), bs, 0, s>>>(na, c->xe_min, c->xe_max, c->xe_mm);
+      k_ent_min_max<<<(c->n_ent + bs - 1) / bs, bs, 0, s>>>(c->n_ent, nullptr, c->ent_off, c->ent_el, c->xe_mm,
+                                                            c->ent_mm);
       LAUNCH_OK();
-   }
-   if (part != 0)
-   {
-      if (!(c->op_const && c->frag && c->bounds_type == 0 && c->n_split >= 0 && c->ent_list && xe_valid))
-      {
-         set_error("split stage: needs the constant-coefficient kernel, overlap bounds, a ghost layer, "
-                   "rmh_dist_split and valid element min/max");
-         return 1;
-      }
-   }
-   if (c->bounds_type == 0)
-   {
-      const int n0 = (part == 2) ? c->n_ent_int : 0, n1 = (part == 1) ? c->n_ent_int : c->n_ent;
-      if (n1 > n0)
-      {
-         // part 1 interleaves the owned elements, part 2 the ghosts (installed by rmh_halo_set since)
-         const int64_t i0 = (part == 2) ? c->ne : 0, i1 = (part == 1) ? c->ne : c->ne + c->ne_ghost;
-         if (i1 > i0)
-         {
-            k_xe_interleave<<<(unsigned)((i1 - i0 + bs - 1) / bs), bs, 0, s>>>(i1 - i0, c->xe_min + i0,
-                                                                                c->xe_max + i0, c->xe_mm + i0);
-         }
-         k_ent_min_max<<<(n1 - n0 + bs - 1) / bs, bs, 0, s>>>(n1 - n0, part ? c->ent_list + n0 : nullptr,
-                                                              c->ent_off, c->ent_el, c->xe_mm, c->ent_mm);
-         LAUNCH_OK();
-      }
    }
    StageArgs sa;
    sa.ho = ho_args(c, y, nullptr, 3);
@@ -2010,20 +2007,15 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    sa.bounds_type = c->bounds_type; sa.dim_n3 = c->N3; sa.lat = c->lat;
    sa.ent_mm = c->ent_mm; sa.bnbr = c->bnbr;
    sa.xe_min = c->xe_min; sa.xe_max = c->xe_max;
-   // the next stage's element min/max must not overwrite the ones this launch still reads
-   // (bounds_type 1 reads neighbours' xe during the kernel) -> double buffer
+   // with overlap bounds the stage kernel leaves the element min/max of its output for the next
+   // stage (bounds_type 1 reads the neighbours' values during the kernel: no in-place update)
    sa.xe_min_out = nullptr; sa.xe_max_out = nullptr;
    if (write_xe && c->bounds_type == 0) { sa.xe_min_out = c->xe_min; sa.xe_max_out = c->xe_max; }
-   // 3D meshes with constant-Jacobian elements: persistent pipelined kernel
-   const bool use_p = c->pipelined && c->dim == 3 && c->all_affine &&
-                      ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
-   if (part != 0 && !use_p) { set_error("split stage: state vectors must be 16-byte aligned"); return 1; }
    StagePArgs pa;
    if (use_p)
    {
-      pa.ne = (part == 1) ? c->n_split : c->ne; pa.y = y; pa.x0 = x0; pa.out = out;
-      pa.e_begin = (part == 2) ? c->n_split : 0;
-      if (pa.e_begin >= pa.ne) { return 0; }
+      pa.ne = c->ne; pa.y = y; pa.x0 = x0; pa.out = out;
+      pa.e_begin = 0;
       pa.Dvol = c->Dvol; pa.Dface = c->Dface; pa.einv = c->einv;
       pa.opc = c->op_lin ? c->opc : nullptr;
       pa.opa = c->op_const ? c->opa : nullptr;
@@ -2035,17 +2027,17 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
       pa.bidx = (c->bounds_type == 0) ? c->lat : c->bnbr;
       pa.ent_mm = c->ent_mm; pa.xe_min = c->xe_min; pa.xe_max = c->xe_max;
       pa.xe_min_out = sa.xe_min_out; pa.xe_max_out = sa.xe_max_out;
+      if (fold)
+      {
+         pa.bidx = c->nb27;
+         pa.ent_mm = reinterpret_cast<const double *>(c->xe_mm2[par]);
+         pa.xe_mm_out = c->xe_mm2[par ^ 1];
+      }
+      dist_stage_args(c, pa, use_c);
    }
    auto run = [&]()
    {
-      if (use_p && c->frag)
-      {
-         static int blk = -1;   // RMH_TENSOR_BLOCK=1: block-per-batch DMMA kernel (stage3t.cuh)
-         if (blk < 0) { const char *ev = getenv("RMH_TENSOR_BLOCK"); blk = (ev && ev[0] == '1') ? 1 : 0; }
-         // (the constant-coefficient kernel keeps the whole orientation-pattern table in shared memory)
-         if (pa.opa && !blk && c->npat <= 16) { return dispatch_stagec(c, pa, s); }
-         return blk ? dispatch_staget(c, pa, s) : dispatch_stagew(c, pa, s);
-      }
+      if (use_p && c->frag) { return use_c ? dispatch_stagec(c, pa, s) : dispatch_stagew(c, pa, s); }
       return use_p ? dispatch_stagep(c, pa, s) : dispatch_stage(c, sa, s);
    };
    if (c->prof)
@@ -2984,8 +2976,9 @@ extern "C" int rmh_dev_free(rmh_ctx *c, double *p)
    CUDA_OK(cudaFree(p));
    return 0;
 }
-extern "C" int rmh_copy_h2d(rmh_ctx *, double *dst, const double *src, int64_t n)
+extern "C" int rmh_copy_h2d(rmh_ctx *c, double *dst, const double *src, int64_t n)
 {
+   if (c && dst == c->xe_ptr) { c->xe_ptr = nullptr; }     // the cached element min/max go stale
    CUDA_OK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
    return 0;
 }
@@ -2994,8 +2987,9 @@ extern "C" int rmh_copy_d2h(rmh_ctx *, double *dst, const double *src, int64_t n
    CUDA_OK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
    return 0;
 }
-extern "C" int rmh_copy_d2d(rmh_ctx *, double *dst, const double *src, int64_t n)
+extern "C" int rmh_copy_d2d(rmh_ctx *c, double *dst, const double *src, int64_t n)
 {
+   if (c && dst == c->xe_ptr) { c->xe_ptr = nullptr; }
    CUDA_OK(cudaMemcpy(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice));
    return 0;
 }
@@ -3006,59 +3000,10 @@ extern "C" int rmh_sync(rmh_ctx *c)
    return 0;
 }
 
-// ---------------------------------------------------------------- halo (multi-GPU) entry points
+// ---------------------------------------------------------------- multi-GPU layer
 extern "C" int rmh_stage_minmax(rmh_ctx *c, const double *y, void *stream)
 {
-   c->xe_ptr = nullptr;
-   launch_elem_min_max(c->ne, c->ND, y, c->xe_min, c->xe_max, (cudaStream_t)stream);
-   LAUNCH_OK();
-   return 0;
+   return stage_minmax(c, y, (cudaStream_t)stream);
 }
 
-extern "C" int rmh_halo_pack(rmh_ctx *c, const double *u, const int32_t *send_local, int64_t n_send,
-                             double *send_u, double *send_mm, void *stream)
-{
-   if (n_send == 0) { return 0; }
-   const int bs = 256;
-   const int64_t n = n_send * c->ND;
-   k_halo_pack<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
-      n_send, c->ND, send_local, u, c->xe_min, c->xe_max, send_u, send_mm);
-   LAUNCH_OK();
-   return 0;
-}
-
-extern "C" int rmh_halo_set(rmh_ctx *c, const double *ghost_u, const double *ghost_mm, void *stream)
-{
-   c->ughost = ghost_u;
-   if (c->ne_ghost == 0) { return 0; }
-   const int bs = 256;
-   k_halo_set_mm<<<(unsigned)((c->ne_ghost + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
-      c->ne_ghost, ghost_mm, c->xe_min + c->ne, c->xe_max + c->ne);
-   LAUNCH_OK();
-   return 0;
-}
-
-// Overlapped multi-GPU stage.  rmh_dist_split: owned elements [0, n_interior) share no vertex with a
-// ghost element (the caller orders them first); rounded down to a multiple of the elements a warp
-// handles at once.  rmh_rk_stage_part(part 1) may run while the halo of y is still in flight,
-// part 2 after rmh_halo_set on the same stream.
-extern "C" int rmh_dist_split(rmh_ctx *c, int64_t n_interior)
-{
-   if (n_interior < 0 || n_interior > c->ne) { set_error("rmh_dist_split: out of range"); return 1; }
-   c->n_split = (n_interior / 8) * 8;
-   return 0;
-}
-extern "C" int rmh_rk_stage_part(rmh_ctx *c, int lo_type, double dt, double a, double b,
-                                 const double *x0, const double *y, double *out, int part, void *stream)
-{
-   if (part != 1 && part != 2) { set_error("rmh_rk_stage_part: part must be 1 (interior) or 2 (boundary)"); return 1; }
-   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0,
-                     (cudaStream_t)stream, part);
-}
-extern "C" int rmh_rk_stage_dist(rmh_ctx *c, int lo_type, double dt, double a, double b,
-                                 const double *x0, const double *y, double *out, void *stream)
-{
-   // element min/max of y (owned: in the context; ghost: installed by rmh_halo_set) are valid
-   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0,
-                     (cudaStream_t)stream);
-}
+#include "dist.cuh"

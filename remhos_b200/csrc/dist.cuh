@@ -1,0 +1,456 @@
+// Multi-GPU layer of the RK-stage path: one process (or context) per GPU, the mesh decomposed into
+// per-rank element sets with a vertex-adjacent ghost ring (rmh_halo_*, dplan.cpp).
+//
+// Replaces ParGridFunction::ExchangeFaceNbrData (remhos.cpp:1813; inside K.Mult), the
+// GroupCommunicator min/max reduction of DofInfo::ComputeOverlapBounds (remhos_tools.cpp:463-466)
+// and the MPI_Allreduce of mass / min / max (remhos.cpp:1073-1076,1403-1415).
+//
+// Exchange = ONE kernel per stage, k_halo_put: it gathers the face traces of the stage input that
+// the peers' ghost faces need (nfd values per face, already in the receiver's face order) and the
+// (min,max) pairs of the ring elements, and stores them straight into the peers' windows over
+// NVLink (CUDA-IPC mapped, or plain peer access inside one process); the last block publishes the
+// stage epoch in every peer's flag word (release, system scope).  No staging buffer, no message,
+// no receive-side unpack.  The receiver's stage kernel (k_stage3c) runs its interior elements first
+// and polls the flags once per warp before it touches the first shell element; the other stage
+// kernels are preceded by k_halo_wait.  Windows are double-buffered by epoch parity: a peer can be
+// at most one stage ahead, because its next put needs this rank's put of the stage in between.
+// Scalars go through ncclAllReduce (NCCL is loaded with dlopen when first needed).
+#ifndef RMH_DIST_CUH
+#define RMH_DIST_CUH
+
+#include <dlfcn.h>
+#include <unistd.h>
+
+struct rmh_dplan;
+extern "C" int rmh_dplan_sizes(const rmh_dplan *p, int64_t *ne, int64_t *ne_ghost, int64_t *n_slots, int32_t *n_peers);
+extern "C" int rmh_dplan_slot_ghosts(const rmh_dplan *p, int32_t *slot_ghost);
+extern "C" int64_t rmh_dplan_blob_bytes(const rmh_dplan *p);
+extern "C" int rmh_dplan_export(const rmh_dplan *p, void *blob);
+extern "C" int rmh_dplan_connect(rmh_dplan *p, int n_blobs, const void *const *blobs, const int64_t *sizes);
+extern "C" int rmh_dplan_peer(const rmh_dplan *p, int k, int32_t *rank, int64_t *n_tr, int64_t *n_mm, int32_t *flag_slot);
+extern "C" int rmh_dplan_peer_tables(const rmh_dplan *p, int k, int32_t *tr_src, int32_t *tr_dst, int32_t *mm_src,
+                                     int32_t *mm_dst);
+
+// ---- the few NCCL entry points used, resolved at run time (torch ships its own libnccl.so.2; a
+// link-time dependency could bind to a different copy than the one already in the process)
+typedef struct ncclComm *rmh_ncclComm_t;
+struct rmh_nccl_id { char internal[128]; };
+struct NcclApi
+{
+   void *lib = nullptr;
+   int (*GetUniqueId)(rmh_nccl_id *) = nullptr;
+   int (*CommInitRank)(rmh_ncclComm_t *, int, rmh_nccl_id, int) = nullptr;
+   int (*AllReduce)(const void *, void *, size_t, int, int, rmh_ncclComm_t, cudaStream_t) = nullptr;
+   int (*CommDestroy)(rmh_ncclComm_t) = nullptr;
+   const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi *nccl_api()
+{
+   static NcclApi api;
+   static bool tried = false;
+   if (!tried)
+   {
+      tried = true;
+      void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+      if (!h) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); }
+      if (!h) { h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL); }
+      if (h)
+      {
+         api.lib = h;
+         api.GetUniqueId = (int (*)(rmh_nccl_id *))dlsym(h, "ncclGetUniqueId");
+         api.CommInitRank = (int (*)(rmh_ncclComm_t *, int, rmh_nccl_id, int))dlsym(h, "ncclCommInitRank");
+         api.AllReduce = (int (*)(const void *, void *, size_t, int, int, rmh_ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+         api.CommDestroy = (int (*)(rmh_ncclComm_t))dlsym(h, "ncclCommDestroy");
+         api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+         if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { api.lib = nullptr; }
+      }
+   }
+   return api.lib ? &api : nullptr;
+}
+
+// ---- device side
+struct PutPeer
+{
+   double *gtr[2];               // the peer's ghost trace arrays
+   double2 *mm[2];               // the peer's (min,max) pair arrays
+   unsigned long long *flag;     // this rank's word among the peer's epoch flags
+   int64_t tr_off, tr_n, mm_off, mm_n;   // ranges in the concatenated tables
+};
+struct PutArgs
+{
+   int npeers;
+   const int32_t *tr_src, *tr_dst, *mm_src, *mm_dst;
+   const double *y;
+   const double2 *mm_in;                  // owned (min,max) pairs, or null: xe_min / xe_max
+   const double *xe_min, *xe_max;
+   unsigned int *counter;
+   unsigned long long epoch;
+   int par;
+   PutPeer peer[RMH_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256) k_halo_put(const __grid_constant__ PutArgs a)
+{
+   const PutPeer &P = a.peer[blockIdx.y];
+   double *gtr = P.gtr[a.par];
+   double2 *mm = P.mm[a.par];
+   const int64_t n = P.tr_n + P.mm_n;
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+   {
+      if (i < P.tr_n) { gtr[a.tr_dst[P.tr_off + i]] = a.y[a.tr_src[P.tr_off + i]]; }
+      else
+      {
+         const int64_t k = P.mm_off + (i - P.tr_n);
+         const int32_t e = a.mm_src[k];
+         mm[a.mm_dst[k]] = a.mm_in ? a.mm_in[e] : make_double2(a.xe_min[e], a.xe_max[e]);
+      }
+   }
+   // publish: all stores of the grid are ordered before the flag stores of the last block
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      const unsigned int total = gridDim.x * gridDim.y;
+      const unsigned int t = atomicAdd(a.counter, 1u);
+      if (t == total - 1)
+      {
+         *a.counter = 0;
+         __threadfence_system();
+         for (int p = 0; p < a.npeers; p++)
+         {
+            asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(a.peer[p].flag), "l"(a.epoch) : "memory");
+         }
+      }
+   }
+}
+
+// wait for the peers' epoch, then unpack the ghost (min,max) pairs for the kernels that read two arrays
+__global__ void __launch_bounds__(256) k_halo_wait(const unsigned long long *flags, int n, unsigned long long epoch,
+                                                   int64_t n_ghost, const double2 *ghost_mm, double *xe_min_g,
+                                                   double *xe_max_g)
+{
+   wait_peer_flags(flags, n, epoch);
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ghost; i += (int64_t)gridDim.x * blockDim.x)
+   {
+      const double2 v = __ldcg(ghost_mm + i);
+      xe_min_g[i] = v.x; xe_max_g[i] = v.y;
+   }
+}
+
+// ---- host side
+struct DistBlobHead
+{
+   uint64_t magic;
+   int32_t rank, world, pid, device;
+   uint64_t win_ptr, win_bytes, off_mm[2], off_tr[2];
+   int64_t host_id;
+   cudaIpcMemHandle_t ipc;
+   rmh_nccl_id nccl_id;
+   int32_t has_nccl_id, pad;
+   int64_t plan_bytes;
+};
+static const uint64_t DIST_MAGIC = 0x524d484449535431ull;   // "RMHDIST1"
+
+struct rmh_dist
+{
+   rmh_ctx *c = nullptr;
+   rmh_dplan *plan = nullptr;
+   int rank = 0, world = 1, npeers = 0;
+   bool connected = false;
+   std::vector<int32_t> peer_rank;
+   std::vector<void *> peer_win;          // mapped windows of the peers
+   std::vector<char> peer_ipc;            // 1: opened with cudaIpcOpenMemHandle
+   PutArgs put;
+   int64_t put_items_max = 0;
+   int32_t *d_tr_src = nullptr, *d_tr_dst = nullptr, *d_mm_src = nullptr, *d_mm_dst = nullptr;
+   unsigned int *d_counter = nullptr;
+   double *d_red = nullptr;
+   rmh_nccl_id nccl_id;
+   bool have_nccl_id = false;
+   rmh_ncclComm_t comm = nullptr;
+};
+
+static void dist_stage_args(rmh_ctx *c, rmh::StagePArgs &pa, bool in_kernel_wait)
+{
+   rmh_dist *d = c->dist;
+   if (!d || !d->connected || !in_kernel_wait || d->npeers == 0) { return; }
+   pa.flags = c->flags; pa.n_wait = d->npeers; pa.epoch = c->epoch;
+   pa.shell_begin = (c->n_split >= 0) ? c->n_split : 0;
+}
+
+static int64_t host_identity()
+{
+   char name[256] = {0};
+   gethostname(name, sizeof(name) - 1);
+   int64_t h = 1469598103934665603ll;
+   for (const char *p = name; *p; p++) { h = (h ^ *p) * 1099511628211ll; }
+   return h;
+}
+
+extern "C" int rmh_dist_create(rmh_ctx *c, rmh_dplan *plan, int rank, int world, int64_t n_interior,
+                               rmh_dist **out)
+{
+   if (!c || !plan || !out) { set_error("rmh_dist_create: null argument"); return 1; }
+   if (c->exec_mode != 0) { set_error("rmh_dist_create: decomposed runs cover transport mode"); return 1; }
+   int64_t ne = 0, ng = 0, ns = 0;
+   int32_t np = 0;
+   rmh_dplan_sizes(plan, &ne, &ng, &ns, &np);
+   if (ne != c->ne || ng != c->ne_ghost || ns != c->n_gslots)
+   { set_error("rmh_dist_create: plan and context describe different decompositions"); return 1; }
+   {
+      std::vector<int32_t> sg((size_t)ns);
+      rmh_dplan_slot_ghosts(plan, sg.data());
+      if (sg != c->gs_ghost) { set_error("rmh_dist_create: ghost-face slots of plan and context differ"); return 1; }
+   }
+   if (np > RMH_MAX_PEERS) { set_error("rmh_dist_create: too many peers"); return 1; }
+   if (n_interior < 0 || n_interior > c->ne) { set_error("rmh_dist_create: n_interior out of range"); return 1; }
+   CUDA_OK(cudaSetDevice(c->device));
+   rmh_dist *d = new rmh_dist;
+   d->c = c; d->plan = plan; d->rank = rank; d->world = world; d->npeers = np;
+   c->n_split = (n_interior / 8) * 8;     // whole warp groups (1, 2 or 8 elements per warp)
+   if (dev_alloc(c, &d->d_counter, 1)) { delete d; return 1; }
+   CUDA_OK(cudaMemset(d->d_counter, 0, sizeof(unsigned int)));
+   if (dev_alloc(c, &d->d_red, 16)) { delete d; return 1; }
+   if (rank == 0 && world > 1)
+   {
+      NcclApi *na = nccl_api();
+      if (na && na->GetUniqueId(&d->nccl_id) == 0) { d->have_nccl_id = true; }
+   }
+   *out = d;
+   return 0;
+}
+
+extern "C" int64_t rmh_dist_blob_bytes(const rmh_dist *d)
+{
+   return (int64_t)sizeof(DistBlobHead) + rmh_dplan_blob_bytes(d->plan);
+}
+
+extern "C" int rmh_dist_export(rmh_dist *d, void *blob)
+{
+   rmh_ctx *c = d->c;
+   CUDA_OK(cudaSetDevice(c->device));
+   DistBlobHead h;
+   memset(&h, 0, sizeof(h));
+   h.magic = DIST_MAGIC; h.rank = d->rank; h.world = d->world; h.pid = (int32_t)getpid(); h.device = c->device;
+   h.win_ptr = (uint64_t)(uintptr_t)c->win; h.win_bytes = c->win_bytes;
+   for (int k = 0; k < 2; k++) { h.off_mm[k] = c->win_off_mm[k]; h.off_tr[k] = c->win_off_tr[k]; }
+   h.host_id = host_identity();
+   CUDA_OK(cudaIpcGetMemHandle(&h.ipc, c->win));
+   h.has_nccl_id = d->have_nccl_id ? 1 : 0;
+   if (d->have_nccl_id) { h.nccl_id = d->nccl_id; }
+   h.plan_bytes = rmh_dplan_blob_bytes(d->plan);
+   memcpy(blob, &h, sizeof(h));
+   return rmh_dplan_export(d->plan, (char *)blob + sizeof(h));
+}
+
+extern "C" int rmh_dist_connect(rmh_dist *d, int n_blobs, const void *const *blobs, const int64_t *sizes)
+{
+   rmh_ctx *c = d->c;
+   if (n_blobs != d->world) { set_error("rmh_dist_connect: need one blob per rank"); return 1; }
+   CUDA_OK(cudaSetDevice(c->device));
+   std::vector<DistBlobHead> heads((size_t)n_blobs);
+   std::vector<const void *> pb((size_t)n_blobs);
+   std::vector<int64_t> ps((size_t)n_blobs);
+   for (int r = 0; r < n_blobs; r++)
+   {
+      if (sizes[r] < (int64_t)sizeof(DistBlobHead)) { set_error("rmh_dist_connect: short blob"); return 1; }
+      memcpy(&heads[r], blobs[r], sizeof(DistBlobHead));
+      if (heads[r].magic != DIST_MAGIC || heads[r].rank != r) { set_error("rmh_dist_connect: bad blob"); return 1; }
+      pb[r] = (const char *)blobs[r] + sizeof(DistBlobHead);
+      ps[r] = sizes[r] - (int64_t)sizeof(DistBlobHead);
+   }
+   if (rmh_dplan_connect(d->plan, n_blobs, pb.data(), ps.data())) { return 1; }
+   if (heads[0].has_nccl_id) { d->nccl_id = heads[0].nccl_id; d->have_nccl_id = true; }
+   // ---- map the peers' windows, concatenate the tables
+   const int np = d->npeers;
+   d->peer_rank.resize(np); d->peer_win.assign(np, nullptr); d->peer_ipc.assign(np, 0);
+   std::vector<int32_t> tr_src, tr_dst, mm_src, mm_dst;
+   memset(&d->put, 0, sizeof(d->put));
+   const int64_t my_host = host_identity();
+   for (int k = 0; k < np; k++)
+   {
+      int32_t pr = -1, fslot = -1;
+      int64_t ntr = 0, nmm = 0;
+      if (rmh_dplan_peer(d->plan, k, &pr, &ntr, &nmm, &fslot)) { return 1; }
+      d->peer_rank[k] = pr;
+      const DistBlobHead &H = heads[pr];
+      if (H.host_id != my_host) { set_error("rmh_dist_connect: peers must be GPUs of one node (NVLink peer memory)"); return 1; }
+      void *w = nullptr;
+      if (H.pid == (int32_t)getpid())
+      {
+         w = (void *)(uintptr_t)H.win_ptr;
+         if (H.device != c->device)
+         {
+            int can = 0;
+            CUDA_OK(cudaDeviceCanAccessPeer(&can, c->device, H.device));
+            if (!can) { set_error("rmh_dist_connect: no peer access between the GPUs"); return 1; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(H.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return 1; }
+            cudaGetLastError();
+         }
+      }
+      else
+      {
+         cudaError_t e = cudaIpcOpenMemHandle(&w, H.ipc, cudaIpcMemLazyEnablePeerAccess);
+         if (e != cudaSuccess)
+         { set_error(std::string("cudaIpcOpenMemHandle (peer window): ") + cudaGetErrorString(e)); return 1; }
+         d->peer_ipc[k] = 1;
+      }
+      d->peer_win[k] = w;
+      PutPeer &P = d->put.peer[k];
+      for (int q = 0; q < 2; q++)
+      {
+         P.gtr[q] = (double *)((char *)w + H.off_tr[q]);
+         P.mm[q] = (double2 *)((char *)w + H.off_mm[q]);
+      }
+      if (fslot < 0 || fslot >= RMH_MAX_PEERS) { set_error("rmh_dist_connect: flag slot out of range"); return 1; }
+      P.flag = (unsigned long long *)w + fslot;
+      P.tr_off = (int64_t)tr_src.size(); P.tr_n = ntr; P.mm_off = (int64_t)mm_src.size(); P.mm_n = nmm;
+      tr_src.resize(tr_src.size() + ntr); tr_dst.resize(tr_dst.size() + ntr);
+      mm_src.resize(mm_src.size() + nmm); mm_dst.resize(mm_dst.size() + nmm);
+      if (rmh_dplan_peer_tables(d->plan, k, tr_src.data() + P.tr_off, tr_dst.data() + P.tr_off,
+                                mm_src.data() + P.mm_off, mm_dst.data() + P.mm_off)) { return 1; }
+      d->put_items_max = std::max(d->put_items_max, ntr + nmm);
+   }
+   if (dev_upload(c, &d->d_tr_src, tr_src.data(), tr_src.size())) { return 1; }
+   if (dev_upload(c, &d->d_tr_dst, tr_dst.data(), tr_dst.size())) { return 1; }
+   if (dev_upload(c, &d->d_mm_src, mm_src.data(), mm_src.size())) { return 1; }
+   if (dev_upload(c, &d->d_mm_dst, mm_dst.data(), mm_dst.size())) { return 1; }
+   d->put.npeers = np;
+   d->put.tr_src = d->d_tr_src; d->put.tr_dst = d->d_tr_dst; d->put.mm_src = d->d_mm_src; d->put.mm_dst = d->d_mm_dst;
+   d->put.counter = d->d_counter;
+   d->connected = true;
+   c->dist = d;
+   return 0;
+}
+
+extern "C" int rmh_dist_destroy(rmh_dist *d)
+{
+   if (!d) { return 0; }
+   rmh_ctx *c = d->c;
+   cudaSetDevice(c->device);
+   cudaDeviceSynchronize();
+   for (size_t k = 0; k < d->peer_win.size(); k++) { if (d->peer_ipc[k] && d->peer_win[k]) { cudaIpcCloseMemHandle(d->peer_win[k]); } }
+   if (d->comm) { NcclApi *na = nccl_api(); if (na) { na->CommDestroy(d->comm); } }
+   if (c->dist == d) { c->dist = nullptr; }
+   delete d;
+   return 0;
+}
+
+// true when stage_impl will run the constant-coefficient kernel (which waits for the halo itself)
+static bool dist_in_kernel_wait(const rmh_ctx *c, const double *x0, const double *y, const double *out)
+{
+   return c->pipelined && c->dim == 3 && c->all_affine && c->frag && c->op_const && c->npat <= 16 &&
+          ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
+}
+
+// One RK stage on the decomposed mesh: out = a x0 + b (y + dt F(y)); the element min/max of y must be
+// in the context (rmh_stage_minmax, or left there by the previous stage)
+extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0,
+                                 const double *y, double *out, void *stream)
+{
+   rmh_ctx *c = d->c;
+   if (!d->connected) { set_error("rmh_dist_rk_stage: not connected"); return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   const unsigned long long ep = c->epoch + 1;
+   const int par = (int)(ep & 1);
+   if (d->npeers > 0)
+   {
+      PutArgs &A = d->put;
+      A.y = y; A.epoch = ep; A.par = par;
+      A.mm_in = c->fold ? c->xe_mm2[par] : nullptr;
+      A.xe_min = c->xe_min; A.xe_max = c->xe_max;
+      const int bs = 256;
+      const int64_t nb = std::max<int64_t>(1, std::min<int64_t>((d->put_items_max + bs - 1) / bs, 4 * (int64_t)c->num_sms));
+      k_halo_put<<<dim3((unsigned)nb, (unsigned)d->npeers), bs, 0, s>>>(A);
+      LAUNCH_OK();
+      if (!dist_in_kernel_wait(c, x0, y, out))
+      {
+         const int64_t nw = std::max<int64_t>(1, std::min<int64_t>((c->ne_ghost + bs - 1) / bs, 2 * (int64_t)c->num_sms));
+         k_halo_wait<<<(unsigned)nw, bs, 0, s>>>(c->flags, d->npeers, ep, c->fold ? 0 : c->ne_ghost,
+                                                 c->xe_mm2[par] + c->ne, c->xe_min + c->ne, c->xe_max + c->ne);
+         LAUNCH_OK();
+      }
+   }
+   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0, s);
+}
+
+// ODESolver::Step for -s 1/2/3 on the decomposed mesh (cf. rmh_rk_step)
+extern "C" int rmh_dist_rk_step(rmh_dist *d, int ode, int lo_type, double *t, double dt, double *u, void *stream)
+{
+   rmh_ctx *c = d->c;
+   cudaStream_t s = (cudaStream_t)stream;
+   const bool chain = (c->bounds_type == 0);
+   const bool have_xe = chain && c->trust_state && c->xe_ptr == u;
+   const bool keep_xe = chain && c->trust_state;
+   if (!have_xe) { if (stage_minmax(c, u, s)) { return 1; } }
+   c->xe_ptr = nullptr;
+   if (ode == 1)
+   {
+      if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
+      CUDA_OK(cudaMemcpyAsync(u, c->w1, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      if (keep_xe) { c->xe_ptr = u; }
+   }
+   else if (ode == 2)
+   {
+      if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
+      if (!chain) { if (stage_minmax(c, c->w1, s)) { return 1; } }
+      if (rmh_dist_rk_stage(d, lo_type, dt, 0.5, 0.5, u, c->w1, u, stream)) { return 1; }
+      if (keep_xe) { c->xe_ptr = u; }
+   }
+   else if (ode == 3)
+   {
+      if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
+      if (!chain) { if (stage_minmax(c, c->w1, s)) { return 1; } }
+      if (rmh_dist_rk_stage(d, lo_type, dt, 0.75, 0.25, u, c->w1, c->w2, stream)) { return 1; }
+      if (!chain) { if (stage_minmax(c, c->w2, s)) { return 1; } }
+      if (rmh_dist_rk_stage(d, lo_type, dt, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, stream)) { return 1; }
+      if (keep_xe) { c->xe_ptr = u; }
+   }
+   else { set_error("rmh_dist_rk_step: ode solver type must be 1, 2 or 3"); return 1; }
+   *t += dt;
+   return 0;
+}
+
+// same with HOST state: H2D of u, one step, D2H (the end-to-end entry point, cf. rmh_rk_step_host)
+extern "C" int rmh_dist_rk_step_host(rmh_dist *d, int ode, int lo_type, double *t, double dt, double *u_host)
+{
+   rmh_ctx *c = d->c;
+   const size_t bytes = (size_t)c->N * sizeof(double);
+   CUDA_OK(cudaMemcpyAsync(c->w3, u_host, bytes, cudaMemcpyHostToDevice, 0));
+   c->xe_ptr = nullptr;
+   if (rmh_dist_rk_step(d, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }
+   CUDA_OK(cudaMemcpyAsync(u_host, c->w3, bytes, cudaMemcpyDeviceToHost, 0));
+   CUDA_OK(cudaStreamSynchronize(0));
+   return 0;
+}
+
+// MPI_Allreduce replacement (remhos.cpp:1073-1076,1403-1415; dt: :538-553): op 0 sum, 1 min, 2 max over the
+// ranks, in place on n <= 16 host doubles; collective
+extern "C" int rmh_dist_allreduce(rmh_dist *d, int op, double *vals, int n, void *stream)
+{
+   if (d->world == 1) { return 0; }
+   if (n < 1 || n > 16) { set_error("rmh_dist_allreduce: 1 <= n <= 16"); return 1; }
+   rmh_ctx *c = d->c;
+   CUDA_OK(cudaSetDevice(c->device));
+   NcclApi *na = nccl_api();
+   if (!na) { set_error("rmh_dist_allreduce: libnccl.so.2 not found"); return 1; }
+   if (!d->comm)
+   {
+      if (!d->have_nccl_id) { set_error("rmh_dist_allreduce: no NCCL id (rank 0 could not create one)"); return 1; }
+      const int rc = na->CommInitRank(&d->comm, d->world, d->nccl_id, d->rank);
+      if (rc != 0)
+      { set_error(std::string("ncclCommInitRank: ") + (na->GetErrorString ? na->GetErrorString(rc) : "error")); return 1; }
+   }
+   cudaStream_t s = (cudaStream_t)stream;
+   CUDA_OK(cudaMemcpyAsync(d->d_red, vals, n * sizeof(double), cudaMemcpyHostToDevice, s));
+   const int nccl_double = 8, nccl_op = (op == 0) ? 0 : (op == 1 ? 3 : 2);   // ncclFloat64; ncclSum / ncclMin / ncclMax
+   const int rc = na->AllReduce(d->d_red, d->d_red, (size_t)n, nccl_double, nccl_op, d->comm, s);
+   if (rc != 0) { set_error(std::string("ncclAllReduce: ") + (na->GetErrorString ? na->GetErrorString(rc) : "error")); return 1; }
+   CUDA_OK(cudaMemcpyAsync(vals, d->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+   CUDA_OK(cudaStreamSynchronize(s));
+   return 0;
+}
+
+#endif

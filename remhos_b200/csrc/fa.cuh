@@ -188,7 +188,7 @@ __device__ __forceinline__ double nbr_value(const FaArgs &A, const double *u, in
    if (nb < 0) { if (gj) { *gj = -1; } return bval; }
    const int loc = A.fn.pat[(int)A.fn.nbr_pat[e * A.NF + f] * A.NFD + a];
    if (gj) { *gj = nb * A.ND + loc; }
-   return (nb < A.fn.ne_owned) ? u[nb * A.ND + loc] : A.fn.ughost[(nb - A.fn.ne_owned) * A.ND + loc];
+   return (nb < A.fn.ne_owned) ? u[nb * A.ND + loc] : A.fn.ughost[(nb - A.fn.ne_owned) * A.NFD + a];
 }
 
 // sum over the faces containing DOF i of BL (u_nbr - u_own)   (LinearFluxLumping, alpha = 0)

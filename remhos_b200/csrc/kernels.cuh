@@ -233,10 +233,10 @@ __device__ __forceinline__ void vol_apply(const double *U, double *R, double *sm
 // Neighbour data needed by the face terms.
 struct FaceNbr
 {
-   const int32_t *nbr_elem;   // [NE][NF]   (-1 boundary; >= ne_owned: ghost)
+   const int32_t *nbr_elem;   // [NE][NF]   (-1 boundary; >= ne_owned: ne_owned + ghost-face slot)
    const uint8_t *nbr_pat;    // [NE][NF]   pattern id
    const int16_t *pat;        // [npat][NFD] neighbour-local DOF of own face DOF j (natural order)
-   const double *ughost;      // ghost DOF blocks [ne_ghost][ND] (may be NULL)
+   const double *ughost;      // ghost face traces [n_slots][NFD], natural face order of the reader (may be NULL)
    int64_t ne_owned;
 };
 
@@ -269,7 +269,7 @@ __device__ __forceinline__ void face_apply(const double *U, double *R, double *s
          {
             const int loc = fn.pat[(int)fn.nbr_pat[ge * NF + f] * NFD + j];
             un = (nb < fn.ne_owned) ? ug[nb * ND + loc]
-                 : fn.ughost[(nb - fn.ne_owned) * ND + loc];
+                 : fn.ughost[(nb - fn.ne_owned) * NFD + j];
          }
          d = own - un;
       }

@@ -414,6 +414,32 @@ void bdr_dofs(int p, int dim, std::vector<int> &bd)
       }
 }
 
+void nat2ref_table(int p, int dim, std::vector<int> &n2r)
+{
+   const int n = p + 1, nf = 2 * dim;
+   int nfd = 1;
+   for (int a = 0; a < dim - 1; a++) { nfd *= n; }
+   std::vector<int> bd;
+   bdr_dofs(p, dim, bd);
+   n2r.assign((size_t)nf * nfd, -1);
+   for (int f = 0; f < nf; f++)
+   {
+      int axis, side;
+      face_axis(dim, f, axis, side);
+      for (int j = 0; j < nfd; j++)
+      {
+         int l[3] = {0, 0, 0}, m = j;
+         for (int a = 0; a < dim; a++)
+         {
+            if (a == axis) { l[a] = side * p; }
+            else { l[a] = m % n; m /= n; }
+         }
+         const int dof = l[0] + n * (l[1] + n * l[2]);
+         for (int r = 0; r < nfd; r++) { if (bd[r * nf + f] == dof) { n2r[f * nfd + j] = r; } }
+      }
+   }
+}
+
 static void sub2ind(int p, int dim, std::vector<int> &s)
 {
    const int n = p + 1;
@@ -764,6 +790,14 @@ extern "C" int rmh_mesh_load(const char *path, rmh_mesh **out)
 extern "C" int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t *lat, int32_t *nbr,
                                int *structured)
 {
+   return rmh::nbr_lattice_rows(dim, ne, ne, n_ent, lat, nbr, structured);
+}
+
+namespace rmh
+{
+int nbr_lattice_rows(int dim, int64_t ne, int64_t ne_rows, int32_t n_ent, const int32_t *lat,
+                     int32_t *nbr, int *structured)
+{
    if (dim != 2 && dim != 3) { set_error("rmh_nbr_lattice: dim must be 2 or 3"); return 1; }
    int n3 = 1;
    for (int a = 0; a < dim; a++) { n3 *= 3; }
@@ -790,9 +824,12 @@ extern "C" int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t
       out.erase(std::unique(out.begin(), out.end()), out.end());
    };
    int ok = 1;
-   std::vector<int32_t> S, T;
+#pragma omp parallel
+   {
+   std::vector<int32_t> S, T, rest;
    // pass 1: neighbours, by increasing number of non-zero offset components
-   for (int64_t e = 0; e < ne; e++)
+#pragma omp for schedule(static) reduction(min : ok)
+   for (int64_t e = 0; e < ne_rows; e++)
    {
       int32_t *nb = nbr + e * n3;
       for (int t = 0; t < n3; t++) { nb[t] = -2; }
@@ -822,7 +859,7 @@ extern "C" int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t
             }
             std::sort(T.begin(), T.end());
             T.erase(std::unique(T.begin(), T.end()), T.end());
-            std::vector<int32_t> rest;
+            rest.clear();
             std::set_difference(S.begin(), S.end(), T.begin(), T.end(), std::back_inserter(rest));
             if (rest.empty()) { nb[t] = -1; }
             else if (rest.size() == 1) { nb[t] = rest[0]; }
@@ -830,7 +867,8 @@ extern "C" int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t
          }
    }
    // pass 2: the neighbourhood must reproduce every entity's element set
-   for (int64_t e = 0; e < ne && ok; e++)
+#pragma omp for schedule(static) reduction(min : ok)
+   for (int64_t e = 0; e < ne_rows; e++)
    {
       const int32_t *nb = nbr + e * n3;
       for (int t = 0; t < n3 && ok; t++)
@@ -855,9 +893,11 @@ extern "C" int rmh_nbr_lattice(int dim, int64_t ne, int32_t n_ent, const int32_t
          if (T != S) { ok = 0; }
       }
    }
+   }
    if (structured) { *structured = ok; }
    return 0;
 }
+} // namespace rmh
 
 extern "C" int rmh_mesh_free(rmh_mesh *m) { delete m; return 0; }
 
@@ -970,11 +1010,22 @@ extern "C" int rmh_mesh_partition(const rmh_mesh *m, int nparts, int32_t *part)
 // ranks sharing at least a vertex with an owned element, ordered by (owner, global id), and per
 // peer the owned elements that are in the peer's ghost ring (ascending global id).  Vertex
 // adjacency is symmetric, so every rank derives matching send/receive lists without talking.
-struct rmh_halo
+int32_t rmh_halo::local_of(int64_t g) const
 {
-   std::vector<int64_t> owned, ghost, send;         // global element ids
-   std::vector<int32_t> ghost_owner, peers, send_off, recv_off;
-};
+   const auto it = std::lower_bound(owned_sorted.begin(), owned_sorted.end(), g);
+   if (it == owned_sorted.end() || *it != g) { return -1; }
+   return owned_pos[it - owned_sorted.begin()];
+}
+
+static void halo_index(rmh_halo *h)
+{
+   const size_t n = h->owned.size();
+   std::vector<int32_t> idx(n);
+   for (size_t i = 0; i < n; i++) { idx[i] = (int32_t)i; }
+   std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return h->owned[a] < h->owned[b]; });
+   h->owned_sorted.resize(n); h->owned_pos.resize(n);
+   for (size_t i = 0; i < n; i++) { h->owned_sorted[i] = h->owned[idx[i]]; h->owned_pos[i] = idx[i]; }
+}
 
 extern "C" int rmh_halo_create(const rmh_mesh *m, const int32_t *part, int rank, rmh_halo **out)
 {
@@ -1028,6 +1079,7 @@ extern "C" int rmh_halo_create(const rmh_mesh *m, const int32_t *part, int rank,
    if ((size_t)h->send_off.back() != sd.size())
    { set_error("halo: asymmetric adjacency"); delete h; return 1; }
    for (auto &x : sd) { h->send.push_back(x.second); }
+   halo_index(h);
    *out = h;
    return 0;
 }
@@ -1050,11 +1102,27 @@ extern "C" int rmh_halo_get(const rmh_halo *h, int64_t *owned, int64_t *ghost, i
    std::copy(h->peers.begin(), h->peers.end(), peers);
    std::copy(h->send_off.begin(), h->send_off.end(), send_off);
    std::copy(h->recv_off.begin(), h->recv_off.end(), recv_off);
-   for (size_t i = 0; i < h->send.size(); i++)
-   {
-      send_local[i] = (int32_t)(std::lower_bound(h->owned.begin(), h->owned.end(), h->send[i]) -
-                                h->owned.begin());
-   }
+   for (size_t i = 0; i < h->send.size(); i++) { send_local[i] = h->local_of(h->send[i]); }
+   return 0;
+}
+
+// Reorder the owned elements: those no peer needs (= those sharing no vertex with a ghost element;
+// vertex adjacency is symmetric) first, in their previous relative order; the others ("shell")
+// last.  The stage kernel runs the leading elements while the halo is still in flight.
+extern "C" int rmh_halo_interior_first(rmh_halo *h, int64_t *n_interior)
+{
+   const size_t n = h->owned.size();
+   std::vector<char> bnd(n, 0);
+   for (int64_t g : h->send) { bnd[h->local_of(g)] = 1; }
+   std::vector<int64_t> o2;
+   o2.reserve(n);
+   for (size_t i = 0; i < n; i++) { if (!bnd[i]) { o2.push_back(h->owned[i]); } }
+   const int64_t ni = (int64_t)o2.size();
+   for (size_t i = 0; i < n; i++) { if (bnd[i]) { o2.push_back(h->owned[i]); } }
+   h->owned.swap(o2);
+   halo_index(h);
+   h->n_interior = ni;
+   if (n_interior) { *n_interior = ni; }
    return 0;
 }
 

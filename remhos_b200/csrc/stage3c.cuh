@@ -31,6 +31,17 @@
 // Shared-memory layout at order 3 (tools/bank_sim_c.py): plane stride 18, element stride 72 doubles:
 // row (128-bit) and z-line accesses are conflict-free, y-lines use their own lane map (planes
 // {0,2} / {1,3} per half-warp) which makes them conflict-free too.
+//
+// FOLD (v14): the overlap bounds (DofInfo::ComputeOverlapBounds, remhos_tools.cpp:432-495) are formed
+// in the kernel from the (min,max) pairs of the 3x3x3 neighbourhood elements (rmh_nbr_lattice) by a
+// separable min/max filter in shared memory -- the separate entity pass (k_ent_min_max +
+// k_xe_interleave, 15 % of a stage in round 1) and its 2 x 113 MB entity array are gone; element
+// (min,max) pairs ping-pong between two arrays (the kernel reads its neighbours' input pairs while
+// other warps already write output pairs).
+// GH + flags (multi-GPU): owned elements are ordered interior first; ghost neighbour traces and
+// ghost (min,max) pairs are written into this rank's window by the peers' k_halo_put (dist.cuh);
+// a warp polls the peers' epoch flags once, before it fetches its first shell group -- one launch
+// per stage, the exchange hidden behind the interior elements.
 #ifndef RMH_STAGE3C_CUH
 #define RMH_STAGE3C_CUH
 
@@ -146,7 +157,8 @@ __device__ __forceinline__ void stagec_fetch_idx(const StagePArgs &a, unsigned s
 }
 
 // lane = (el, row): its own row of y; then the group's neighbour traces, bounds and coefficients.
-// GH: some neighbours are ghost elements (multi-GPU), their DOF blocks live in a.fn.ughost.
+// GH: some neighbours are ghost elements (multi-GPU): nbr_elem = ne_owned + slot, the neighbour's
+// face trace in this element's natural face order is a.fn.ughost[slot][NFD].
 template <int D1, int NST, bool GH>
 __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *dst, const int *ix,
                                                   const int16_t *spat, int64_t e0, int nv, int lane,
@@ -202,7 +214,7 @@ __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *d
             const double *src = a.y + (unsigned)((nb < 0 ? 0 : nb) * ND + loc);
             if (GH)
             {
-               if (nb >= a.fn.ne_owned) { src = a.fn.ughost + (unsigned)((nb - (int)a.fn.ne_owned) * ND + loc); }
+               if (nb >= a.fn.ne_owned) { src = a.fn.ughost + (unsigned)((nb - (int)a.fn.ne_owned) * NFD + j); }
             }
             cps8z(d, src, nb < 0 ? 0u : 8u);
          }
@@ -240,6 +252,46 @@ __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *d
    }
 }
 
+// One axis of the separable min/max filter over the 3x3x3 neighbourhood pairs BD[el][27]
+// (index dx + 3 dy + 9 dz, (min,max) as double2): the three values along the axis become
+// (v0 ^ v1, v1, v1 ^ v2).  After the x-, y- and z-pass entry (cx,cy,cz) is the (min,max) over the
+// elements sharing lattice entity (cx,cy,cz) of the element (c = 0 | 1 | 2: low face, interior, high
+// face along that axis).  9 lines per element and pass, in place (a lane owns its line).
+template <int E, int BEL, int AX>
+__device__ __forceinline__ void fold_pass(double *BD, int lane)
+{
+   constexpr int ST = (AX == 0) ? 1 : (AX == 1 ? 3 : 9);
+#pragma unroll
+   for (int t0 = 0; t0 < E * 9; t0 += 32)
+   {
+      const int t = t0 + lane;
+      if (t < E * 9)
+      {
+         const int el = t / 9, r = t - el * 9, q0 = r % 3, q1 = r / 3;
+         const int i0 = (AX == 0) ? (3 * q0 + 9 * q1) : (AX == 1 ? (q0 + 9 * q1) : (q0 + 3 * q1));
+         double2 *p = reinterpret_cast<double2 *>(BD + el * BEL) + i0;
+         const double2 v0 = p[0], v1 = p[ST], v2 = p[2 * ST];
+         p[0] = make_double2(v0.x < v1.x ? v0.x : v1.x, v0.y > v1.y ? v0.y : v1.y);
+         p[2 * ST] = make_double2(v2.x < v1.x ? v2.x : v1.x, v2.y > v1.y ? v2.y : v1.y);
+      }
+   }
+}
+
+// every lane waits until all n peers have published epoch (k_halo_put's release store, system scope)
+__device__ __forceinline__ void wait_peer_flags(const unsigned long long *flags, int n, unsigned long long epoch)
+{
+   for (int p = 0; p < n; p++)
+   {
+      unsigned long long v;
+      while (true)
+      {
+         asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flags + p) : "memory");
+         if (v >= epoch) { break; }
+         __nanosleep(128);
+      }
+   }
+}
+
 template <int LG>
 __device__ __forceinline__ double group_sum(double v)
 {
@@ -248,7 +300,7 @@ __device__ __forceinline__ double group_sum(double v)
    return v;
 }
 
-template <int D1, int NW, int MINB, int NST, bool GH>
+template <int D1, int NW, int MINB, int NST, bool GH, bool FOLD>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_stage3c(StagePArgs a, const TabC<D1> tab)
 {
@@ -296,6 +348,15 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    if (gi >= NG) { return; }
    const int last_nv = (int)(a.ne - (NG - 1) * E);
    auto nvalid = [&](int64_t g) { return (g + 1 == NG) ? last_nv : E; };
+   // multi-GPU: the halo of y must have landed before the first group at or behind shell_begin is fetched
+   bool halo_ok = !(GH && a.flags != nullptr);
+   auto need_halo = [&](int64_t g)
+   {
+      if (GH)
+      {
+         if (!halo_ok && g * E + E > a.shell_begin) { wait_peer_flags(a.flags, a.n_wait, a.epoch); halo_ok = true; }
+      }
+   };
    // ---- prologue: indices of the first NST-1 groups, then their data and the next NST-1 index sets
 #pragma unroll
    for (int m = 0; m < NST - 1; m++)
@@ -313,6 +374,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
       if (g < NG)
       {
          const int nv = nvalid(g);
+         need_halo(g);
          stagec_fetch_data<D1, NST, GH>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, g * E, nv, lane,
                                     lane_on && el < nv, row_src, row_dst);
       }
@@ -373,6 +435,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          if (g1 < NG)
          {
             const int nv1 = nvalid(g1);
+            need_halo(g1);
             stagec_fetch_data<D1, NST, GH>(a, wsm + s1 * S::PSZ, ismem + s1 * S::ISZ, spat, g1 * E, nv1, lane,
                                        lane_on && el < nv1, row_src, row_dst);
          }
@@ -380,6 +443,8 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          cp_async_commit();
          if (gi + GW < NG) { load_x0(gi + GW); }
       }
+      double *BDW = dat + S::P_B;
+      if (FOLD) { fold_pass<E, BEL, 0>(BDW, lane); }
       // ================= y-lines and z-lines -> XY, XZ (every lane owns one line of each kind)
       //   out_i = sum_k c_k v_k - (Minv[i][0] vs_lo) nbr_lo - (Minv[i][p] vs_hi) nbr_hi,
       //   c = -a T[i][:], c_0 += Minv[i][0] vs_lo, c_p += Minv[i][p] vs_hi
@@ -400,6 +465,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
             XY[yl_base + i * RS] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -ay * sacc));
          }
       }
+      if (FOLD) { __syncwarp(); fold_pass<E, BEL, 1>(BDW, lane); }
       if (on)
       {
          const double az = A[el * 4 + 2];
@@ -417,6 +483,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
             XZ[zl_base + i * SZ] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -az * sacc));
          }
       }
+      if (FOLD) { __syncwarp(); fold_pass<E, BEL, 2>(BDW, lane); }
       // ================= x-row in registers
       double u[D1], ho[D1];
 #pragma unroll
@@ -560,7 +627,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
                for (int i = 0; i < D1; i++) { p[i] = o[i]; }
             }
          }
-         if (a.xe_min_out)
+         if (FOLD || a.xe_min_out)
          {
 #pragma unroll
             for (int s = LG / 2; s > 0; s >>= 1)
@@ -568,7 +635,11 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
                omin = dmin(omin, __shfl_xor_sync(0xffffffffu, omin, s));
                omax = dmax(omax, __shfl_xor_sync(0xffffffffu, omax, s));
             }
-            if (r == 0 && el < nv) { a.xe_min_out[gi * E + el] = omin; a.xe_max_out[gi * E + el] = omax; }
+            if (r == 0 && el < nv)
+            {
+               if (FOLD) { a.xe_mm_out[gi * E + el] = make_double2(omin, omax); }
+               else { a.xe_min_out[gi * E + el] = omin; a.xe_max_out[gi * E + el] = omax; }
+            }
          }
       }
       slot = (slot + 1 == NST) ? 0 : slot + 1;

@@ -70,7 +70,7 @@ struct Pre3
    double d0[Q], d1[Q], d2[Q];
    double df[K2][Q];
    // frag = false: Dvol [e][3][NQ], Dface [e][qb][f][qa];  frag = true: the fragment-ordered
-   // layout of stage3t.cuh, Dvol [e][col][qz (RQ)][3], Dface [e][f][qa][qb (RQ)]
+   // layout of stage3w.cuh, Dvol [e][col][qz (RQ)][3], Dface [e][f][qa][qb (RQ)]
    __device__ __forceinline__ void load(const double *__restrict__ Dvol,
                                         const double *__restrict__ Dface, int64_t e0, int ne,
                                         bool frag)
@@ -128,7 +128,7 @@ __device__ __forceinline__ void face3_gather(double *sm, const double *__restric
          if (nb >= 0)
          {
             const int loc = fn.pat[(int)fn.nbr_pat[ge * NF + f] * NFD + j];
-            un = (nb < fn.ne_owned) ? ug[nb * ND + loc] : fn.ughost[(nb - fn.ne_owned) * ND + loc];
+            un = (nb < fn.ne_owned) ? ug[nb * ND + loc] : fn.ughost[(nb - fn.ne_owned) * NFD + j];
          }
          d = own - un;
       }

@@ -95,12 +95,20 @@ struct StagePArgs
    const int32_t *nbr_pat32;  // [NE][NF] pattern ids as int32 (cp.async granularity)
    double a, b, dt;
    int out_mode, has_x0;
-   int frag;                  // stored quadrature data in fragment order (stage3t.cuh)
+   int frag;                  // stored quadrature data in fragment order (stage3w.cuh)
    int bounds_type;           // 0: bidx = lat [NE][27] -> ent_mm; 1: bidx = bnbr [NE][NF] -> xe_min/xe_max
    const int32_t *bidx;
    const double *ent_mm;      // [n_ent][2]
    const double *xe_min, *xe_max;
    double *xe_min_out, *xe_max_out;
+   // k_stage3c<FOLD>: bidx = nb27 [NE][27] (element ids; boundary -> the (inf,-inf) sentinel), ent_mm =
+   // the input (min,max) pairs [ne + ne_ghost + 1], xe_mm_out = the output pairs (other buffer)
+   double2 *xe_mm_out = nullptr;
+   // multi-GPU (dist.cuh): peers' epoch flags [n_wait]; elements >= shell_begin depend on the halo
+   const unsigned long long *flags = nullptr;
+   int n_wait = 0;
+   unsigned long long epoch = 0;
+   int64_t shell_begin = 0;
 };
 
 template <int D1, int Q, int E>
@@ -177,7 +185,7 @@ __device__ __forceinline__ void stagep_fetch_data(const StagePArgs &a, double *d
             const int loc = (pid < S::PATMAX) ? spat[pid * NFD + j] : a.fn.pat[pid * NFD + j];
             const double *src = (nb < a.fn.ne_owned)
                                    ? a.y + (int64_t)nb * ND + loc
-                                   : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * ND + loc;
+                                   : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * NFD + j;
             cp_async8(NB + id, src);
          }
          else { NB[id] = 0.0; }

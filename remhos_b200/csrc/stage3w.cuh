@@ -10,11 +10,11 @@
 //     through (neighbour element, orientation pattern), entity (min,max) pairs, 1/volume; the
 //     gather indices are fetched one element further ahead.  The stored quadrature data of the
 //     next element is pulled into L2 with prefetch.global.L2 and read by plain 16-byte loads in
-//     fragment order (see stage3t.cuh for the layout) right where it is consumed.
+//     fragment order (layout below) right where it is consumed.
 //   contractions: 8-line DMMA tiles with compile-time tile indices (all shared-memory offsets
 //     are per-lane constants); the 1-D matrices are register fragments; the z-stage
 //     (forward-z, D.grad u, backward-z) and the fused face stage chain D fragments as A operands
-//     and never leave registers (stage3t.cuh explains the fragment algebra).
+//     and never leave registers (fragment algebra below).
 //   tail: MassBasedAvg, bounds gather, ClipScale (two shuffle reductions), RK combination and the
 //     element min/max of the output, on the same warp.
 //
@@ -22,13 +22,32 @@
 // instructions are DFMA; sm_100a DFMA takes no constant operand, so each coefficient costs an
 // LDCU, each 4x6 line 10 LDS/STS).  DMMA has the same measured peak (36.9 TFLOP/s) at 1/8 of the
 // issue slots.
+//
+// Fragment algebra.  Every contraction is a set of 8-line tiles  D[8 x 8] += A[8 x 4] B[4 x 8]
+// (g = lane/4, c = lane%4):
+//     A fragment: A[g][c]          B fragment: B[k=c][n=g]          D fragment: D[g][2c], D[g][2c+1]
+// A 1-D matrix M (Q x D1 forward, D1 x Q backward) is held once per thread as fragment registers
+// (the same register serves as A operand "rows = outputs" and as B operand "cols = outputs").
+// A D fragment whose columns are the next contracted index is fed straight back as the A operand
+// of the following DMMA (columns 2c -> k-step 1, 2c+1 -> k-step 2, coefficient rows permuted to
+// match).  The stored quadrature data is laid out in HBM in fragment order (ctx.cu, run_geom):
+//     Dvol [e][col = qy*Q+qx][qz (RQ)][3]     -> 3 x 16-byte loads per thread and tile, coalesced
+//     Dface[e][f][qa][qb (RQ)]                -> 1 x 16-byte load per thread and tile
 #ifndef RMH_STAGE3W_CUH
 #define RMH_STAGE3W_CUH
 
-#include "stage3t.cuh"
+#include "stage3p.cuh"
 
 namespace rmh
 {
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(d0), "+d"(d1)
+                : "d"(a), "d"(b));
+}
+
 
 template <int D1, int Q>
 struct SmemW
@@ -198,7 +217,7 @@ __device__ __forceinline__ void stagew_fetch_data(const StagePArgs &a, double *d
                const int loc = (pid < S::PATMAX) ? spat[pid * NFD + j] : a.fn.pat[pid * NFD + j];
                const double *src = (nb < a.fn.ne_owned)
                                       ? a.y + (int64_t)nb * ND + loc
-                                      : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * ND + loc;
+                                      : a.fn.ughost + ((int64_t)nb - a.fn.ne_owned) * NFD + j;
                cp_async8(NB + id, src);
             }
             else { NB[id] = 0.0; }

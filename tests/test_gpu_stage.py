@@ -123,10 +123,13 @@ def test_stage_kernel_variants(problem, order, bt, const, lin, monkeypatch):
     ref = run.mult(u, 0.0, run.dt)
     tol = 1e-10 if order <= 3 else 1e-8
     out = []
-    for env, flags in [({}, 3 | (8 if const else 0)),
+    # bit 4: overlap bounds formed inside the constant-coefficient kernel (k_stage3c<FOLD>)
+    fold = 16 if (const and bt == 0) else 0
+    for env, flags in [({}, 3 | (8 if const else 0) | fold),
                        ({'RMH_LINEAR_OP': '1', 'RMH_NO_CONST_OP': '1'}, 3 | (4 if lin else 0)),
-                       ({'RMH_NO_CONST_OP': '1'}, 3)]:
-        for k_ in ('RMH_LINEAR_OP', 'RMH_NO_CONST_OP'):
+                       ({'RMH_NO_CONST_OP': '1'}, 3),
+                       ({'RMH_NO_FOLD': '1'}, 3 | (8 if const else 0))]:
+        for k_ in ('RMH_LINEAR_OP', 'RMH_NO_CONST_OP', 'RMH_NO_FOLD'):
             monkeypatch.delenv(k_, raising=False)
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
@@ -138,21 +141,23 @@ def test_stage_kernel_variants(problem, order, bt, const, lin, monkeypatch):
         assert rel_err(out[-1].reshape(u.shape), ref) < tol, env
         ctx.close()
     assert rel_err(out[0], out[2]) < 1e-12 and rel_err(out[1], out[2]) < 1e-12
+    assert rel_err(out[3], out[0]) < 1e-13      # bounds through the entity pass or in the kernel: same operator
 
 
 def test_const_kernel_ring_depths(monkeypatch):
-    """every (warps, resident blocks, ring depth) configuration of k_stage3c gives the same RK3 step"""
+    """every (warps, resident blocks) configuration of k_stage3c, with the overlap bounds formed in
+    the kernel or by the entity pass, gives the same RK3 step"""
     run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=0,
                      rs_levels=2, order=3, dt=0.005, max_steps=2)
     res = []
-    for cfg in ('0', '822', '632', '1213', '2012', '1022'):
+    for cfg, nofold in (('0', '0'), ('822', '0'), ('0', '1'), ('822', '1')):
         # the configuration is latched per process on first use: run each in a fresh interpreter
         import subprocess, sys, os, json
         code = ("import sys, os, numpy as np, torch; sys.path[:0] = [%r, %r, %r];"
                 "from helpers import oracle_run, ctx_from_oracle;"
                 "run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=0,"
                 " rs_levels=2, order=3, dt=0.005, max_steps=2);"
-                "ctx = ctx_from_oracle(run); assert ctx.path_flags == 11;"
+                "ctx = ctx_from_oracle(run); assert ctx.path_flags in (11, 27);"
                 "u = torch.tensor(run.u.reshape(-1), device='cuda'); t = 0.0\n"
                 "for _ in range(2): t = ctx.rk_step(3, 5, t, run.dt, u)\n"
                 "np.save(sys.argv[1], u.cpu().numpy())")
@@ -161,7 +166,7 @@ def test_const_kernel_ring_depths(monkeypatch):
         import tempfile
         with tempfile.TemporaryDirectory() as td:
             f = os.path.join(td, 'u.npy')
-            env = dict(os.environ, RMH_C_CFG=cfg)
+            env = dict(os.environ, RMH_C_CFG=cfg, RMH_NO_FOLD=nofold)
             subprocess.check_call([sys.executable, '-c', code, f], env=env)
             res.append(np.load(f))
     run.run()
