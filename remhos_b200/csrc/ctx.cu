@@ -2033,7 +2033,7 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
          pa.ent_mm = reinterpret_cast<const double *>(c->xe_mm2[par]);
          pa.xe_mm_out = c->xe_mm2[par ^ 1];
       }
-      dist_stage_args(c, pa, use_c);
+      dist_stage_args(c, pa, fold);
    }
    auto run = [&]()
    {

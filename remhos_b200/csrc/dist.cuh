@@ -338,10 +338,11 @@ extern "C" int rmh_dist_destroy(rmh_dist *d)
    return 0;
 }
 
-// true when stage_impl will run the constant-coefficient kernel (which waits for the halo itself)
+// true when stage_impl will run k_stage3c<FOLD>, which waits for the halo itself (every other kernel --
+// and the entity pass in front of it -- reads ghost (min,max) from xe_min / xe_max: k_halo_wait first)
 static bool dist_in_kernel_wait(const rmh_ctx *c, const double *x0, const double *y, const double *out)
 {
-   return c->pipelined && c->dim == 3 && c->all_affine && c->frag && c->op_const && c->npat <= 16 &&
+   return c->fold && c->pipelined && c->dim == 3 && c->all_affine && c->frag && c->op_const && c->npat <= 16 &&
           ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
 }
 

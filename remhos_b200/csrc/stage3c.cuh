@@ -34,7 +34,7 @@
 //
 // FOLD (v14): the overlap bounds (DofInfo::ComputeOverlapBounds, remhos_tools.cpp:432-495) are formed
 // in the kernel from the (min,max) pairs of the 3x3x3 neighbourhood elements (rmh_nbr_lattice) by a
-// separable min/max filter in shared memory -- the separate entity pass (k_ent_min_max +
+// separable min/max filter in registers (fold_bounds) -- the separate entity pass (k_ent_min_max +
 // k_xe_interleave, 15 % of a stage in round 1) and its 2 x 113 MB entity array are gone; element
 // (min,max) pairs ping-pong between two arrays (the kernel reads its neighbours' input pairs while
 // other warps already write output pairs).
@@ -252,28 +252,32 @@ __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *d
    }
 }
 
-// One axis of the separable min/max filter over the 3x3x3 neighbourhood pairs BD[el][27]
-// (index dx + 3 dy + 9 dz, (min,max) as double2): the three values along the axis become
-// (v0 ^ v1, v1, v1 ^ v2).  After the x-, y- and z-pass entry (cx,cy,cz) is the (min,max) over the
-// elements sharing lattice entity (cx,cy,cz) of the element (c = 0 | 1 | 2: low face, interior, high
-// face along that axis).  9 lines per element and pass, in place (a lane owns its line).
-template <int E, int BEL, int AX>
-__device__ __forceinline__ void fold_pass(double *BD, int lane)
+// Separable min/max filter over the 3x3x3 neighbourhood pairs BD[el][27] (index dx + 3 dy + 9 dz,
+// (min,max) as double2), in registers: lane L < 27 holds pair L; along each axis in turn the two
+// outer values absorb the middle one -- (v0 ^ v1, v1, v1 ^ v2) -- through one shuffle from the middle
+// lane of the line.  After the x-, y- and z-pass entry (cx,cy,cz) is the (min,max) over the elements
+// sharing lattice entity (cx,cy,cz) of the element (c = 0 | 1 | 2: low face, interior, high face
+// along that axis).  No shared-memory round trips and no barrier between the passes, so the chain
+// overlaps with the line contractions that follow it.
+template <int E, int BEL>
+__device__ __forceinline__ void fold_bounds(double *BD, int lane)
 {
-   constexpr int ST = (AX == 0) ? 1 : (AX == 1 ? 3 : 9);
+   const int dx = lane % 3, dy = (lane / 3) % 3, dz = lane / 9;
+   const int sx = lane - dx + 1, sy = lane - 3 * dy + 3, sz = lane - 9 * dz + 9;   // middle lane of the line
+   const bool ex = (dx != 1), ey = (dy != 1), ez = (dz != 1);
+   const int ld = lane < 27 ? lane : 26;
 #pragma unroll
-   for (int t0 = 0; t0 < E * 9; t0 += 32)
+   for (int el = 0; el < E; el++)
    {
-      const int t = t0 + lane;
-      if (t < E * 9)
-      {
-         const int el = t / 9, r = t - el * 9, q0 = r % 3, q1 = r / 3;
-         const int i0 = (AX == 0) ? (3 * q0 + 9 * q1) : (AX == 1 ? (q0 + 9 * q1) : (q0 + 3 * q1));
-         double2 *p = reinterpret_cast<double2 *>(BD + el * BEL) + i0;
-         const double2 v0 = p[0], v1 = p[ST], v2 = p[2 * ST];
-         p[0] = make_double2(v0.x < v1.x ? v0.x : v1.x, v0.y > v1.y ? v0.y : v1.y);
-         p[2 * ST] = make_double2(v2.x < v1.x ? v2.x : v1.x, v2.y > v1.y ? v2.y : v1.y);
-      }
+      double2 *p = reinterpret_cast<double2 *>(BD + el * BEL);
+      double2 v = p[ld];
+      double mn = __shfl_sync(0xffffffffu, v.x, sx), mx = __shfl_sync(0xffffffffu, v.y, sx);
+      if (ex) { v.x = mn < v.x ? mn : v.x; v.y = mx > v.y ? mx : v.y; }
+      mn = __shfl_sync(0xffffffffu, v.x, sy); mx = __shfl_sync(0xffffffffu, v.y, sy);
+      if (ey) { v.x = mn < v.x ? mn : v.x; v.y = mx > v.y ? mx : v.y; }
+      mn = __shfl_sync(0xffffffffu, v.x, sz); mx = __shfl_sync(0xffffffffu, v.y, sz);
+      if (ez) { v.x = mn < v.x ? mn : v.x; v.y = mx > v.y ? mx : v.y; }
+      if (lane < 27) { p[lane] = v; }
    }
 }
 
@@ -443,8 +447,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          cp_async_commit();
          if (gi + GW < NG) { load_x0(gi + GW); }
       }
-      double *BDW = dat + S::P_B;
-      if (FOLD) { fold_pass<E, BEL, 0>(BDW, lane); }
+      if (FOLD) { fold_bounds<E, BEL>(dat + S::P_B, lane); }     // visible to the tail after the __syncwarp below
       // ================= y-lines and z-lines -> XY, XZ (every lane owns one line of each kind)
       //   out_i = sum_k c_k v_k - (Minv[i][0] vs_lo) nbr_lo - (Minv[i][p] vs_hi) nbr_hi,
       //   c = -a T[i][:], c_0 += Minv[i][0] vs_lo, c_p += Minv[i][p] vs_hi
@@ -465,7 +468,6 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
             XY[yl_base + i * RS] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -ay * sacc));
          }
       }
-      if (FOLD) { __syncwarp(); fold_pass<E, BEL, 1>(BDW, lane); }
       if (on)
       {
          const double az = A[el * 4 + 2];
@@ -483,7 +485,6 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
             XZ[zl_base + i * SZ] = fma(tab.Mp[i], jh, fma(tab.M0[i], jl, -az * sacc));
          }
       }
-      if (FOLD) { __syncwarp(); fold_pass<E, BEL, 2>(BDW, lane); }
       // ================= x-row in registers
       double u[D1], ho[D1];
 #pragma unroll
