@@ -90,6 +90,37 @@ class Port:
         u0 = problems.u0(problem, sp.dof_points(m.X).reshape(-1, 3), bb_min, bb_max).reshape(m.ne, sp.nd)
         return port, u0
 
+    @classmethod
+    def from_mesh_file(cls, path, rs, order, problem=0, mesh_order=2, nodal_velocity=None):
+        """Port on a mesh file refined rs times, built with the oracle's own mesh code (reader,
+        refinement, topology, NbrDof map) -- the element order is the one of the product's mesh module
+        (tests/test_mesh.py pins the maps bit for bit).  No dense element matrices are assembled, so
+        this scales to the -rs 3/4 meshes the numpy oracle is too heavy for.
+        Returns (port, u0 [ne, nd], (u0_min, u0_max))."""
+        from . import mesh as meshmod, dg, problems
+        m = meshmod.read_mesh(path)
+        for _ in range(rs):
+            m = meshmod.refine_uniform(m)
+        bb_min, bb_max = meshmod.bounding_box(m)
+        m = meshmod.set_curvature(m, mesh_order)
+        topo = meshmod.Topology(m)
+        sp = dg.Space(3, order, mesh_order)
+        nbr = dg.nbr_dof_map(topo, order)
+
+        def vel(pts):
+            return problems.velocity(problem, pts.reshape(-1, 3), bb_min, bb_max).reshape(pts.shape)
+        if nodal_velocity is None:
+            nodal_velocity = (problem % 20) in (0, 1, 2, 4, 5, 6, 7)
+        kw = {}
+        if nodal_velocity:
+            kw['vel_nodes'] = vel(m.X)
+        else:
+            kw['vel_quad'] = vel(sp.quad_points(m.X))
+            kw['vel_face'] = np.stack([vel(sp.face_quad_points(m.X, f)) for f in range(sp.nf)], axis=1)
+        port = cls(order, mesh_order, 0, m.X, nbr, topo.lat, topo.n_ent, **kw)
+        u0 = problems.u0(problem, sp.dof_points(m.X).reshape(-1, 3), bb_min, bb_max).reshape(m.ne, sp.nd)
+        return port, u0
+
     def close(self):
         if self.h:
             lib().roc_destroy(self.h)

@@ -9,8 +9,12 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <fstream>
 #include <map>
 #include <sstream>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 
 namespace remhos
 {
@@ -18,6 +22,78 @@ namespace remhos
 void Abort(const std::string &msg) { throw std::runtime_error(msg); }
 void Verify(bool cond, const std::string &msg) { if (!cond) { Abort(msg); } }
 void Check(int status) { if (status != 0) { Abort(rmh_last_error()); } }
+
+// ------------------------------------------------------------------------------------ Communicator
+Communicator::Communicator()
+{
+   auto env_int = [](const char *k, int dflt) { const char *v = std::getenv(k); return v ? std::atoi(v) : dflt; };
+   rank = env_int("RANK", 0); world = env_int("WORLD_SIZE", 1); local_rank = env_int("LOCAL_RANK", rank);
+   Verify(world >= 1 && rank >= 0 && rank < world, "bad RANK / WORLD_SIZE");
+   if (world > 1)
+   {
+      const char *d = std::getenv("RMH_RDZV_DIR");
+      if (d) { dir = d; }
+      else
+      {
+         // workers of one launcher share the parent process and the rendezvous port
+         std::ostringstream os;
+         os << "/dev/shm/rmh_rdzv_" << (long)getppid() << "_" << env_int("MASTER_PORT", 0);
+         dir = os.str();
+      }
+      mkdir(dir.c_str(), 0700);
+   }
+}
+
+// every rank writes <dir>/<seq>.<rank> (temporary name, then rename: readers never see a partial
+// file) and reads the others'; blobs come back ordered by rank
+std::vector<std::string> Communicator::AllGather(const std::string &mine)
+{
+   std::vector<std::string> out(world);
+   if (world == 1) { out[0] = mine; return out; }
+   const int id = seq++;
+   auto name = [&](int r) { std::ostringstream os; os << dir << "/" << id << "." << r; return os.str(); };
+   {
+      const std::string tmp = name(rank) + ".tmp";
+      std::ofstream f(tmp, std::ios::binary);
+      f.write(mine.data(), (std::streamsize)mine.size());
+      f.close();
+      Verify((bool)f, "rendezvous: cannot write " + tmp);
+      Verify(std::rename(tmp.c_str(), name(rank).c_str()) == 0, "rendezvous: rename failed");
+   }
+   const auto t0 = std::chrono::steady_clock::now();
+   for (int r = 0; r < world; r++)
+   {
+      if (r == rank) { out[r] = mine; continue; }
+      while (true)
+      {
+         std::ifstream f(name(r), std::ios::binary);
+         if (f)
+         {
+            std::ostringstream ss;
+            ss << f.rdbuf();
+            out[r] = ss.str();
+            break;
+         }
+         const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+         Verify(waited < 600.0, "rendezvous: timed out waiting for rank " + std::to_string(r));
+         std::this_thread::sleep_for(std::chrono::milliseconds(2));
+      }
+   }
+   return out;
+}
+
+void Communicator::Finalize()
+{
+   if (world == 1) { return; }
+   Barrier();
+   // everybody has passed gather seq-1, hence read every earlier file: drop my own (the files of the
+   // last barrier stay until the launcher removes the directory)
+   for (int id = 0; id + 1 < seq; id++)
+   {
+      std::ostringstream os; os << dir << "/" << id << "." << rank;
+      std::remove(os.str().c_str());
+   }
+}
 
 // ------------------------------------------------------------------------------------ Vector
 Vector::Vector(const ParFiniteElementSpace &space) { SetSpace(space); }
@@ -75,13 +151,15 @@ void Vector::Add(double a, const Vector &x)
 // ------------------------------------------------------------------------------------ space
 ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int order_, int mesh_order_,
                                              int bounds_type_, double &dt, double &t_final_,
-                                             int device)
-   : mesh(m), order(order_), mesh_order(mesh_order_), bounds_type(bounds_type_), problem(problem_)
+                                             int device, Communicator *comm_)
+   : mesh(m), order(order_), mesh_order(mesh_order_), bounds_type(bounds_type_), problem(problem_),
+     comm(comm_)
 {
    dim = rmh_mesh_dim(m);
    exec_mode = (problem < 10) ? 0 : 1;                                   // remhos.cpp:438-440
    bb_min.assign(dim, 0.0); bb_max.assign(dim, 0.0);
    Check(rmh_mesh_bounding_box(m, bb_min.data(), bb_max.data()));        // :457
+   if (comm && comm->world > 1) { SetupDistributed(dt, t_final_, device); return; }
    Check(rmh_mesh_set_curvature(m, mesh_order));                         // :513
    if (dt < 0.0) { Check(rmh_cfl_dt(m, problem, bb_min.data(), bb_max.data(), &dt)); }   // :538-553
    dt_cfl = dt;
@@ -167,9 +245,107 @@ ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int orde
    bdr_dofs = bd;
    nbr_elem = nbe;
 }
+// One rank's share of a decomposed run: what ParMesh(MPI_COMM_WORLD, mesh) and the parallel space do
+// at remhos.cpp:459-463,588-623.  Partition (every rank computes the same recursive bisection), halo
+// plan with the owned elements interior first, local mesh = owned + ghost ring, context with a ghost
+// layer, exchange plan, device layer; the set-up blobs travel through the Communicator.
+void ParFiniteElementSpace::SetupDistributed(double &dt, double &t_final_, int device)
+{
+   Verify(exec_mode == 0, "decomposed runs cover transport mode");
+   const int pv = problem % 20;
+   Verify(pv == 0 || pv == 1 || pv == 2 || pv == 4 || pv == 5 || pv == 6 || pv == 7,
+          "decomposed runs sample the velocity at the mesh nodes (problems 0, 1, 2, 4, 5, 6, 7)");
+   global_mesh = mesh;
+   const int rank = comm->rank, world = comm->world;
+   std::vector<int32_t> part((size_t)rmh_mesh_ne(global_mesh));
+   Check(rmh_mesh_partition(global_mesh, world, part.data()));
+   Check(rmh_halo_create(global_mesh, part.data(), rank, &halo));
+   int64_t n_interior = 0;
+   Check(rmh_halo_interior_first(halo, &n_interior));
+   int64_t no = 0, ng = 0, nsend = 0;
+   int32_t npeer = 0;
+   Check(rmh_halo_sizes(halo, &no, &ng, &npeer, &nsend));
+   std::vector<int64_t> ids((size_t)(no + ng));
+   {
+      std::vector<int32_t> peers(npeer), soff(npeer + 1), roff(npeer + 1), sloc((size_t)nsend);
+      Check(rmh_halo_get(halo, ids.data(), ids.data() + no, peers.data(), soff.data(), roff.data(), sloc.data()));
+   }
+   Check(rmh_mesh_extract(global_mesh, no + ng, ids.data(), &local_mesh));
+   Check(rmh_mesh_set_curvature(local_mesh, mesh_order));                // :513
+   std::vector<int64_t> own((size_t)no);
+   for (int64_t i = 0; i < no; i++) { own[i] = i; }
+   Check(rmh_mesh_extract(local_mesh, no, own.data(), &mesh));           // owned part: what GetNE() counts
+   int ngn = 1, nd = 1, nf = 2 * dim, nfd = 1, n3 = 1, nsub = 1, ncorner = 1;
+   for (int a = 0; a < dim; a++) { ngn *= mesh_order + 1; nd *= order + 1; n3 *= 3; nsub *= std::max(order, 1); ncorner *= 2; }
+   for (int a = 0; a < dim - 1; a++) { nfd *= order + 1; }
+   const double *nodes = rmh_mesh_nodes(mesh);
+   std::vector<double> vel_nodes((size_t)no * ngn * dim);
+   Check(rmh_velocity(problem, dim, no * ngn, nodes, bb_min.data(), bb_max.data(), vel_nodes.data()));
+   const int64_t na = no + ng;
+   std::vector<int32_t> bd((size_t)nfd * nf), nbr((size_t)na * nf * nfd), s2i((size_t)nsub * ncorner),
+       lat((size_t)na * n3), nbe((size_t)na * nf);
+   int32_t n_ent = 0;
+   Check(rmh_mesh_dof_maps(local_mesh, order, bd.data(), nbr.data(), s2i.data(), lat.data(), &n_ent, nbe.data()));
+   std::vector<double> lp(order + 1);
+   for (int i = 0; i <= order; i++) { lp[i] = (double)i / std::max(order, 1); }
+   std::vector<double> xdof((size_t)no * nd * dim), infl((size_t)no * nd);
+   Check(rmh_mesh_eval(mesh, order + 1, lp.data(), -1, xdof.data()));
+   Check(rmh_inflow_project(mesh, problem, order, infl.data()));
+   rmh_desc d;
+   std::memset(&d, 0, sizeof(d));
+   d.dim = dim; d.order = order; d.mesh_order = mesh_order; d.exec_mode = exec_mode;
+   d.bounds_type = bounds_type; d.device = device; d.ne = no; d.ne_ghost = ng;
+   d.nodes = nodes; d.vel_nodes = vel_nodes.data();
+   d.nbr_dof = nbr.data(); d.lat = lat.data(); d.n_ent = n_ent; d.nbr_elem = nbe.data();
+   d.inflow = infl.data();
+   Check(rmh_ctx_create(&d, &ctx));
+   Check(rmh_dplan_create(halo, rank, world, dim, order, nbr.data(), &dplan));
+   Check(rmh_dist_create(ctx, dplan, rank, world, n_interior, &dist));
+   {
+      std::string blob((size_t)rmh_dist_blob_bytes(dist), '\0');
+      Check(rmh_dist_export(dist, &blob[0]));
+      const std::vector<std::string> all = comm->AllGather(blob);
+      std::vector<const void *> ptrs(world);
+      std::vector<int64_t> sizes(world);
+      for (int r = 0; r < world; r++) { ptrs[r] = all[r].data(); sizes[r] = (int64_t)all[r].size(); }
+      Check(rmh_dist_connect(dist, world, ptrs.data(), sizes.data()));
+   }
+   if (dt < 0.0)                                                         // :538-553 (MPI_MIN at :551)
+   {
+      Check(rmh_cfl_dt(mesh, problem, bb_min.data(), bb_max.data(), &dt));
+      dt = Reduce(dt, 1);
+   }
+   dt_cfl = dt;
+   t_final = t_final_;
+   global_vsize = (int64_t)std::llround(Reduce((double)(no * nd), 0));
+   u0.resize((size_t)no * nd);
+   Check(rmh_u0(problem, dim, no * nd, xdof.data(), bb_min.data(), bb_max.data(), u0.data()));
+   xlat = xdof;
+   bdr_dofs = bd;
+   nbr_elem.assign(nbe.begin(), nbe.begin() + (size_t)no * nf);
+}
+
+double ParFiniteElementSpace::Reduce(double v, int op) const
+{
+   if (!dist) { return v; }
+   Check(rmh_dist_allreduce(dist, op, &v, 1, nullptr));
+   return v;
+}
+
 ParFiniteElementSpace::~ParFiniteElementSpace()
 {
+   if (dist)
+   {
+      // no rank may tear its window down while a peer can still write into it
+      Check(rmh_sync(ctx));
+      comm->Barrier();
+      rmh_dist_destroy(dist); dist = nullptr;
+   }
    if (ctx) { rmh_ctx_destroy(ctx); ctx = nullptr; }
+   if (dplan) { rmh_dplan_free(dplan); }
+   if (halo) { rmh_halo_free(halo); }
+   if (local_mesh) { rmh_mesh_free(local_mesh); }
+   if (global_mesh && mesh && mesh != global_mesh) { rmh_mesh_free(mesh); mesh = global_mesh; }
 }
 int64_t ParFiniteElementSpace::GetNE() const { return rmh_mesh_ne(mesh); }
 int64_t ParFiniteElementSpace::GetVSize() const { return rmh_ctx_ndofs(ctx); }
@@ -530,6 +706,12 @@ void ODESolver::Step(Vector &x, double &t, double &dt)
       t += dt;
       return;
    }
+   if (f->Space().dist)
+   {
+      // decomposed mesh: fused stage path with the halo exchange behind the C ABI (remhos.cpp:1813)
+      Check(rmh_dist_rk_step(f->Space().dist, type, f->LOType(), &t, dt, x.ReadWrite(), nullptr));
+      return;
+   }
    const int rc = rmh_ode_step(f->Space().ctx, type, f->HOType(), f->LOType(), f->FCTType(), &t, dt,
                                x.ReadWrite(), nullptr);
    Check(rc);
@@ -543,6 +725,7 @@ struct Opt
    std::string mesh_file = "default", device = "cpu";
    int dim = 3, epm = 1, problem = 0, rs = 2, rp = 0, order = 3, mesh_order = 2, ode = 3, ho = 3,
        lo = 0, fct = 0, mono = 0, bt = 0, si = 0, dtc = 0, max_steps = -1, vis_steps = 100, pool = 4;
+   int gpus = 1;          // -gpus N: one process per GPU, started by main() (the reference: mpirun -np N)
    bool pa = false, full = false, gam = false, vis = true, save = false, visit = false, vb = false,
         ps = false;
    double t_final = 4.0, dt = 0.005;
@@ -555,7 +738,8 @@ void usage(std::ostream &os)
          "  -s <ode: 1,2,3,4,6,11,12,13,14,16>  -ho <0|1|2|3>  -lo <0..5>  -fct <0|1|2>  -mono <0|1|2>\n"
          "  -bt <0|1>  -pa/-no-pa  -full/-no-full  -d <device>  -gam/-no-gam  -si <0>  -tf <t>\n"
          "  -dtc <0>  -dt <dt>  -ms <steps>  -vis/-no-vis  -save/-no-save  -visit/-no-visit\n"
-         "  -vb/-no-vb  -ps/-no-ps  -vs <steps>  -pool <GB>\n";
+         "  -vb/-no-vb  -ps/-no-ps  -vs <steps>  -pool <GB>\n"
+         "  -gpus <N>  decompose the mesh over N GPUs of this node (one process per GPU; -ho 3 -lo 5 -fct 2)\n";
 }
 
 // returns false on a bad command line (remhos.cpp:335-339 prints the usage and returns 1)
@@ -571,6 +755,7 @@ bool parse(int argc, char *argv[], Opt &o)
       {"-bt", &o.bt}, {"--bounds-type", &o.bt}, {"-si", &o.si}, {"--smth_ind", &o.si},
       {"-dtc", &o.dtc}, {"--dt-control", &o.dtc}, {"-ms", &o.max_steps}, {"--max-steps", &o.max_steps},
       {"-vs", &o.vis_steps}, {"--visualization-steps", &o.vis_steps}, {"-pool", &o.pool},
+      {"-gpus", &o.gpus}, {"--num-gpus", &o.gpus},
       {"--dev-pool-size", &o.pool}};
    std::map<std::string, double *> dbls = {{"-tf", &o.t_final}, {"--t-final", &o.t_final},
                                            {"-dt", &o.dt}, {"--time-step", &o.dt}};
@@ -624,7 +809,17 @@ bool parse(int argc, char *argv[], Opt &o)
 int remhos(int argc, char *argv[], double &final_mass_u)
 {
    Opt o;
+   Communicator comm;                                                    // remhos.cpp:212-214 (Mpi::Init)
+   // like the reference, only the root rank talks (remhos.cpp:335-339 and every "if (myid == 0)")
+   std::ostringstream null_out;
+   std::streambuf *cout_buf = comm.Root() ? nullptr : std::cout.rdbuf(null_out.rdbuf());
+   struct Restore { std::streambuf *b; ~Restore() { if (b) { std::cout.rdbuf(b); } } } restore{cout_buf};
    if (!parse(argc, argv, o)) { usage(std::cout); return 1; }           // remhos.cpp:335-339
+   if (comm.world > 1)
+   {
+      Verify(o.ho == 3 && o.lo == 5 && o.fct == 2 && o.mono == 0 && o.ode >= 1 && o.ode <= 3 && !o.dtc && !o.vb,
+             "decomposed runs (WORLD_SIZE > 1) cover -ho 3 -lo 5 -fct 2 -s 1/2/3 (the fused stage path)");
+   }
    // ---- combinations the reference rejects (Appendix A of SURVEY.md) or this build lacks
    if (!ODESolver::Known(o.ode))
    {
@@ -657,24 +852,35 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    rmh_mesh *mesh = nullptr;
    if (o.mesh_file == "default")
    {
+      // PartitionMPI(dim, world, elem_per_mpi, ..., rp_levels) (remhos.cpp:451-455): a Cartesian mesh of
+      // the unit box with world * epm elements AFTER the -rp refinements, so that every rank ends up
+      // with exactly elem_per_mpi elements (verified at remhos.cpp:466-471); -rs applies to file meshes only
       Verify(o.dim == 2 || o.dim == 3, "-dim must be 2 or 3");
+      Verify(o.epm >= 1 && o.rp >= 0, "Mesh generation error.");
+      const long total = (long)comm.world * o.epm, per = 1L << (o.dim * o.rp);
+      Verify(total % per == 0, "Mesh generation error.");
       int n[3] = {1, 1, 1};
-      int left = o.epm;                       // one rank: epm elements, as cubic as possible
+      long left = total / per;                 // coarse elements, as cubic as possible
       for (int a = 0; a < o.dim; a++)
       {
-         int k = (int)std::lround(std::pow((double)left, 1.0 / (o.dim - a)));
+         long k = std::lround(std::pow((double)left, 1.0 / (o.dim - a)));
          while (k > 1 && left % k) { k--; }
-         n[a] = std::max(k, 1); left /= n[a];
+         n[a] = (int)std::max(k, 1L); left /= n[a];
       }
       const double org[3] = {0, 0, 0}, sz[3] = {1, 1, 1};
       Check(rmh_mesh_cartesian(o.dim, n, org, sz, 0, &mesh));
+      Check(rmh_mesh_refine(mesh, o.rp));
+      Verify((long)rmh_mesh_ne(mesh) == total, "Mesh generation error.");
    }
-   else { Check(rmh_mesh_load(o.mesh_file.c_str(), &mesh)); }
-   Check(rmh_mesh_refine(mesh, o.rs + o.rp));
+   else
+   {
+      Check(rmh_mesh_load(o.mesh_file.c_str(), &mesh));
+      Check(rmh_mesh_refine(mesh, o.rs + o.rp));
+   }
    double dt = o.dt, t_final = o.t_final;
    int rc = 0;
    {
-      ParFiniteElementSpace pfes(mesh, o.problem, o.order, o.mesh_order, o.bt, dt, t_final, 0);
+      ParFiniteElementSpace pfes(mesh, o.problem, o.order, o.mesh_order, o.bt, dt, t_final, comm.local_rank, &comm);
       std::cout << "Number of unknowns: " << pfes.GlobalVSize() << std::endl;   // remhos.cpp:623
       Vector u(pfes), lumpedM(pfes);
       u.SetFromHost(pfes.u0);
@@ -707,6 +913,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       Check(rmh_reduce(pfes.ctx, 0, u.Read(), lumpedM.Read(), &mass0_u, nullptr));   // :1073-1076
       Check(rmh_reduce(pfes.ctx, 1, u.Read(), nullptr, &u_min, nullptr));
       Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &u_max, nullptr));
+      mass0_u = pfes.Reduce(mass0_u, 0); u_min = pfes.Reduce(u_min, 1); u_max = pfes.Reduce(u_max, 2);   // MPI_Allreduce
       ODESolver ode_solver(o.ode);
       ode_solver.Init(adv);
       // the time loop below only reads the state between steps: the element min/max the last RK
@@ -775,6 +982,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       double mass_u = 0.0;
       Check(rmh_reduce(pfes.ctx, 0, u.Read(), lumpedM.Read(), &mass_u, nullptr));
       Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &u_max, nullptr));
+      mass_u = pfes.Reduce(mass_u, 0); u_max = pfes.Reduce(u_max, 2);     // remhos.cpp:1403-1415
       final_mass_u = mass_u;
       std::cout << std::setprecision(10) << "Final mass u:  " << mass_u << std::endl
                 << "Max value u:   " << u_max << std::endl << std::setprecision(6)
@@ -794,6 +1002,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       delete mono_solver; delete smth_indicator; delete fct_solver; delete lo_solver; delete ho_solver;   // remhos.cpp:1484-1489
    }
    rmh_mesh_free(mesh);
+   comm.Finalize();
    return rc;
 }
 

@@ -34,6 +34,24 @@ void Check(int status);   // nonzero C-ABI status -> Abort(rmh_last_error())
 
 class ParFiniteElementSpace;
 
+// What MPI_COMM_WORLD is to the reference (remhos.cpp:212-214): rank / size of a run with one process
+// per GPU of one node, and a byte all-gather for the set-up blobs.  Ranks come from the environment
+// (RANK, WORLD_SIZE, LOCAL_RANK: torchrun --no-python, or the driver's own -gpus N launcher); the
+// all-gather goes through files in a shared directory (RMH_RDZV_DIR, default under /dev/shm).  The
+// data path never goes through here: halo puts and reductions live behind the C ABI (rmh_dist_*).
+class Communicator
+{
+   int seq = 0;
+   std::string dir;
+public:
+   int rank = 0, world = 1, local_rank = 0;
+   Communicator();
+   bool Root() const { return rank == 0; }
+   std::vector<std::string> AllGather(const std::string &mine);
+   void Barrier() { AllGather("b"); }
+   void Finalize();
+};
+
 // FP64 vector living in device memory of the space's context
 class Vector
 {
@@ -74,11 +92,23 @@ public:
    double dt_cfl = 0.0;
    double t_final = 0.0;
    bool subcells_ready = false;
+   // decomposed runs (comm.world > 1): `mesh` is this rank's owned part, the members below hold the rest
+   Communicator *comm = nullptr;
+   rmh_mesh *global_mesh = nullptr, *local_mesh = nullptr;   // local = owned + ghost ring
+   rmh_halo *halo = nullptr;
+   rmh_dplan *dplan = nullptr;
+   rmh_dist *dist = nullptr;
+   int64_t global_vsize = 0;
    ParFiniteElementSpace(rmh_mesh *m, int problem, int order, int mesh_order, int bounds_type,
-                         double &dt, double &t_final, int device);
+                         double &dt, double &t_final, int device, Communicator *comm = nullptr);
    ~ParFiniteElementSpace();
    int64_t GetNE() const;
-   int64_t GlobalVSize() const { return GetVSize(); }
+   int64_t GlobalVSize() const { return dist ? global_vsize : GetVSize(); }
+   // MPI_Allreduce of one scalar (op 0 sum, 1 min, 2 max); identity on one rank
+   double Reduce(double v, int op) const;
+private:
+   void SetupDistributed(double &dt, double &t_final, int device);
+public:
    int64_t GetVSize() const;
    int GetNDofs() const;
 };

@@ -249,3 +249,39 @@ def test_new_flag_combinations_validated():
                        (['-ho', '3', '-lo', '5', '-fct', '2', '-dtc', '2'], 'time step control must be')):
         rc, _, err = run_cli('-m', 'x', *flags)
         assert rc == 134 and msg in err, (flags, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('order,bt,dt', [(3, 0, '0.004'), (4, 1, '-1'), (2, 0, '-1')])
+def test_cli_decomposed_matches_single_gpu(order, bt, dt):
+    """`remhos -gpus 2` (one process per GPU, started by the driver itself as mpirun -np 2 starts the
+    reference; halo puts, in-kernel halo wait and ncclAllReduce behind the C ABI) prints the same
+    unknown count, final mass and maximum as the single-GPU run; with -dt -1 the CFL time step is the
+    MPI_MIN over the ranks (remhos.cpp:551)."""
+    torch = pytest.importorskip('torch')
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    args = ['-m', mesh('periodic-cube.mesh'), '-p', 0, '-rs', 2, '-o', order, '-dt', dt, '-tf', 0.05, '-ho', 3,
+            '-lo', 5, '-fct', 2, '-pa', '-bt', bt, '-no-vis']
+    rc1, out1, err1 = run_cli(*args)
+    assert rc1 == 0, err1
+    rc2, out2, err2 = run_cli(*args, '-gpus', 2)
+    assert rc2 == 0, out2[-2000:] + err2[-2000:]
+    a, b = parse(out1), parse(out2)
+    assert a['n'] == b['n']
+    assert abs(a['mass'] - b['mass']) <= 1e-10 * abs(a['mass'])     # the 10 printed digits
+    assert abs(a['umax'] - b['umax']) <= 1e-10 * abs(a['umax'])
+    assert out2.count('Final mass u:') == 1                          # only the root rank talks
+
+
+@pytest.mark.gpu
+def test_cli_default_mesh_has_epm_elements():
+    """-m default: PartitionMPI builds world * elem_per_mpi elements AFTER the -rp refinements
+    (verified by the reference at remhos.cpp:466-471); -rs applies to file meshes only (:448-449)."""
+    for extra in ([], ['-rs', 3]):
+        rc, out, err = run_cli('-m', 'default', '-dim', 3, '-epm', 64, '-rp', 1, '-o', 2, '-p', 0, '-dt', 0.002,
+                               '-tf', 0.004, '-ho', 3, '-lo', 5, '-fct', 2, '-no-vis', *extra)
+        assert rc == 0, err
+        assert parse(out)['n'] == 64 * 27
+    rc, _, err = run_cli('-m', 'default', '-dim', 3, '-epm', 12, '-rp', 1, '-o', 2, '-ho', 3, '-lo', 5, '-fct', 2)
+    assert rc == 134 and 'Mesh generation error' in err     # 12 is not a multiple of 8
