@@ -279,6 +279,45 @@ int rmh_fct_flux_based(rmh_ctx *ctx, double dt, const double *u_dev, const doubl
                        const double *xi_min_dev, const double *xi_max_dev, double *du_dev,
                        void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Product-field remap (-ps; remap mode): the state is the block (u, us) of 2 N doubles
+ * (BlockVector S, remhos.cpp:594-598,886-903).  Flags are bytes (Array<bool>).
+ * ---------------------------------------------------------------------------------------- */
+/* on != 0: rmh_mult_unlimited / rmh_limit_mult / rmh_mult / rmh_ode_step take and return (u, us)
+ * blocks: MultUnlimited remaps us with the same HO operator (remhos.cpp:1714-1738), LimitMult runs its
+ * second pass (:1848-1915).  "Products are processed only in remap mode." (:1850) */
+int rmh_product_enable(rmh_ctx *ctx, int on);
+/* RKIDPSolver::UseMask (remhos_solvers.hpp; the driver switches the masks off, remhos.cpp:502-507):
+ * -s 12/13/14/16 with ComputeMask / UpdateMask / AddMasked (remhos_solvers.cpp:97-147,171-249) */
+int rmh_idp_use_mask(rmh_ctx *ctx, int on);
+/* AdvectionOperator::ComputeMask (remhos.cpp:1741-1796): mask_dev [state length] */
+int rmh_compute_mask(rmh_ctx *ctx, const double *state_dev, uint8_t *mask_dev, void *stream);
+/* ComputeBoolIndicators (remhos_sync.cpp:24-47): el_dev [ne], dof_dev [N]; EMPTY_ZONE_TOL = 1e-12 */
+int rmh_prod_bool_indicators(rmh_ctx *ctx, const double *u_dev, uint8_t *el_dev, uint8_t *dof_dev, void *stream);
+/* ComputeRatio (remhos_sync.cpp:50-94): s = us / u on active dofs, their average elsewhere in an
+ * active element, 0 in empty elements */
+int rmh_prod_compute_ratio(rmh_ctx *ctx, const double *us_dev, const double *u_dev, double *s_dev,
+                           uint8_t *el_dev, uint8_t *dof_dev, void *stream);
+/* DofInfo::ComputeElementsMinMax with active_el / active_dof (remhos_tools.cpp:497-523); either mask
+ * may be NULL; inactive elements get (inf, -inf) and so drop out of rmh_bounds */
+int rmh_elem_min_max_masked(rmh_ctx *ctx, const double *u_dev, const uint8_t *el_dev, const uint8_t *dof_dev,
+                            double *xe_min_dev, double *xe_max_dev, void *stream);
+/* FCTSolver::CalcCompatibleLOProduct (remhos_fct.cpp:26-118); s_min / s_max adjusted in place */
+int rmh_prod_compatible_lo(rmh_ctx *ctx, double dt, const double *us_dev, const double *m_dev,
+                           const double *d_us_ho_dev, double *s_min_dev, double *s_max_dev,
+                           const double *u_new_dev, const uint8_t *el_dev, const uint8_t *dof_dev,
+                           double *d_us_lo_new_dev, void *stream);
+/* ZeroOutEmptyDofs (remhos_sync.cpp:96-114) */
+int rmh_prod_zero_empty(rmh_ctx *ctx, const uint8_t *el_dev, const uint8_t *dof_dev, double *d_us_dev, void *stream);
+/* FCTSolver::CalcFCTProduct of FluxBasedFCT (fct_type 1, remhos_fct.cpp:183-294), ClipScaleSolver (2,
+ * :543-563), ElementFCTProjection (4, :735-758): compatible LO product, ScaleProductBounds (:120-153),
+ * the solver's limiter on us, empty dofs zeroed.  d_us_lo_dev is read by fct_type 1 only
+ * (NeedsLOProductInput, remhos.cpp:1865-1869). */
+int rmh_fct_product(rmh_ctx *ctx, int fct_type, double dt, const double *us_dev, const double *m_dev,
+                    const double *d_us_ho_dev, const double *d_us_lo_dev, double *s_min_dev, double *s_max_dev,
+                    const double *u_new_dev, const uint8_t *el_dev, const uint8_t *dof_dev, double *d_us_dev,
+                    void *stream);
+
 /* LimitedTimeDependentOperator::Mult (remhos_solvers.hpp:46-50) for any supported combination of
  * -ho {0,1,3} -lo {0,1,2,3,4,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
  * remhos.cpp:1598-1677): k = F(u; t, dt).  Orchestrates the separate kernels exactly as

@@ -295,9 +295,19 @@ class Run:
         # ZeroOutEmptyDofs (remhos_sync.cpp:96-114)
         return np.where(~el_new[:, None] & ~dof_new, 0.0, d_us)
 
-    def idp_step(self, u, t, dt):
-        """ForwardEulerIDPSolver / RKIDPSolver::Step with masks off (remhos_solvers.cpp:29-38,
-        40-95, 171-249; tables :252-279; remhos.cpp:502-507)."""
+    @staticmethod
+    def compute_mask(x):
+        """AdvectionOperator::ComputeMask (remhos.cpp:1741-1796): only a product state (u, us) is
+        masked; an element is on iff all of its u dofs are active; the same mask for both fields"""
+        if x.ndim != 3:
+            return np.ones(x.shape, dtype=bool)
+        full = (x[0] > 1e-12).all(axis=1)
+        return np.broadcast_to(full[None, :, None], x.shape).copy()
+
+    def idp_step(self, u, t, dt, use_mask=False):
+        """ForwardEulerIDPSolver / RKIDPSolver::Step (remhos_solvers.cpp:29-38, 40-95, 171-249; tables
+        :252-279).  The driver switches the masks off (remhos.cpp:502-507); use_mask=True restates
+        the masked variant (ComputeMask / UpdateMask / AddMasked, remhos_solvers.cpp:97-147)."""
         s = self.opt.ode_solver
         if s == 11:
             k = self.limit_mult(u, self.mult_unlimited(u, t, dt), dt)
@@ -338,17 +348,29 @@ class Run:
         tcur = t
         ks[0] = self.limit_mult(x, self.mult_unlimited(x, tcur, c[0] * dt), c[0] * dt)
         c_next = c[1] if ns > 2 else 1.0
+        mask = None
         if c_next > c[0]:
             x = x + c[0] * dt * ks[0]
+            if use_mask:
+                mask = self.compute_mask(x)
             tcur = t + c[0] * dt
             c_o = c[0]
+        elif use_mask:
+            mask = self.compute_mask(x + c[0] * dt * ks[0])
         for i in range(1, ns):
             c_n = c[i] if i < ns - 1 else 1.0
             dct = (c_n - c_o) * dt
             di = i * (i + 1) // 2
-            k = self.mult_unlimited(x, tcur, dct) * d[di + i]
-            for j in range(i):
-                k = k + d[di + j] * ks[j]
+            k = self.mult_unlimited(x, tcur, dct)
+            if use_mask:
+                mask = mask & self.compute_mask(x + dct * k if dct != 0.0 else x)       # UpdateMask
+                k = k + np.where(mask, (d[di + i] - 1.0) * k, 0.0)                       # AddMasked
+                for j in range(i):
+                    k = k + np.where(mask, d[di + j] * ks[j], 0.0)
+            else:
+                k = k * d[di + i]
+                for j in range(i):
+                    k = k + d[di + j] * ks[j]
             ks[i] = self.limit_mult(x, k, dct)
             c_next = c[i + 1] if i < ns - 2 else 1.0
             if i == ns - 1 or c_next > c_n:

@@ -455,6 +455,46 @@ class Context:
                                        _dp(du_lo), _dp(xi_min), _dp(xi_max), _dp(du),
                                        C.c_void_p(s)))
 
+    # ---- product-field remap (-ps): flags are uint8 device arrays
+    def product_enable(self, on=True):
+        check(lib().rmh_product_enable(self.h, int(bool(on))))
+
+    def idp_use_mask(self, on=True):
+        check(lib().rmh_idp_use_mask(self.h, int(bool(on))))
+
+    def compute_mask(self, state, mask, s=0):
+        check(lib().rmh_compute_mask(self.h, _dp(state), _dp(mask), C.c_void_p(s)))
+
+    def prod_bool_indicators(self, u, el, dof, s=0):
+        check(lib().rmh_prod_bool_indicators(self.h, _dp(u), _dp(el), _dp(dof), C.c_void_p(s)))
+
+    def prod_compute_ratio(self, us, u, sr, el, dof, s=0):
+        check(lib().rmh_prod_compute_ratio(self.h, _dp(us), _dp(u), _dp(sr), _dp(el), _dp(dof), C.c_void_p(s)))
+
+    def elem_min_max_masked(self, u, el, dof, xe_min, xe_max, s=0):
+        check(lib().rmh_elem_min_max_masked(self.h, _dp(u), _dp(el), _dp(dof), _dp(xe_min), _dp(xe_max),
+                                            C.c_void_p(s)))
+
+    def prod_compatible_lo(self, dt, us, m, d_us_ho, s_min, s_max, u_new, el, dof, d_lo, s=0):
+        check(lib().rmh_prod_compatible_lo(self.h, C.c_double(dt), _dp(us), _dp(m), _dp(d_us_ho), _dp(s_min),
+                                           _dp(s_max), _dp(u_new), _dp(el), _dp(dof), _dp(d_lo), C.c_void_p(s)))
+
+    def prod_zero_empty(self, el, dof, d_us, s=0):
+        check(lib().rmh_prod_zero_empty(self.h, _dp(el), _dp(dof), _dp(d_us), C.c_void_p(s)))
+
+    def fct_product(self, fct_type, dt, us, m, d_us_ho, d_us_lo, s_min, s_max, u_new, el, dof, d_us, s=0):
+        check(lib().rmh_fct_product(self.h, int(fct_type), C.c_double(dt), _dp(us), _dp(m), _dp(d_us_ho),
+                                    _dp(d_us_lo), _dp(s_min), _dp(s_max), _dp(u_new), _dp(el), _dp(dof),
+                                    _dp(d_us), C.c_void_p(s)))
+
+    def limit_mult(self, lo_type, fct_type, dt, u, k, s=0):
+        check(lib().rmh_limit_mult(self.h, int(lo_type), int(fct_type), C.c_double(dt), _dp(u), _dp(k),
+                                   C.c_void_p(s)))
+
+    def mult_unlimited(self, ho_type, lo_type, fct_type, t, dt, u, k, s=0):
+        check(lib().rmh_mult_unlimited(self.h, int(ho_type), int(lo_type), int(fct_type), C.c_double(t),
+                                       C.c_double(dt), _dp(u), _dp(k), C.c_void_p(s)))
+
     def mult(self, ho_type, lo_type, fct_type, t, dt, u, k, s=0):
         check(lib().rmh_mult(self.h, int(ho_type), int(lo_type), int(fct_type), C.c_double(t),
                              C.c_double(dt), _dp(u), _dp(k), C.c_void_p(s)))

@@ -8,6 +8,7 @@
 #include "stage3w.cuh"
 #include "stage3c.cuh"
 #include "fa.cuh"
+#include "product.cuh"
 #include "geom3.cuh"
 
 #include <algorithm>
@@ -115,6 +116,10 @@ struct rmh_ctx
    // subcell residual distribution (-lo 4): lattice points, velocity samples, weights
    double *sub_x = nullptr, *sub_v = nullptr, *sub_w = nullptr;
    bool sub_on = false;
+   // product remap (-ps): the state of rmh_mult* / rmh_limit_mult / rmh_ode_step is the block (u, us)
+   bool product = false, idp_mask = false;
+   double *pw[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   uint8_t *pf_el[2] = {nullptr, nullptr}, *pf_dof[2] = {nullptr, nullptr}, *pmask = nullptr;
    // work vectors of the unfused solver path (allocated on first use)
    double *wk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    double *rk[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -2162,10 +2167,11 @@ static FaArgs fa_args(rmh_ctx *c)
    return A;
 }
 
+static int64_t state_len(const rmh_ctx *c) { return c->product ? 2 * c->N : c->N; }
 static int work_vec(rmh_ctx *c, double **slot)
 {
    if (*slot) { return 0; }
-   return dev_alloc(c, slot, (size_t)c->N);
+   return dev_alloc(c, slot, (size_t)state_len(c));
 }
 
 extern "C" int rmh_fa_setup(rmh_ctx *c, void *stream)
@@ -2676,8 +2682,8 @@ static int check_combo(int ho_type, int lo_type, int fct_type)
 
 // AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739): remap re-assembly at time t, then the
 // HO rate when an FCT solver will limit it later, else the LO or HO rate.
-extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t,
-                                  double dt, const double *u, double *k, void *stream)
+static int mult_unlimited_1(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t,
+                            double dt, const double *u, double *k, void *stream)
 {
    if (c->mono_type)      // the monolithic solver takes precedence (remhos.cpp:1687)
    {
@@ -2705,8 +2711,8 @@ extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_
 
 // AdvectionOperator::LimitMult (remhos.cpp:1798-1916): k holds the (possibly combined) HO rate
 // on entry and the limited rate on exit; a no-op without an FCT solver.
-extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u,
-                              double *k, void *stream)
+static int limit_mult_1(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u,
+                        double *k, void *stream)
 {
    if (!fct_type || c->mono_type) { return 0; }            // remhos.cpp:1803: no FCT solver, nothing to limit
    if (check_combo(3, lo_type, fct_type)) { return 1; }
@@ -2720,6 +2726,7 @@ extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, 
    else if (lo_type == 2) { if (rmh_lo_discrete_upwind_prec(c, u, du_lo, stream)) { return 1; } }
    else if (lo_type == 4) { if (rmh_lo_res_dist_subcell(c, u, du_lo, stream)) { return 1; } }
    else { if (rmh_lo_res_dist(c, u, du_lo, stream)) { return 1; } }
+   c->xe_ptr = nullptr;       // the context's element min/max change owner (rmh_ctx_trust_state)
    if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
    if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
    int rc;
@@ -2737,13 +2744,211 @@ extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, 
    return 0;
 }
 
+// ---------------------------------------------------------------- product-field remap (-ps)
+static int prod_buffers(rmh_ctx *c)
+{
+   for (int i = 0; i < 10; i++) { if (!c->pw[i]) { if (dev_alloc(c, &c->pw[i], (size_t)c->N)) { return 1; } } }
+   for (int i = 0; i < 2; i++)
+   {
+      if (!c->pf_el[i]) { if (dev_alloc(c, &c->pf_el[i], (size_t)c->ne)) { return 1; } }
+      if (!c->pf_dof[i]) { if (dev_alloc(c, &c->pf_dof[i], (size_t)c->N)) { return 1; } }
+   }
+   if (!c->pmask) { if (dev_alloc(c, &c->pmask, (size_t)2 * c->N)) { return 1; } }
+   return 0;
+}
+
+static unsigned warp_grid(int64_t ne, int bs) { return (unsigned)((ne * 32 + bs - 1) / bs); }
+
+// on != 0: the state vectors of rmh_mult_unlimited / rmh_limit_mult / rmh_mult / rmh_ode_step are the
+// block (u, us) of 2 N doubles (BlockVector S, remhos.cpp:594-598,886-903); remap mode only
+extern "C" int rmh_product_enable(rmh_ctx *c, int on)
+{
+   if (on && c->exec_mode != 1) { set_error("Products are processed only in remap mode."); return 1; }   // remhos.cpp:1850
+   if ((on != 0) != c->product)
+   {
+      // work vectors are sized by the state: start over
+      for (int i = 0; i < 8; i++) { c->wk[i] = nullptr; }
+      for (int i = 0; i < 9; i++) { c->rk[i] = nullptr; }
+   }
+   c->product = (on != 0);
+   c->xe_ptr = nullptr;
+   return on ? prod_buffers(c) : 0;
+}
+
+// use_masks of RKIDPSolver (remhos_solvers.hpp; the driver switches them off, remhos.cpp:502-507)
+extern "C" int rmh_idp_use_mask(rmh_ctx *c, int on)
+{
+   c->idp_mask = (on != 0);
+   return 0;
+}
+
+extern "C" int rmh_prod_bool_indicators(rmh_ctx *c, const double *u, uint8_t *el, uint8_t *dof, void *stream)
+{
+   const int bs = 128;
+   k_bool_indicators<<<warp_grid(c->ne, bs), bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, u, el, dof);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_prod_compute_ratio(rmh_ctx *c, const double *us, const double *u, double *s, uint8_t *el,
+                                      uint8_t *dof, void *stream)
+{
+   const int bs = 128;
+   k_prod_ratio<<<warp_grid(c->ne, bs), bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, us, u, s, el, dof, nullptr,
+                                                                      nullptr);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_elem_min_max_masked(rmh_ctx *c, const double *u, const uint8_t *el, const uint8_t *dof,
+                                       double *xe_min, double *xe_max, void *stream)
+{
+   if (xe_min == c->xe_min || xe_max == c->xe_max) { c->xe_ptr = nullptr; }
+   const int bs = 128;
+   k_elem_min_max_masked<<<warp_grid(c->ne, bs), bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, u, el, dof, xe_min,
+                                                                               xe_max);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_prod_compatible_lo(rmh_ctx *c, double dt, const double *us, const double *m,
+                                      const double *d_us_ho, double *s_min, double *s_max, const double *u_new,
+                                      const uint8_t *el, const uint8_t *dof, double *d_us_lo_new, void *stream)
+{
+   const int bs = 128;
+   k_prod_compatible_lo<<<warp_grid(c->ne, bs), bs, 0, (cudaStream_t)stream>>>(
+      c->ne, c->ND, dt, us, m, d_us_ho, s_min, s_max, u_new, el, dof, d_us_lo_new, nullptr, nullptr);
+   LAUNCH_OK();
+   return 0;
+}
+
+extern "C" int rmh_prod_zero_empty(rmh_ctx *c, const uint8_t *el, const uint8_t *dof, double *d_us, void *stream)
+{
+   const int bs = 256;
+   k_zero_empty<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(c->N, c->ND, el, dof, d_us);
+   LAUNCH_OK();
+   return 0;
+}
+
+// FCTSolver::CalcFCTProduct of FluxBasedFCT (fct_type 1, remhos_fct.cpp:183-294), ClipScaleSolver (2,
+// :543-563) and ElementFCTProjection (4, :735-758): compatible LO product, scaled bounds, the solver's
+// own limiter on us, empty dofs zeroed.  s_min / s_max are adjusted in place as in the reference;
+// d_us_lo is read by the flux-based solver only (NeedsLOProductInput).
+extern "C" int rmh_fct_product(rmh_ctx *c, int fct_type, double dt, const double *us, const double *m,
+                               const double *d_us_ho, const double *d_us_lo, double *s_min, double *s_max,
+                               const double *u_new, const uint8_t *el, const uint8_t *dof, double *d_us,
+                               void *stream)
+{
+   if (fct_type != 1 && fct_type != 2 && fct_type != 4) { set_error("rmh_fct_product: FCT solver must be 1, 2 or 4"); return 1; }
+   if (prod_buffers(c)) { return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   double *d_lo_c = c->pw[5], *us_min = c->pw[6], *us_max = c->pw[7];
+   const int bs = 128;
+   k_prod_compatible_lo<<<warp_grid(c->ne, bs), bs, 0, s>>>(c->ne, c->ND, dt, us, m, d_us_ho, s_min, s_max, u_new,
+                                                            el, dof, d_lo_c, us_min, us_max);
+   LAUNCH_OK();
+   if (fct_type == 2) { if (rmh_fct_clip_scale(c, dt, us, m, d_us_ho, d_lo_c, us_min, us_max, d_us, stream)) { return 1; } }
+   else if (fct_type == 4) { if (rmh_fct_project(c, dt, us, d_us_ho, d_lo_c, us_min, us_max, d_us, stream)) { return 1; } }
+   else
+   {
+      if (!c->fa_on) { set_error("rmh_fct_product: call rmh_fa_setup first (assembled K_HO, M)"); return 1; }
+      if (!d_us_lo) { set_error("rmh_fct_product: the flux-based solver needs the LO product rate"); return 1; }
+      double *fel = c->pw[8], *beta = c->pw[9];
+      k_prod_flux_el<<<warp_grid(c->ne, bs), bs, 0, s>>>(c->ne, c->ND, dt, m, d_us_lo, d_lo_c, u_new, el, fel, beta);
+      LAUNCH_OK();
+      if (work_vec(c, &c->wk[1]) || work_vec(c, &c->wk[2])) { return 1; }
+      FaArgs A = fa_args(c);
+      A.ml = m; A.pbeta = beta; A.pfel = fel;
+      const int fb = std::min(256, ((c->ND + 31) / 32) * 32);
+      const size_t shb = 2 * c->ND * sizeof(double);
+      k_flux_coeff<<<(unsigned)c->ne, fb, shb, s>>>(A, dt, us, d_us_ho, d_lo_c, us_min, us_max, c->wk[1], c->wk[2]);
+      LAUNCH_OK();
+      k_flux_apply<<<(unsigned)c->ne, fb, shb, s>>>(A, dt, us, d_us_ho, d_lo_c, c->wk[1], c->wk[2], d_us);
+      LAUNCH_OK();
+   }
+   return rmh_prod_zero_empty(c, el, dof, d_us, stream);
+}
+
+static int calc_lo_1(rmh_ctx *c, int lo_type, double dt, const double *u, const double *du_ho, double *du_lo,
+                     void *stream)
+{
+   if (lo_type == 5) { return rmh_lo_mass_avg(c, dt, u, du_ho, du_lo, stream); }
+   if (lo_type == 1) { return rmh_lo_discrete_upwind(c, u, du_lo, stream); }
+   if (lo_type == 2) { return rmh_lo_discrete_upwind_prec(c, u, du_lo, stream); }
+   if (lo_type == 4) { return rmh_lo_res_dist_subcell(c, u, du_lo, stream); }
+   return rmh_lo_res_dist(c, u, du_lo, stream);
+}
+
+// second pass of AdvectionOperator::LimitMult (remhos.cpp:1848-1915): d_us holds the HO product rate
+// on entry and the limited one on exit; d_u is the limited rate of u
+static int limit_product(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u, const double *d_u,
+                         const double *us, double *d_us, void *stream)
+{
+   if (!fct_type) { return 0; }
+   if (c->dt_control) { set_error("Automatic time step is not implemented for product remap."); return 1; }   // :1851
+   if (prod_buffers(c)) { return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   double *d_us_ho = c->pw[0], *d_us_lo = c->pw[1], *smin = c->pw[2], *smax = c->pw[3], *u_new = c->pw[4];
+   CUDA_OK(cudaMemcpyAsync(d_us_ho, d_us, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+   if (fct_type == 1) { if (calc_lo_1(c, lo_type, dt, us, d_us_ho, d_us_lo, stream)) { return 1; } }   // NeedsLOProductInput
+   // s = us_old / u_old on the old active dofs, and its bounds from those dofs only
+   const int bs = 128;
+   c->xe_ptr = nullptr;
+   k_prod_ratio<<<warp_grid(c->ne, bs), bs, 0, s>>>(c->ne, c->ND, us, u, nullptr, c->pf_el[0], c->pf_dof[0], c->xe_min,
+                                                    c->xe_max);
+   LAUNCH_OK();
+   if (rmh_bounds(c, c->xe_min, c->xe_max, smin, smax, stream)) { return 1; }
+   // evolve u, new active dofs
+   k_axpy_out<<<(unsigned)((c->N + 255) / 256), 256, 0, s>>>(c->N, dt, u, d_u, u_new);
+   LAUNCH_OK();
+   if (rmh_prod_bool_indicators(c, u_new, c->pf_el[1], c->pf_dof[1], stream)) { return 1; }
+   return rmh_fct_product(c, fct_type, dt, us, c->ml, d_us_ho, d_us_lo, smin, smax, u_new, c->pf_el[1], c->pf_dof[1],
+                          d_us, stream);
+}
+
+// AdvectionOperator::ComputeMask (remhos.cpp:1741-1796) for the product state (u, us) [2 N bytes]
+extern "C" int rmh_compute_mask(rmh_ctx *c, const double *state, uint8_t *mask, void *stream)
+{
+   const int bs = 128;
+   if (!c->product)
+   {
+      CUDA_OK(cudaMemsetAsync(mask, 1, (size_t)c->N, (cudaStream_t)stream));     // only product fields are masked
+      return 0;
+   }
+   k_compute_mask<<<warp_grid(c->ne, bs), bs, 0, (cudaStream_t)stream>>>(c->ne, c->ND, state, mask, 2);
+   LAUNCH_OK();
+   return 0;
+}
+
+// AdvectionOperator::MultUnlimited (remhos.cpp:1596-1739): see rmh_mult_unlimited in the header.  With a
+// product field the second block is remapped with the same HO operator (:1714-1738).
+extern "C" int rmh_mult_unlimited(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t,
+                                  double dt, const double *u, double *k, void *stream)
+{
+   if (mult_unlimited_1(c, ho_type, lo_type, fct_type, t, dt, u, k, stream)) { return 1; }
+   if (!c->product) { return 0; }
+   if (!fct_type || c->mono_type) { set_error("product remap needs an FCT solver (remhos.cpp:1858)"); return 1; }
+   const double *us = u + c->N;
+   double *kus = k + c->N;
+   return ho_type == 1 ? rmh_ho_neumann(c, us, kus, stream) : rmh_ho_local_inverse(c, us, kus, stream);
+}
+
+// AdvectionOperator::LimitMult (remhos.cpp:1798-1916): see rmh_limit_mult in the header
+extern "C" int rmh_limit_mult(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u,
+                              double *k, void *stream)
+{
+   if (limit_mult_1(c, lo_type, fct_type, dt, u, k, stream)) { return 1; }
+   if (!c->product) { return 0; }
+   return limit_product(c, lo_type, fct_type, dt, u, k, u + c->N, k + c->N, stream);
+}
+
 // LimitedTimeDependentOperator::Mult = MultUnlimited + LimitMult (remhos_solvers.hpp:46-50);
 // the combination -ho 3 -lo 5 -fct 2 goes to the fused stage kernel.
 extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, double t, double dt,
                         const double *u, double *k, void *stream)
 {
    if (c->mono_type) { return rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t, dt, u, k, stream); }
-   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control)
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control && !c->product)
    {
       if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
       if (rmh_set_time(c, t, stream)) { return 1; }
@@ -2753,8 +2958,9 @@ extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, doub
    return rmh_limit_mult(c, lo_type, fct_type, dt, u, k, stream);
 }
 
+// over the state length (N, or 2 N for a product state) unless len is given
 static int lincomb(rmh_ctx *c, int n, const double *coef, const double *const *x, double *out,
-                   cudaStream_t s)
+                   cudaStream_t s, int64_t len = -1)
 {
    LinComb L;
    L.n = 0;
@@ -2764,7 +2970,8 @@ static int lincomb(rmh_ctx *c, int n, const double *coef, const double *const *x
       L.c[L.n] = coef[i]; L.x[L.n] = x[i]; L.n++;
    }
    const int bs = 256;
-   k_lincomb<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->N, L, out);
+   const int64_t n_state = (len >= 0) ? len : state_len(c);
+   k_lincomb<<<(unsigned)((n_state + bs - 1) / bs), bs, 0, s>>>(n_state, L, out);
    LAUNCH_OK();
    return 0;
 }
@@ -2773,7 +2980,7 @@ extern "C" int rmh_lincomb(rmh_ctx *c, int n, const double *coef, const double *
                            double *out_dev, void *stream)
 {
    if (n < 1 || n > 9) { set_error("rmh_lincomb: 1..9 terms"); return 1; }
-   return lincomb(c, n, coef, x_dev, out_dev, (cudaStream_t)stream);
+   return lincomb(c, n, coef, x_dev, out_dev, (cudaStream_t)stream, c->N);
 }
 
 // ODESolver::Step for -s 1/2/3/4/6 (remhos.cpp:488-492) over rmh_mult: explicit RK in Butcher
@@ -2784,10 +2991,11 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
 {
    cudaStream_t s = (cudaStream_t)stream;
    // (with automatic time step control the LO rate must be visible to the dt estimate: unfused path)
-   if (!c->mono_type && !c->dt_control && ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 && ode <= 3)
+   if (!c->mono_type && !c->dt_control && !c->product && ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 &&
+       ode <= 3)
    { return rmh_rk_step(c, ode, lo_type, t, dt, u, stream); }
    const double t0 = *t;
-   const size_t bytes = (size_t)c->N * sizeof(double);
+   const size_t bytes = (size_t)state_len(c) * sizeof(double);
    auto F = [&](const double *x, double tt, double *k) { return rmh_mult(c, ho_type, lo_type, fct_type, tt, dt, x, k, stream); };
    for (int i = 0; i < 2; i++) { if (work_vec(c, &c->rk[i])) { return 1; } }
    double *k0 = c->rk[0], *y = c->rk[1];
@@ -2913,6 +3121,22 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
          }
       }
       for (int i = 0; i < ns; i++) { if (work_vec(c, &c->rk[i])) { return 1; } }
+      // masks (RKIDPSolver::use_masks): only a product state is ever masked (remhos.cpp:1746-1752)
+      const bool masks = c->idp_mask && c->product;
+      const int64_t nstate = state_len(c);
+      uint8_t *mask = c->pmask, *mask_new = nullptr;
+      double *x_new = nullptr;
+      if (masks)
+      {
+         if (work_vec(c, &c->wk[7])) { return 1; }
+         x_new = c->wk[7];
+         if (!c->pf_dof[0]) { if (prod_buffers(c)) { return 1; } }
+         uint8_t *mn = nullptr;
+         if (dev_alloc(c, &mn, (size_t)nstate)) { return 1; }     // (kept until the context goes)
+         mask_new = mn;
+      }
+      const int mbs = 256;
+      const unsigned mgrid = (unsigned)((nstate + mbs - 1) / mbs);
       double c_o = 0.;
       double tcur = t0;
       if (rmh_mult_unlimited(c, ho_type, lo_type, fct_type, tcur, cc[0] * dt, u, c->rk[0], stream)) { return 1; }
@@ -2923,8 +3147,15 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
          {
             const double cf[2] = {1.0, cc[0] * dt}; const double *xs[2] = {u, c->rk[0]};
             if (lincomb(c, 2, cf, xs, u, s)) { return 1; }
+            if (masks) { if (rmh_compute_mask(c, u, mask, stream)) { return 1; } }
             tcur = t0 + cc[0] * dt;
             c_o = cc[0];
+         }
+         else if (masks)
+         {
+            const double cf[2] = {1.0, cc[0] * dt}; const double *xs[2] = {u, c->rk[0]};
+            if (lincomb(c, 2, cf, xs, x_new, s)) { return 1; }
+            if (rmh_compute_mask(c, x_new, mask, stream)) { return 1; }
          }
       }
       const double *d_i = d + 1;
@@ -2933,6 +3164,24 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
          const double c_n = (i < ns - 1) ? cc[i] : 1.;
          const double dc = c_n - c_o, dct = dc * dt;
          if (rmh_mult_unlimited(c, ho_type, lo_type, fct_type, tcur, dct, u, c->rk[i], stream)) { return 1; }
+         if (masks)
+         {
+            // UpdateMask with the HO update, then the masked combination: where the mask is off the
+            // stage stays the plain HO rate (forward Euler), remhos_solvers.cpp:213-231
+            const double *xm = u;
+            if (dct != 0.)
+            {
+               const double cf[2] = {1.0, dct}; const double *xs[2] = {u, c->rk[i]};
+               if (lincomb(c, 2, cf, xs, x_new, s)) { return 1; }
+               xm = x_new;
+            }
+            if (rmh_compute_mask(c, xm, mask_new, stream)) { return 1; }
+            k_mask_and<<<mgrid, mbs, 0, s>>>(nstate, mask, mask_new); LAUNCH_OK();
+            k_add_masked<<<mgrid, mbs, 0, s>>>(nstate, mask, d_i[i] - 1., c->rk[i], c->rk[i]); LAUNCH_OK();
+            for (int j = 0; j < i; j++)
+            { k_add_masked<<<mgrid, mbs, 0, s>>>(nstate, mask, d_i[j], c->rk[j], c->rk[i]); LAUNCH_OK(); }
+         }
+         else
          {
             double cf[9]; const double *xs[9];
             cf[0] = d_i[i]; xs[0] = c->rk[i];

@@ -177,6 +177,9 @@ struct FaArgs
    const int16_t *pat_idx;    // [npat][NFD] natural index, on the neighbour's face, of pat[id][j]
    const uint8_t *pat_face;   // [npat] the neighbour's local face
    const double *K, *KH, *M, *BI, *BL, *ml, *inflow;
+   // product remap (FluxBasedFCT::CalcFCTProduct, remhos_fct.cpp:214-246): element-local fluxes
+   // beta_j fel_i - beta_i fel_j added to the in-element couplings (null: none)
+   const double *pbeta = nullptr, *pfel = nullptr;
 };
 
 // exterior state seen by face DOF (f, a) of element e: the neighbour's value, or `bval` on the
@@ -859,7 +862,14 @@ __device__ __forceinline__ void flux_visit(const FaArgs &A, const double *u, con
       const double kij = KHe[i * ND + j], kji = KHe[j * ND + i];
       const double dij = fmax(fmax(0.0, -kij), -kji);
       // remhos_fct.cpp:313-318 + 334-338: dt d_ij (u_i - u_j) + dt M_ij (du_i - du_j)
-      const double f = dt * dij * (ui - ue[j]) + Me[i * ND + j] * dt * (di - dhe[j]);
+      double f = dt * dij * (ui - ue[j]) + Me[i * ND + j] * dt * (di - dhe[j]);
+      if (A.pbeta)
+      {
+         // explicit roundings: the same two products enter from either end, so f_ji = -f_ij still holds
+         const double t1 = __dmul_rn(A.pbeta[e * ND + j], A.pfel[e * ND + i]);
+         const double t2 = __dmul_rn(A.pbeta[e * ND + i], A.pfel[e * ND + j]);
+         f = __dadd_rn(f, __dsub_rn(t1, t2));
+      }
       visit(e * ND + j, f);
    }
    int l[3];

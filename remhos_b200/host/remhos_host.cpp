@@ -96,15 +96,17 @@ void Communicator::Finalize()
 }
 
 // ------------------------------------------------------------------------------------ Vector
-Vector::Vector(const ParFiniteElementSpace &space) { SetSpace(space); }
+Vector::Vector(const ParFiniteElementSpace &space, int blocks_) { SetSpace(space, blocks_); }
 Vector::Vector(const Vector &o)
 {
-   if (o.fes) { SetSpace(*o.fes); Check(rmh_copy_d2d(fes->ctx, d, o.d, n)); }
+   if (o.fes) { SetSpace(*o.fes, o.blocks); Check(rmh_copy_d2d(fes->ctx, d, o.d, n)); }
 }
+const double *Vector::Block(int b) const { return d + (int64_t)b * (n / blocks); }
+double *Vector::Block(int b) { return d + (int64_t)b * (n / blocks); }
 Vector &Vector::operator=(const Vector &o)
 {
    if (this == &o) { return *this; }
-   if (!fes && o.fes) { SetSpace(*o.fes); }
+   if (!fes && o.fes) { SetSpace(*o.fes, o.blocks); }
    Verify(n == o.n, "Vector::operator=: size mismatch");
    if (n) { Check(rmh_copy_d2d(fes->ctx, d, o.d, n)); }
    return *this;
@@ -118,11 +120,12 @@ Vector &Vector::operator=(double v)
    return *this;
 }
 Vector::~Vector() { if (d && fes && fes->ctx) { rmh_dev_free(fes->ctx, d); } }
-void Vector::SetSpace(const ParFiniteElementSpace &space)
+void Vector::SetSpace(const ParFiniteElementSpace &space, int blocks_)
 {
    Verify(d == nullptr, "Vector::SetSpace: already allocated");
    fes = &space;
-   n = space.GetVSize();
+   blocks = blocks_;
+   n = space.GetVSize() * blocks;
    Check(rmh_dev_malloc(space.ctx, n, &d));
    const double c = 0.0;
    const double *x = d;
@@ -838,7 +841,12 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    Verify(o.fct >= 0 && o.fct <= 4 && o.fct != 3,
           "only -fct 0, 1 (FluxBased), 2 (ClipScale), 4 (FCTProject) are part of this build");
    Verify(!(o.fct == 4 && o.pa), "FCTProject needs the assembled element mass (no -pa).");
-   Verify(!o.ps, "product remap (-ps) is not part of this build");
+   if (o.ps)
+   {
+      Verify(o.problem >= 10, "Products are processed only in remap mode.");                 // remhos.cpp:1850
+      Verify(!o.dtc, "Automatic time step is not implemented for product remap.");          // :1851
+      Verify(o.fct != 0 && !o.mono && !o.vb, "product remap (-ps) needs an FCT solver (and no -vb / -mono) in this build");
+   }
    Verify(o.si >= 0 && o.si <= 2, "Bad smoothness indicator id!");
    if (o.si) { Verify(o.mono != 0 && o.order == 1, "smoothness indicators (-si) are built for -mono with -o 1 only"); }
    Verify(o.dtc == 0 || o.dtc == 1, "time step control must be 0 (fixed) or 1 (LO bounds error)");
@@ -882,8 +890,33 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    {
       ParFiniteElementSpace pfes(mesh, o.problem, o.order, o.mesh_order, o.bt, dt, t_final, comm.local_rank, &comm);
       std::cout << "Number of unknowns: " << pfes.GlobalVSize() << std::endl;   // remhos.cpp:623
-      Vector u(pfes), lumpedM(pfes);
-      u.SetFromHost(pfes.u0);
+      // S = (u, us) with a product field (BlockVector, remhos.cpp:594-598); `u` names block 0 throughout
+      Vector u(pfes, o.ps ? 2 : 1), lumpedM(pfes);
+      const int64_t NV = pfes.GetVSize();
+      if (!o.ps) { u.SetFromHost(pfes.u0); }
+      else
+      {
+         // us = u * s, s = s0_function on the elements where u is active (BoolFunctionCoefficient over
+         // ComputeBoolIndicators), sampled at the lattice points (remhos.cpp:886-903, 2357-2361)
+         Verify(comm.world == 1, "product remap runs on one GPU");
+         std::vector<double> S0(pfes.u0);
+         S0.resize((size_t)2 * NV, 0.0);
+         const int nd = pfes.GetNDofs(), dim = pfes.dim;
+         const double two_pi = 2.0 * M_PI;
+         for (int64_t e = 0; e < NV / nd; e++)
+         {
+            bool active = false;
+            for (int j = 0; j < nd; j++) { if (pfes.u0[e * nd + j] > 1e-12) { active = true; } }   // EMPTY_ZONE_TOL
+            for (int j = 0; j < nd; j++)
+            {
+               const double *x = &pfes.xlat[((size_t)e * nd + j) * dim];
+               const double s0 = active ? 2.0 + std::sin(two_pi * x[0]) * std::sin(two_pi * x[1]) : 0.0;
+               S0[NV + e * nd + j] = pfes.u0[e * nd + j] * s0;
+            }
+         }
+         u.SetFromHost(S0);
+         Check(rmh_product_enable(pfes.ctx, 1));
+      }
       Check(rmh_lumped_mass(pfes.ctx, lumpedM.Write(), nullptr));
       DofInfo dofs(pfes, o.bt);
       HOSolver *ho_solver = nullptr;
@@ -914,6 +947,8 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       Check(rmh_reduce(pfes.ctx, 1, u.Read(), nullptr, &u_min, nullptr));
       Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &u_max, nullptr));
       mass0_u = pfes.Reduce(mass0_u, 0); u_min = pfes.Reduce(u_min, 1); u_max = pfes.Reduce(u_max, 2);   // MPI_Allreduce
+      double mass0_us = 0.0;
+      if (o.ps) { Check(rmh_reduce(pfes.ctx, 0, u.Block(1), lumpedM.Read(), &mass0_us, nullptr)); }   // :1079-1083
       ODESolver ode_solver(o.ode);
       ode_solver.Init(adv);
       // the time loop below only reads the state between steps: the element min/max the last RK
@@ -987,6 +1022,20 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       std::cout << std::setprecision(10) << "Final mass u:  " << mass_u << std::endl
                 << "Max value u:   " << u_max << std::endl << std::setprecision(6)
                 << "Mass loss u:   " << std::abs(mass0_u - mass_u) << std::endl;
+      if (o.ps)                                                          // remhos.cpp:1416-1436
+      {
+         double mass_us = 0.0, s_max = 0.0;
+         Check(rmh_reduce(pfes.ctx, 0, u.Block(1), lumpedM.Read(), &mass_us, nullptr));
+         // ComputeRatio(us, u, s, ...); s.Max()
+         Vector s(pfes), flags(pfes);      // flags: byte arrays (ne + N bytes fit in N doubles)
+         uint8_t *el = reinterpret_cast<uint8_t *>(flags.Write());
+         uint8_t *dof = el + ((pfes.GetNE() + 15) / 16) * 16;
+         Check(rmh_prod_compute_ratio(pfes.ctx, u.Block(1), u.Block(0), s.Write(), el, dof, nullptr));
+         Check(rmh_reduce(pfes.ctx, 2, s.Read(), nullptr, &s_max, nullptr));
+         std::cout << std::setprecision(10) << "Final mass us: " << mass_us << std::endl
+                   << "Max value s:   " << s_max << std::endl << std::setprecision(6)
+                   << "Mass loss us:  " << std::abs(mass0_us - mass_us) << std::endl;
+      }
       if (o.save)
       {
          // sltn_final.gf in MFEM GridFunction text format (remhos.cpp:1366-1380)

@@ -58,14 +58,19 @@ class Vector
    const ParFiniteElementSpace *fes = nullptr;
    double *d = nullptr;
    int64_t n = 0;
+   int blocks = 1;
 public:
    Vector() {}
-   explicit Vector(const ParFiniteElementSpace &space);
+   // blocks > 1: a BlockVector of that many fields on the space (remhos.cpp:594-598: S = (u, us))
+   explicit Vector(const ParFiniteElementSpace &space, int blocks = 1);
    Vector(const Vector &o);
    Vector &operator=(const Vector &o);
    Vector &operator=(double v);
    ~Vector();
-   void SetSpace(const ParFiniteElementSpace &space);
+   void SetSpace(const ParFiniteElementSpace &space, int blocks = 1);
+   // device pointer of block b
+   const double *Block(int b) const;
+   double *Block(int b);
    int64_t Size() const { return n; }
    const double *Read() const { return d; }
    double *Write() { return d; }

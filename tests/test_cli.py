@@ -285,3 +285,35 @@ def test_cli_default_mesh_has_epm_elements():
         assert parse(out)['n'] == 64 * 27
     rc, _, err = run_cli('-m', 'default', '-dim', 3, '-epm', 12, '-rp', 1, '-o', 2, '-ho', 3, '-lo', 5, '-fct', 2)
     assert rc == 134 and 'Mesh generation error' in err     # 12 is not a multiple of 8
+
+
+# Product-field remap through the GPU CLI: the three reference known answers for -ps
+# (autotest/out_baseline.dat:187-200: -fct 1 -s 1, -fct 2 -s 12, -fct 4 -s 13), 10 printed digits
+PS_ROWS = [
+    (['-ho', 3, '-lo', 1, '-fct', 1, '-ps', '-s', 1], dict(mass_us=0.1815368098, loss_us=0.00192894)),
+    (['-ho', 1, '-lo', 5, '-fct', 2, '-ps', '-s', 12], dict(mass_us=0.1796076412, loss_us=2.31348e-07)),
+    (['-ho', 3, '-lo', 5, '-fct', 4, '-ps', '-s', 13], dict(mass=0.08980386855, mass_us=0.179607829)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('flags,exp', PS_ROWS, ids=['fct1-s1', 'fct2-s12', 'fct4-s13'])
+def test_cli_product_remap_reproduces_reference_known_answers(flags, exp):
+    rc, out, err = run_cli('-no-vis', '-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 2, '-dt', 0.005, '-tf', 0.75,
+                           *flags)
+    assert rc == 0, err
+    g = lambda pat: float(re.search(pat, out).group(1))
+    got = dict(mass=g(r'Final mass u:\s+(\S+)'), mass_us=g(r'Final mass us:\s+(\S+)'),
+               loss_us=g(r'Mass loss us:\s+(\S+)'), s_max=g(r'Max value s:\s+(\S+)'))
+    for k, v in exp.items():
+        tol = 5e-10 if k.startswith('mass') else 2e-5          # 10 digits; losses are printed with 6
+        assert abs(got[k] - v) <= tol * abs(v), (k, got[k], v)
+    assert 1.0 <= got['s_max'] <= 3.0 + 1e-6                   # s0 = 2 + sin sin stays in its range
+
+
+@pytest.mark.gpu
+def test_cli_product_remap_rejections():
+    rc, _, err = run_cli('-m', mesh('periodic-square.mesh'), '-p', 0, '-ho', 3, '-lo', 5, '-fct', 2, '-ps')
+    assert rc == 134 and 'Products are processed only in remap mode.' in err      # remhos.cpp:1850
+    rc, _, err = run_cli('-m', mesh('inline-quad.mesh'), '-p', 14, '-ho', 3, '-lo', 5, '-fct', 4, '-ps', '-dtc', 1)
+    assert rc == 134 and 'Automatic time step is not implemented for product remap.' in err
