@@ -281,6 +281,10 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--rs', type=int, default=5)
     ap.add_argument('--order', type=int, default=3)
+    ap.add_argument('--nloc', type=int, default=0,
+                    help='elements per direction of the periodic Cartesian brick every GPU owns (default '
+                         '3 * 2^rs, the refined periodic-cube mesh); BASELINE config 4 = --order 4 --nloc 74 '
+                         '--gpus 8: 148^3 elements, 405 M DOFs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-dist-check', action='store_true')
@@ -291,8 +295,13 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    workload = ('3D periodic-cube transport, order %d hex, -rs %d, -ho 3 -lo 5 -fct 2 -pa -s 3 '
-                '(problem %d)' % (a.order, a.rs, a.problem))
+    nloc = a.nloc if a.nloc > 0 else 3 * 2 ** a.rs
+    if a.nloc > 0:
+        workload = ('3D periodic Cartesian transport, order %d hex, %d^3 elements per GPU, -ho 3 -lo 5 -fct 2 '
+                    '-pa -s 3 (problem %d)' % (a.order, nloc, a.problem))
+    else:
+        workload = ('3D periodic-cube transport, order %d hex, -rs %d, -ho 3 -lo 5 -fct 2 -pa -s 3 '
+                    '(problem %d)' % (a.order, a.rs, a.problem))
     metric = 'DOF*RK-stage updates/sec (3D hex, order 3, FCT)'
 
     if a.impl == 'reference':
@@ -331,11 +340,14 @@ def main():
     if world > 1 and not a.no_dist_check:
         dist_err, dist_cases = dist_parity_check(rank, world, local_rank)
 
-    h = 2.0 / (3 * 2 ** a.rs)
+    h = 2.0 / nloc
     dt = 0.25 * h / a.order            # fixed dt = 0.25 h/|v| /p, |v| = 1
     if world == 1:
-        mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
-        mesh.refine(a.rs)
+        if a.nloc > 0:
+            mesh = rb.Mesh.cartesian([nloc] * 3, [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+        else:
+            mesh = rb.Mesh.cartesian([3, 3, 3], [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
+            mesh.refine(a.rs)
         prob = Problem(mesh, problem=a.problem, order=a.order, mesh_order=2, bounds_type=0, dt=dt,
                        device=local_rank)
         ctx = prob.ctx
@@ -353,7 +365,6 @@ def main():
         pdims = {2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}.get(world)
         if pdims is None:
             raise SystemExit('bench.py: --gpus must be 1, 2, 4 or 8')
-        nloc = 3 * 2 ** a.rs
         mesh = rb.Mesh.cartesian([nloc * d for d in pdims], [2.0 * d for d in pdims],
                                  origin=[-1.0 * d for d in pdims], periodic=True)
         prob = DistProblem(mesh, rank, world, problem=a.problem, order=a.order, mesh_order=2,
@@ -441,7 +452,7 @@ def main():
     else:
         kid = 'k_stage3w'
         kname = 'k_stage3w<%d,%d> (FP64 DMMA, warp per element)' % (a.order + 1, a.order + 3)
-    traffic, tsrc = read_traffic('%s|o%d|rs%d|p%d' % (kid, a.order, a.rs, a.problem))
+    traffic, tsrc = read_traffic('%s|o%d|rs%d|p%d' % (kid, a.order, a.rs, a.problem)) if a.nloc == 0 else (None, None)
     roof = {'bound': 'hbm', 'kernel': kname, 'peak': peak, 'peak_source': which, 'unit': 'GB/s',
             # the kernel's own DRAM traffic (ncu) over its own time (CUDA events, this run)
             'traffic': traffic, 'traffic_unit': 'bytes per launch', 'traffic_source': tsrc,
@@ -462,7 +473,7 @@ def main():
         'data': 'synthetic',
         'config': {'workload': workload, 'dofs_per_gpu': N, 'elements_per_gpu': ctx.ne,
                    'stages_per_step': STAGES, 'dt': dt,
-                   'l2': 'state vectors (453 MB each at -rs 5) exceed the 126 MB L2',
+                   'l2': 'state vectors (%d MB each) exceed the 126 MB L2' % (8 * N // 10 ** 6),
                    'problem': a.problem,
                    'parallelism': ('domain decomposition %dx%dx%d bricks; per stage one put kernel (face '
                                    'traces + (min,max) pairs stored into the peers\' windows over NVLink) '
