@@ -265,6 +265,18 @@ int rmh_mono_rd(rmh_ctx *ctx, const double *u_dev, double *du_dev, void *stream)
 int rmh_fct_project(rmh_ctx *ctx, double dt, const double *u_dev, const double *du_ho_dev,
                     const double *du_lo_dev, const double *xi_min_dev, const double *xi_max_dev,
                     double *du_dev, void *stream);
+/* NonlinearPenaltySolver::CalcFCTSolution (remhos_fct.cpp:760-996; -fct 3): rate clipped to the bounds,
+ * conservation restored per element by the penalised flux correction of CorrectFlux / get_lambda
+ * (bisection, every sum in DOF order as the host loop; both loops capped at 200 rounds).
+ * eps_w = Mesh::GetElementSize(0, 0) / order (:961). */
+int rmh_fct_nonlinear_penalty(rmh_ctx *ctx, double dt, double eps_w, const double *u_dev, const double *m_dev,
+                              const double *du_ho_dev, const double *du_lo_dev, const double *xi_min_dev,
+                              const double *xi_max_dev, double *du_dev, void *stream);
+/* SmoothnessIndicator::UpdateBounds (remhos_tools.cpp:183-190) on every dof: si_dev = rmh_si_values(u),
+ * u_HO = u + dt du_HO; xi_min / xi_max relaxed in place.  While a smoothness indicator is set
+ * (rmh_si_setup), rmh_limit_mult applies it in front of -fct 2 and -fct 3 (remhos_fct.cpp:498-504,780-795). */
+int rmh_si_update_bounds(rmh_ctx *ctx, double dt, const double *u_dev, const double *du_ho_dev,
+                         const double *si_dev, double *xi_min_dev, double *xi_max_dev, void *stream);
 /* Automatic time step control, -dtc 1 (remhos.cpp:312-316): with mode 1 every rmh_limit_mult runs
  * AdvectionOperator::UpdateTimeStepEstimate (remhos.cpp:1968-1998) on the LO rate.  rmh_dt_ratio =
  * GetTimeStepRatio (minimum of dt_estimate / dt since the last reset), reset != 0 =
@@ -319,7 +331,7 @@ int rmh_fct_product(rmh_ctx *ctx, int fct_type, double dt, const double *us_dev,
                     void *stream);
 
 /* LimitedTimeDependentOperator::Mult (remhos_solvers.hpp:46-50) for any supported combination of
- * -ho {0,1,3} -lo {0,1,2,3,4,5} -fct {0,1,2} at time t (remap: mesh moved to x0 + t v first,
+ * -ho {0,1,3} -lo {0,1,2,3,4,5} -fct {0,1,2,3,4} at time t (remap: mesh moved to x0 + t v first,
  * remhos.cpp:1598-1677): k = F(u; t, dt).  Orchestrates the separate kernels exactly as
  * MultUnlimited / LimitMult do (remhos.cpp:1596-1739, 1798-1916); -ho 3 -lo 5 -fct 2 runs the
  * fused stage kernel. */

@@ -203,10 +203,16 @@ class Run:
             umin, umax = d.bounds(u, o.bounds_type)
             if o.verify_bounds:
                 self.check(u, dt, du_lo, umin, umax, 'LO')
+            si_tmp = self.si.dof_values(u) if (self.si is not None and o.fct_type in (2, 3)) else None
             if o.fct_type == 2:
-                du = d.fct_clip_scale(u, A.ml, du_ho, du_lo, umin, umax, dt)
+                bmin, bmax = umin, umax
+                if si_tmp is not None:      # the bound relaxation the reference's kernel intends (remhos_fct.cpp:498-504)
+                    bmin, bmax = d.si_update_bounds(u + dt * du_ho, si_tmp, umin, umax)
+                du = d.fct_clip_scale(u, A.ml, du_ho, du_lo, bmin, bmax, dt)
             elif o.fct_type == 1:
                 du = d.fct_flux_based(u, A.ml, du_ho, du_lo, umin, umax, dt)
+            elif o.fct_type == 3:
+                du = d.fct_nonlinear_penalty(u, A.ml, du_ho, du_lo, umin, umax, dt, self.penalty_eps(), si_tmp)
             elif o.fct_type == 4:
                 du = d.fct_project(u, du_ho, du_lo, umin, umax, dt)
             else:
@@ -219,6 +225,17 @@ class Run:
         if o.lo_type:
             return self.calc_lo(u, None, dt)
         return self.calc_ho(u)
+
+    def penalty_eps(self):
+        """GetElementSize(0, 0) / GetOrder(0) of NonlinearPenaltySolver::CorrectFlux (remhos_fct.cpp:961):
+        size of element 0 = |det J(centre)|^(1/dim) at the current mesh position"""
+        sp = self.space
+        dim = sp.dim
+        c = np.array([0.5])
+        dLc = [fe.tensor_basis([fe.lagrange_deriv(sp.gll, c) if a == b else fe.lagrange(sp.gll, c)
+                                for b in range(dim)]) for a in range(dim)]
+        det, _ = sp.det_adj(sp.jacobians(self.disc.cur.X[:1], dLc))
+        return float(np.abs(det[0, 0]) ** (1.0 / dim)) / sp.p
 
     def calc_ho(self, u):
         if self.opt.ho_type == 1:
@@ -263,8 +280,13 @@ class Run:
         A = d.cur
         du_lo = self.calc_lo(u, du_ho, dt)
         umin, umax = d.bounds(u, o.bounds_type)
+        si_tmp = self.si.dof_values(u) if (self.si is not None and o.fct_type in (2, 3)) else None
         if o.fct_type == 2:
+            if si_tmp is not None:          # the bound relaxation the reference's kernel intends (remhos_fct.cpp:498-504)
+                umin, umax = d.si_update_bounds(u + dt * du_ho, si_tmp, umin, umax)
             return d.fct_clip_scale(u, A.ml, du_ho, du_lo, umin, umax, dt)
+        if o.fct_type == 3:
+            return d.fct_nonlinear_penalty(u, A.ml, du_ho, du_lo, umin, umax, dt, self.penalty_eps(), si_tmp)
         if o.fct_type == 4:
             return d.fct_project(u, du_ho, du_lo, umin, umax, dt)
         return d.fct_flux_based(u, A.ml, du_ho, du_lo, umin, umax, dt)

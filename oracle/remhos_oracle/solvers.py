@@ -418,6 +418,84 @@ class Discretization:
             f = np.where((new_mass < -eps)[:, None], fneg, f)
         return du_lo + f / m
 
+    @staticmethod
+    def si_update_bounds(u_ho, si_tmp, umin, umax):
+        """SmoothnessIndicator::UpdateBounds (remhos_tools.cpp:183-190), all dofs at once: si_tmp is the
+        indicator at the dof (1 on the domain boundary); u_ho = u + dt du_HO"""
+        return (np.maximum(0.0, si_tmp * u_ho + (1.0 - si_tmp) * umin),
+                np.minimum(1.0, si_tmp * u_ho + (1.0 - si_tmp) * umax))
+
+    @staticmethod
+    def _penalty_get_z(lam, w, flux):
+        return np.where(np.abs(flux) >= lam * np.abs(w), lam * w, flux)
+
+    @classmethod
+    def _penalty_get_lambda(cls, delta, w, flux, max_iter=200):
+        """get_lambda (remhos_fct.cpp:843-926), statement by statement; sums run in DOF order.  The
+        reference loops until abs(F) <= 1e-15 with no cap; here both loops stop after max_iter rounds (the
+        bracket has collapsed to one double long before), stated in DESIGN.md."""
+        tol = 1e-15
+
+        def lsz(lam):                                          # get_lambda_times_sum_z
+            z = cls._penalty_get_z(lam, w, flux)
+            acc = 0.0
+            for v in z:
+                acc += v
+            return acc
+        lam = 1.0
+        F = delta - lsz(lam)
+        factor = 1.0
+        for _ in range(max_iter):
+            factor *= 2.0
+            lo, hi = lam / factor, factor * lam
+            FL, FU = delta - lsz(lo), delta - lsz(hi)
+            if not (F * FL > 0 and F * FU > 0):
+                break
+        if F * FL < 0:
+            hi = lam
+        else:
+            lo = lam
+        FL, FU = delta - lsz(lo), delta - lsz(hi)
+        for _ in range(max_iter):
+            lam = 0.5 * (lo + hi)
+            F = delta - lsz(lam)
+            if F * FL < 0:
+                hi, FU = lam, F
+            else:
+                lo, FL = lam, F
+            if not abs(F) > tol:
+                break
+        lam = 0.5 * (lo + hi)
+        return cls._penalty_get_z(lam, w, flux)
+
+    def fct_nonlinear_penalty(self, u, m, du_ho, du_lo, umin, umax, dt, eps_w, si_tmp=None):
+        """NonlinearPenaltySolver::CalcFCTSolution + CorrectFlux (remhos_fct.cpp:760-996).  eps_w =
+        GetElementSize(0, 0) / order (:961)."""
+        if si_tmp is not None:
+            umin, umax = self.si_update_bounds(u + dt * du_ho, si_tmp, umin, umax)
+        star = np.minimum((umax - u) / dt, np.maximum(du_ho, (umin - u) / dt))     # uses u at the old time
+        fL = m * (star - du_lo)
+        fH = m * (star - du_ho)
+        corr = np.zeros_like(fL)
+        for e in range(u.shape[0]):
+            fl, fh = fL[e], fH[e]
+            fp = 0.0; fn = 0.0
+            for v in fl:
+                if v >= 0.0:
+                    fp += v
+                else:
+                    fn += v
+            delta = fp + fn
+            if delta == 0.0:
+                continue
+            mx = max(np.abs(fh).max(), -1.0)
+            if delta > 0.0:
+                w = np.where(fl > 0.0, eps_w * np.abs(fl) + abs(mx), 0.0)
+            else:
+                w = np.where(fl < 0.0, -eps_w * np.abs(fl) - abs(mx), 0.0)
+            corr[e] = -self._penalty_get_lambda(delta, w, fl)
+        return du_lo + (fL + corr) / m
+
     def fct_project(self, u, du_ho, du_lo, umin, umax, dt):
         """ElementFCTProjection::CalcFCTSolution (remhos_fct.cpp:613-733): element-local Zalesak
         limiter on the fluxes F_ij = M_ij (du_i - du_j) + (beta_j z_i - beta_i z_j), beta = M_L / sum M_L,

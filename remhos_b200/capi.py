@@ -417,6 +417,14 @@ class Context:
         check(lib().rmh_fct_project(self.h, C.c_double(dt), _dp(u), _dp(du_ho), _dp(du_lo), _dp(xmin),
                                     _dp(xmax), _dp(du), C.c_void_p(s)))
 
+    def fct_nonlinear_penalty(self, dt, eps_w, u, m, du_ho, du_lo, xmin, xmax, du, s=0):
+        check(lib().rmh_fct_nonlinear_penalty(self.h, C.c_double(dt), C.c_double(eps_w), _dp(u), _dp(m), _dp(du_ho),
+                                              _dp(du_lo), _dp(xmin), _dp(xmax), _dp(du), C.c_void_p(s)))
+
+    def si_update_bounds(self, dt, u, du_ho, si, xmin, xmax, s=0):
+        check(lib().rmh_si_update_bounds(self.h, C.c_double(dt), _dp(u), _dp(du_ho), _dp(si), _dp(xmin), _dp(xmax),
+                                         C.c_void_p(s)))
+
     def dt_control(self, mode):
         check(lib().rmh_dt_control(self.h, int(mode)))
 

@@ -145,6 +145,7 @@ struct rmh_ctx
    // scratch
    double *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *red = nullptr;
    double *pin = nullptr;   // pinned host staging (e2e entry point)
+   std::vector<double> x0_e0, v_e0;   // nodes / node velocities of element 0 (Mesh::GetElementSize(0, 0))
    // optional per-launch timing of the fused stage kernel (bench.py roofline)
    bool prof = false;
    std::vector<cudaEvent_t> prof_ev;
@@ -1564,6 +1565,11 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    if (!d->nodes) { set_error("desc.nodes is required"); return fail(); }
    if (dev_upload(c, &c->X0, d->nodes, nnod)) { return fail(); }
    if (d->vel_nodes) { if (dev_upload(c, &c->V, d->vel_nodes, nnod)) { return fail(); } }
+   if (c->ne > 0)
+   {
+      c->x0_e0.assign(d->nodes, d->nodes + (size_t)c->NGN * c->dim);
+      if (d->vel_nodes && c->exec_mode == 1) { c->v_e0.assign(d->vel_nodes, d->vel_nodes + (size_t)c->NGN * c->dim); }
+   }
    if (c->exec_mode == 1 && !d->vel_nodes)
    { set_error("remap mode needs desc.vel_nodes (mesh velocity)"); return fail(); }
    if (c->exec_mode == 0)
@@ -2670,8 +2676,8 @@ static int check_combo(int ho_type, int lo_type, int fct_type)
    { set_error("stage operator: HO solver must be 0, 1 (Neumann) or 3 (LocalInverse)"); return 1; }
    if (lo_type < 0 || lo_type > 5)
    { set_error("stage operator: LO solver must be 0 .. 5"); return 1; }
-   if (fct_type < 0 || fct_type > 4 || fct_type == 3)
-   { set_error("stage operator: FCT solver must be 0, 1 (FluxBased), 2 (ClipScale) or 4 (FCTProject)"); return 1; }
+   if (fct_type < 0 || fct_type > 4)
+   { set_error("stage operator: FCT solver must be 0, 1 (FluxBased), 2 (ClipScale), 3 (NonlinearPenalty) or 4 (FCTProject)"); return 1; }
    if (fct_type && (ho_type == 0 || lo_type == 0))
    { set_error("FCT requires HO and LO solvers."); return 1; }        // remhos.cpp:1690
    if (!fct_type && lo_type == 5 && ho_type == 0)
@@ -2711,6 +2717,39 @@ static int mult_unlimited_1(rmh_ctx *c, int ho_type, int lo_type, int fct_type, 
 
 // AdvectionOperator::LimitMult (remhos.cpp:1798-1916): k holds the (possibly combined) HO rate
 // on entry and the limited rate on exit; a no-op without an FCT solver.
+// Mesh::GetElementSize(0, 0) at the current mesh position: |det J(centre of element 0)|^(1/dim)
+static double elem0_size(const rmh_ctx *c)
+{
+   const int dim = c->dim, n1 = c->NG1;
+   const std::vector<double> gll = gauss_lobatto_01(n1), half = {0.5};
+   const std::vector<double> L = lagrange(gll, half), dL = lagrange_deriv(gll, half);
+   double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+   for (int node = 0; node < c->NGN; node++)
+   {
+      int id[3] = {0, 0, 0}, r = node;
+      for (int a = 0; a < dim; a++) { id[a] = r % n1; r /= n1; }
+      for (int a = 0; a < dim; a++)          // derivative direction
+      {
+         double g = 1.0;
+         for (int b = 0; b < dim; b++) { g *= (a == b) ? dL[id[b]] : L[id[b]]; }
+         for (int i = 0; i < dim; i++)
+         {
+            double x = c->x0_e0[(size_t)node * dim + i];
+            if (!c->v_e0.empty()) { x += c->t_cur * c->v_e0[(size_t)node * dim + i]; }
+            J[i][a] += g * x;
+         }
+      }
+   }
+   double det;
+   if (dim == 2) { det = J[0][0] * J[1][1] - J[0][1] * J[1][0]; }
+   else
+   {
+      det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+            J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+   }
+   return std::pow(std::fabs(det), 1.0 / dim);
+}
+
 static int limit_mult_1(rmh_ctx *c, int lo_type, int fct_type, double dt, const double *u,
                         double *k, void *stream)
 {
@@ -2730,7 +2769,17 @@ static int limit_mult_1(rmh_ctx *c, int lo_type, int fct_type, double dt, const 
    if (rmh_elem_min_max(c, u, c->xe_min, c->xe_max, stream)) { return 1; }
    if (rmh_bounds(c, c->xe_min, c->xe_max, xmn, xmx, stream)) { return 1; }
    int rc;
+   if (c->si_type && (fct_type == 2 || fct_type == 3))
+   {
+      // bounds relaxed where the solution is smooth (SmoothnessIndicator::UpdateBounds: NonlinearPenaltySolver
+      // remhos_fct.cpp:780-795; ClipScaleSolver :498-504, which the reference's device kernel aborts on)
+      if (work_vec(c, &c->wk[7])) { return 1; }
+      if (rmh_si_values(c, u, c->wk[7], stream)) { return 1; }
+      if (rmh_si_update_bounds(c, dt, u, du_ho, c->wk[7], xmn, xmx, stream)) { return 1; }
+   }
    if (fct_type == 2) { rc = rmh_fct_clip_scale(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
+   else if (fct_type == 3)
+   { rc = rmh_fct_nonlinear_penalty(c, dt, elem0_size(c) / c->p, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
    else if (fct_type == 4) { rc = rmh_fct_project(c, dt, u, du_ho, du_lo, xmn, xmx, k, stream); }
    else { rc = rmh_fct_flux_based(c, dt, u, c->ml, du_ho, du_lo, xmn, xmx, k, stream); }
    if (rc) { return rc; }
@@ -2741,6 +2790,35 @@ static int limit_mult_1(rmh_ctx *c, int lo_type, int fct_type, double dt, const 
                                                                                        xmx, c->dt_ratio);
       LAUNCH_OK();
    }
+   return 0;
+}
+
+// SmoothnessIndicator::UpdateBounds (remhos_tools.cpp:183-190) on all dofs; si_dev from rmh_si_values
+extern "C" int rmh_si_update_bounds(rmh_ctx *c, double dt, const double *u, const double *du_ho, const double *si,
+                                    double *xi_min, double *xi_max, void *stream)
+{
+   const int bs = 256;
+   k_si_update_bounds<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(c->N, dt, u, du_ho, si,
+                                                                                        xi_min, xi_max);
+   LAUNCH_OK();
+   return 0;
+}
+
+// NonlinearPenaltySolver::CalcFCTSolution (remhos_fct.cpp:760-996); eps_w = GetElementSize(0, 0) /
+// GetOrder(0) (:961).  The bound relaxation by a smoothness indicator (:780-795) is rmh_si_update_bounds.
+extern "C" int rmh_fct_nonlinear_penalty(rmh_ctx *c, double dt, double eps_w, const double *u, const double *m,
+                                         const double *du_ho, const double *du_lo, const double *xi_min,
+                                         const double *xi_max, double *du, void *stream)
+{
+   if (work_vec(c, &c->wk[0]) || work_vec(c, &c->wk[1]) || work_vec(c, &c->wk[2])) { return 1; }
+   cudaStream_t s = (cudaStream_t)stream;
+   const int bs = 256;
+   k_penalty_flux<<<(unsigned)((c->N + bs - 1) / bs), bs, 0, s>>>(c->N, dt, u, m, du_ho, du_lo, xi_min, xi_max,
+                                                                 c->wk[0], c->wk[1]);
+   LAUNCH_OK();
+   k_penalty_correct<<<(unsigned)((c->ne + 63) / 64), 64, 0, s>>>(c->ne, c->ND, eps_w, m, du_lo, c->wk[0], c->wk[1],
+                                                                 c->wk[2], du);
+   LAUNCH_OK();
    return 0;
 }
 
@@ -2948,7 +3026,7 @@ extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, doub
                         const double *u, double *k, void *stream)
 {
    if (c->mono_type) { return rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t, dt, u, k, stream); }
-   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control && !c->product)
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control && !c->product && !c->si_type)
    {
       if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
       if (rmh_set_time(c, t, stream)) { return 1; }
@@ -2991,8 +3069,8 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
 {
    cudaStream_t s = (cudaStream_t)stream;
    // (with automatic time step control the LO rate must be visible to the dt estimate: unfused path)
-   if (!c->mono_type && !c->dt_control && !c->product && ho_type == 3 && lo_type == 5 && fct_type == 2 && ode >= 1 &&
-       ode <= 3)
+   if (!c->mono_type && !c->dt_control && !c->product && !c->si_type && ho_type == 3 && lo_type == 5 && fct_type == 2 &&
+       ode >= 1 && ode <= 3)
    { return rmh_rk_step(c, ode, lo_type, t, dt, u, stream); }
    const double t0 = *t;
    const size_t bytes = (size_t)state_len(c) * sizeof(double);

@@ -756,6 +756,96 @@ __global__ void k_fct_project(FaArgs A, double dt, const double *u, const double
    }
 }
 
+// ---- SmoothnessIndicator::UpdateBounds (remhos_tools.cpp:183-190) for every dof: si = the indicator
+// at the dof (1 on the domain boundary), u_HO = u + dt du_HO
+__global__ void k_si_update_bounds(int64_t n, double dt, const double *u, const double *du_ho, const double *si,
+                                   double *xi_min, double *xi_max)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   const double t = si[i], uh = u[i] + dt * du_ho[i];
+   xi_min[i] = fmax(0.0, t * uh + (1.0 - t) * xi_min[i]);
+   xi_max[i] = fmin(1.0, t * uh + (1.0 - t) * xi_max[i]);
+}
+
+// ---- NonlinearPenaltySolver (remhos_fct.cpp:760-996).  k_penalty_flux: the clipped rate and the two
+// non-conservative fluxes per dof (:787-807); k_penalty_correct: CorrectFlux + get_lambda (:843-996)
+// per element, one thread each, every sum in DOF order and every branch as in the reference, so the
+// bisection takes the same path as the host loop it replaces.  Both loops of get_lambda are capped at
+// 200 rounds (the reference has no cap; the bracket has collapsed to one double long before).
+__global__ void k_penalty_flux(int64_t n, double dt, const double *u, const double *m, const double *du_ho,
+                               const double *du_lo, const double *xi_min, const double *xi_max, double *fL,
+                               double *fH)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   // note that this uses u(i) at the old time (:801)
+   const double star = fmin((xi_max[i] - u[i]) / dt, fmax(du_ho[i], (xi_min[i] - u[i]) / dt));
+   fL[i] = m[i] * (star - du_lo[i]);
+   fH[i] = m[i] * (star - du_ho[i]);
+}
+
+__device__ __forceinline__ double penalty_sum_z(double lam, int nd, const double *w, const double *fl)
+{
+   double acc = 0.0;
+   for (int j = 0; j < nd; j++) { acc += (fabs(fl[j]) >= lam * fabs(w[j])) ? lam * w[j] : fl[j]; }
+   return acc;
+}
+
+__global__ void k_penalty_correct(int64_t ne, int nd, double eps_w, const double *m, const double *du_lo,
+                                  const double *fL, const double *fH, double *w_all, double *du)
+{
+   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= ne) { return; }
+   const double *fl = fL + e * nd, *fh = fH + e * nd;
+   double *w = w_all + e * nd;
+   double fp = 0.0, fn = 0.0;
+   for (int j = 0; j < nd; j++) { if (fl[j] >= 0.0) { fp += fl[j]; } else { fn += fl[j]; } }
+   const double delta = fp + fn;
+   if (delta == 0.0)
+   {
+      for (int j = 0; j < nd; j++) { du[e * nd + j] = du_lo[e * nd + j] + fl[j] / m[e * nd + j]; }
+      return;
+   }
+   double mx = -1.0;                                           // get_max_on_cellNi
+   for (int j = 0; j < nd; j++) { mx = fmax(fabs(fh[j]), mx); }
+   for (int j = 0; j < nd; j++)
+   {
+      if (delta > 0.0) { w[j] = (fl[j] > 0.0) ? eps_w * fabs(fl[j]) + fabs(mx) : 0.0; }
+      else { w[j] = (fl[j] < 0.0) ? -eps_w * fabs(fl[j]) - fabs(mx) : 0.0; }
+   }
+   // get_lambda
+   const double tol = 1e-15;
+   double lam = 1.0;
+   double F = delta - penalty_sum_z(lam, nd, w, fl);
+   double lo = 0.0, hi = 0.0, FL = 0.0, FU = 0.0, factor = 1.0;
+   for (int it = 0; it < 200; it++)
+   {
+      factor *= 2.0;
+      lo = lam / factor; hi = factor * lam;
+      FL = delta - penalty_sum_z(lo, nd, w, fl);
+      FU = delta - penalty_sum_z(hi, nd, w, fl);
+      if (!(F * FL > 0 && F * FU > 0)) { break; }
+   }
+   if (F * FL < 0) { hi = lam; } else { lo = lam; }
+   FL = delta - penalty_sum_z(lo, nd, w, fl);
+   FU = delta - penalty_sum_z(hi, nd, w, fl);
+   for (int it = 0; it < 200; it++)
+   {
+      lam = 0.5 * (lo + hi);
+      F = delta - penalty_sum_z(lam, nd, w, fl);
+      if (F * FL < 0) { hi = lam; FU = F; } else { lo = lam; FL = F; }
+      if (!(fabs(F) > tol)) { break; }
+   }
+   lam = 0.5 * (lo + hi);                                       // (:924: the midpoint of the last bracket)
+   (void)FU;
+   for (int j = 0; j < nd; j++)
+   {
+      const double z = (fabs(fl[j]) >= lam * fabs(w[j])) ? lam * w[j] : fl[j];
+      du[e * nd + j] = du_lo[e * nd + j] + (fl[j] + (-z)) / m[e * nd + j];
+   }
+}
+
 // AdvectionOperator::UpdateTimeStepEstimate (remhos.cpp:1968-1998): ratio <- min(ratio, dt_est / dt)
 __global__ void k_dt_estimate(int64_t n, double dt, const double *x, const double *dx,
                               const double *x_min, const double *x_max, double *ratio)

@@ -453,6 +453,12 @@ void SmoothnessIndicator::ComputeSmoothnessIndicator(const Vector &u, Vector &si
 {
    Check(rmh_si_values(pfes.ctx, u.Read(), si_vals_u.Write(), nullptr));
 }
+void SmoothnessIndicator::UpdateBounds(double dt, const Vector &u, const Vector &du_ho, const Vector &si_vals_u,
+                                       Vector &u_min, Vector &u_max) const
+{
+   Check(rmh_si_update_bounds(pfes.ctx, dt, u.Read(), du_ho.Read(), si_vals_u.Read(), u_min.Write(), u_max.Write(),
+                              nullptr));
+}
 
 // ---- monolithic solver (remhos_mono.cpp)
 MonoRDSolver::MonoRDSolver(ParFiniteElementSpace &space, SmoothnessIndicator *si, bool subcell,
@@ -546,6 +552,27 @@ void ClipScaleSolver::CalcFCTSolution(const Vector &u, const Vector &m, const Ve
 {
    Check(rmh_fct_clip_scale(pfes.ctx, dt, u.Read(), m.Read(), du_ho.Read(), du_lo.Read(),
                             u_min.Read(), u_max.Read(), du.Write(), nullptr));
+}
+
+void NonlinearPenaltySolver::CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho,
+                                             const Vector &du_lo, const Vector &u_min, const Vector &u_max,
+                                             Vector &du) const
+{
+   // eps of CorrectFlux: GetElementSize(0, 0) / GetOrder(0) (remhos_fct.cpp:961)
+   std::vector<double> h((size_t)rmh_mesh_ne(pfes.mesh));
+   Check(rmh_mesh_elem_sizes(pfes.mesh, h.data()));
+   const double eps_w = h.empty() ? 0.0 : h[0] / pfes.order;
+   if (smth_indicator)
+   {
+      Vector si(pfes), mn(u_min), mx(u_max);
+      smth_indicator->ComputeSmoothnessIndicator(u, si);
+      smth_indicator->UpdateBounds(dt, u, du_ho, si, mn, mx);
+      Check(rmh_fct_nonlinear_penalty(pfes.ctx, dt, eps_w, u.Read(), m.Read(), du_ho.Read(), du_lo.Read(),
+                                      mn.Read(), mx.Read(), du.Write(), nullptr));
+      return;
+   }
+   Check(rmh_fct_nonlinear_penalty(pfes.ctx, dt, eps_w, u.Read(), m.Read(), du_ho.Read(), du_lo.Read(),
+                                   u_min.Read(), u_max.Read(), du.Write(), nullptr));
 }
 
 // ------------------------------------------------------------------------------------ DofInfo
@@ -838,8 +865,8 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    Verify(!(o.ho == 1 && o.pa), "PA for DG is not supported for Neummann Solver.");   // remhos_ho.cpp:138-139
    Verify(o.lo >= 0 && o.lo <= 5, "LO solver type must be 0 .. 5");
    if (o.lo == 4) { Verify(o.order > 1, "Subcell schemes require FE order > 1."); }
-   Verify(o.fct >= 0 && o.fct <= 4 && o.fct != 3,
-          "only -fct 0, 1 (FluxBased), 2 (ClipScale), 4 (FCTProject) are part of this build");
+   Verify(o.fct >= 0 && o.fct <= 4, "FCT solver type must be 0 .. 4");
+   Verify(!(o.fct == 3 && o.problem >= 10), "-fct 3 (NonlinearPenalty) is built for transport mode");
    Verify(!(o.fct == 4 && o.pa), "FCTProject needs the assembled element mass (no -pa).");
    if (o.ps)
    {
@@ -848,7 +875,11 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       Verify(o.fct != 0 && !o.mono && !o.vb, "product remap (-ps) needs an FCT solver (and no -vb / -mono) in this build");
    }
    Verify(o.si >= 0 && o.si <= 2, "Bad smoothness indicator id!");
-   if (o.si) { Verify(o.mono != 0 && o.order == 1, "smoothness indicators (-si) are built for -mono with -o 1 only"); }
+   if (o.si)
+   {
+      Verify(o.order == 1, "smoothness indicators (-si) are built for -o 1 only");
+      Verify(o.mono != 0 || o.fct == 2 || o.fct == 3, "smoothness indicators (-si) act on -mono, -fct 2 and -fct 3");
+   }
    Verify(o.dtc == 0 || o.dtc == 1, "time step control must be 0 (fixed) or 1 (LO bounds error)");
    if (o.dtc) { Verify(o.fct != 0 && !o.vb, "-dtc 1 needs an FCT solver (and no -vb) in this build"); }
    Verify(!(o.fct == 1 && o.pa), "Flux-based FCT is not compatible with partial assembly.");   // :1088
@@ -928,16 +959,17 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       else if (o.lo == 3) { lo_solver = new ResidualDistribution(pfes); }
       else if (o.lo == 4) { lo_solver = new ResidualDistributionSubcell(pfes); }
       else if (o.lo == 5) { lo_solver = new MassBasedAvg(pfes, *ho_solver); }
+      SmoothnessIndicator *smth_indicator = nullptr;                     // remhos.cpp:905-911
+      if (o.si) { smth_indicator = new SmoothnessIndicator(o.si, pfes); }
       FCTSolver *fct_solver = nullptr;
       if (o.fct == 1) { fct_solver = new FluxBasedFCT(pfes, dt); }
       else if (o.fct == 2) { fct_solver = new ClipScaleSolver(pfes, dt); }
+      else if (o.fct == 3) { fct_solver = new NonlinearPenaltySolver(pfes, smth_indicator, dt); }
       else if (o.fct == 4) { fct_solver = new ElementFCTProjection(pfes, dt); }
       if (o.dtc) { Check(rmh_dt_control(pfes.ctx, 1)); }
       // monolithic solver (remhos.cpp:997-1011)
       MonolithicSolver *mono_solver = nullptr;
       const bool mass_lim = (o.problem != 6 && o.problem != 7);
-      SmoothnessIndicator *smth_indicator = nullptr;                     // remhos.cpp:905-911
-      if (o.si) { smth_indicator = new SmoothnessIndicator(o.si, pfes); }
       if (o.mono)
       { mono_solver = new MonoRDSolver(pfes, smth_indicator, o.mono == 2, pfes.exec_mode == 1, mass_lim); }
       AdvectionOperator adv(pfes, lumpedM, dofs, ho_solver, lo_solver, fct_solver, mono_solver);

@@ -242,6 +242,20 @@ public:
    int Type() const override { return 2; }
 };
 
+// remhos_fct.hpp:177-192 (-fct 3): penalty-based flux correction; with a smoothness indicator the
+// bounds are relaxed first (remhos_fct.cpp:780-795)
+class SmoothnessIndicator;
+class NonlinearPenaltySolver : public FCTSolver
+{
+   SmoothnessIndicator *smth_indicator;
+public:
+   NonlinearPenaltySolver(ParFiniteElementSpace &space, SmoothnessIndicator *si, double dt_)
+      : FCTSolver(space, dt_), smth_indicator(si) {}
+   void CalcFCTSolution(const Vector &u, const Vector &m, const Vector &du_ho, const Vector &du_lo,
+                        const Vector &u_min, const Vector &u_max, Vector &du) const override;
+   int Type() const override { return 3; }
+};
+
 // remhos_tools.hpp SmoothnessIndicator (remhos_tools.cpp:24-354; created at remhos.cpp:905-911).
 // Order-1 spaces only; the H1 operators live in the device context of the space.
 class SmoothnessIndicator
@@ -253,6 +267,9 @@ public:
    ~SmoothnessIndicator();
    // one value per DG dof: the indicator at the dof's vertex, 1 on the domain boundary
    void ComputeSmoothnessIndicator(const Vector &u, Vector &si_vals_u) const;
+   // UpdateBounds (remhos_tools.cpp:183-190) on every dof, u_HO = u + dt du_HO
+   void UpdateBounds(double dt, const Vector &u, const Vector &du_ho, const Vector &si_vals_u, Vector &u_min,
+                     Vector &u_max) const;
 };
 
 // remhos_mono.hpp:28-39

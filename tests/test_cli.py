@@ -317,3 +317,19 @@ def test_cli_product_remap_rejections():
     assert rc == 134 and 'Products are processed only in remap mode.' in err      # remhos.cpp:1850
     rc, _, err = run_cli('-m', mesh('inline-quad.mesh'), '-p', 14, '-ho', 3, '-lo', 5, '-fct', 4, '-ps', '-dtc', 1)
     assert rc == 134 and 'Automatic time step is not implemented for product remap.' in err
+
+
+@pytest.mark.gpu
+def test_cli_nonlinear_penalty_matches_oracle():
+    """-fct 3 through the driver (README.md:210's combination -ho 1 -lo 4 -fct 3 on a short run): no
+    reference number exists; the oracle's transcription is the checker"""
+    args = dict(problem=5, rs_levels=2, order=2, dt=0.002, t_final=0.02, ho_type=3, lo_type=3, fct_type=3)
+    run = oracle_run('periodic-square.mesh', **args)
+    run.run()
+    rc, out, err = run_cli('-no-vis', '-m', mesh('periodic-square.mesh'), '-p', 5, '-rs', 2, '-o', 2, '-dt', 0.002,
+                           '-tf', 0.02, '-ho', 3, '-lo', 3, '-fct', 3)
+    assert rc == 0, err
+    got = parse(out)
+    # (loose: the penalty solver amplifies one-ulp input differences, see tests/test_gpu_penalty.py)
+    assert abs(got['mass'] - run.final_mass) < 1e-5 * abs(run.final_mass)
+    assert abs(got['umax'] - run.final_max) < 1e-6
