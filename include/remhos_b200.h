@@ -61,6 +61,14 @@ const int64_t *rmh_mesh_elem_vertices(const rmh_mesh *m);
 /* Keep only the listed elements (used by the domain decomposition); ids are global. */
 int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *elem_ids, rmh_mesh **out);
 
+/* On-disk formats (-save, -visit: remhos.cpp:1016-1043,1366-1380).  rmh_mesh_save = Mesh::Print in
+ * "MFEM mesh v1.0" with the nodes as the element-wise Gauss-Lobatto field L2_T1_<dim>D_P<g> (nodes ==
+ * NULL: the mesh's own; else e.g. the moved mesh of a remap run); readable by MFEM / GLVis and by
+ * rmh_mesh_load.  rmh_gf_save = GridFunction::Save of a scalar DG field (basis_type 2 = Positive). */
+int rmh_mesh_save(const rmh_mesh *m, const char *path, const double *nodes, int precision);
+int rmh_gf_save(const char *path, int dim, int order, int basis_type, int64_t n, const double *vals,
+                int precision);
+
 /* Domain decomposition (replaces ParMesh's METIS / Cartesian partitioning, remhos.cpp:451-461):
  * recursive coordinate bisection of the element centroids; part[ne] receives the owner rank. */
 int rmh_mesh_partition(const rmh_mesh *m, int nparts, int32_t *part);

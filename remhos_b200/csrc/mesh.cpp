@@ -963,6 +963,79 @@ extern "C" int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *ids
    return 0;
 }
 
+// ------------------------------------------------------------------- on-disk formats
+// Mesh::Print in "MFEM mesh v1.0" (what pmesh.PrintAsOne writes for -save, remhos.cpp:1016-1030,
+// 1366-1380, and VisItDataCollection for -visit, :1034-1043): elements in MFEM's vertex order,
+// boundary = the faces without a neighbour (attribute 1), nodes as the element-wise Gauss-Lobatto
+// field L2_T1_<dim>D_P<g> (byVDIM) -- the representation MFEM itself uses for periodic meshes, valid
+// for every mesh, and read back by rmh_mesh_load.  nodes == NULL: the mesh's own nodes; else
+// [ne][(g+1)^dim][dim] (e.g. the moved mesh of a remap run).
+extern "C" int rmh_mesh_save(const rmh_mesh *mm, const char *path, const double *nodes, int precision)
+{
+   const Mesh &m = mm->m;
+   const int dim = m.dim, nvx = m.nvert(), nf = 2 * dim, nfc = 1 << (dim - 1);
+   Topology T;
+   if (build_topology(m, T)) { return 1; }
+   FILE *fp = std::fopen(path, "w");
+   if (!fp) { set_error(std::string("cannot write ") + path); return 1; }
+   std::fprintf(fp, "MFEM mesh v1.0\n\ndimension\n%d\n\nelements\n%lld\n", dim, (long long)m.ne);
+   const int *perm = (dim == 2) ? MFEM2LEX2 : MFEM2LEX3;
+   for (int64_t e = 0; e < m.ne; e++)
+   {
+      std::fprintf(fp, "1 %d", dim == 2 ? 3 : 5);
+      for (int k = 0; k < nvx; k++) { std::fprintf(fp, " %lld", (long long)m.ev[e * nvx + perm[k]]); }
+      std::fprintf(fp, "\n");
+   }
+   int64_t nb = 0;
+   for (int64_t i = 0; i < m.ne * nf; i++) { if (T.nbr_elem[i] < 0) { nb++; } }
+   std::fprintf(fp, "\nboundary\n%lld\n", (long long)nb);
+   for (int64_t e = 0; e < m.ne; e++)
+      for (int f = 0; f < nf; f++)
+      {
+         if (T.nbr_elem[e * nf + f] >= 0) { continue; }
+         int fc[4], axis, side;
+         face_corners(dim, f, fc);
+         face_axis(dim, f, axis, side);
+         // counter-clockwise seen from outside (natural parametrisation: remaining axes ascending)
+         int order[4] = {0, 1, 3, 2};
+         if (dim == 2) { order[0] = 0; order[1] = 1; }
+         const bool flip = (dim == 3) ? ((axis == 2 && side == 0) || (axis == 1 && side == 1) || (axis == 0 && side == 0))
+                                      : ((axis == 1 && side == 1) || (axis == 0 && side == 0));
+         std::fprintf(fp, "1 %d", dim == 2 ? 1 : 3);
+         for (int k = 0; k < nfc; k++)
+         {
+            const int kk = flip ? (nfc - k) % nfc : k;       // reversed cycle, same starting corner
+            std::fprintf(fp, " %lld", (long long)m.ev[e * nvx + fc[order[kk]]]);
+         }
+         std::fprintf(fp, "\n");
+      }
+   std::fprintf(fp, "\nvertices\n%lld\n\nnodes\nFiniteElementSpace\nFiniteElementCollection: L2_T1_%dD_P%d\n"
+                    "VDim: %d\nOrdering: 1\n\n", (long long)m.nv, dim, m.g, dim);
+   const double *X = nodes ? nodes : m.X.data();
+   const size_t np = (size_t)m.ne * m.npe();
+   for (size_t i = 0; i < np; i++)
+   {
+      for (int a = 0; a < dim; a++) { std::fprintf(fp, a ? " %.*g" : "%.*g", precision, X[i * dim + a]); }
+      std::fprintf(fp, "\n");
+   }
+   std::fclose(fp);
+   return 0;
+}
+
+// GridFunction::Save of a scalar field in the DG space of the run (u.SaveAsOne, remhos.cpp:1027-1029):
+// L2_T<basis>_<dim>D_P<order>, basis 2 = Positive (Bernstein, remhos.cpp:588-590), element-major values
+extern "C" int rmh_gf_save(const char *path, int dim, int order, int basis_type, int64_t n, const double *vals,
+                           int precision)
+{
+   FILE *fp = std::fopen(path, "w");
+   if (!fp) { set_error(std::string("cannot write ") + path); return 1; }
+   std::fprintf(fp, "FiniteElementSpace\nFiniteElementCollection: L2_T%d_%dD_P%d\nVDim: 1\nOrdering: 0\n\n", basis_type,
+                dim, order);
+   for (int64_t i = 0; i < n; i++) { std::fprintf(fp, "%.*g\n", precision, vals[i]); }
+   std::fclose(fp);
+   return 0;
+}
+
 // ------------------------------------------------------------------- domain decomposition
 // Recursive coordinate bisection of the element centroids into nparts (any count; splits are
 // proportional).  Replaces the METIS / Cartesian partitioning ParMesh does (remhos.cpp:451-461).

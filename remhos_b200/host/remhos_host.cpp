@@ -178,6 +178,7 @@ ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int orde
       vel_nodes.resize(nnod);
       Check(rmh_remap_mesh_velocity(m, problem, bb_min.data(), bb_max.data(), dt, t_final_,
                                     vel_nodes.data()));
+      vel_nodes_host = vel_nodes;
       t_final_ = 1.0;                                                    // :1128-1134
    }
    else
@@ -326,6 +327,56 @@ void ParFiniteElementSpace::SetupDistributed(double &dt, double &t_final_, int d
    xlat = xdof;
    bdr_dofs = bd;
    nbr_elem.assign(nbe.begin(), nbe.begin() + (size_t)no * nf);
+}
+
+void ParFiniteElementSpace::SaveMesh(const std::string &path, double t, int precision) const
+{
+   if (exec_mode == 1 && !vel_nodes_host.empty())
+   {
+      const double *x0 = rmh_mesh_nodes(mesh);
+      std::vector<double> x(vel_nodes_host.size());
+      for (size_t i = 0; i < x.size(); i++) { x[i] = x0[i] + t * vel_nodes_host[i]; }   // remhos.cpp:1602
+      Check(rmh_mesh_save(mesh, path.c_str(), x.data(), precision));
+      return;
+   }
+   Check(rmh_mesh_save(mesh, path.c_str(), nullptr, precision));
+}
+
+void ParFiniteElementSpace::SaveGridFunction(const std::string &path, const std::vector<double> &vals,
+                                             int precision) const
+{
+   Check(rmh_gf_save(path.c_str(), dim, order, 2, (int64_t)vals.size(), vals.data(), precision));
+}
+
+void VisItDataCollection::Save() const
+{
+   char cyc[16], rk[16];
+   std::snprintf(cyc, sizeof(cyc), "%06d", cycle);
+   const int rank = pfes.comm ? pfes.comm->rank : 0, world = pfes.comm ? pfes.comm->world : 1;
+   std::snprintf(rk, sizeof(rk), "%06d", rank);
+   const std::string dir = name + "_" + cyc;
+   mkdir(dir.c_str(), 0755);
+   pfes.SaveMesh(dir + "/mesh." + rk, time, precision);
+   for (const auto &f : fields)
+   {
+      std::vector<double> h = f.second->HostRead();
+      h.resize((size_t)pfes.GetVSize());                     // block 0 of a product state
+      pfes.SaveGridFunction(dir + "/" + f.first + "." + rk, h, precision);
+   }
+   if (rank != 0) { return; }
+   std::ofstream root(dir + ".mfem_root");
+   root << "{\n  \"dsets\": {\n    \"main\": {\n      \"cycle\": " << cycle << ",\n      \"domains\": " << world
+        << ",\n      \"fields\": {\n";
+   for (size_t i = 0; i < fields.size(); i++)
+   {
+      root << "        \"" << fields[i].first << "\": {\n          \"path\": \"" << dir << "/" << fields[i].first
+           << ".%06d\",\n          \"tags\": {\n            \"assoc\": \"nodes\",\n            \"comps\": \"1\",\n"
+           << "            \"lod\": \"" << std::max(pfes.order, 1) << "\"\n          }\n        }"
+           << (i + 1 < fields.size() ? "," : "") << "\n";
+   }
+   root << "      },\n      \"mesh\": {\n        \"path\": \"" << dir << "/mesh.%06d\",\n        \"tags\": {\n"
+        << "          \"max_lods\": \"32\"\n        }\n      },\n      \"time\": " << std::setprecision(16) << time
+        << ",\n      \"time_step\": 0.0\n    }\n  }\n}\n";
 }
 
 double ParFiniteElementSpace::Reduce(double v, int op) const
@@ -981,6 +1032,25 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       mass0_u = pfes.Reduce(mass0_u, 0); u_min = pfes.Reduce(u_min, 1); u_max = pfes.Reduce(u_max, 2);   // MPI_Allreduce
       double mass0_us = 0.0;
       if (o.ps) { Check(rmh_reduce(pfes.ctx, 0, u.Block(1), lumpedM.Read(), &mass0_us, nullptr)); }   // :1079-1083
+      // Print the starting mesh and initial condition (remhos.cpp:1015-1030); VisIt collection (:1032-1043)
+      const int precision = 8;
+      if (o.save)
+      {
+         Verify(comm.world == 1, "-save writes one rank's files (PrintAsOne): run it on one GPU");
+         pfes.SaveMesh("meshHO_init.mesh", 0.0, precision);
+         std::vector<double> h = u.HostRead();
+         h.resize((size_t)NV);
+         pfes.SaveGridFunction("sltn_init.gf", h, precision);
+      }
+      VisItDataCollection *dc = nullptr;
+      if (o.visit)
+      {
+         dc = new VisItDataCollection("Remhos", pfes);
+         dc->SetPrecision(precision);
+         dc->RegisterField("solution", &u);
+         dc->SetCycle(0); dc->SetTime(0.0);
+         dc->Save();
+      }
       ODESolver ode_solver(o.ode);
       ode_solver.Init(adv);
       // the time loop below only reads the state between steps: the element min/max the last RK
@@ -1035,6 +1105,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
          {
             std::cout << "time step: " << ti << ", time: " << t << ", dt: " << dt
                       << ", residual: " << residual << std::endl;
+            if (dc) { dc->SetCycle(ti); dc->SetTime(t); dc->Save(); }   // remhos.cpp:1323-1328
          }
       }
       Check(rmh_sync(pfes.ctx));
@@ -1068,18 +1139,21 @@ int remhos(int argc, char *argv[], double &final_mass_u)
                    << "Max value s:   " << s_max << std::endl << std::setprecision(6)
                    << "Mass loss us:  " << std::abs(mass0_us - mass_us) << std::endl;
       }
-      if (o.save)
+      if (o.save)                                                        // remhos.cpp:1365-1380,1472-1482
       {
-         // sltn_final.gf in MFEM GridFunction text format (remhos.cpp:1366-1380)
-         FILE *fp = std::fopen("sltn_final.gf", "w");
-         if (fp)
+         pfes.SaveMesh("meshHO_final.mesh", t, precision);
+         std::vector<double> h = u.HostRead();
+         h.resize((size_t)NV);
+         pfes.SaveGridFunction("sltn_final.gf", h, precision);
+         if (smth_indicator)
          {
-            std::fprintf(fp, "FiniteElementSpace\nFiniteElementCollection: L2_T2_%dD_P%d\nVDim: 1\nOrdering: 0\n\n",
-                         pfes.dim, pfes.order);
-            for (double v : u.HostRead()) { std::fprintf(fp, "%.8g\n", v); }
-            std::fclose(fp);
+            Vector si_val(pfes), u0v(pfes);
+            Check(rmh_copy_d2d(pfes.ctx, u0v.Write(), u.Block(0), NV));
+            smth_indicator->ComputeSmoothnessIndicator(u0v, si_val);
+            pfes.SaveGridFunction("si_final.gf", si_val.HostRead(), precision);
          }
       }
+      delete dc;
       delete mono_solver; delete smth_indicator; delete fct_solver; delete lo_solver; delete ho_solver;   // remhos.cpp:1484-1489
    }
    rmh_mesh_free(mesh);

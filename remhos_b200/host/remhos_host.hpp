@@ -94,9 +94,13 @@ public:
    std::vector<double> u0;          // ProjectCoefficient(u0_function) (remhos.cpp:883)
    std::vector<double> xlat;        // lattice points i/p of every element at t = 0 [ne][nd][dim]
    std::vector<int32_t> bdr_dofs, nbr_elem;   // BdrDofs [nfd][nf]; face neighbours [ne][nf]
+   std::vector<double> vel_nodes_host;   // remap: mesh velocity at the nodes (the mesh at time t is x0 + t v)
    double dt_cfl = 0.0;
    double t_final = 0.0;
    bool subcells_ready = false;
+   // pmesh.Print of the mesh at time t (remap: moved nodes) / u.Save, in MFEM's formats (remhos.cpp:1016-1030)
+   void SaveMesh(const std::string &path, double t, int precision = 8) const;
+   void SaveGridFunction(const std::string &path, const std::vector<double> &vals, int precision = 8) const;
    // decomposed runs (comm.world > 1): `mesh` is this rank's owned part, the members below hold the rest
    Communicator *comm = nullptr;
    rmh_mesh *global_mesh = nullptr, *local_mesh = nullptr;   // local = owned + ghost ring
@@ -376,6 +380,26 @@ public:
    void Init(AdvectionOperator &op) { f = &op; }
    void Step(Vector &x, double &t, double &dt);
    int Stages() const;
+};
+
+// VisItDataCollection("Remhos", &pmesh) as the driver uses it (remhos.cpp:1034-1043,1323-1328): every
+// Save() writes <name>_<cycle>.mfem_root (JSON index) and <name>_<cycle>/{mesh,<field>}.<rank> in MFEM's
+// mesh / GridFunction formats, one domain per rank.
+class VisItDataCollection
+{
+   std::string name;
+   ParFiniteElementSpace &pfes;
+   std::vector<std::pair<std::string, const Vector *>> fields;
+   int cycle = 0, precision = 8;
+   double time = 0.0;
+public:
+   VisItDataCollection(const std::string &collection_name, ParFiniteElementSpace &space)
+      : name(collection_name), pfes(space) {}
+   void SetPrecision(int p) { precision = p; }
+   void RegisterField(const std::string &field_name, const Vector *gf) { fields.emplace_back(field_name, gf); }
+   void SetCycle(int c) { cycle = c; }
+   void SetTime(double t) { time = t; }
+   void Save() const;
 };
 
 // The driver (remhos.cpp:210): returns 0 ok, 1 bad flags, 3 unknown ODE solver.

@@ -333,3 +333,35 @@ def test_cli_nonlinear_penalty_matches_oracle():
     # (loose: the penalty solver amplifies one-ulp input differences, see tests/test_gpu_penalty.py)
     assert abs(got['mass'] - run.final_mass) < 1e-5 * abs(run.final_mass)
     assert abs(got['umax'] - run.final_max) < 1e-6
+
+
+@pytest.mark.gpu
+def test_cli_save_and_visit_write_mfem_files(tmp_path):
+    """-save: meshHO_init/final.mesh + sltn_init/final.gf (remhos.cpp:1016-1030,1366-1380); -visit: a
+    VisItDataCollection "Remhos" per visualisation step (:1034-1043,1323-1328).  Remap run, so the final
+    mesh is the moved one."""
+    import json
+    import remhos_b200 as rb
+    args = ['-no-vis', '-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-o', 2, '-dt', 0.01, '-tf', 0.1, '-ho', 3,
+            '-lo', 5, '-fct', 2, '-save', '-visit', '-vs', 5]
+    p = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=180, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    names = sorted(os.listdir(tmp_path))
+    for f in ('meshHO_init.mesh', 'meshHO_final.mesh', 'sltn_init.gf', 'sltn_final.gf', 'Remhos_000000.mfem_root',
+              'Remhos_000005.mfem_root', 'Remhos_000010.mfem_root'):
+        assert f in names, names
+    m0 = rb.Mesh.load(str(tmp_path / 'meshHO_init.mesh'))
+    m1 = rb.Mesh.load(str(tmp_path / 'meshHO_final.mesh'))
+    assert m0.ne == m1.ne == 64 and m0.geom_order == 2
+    assert np.abs(m0.nodes() - m1.nodes()).max() > 1e-3            # the remap mesh moved
+    ref = rb.Mesh.load(mesh('inline-quad.mesh')).refine(1)
+    ref.set_curvature(2)
+    assert np.abs(m0.nodes() - ref.nodes()).max() < 1e-7           # 8 digits written
+    gf = open(tmp_path / 'sltn_final.gf').read().split('\n')
+    assert gf[1] == 'FiniteElementCollection: L2_T2_2D_P2'
+    vals = np.array([float(v) for v in gf[5:] if v.strip()])
+    assert vals.size == 64 * 9 and abs(vals.max() - parse(p.stdout)['umax']) < 1e-7
+    root = json.load(open(tmp_path / 'Remhos_000010.mfem_root'))['dsets']['main']
+    assert root['cycle'] == 10 and root['domains'] == 1 and 'solution' in root['fields']
+    assert os.path.exists(tmp_path / (root['mesh']['path'] % 0)) and os.path.exists(tmp_path / (root['fields']['solution']['path'] % 0))
+    assert rb.Mesh.load(str(tmp_path / (root['mesh']['path'] % 0))).ne == 64

@@ -136,3 +136,40 @@ def test_nbr_lattice(name, structured):
     for f, (axis, side) in enumerate(faces):
         d = n3 // 2 + (1 if side else -1) * 3 ** axis
         assert np.array_equal(nbr[:, d], maps['nbr_elem'][:, f]), f
+
+
+@pytest.mark.parametrize('name,rs,g', [('periodic-cube.mesh', 1, 2), ('inline-quad.mesh', 1, 2), ('cube01_hex.mesh', 1, 3),
+                                       ('periodic-hexagon.mesh', 0, 2), ('periodic-square.mesh', 1, 1)])
+def test_mesh_save_round_trip(name, rs, g, tmp_path):
+    """rmh_mesh_save (Mesh::Print in "MFEM mesh v1.0", nodes as L2_T1 Gauss-Lobatto field; -save / -visit,
+    remhos.cpp:1016-1043): the file reads back to the same nodes, vertices and DofInfo maps through the
+    product's reader and through the oracle's, and lists exactly the faces without a neighbour as boundary"""
+    import ctypes as C
+    from remhos_b200.capi import lib, check
+    from remhos_oracle import mesh as om
+    m = rb.Mesh.load(os.path.join(DATA, name)).refine(rs)
+    m.set_curvature(g)
+    p = str(tmp_path / 'out.mesh')
+    check(lib().rmh_mesh_save(m.h, p.encode(), None, 17))
+    m2 = rb.Mesh.load(p)
+    assert m2.ne == m.ne and m2.geom_order == g
+    assert np.array_equal(m.nodes(), m2.nodes()) and np.array_equal(m.elem_vertices(), m2.elem_vertices())
+    a, b = m.dof_maps(2), m2.dof_maps(2)
+    for k in ('nbr_dof', 'lat', 'nbr_elem', 'bdr_dofs'):
+        assert np.array_equal(a[k], b[k]), k
+    mo = om.read_mesh(p)
+    assert mo.ne == m.ne and np.array_equal(mo.X, m.nodes())
+    txt = open(p).read()
+    nb = int(txt.split('boundary\n')[1].split('\n')[0])
+    assert nb == int((a['nbr_elem'] < 0).sum())
+    # moved nodes (remap) and the GridFunction writer
+    x = m.nodes() + 0.01
+    check(lib().rmh_mesh_save(m.h, p.encode(), x.ctypes.data_as(C.c_void_p), 17))
+    assert np.array_equal(rb.Mesh.load(p).nodes(), x)
+    vals = np.linspace(0.0, 1.0, 37)
+    g_path = str(tmp_path / 'u.gf')
+    check(lib().rmh_gf_save(g_path.encode(), m.dim, 3, 2, C.c_int64(vals.size), vals.ctypes.data_as(C.c_void_p), 17))
+    lines = open(g_path).read().split('\n')
+    assert lines[0] == 'FiniteElementSpace' and lines[1] == 'FiniteElementCollection: L2_T2_%dD_P3' % m.dim
+    assert lines[2] == 'VDim: 1' and lines[3] == 'Ordering: 0'
+    assert np.array_equal(np.array([float(v) for v in lines[5:5 + vals.size]]), vals)
