@@ -94,22 +94,33 @@ __global__ void __launch_bounds__(256) k_halo_put(const __grid_constant__ PutArg
    const PutPeer &P = a.peer[blockIdx.y];
    double *gtr = P.gtr[a.par];
    double2 *mm = P.mm[a.par];
-   const int64_t n = P.tr_n + P.mm_n;
-   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   // traces: four independent gather -> remote-store chains per thread and round
    {
-      if (i < P.tr_n) { gtr[a.tr_dst[P.tr_off + i]] = a.y[a.tr_src[P.tr_off + i]]; }
-      else
+      const int32_t *src = a.tr_src + P.tr_off, *dst = a.tr_dst + P.tr_off;
+      int64_t i = i0;
+      for (; i + 3 * stride < P.tr_n; i += 4 * stride)
       {
-         const int64_t k = P.mm_off + (i - P.tr_n);
-         const int32_t e = a.mm_src[k];
-         mm[a.mm_dst[k]] = a.mm_in ? a.mm_in[e] : make_double2(a.xe_min[e], a.xe_max[e]);
+         const int32_t s0 = src[i], s1 = src[i + stride], s2 = src[i + 2 * stride], s3 = src[i + 3 * stride];
+         const int32_t d0 = dst[i], d1 = dst[i + stride], d2 = dst[i + 2 * stride], d3 = dst[i + 3 * stride];
+         const double v0 = a.y[s0], v1 = a.y[s1], v2 = a.y[s2], v3 = a.y[s3];
+         gtr[d0] = v0; gtr[d1] = v1; gtr[d2] = v2; gtr[d3] = v3;
       }
+      for (; i < P.tr_n; i += stride) { gtr[dst[i]] = a.y[src[i]]; }
    }
-   // publish: all stores of the grid are ordered before the flag stores of the last block
-   __threadfence_system();
+   for (int64_t i = i0; i < P.mm_n; i += stride)
+   {
+      const int64_t k = P.mm_off + i;
+      const int32_t e = a.mm_src[k];
+      mm[a.mm_dst[k]] = a.mm_in ? a.mm_in[e] : make_double2(a.xe_min[e], a.xe_max[e]);
+   }
+   // publish: the block barrier orders every thread's stores before thread 0's system-scope fence
+   // (cumulativity, as in a grid-wide barrier); the last block to arrive stores the epoch flags
    __syncthreads();
    if (threadIdx.x == 0)
    {
+      __threadfence_system();
       const unsigned int total = gridDim.x * gridDim.y;
       const unsigned int t = atomicAdd(a.counter, 1u);
       if (t == total - 1)
@@ -363,7 +374,9 @@ extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, 
       A.mm_in = c->fold ? c->xe_mm2[par] : nullptr;
       A.xe_min = c->xe_min; A.xe_max = c->xe_max;
       const int bs = 256;
-      const int64_t nb = std::max<int64_t>(1, std::min<int64_t>((d->put_items_max + bs - 1) / bs, 4 * (int64_t)c->num_sms));
+      // about two blocks per SM over all peers: one wave, a handful of items per thread
+      const int64_t nb = std::max<int64_t>(1, std::min<int64_t>((d->put_items_max + 4 * bs - 1) / (4 * bs),
+                                                              std::max<int64_t>(1, 2 * (int64_t)c->num_sms / d->npeers)));
       k_halo_put<<<dim3((unsigned)nb, (unsigned)d->npeers), bs, 0, s>>>(A);
       LAUNCH_OK();
       if (!dist_in_kernel_wait(c, x0, y, out))
