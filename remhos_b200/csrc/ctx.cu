@@ -126,6 +126,7 @@ struct rmh_ctx
    // halo (multi-GPU, dist.cuh).  Faces with a ghost neighbour get one slot each: nbr_elem = ne + slot,
    // the neighbour's face trace (this element's natural face order) is ughost[slot][NFD].
    const double *ughost = nullptr;
+   const double *halo_ptr = nullptr;    // state whose ghost traces / (min,max) the window holds (unfused path)
    int64_t n_gslots = 0;
    std::vector<int32_t> gs_ghost, gs_pid;   // per slot: ghost element (0 .. ne_ghost-1), pattern id
    std::vector<int16_t> pat_h;              // host copy of the pattern table [npat][NFD]
@@ -158,6 +159,9 @@ struct rmh_ctx
 namespace rmh { struct StagePArgs; }
 // multi-GPU hook (dist.cuh): flags / epoch / shell range of the in-kernel halo wait
 static void dist_stage_args(rmh_ctx *c, rmh::StagePArgs &pa, bool in_kernel_wait);
+// decomposed meshes, unfused solver path: element min/max of u, then face traces + (min,max) pairs of u
+// exchanged with the peers (one put kernel + k_halo_wait); a no-op on a single rank
+static int dist_halo(rmh_ctx *c, const double *u, cudaStream_t s);
 
 template <typename Tp>
 static int dev_alloc(rmh_ctx *c, Tp **p, size_t n)
@@ -1998,6 +2002,7 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
    c->epoch++;
    const int par = (int)(c->epoch & 1);
    c->ughost = c->gtr[par];
+   c->halo_ptr = nullptr;
    // 3D meshes with constant-Jacobian elements: persistent pipelined kernels
    const bool use_p = c->pipelined && c->dim == 3 && c->all_affine &&
                       ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
@@ -2699,6 +2704,7 @@ static int mult_unlimited_1(rmh_ctx *c, int ho_type, int lo_type, int fct_type, 
    if (check_combo(ho_type, lo_type, fct_type)) { return 1; }
    if (k == u) { set_error("rmh_mult_unlimited: output must not alias the input"); return 1; }
    if (rmh_set_time(c, t, stream)) { return 1; }
+   if (dist_halo(c, u, (cudaStream_t)stream)) { return 1; }      // x_gf.ExchangeFaceNbrData() (remhos.cpp:1813)
    auto HO = [&](double *out)
    { return ho_type == 1 ? rmh_ho_neumann(c, u, out, stream) : rmh_ho_local_inverse(c, u, out, stream); };
    if (fct_type) { return HO(k); }
@@ -2756,6 +2762,7 @@ static int limit_mult_1(rmh_ctx *c, int lo_type, int fct_type, double dt, const 
    if (!fct_type || c->mono_type) { return 0; }            // remhos.cpp:1803: no FCT solver, nothing to limit
    if (check_combo(3, lo_type, fct_type)) { return 1; }
    if (k == u) { set_error("rmh_limit_mult: the rate must not alias the state"); return 1; }
+   if (c->halo_ptr != u) { if (dist_halo(c, u, (cudaStream_t)stream)) { return 1; } }
    for (int i = 3; i < 7; i++) { if (work_vec(c, &c->wk[i])) { return 1; } }
    double *du_ho = c->wk[3], *du_lo = c->wk[4], *xmn = c->wk[5], *xmx = c->wk[6];
    CUDA_OK(cudaMemcpyAsync(du_ho, k, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -3026,7 +3033,7 @@ extern "C" int rmh_mult(rmh_ctx *c, int ho_type, int lo_type, int fct_type, doub
                         const double *u, double *k, void *stream)
 {
    if (c->mono_type) { return rmh_mult_unlimited(c, ho_type, lo_type, fct_type, t, dt, u, k, stream); }
-   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control && !c->product && !c->si_type)
+   if (ho_type == 3 && lo_type == 5 && fct_type == 2 && !c->dt_control && !c->product && !c->si_type && !c->dist)
    {
       if (k == u) { set_error("rmh_mult: output must not alias the input"); return 1; }
       if (rmh_set_time(c, t, stream)) { return 1; }
@@ -3069,8 +3076,8 @@ extern "C" int rmh_ode_step(rmh_ctx *c, int ode, int ho_type, int lo_type, int f
 {
    cudaStream_t s = (cudaStream_t)stream;
    // (with automatic time step control the LO rate must be visible to the dt estimate: unfused path)
-   if (!c->mono_type && !c->dt_control && !c->product && !c->si_type && ho_type == 3 && lo_type == 5 && fct_type == 2 &&
-       ode >= 1 && ode <= 3)
+   if (!c->mono_type && !c->dt_control && !c->product && !c->si_type && !c->dist && ho_type == 3 && lo_type == 5 &&
+       fct_type == 2 && ode >= 1 && ode <= 3)
    { return rmh_rk_step(c, ode, lo_type, t, dt, u, stream); }
    const double t0 = *t;
    const size_t bytes = (size_t)state_len(c) * sizeof(double);

@@ -357,6 +357,9 @@ static bool dist_in_kernel_wait(const rmh_ctx *c, const double *x0, const double
           ((((uintptr_t)y | (uintptr_t)x0 | (uintptr_t)out) & 15) == 0);
 }
 
+static int dist_put(rmh_dist *d, const double *y, unsigned long long ep, bool pairs, cudaStream_t s);
+static int dist_wait(rmh_dist *d, unsigned long long ep, bool unpack, cudaStream_t s);
+
 // One RK stage on the decomposed mesh: out = a x0 + b (y + dt F(y)); the element min/max of y must be
 // in the context (rmh_stage_minmax, or left there by the previous stage)
 extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0,
@@ -366,28 +369,61 @@ extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, 
    if (!d->connected) { set_error("rmh_dist_rk_stage: not connected"); return 1; }
    cudaStream_t s = (cudaStream_t)stream;
    const unsigned long long ep = c->epoch + 1;
-   const int par = (int)(ep & 1);
    if (d->npeers > 0)
    {
-      PutArgs &A = d->put;
-      A.y = y; A.epoch = ep; A.par = par;
-      A.mm_in = c->fold ? c->xe_mm2[par] : nullptr;
-      A.xe_min = c->xe_min; A.xe_max = c->xe_max;
-      const int bs = 256;
-      // about two blocks per SM over all peers: one wave, a handful of items per thread
-      const int64_t nb = std::max<int64_t>(1, std::min<int64_t>((d->put_items_max + 4 * bs - 1) / (4 * bs),
-                                                              std::max<int64_t>(1, 2 * (int64_t)c->num_sms / d->npeers)));
-      k_halo_put<<<dim3((unsigned)nb, (unsigned)d->npeers), bs, 0, s>>>(A);
-      LAUNCH_OK();
-      if (!dist_in_kernel_wait(c, x0, y, out))
-      {
-         const int64_t nw = std::max<int64_t>(1, std::min<int64_t>((c->ne_ghost + bs - 1) / bs, 2 * (int64_t)c->num_sms));
-         k_halo_wait<<<(unsigned)nw, bs, 0, s>>>(c->flags, d->npeers, ep, c->fold ? 0 : c->ne_ghost,
-                                                 c->xe_mm2[par] + c->ne, c->xe_min + c->ne, c->xe_max + c->ne);
-         LAUNCH_OK();
-      }
+      if (dist_put(d, y, ep, c->fold, s)) { return 1; }
+      if (!dist_in_kernel_wait(c, x0, y, out)) { if (dist_wait(d, ep, !c->fold, s)) { return 1; } }
    }
    return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0, s);
+}
+
+static int dist_put(rmh_dist *d, const double *y, unsigned long long ep, bool pairs, cudaStream_t s)
+{
+   rmh_ctx *c = d->c;
+   const int par = (int)(ep & 1);
+   PutArgs &A = d->put;
+   A.y = y; A.epoch = ep; A.par = par;
+   A.mm_in = pairs ? c->xe_mm2[par] : nullptr;
+   A.xe_min = c->xe_min; A.xe_max = c->xe_max;
+   const int bs = 256;
+   // about two blocks per SM over all peers: one wave, a handful of items per thread
+   const int64_t nb = std::max<int64_t>(1, std::min<int64_t>((d->put_items_max + 4 * bs - 1) / (4 * bs),
+                                                           std::max<int64_t>(1, 2 * (int64_t)c->num_sms / d->npeers)));
+   k_halo_put<<<dim3((unsigned)nb, (unsigned)d->npeers), bs, 0, s>>>(A);
+   LAUNCH_OK();
+   return 0;
+}
+
+static int dist_wait(rmh_dist *d, unsigned long long ep, bool unpack, cudaStream_t s)
+{
+   rmh_ctx *c = d->c;
+   const int bs = 256, par = (int)(ep & 1);
+   const int64_t nw = std::max<int64_t>(1, std::min<int64_t>((c->ne_ghost + bs - 1) / bs, 2 * (int64_t)c->num_sms));
+   k_halo_wait<<<(unsigned)nw, bs, 0, s>>>(c->flags, d->npeers, ep, unpack ? c->ne_ghost : 0, c->xe_mm2[par] + c->ne,
+                                           c->xe_min + c->ne, c->xe_max + c->ne);
+   LAUNCH_OK();
+   return 0;
+}
+
+// ParGridFunction::ExchangeFaceNbrData + the shared min/max of DofInfo for the unfused solver path
+// (remhos.cpp:1813, remhos_tools.cpp:399,463-466): every solver entry point that reads neighbour traces
+// (HO, DU / RD face terms, Neumann) or ghost element bounds finds them in the window afterwards
+static int dist_halo(rmh_ctx *c, const double *u, cudaStream_t s)
+{
+   rmh_dist *d = c->dist;
+   if (!d || !d->connected) { return 0; }
+   c->xe_ptr = nullptr;
+   launch_elem_min_max(c->ne, c->ND, u, c->xe_min, c->xe_max, s);
+   LAUNCH_OK();
+   const unsigned long long ep = ++c->epoch;
+   if (d->npeers > 0)
+   {
+      if (dist_put(d, u, ep, false, s)) { return 1; }
+      if (dist_wait(d, ep, true, s)) { return 1; }
+   }
+   c->ughost = c->gtr[ep & 1];
+   c->halo_ptr = u;
+   return 0;
 }
 
 // ODESolver::Step for -s 1/2/3 on the decomposed mesh (cf. rmh_rk_step)

@@ -787,12 +787,14 @@ void ODESolver::Step(Vector &x, double &t, double &dt)
       t += dt;
       return;
    }
-   if (f->Space().dist)
+   if (f->Space().dist && type >= 1 && type <= 3 && f->HOType() == 3 && f->LOType() == 5 && f->FCTType() == 2 &&
+       !f->Space().dt_control_on)
    {
       // decomposed mesh: fused stage path with the halo exchange behind the C ABI (remhos.cpp:1813)
       Check(rmh_dist_rk_step(f->Space().dist, type, f->LOType(), &t, dt, x.ReadWrite(), nullptr));
       return;
    }
+   // (on a decomposed mesh rmh_ode_step exchanges the halo of every operator input itself)
    const int rc = rmh_ode_step(f->Space().ctx, type, f->HOType(), f->LOType(), f->FCTType(), &t, dt,
                                x.ReadWrite(), nullptr);
    Check(rc);
@@ -898,8 +900,12 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    if (!parse(argc, argv, o)) { usage(std::cout); return 1; }           // remhos.cpp:335-339
    if (comm.world > 1)
    {
-      Verify(o.ho == 3 && o.lo == 5 && o.fct == 2 && o.mono == 0 && o.ode >= 1 && o.ode <= 3 && !o.dtc && !o.vb,
-             "decomposed runs (WORLD_SIZE > 1) cover -ho 3 -lo 5 -fct 2 -s 1/2/3 (the fused stage path)");
+      // fused stage path for -ho 3 -lo 5 -fct 2 -s 1/2/3; every other combination runs solver by solver with
+      // one halo exchange per operator evaluation.  Not decomposed: the flux-based FCT (needs the neighbours'
+      // matrix blocks and the R+- exchanges, remhos_fct.cpp:406-409), the monolithic solver (serial in the
+      // reference too), smoothness indicators, product remap, the per-stage -vb checks.
+      Verify(o.fct != 1 && o.mono == 0 && o.si == 0 && !o.ps && !o.vb,
+             "decomposed runs (WORLD_SIZE > 1) do not cover -fct 1, -mono, -si, -ps and -vb");
    }
    // ---- combinations the reference rejects (Appendix A of SURVEY.md) or this build lacks
    if (!ODESolver::Known(o.ode))
@@ -1017,7 +1023,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       else if (o.fct == 2) { fct_solver = new ClipScaleSolver(pfes, dt); }
       else if (o.fct == 3) { fct_solver = new NonlinearPenaltySolver(pfes, smth_indicator, dt); }
       else if (o.fct == 4) { fct_solver = new ElementFCTProjection(pfes, dt); }
-      if (o.dtc) { Check(rmh_dt_control(pfes.ctx, 1)); }
+      if (o.dtc) { Check(rmh_dt_control(pfes.ctx, 1)); pfes.dt_control_on = true; }
       // monolithic solver (remhos.cpp:997-1011)
       MonolithicSolver *mono_solver = nullptr;
       const bool mass_lim = (o.problem != 6 && o.problem != 7);
@@ -1061,7 +1067,8 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       if (steady) { res_h = u.HostRead(); ml_h = lumpedM.HostRead(); }
       double t = 0.0, residual = 0.0;
       bool done = false;
-      int ti = 0;
+      int ti = 0, ti_total = 0;       // ti_total also counts the steps -dtc repeats (remhos.cpp:1142,1176)
+      const bool forced_bounds = (o.lo != 0 || o.mono != 0);            // remhos.cpp:593-594
       Check(rmh_sync(pfes.ctx));
       const auto w0 = std::chrono::steady_clock::now();
       while (!done)                                                      // remhos.cpp:1146-1330
@@ -1072,10 +1079,12 @@ int remhos(int argc, char *argv[], double &final_mass_u)
          if (o.dtc) { Check(rmh_dt_ratio(pfes.ctx, 1, nullptr)); }    // ResetTimeStepRatio
          ode_solver.Step(u, t, dt_real);
          ti++;
+         ti_total++;
          if (o.dtc)                                                    // remhos.cpp:1178-1197
          {
             double dt_ratio = 0.0;
             Check(rmh_dt_ratio(pfes.ctx, 0, &dt_ratio));
+            dt_ratio = pfes.Reduce(dt_ratio, 1);                        // MPI_MIN (remhos.cpp:1990-1996)
             if (dt_ratio < 1.)
             {
                std::cout << "Repeat / decrease dt: " << dt_real << " --> " << 0.85 * dt << std::endl;
@@ -1087,6 +1096,27 @@ int remhos(int argc, char *argv[], double &final_mass_u)
             else if (dt_ratio > 1.25) { dt *= 1.02; }
             delete u_old;
          }
+         // Monotonicity check (remhos.cpp:1218-1260): global extrema against the previous step's
+         if (o.vb && forced_bounds && smth_indicator == nullptr)
+         {
+            const double eps = 1e-10;
+            double mn = 0.0, mx = 0.0;
+            Check(rmh_reduce(pfes.ctx, 1, u.Read(), nullptr, &mn, nullptr));
+            Check(rmh_reduce(pfes.ctx, 2, u.Read(), nullptr, &mx, nullptr));
+            mn = pfes.Reduce(mn, 1); mx = pfes.Reduce(mx, 2);
+            auto msg = [](const char *what, double v) { std::ostringstream os; os << what << v; return os.str(); };
+            if (o.problem % 10 != 6 && o.problem % 10 != 7)
+            {
+               Verify(mn > u_min - eps, msg("Undershoot of ", u_min - mn));
+               Verify(mx < u_max + eps, msg("Overshoot of ", mx - u_max));
+               u_min = mn; u_max = mx;
+            }
+            else
+            {
+               Verify(mn > 0.0 - eps, msg("Undershoot of ", 0.0 - mn));
+               Verify(mx < 1.0 + eps, msg("Overshoot of ", mx - 1.0));
+            }
+         }
          if (!steady) { done = (t >= t_final - 1.e-8 * dt); }
          else
          {
@@ -1096,11 +1126,11 @@ int remhos(int argc, char *argv[], double &final_mass_u)
             {
                r += std::pow((ml_h[i] * uh[i] / dt) - (ml_h[i] * res_h[i] / dt), 2.);
             }
-            residual = std::sqrt(r);
+            residual = std::sqrt(pfes.Reduce(r, 0));                    // MPI_SUM (remhos.cpp:1288)
             if (residual < 1.e-12 && t >= 1.) { done = true; u.SetFromHost(res_h); }
             else { res_h = uh; }
          }
-         if (ti == o.max_steps) { done = true; }
+         if (ti_total == o.max_steps) { done = true; }                 // remhos.cpp:1296
          if (done || ti % o.vis_steps == 0)
          {
             std::cout << "time step: " << ti << ", time: " << t << ", dt: " << dt
@@ -1110,7 +1140,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       }
       Check(rmh_sync(pfes.ctx));
       const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
-      adv.PrintTimingData(ti * ode_solver.Stages(), wall);
+      adv.PrintTimingData(ti_total * ode_solver.Stages(), wall);      // remhos.cpp:1340-1348
       // final mass on the final mesh (remhos.cpp:1382-1415)
       if (pfes.exec_mode == 1)
       {

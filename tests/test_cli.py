@@ -365,3 +365,50 @@ def test_cli_save_and_visit_write_mfem_files(tmp_path):
     assert root['cycle'] == 10 and root['domains'] == 1 and 'solution' in root['fields']
     assert os.path.exists(tmp_path / (root['mesh']['path'] % 0)) and os.path.exists(tmp_path / (root['fields']['solution']['path'] % 0))
     assert rb.Mesh.load(str(tmp_path / (root['mesh']['path'] % 0))).ne == 64
+
+
+DECOMP_GENERAL = [
+    ('periodic-square.mesh', ['-p', 5, '-rs', 3, '-o', 2, '-dt', 0.004, '-tf', 0.04, '-ho', 3, '-lo', 3, '-fct', 2]),
+    ('periodic-square.mesh', ['-p', 5, '-rs', 3, '-o', 2, '-dt', 0.004, '-tf', 0.04, '-ho', 3, '-lo', 1, '-fct', 2, '-s', 2]),
+    ('periodic-hexagon.mesh', ['-p', 0, '-rs', 2, '-o', 2, '-dt', 0.005, '-tf', 0.05, '-ho', 1, '-lo', 2, '-fct', 2]),
+    ('periodic-cube.mesh', ['-p', 0, '-rs', 1, '-o', 2, '-dt', 0.01, '-tf', 0.05, '-ho', 3, '-lo', 4, '-fct', 2]),
+    ('periodic-square.mesh', ['-p', 5, '-rs', 3, '-o', 3, '-dt', 0.004, '-tf', 0.04, '-ho', 3, '-lo', 5, '-fct', 4, '-s', 13]),
+    ('periodic-cube.mesh', ['-p', 1, '-rs', 1, '-o', 3, '-dt', 0.01, '-tf', 0.05, '-ho', 3, '-lo', 5, '-fct', 2, '-s', 4, '-pa']),
+    ('periodic-square.mesh', ['-p', 5, '-rs', 3, '-o', 2, '-dt', 0.01, '-tf', 0.08, '-ho', 3, '-lo', 5, '-fct', 4, '-bt', 1, '-dtc', 1]),
+    ('periodic-square.mesh', ['-p', 5, '-rs', 2, '-o', 2, '-dt', 0.004, '-tf', 0.02, '-ho', 3, '-lo', 3, '-fct', 0]),
+    ('inline-quad.mesh', ['-p', 4, '-rs', 2, '-o', 2, '-dt', 0.002, '-tf', 0.02, '-ho', 3, '-lo', 1, '-fct', 2]),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mesh_name,flags', DECOMP_GENERAL,
+                         ids=['RD-clipscale', 'DU-clipscale-rk2', 'hexagon-Neumann-DUprec', 'cube-RDsub', 'idp3-fctproject',
+                              'cube-rk4-rotation', 'dtc', 'LO-only', 'inline-quad-boundary'])
+def test_cli_decomposed_solver_by_solver(mesh_name, flags):
+    """Decomposed runs of the matrix-based / unfused solver combinations (DU, RD, subcell RD, Neumann,
+    FCTProject, IDP and RK4 time stepping, automatic dt): `remhos -gpus 2` against the single-GPU run.
+    One halo exchange (face traces + ghost (min,max)) per operator evaluation replaces the
+    ExchangeFaceNbrData calls of remhos_lo.cpp:57,131 / remhos_tools.cpp:399 / remhos.cpp:1813."""
+    torch = pytest.importorskip('torch')
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    args = ['-no-vis', '-m', mesh(mesh_name)] + flags
+    rc1, out1, err1 = run_cli(*args)
+    assert rc1 == 0, err1
+    rc2, out2, err2 = run_cli(*args, '-gpus', 2)
+    assert rc2 == 0, out2[-2000:] + err2[-2000:]
+    a, b = parse(out1), parse(out2)
+    assert a['n'] == b['n']
+    assert abs(a['mass'] - b['mass']) <= 1e-10 * abs(a['mass'])
+    assert abs(a['umax'] - b['umax']) <= 1e-10 * max(abs(a['umax']), 1e-300)
+    if '-dtc' in flags:
+        assert out1.count('Repeat / decrease dt') == out2.count('Repeat / decrease dt')
+
+
+@pytest.mark.gpu
+def test_cli_decomposed_rejections():
+    torch = pytest.importorskip('torch')
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    rc, out, err = run_cli('-no-vis', '-m', mesh('periodic-square.mesh'), '-p', 5, '-ho', 3, '-lo', 1, '-fct', 1, '-gpus', 2)
+    assert rc == 134 and 'decomposed runs' in err
