@@ -1054,7 +1054,8 @@ static int launch_ho_E(rmh_ctx *c, const HoArgs &a, cudaStream_t s)
          for (int j = 0; j < D1; j++) { v += c->hMinv[i * D1 + j] * c->hB[q * D1 + j]; }
          tab.C[i][q] = v;
       }
-   static bool attr_set = false;
+   static bool attr_set_dev[RMH_MAX_DEVICES] = {false};     // function attributes are per device
+   bool &attr_set = attr_set_dev[c->device % RMH_MAX_DEVICES];
    if (!attr_set)
    {
       CUDA_OK(cudaFuncSetAttribute(k_ho<DIM, D1, Q, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1119,7 +1120,8 @@ static int launch_stage_EA(rmh_ctx *c, const StageArgs &a, cudaStream_t s)
          for (int j = 0; j < D1; j++) { v += c->hMinv[i * D1 + j] * c->hB[q * D1 + j]; }
          tab.C[i][q] = v;
       }
-   static bool attr_set = false;
+   static bool attr_set_dev[RMH_MAX_DEVICES] = {false};
+   bool &attr_set = attr_set_dev[c->device % RMH_MAX_DEVICES];
    if (!attr_set)
    {
       CUDA_OK(cudaFuncSetAttribute(k_stage<DIM, D1, Q, E, AFF>,
@@ -1183,7 +1185,8 @@ static int launch_stagep_E(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    using S = SmemP<D1, Q, E>;
    constexpr int MINB0 = (int)((227 * 1024) / (S::BYTES + 1024));
    constexpr int MINB = MINB0 < 1 ? 1 : (MINB0 > 3 ? 3 : MINB0);
-   static int blocks_per_sm = 0;
+   static int blocks_per_sm_dev[RMH_MAX_DEVICES] = {0};
+   int &blocks_per_sm = blocks_per_sm_dev[c->device % RMH_MAX_DEVICES];
    if (blocks_per_sm == 0)
    {
       CUDA_OK(cudaFuncSetAttribute(k_stage3p<D1, Q, E, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1237,7 +1240,8 @@ static int launch_stagew_L(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    using S = SmemW<D1, Q>;
    constexpr size_t BYTES = S::bytes(NW);
-   static int blocks_per_sm = 0;
+   static int blocks_per_sm_dev[RMH_MAX_DEVICES] = {0};
+   int &blocks_per_sm = blocks_per_sm_dev[c->device % RMH_MAX_DEVICES];
    if (blocks_per_sm == 0)
    {
       CUDA_OK(cudaFuncSetAttribute(k_stage3w<D1, Q, NW, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2640,7 +2644,8 @@ extern "C" int rmh_mono_rd(rmh_ctx *c, const double *u, double *du, void *stream
    for (int a = 0; a < c->dim; a++) { ns *= c->p; }
    const int wpb = 2;
    const size_t shb = (size_t)wpb * (8 * c->ND + 3 * c->NFD + ns * 6) * sizeof(double);
-   static bool attr = false;
+   static bool attr_dev[RMH_MAX_DEVICES] = {false};
+   bool &attr = attr_dev[c->device % RMH_MAX_DEVICES];
    if (!attr)
    {
       CUDA_OK(cudaFuncSetAttribute(k_mono_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

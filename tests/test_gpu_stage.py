@@ -224,3 +224,31 @@ def test_const_kernel_edge_cases(mesh, rs, order, bt):
     run.run()
     assert rel_err(ud.cpu().numpy().reshape(run.u.shape), run.u) < (1e-12 if order <= 3 else 1e-10)
     ctx.close()
+
+
+@pytest.mark.parametrize('env,flags', [({'RMH_NO_TENSOR': '1'}, 1), ({'RMH_NO_PIPELINE': '1'}, None)],
+                         ids=['dfma-pipelined-k_stage3p', 'one-batch-per-block-k_stage'])
+@pytest.mark.parametrize('order,bt', [(3, 0), (2, 1), (4, 0)])
+def test_fallback_stage_kernels(env, flags, order, bt, monkeypatch):
+    """the two fall-back fused stage kernels of affine 3D meshes stay correct: k_stage3p (DFMA,
+    persistent, RMH_NO_TENSOR=1: stored quadrature data in the generic order) and k_stage (the
+    non-affine / 2D kernel, RMH_NO_PIPELINE=1)"""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    run = oracle_run('periodic-cube.mesh', ho_type=3, lo_type=5, fct_type=2, problem=1, rs_levels=1, order=order,
+                     dt=0.005, bounds_type=bt, max_steps=2)
+    ctx = ctx_from_oracle(run)
+    if flags is not None:
+        assert ctx.path_flags == flags, ctx.path_flags          # affine, generic data order, no DMMA / const kernel
+    rng = np.random.default_rng(3)
+    u = np.clip(run.u + 0.02 * rng.standard_normal(run.u.shape), 0.0, None)
+    k = torch.empty(ctx.ndofs, dtype=torch.float64, device='cuda')
+    ctx.stage(5, run.dt, dev(u), k)
+    assert rel_err(k.cpu().numpy().reshape(u.shape), run.mult(u, 0.0, run.dt)) < (1e-10 if order <= 3 else 1e-8)
+    ud = dev(run.u)
+    t = 0.0
+    for _ in range(2):
+        t = ctx.rk_step(3, 5, t, run.dt, ud)
+    run.run()
+    assert rel_err(ud.cpu().numpy().reshape(run.u.shape), run.u) < (1e-12 if order <= 3 else 1e-10)
+    ctx.close()
