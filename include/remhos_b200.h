@@ -252,8 +252,9 @@ int rmh_subcell_setup(rmh_ctx *ctx, const double *xlat_host, const double *vel_h
 int rmh_lo_res_dist_subcell(rmh_ctx *ctx, const double *u_dev, double *du_lo_dev, void *stream);
 
 /* SmoothnessIndicator (remhos_tools.hpp; remhos_tools.cpp:24-354; created at remhos.cpp:905-911):
- * si_type 1 or 2 (-si), 0 removes it.  Built for order-1 spaces (the configuration of the
- * reference's monolithic-solver known answers); while set, rmh_mono_rd uses it as
+ * si_type 1 or 2 (-si), 0 removes it.  Any order: the H1 operators live on the subcell mesh (one dof per
+ * distinct lattice point; order 1 = the configuration of the reference's monolithic-solver known
+ * answers); while set, rmh_mono_rd uses it as
  * remhos_mono.cpp:132-153,300-324 do.  rmh_si_values = ComputeSmoothnessIndicator followed by the
  * DG2CG gather: one value per DG dof (1 on the domain boundary); out_dev may be NULL. */
 int rmh_si_setup(rmh_ctx *ctx, int si_type, void *stream);

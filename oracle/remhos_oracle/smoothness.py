@@ -1,6 +1,6 @@
-"""TEST INFRASTRUCTURE (oracle): SmoothnessIndicator of remhos_tools.cpp:24-354 for order-1 spaces
-(`-si 1|2` with `-o 1`, the configuration of the reference's two monolithic-solver known answers,
-autotest/out_baseline.dat:212-220).
+"""TEST INFRASTRUCTURE (oracle): SmoothnessIndicator of remhos_tools.cpp:24-354 (`-si 1|2`).  Pinned for
+`-o 1` by the reference's two monolithic-solver known answers (autotest/out_baseline.dat:212-220);
+orders above 1 follow the same statements on the subcell mesh and have no reference number.
 
 For order 1 the "subcell mesh" is the mesh itself (remhos.cpp:870) and the H1 space of
 positive order-1 elements has one DOF per mesh vertex; ShapeEval is the identity (Bernstein
@@ -24,31 +24,37 @@ from . import fe
 
 
 class SmoothnessIndicator:
+    """Any order p >= 1.  The H1 space is the positive order-1 space on the SUBCELL mesh (every element
+    split into p^dim subcells whose vertices are the lattice points i/p, remhos.cpp:797-868): one DOF
+    per distinct lattice point.  The DG solution enters through its values at the lattice points
+    (ShapeEval, remhos_tools.cpp:107-125) and the subcell Q1 mass blocks (ComputeVariationalMatrix,
+    :192-237); for p = 1 the subcell mesh is the mesh and ShapeEval the identity."""
+
     def __init__(self, run, si_type):
         sp, m, topo = run.space, run.mesh, run.topo
-        if sp.p != 1:
-            raise NotImplementedError('smoothness indicator: order 1 only')
         assert si_type in (1, 2), 'Bad smoothness indicator id!'
         self.type = si_type
         self.param = 5.0 if si_type == 1 else 3.0
-        dim, ne = sp.dim, m.ne
+        dim, ne, p, nd = sp.dim, m.ne, sp.p, sp.nd
         nv = 2 ** dim
-        g1 = sp.g + 1
-        # corner nodes of the geometry and DG dof -> H1 dof (vertex) map, lexicographic corners
-        corner_node = np.zeros(nv, dtype=int)
-        corner_lat = np.zeros(nv, dtype=int)
-        for j in range(nv):
-            n = t = 0
-            for a in reversed(range(dim)):
-                b = (j >> a) & 1
-                n = n * g1 + b * sp.g
-                t = t * 3 + 2 * b
-            corner_node[j], corner_lat[j] = n, t
-        ent = topo.lat[:, corner_lat]                                   # [ne, nv] vertex entity ids
-        uniq, cg = np.unique(ent.reshape(-1), return_inverse=True)
-        self.N = uniq.size
-        self.cg = cg.reshape(ne, nv)                                    # element -> H1 dofs
-        Xc = m.X[:, corner_node, :]                                     # [ne, nv, dim]
+        from . import dg
+        from .dg import FACE_AXIS
+        import scipy.sparse as sps
+        from scipy.sparse.csgraph import connected_components
+        # H1 dofs = classes of coincident lattice points: DG dof (e, BdrDofs(j, f)) coincides with
+        # NbrDof(e, f, j) (remhos_tools.cpp:525-676); the classes are the connected components
+        nbr = run.disc.nbr                                              # [ne, nf, nfd]
+        own = (np.arange(ne)[:, None, None] * nd + sp.bd.T[None, :, :])  # [ne, nf, nfd]
+        ok = nbr >= 0
+        N_dg = ne * nd
+        G = sps.coo_matrix((np.ones(ok.sum()), (own[ok], nbr[ok])), shape=(N_dg, N_dg))
+        self.N, lab = connected_components(G, directed=False)
+        cg_dof = lab.reshape(ne, nd)                                    # DG dof -> H1 dof
+        s2i = dg.sub2ind(p, dim)                                        # [nsub, nv] lexicographic corners
+        nsub = s2i.shape[0]
+        self.cg = cg_dof[:, s2i]                                        # [ne, nsub, nv]
+        xlat = sp.dof_points(m.X)                                       # [ne, nd, dim]
+        Xc = xlat[:, s2i, :].reshape(ne * nsub, nv, dim)                # subcell corners
         # Q1 shape functions and gradients on a 3-point Gauss rule
         xq, wq = fe.gauss_legendre_01(3)
         L = fe.lagrange(np.array([0.0, 1.0]), xq)                        # [3, 2]
@@ -63,14 +69,15 @@ class SmoothnessIndicator:
         wdet = wt[None, :] * np.abs(det)
         Me = np.einsum('eq,qi,qj->eij', wdet, Phi, Phi)
         Ke = -np.einsum('eq,eqid,eqjd->eij', wdet, grad, grad)
-        # boundary faces: + <dn phi_j, phi_i>
+        # subcell faces on the domain boundary: + <dn phi_j, phi_i>
         xf, wf = fe.gauss_legendre_01(3)
-        from .dg import FACE_AXIS
+        sub_lat = dg.dof_lattice(p - 1, dim) if p > 1 else np.zeros((1, dim), dtype=int)   # [nsub, dim]
         for f in range(sp.nf):
-            bnd = topo.nbr_elem[:, f] < 0
+            axis, side = FACE_AXIS[dim][f]
+            touches = sub_lat[:, axis] == (p - 1 if side else 0)        # subcells on element face f
+            bnd = ((topo.nbr_elem[:, f] < 0)[:, None] & touches[None, :]).reshape(-1)
             if not bnd.any():
                 continue
-            axis, side = FACE_AXIS[dim][f]
             one = np.array([float(side)])
             Ls = [fe.lagrange(np.array([0.0, 1.0]), one if b == axis else xf) for b in range(dim)]
             dLs = [[fe.lagrange_deriv(np.array([0.0, 1.0]), one if b == axis else xf) if a == b
@@ -85,27 +92,29 @@ class SmoothnessIndicator:
             gradf = np.einsum('aqn,eqai->eqni', np.stack(dPf), Jfi)
             # outward normal times surface element: sign * det(J) * J^-T e_axis
             nrm = (1.0 if side else -1.0) * detf[:, :, None] * Jfi[:, :, axis, :]
-            if dim == 2 or dim == 3:
-                dn = np.einsum('eqni,eqi->eqn', gradf, nrm)             # (grad phi_j . n) dS / w
+            dn = np.einsum('eqni,eqi->eqn', gradf, nrm)                 # (grad phi_j . n) dS / w
             Bf = np.einsum('q,eqi,eqj->eij', wft, Pf[None, :, :].repeat(bnd.sum(), 0), dn)
             Ke[bnd] += Bf
-        # assemble (dense is fine at oracle sizes; keep CSR-like structures via index lists)
         N = self.N
-        rows = np.repeat(self.cg[:, :, None], nv, axis=2).reshape(-1)
-        cols = np.repeat(self.cg[:, None, :], nv, axis=1).reshape(-1)
-        import scipy.sparse as sps
+        cgs = self.cg.reshape(ne * nsub, nv)
+        rows = np.repeat(cgs[:, :, None], nv, axis=2).reshape(-1)
+        cols = np.repeat(cgs[:, None, :], nv, axis=1).reshape(-1)
         self.M = sps.csr_matrix((Me.reshape(-1), (rows, cols)), shape=(N, N))
         self.M.sum_duplicates()
         self.Lap = sps.csr_matrix((Ke.reshape(-1), (rows, cols)), shape=(N, N))
         self.Lap.sum_duplicates()
         self.ml = np.asarray(self.M.sum(axis=1)).reshape(-1)            # LumpedIntegrator: row sums
-        # MassMixed: rows H1 dofs, columns DG dofs (same corner order: the "switchero" of :76-92
-        # only translates MFEM's counter-clockwise vertex order into the lexicographic DG order)
-        dgcol = (np.arange(ne)[:, None] * sp.nd + np.arange(nv)[None, :])
+        # MassMixed: rows H1 dofs, columns the lattice-point values of the DG field (the "switchero" of
+        # :76-92 only translates MFEM's counter-clockwise vertex order into the lexicographic DG order)
+        dgcol = (np.arange(ne)[:, None, None] * nd + s2i[None, :, :]).reshape(ne * nsub, nv)
         mc = np.repeat(dgcol[:, None, :], nv, axis=1).reshape(-1)
-        self.Mmix = sps.csr_matrix((Me.reshape(-1), (rows, mc)), shape=(N, ne * sp.nd))
+        self.Mmix = sps.csr_matrix((Me.reshape(-1), (rows, mc)), shape=(N, ne * nd))
+        self.Mmix.sum_duplicates()
+        # ShapeEval: Bernstein coefficients -> values at the closed uniform points (:107-125)
+        lat_pts = np.arange(p + 1) / max(p, 1)
+        self.V = fe.tensor_basis([fe.bernstein(p, lat_pts)] * dim)       # [nd points, nd coefficients]
         # DG2CG: H1 dof of every DG dof, -1 on the domain boundary (:94-105)
-        d2c = self.cg.copy()
+        d2c = cg_dof.copy()
         for f in range(sp.nf):
             bnd = topo.nbr_elem[:, f] < 0
             if bnd.any():
@@ -126,7 +135,7 @@ class SmoothnessIndicator:
 
     def compute(self, u):
         """u: [ne, nd] DG coefficients -> si per H1 dof [N]"""
-        rhs = self.Mmix @ u.reshape(-1)
+        rhs = self.Mmix @ (u @ self.V.T).reshape(-1)                    # xEval = ShapeEval u, element by element
         y = self._solve2(rhs)
         g = self._solve2(self.Lap @ y)
         gmin = np.minimum.reduceat(g[self.pJ], self.pI[:-1])

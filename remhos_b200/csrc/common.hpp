@@ -27,6 +27,8 @@ std::vector<double> invert_small(const std::vector<double> &A, int n);
 
 void face_axis(int dim, int f, int &axis, int &side);
 void bdr_dofs(int p, int dim, std::vector<int> &bd);
+// Sub2Ind [p^dim][2^dim]: DG dofs of the lexicographic corners of every subcell (remhos_tools.cpp:678-734)
+void sub2ind(int p, int dim, std::vector<int> &s);
 // natural face order (remaining axes ascending, first fastest) -> row of BdrDofs: [nf][nfd]
 void nat2ref_table(int p, int dim, std::vector<int> &n2r);
 // rmh_nbr_lattice restricted to the first ne_rows elements (the owned ones of a decomposed mesh;

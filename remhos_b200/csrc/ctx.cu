@@ -2453,66 +2453,135 @@ extern "C" int rmh_si_setup(rmh_ctx *c, int si_type, void *stream)
 {
    if (si_type == 0) { c->si_type = 0; return 0; }
    if (si_type != 1 && si_type != 2) { set_error("Bad smoothness indicator id!"); return 1; }   // remhos_tools.cpp:36
-   if (c->p != 1) { set_error("rmh_si_setup: the smoothness indicator is built for order 1 only"); return 1; }
-   if (!c->lat) { set_error("rmh_si_setup: needs the lattice entity map (bounds_type 0)"); return 1; }
    if (c->ne_ghost > 0) { set_error("rmh_si_setup: decomposed meshes are not supported"); return 1; }
-   const int dim = c->dim, nv = 1 << dim, NF = c->NF, ND = c->ND;
+   // Any order: the H1 space is the positive order-1 space on the SUBCELL mesh (p^dim subcells per element,
+   // vertices = the lattice points i/p; for p = 1 the mesh itself), one dof per distinct lattice point.
+   const int dim = c->dim, nv = 1 << dim, NF = c->NF, ND = c->ND, NFD = c->NFD, p = c->p, D1 = c->D1;
    const int64_t ne = c->ne;
    std::vector<double> X((size_t)ne * c->NGN * dim);
-   std::vector<int32_t> lat((size_t)ne * c->N3), nbe((size_t)ne * NF);
+   std::vector<int32_t> nbe((size_t)ne * NF);
+   std::vector<uint8_t> npat((size_t)ne * NF);
    CUDA_OK(cudaMemcpy(X.data(), c->X0, X.size() * sizeof(double), cudaMemcpyDeviceToHost));
-   CUDA_OK(cudaMemcpy(lat.data(), c->lat, lat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
    CUDA_OK(cudaMemcpy(nbe.data(), c->nbr_elem, nbe.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-   // corner j (bit a = coordinate a): geometry node and lattice entity position
-   int cnode[8], clat[8];
-   for (int j = 0; j < nv; j++)
+   CUDA_OK(cudaMemcpy(npat.data(), c->nbr_pat, npat.size(), cudaMemcpyDeviceToHost));
+   // ---- H1 dofs: classes of coincident lattice points.  DG dof (e, face dof j of face f) coincides with
+   // the neighbour's dof pat[pid][j] (NbrDof, remhos_tools.cpp:525-676): union-find over the face pairs
+   std::vector<int32_t> parent((size_t)ne * ND);
+   for (size_t i = 0; i < parent.size(); i++) { parent[i] = (int32_t)i; }
+   auto find = [&](int32_t x)
    {
-      int n = 0, t = 0;
-      for (int a = dim - 1; a >= 0; a--)
+      while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+      return x;
+   };
+   for (int64_t e = 0; e < ne; e++)
+      for (int f = 0; f < NF; f++)
       {
-         const int b = (j >> a) & 1;
-         n = n * c->NG1 + b * (c->NG1 - 1);
-         t = t * 3 + 2 * b;
+         const int32_t nb = nbe[e * NF + f];
+         if (nb < 0) { continue; }
+         int axis, side;
+         face_axis(dim, f, axis, side);
+         for (int j = 0; j < NFD; j++)
+         {
+            int l[3] = {0, 0, 0}, m = j;
+            for (int a = 0; a < dim; a++)
+            {
+               if (a == axis) { l[a] = side * p; }
+               else { l[a] = m % D1; m /= D1; }
+            }
+            const int own = l[0] + D1 * (l[1] + D1 * l[2]);
+            const int32_t x = find((int32_t)(e * ND + own));
+            const int32_t y = find((int32_t)(nb * ND + c->pat_h[(size_t)npat[e * NF + f] * NFD + j]));
+            if (x != y) { parent[std::max(x, y)] = std::min(x, y); }
+         }
       }
-      cnode[j] = n; clat[j] = t;
+   std::vector<int32_t> cgdof((size_t)ne * ND);
+   int N = 0;
+   {
+      std::vector<int32_t> root_id((size_t)ne * ND, -1);
+      for (size_t i = 0; i < cgdof.size(); i++)
+      {
+         const int32_t r = find((int32_t)i);
+         if (root_id[r] < 0) { root_id[r] = N++; }
+         cgdof[i] = root_id[r];
+      }
    }
-   // H1 dofs = the vertex entities that occur, compactly numbered in ascending entity id
-   std::vector<int32_t> ids;
-   ids.reserve((size_t)ne * nv);
-   for (int64_t e = 0; e < ne; e++) for (int j = 0; j < nv; j++) { ids.push_back(lat[e * c->N3 + clat[j]]); }
-   std::vector<int32_t> uniq(ids);
-   std::sort(uniq.begin(), uniq.end());
-   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-   const int N = (int)uniq.size();
-   std::vector<int32_t> cg(ids.size());
-   for (size_t i = 0; i < ids.size(); i++)
-   { cg[i] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), ids[i]) - uniq.begin()); }
+   // ---- lattice point coordinates (subcell vertices) and ShapeEval (Bernstein -> lattice values, :107-125)
+   std::vector<double> lat1((size_t)D1);
+   for (int i = 0; i < D1; i++) { lat1[i] = (double)i / std::max(p, 1); }
+   const std::vector<double> gll = gauss_lobatto_01(c->NG1);
+   const std::vector<double> Lg = lagrange(gll, lat1);            // [D1][NG1]
+   const std::vector<double> Bl = bernstein(p, lat1);             // [D1 points][D1 coefficients]
+   std::vector<double> xlat((size_t)ne * ND * dim, 0.0);
+   for (int64_t e = 0; e < ne; e++)
+      for (int j = 0; j < ND; j++)
+      {
+         int lj[3] = {0, 0, 0}, r = j;
+         for (int a = 0; a < dim; a++) { lj[a] = r % D1; r /= D1; }
+         for (int n = 0; n < c->NGN; n++)
+         {
+            int ln[3] = {0, 0, 0}, q = n;
+            double w = 1.0;
+            for (int a = 0; a < dim; a++) { ln[a] = q % c->NG1; q /= c->NG1; w *= Lg[lj[a] * c->NG1 + ln[a]]; }
+            if (w == 0.0) { continue; }
+            for (int i = 0; i < dim; i++) { xlat[((size_t)e * ND + j) * dim + i] += w * X[((size_t)e * c->NGN + n) * dim + i]; }
+         }
+      }
+   std::vector<double> V((size_t)ND * ND);                        // [lattice point][coefficient]
+   for (int l = 0; l < ND; l++)
+      for (int k = 0; k < ND; k++)
+      {
+         int ll[3] = {0, 0, 0}, kk[3] = {0, 0, 0}, r = l, q = k;
+         double w = 1.0;
+         for (int a = 0; a < dim; a++) { ll[a] = r % D1; r /= D1; kk[a] = q % D1; q /= D1; w *= Bl[ll[a] * D1 + kk[a]]; }
+         V[(size_t)l * ND + k] = w;
+      }
+   std::vector<int> s2i;
+   sub2ind(p, dim, s2i);
+   int nsub = 1;
+   for (int a = 0; a < dim; a++) { nsub *= p; }
    std::vector<Trip> tm, tl, tx;
-   std::vector<int32_t> d2c((size_t)ne * ND);
+   std::vector<int32_t> d2c(cgdof);
    std::vector<int> bd;
-   bdr_dofs(c->p, dim, bd);     // [NFD][NF]
+   bdr_dofs(p, dim, bd);     // [NFD][NF]
    for (int64_t e = 0; e < ne; e++)
    {
-      double Xc[8 * 3], Me[64], Ke[64];
-      bool bnd[6];
-      for (int j = 0; j < nv; j++)
-         for (int i = 0; i < dim; i++) { Xc[j * dim + i] = X[((size_t)e * c->NGN + cnode[j]) * dim + i]; }
-      for (int f = 0; f < NF; f++) { bnd[f] = nbe[e * NF + f] < 0; }
-      q1_element(dim, Xc, bnd, Me, Ke);
-      for (int i = 0; i < nv; i++)
+      for (int m = 0; m < nsub; m++)
       {
-         d2c[e * ND + i] = cg[e * nv + i];
+         double Xc[8 * 3], Me[64], Ke[64];
+         bool bnd[6];
+         int sl[3] = {0, 0, 0}, r = m;
+         for (int a = 0; a < dim; a++) { sl[a] = r % p; r /= p; }
+         const int *sc = &s2i[(size_t)m * nv];
          for (int j = 0; j < nv; j++)
+            for (int i = 0; i < dim; i++) { Xc[j * dim + i] = xlat[((size_t)e * ND + sc[j]) * dim + i]; }
+         for (int f = 0; f < NF; f++)
          {
-            tm.push_back({cg[e * nv + i], cg[e * nv + j], Me[i * nv + j]});
-            tl.push_back({cg[e * nv + i], cg[e * nv + j], Ke[i * nv + j]});
-            tx.push_back({cg[e * nv + i], (int32_t)(e * ND + j), Me[i * nv + j]});
+            int axis, side;
+            face_axis(dim, f, axis, side);
+            bnd[f] = (nbe[e * NF + f] < 0) && (sl[axis] == (side ? p - 1 : 0));
+         }
+         q1_element(dim, Xc, bnd, Me, Ke);
+         for (int i = 0; i < nv; i++)
+         {
+            const int32_t ri = cgdof[e * ND + sc[i]];
+            for (int j = 0; j < nv; j++)
+            {
+               const int32_t cj = cgdof[e * ND + sc[j]];
+               tm.push_back({ri, cj, Me[i * nv + j]});
+               tl.push_back({ri, cj, Ke[i * nv + j]});
+               // MassMixed x ShapeEval: the lattice value sc[j] is sum_k V[sc[j]][k] u_k
+               for (int k = 0; k < ND; k++)
+               {
+                  const double v = Me[i * nv + j] * V[(size_t)sc[j] * ND + k];
+                  if (v != 0.0) { tx.push_back({ri, (int32_t)(e * ND + k), v}); }
+               }
+            }
          }
       }
       for (int f = 0; f < NF; f++)
       {
-         if (!bnd[f]) { continue; }
-         for (int j = 0; j < c->NFD; j++) { d2c[e * ND + bd[j * NF + f]] = -1; }     // remhos_tools.cpp:94-105
+         if (nbe[e * NF + f] >= 0) { continue; }
+         for (int j = 0; j < NFD; j++) { d2c[e * ND + bd[j * NF + f]] = -1; }     // remhos_tools.cpp:94-105
       }
    }
    std::vector<int32_t> MI, MJ, LI, LJ, XI, XJ;

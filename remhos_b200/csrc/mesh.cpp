@@ -440,7 +440,7 @@ void nat2ref_table(int p, int dim, std::vector<int> &n2r)
    }
 }
 
-static void sub2ind(int p, int dim, std::vector<int> &s)
+void sub2ind(int p, int dim, std::vector<int> &s)
 {
    const int n = p + 1;
    int ns = 1;

@@ -934,7 +934,6 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    Verify(o.si >= 0 && o.si <= 2, "Bad smoothness indicator id!");
    if (o.si)
    {
-      Verify(o.order == 1, "smoothness indicators (-si) are built for -o 1 only");
       Verify(o.mono != 0 || o.fct == 2 || o.fct == 3, "smoothness indicators (-si) act on -mono, -fct 2 and -fct 3");
    }
    Verify(o.dtc == 0 || o.dtc == 1, "time step control must be 0 (fixed) or 1 (LO bounds error)");

@@ -262,7 +262,7 @@ public:
 };
 
 // remhos_tools.hpp SmoothnessIndicator (remhos_tools.cpp:24-354; created at remhos.cpp:905-911).
-// Order-1 spaces only; the H1 operators live in the device context of the space.
+// Any order: H1 order-1 operators on the subcell mesh, assembled into the device context of the space.
 class SmoothnessIndicator
 {
    ParFiniteElementSpace &pfes;

@@ -238,13 +238,14 @@ def test_cli_config5_star_q3_mono_subcell_matches_oracle(tmp_path):
 
 
 def test_new_flag_combinations_validated():
-    """-si needs -mono and order 1 in this build; -fct 4 needs assembled matrices; -fct 3 is not built;
-    -dtc 1 needs an FCT solver"""
-    for flags, msg in ((['-si', '1'], 'smoothness indicators'),
+    """-si acts on -mono, -fct 2 and -fct 3; -fct 4 needs assembled matrices; -fct 3 is transport only;
+    -dtc 1 needs an FCT solver; -ps needs remap mode"""
+    for flags, msg in ((['-si', '1', '-ho', '3', '-o', '1'], 'smoothness indicators (-si) act on'),
                        (['-si', '3', '-mono', '1', '-o', '1'], 'Bad smoothness indicator id!'),
-                       (['-mono', '1', '-si', '1', '-o', '2'], 'smoothness indicators'),
                        (['-ho', '3', '-lo', '5', '-fct', '4', '-pa'], 'FCTProject needs the assembled'),
-                       (['-ho', '3', '-lo', '5', '-fct', '3'], 'only -fct 0, 1'),
+                       (['-ho', '3', '-lo', '5', '-fct', '3', '-p', '10'], '-fct 3 (NonlinearPenalty) is built for transport'),
+                       (['-ho', '3', '-lo', '5', '-fct', '5'], 'FCT solver type must be 0 .. 4'),
+                       (['-ho', '3', '-lo', '5', '-fct', '2', '-ps'], 'Products are processed only in remap mode.'),
                        (['-ho', '3', '-dtc', '1'], '-dtc 1 needs an FCT solver'),
                        (['-ho', '3', '-lo', '5', '-fct', '2', '-dtc', '2'], 'time step control must be')):
         rc, _, err = run_cli('-m', 'x', *flags)

@@ -173,7 +173,7 @@ def test_mult_rejects_unsupported(setup):
     import remhos_b200 as rb
     run, ctx, u = setup
     k = empty(ctx)
-    for combo in [(2, 1, 2), (3, 6, 2), (3, 1, 3), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
+    for combo in [(2, 1, 2), (3, 6, 2), (3, 1, 5), (3, 0, 2), (0, 5, 0), (0, 0, 0)]:
         with pytest.raises(rb.RmhError):
             ctx.mult(*combo, 0.0, 0.01, dev(u), k)
 
