@@ -202,7 +202,6 @@ extern "C" int rmh_dist_create(rmh_ctx *c, rmh_dplan *plan, int rank, int world,
                                rmh_dist **out)
 {
    if (!c || !plan || !out) { set_error("rmh_dist_create: null argument"); return 1; }
-   if (c->exec_mode != 0) { set_error("rmh_dist_create: decomposed runs cover transport mode"); return 1; }
    int64_t ne = 0, ng = 0, ns = 0;
    int32_t np = 0;
    rmh_dplan_sizes(plan, &ne, &ng, &ns, &np);
@@ -436,25 +435,33 @@ extern "C" int rmh_dist_rk_step(rmh_dist *d, int ode, int lo_type, double *t, do
    const bool keep_xe = chain && c->trust_state;
    if (!have_xe) { if (stage_minmax(c, u, s)) { return 1; } }
    c->xe_ptr = nullptr;
+   // remap: every stage re-assembles at its own time (rmh_set_time; a no-op in transport mode)
+   const double t0 = *t;
    if (ode == 1)
    {
+      if (rmh_set_time(c, t0, stream)) { return 1; }
       if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
       CUDA_OK(cudaMemcpyAsync(u, c->w1, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, s));
       if (keep_xe) { c->xe_ptr = u; }
    }
    else if (ode == 2)
    {
+      if (rmh_set_time(c, t0, stream)) { return 1; }
       if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
       if (!chain) { if (stage_minmax(c, c->w1, s)) { return 1; } }
+      if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
       if (rmh_dist_rk_stage(d, lo_type, dt, 0.5, 0.5, u, c->w1, u, stream)) { return 1; }
       if (keep_xe) { c->xe_ptr = u; }
    }
    else if (ode == 3)
    {
+      if (rmh_set_time(c, t0, stream)) { return 1; }
       if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
       if (!chain) { if (stage_minmax(c, c->w1, s)) { return 1; } }
+      if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
       if (rmh_dist_rk_stage(d, lo_type, dt, 0.75, 0.25, u, c->w1, c->w2, stream)) { return 1; }
       if (!chain) { if (stage_minmax(c, c->w2, s)) { return 1; } }
+      if (rmh_set_time(c, t0 + dt / 2, stream)) { return 1; }
       if (rmh_dist_rk_stage(d, lo_type, dt, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, stream)) { return 1; }
       if (keep_xe) { c->xe_ptr = u; }
    }

@@ -255,10 +255,9 @@ ParFiniteElementSpace::ParFiniteElementSpace(rmh_mesh *m, int problem_, int orde
 // layer, exchange plan, device layer; the set-up blobs travel through the Communicator.
 void ParFiniteElementSpace::SetupDistributed(double &dt, double &t_final_, int device)
 {
-   Verify(exec_mode == 0, "decomposed runs cover transport mode");
    const int pv = problem % 20;
-   Verify(pv == 0 || pv == 1 || pv == 2 || pv == 4 || pv == 5 || pv == 6 || pv == 7,
-          "decomposed runs sample the velocity at the mesh nodes (problems 0, 1, 2, 4, 5, 6, 7)");
+   Verify(exec_mode == 1 || pv == 0 || pv == 1 || pv == 2 || pv == 4 || pv == 5 || pv == 6 || pv == 7,
+          "decomposed transport runs sample the velocity at the mesh nodes (problems 0, 1, 2, 4, 5, 6, 7)");
    global_mesh = mesh;
    const int rank = comm->rank, world = comm->world;
    std::vector<int32_t> part((size_t)rmh_mesh_ne(global_mesh));
@@ -284,7 +283,26 @@ void ParFiniteElementSpace::SetupDistributed(double &dt, double &t_final_, int d
    for (int a = 0; a < dim - 1; a++) { nfd *= order + 1; }
    const double *nodes = rmh_mesh_nodes(mesh);
    std::vector<double> vel_nodes((size_t)no * ngn * dim);
-   Check(rmh_velocity(problem, dim, no * ngn, nodes, bb_min.data(), bb_max.data(), vel_nodes.data()));
+   auto rank_min = [&](double v)          // MPI_MIN before the device layer exists: through the rendezvous
+   {
+      const std::vector<std::string> all = comm->AllGather(std::string(reinterpret_cast<const char *>(&v), sizeof(v)));
+      for (const std::string &sv : all) { double w; std::memcpy(&w, sv.data(), sizeof(w)); v = std::min(v, w); }
+      return v;
+   };
+   bool dt_done = false;
+   if (exec_mode == 1)                                                   // remhos.cpp:538-584
+   {
+      if (dt < 0.0)
+      {
+         Check(rmh_cfl_dt(mesh, problem, bb_min.data(), bb_max.data(), &dt));
+         dt = rank_min(dt);
+      }
+      dt_done = true;
+      Check(rmh_remap_mesh_velocity(mesh, problem, bb_min.data(), bb_max.data(), dt, t_final_, vel_nodes.data()));
+      vel_nodes_host = vel_nodes;
+      t_final_ = 1.0;                                                    // :1128-1134
+   }
+   else { Check(rmh_velocity(problem, dim, no * ngn, nodes, bb_min.data(), bb_max.data(), vel_nodes.data())); }
    const int64_t na = no + ng;
    std::vector<int32_t> bd((size_t)nfd * nf), nbr((size_t)na * nf * nfd), s2i((size_t)nsub * ncorner),
        lat((size_t)na * n3), nbe((size_t)na * nf);
@@ -314,7 +332,7 @@ void ParFiniteElementSpace::SetupDistributed(double &dt, double &t_final_, int d
       for (int r = 0; r < world; r++) { ptrs[r] = all[r].data(); sizes[r] = (int64_t)all[r].size(); }
       Check(rmh_dist_connect(dist, world, ptrs.data(), sizes.data()));
    }
-   if (dt < 0.0)                                                         // :538-553 (MPI_MIN at :551)
+   if (dt < 0.0 && !dt_done)                                             // :538-553 (MPI_MIN at :551)
    {
       Check(rmh_cfl_dt(mesh, problem, bb_min.data(), bb_max.data(), &dt));
       dt = Reduce(dt, 1);

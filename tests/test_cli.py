@@ -378,13 +378,18 @@ DECOMP_GENERAL = [
     ('periodic-square.mesh', ['-p', 5, '-rs', 3, '-o', 2, '-dt', 0.01, '-tf', 0.08, '-ho', 3, '-lo', 5, '-fct', 4, '-bt', 1, '-dtc', 1]),
     ('periodic-square.mesh', ['-p', 5, '-rs', 2, '-o', 2, '-dt', 0.004, '-tf', 0.02, '-ho', 3, '-lo', 3, '-fct', 0]),
     ('inline-quad.mesh', ['-p', 4, '-rs', 2, '-o', 2, '-dt', 0.002, '-tf', 0.02, '-ho', 3, '-lo', 1, '-fct', 2]),
+    # remap mode on a decomposed mesh: fused stage path (3D, re-assembly every stage) and solver by solver (2D)
+    ('cube01_hex.mesh', ['-p', 10, '-rs', 2, '-o', 2, '-dt', -1, '-tf', 0.5, '-ho', 3, '-lo', 5, '-fct', 2, '-ms', 6, '-pa']),
+    ('inline-quad.mesh', ['-p', 14, '-rs', 2, '-o', 3, '-dt', -1, '-tf', 0.5, '-ho', 3, '-lo', 3, '-fct', 2, '-ms', 8]),
+    ('inline-quad.mesh', ['-p', 14, '-rs', 2, '-o', 2, '-dt', 0.004, '-tf', 0.04, '-ho', 3, '-lo', 5, '-fct', 4, '-s', 12]),
 ]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('mesh_name,flags', DECOMP_GENERAL,
                          ids=['RD-clipscale', 'DU-clipscale-rk2', 'hexagon-Neumann-DUprec', 'cube-RDsub', 'idp3-fctproject',
-                              'cube-rk4-rotation', 'dtc', 'LO-only', 'inline-quad-boundary'])
+                              'cube-rk4-rotation', 'dtc', 'LO-only', 'inline-quad-boundary', 'remap-3d-fused',
+                              'remap-2d-RD', 'remap-2d-idp2-fctproject'])
 def test_cli_decomposed_solver_by_solver(mesh_name, flags):
     """Decomposed runs of the matrix-based / unfused solver combinations (DU, RD, subcell RD, Neumann,
     FCTProject, IDP and RK4 time stepping, automatic dt): `remhos -gpus 2` against the single-GPU run.
