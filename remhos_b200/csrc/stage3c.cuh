@@ -287,11 +287,14 @@ __device__ __forceinline__ void wait_peer_flags(const unsigned long long *flags,
    for (int p = 0; p < n; p++)
    {
       unsigned long long v;
+      unsigned int spins = 0;
       while (true)
       {
          asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flags + p) : "memory");
          if (v >= epoch) { break; }
-         __nanosleep(128);
+         __nanosleep(256);
+         // a peer that died must not hang this GPU: give up after ~20 s and fail the launch loudly
+         if (++spins > (1u << 26)) { __trap(); }
       }
    }
 }

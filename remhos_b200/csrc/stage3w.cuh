@@ -295,7 +295,7 @@ k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
    double *wsm = reinterpret_cast<double *>(reinterpret_cast<char *>(sm) + S::CBYTES) + (size_t)w * (S::WBYTES / 8);
    int *ismem = reinterpret_cast<int *>(wsm + S::WDBL);
    const double inv_dt = 1.0 / a.dt;
-   // ---- coefficient fragments (see stage3t.cuh)
+   // ---- coefficient fragments (fragment algebra: file header)
    double fB[KF], fG[KF], bC[KB];
 #pragma unroll
    for (int ks = 0; ks < KF; ks++)
