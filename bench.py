@@ -484,7 +484,14 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roof,
-        'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0), 'u_min': umin, 'u_max': umax},
+        'check': {'mass_rel_drift': abs(mass1 - mass0) / abs(mass0),
+                  'mass_rel_drift_per_stage': abs(mass1 - mass0) / abs(mass0) / (STAGES * a.steps),
+                  'mass_note': 'ClipScale rescales an element only when |sum of clipped fluxes| > 1e-15 '
+                               '(remhos_fct.cpp:517-538, absolute threshold): in the far field of the bump '
+                               '(u < 1e-9, most elements) the fluxes are below it and stay unbalanced -- the '
+                               'reference algorithm\'s own defect, about 1e-14 of the mass per stage here; '
+                               'the C port of the path drifts at the same rate',
+                  'u_min': umin, 'u_max': umax},
     }
     if world > 1:
         line['check']['dist_rel_err'] = dist_err

@@ -1310,21 +1310,91 @@ static int dispatch_stagew(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 }
 
 // ---- constant-coefficient kernel (stage3c.cuh)
+// 1-D operators of the constant-coefficient kernel.  The integrals are rational numbers (Bernstein
+// products), so they are formed in extended precision from their closed forms -- the same matrices the
+// Q-point Gauss rule gives exactly, M1 = B^T W B and S = B^T W G -- and rounded once:
+//    M1_ij = C(p,i) C(p,j) / (C(2p,i+j) (2p+1)),     S_ik = int B_i^p (B_k^p)' = p (I_{i,k-1} - I_{i,k}),
+//    I_ij = int B_i^p B_j^{p-1} = C(p,i) C(p-1,j) / (C(2p-1,i+j) 2p),          T = M1^-1 S.
+// Then the column sums are made exact in double: sum_i T[i][k] = D1 (delta_kp - delta_k0) and
+// sum_i Minv[i][0] = sum_i Minv[i][p] = D1 (partition of unity: 1^T M1 = 1^T / D1).  These sums are what
+// makes the scheme conservative -- the mass an element loses through a face is D1 Minv-weighted on one
+// side and on the other -- and with tables rounded entry by entry they were off by cond(M1) eps ~ 1e-14,
+// a SYSTEMATIC source (u > 0 everywhere) that showed as a mass drift of 2e-14 per stage.
+static long double binom_ld(int n, int k)
+{
+   if (k < 0 || k > n) { return 0.0L; }
+   long double r = 1.0L;
+   for (int i = 1; i <= k; i++) { r = r * (long double)(n - k + i) / (long double)i; }
+   return r;
+}
+
 template <int D1, int Q>
 static TabC<D1> make_tabc(const rmh_ctx *c)
 {
-   const Tab<D1, Q> t = make_tab<D1, Q>(c);
+   (void)c;
+   constexpr int p = D1 - 1;
+   long double M[D1][2 * D1], S[D1][D1];
+   for (int i = 0; i < D1; i++)
+   {
+      for (int j = 0; j < D1; j++)
+      {
+         M[i][j] = binom_ld(p, i) * binom_ld(p, j) / (binom_ld(2 * p, i + j) * (long double)(2 * p + 1));
+         M[i][D1 + j] = (i == j) ? 1.0L : 0.0L;
+      }
+      for (int k = 0; k < D1; k++)
+      {
+         auto I = [&](int jj) -> long double
+         {
+            if (p == 0 || jj < 0 || jj > p - 1) { return 0.0L; }
+            return binom_ld(p, i) * binom_ld(p - 1, jj) / (binom_ld(2 * p - 1, i + jj) * (long double)(2 * p));
+         };
+         S[i][k] = (long double)p * (I(k - 1) - I(k));
+      }
+   }
+   for (int col = 0; col < D1; col++)           // Gauss-Jordan with partial pivoting
+   {
+      int piv = col;
+      for (int r = col + 1; r < D1; r++) { if (fabsl(M[r][col]) > fabsl(M[piv][col])) { piv = r; } }
+      for (int j = 0; j < 2 * D1; j++) { std::swap(M[col][j], M[piv][j]); }
+      const long double d = M[col][col];
+      for (int j = 0; j < 2 * D1; j++) { M[col][j] /= d; }
+      for (int r = 0; r < D1; r++)
+      {
+         if (r == col) { continue; }
+         const long double f = M[r][col];
+         for (int j = 0; j < 2 * D1; j++) { M[r][j] -= f * M[col][j]; }
+      }
+   }
    TabC<D1> o;
    for (int i = 0; i < D1; i++)
    {
       for (int k = 0; k < D1; k++)
       {
-         double v = 0.0;
-         for (int q = 0; q < Q; q++) { v += t.C[i][q] * t.wq[q] * t.G[q][k]; }
-         o.T[i][k] = v;
+         long double v = 0.0L;
+         for (int j = 0; j < D1; j++) { v += M[i][D1 + j] * S[j][k]; }
+         o.T[i][k] = (double)v;
       }
-      o.M0[i] = t.Minv[i][0]; o.Mp[i] = t.Minv[i][D1 - 1];
+      o.M0[i] = (double)M[i][D1]; o.Mp[i] = (double)M[i][D1 + D1 - 1];
    }
+   // exact column sums in double (the entry of largest magnitude absorbs the rounding)
+   auto fix = [&](auto get, auto put, double target)
+   {
+      for (int it = 0; it < 3; it++)
+      {
+         double sum = 0.0;
+         int big = 0;
+         for (int i = 0; i < D1; i++) { sum += get(i); if (std::fabs(get(i)) > std::fabs(get(big))) { big = i; } }
+         if (sum == target) { break; }
+         put(big, get(big) + (target - sum));
+      }
+   };
+   for (int k = 0; k < D1; k++)
+   {
+      const double target = (double)D1 * ((k == p ? 1.0 : 0.0) - (k == 0 ? 1.0 : 0.0));
+      fix([&](int i) { return o.T[i][k]; }, [&](int i, double v) { o.T[i][k] = v; }, target);
+   }
+   fix([&](int i) { return o.M0[i]; }, [&](int i, double v) { o.M0[i] = v; }, (double)D1);
+   fix([&](int i) { return o.Mp[i]; }, [&](int i, double v) { o.Mp[i] = v; }, (double)D1);
    return o;
 }
 
