@@ -288,6 +288,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-dist-check', action='store_true')
+    ap.add_argument('--replicas', action='store_true', help='under torchrun: independent replicas, no halo (experiment)')
+    ap.add_argument('--force-dist', action='store_true',
+                    help='N=1 through the decomposed path (ghost-aware kernel, no peers): isolates its overhead')
     ap.add_argument('--problem', type=int, default=0,
                     help='0: constant velocity (BASELINE config); 1: rotation (velocity linear in x: '
                          'exercises the general FP64 tensor-core kernel)')
@@ -336,13 +339,17 @@ def main():
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
+    if a.replicas and world > 1:
+        # experiment: N independent single-rank problems side by side (process group initialised, no halo):
+        # isolates what merely running next to busy peers costs; every rank prints its own line
+        world, rank = 1, 0
     dist_err, dist_cases = None, None
     if world > 1 and not a.no_dist_check:
         dist_err, dist_cases = dist_parity_check(rank, world, local_rank)
 
     h = 2.0 / nloc
     dt = 0.25 * h / a.order            # fixed dt = 0.25 h/|v| /p, |v| = 1
-    if world == 1:
+    if world == 1 and not a.force_dist:
         if a.nloc > 0:
             mesh = rb.Mesh.cartesian([nloc] * 3, [2.0, 2.0, 2.0], origin=[-1.0, -1.0, -1.0], periodic=True)
         else:
@@ -357,12 +364,15 @@ def main():
 
         def step_host(t, uh):
             return ctx.rk_step_host(3, 5, t, dt, uh.data_ptr())
+
+        def step_host_async(t, uh):
+            return ctx.rk_step_host_async(3, 5, t, dt, uh.data_ptr())
         pdims = [1, 1, 1]
     else:
         # weak scaling: every rank owns a (3*2^rs)^3 brick of a periodic box that grows with the
         # rank count; recursive coordinate bisection of the global Cartesian mesh yields the bricks
         from remhos_b200.dist import DistProblem
-        pdims = {2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}.get(world)
+        pdims = {1: [1, 1, 1], 2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}.get(world)
         if pdims is None:
             raise SystemExit('bench.py: --gpus must be 1, 2, 4 or 8')
         mesh = rb.Mesh.cartesian([nloc * d for d in pdims], [2.0 * d for d in pdims],
@@ -377,6 +387,9 @@ def main():
 
         def step_host(t, uh):
             return prob.dist.rk_step_host(3, 5, t, dt, uh.data_ptr())
+
+        def step_host_async(t, uh):
+            return prob.dist.rk_step_host_async(3, 5, t, dt, uh.data_ptr())
     # the time loop below never touches the state between steps (neither does the reference's,
     # remhos.cpp:1146-1330): the element min/max the last stage computes for its output are
     # reused by the next step instead of a separate pass over the state
@@ -403,6 +416,8 @@ def main():
         t = step(t, u, stream)
     barrier()
     rb.launch_count(reset=True)
+    if world > 1:
+        ctx.halo_wait_stats(reset=True)
     ctx.profile(1)
     t_wall0 = time.time()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
@@ -415,26 +430,71 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = rb.launch_count(reset=True)
     kms, klaunch = ctx.profile(0)
+    hw = None
+    if world > 1:
+        st = ctx.halo_wait_stats()
+        hwt = torch.tensor([st[k] for k in ('warps_waited', 'wait_ns_sum', 'wait_ns_max', 'warps_shell', 'shell_ns_sum',
+                                            'warps', 'run_ns_sum')], dtype=torch.float64, device='cuda')
+        hwl = [torch.empty_like(hwt) for _ in range(world)]
+        dist.all_gather(hwl, hwt)
+        hw = [[float(x) for x in h_] for h_ in hwl]
     mass1 = gred(ctx.reduce(0, u, m))
     umin, umax = gred(ctx.reduce(1, u), 'min'), gred(ctx.reduce(2, u), 'max')
 
-    # end-to-end: state in pinned host memory, H2D + step + D2H every step
+    # end-to-end: state in pinned host memory, H2D + step + D2H every step, three ways:
+    #  serial      rmh_rk_step_host, one blocking call per step (copy, stages, copy back to back);
+    #  pipelined   rmh_rk_step_host_async on the SAME host buffer: every step still uploads its input and
+    #              downloads its result in full, but slab k of the next upload follows slab k of the previous
+    #              download, so both directions of the link are busy (the headline e2e);
+    #  fields      the same call on three independent host states in turn (several fields transported by the
+    #              same velocity): upload, stages and download of consecutive calls overlap fully.
     uh = u.cpu().pin_memory()
-    for _ in range(2):
-        step_host(t, uh)
-    barrier()
-    t0 = time.perf_counter()
     e_steps = max(3, min(a.steps // 2, 30))
-    for _ in range(e_steps):
-        step_host(t, uh)
-    barrier()
-    e_ms = (time.perf_counter() - t0) * 1e3
+
+    def timed(fn, n):
+        barrier()
+        t0 = time.perf_counter()
+        fn(n)
+        barrier()
+        return (time.perf_counter() - t0) * 1e3
+
+    def run_serial(n):
+        for _ in range(n):
+            step_host(t, uh)
+
+    def run_pipe(n):
+        for _ in range(n):
+            step_host_async(t, uh)
+        ctx.host_sync()
+
+    run_serial(2)
+    es_ms = timed(run_serial, e_steps)
+    # the pipelined steps must produce what the serial ones do: same start, same number of steps
+    ua = uh.clone().pin_memory(); ub = uh.clone().pin_memory()
+    for _ in range(3):
+        step_host(t, ua)
+    for _ in range(3):
+        step_host_async(t, ub)
+    ctx.host_sync()
+    pipe_ok = bool(torch.equal(ua, ub))
+    run_pipe(2)
+    e_ms = timed(run_pipe, e_steps)
+    fields = [uh, ua, ub]
+
+    def run_fields(n):
+        for k in range(n):
+            step_host_async(t, fields[k % 3])
+        ctx.host_sync()
+
+    run_fields(3)
+    ef_ms = timed(run_fields, e_steps)
+    del ua, ub
     clocks = sampler.stop(t_wall0, time.time())
 
-    tmax = torch.tensor([ms, e_ms], dtype=torch.float64, device='cuda')
+    tmax = torch.tensor([ms, e_ms, es_ms, ef_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, e_ms = float(tmax[0]), float(tmax[1])
+    ms, e_ms, es_ms, ef_ms = (float(v) for v in tmax)
     total_dofs = N * world
     value = total_dofs * STAGES * a.steps / (ms * 1e-3)
     e2e = total_dofs * STAGES * e_steps / (e_ms * 1e-3)
@@ -480,7 +540,17 @@ def main():
                                    'and one stage kernel that waits for the halo before its shell elements'
                                    % tuple(pdims)) if world > 1 else 'single GPU'},
         'e2e': {'value': e2e, 'unit': 'DOF*stage/s', 'h2d_bytes_per_step': 8 * N,
-                'd2h_bytes_per_step': 8 * N, 'steps': e_steps},
+                'd2h_bytes_per_step': 8 * N, 'steps': e_steps,
+                'api': 'rmh_rk_step_host_async on one pinned host state + rmh_host_sync: every step uploads its '
+                       'input and downloads its result in full; upload of step n+1 follows the download of '
+                       'step n slab by slab (both PCIe directions busy)',
+                'ms_per_step': e_ms / e_steps,
+                'pipelined_equals_serial': pipe_ok,
+                'serial_value': total_dofs * STAGES * e_steps / (es_ms * 1e-3),
+                'serial_api': 'rmh_rk_step_host, one blocking call per step (H2D, stages, D2H back to back)',
+                'independent_fields_value': total_dofs * STAGES * e_steps / (ef_ms * 1e-3),
+                'independent_fields_api': 'rmh_rk_step_host_async on three independent pinned states in turn',
+                'link_GBps_each_way': 8 * N / (e_ms / e_steps * 1e-3) / 1e9},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roof,
@@ -494,6 +564,16 @@ def main():
                   'u_min': umin, 'u_max': umax},
     }
     if world > 1:
+        # in-kernel halo waits of rank 0 over the timed steps: warps that found a peer's flag unpublished
+        line['halo_wait'] = {'per_rank': [{'warps_waited': int(h_[0]), 'mean_wait_us': (h_[1] / h_[0] / 1e3) if h_[0] else 0.0,
+                                           'longest_wait_us': h_[2] / 1e3,
+                                           'mean_warp_run_us': (h_[6] / h_[5] / 1e3) if h_[5] else None,
+                                           'mean_warp_shell_phase_us': (h_[4] / h_[3] / 1e3) if h_[3] else None}
+                                          for h_ in hw],
+                             'warps_per_rank': int(hw[0][5]),
+                             'note': 'a warp waits when it reaches its first shell group before every peer has '
+                                     'published the halo of this stage; shell phase = from that point to the '
+                                     'end of the warp'}
         line['check']['dist_rel_err'] = dist_err
         line['check']['dist_cases'] = dist_cases
         if dist_err is not None and not (dist_err < 1e-12):
@@ -511,7 +591,7 @@ def main():
         prob.close()
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

@@ -382,6 +382,16 @@ int rmh_rk_step(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, doubl
 /* Same call with HOST state: H2D of u, one step, D2H of u (the end-to-end entry point). */
 int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, double dt,
                      double *u_host);
+/* The same step QUEUED on three streams (H2D, stages, D2H) with a ring of three device buffers: returns at
+ * once, rmh_host_sync waits for everything queued.  Consecutive calls overlap -- independent host states
+ * (several fields transported by the same velocity) run H2D of call n+1, the stages of call n and D2H of
+ * call n-1 together; the same host buffer stepped again follows the previous D2H slab by slab, so that both
+ * directions of the PCIe link are busy.  The state read is the one at u_in_host when the copy runs; t is the
+ * time at the start of the step.  Host buffers must be pinned, and identical or disjoint between calls.
+ * (ODESolver::Step on the reference's host-resident vectors, remhos.cpp:1146-1180.) */
+int rmh_rk_step_host_async(rmh_ctx *ctx, int ode_solver_type, int lo_type, double t, double dt,
+                           const double *u_in_host, double *u_out_host);
+int rmh_host_sync(rmh_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: the mesh decomposed over the GPUs of one node, one context per rank (one process per
@@ -439,6 +449,14 @@ int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, c
 int rmh_dist_rk_step(rmh_dist *d, int ode_solver_type, int lo_type, double *t, double dt, double *u_dev,
                      void *stream);
 int rmh_dist_rk_step_host(rmh_dist *d, int ode_solver_type, int lo_type, double *t, double dt, double *u_host);
+/* queued variant, see rmh_rk_step_host_async; rmh_host_sync(ctx) waits */
+int rmh_dist_rk_step_host_async(rmh_dist *d, int ode_solver_type, int lo_type, double t, double dt,
+                                const double *u_in_host, double *u_out_host);
+/* diagnostic: in-kernel halo waits on this device since the last reset -- out[0] warps that found a peer's
+ * epoch flag unpublished, out[1] their summed and out[2] longest wait in ns; out[3] warps that reached a
+ * shell group, out[4] their summed time from there to their end; out[5] all warps of the ghost-aware
+ * launches, out[6] their summed run time (ns).  Synchronises the device. */
+int rmh_halo_wait_stats(rmh_ctx *ctx, unsigned long long *out7, int reset);
 /* op 0 sum, 1 min, 2 max over the ranks, in place on n <= 16 host doubles (ncclAllReduce); collective */
 int rmh_dist_allreduce(rmh_dist *d, int op, double *vals, int n, void *stream);
 

@@ -305,6 +305,13 @@ class Dist:
                                           C.c_double(dt), C.c_void_p(int(u_host))))
         return tt.value
 
+    def rk_step_host_async(self, ode_solver_type, lo_type, t, dt, u_in_host, u_out_host=None):
+        """queued variant (rmh_dist_rk_step_host_async); Context.host_sync() waits"""
+        check(lib().rmh_dist_rk_step_host_async(self.h, int(ode_solver_type), int(lo_type), C.c_double(t),
+                                                C.c_double(dt), C.c_void_p(int(u_in_host)),
+                                                C.c_void_p(int(u_in_host if u_out_host is None else u_out_host))))
+        return t + dt
+
     def allreduce(self, values, op='sum', s=0):
         v = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).copy()
         check(lib().rmh_dist_allreduce(self.h, {'sum': 0, 'min': 1, 'max': 2}[op], _ptr(v), int(v.size),
@@ -549,6 +556,23 @@ class Context:
         check(lib().rmh_rk_step_host(self.h, int(ode_solver_type), int(lo_type), C.byref(tt),
                                      C.c_double(dt), C.c_void_p(int(u_host))))
         return tt.value
+
+    def rk_step_host_async(self, ode_solver_type, lo_type, t, dt, u_in_host, u_out_host=None):
+        """queue H2D + step + D2H (pinned host pointers); host_sync() waits"""
+        check(lib().rmh_rk_step_host_async(self.h, int(ode_solver_type), int(lo_type), C.c_double(t), C.c_double(dt),
+                                           C.c_void_p(int(u_in_host)),
+                                           C.c_void_p(int(u_in_host if u_out_host is None else u_out_host))))
+        return t + dt
+
+    def halo_wait_stats(self, reset=False):
+        """in-kernel halo diagnostics since the last reset (rmh_halo_wait_stats): dict of counts and ns"""
+        out = (C.c_ulonglong * 7)()
+        check(lib().rmh_halo_wait_stats(self.h, out, int(bool(reset))))
+        keys = ('warps_waited', 'wait_ns_sum', 'wait_ns_max', 'warps_shell', 'shell_ns_sum', 'warps', 'run_ns_sum')
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def host_sync(self):
+        check(lib().rmh_host_sync(self.h))
 
     def stage_minmax(self, y, s=0):
         check(lib().rmh_stage_minmax(self.h, _dp(y), C.c_void_p(s)))

@@ -50,6 +50,7 @@ static std::atomic<int64_t> g_launches{0};
    } while (0)
 
 // ============================================================================ context
+struct HostPipe;
 struct rmh_ctx
 {
    int dim, p, mo, exec_mode, bounds_type, device;
@@ -127,6 +128,11 @@ struct rmh_ctx
    // the neighbour's face trace (this element's natural face order) is ughost[slot][NFD].
    const double *ughost = nullptr;
    const double *halo_ptr = nullptr;    // state whose ghost traces / (min,max) the window holds (unfused path)
+   struct HostPipe *pipe = nullptr;      // rmh_rk_step_host_async
+   // fused halo send (dist.cuh): the stage kernel that wrote sent_ptr has already stored its halo for epoch sent_epoch
+   bool send_next = false;
+   const double *sent_ptr = nullptr;
+   unsigned long long sent_epoch = 0;
    int64_t n_gslots = 0;
    std::vector<int32_t> gs_ghost, gs_pid;   // per slot: ghost element (0 .. ne_ghost-1), pattern id
    std::vector<int16_t> pat_h;              // host copy of the pattern table [npat][NFD]
@@ -135,6 +141,7 @@ struct rmh_ctx
    int32_t *nb27 = nullptr;
    bool fold = false;
    double2 *xe_mm2[2] = {nullptr, nullptr};
+   double *zeros = nullptr;              // 64 zeros
    unsigned long long epoch = 0;   // stage counter: stage k reads pairs / ghost traces [k & 1], writes pairs [(k+1) & 1]
    // the window peers write into (one allocation = one IPC handle):
    // flags[RMH_MAX_PEERS] | xe_mm2[0] | xe_mm2[1] | gtr[0] | gtr[1]
@@ -1398,7 +1405,7 @@ static TabC<D1> make_tabc(const rmh_ctx *c)
    return o;
 }
 
-template <int D1, int Q, int NW, int MINB, int NST, bool GH, bool FOLD>
+template <int D1, int Q, int NW, int MINB, int NST, bool GH, bool FOLD, bool SEND = false>
 static int launch_stagec_G(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    using S = SmemC<D1, NST>;
@@ -1407,22 +1414,22 @@ static int launch_stagec_G(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    int &bps = blocks_per_sm[c->device % RMH_MAX_DEVICES];
    if (bps == 0)
    {
-      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST, GH, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_OK(cudaFuncSetAttribute(k_stage3c<D1, NW, MINB, NST, GH, FOLD, SEND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)BYTES));
       int nb = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST, GH, FOLD>, NW * 32, BYTES));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage3c<D1, NW, MINB, NST, GH, FOLD, SEND>, NW * 32, BYTES));
       if (nb < 1) { set_error("k_stage3c does not fit on an SM"); return 1; }
       bps = std::min(nb, MINB);
       if (getenv("RMH_VERBOSE"))
       {
-         fprintf(stderr, "k_stage3c<%d,%d,%d,%d,%s,%s>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
-                 GH ? "ghosts" : "local", FOLD ? "fold" : "entities", bps, nb, BYTES);
+         fprintf(stderr, "k_stage3c<%d,%d,%d,%d,%s,%s%s>: %d blocks/SM (occupancy %d), %zu B shared\n", D1, NW, MINB, NST,
+                 GH ? "ghosts" : "local", FOLD ? "fold" : "entities", SEND ? ",send" : "", bps, nb, BYTES);
       }
    }
    const int64_t ngrp = (a.ne + S::E - 1) / S::E - a.e_begin / S::E;
    const int64_t nblk = (ngrp + NW - 1) / NW;
    const int64_t grid = std::min<int64_t>(nblk, (int64_t)bps * c->num_sms);
-   k_stage3c<D1, NW, MINB, NST, GH, FOLD><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
+   k_stage3c<D1, NW, MINB, NST, GH, FOLD, SEND><<<(unsigned)grid, NW * 32, BYTES, s>>>(a, make_tabc<D1, Q>(c));
    LAUNCH_OK();
    return 0;
 }
@@ -1431,8 +1438,11 @@ template <int D1, int Q, int NW, int MINB, int NST>
 static int launch_stagec_N(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
 {
    const bool fold = (a.xe_mm_out != nullptr);
-   if (c->ne_ghost > 0)
+   static int force_gh = -1;        // RMH_FORCE_GH=1: the ghost-aware instantiation on a mesh without ghosts (profiling)
+   if (force_gh < 0) { const char *ev = getenv("RMH_FORCE_GH"); force_gh = (ev && ev[0] == '1') ? 1 : 0; }
+   if (c->ne_ghost > 0 || force_gh)
    {
+      if (fold && a.send != nullptr) { return launch_stagec_G<D1, Q, NW, MINB, NST, true, true, true>(c, a, s); }
       return fold ? launch_stagec_G<D1, Q, NW, MINB, NST, true, true>(c, a, s)
                   : launch_stagec_G<D1, Q, NW, MINB, NST, true, false>(c, a, s);
    }
@@ -1570,6 +1580,8 @@ extern "C" int64_t rmh_launch_count(int reset)
    return v;
 }
 
+static void host_pipe_free(rmh_ctx *c);
+
 extern "C" int rmh_ctx_destroy(rmh_ctx *c)
 {
    if (!c) { return 0; }
@@ -1577,6 +1589,7 @@ extern "C" int rmh_ctx_destroy(rmh_ctx *c)
    for (void *p : c->allocs) { cudaFree(p); }
    for (cudaEvent_t ev : c->prof_ev) { cudaEventDestroy(ev); }
    if (c->pin) { cudaFreeHost(c->pin); }
+   host_pipe_free(c);
    delete c;
    return 0;
 }
@@ -1789,6 +1802,8 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
       c->allocs.push_back(c->win);
       CUDA_OK(cudaMemset(c->win, 0, off));
       c->flags = (unsigned long long *)c->win;
+      if (dev_alloc(c, &c->zeros, 64)) { return fail(); }
+      CUDA_OK(cudaMemset(c->zeros, 0, 64 * sizeof(double)));
       const double2 sentinel = make_double2(INFINITY, -INFINITY);
       for (int k = 0; k < 2; k++)
       {
@@ -2123,6 +2138,7 @@ static int stage_impl(rmh_ctx *c, int lo_type, double dt, int out_mode, double a
          pa.ent_mm = reinterpret_cast<const double *>(c->xe_mm2[par]);
          pa.xe_mm_out = c->xe_mm2[par ^ 1];
       }
+      pa.zeros = c->zeros;
       dist_stage_args(c, pa, fold);
    }
    auto run = [&]()
@@ -2236,6 +2252,131 @@ extern "C" int rmh_rk_step_host(rmh_ctx *c, int ode, int lo_type, double *t, dou
    if (rmh_rk_step(c, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }
    CUDA_OK(cudaMemcpyAsync(u_host, c->w3, bytes, cudaMemcpyDeviceToHost, 0));
    CUDA_OK(cudaStreamSynchronize(0));
+   return 0;
+}
+
+// ---- pipelined host-state stepping.  A step of a host-resident state is three transfers over two different
+// resources: H2D (PCIe down), the stages (HBM), D2H (PCIe up).  rmh_rk_step_host runs them back to back;
+// here they are queued on three streams with a ring of device buffers, so that consecutive calls overlap:
+//  * independent states (several fields advected by the same velocity, one call each): H2D of call n+1,
+//    the stages of call n and D2H of call n-1 run at the same time;
+//  * the SAME host buffer stepped repeatedly: the copies are cut into slabs and slab k of the next H2D is
+//    ordered behind slab k of the previous D2H only, so both directions of the link stay busy.
+// Host buffers of different calls must be identical or disjoint.
+struct HostPipe
+{
+   static constexpr int NBUF = 3, NSLAB = 16;
+   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+   double *buf[NBUF] = {nullptr, nullptr, nullptr};
+   cudaEvent_t in_done[NBUF], cmp_done[NBUF], out_done[NBUF], slab_out[NBUF][NSLAB];
+   const double *in_host[NBUF] = {nullptr, nullptr, nullptr};
+   double *out_host[NBUF] = {nullptr, nullptr, nullptr};
+   uint64_t n = 0;
+};
+
+static void host_pipe_free(rmh_ctx *c)
+{
+   HostPipe *P = c->pipe;
+   if (!P) { return; }
+   for (int i = 0; i < HostPipe::NBUF; i++)
+   {
+      cudaEventDestroy(P->in_done[i]); cudaEventDestroy(P->cmp_done[i]); cudaEventDestroy(P->out_done[i]);
+      for (int k = 0; k < HostPipe::NSLAB; k++) { cudaEventDestroy(P->slab_out[i][k]); }
+   }
+   cudaStreamDestroy(P->s_in); cudaStreamDestroy(P->s_cmp); cudaStreamDestroy(P->s_out);
+   delete P;
+   c->pipe = nullptr;
+}
+
+static int host_pipe_get(rmh_ctx *c, HostPipe **out)
+{
+   if (c->pipe) { *out = c->pipe; return 0; }
+   HostPipe *P = new HostPipe;
+   c->pipe = P;
+   CUDA_OK(cudaStreamCreateWithFlags(&P->s_in, cudaStreamNonBlocking));
+   CUDA_OK(cudaStreamCreateWithFlags(&P->s_cmp, cudaStreamNonBlocking));
+   CUDA_OK(cudaStreamCreateWithFlags(&P->s_out, cudaStreamNonBlocking));
+   for (int i = 0; i < HostPipe::NBUF; i++)
+   {
+      if (dev_alloc(c, &P->buf[i], (size_t)c->N)) { return 1; }
+      CUDA_OK(cudaEventCreateWithFlags(&P->in_done[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&P->cmp_done[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&P->out_done[i], cudaEventDisableTiming));
+      for (int k = 0; k < HostPipe::NSLAB; k++) { CUDA_OK(cudaEventCreateWithFlags(&P->slab_out[i][k], cudaEventDisableTiming)); }
+   }
+   *out = P;
+   return 0;
+}
+
+// step(u_dev, stream) advances the device copy in place
+template <typename StepFn>
+static int host_pipe_step(rmh_ctx *c, const double *u_in_host, double *u_out_host, StepFn step)
+{
+   if (!u_in_host || !u_out_host) { set_error("rmh_rk_step_host_async: null host buffer"); return 1; }
+   HostPipe *P = nullptr;
+   if (host_pipe_get(c, &P)) { return 1; }
+   constexpr int NB = HostPipe::NBUF, NS = HostPipe::NSLAB;
+   const int i = (int)(P->n % NB);
+   const int64_t N = c->N, per = ((N + NS - 1) / NS + 1) & ~(int64_t)1;
+   // the device buffer is free once the D2H of the call that used it last is through
+   if (P->n >= (uint64_t)NB) { CUDA_OK(cudaStreamWaitEvent(P->s_in, P->out_done[i], 0)); }
+   // a call in flight that writes the buffer we are about to read: follow it slab by slab
+   int dep = -1;
+   for (int r = 0; r < NB; r++) { if (r != i && P->out_host[r] == u_in_host && P->n > 0) { dep = r; } }
+   // ... and the newest such call only (older ones are ordered before it on s_out)
+   if (dep >= 0)
+   {
+      const int last = (int)((P->n - 1) % NB);
+      if (P->out_host[last] == u_in_host) { dep = last; }
+   }
+   for (int k = 0; k < NS; k++)
+   {
+      const int64_t o = k * per, len = std::min<int64_t>(per, N - o);
+      if (len <= 0) { break; }
+      if (dep >= 0) { CUDA_OK(cudaStreamWaitEvent(P->s_in, P->slab_out[dep][k], 0)); }
+      CUDA_OK(cudaMemcpyAsync(P->buf[i] + o, u_in_host + o, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, P->s_in));
+   }
+   CUDA_OK(cudaEventRecord(P->in_done[i], P->s_in));
+   CUDA_OK(cudaStreamWaitEvent(P->s_cmp, P->in_done[i], 0));
+   c->xe_ptr = nullptr; c->sent_ptr = nullptr;          // fresh state from the host
+   if (step(P->buf[i], P->s_cmp)) { return 1; }
+   c->xe_ptr = nullptr;
+   CUDA_OK(cudaEventRecord(P->cmp_done[i], P->s_cmp));
+   CUDA_OK(cudaStreamWaitEvent(P->s_out, P->cmp_done[i], 0));
+   // a call in flight that still reads the buffer we are about to write (other than this one)
+   for (int r = 0; r < NB; r++)
+   { if (r != i && P->in_host[r] == u_out_host && P->n > 0) { CUDA_OK(cudaStreamWaitEvent(P->s_out, P->in_done[r], 0)); } }
+   for (int k = 0; k < NS; k++)
+   {
+      const int64_t o = k * per, len = std::min<int64_t>(per, N - o);
+      if (len > 0)
+      { CUDA_OK(cudaMemcpyAsync(u_out_host + o, P->buf[i] + o, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, P->s_out)); }
+      CUDA_OK(cudaEventRecord(P->slab_out[i][k], P->s_out));
+   }
+   CUDA_OK(cudaEventRecord(P->out_done[i], P->s_out));
+   P->in_host[i] = u_in_host; P->out_host[i] = u_out_host;
+   P->n++;
+   return 0;
+}
+
+extern "C" int rmh_rk_step_host_async(rmh_ctx *c, int ode, int lo_type, double t, double dt, const double *u_in_host,
+                                      double *u_out_host)
+{
+   return host_pipe_step(c, u_in_host, u_out_host, [&](double *u, cudaStream_t s)
+   {
+      double tt = t;
+      return rmh_rk_step(c, ode, lo_type, &tt, dt, u, (void *)s);
+   });
+}
+
+extern "C" int rmh_host_sync(rmh_ctx *c)
+{
+   HostPipe *P = c->pipe;
+   if (!P) { return 0; }
+   CUDA_OK(cudaStreamSynchronize(P->s_in));
+   CUDA_OK(cudaStreamSynchronize(P->s_cmp));
+   CUDA_OK(cudaStreamSynchronize(P->s_out));
+   for (int r = 0; r < HostPipe::NBUF; r++) { P->in_host[r] = nullptr; P->out_host[r] = nullptr; }
    return 0;
 }
 

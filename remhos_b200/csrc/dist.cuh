@@ -69,13 +69,6 @@ static NcclApi *nccl_api()
 }
 
 // ---- device side
-struct PutPeer
-{
-   double *gtr[2];               // the peer's ghost trace arrays
-   double2 *mm[2];               // the peer's (min,max) pair arrays
-   unsigned long long *flag;     // this rank's word among the peer's epoch flags
-   int64_t tr_off, tr_n, mm_off, mm_n;   // ranges in the concatenated tables
-};
 struct PutArgs
 {
    int npeers;
@@ -176,17 +169,36 @@ struct rmh_dist
    int32_t *d_tr_src = nullptr, *d_tr_dst = nullptr, *d_mm_src = nullptr, *d_mm_dst = nullptr;
    unsigned int *d_counter = nullptr;
    double *d_red = nullptr;
+   // fused send of k_stage3c (tables in device memory, see StageSend)
+   StageSend *d_send = nullptr;
+   unsigned int *d_send_counter = nullptr;
+   unsigned int send_groups = 0;
+   bool send_ready = false;
    rmh_nccl_id nccl_id;
    bool have_nccl_id = false;
    rmh_ncclComm_t comm = nullptr;
 };
 
+// RMH_DEBUG_HALO (timing experiments only, results are WRONG): 1 = no put and no wait, 2 = put, no wait
+static int dist_debug_halo()
+{
+   static int v = -1;
+   if (v < 0) { const char *e = getenv("RMH_DEBUG_HALO"); v = e ? atoi(e) : 0; }
+   return v;
+}
+
 static void dist_stage_args(rmh_ctx *c, rmh::StagePArgs &pa, bool in_kernel_wait)
 {
    rmh_dist *d = c->dist;
    if (!d || !d->connected || !in_kernel_wait || d->npeers == 0) { return; }
+   if (dist_debug_halo()) { return; }
    pa.flags = c->flags; pa.n_wait = d->npeers; pa.epoch = c->epoch;
    pa.shell_begin = (c->n_split >= 0) ? c->n_split : 0;
+   if (c->send_next && d->send_ready)
+   {
+      pa.send = d->d_send; pa.send_par = (int)((c->epoch + 1) & 1); pa.send_epoch = c->epoch + 1;
+      pa.send_groups = d->send_groups;
+   }
 }
 
 static int64_t host_identity()
@@ -330,6 +342,111 @@ extern "C" int rmh_dist_connect(rmh_dist *d, int n_blobs, const void *const *blo
    d->put.npeers = np;
    d->put.tr_src = d->d_tr_src; d->put.tr_dst = d->d_tr_dst; d->put.mm_src = d->d_mm_src; d->put.mm_dst = d->d_mm_dst;
    d->put.counter = d->d_counter;
+   // ---- fused send tables: who reads which face of which shell element
+   {
+      // opt-in (RMH_FUSED_SEND=1): measured on 2 B200s the kernel loses to the rotation and the remote stores
+      // what the put launch costs (profiles/r02/README.md), so the stand-alone put kernel is the default
+      const char *nf = getenv("RMH_FUSED_SEND");
+      const int ND = c->ND, NFD = c->NFD, NF = c->NF, D1 = c->D1, dim = c->dim, pdeg = c->p;
+      const int64_t sb = c->n_split, n_shell = c->ne - sb;
+      if (c->fold && dim == 3 && np > 0 && n_shell > 0 && (nf && nf[0] == '1'))
+      {
+         std::vector<int2> face((size_t)n_shell * NF, make_int2(-1, 0));
+         std::vector<uint8_t> perm((size_t)n_shell * NF, 0);
+         std::vector<int16_t> rperm;
+         std::map<std::vector<int16_t>, int> perms;
+         std::vector<std::vector<int2>> mm_of((size_t)n_shell);
+         bool ok = true;
+         for (int k = 0; k < np && ok; k++)
+         {
+            const PutPeer &P = d->put.peer[k];
+            for (int64_t r0 = 0; r0 + NFD <= P.tr_n && ok; r0 += NFD)
+            {
+               const int32_t *src = tr_src.data() + P.tr_off + r0, *dst = tr_dst.data() + P.tr_off + r0;
+               const int64_t le = src[0] / ND;
+               const int32_t slot = dst[0] / NFD;
+               if (le < sb) { ok = false; break; }
+               // my face: the one every requested dof lies on
+               int fs = -1;
+               for (int f = 0; f < NF && fs < 0; f++)
+               {
+                  int axis, side;
+                  face_axis(dim, f, axis, side);
+                  bool all = true;
+                  for (int j = 0; j < NFD && all; j++)
+                  {
+                     int m = src[j] % ND, l[3] = {0, 0, 0};
+                     for (int a = 0; a < dim; a++) { l[a] = m % D1; m /= D1; }
+                     all = (src[j] / ND == le) && (l[axis] == side * pdeg);
+                  }
+                  if (all) { fs = f; }
+               }
+               if (fs < 0) { ok = false; break; }
+               int axis, side;
+               face_axis(dim, fs, axis, side);
+               std::vector<int16_t> key((size_t)NFD, 0);
+               for (int j = 0; j < NFD; j++)          // j = the reader's face index
+               {
+                  int m = src[j] % ND, l[3] = {0, 0, 0}, nat = 0, mul = 1;
+                  for (int a = 0; a < dim; a++) { l[a] = m % D1; m /= D1; }
+                  for (int a = 0; a < dim; a++) { if (a != axis) { nat += l[a] * mul; mul *= D1; } }
+                  if (dst[j] != slot * NFD + j) { ok = false; }
+                  key[nat] = (int16_t)j;               // my natural index -> reader's index
+               }
+               auto it = perms.find(key);
+               int id;
+               if (it == perms.end())
+               {
+                  id = (int)perms.size();
+                  if (id > 255) { ok = false; break; }
+                  perms[key] = id;
+                  rperm.insert(rperm.end(), key.begin(), key.end());
+               }
+               else { id = it->second; }
+               face[(size_t)(le - sb) * NF + fs] = make_int2(k, slot);
+               perm[(size_t)(le - sb) * NF + fs] = (uint8_t)id;
+            }
+            for (int64_t i = 0; i < P.mm_n && ok; i++)
+            {
+               const int64_t e = mm_src[P.mm_off + i];
+               if (e < sb) { ok = false; break; }
+               mm_of[(size_t)(e - sb)].push_back(make_int2(k, mm_dst[P.mm_off + i]));
+            }
+         }
+         if (ok)
+         {
+            std::vector<int32_t> mm_off((size_t)n_shell + 1, 0);
+            std::vector<int2> mm_flat;
+            for (int64_t e = 0; e < n_shell; e++)
+            {
+               mm_off[e] = (int32_t)mm_flat.size();
+               mm_flat.insert(mm_flat.end(), mm_of[e].begin(), mm_of[e].end());
+            }
+            mm_off[n_shell] = (int32_t)mm_flat.size();
+            if (rperm.empty()) { rperm.assign(NFD, 0); }
+            if (mm_flat.empty()) { mm_flat.push_back(make_int2(0, 0)); }
+            PutPeer *d_peers = nullptr;
+            int2 *d_face = nullptr, *d_mm = nullptr;
+            uint8_t *d_perm = nullptr;
+            int16_t *d_rperm = nullptr;
+            int32_t *d_mm_off = nullptr;
+            if (dev_upload(c, &d_peers, d->put.peer, (size_t)np) || dev_upload(c, &d_face, face.data(), face.size()) ||
+                dev_upload(c, &d_perm, perm.data(), perm.size()) || dev_upload(c, &d_rperm, rperm.data(), rperm.size()) ||
+                dev_upload(c, &d_mm_off, mm_off.data(), mm_off.size()) || dev_upload(c, &d_mm, mm_flat.data(), mm_flat.size()) ||
+                dev_alloc(c, &d->d_send_counter, 1)) { return 1; }
+            CUDA_OK(cudaMemset(d->d_send_counter, 0, sizeof(unsigned int)));
+            StageSend hs;
+            hs.peer = d_peers; hs.npeers = np; hs.face = d_face; hs.perm = d_perm; hs.rperm = d_rperm;
+            hs.mm_off = d_mm_off; hs.mm = d_mm; hs.counter = d->d_send_counter;
+            if (dev_upload(c, &d->d_send, &hs, 1)) { return 1; }
+            // groups of the kernel: E elements per warp iteration (SmemC::LG)
+            const int NL = D1 * D1, LG = NL <= 4 ? 4 : (NL <= 8 ? 8 : (NL <= 16 ? 16 : 32)), E = 32 / LG;
+            const int64_t NG = (c->ne + E - 1) / E;
+            d->send_groups = (unsigned int)(NG - sb / E);
+            d->send_ready = true;
+         }
+      }
+   }
    d->connected = true;
    c->dist = d;
    return 0;
@@ -361,19 +478,27 @@ static int dist_wait(rmh_dist *d, unsigned long long ep, bool unpack, cudaStream
 
 // One RK stage on the decomposed mesh: out = a x0 + b (y + dt F(y)); the element min/max of y must be
 // in the context (rmh_stage_minmax, or left there by the previous stage)
-extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0,
-                                 const double *y, double *out, void *stream)
+static int dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0,
+                         const double *y, double *out, void *stream, bool send_out)
 {
    rmh_ctx *c = d->c;
    if (!d->connected) { set_error("rmh_dist_rk_stage: not connected"); return 1; }
    cudaStream_t s = (cudaStream_t)stream;
+   const bool ikw = dist_in_kernel_wait(c, x0, y, out);
+   const bool have_halo = (c->sent_ptr == y && c->sent_epoch == c->epoch + 1);
+   if (!have_halo && c->sent_epoch == c->epoch + 1) { c->epoch += 2; }    // a stale early send owns that epoch
    const unsigned long long ep = c->epoch + 1;
    if (d->npeers > 0)
    {
-      if (dist_put(d, y, ep, c->fold, s)) { return 1; }
-      if (!dist_in_kernel_wait(c, x0, y, out)) { if (dist_wait(d, ep, !c->fold, s)) { return 1; } }
+      if (!have_halo && dist_debug_halo() != 1) { if (dist_put(d, y, ep, c->fold, s)) { return 1; } }
+      if (!ikw) { if (dist_wait(d, ep, !c->fold, s)) { return 1; } }
    }
-   return stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0, s);
+   // the output of this stage is the next stage's input: let the kernel send its halo (shell groups first)
+   c->send_next = send_out && ikw && d->send_ready && d->npeers > 0;
+   const int rc = stage_impl(c, lo_type, dt, 1, a, b, x0, y, out, true, c->bounds_type == 0, s);
+   if (c->send_next && rc == 0) { c->sent_ptr = out; c->sent_epoch = c->epoch + 1; }
+   c->send_next = false;
+   return rc;
 }
 
 static int dist_put(rmh_dist *d, const double *y, unsigned long long ep, bool pairs, cudaStream_t s)
@@ -414,6 +539,8 @@ static int dist_halo(rmh_ctx *c, const double *u, cudaStream_t s)
    c->xe_ptr = nullptr;
    launch_elem_min_max(c->ne, c->ND, u, c->xe_min, c->xe_max, s);
    LAUNCH_OK();
+   if (c->sent_epoch == c->epoch + 1) { c->epoch += 2; }     // an unused early send owns that epoch (dist_rk_stage)
+   c->sent_ptr = nullptr;
    const unsigned long long ep = ++c->epoch;
    if (d->npeers > 0)
    {
@@ -425,6 +552,13 @@ static int dist_halo(rmh_ctx *c, const double *u, cudaStream_t s)
    return 0;
 }
 
+extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0,
+                                 const double *y, double *out, void *stream)
+{
+   d->c->sent_ptr = nullptr;                 // y may have been written by the caller since
+   return dist_rk_stage(d, lo_type, dt, a, b, x0, y, out, stream, false);
+}
+
 // ODESolver::Step for -s 1/2/3 on the decomposed mesh (cf. rmh_rk_step)
 extern "C" int rmh_dist_rk_step(rmh_dist *d, int ode, int lo_type, double *t, double dt, double *u, void *stream)
 {
@@ -433,36 +567,38 @@ extern "C" int rmh_dist_rk_step(rmh_dist *d, int ode, int lo_type, double *t, do
    const bool chain = (c->bounds_type == 0);
    const bool have_xe = chain && c->trust_state && c->xe_ptr == u;
    const bool keep_xe = chain && c->trust_state;
-   if (!have_xe) { if (stage_minmax(c, u, s)) { return 1; } }
+   if (!have_xe) { c->sent_ptr = nullptr; if (stage_minmax(c, u, s)) { return 1; } }
    c->xe_ptr = nullptr;
+   // the output of a stage goes out from inside its kernel when the next stage reads it (w1, w2; u if it is trusted)
+   const bool snd = chain && c->exec_mode != 1;
    // remap: every stage re-assembles at its own time (rmh_set_time; a no-op in transport mode)
    const double t0 = *t;
    if (ode == 1)
    {
       if (rmh_set_time(c, t0, stream)) { return 1; }
-      if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
+      if (dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream, false)) { return 1; }
       CUDA_OK(cudaMemcpyAsync(u, c->w1, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, s));
       if (keep_xe) { c->xe_ptr = u; }
    }
    else if (ode == 2)
    {
       if (rmh_set_time(c, t0, stream)) { return 1; }
-      if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
+      if (dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream, snd)) { return 1; }
       if (!chain) { if (stage_minmax(c, c->w1, s)) { return 1; } }
       if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
-      if (rmh_dist_rk_stage(d, lo_type, dt, 0.5, 0.5, u, c->w1, u, stream)) { return 1; }
+      if (dist_rk_stage(d, lo_type, dt, 0.5, 0.5, u, c->w1, u, stream, snd && keep_xe)) { return 1; }
       if (keep_xe) { c->xe_ptr = u; }
    }
    else if (ode == 3)
    {
       if (rmh_set_time(c, t0, stream)) { return 1; }
-      if (rmh_dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream)) { return 1; }
+      if (dist_rk_stage(d, lo_type, dt, 0.0, 1.0, u, u, c->w1, stream, snd)) { return 1; }
       if (!chain) { if (stage_minmax(c, c->w1, s)) { return 1; } }
       if (rmh_set_time(c, t0 + dt, stream)) { return 1; }
-      if (rmh_dist_rk_stage(d, lo_type, dt, 0.75, 0.25, u, c->w1, c->w2, stream)) { return 1; }
+      if (dist_rk_stage(d, lo_type, dt, 0.75, 0.25, u, c->w1, c->w2, stream, snd)) { return 1; }
       if (!chain) { if (stage_minmax(c, c->w2, s)) { return 1; } }
       if (rmh_set_time(c, t0 + dt / 2, stream)) { return 1; }
-      if (rmh_dist_rk_stage(d, lo_type, dt, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, stream)) { return 1; }
+      if (dist_rk_stage(d, lo_type, dt, 1.0 / 3.0, 2.0 / 3.0, u, c->w2, u, stream, snd && keep_xe)) { return 1; }
       if (keep_xe) { c->xe_ptr = u; }
    }
    else { set_error("rmh_dist_rk_step: ode solver type must be 1, 2 or 3"); return 1; }
@@ -480,6 +616,39 @@ extern "C" int rmh_dist_rk_step_host(rmh_dist *d, int ode, int lo_type, double *
    if (rmh_dist_rk_step(d, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }
    CUDA_OK(cudaMemcpyAsync(u_host, c->w3, bytes, cudaMemcpyDeviceToHost, 0));
    CUDA_OK(cudaStreamSynchronize(0));
+   return 0;
+}
+
+// pipelined variant (host_pipe_step in ctx.cu): every rank queues its step; the halo puts and flag waits of
+// consecutive calls stay ordered on the compute stream
+extern "C" int rmh_dist_rk_step_host_async(rmh_dist *d, int ode, int lo_type, double t, double dt,
+                                           const double *u_in_host, double *u_out_host)
+{
+   return host_pipe_step(d->c, u_in_host, u_out_host, [&](double *u, cudaStream_t s)
+   {
+      double tt = t;
+      return rmh_dist_rk_step(d, ode, lo_type, &tt, dt, u, (void *)s);
+   });
+}
+
+// in-kernel halo wait statistics of this device since the last reset: out[0] warps that had to wait for a
+// peer's flag, out[1] their summed and out[2] longest wait in ns; out[3] warps that reached a shell group
+// and out[4] their summed time from there to their end (ns); out[5] all warps of the ghost-aware launches
+// and out[6] their summed run time (a diagnostic: which rank waits for whom, what the shell costs)
+extern "C" int rmh_halo_wait_stats(rmh_ctx *c, unsigned long long *out, int reset)
+{
+   CUDA_OK(cudaSetDevice(c->device));
+   CUDA_OK(cudaDeviceSynchronize());
+   unsigned long long g[9];
+   CUDA_OK(cudaMemcpyFromSymbol(g, g_halo_wait, sizeof(g)));
+   out[0] = g[0]; out[1] = g[1]; out[2] = g[2];
+   // phase clocks: warps that reached a shell group, their summed time behind that point; all warps, summed run time
+   out[3] = g[5]; out[4] = g[4] - g[3]; out[5] = g[8]; out[6] = g[7] - g[6];
+   if (reset)
+   {
+      const unsigned long long z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      CUDA_OK(cudaMemcpyToSymbol(g_halo_wait, z, sizeof(z)));
+   }
    return 0;
 }
 

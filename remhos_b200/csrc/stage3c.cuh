@@ -77,11 +77,14 @@ struct SmemC
    static constexpr int PSZ = P_A + E * 4;
    static constexpr int OFF_X = NST * PSZ;                  // y- and z-line results [2][E * EL]
    static constexpr int WDBL = OFF_X + 2 * E * EL;
-   static constexpr int I_NE = 0, I_NP = E * NF, I_BI = 2 * E * NF, ISZ = (2 * E * NF + E * N3 + 3) & ~3;
+   // I_B64 (ghost-aware kernels): 64-bit source address of every neighbour face, filled from NE / NP once the
+   // indices have landed
+   static constexpr int I_NE = 0, I_NP = E * NF, I_BI = 2 * E * NF, I_B64 = (2 * E * NF + E * N3 + 1) & ~1;
+   static constexpr int ISZ = (I_B64 + 2 * E * NF + 3) & ~3;
    static constexpr int WINT = NST * ISZ;
    static constexpr int WBYTES = ((WDBL * 8 + WINT * 4) + 15) & ~15;
    static constexpr int PATMAX = 16;
-   static constexpr int CBYTES = (PATMAX * NFD * 2 + 15) & ~15;
+   static constexpr int CBYTES = ((PATMAX + 1) * NFD * 2 + 15) & ~15;     // + the identity pattern (row PATMAX)
    static constexpr size_t bytes(int nw) { return (size_t)CBYTES + (size_t)nw * WBYTES; }
 };
 
@@ -195,6 +198,30 @@ __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *d
    }
    {
       const int *NE_ = ix + S::I_NE, *NP_ = ix + S::I_NP;
+      if (GH)
+      {
+         // per FACE, once: where its trace comes from -- the neighbour's block of y (its pattern row), the
+         // ghost trace array (already in this element's face order: identity row) or, at a domain boundary,
+         // a block of zeros -- so that the per-value loop below is free of case distinctions
+         long long *B64 = reinterpret_cast<long long *>(const_cast<int *>(ix) + S::I_B64);
+         int *NPw = const_cast<int *>(ix) + S::I_NP;
+         const int ne_own = (int)a.fn.ne_owned;
+#pragma unroll
+         for (int f0 = 0; f0 < E * NF; f0 += 32)
+         {
+            const int f = f0 + lane;
+            if (f < nv * NF)
+            {
+               const int nb = NE_[f], pid = NP_[f];
+               const bool gh = nb >= ne_own;
+               const double *p = (nb < 0) ? a.zeros
+                                 : (gh ? a.fn.ughost + (int64_t)(nb - ne_own) * NFD : a.y + (int64_t)nb * ND);
+               B64[f] = (long long)p;
+               NPw[f] = ((nb < 0 || gh) ? S::PATMAX : pid) * NFD;
+            }
+         }
+         __syncwarp();
+      }
       // 32 % NFD == 0 (orders 1 and 3): face and face-DOF index of a lane differ by constants per slot
       constexpr bool P2 = (32 % NFD == 0);
       const int lq = lane / NFD, lj = lane % NFD;
@@ -207,16 +234,21 @@ __device__ __forceinline__ void stagec_fetch_data(const StagePArgs &a, double *d
          if (F < nv * NF)
          {
             const int el = F / NF;
-            const int nb = NE_[F];
-            const int pid = NP_[F];
-            const int loc = spat[pid * NFD + j];
             const unsigned d = sd + (S::P_N + F * NFD + el * (S::NEL - NF * NFD) + j) * 8;
-            const double *src = a.y + (unsigned)((nb < 0 ? 0 : nb) * ND + loc);
             if (GH)
             {
-               if (nb >= a.fn.ne_owned) { src = a.fn.ughost + (unsigned)((nb - (int)a.fn.ne_owned) * NFD + j); }
+               const long long *B64 = reinterpret_cast<const long long *>(ix + S::I_B64);
+               const int loc = spat[NP_[F] + j];
+               cps8(d, reinterpret_cast<const double *>(B64[F]) + loc);
             }
-            cps8z(d, src, nb < 0 ? 0u : 8u);
+            else
+            {
+               const int nb = NE_[F];
+               const int pid = NP_[F];
+               const int loc = spat[pid * NFD + j];
+               const double *src = a.y + (unsigned)((nb < 0 ? 0 : nb) * ND + loc);
+               cps8z(d, src, nb < 0 ? 0u : 8u);
+            }
          }
       }
    }
@@ -281,9 +313,24 @@ __device__ __forceinline__ void fold_bounds(double *BD, int lane)
    }
 }
 
+// halo wait statistics (rmh_halo_wait_stats): [0] warps that found a flag not yet published, [1] their
+// summed and [2] longest wait in ns (only the slow path touches them); phase clocks of the ghost-aware
+// kernels, summed over the warps (differences are exact modulo 2^64): [3] time at the first shell group,
+// [4] end of those warps, [5] their number, [6] start, [7] end and [8] number of all warps.
+__device__ unsigned long long g_halo_wait[9];
+
+__device__ __forceinline__ unsigned long long gtimer()
+{
+   unsigned long long t;
+   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+   return t;
+}
+
 // every lane waits until all n peers have published epoch (k_halo_put's release store, system scope)
 __device__ __forceinline__ void wait_peer_flags(const unsigned long long *flags, int n, unsigned long long epoch)
 {
+   unsigned long long t0 = 0;
+   bool spun = false;
    for (int p = 0; p < n; p++)
    {
       unsigned long long v;
@@ -292,10 +339,17 @@ __device__ __forceinline__ void wait_peer_flags(const unsigned long long *flags,
       {
          asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flags + p) : "memory");
          if (v >= epoch) { break; }
+         if (!spun) { spun = true; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); }
          __nanosleep(256);
          // a peer that died must not hang this GPU: give up after ~20 s and fail the launch loudly
          if (++spins > (1u << 26)) { __trap(); }
       }
+   }
+   if (spun && (threadIdx.x & 31) == 0)
+   {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicAdd(&g_halo_wait[0], 1ull); atomicAdd(&g_halo_wait[1], t1 - t0); atomicMax(&g_halo_wait[2], t1 - t0);
    }
 }
 
@@ -307,7 +361,7 @@ __device__ __forceinline__ double group_sum(double v)
    return v;
 }
 
-template <int D1, int NW, int MINB, int NST, bool GH, bool FOLD>
+template <int D1, int NW, int MINB, int NST, bool GH, bool FOLD, bool SEND>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_stage3c(StagePArgs a, const TabC<D1> tab)
 {
@@ -325,6 +379,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    {
       const int np = a.npat < S::PATMAX ? a.npat : S::PATMAX;
       for (int i = threadIdx.x; i < np * NFD; i += NW * 32) { spat[i] = a.fn.pat[i]; }
+      if (GH) { for (int i = threadIdx.x; i < NFD; i += NW * 32) { spat[S::PATMAX * NFD + i] = (int16_t)i; } }
    }
    // ---- lane roles
    // row owner: element el, row r = iz * D1 + iy
@@ -351,17 +406,31 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    __syncthreads();     // the only block barrier: the pattern table is in place
    const int64_t NG = (a.ne + E - 1) / E;                           // element groups
    const int64_t GW = (int64_t)gridDim.x * NW;
-   int64_t gi = a.e_begin / E + (int64_t)blockIdx.x * NW + w;
+   int64_t gi = (int64_t)blockIdx.x * NW + w;       // LOGICAL group index
    if (gi >= NG) { return; }
+   if (GH) { if (a.flags != nullptr && lane == 0) { atomicAdd(&g_halo_wait[6], gtimer()); atomicAdd(&g_halo_wait[8], 1ull); } }
    const int last_nv = (int)(a.ne - (NG - 1) * E);
    auto nvalid = [&](int64_t g) { return (g + 1 == NG) ? last_nv : E; };
+   // Fused halo send (multi-GPU, a.send): the shell groups [G0, NG) come FIRST, so that their face traces and
+   // (min,max) pairs are on their way to the peers while the interior groups are still being computed:
+   // logical group g is physical group (g + G0) mod NG.  Everything below that touches memory uses the
+   // physical index.
+   // (SEND is its own instantiation: the rotation defeats the strength reduction of every group base address)
+   const int64_t G0 = SEND ? a.shell_begin / E : 0;
+   unsigned int n_sent = 0;                      // shell groups this warp has sent
+   auto ph = [&](int64_t g) { if (SEND) { g += G0; return g >= NG ? g - NG : g; } return g; };
    // multi-GPU: the halo of y must have landed before the first group at or behind shell_begin is fetched
    bool halo_ok = !(GH && a.flags != nullptr);
    auto need_halo = [&](int64_t g)
    {
       if (GH)
       {
-         if (!halo_ok && g * E + E > a.shell_begin) { wait_peer_flags(a.flags, a.n_wait, a.epoch); halo_ok = true; }
+         if (!halo_ok && g * E + E > a.shell_begin)
+         {
+            if (lane == 0) { atomicAdd(&g_halo_wait[3], gtimer()); atomicAdd(&g_halo_wait[5], 1ull); }
+            wait_peer_flags(a.flags, a.n_wait, a.epoch);
+            halo_ok = true;
+         }
       }
    };
    // ---- prologue: indices of the first NST-1 groups, then their data and the next NST-1 index sets
@@ -369,7 +438,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    for (int m = 0; m < NST - 1; m++)
    {
       const int64_t g = gi + m * GW;
-      if (g < NG) { stagec_fetch_idx<D1, NST>(a, six0 + (m % NST) * S::ISZ * 4, g * E, nvalid(g), lane); }
+      if (g < NG) { const int64_t gp = ph(g); stagec_fetch_idx<D1, NST>(a, six0 + (m % NST) * S::ISZ * 4, gp * E, nvalid(gp), lane); }
    }
    cp_async_commit();
    cp_async_wait_all();
@@ -380,9 +449,10 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
       const int64_t g = gi + m * GW;
       if (g < NG)
       {
-         const int nv = nvalid(g);
-         need_halo(g);
-         stagec_fetch_data<D1, NST, GH>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, g * E, nv, lane,
+         const int64_t gp = ph(g);
+         const int nv = nvalid(gp);
+         need_halo(gp);
+         stagec_fetch_data<D1, NST, GH>(a, wsm + (m % NST) * S::PSZ, ismem + (m % NST) * S::ISZ, spat, gp * E, nv, lane,
                                     lane_on && el < nv, row_src, row_dst);
       }
    }
@@ -391,7 +461,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
    for (int m = NST - 1; m < 2 * (NST - 1); m++)
    {
       const int64_t g = gi + m * GW;
-      if (g < NG) { stagec_fetch_idx<D1, NST>(a, six0 + (m % NST) * S::ISZ * 4, g * E, nvalid(g), lane); }
+      if (g < NG) { const int64_t gp = ph(g); stagec_fetch_idx<D1, NST>(a, six0 + (m % NST) * S::ISZ * 4, gp * E, nvalid(gp), lane); }
    }
    cp_async_commit();
 #pragma unroll
@@ -422,13 +492,14 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          }
       }
    };
-   load_x0(gi);
+   load_x0(ph(gi));
    int slot = 0;                 // it % NST
    for (; gi < NG; gi += GW)
    {
       double *dat = wsm + slot * S::PSZ;
       const double *U = dat + S::P_U, *NB = dat + S::P_N, *A = dat + S::P_A, *BD = dat + S::P_B;
-      const int nv = nvalid(gi);
+      const int64_t gp = ph(gi);                 // physical group
+      const int nv = nvalid(gp);
       const bool on = lane_on && el < nv;
       cp_async_wait_group<NST - 2>();
       __syncwarp();      // data(g) and idx(g + (NST-1) GW) landed; the previous group is fully consumed
@@ -441,14 +512,15 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          const int64_t g1 = gi + (int64_t)(NST - 1) * GW, g2 = gi + (int64_t)(2 * (NST - 1)) * GW;
          if (g1 < NG)
          {
-            const int nv1 = nvalid(g1);
-            need_halo(g1);
-            stagec_fetch_data<D1, NST, GH>(a, wsm + s1 * S::PSZ, ismem + s1 * S::ISZ, spat, g1 * E, nv1, lane,
+            const int64_t gp1 = ph(g1);
+            const int nv1 = nvalid(gp1);
+            need_halo(gp1);
+            stagec_fetch_data<D1, NST, GH>(a, wsm + s1 * S::PSZ, ismem + s1 * S::ISZ, spat, gp1 * E, nv1, lane,
                                        lane_on && el < nv1, row_src, row_dst);
          }
-         if (g2 < NG) { stagec_fetch_idx<D1, NST>(a, six0 + s2 * S::ISZ * 4, g2 * E, nvalid(g2), lane); }
+         if (g2 < NG) { const int64_t gp2 = ph(g2); stagec_fetch_idx<D1, NST>(a, six0 + s2 * S::ISZ * 4, gp2 * E, nvalid(gp2), lane); }
          cp_async_commit();
-         if (gi + GW < NG) { load_x0(gi + GW); }
+         if (gi + GW < NG) { load_x0(ph(gi + GW)); }
       }
       if (FOLD) { fold_bounds<E, BEL>(dat + S::P_B, lane); }     // visible to the tail after the __syncwarp below
       // ================= y-lines and z-lines -> XY, XZ (every lane owns one line of each kind)
@@ -619,7 +691,7 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
          }
          if (on)
          {
-            double *p = a.out + gi * (E * ND) + row_src;
+            double *p = a.out + gp * (E * ND) + row_src;
             if (S::V2)
             {
 #pragma unroll
@@ -641,12 +713,79 @@ k_stage3c(StagePArgs a, const TabC<D1> tab)
             }
             if (r == 0 && el < nv)
             {
-               if (FOLD) { a.xe_mm_out[gi * E + el] = make_double2(omin, omax); }
-               else { a.xe_min_out[gi * E + el] = omin; a.xe_max_out[gi * E + el] = omax; }
+               if (FOLD) { a.xe_mm_out[gp * E + el] = make_double2(omin, omax); }
+               else { a.xe_min_out[gp * E + el] = omin; a.xe_max_out[gp * E + el] = omax; }
+            }
+         }
+         // ================= fused halo send: this group's output IS the next stage's input -- store the face
+         // traces the peers asked for (receiver's face order) and the (min,max) pair of every ring element
+         // straight into their windows; the last shell group of the grid publishes the next epoch
+         if (SEND)
+         {
+            if (gp >= G0)
+            {
+               const StageSend &S_ = *a.send;
+               if (on)
+               {
+                  const int64_t es = gp * E + el - a.shell_begin;            // shell-local element
+                  const int2 *sf = S_.face + es * NF;
+                  const uint8_t *sp = S_.perm + es * NF;
+                  auto put = [&](int f, int j, double v)
+                  {
+                     const int2 ps = sf[f];
+                     if (ps.x >= 0) { S_.peer[ps.x].gtr[a.send_par][(int64_t)ps.y * NFD + S_.rperm[(int)sp[f] * NFD + j]] = v; }
+                  };
+                  put(4, iy + D1 * iz, o[0]);
+                  put(2, iy + D1 * iz, o[D1 - 1]);
+#pragma unroll
+                  for (int i = 0; i < D1; i++)
+                  {
+                     if (iy == 0) { put(1, i + D1 * iz, o[i]); }
+                     if (iy == D1 - 1) { put(3, i + D1 * iz, o[i]); }
+                     if (iz == 0) { put(0, i + D1 * iy, o[i]); }
+                     if (iz == D1 - 1) { put(5, i + D1 * iy, o[i]); }
+                  }
+                  if (r == 0)
+                  {
+                     const double2 mm = make_double2(omin, omax);
+                     for (int k = S_.mm_off[es]; k < S_.mm_off[es + 1]; k++)
+                     {
+                        const int2 pd = S_.mm[k];
+                        S_.peer[pd.x].mm[a.send_par][pd.y] = mm;
+                     }
+                  }
+               }
+               // one system fence per WARP, behind its last shell group (they are its first groups): a fence
+               // per group would stall the warp for an NVLink round trip every time
+               n_sent++;
+               __syncwarp();
+               if (lane == 0 && gi + GW >= (int64_t)a.send_groups)
+               {
+                  __threadfence_system();
+                  const unsigned int t = atomicAdd(S_.counter, n_sent);
+                  if (t + n_sent == a.send_groups)
+                  {
+                     *S_.counter = 0;
+                     __threadfence_system();
+                     for (int q = 0; q < S_.npeers; q++)
+                     {
+                        asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(S_.peer[q].flag), "l"(a.send_epoch) : "memory");
+                     }
+                  }
+               }
             }
          }
       }
       slot = (slot + 1 == NST) ? 0 : slot + 1;
+   }
+   if (GH)
+   {
+      if (a.flags != nullptr && lane == 0)
+      {
+         const unsigned long long t = gtimer();
+         atomicAdd(&g_halo_wait[7], t);
+         if (halo_ok) { atomicAdd(&g_halo_wait[4], t); }
+      }
    }
 }
 

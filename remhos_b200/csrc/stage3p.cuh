@@ -80,6 +80,30 @@ struct SmemP
    static constexpr size_t BYTES = (size_t)NDBL * 8 + (size_t)NINT * 4;
 };
 
+// multi-GPU: a peer's window as seen from this rank (dist.cuh)
+struct PutPeer
+{
+   double *gtr[2];               // the peer's ghost trace arrays
+   double2 *mm[2];               // the peer's (min,max) pair arrays
+   unsigned long long *flag;     // this rank's word among the peer's epoch flags
+   int64_t tr_off, tr_n, mm_off, mm_n;   // ranges in the concatenated put tables
+};
+
+// fused halo send of k_stage3c (device memory, built by rmh_dist_connect): per shell element and face the
+// peer that reads it (x = peer index or -1, y = its ghost-face slot) and the permutation from this
+// element's natural face order to the reader's; per shell element the ghost entries that hold its (min,max)
+struct StageSend
+{
+   const PutPeer *peer;
+   int npeers;
+   const int2 *face;             // [n_shell][NF]
+   const uint8_t *perm;          // [n_shell][NF]
+   const int16_t *rperm;         // [n_perm][NFD]
+   const int32_t *mm_off;        // [n_shell + 1]
+   const int2 *mm;               // (peer index, index in the peer's pair array)
+   unsigned int *counter;
+};
+
 struct StagePArgs
 {
    int64_t ne;                // owned elements (end of the launch range)
@@ -104,11 +128,18 @@ struct StagePArgs
    // k_stage3c<FOLD>: bidx = nb27 [NE][27] (element ids; boundary -> the (inf,-inf) sentinel), ent_mm =
    // the input (min,max) pairs [ne + ne_ghost + 1], xe_mm_out = the output pairs (other buffer)
    double2 *xe_mm_out = nullptr;
+   const double *zeros = nullptr;        // NFD zeros: the exterior trace at a domain boundary (ghost-aware kernels)
    // multi-GPU (dist.cuh): peers' epoch flags [n_wait]; elements >= shell_begin depend on the halo
    const unsigned long long *flags = nullptr;
    int n_wait = 0;
    unsigned long long epoch = 0;
    int64_t shell_begin = 0;
+   // k_stage3c<GH, FOLD>: shell groups first, their output sent from the kernel (tables in device memory);
+   // send_par / send_epoch: window parity and epoch of the NEXT stage, send_groups: shell groups of the launch
+   const StageSend *send = nullptr;
+   int send_par = 0;
+   unsigned long long send_epoch = 0;
+   unsigned int send_groups = 0;
 };
 
 template <int D1, int Q, int E>
