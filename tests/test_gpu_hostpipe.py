@@ -87,3 +87,15 @@ def test_null_buffer_is_an_error():
     with pytest.raises(rb.RmhError, match='null host buffer'):
         prob.ctx.rk_step_host_async(3, 5, 0.0, dt, 0)
     prob.close()
+
+
+def test_halo_wait_stats_shape():
+    """rmh_halo_wait_stats on a context without peers: the seven counters, all readable and resettable"""
+    prob, dt = make(1, 0, 0, 0)
+    st = prob.ctx.halo_wait_stats(reset=True)
+    assert set(st) == {'warps_waited', 'wait_ns_sum', 'wait_ns_max', 'warps_shell', 'shell_ns_sum', 'warps', 'run_ns_sum'}
+    u = torch.tensor(prob.u0, device='cuda')
+    prob.ctx.rk_step(3, 5, 0.0, dt, u)
+    st = prob.ctx.halo_wait_stats()
+    assert all(v == 0 for v in st.values()), 'no ghost-aware launch, no halo wait on a single GPU'
+    prob.close()
