@@ -388,6 +388,8 @@ int rmh_rk_step_host(rmh_ctx *ctx, int ode_solver_type, int lo_type, double *t, 
  * call n-1 together; the same host buffer stepped again follows the previous D2H slab by slab, so that both
  * directions of the PCIe link are busy.  The state read is the one at u_in_host when the copy runs; t is the
  * time at the start of the step.  Host buffers must be pinned, and identical or disjoint between calls.
+ * The queued steps use the context's stage intermediates: call rmh_host_sync before entering the context
+ * through any other entry point on another stream (rmh_rk_step_host does so itself).
  * (ODESolver::Step on the reference's host-resident vectors, remhos.cpp:1146-1180.) */
 int rmh_rk_step_host_async(rmh_ctx *ctx, int ode_solver_type, int lo_type, double t, double dt,
                            const double *u_in_host, double *u_out_host);

@@ -109,6 +109,8 @@ struct rmh_ctx
    // matrix-based ("FA") solver data: lumped face matrices always; dense blocks after rmh_fa_setup
    double *dG = nullptr, *BL = nullptr;
    double *faK = nullptr, *faKH = nullptr, *faM = nullptr, *faBI = nullptr;
+   // decomposed FluxBasedFCT: neighbour-side blocks of the ghost faces, private copies of ghost traces (u, R+, R-)
+   double *faBIg = nullptr, *gtr_u = nullptr, *gtr_cp = nullptr, *gtr_cn = nullptr;
    double *faKP = nullptr;     // M_L M^-1 K (PrecondConvectionIntegrator), valid at time kp_t
    double kp_t = -1.0e300;
    int16_t *pat_idx = nullptr;
@@ -169,6 +171,9 @@ static void dist_stage_args(rmh_ctx *c, rmh::StagePArgs &pa, bool in_kernel_wait
 // decomposed meshes, unfused solver path: element min/max of u, then face traces + (min,max) pairs of u
 // exchanged with the peers (one put kernel + k_halo_wait); a no-op on a single rank
 static int dist_halo(rmh_ctx *c, const double *u, cudaStream_t s);
+// face traces of any DOF vector exchanged with the peers and copied into dst [n_gslots][NFD]; the window no
+// longer holds the halo of the state afterwards
+static int dist_traces(rmh_ctx *c, const double *vec, double *dst, cudaStream_t s);
 
 template <typename Tp>
 static int dev_alloc(rmh_ctx *c, Tp **p, size_t n)
@@ -1481,6 +1486,58 @@ static int dispatch_stagec(rmh_ctx *c, const StagePArgs &a, cudaStream_t s)
    RMH_DISPATCH(launch_stagec, c, a, s);
 }
 
+// Decomposed meshes, FluxBasedFCT: the face block the NEIGHBOUR assembles for a face on the rank boundary,
+// k_ji = BI_nbr[b][a] = -sum_q w S(-v.n) phi_a phi_b with S the upwind switch of k_geom_face, formed from
+// this side's geometry at the same quadrature points (conforming face: same points, same weights, opposite
+// normal).  One block per (owned element, face); BIg[slot][a][b] in this element's face numbering.
+template <int DIM>
+__global__ void k_fa_ghost_blocks(GeomArgs g, OpData o, const int32_t *nbr_elem, int64_t ne_owned, double *BIg)
+{
+   __shared__ double dn[64];
+   const int Q = g.Q, NF = 2 * DIM, NFD = o.NFD, NQF = o.NQF;
+   const int64_t e = blockIdx.x / NF;
+   const int f = (int)(blockIdx.x - e * NF);
+   const int64_t nb = nbr_elem[e * NF + f];
+   if (nb < ne_owned) { return; }
+   const int64_t slot = nb - ne_owned;
+   int axis, side;
+   face_axis_side(DIM, f, axis, side);
+   for (int qf = threadIdx.x; qf < NQF; qf += blockDim.x)
+   {
+      const double *l[3], *dl[3];
+      double w = 1.0;
+      int m = qf;
+      for (int a = 0; a < DIM; a++)
+      {
+         if (a == axis) { l[a] = g.Ls + side * g.NG1; dl[a] = g.dLs + side * g.NG1; }
+         else
+         {
+            const int q = m % Q; m /= Q;
+            w *= g.w[q];
+            l[a] = g.L + q * g.NG1; dl[a] = g.dL + q * g.NG1;
+         }
+      }
+      double J[3][3], v[3], det, adj[3][3];
+      const bool nodal_v = (g.velf == nullptr);
+      eval_geom<DIM>(g, e, l, dl, J, v, nodal_v);
+      det_adj<DIM>(J, det, adj);
+      if (!nodal_v) { for (int i = 0; i < DIM; i++) { v[i] = g.velf[((size_t)(e * NF + f) * NQF + qf) * DIM + i]; } }
+      const double sgn = side ? 1.0 : -1.0;
+      double vn = 0.0;
+      for (int i = 0; i < DIM; i++) { vn += v[i] * sgn * adj[axis][i]; }
+      vn = -vn;                                    // seen from the neighbour
+      dn[qf] = w * ((g.exec_mode == 1) ? -fmax(0.0, vn) : fmin(0.0, vn));
+   }
+   __syncthreads();
+   for (int t = threadIdx.x; t < NFD * NFD; t += blockDim.x)
+   {
+      const int a = t / NFD, b = t - a * NFD;
+      double s = 0.0;
+      for (int qf = 0; qf < NQF; qf++) { s += dn[qf] * (face_phi(o, a, qf) * face_phi(o, b, qf)); }
+      BIg[(size_t)slot * NFD * NFD + t] = -s;
+   }
+}
+
 static OpData op_data(const rmh_ctx *c)
 {
    OpData o;
@@ -1566,6 +1623,13 @@ static int run_geom(rmh_ctx *c, double t, cudaStream_t s)
          const size_t shb = (size_t)((c->dim + 1) * c->NQ + 2 * c->Q * c->D1) * sizeof(double);
          k_fa_dense<<<(unsigned)c->ne, 256, shb, s>>>(o, c->ne, c->faK, c->faKH, c->faM, c->faBI);
          LAUNCH_OK();
+         if (c->ne_ghost > 0 && c->n_gslots > 0)
+         {
+            if (c->NQF > 64) { set_error("k_fa_ghost_blocks: more than 64 face quadrature points"); return 1; }
+            if (c->dim == 2) { k_fa_ghost_blocks<2><<<(unsigned)(c->ne * c->NF), 64, 0, s>>>(g, o, c->nbr_elem, c->ne, c->faBIg); }
+            else { k_fa_ghost_blocks<3><<<(unsigned)(c->ne * c->NF), 64, 0, s>>>(g, o, c->nbr_elem, c->ne, c->faBIg); }
+            LAUNCH_OK();
+         }
       }
    }
    c->t_cur = t;
@@ -1586,10 +1650,10 @@ extern "C" int rmh_ctx_destroy(rmh_ctx *c)
 {
    if (!c) { return 0; }
    cudaSetDevice(c->device);
+   host_pipe_free(c);
    for (void *p : c->allocs) { cudaFree(p); }
    for (cudaEvent_t ev : c->prof_ev) { cudaEventDestroy(ev); }
    if (c->pin) { cudaFreeHost(c->pin); }
-   host_pipe_free(c);
    delete c;
    return 0;
 }
@@ -2247,6 +2311,7 @@ extern "C" int rmh_rk_step_host(rmh_ctx *c, int ode, int lo_type, double *t, dou
    // end-to-end entry point: state lives in host memory (as the reference's ODESolver vectors do,
    // remhos.cpp:1680); H2D, one step, D2H.  u_host should be pinned for full PCIe bandwidth.
    const size_t bytes = (size_t)c->N * sizeof(double);
+   if (rmh_host_sync(c)) { return 1; }      // queued steps share the stage intermediates with this call
    CUDA_OK(cudaMemcpyAsync(c->w3, u_host, bytes, cudaMemcpyHostToDevice, 0));
    c->xe_ptr = nullptr;     // fresh state from the host
    if (rmh_rk_step(c, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }
@@ -2268,7 +2333,7 @@ struct HostPipe
    static constexpr int NBUF = 3, NSLAB = 16;
    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
    double *buf[NBUF] = {nullptr, nullptr, nullptr};
-   cudaEvent_t in_done[NBUF], cmp_done[NBUF], out_done[NBUF], slab_out[NBUF][NSLAB];
+   cudaEvent_t in_done[NBUF] = {}, cmp_done[NBUF] = {}, out_done[NBUF] = {}, slab_out[NBUF][NSLAB] = {};
    const double *in_host[NBUF] = {nullptr, nullptr, nullptr};
    double *out_host[NBUF] = {nullptr, nullptr, nullptr};
    uint64_t n = 0;
@@ -2278,12 +2343,15 @@ static void host_pipe_free(rmh_ctx *c)
 {
    HostPipe *P = c->pipe;
    if (!P) { return; }
+   // queued work may still read the buffers that are about to be freed
+   for (cudaStream_t st : {P->s_in, P->s_cmp, P->s_out}) { if (st) { cudaStreamSynchronize(st); } }
+   auto drop = [](cudaEvent_t e) { if (e) { cudaEventDestroy(e); } };
    for (int i = 0; i < HostPipe::NBUF; i++)
    {
-      cudaEventDestroy(P->in_done[i]); cudaEventDestroy(P->cmp_done[i]); cudaEventDestroy(P->out_done[i]);
-      for (int k = 0; k < HostPipe::NSLAB; k++) { cudaEventDestroy(P->slab_out[i][k]); }
+      drop(P->in_done[i]); drop(P->cmp_done[i]); drop(P->out_done[i]);
+      for (int k = 0; k < HostPipe::NSLAB; k++) { drop(P->slab_out[i][k]); }
    }
-   cudaStreamDestroy(P->s_in); cudaStreamDestroy(P->s_cmp); cudaStreamDestroy(P->s_out);
+   for (cudaStream_t st : {P->s_in, P->s_cmp, P->s_out}) { if (st) { cudaStreamDestroy(st); } }
    delete P;
    c->pipe = nullptr;
 }
@@ -2406,6 +2474,12 @@ extern "C" int rmh_fa_setup(rmh_ctx *c, void *stream)
    const size_t nn = (size_t)c->ne * c->ND * c->ND;
    if (dev_alloc(c, &c->faK, nn) || dev_alloc(c, &c->faKH, nn) || dev_alloc(c, &c->faM, nn) ||
        dev_alloc(c, &c->faBI, (size_t)c->ne * c->NF * c->NFD * c->NFD)) { return 1; }
+   if (c->ne_ghost > 0 && c->n_gslots > 0)
+   {
+      const size_t ng = (size_t)c->n_gslots * c->NFD;
+      if (dev_alloc(c, &c->faBIg, ng * c->NFD) || dev_alloc(c, &c->gtr_u, ng) || dev_alloc(c, &c->gtr_cp, ng) ||
+          dev_alloc(c, &c->gtr_cn, ng)) { return 1; }
+   }
    c->fa_on = true;
    return run_geom(c, c->t_cur, (cudaStream_t)stream);
 }
@@ -2491,6 +2565,9 @@ extern "C" int rmh_ho_neumann(rmh_ctx *c, const double *u, double *du, void *str
       LAUNCH_OK();
       double r2 = 0.0;
       if (rmh_reduce(c, 0, res, res, &r2, stream)) { return 1; }
+      // the stopping test is on the GLOBAL residual (MPI_Allreduce, remhos_ho.cpp:174-177): every rank of a
+      // decomposed run does the same number of sweeps as the single-GPU run
+      if (c->dist) { if (rmh_dist_allreduce(c->dist, 0, &r2, 1, stream)) { return 1; } }
       if (std::sqrt(r2) <= 1.0e-4) { return 0; }
       k_neumann_update<<<nb, bs, 0, s>>>(c->N, res, c->ml, du);
       LAUNCH_OK();
@@ -2945,16 +3022,30 @@ extern "C" int rmh_fct_flux_based(rmh_ctx *c, double dt, const double *u, const 
                                   const double *xi_max, double *du, void *stream)
 {
    if (!c->fa_on) { set_error("rmh_fct_flux_based: call rmh_fa_setup first (assembled K_HO, M)"); return 1; }
-   if (c->ne_ghost > 0)
-   { set_error("rmh_fct_flux_based: decomposed meshes are not supported (needs ghost matrices)"); return 1; }
    if (work_vec(c, &c->wk[1]) || work_vec(c, &c->wk[2])) { return 1; }
    FaArgs A = fa_args(c);
    A.ml = m;
    cudaStream_t s = (cudaStream_t)stream;
+   const bool ghosts = (c->ne_ghost > 0 && c->n_gslots > 0);
+   if (ghosts)
+   {
+      // the window holds the halo of u (rmh_limit_mult / the caller's rmh_dist_halo): keep a private copy,
+      // the two coefficient exchanges below reuse the window
+      if (!c->dist) { set_error("rmh_fct_flux_based: ghost elements without a connected rmh_dist"); return 1; }
+      if (c->halo_ptr != u) { if (dist_halo(c, u, s)) { return 1; } }
+      CUDA_OK(cudaMemcpyAsync(c->gtr_u, c->ughost, (size_t)c->n_gslots * c->NFD * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      A.fn.ughost = c->gtr_u;
+      A.BIg = c->faBIg; A.gcp = c->gtr_cp; A.gcn = c->gtr_cn;
+   }
    const int bs = std::min(256, ((c->ND + 31) / 32) * 32);
    const size_t shb = 2 * c->ND * sizeof(double);
    k_flux_coeff<<<(unsigned)c->ne, bs, shb, s>>>(A, dt, u, du_ho, du_lo, xi_min, xi_max, c->wk[1], c->wk[2]);
    LAUNCH_OK();
+   if (ghosts)
+   {
+      // coeff_pos / coeff_neg of the face neighbours (ExchangeFaceNbrData, remhos_fct.cpp:406-409)
+      if (dist_traces(c, c->wk[1], c->gtr_cp, s) || dist_traces(c, c->wk[2], c->gtr_cn, s)) { return 1; }
+   }
    k_flux_apply<<<(unsigned)c->ne, bs, shb, s>>>(A, dt, u, du_ho, du_lo, c->wk[1], c->wk[2], du);
    LAUNCH_OK();
    return 0;

@@ -183,7 +183,12 @@ struct rmh_dist
 static int dist_debug_halo()
 {
    static int v = -1;
-   if (v < 0) { const char *e = getenv("RMH_DEBUG_HALO"); v = e ? atoi(e) : 0; }
+   if (v < 0)
+   {
+      const char *e = getenv("RMH_DEBUG_HALO");
+      v = e ? atoi(e) : 0;
+      if (v) { fprintf(stderr, "remhos_b200: RMH_DEBUG_HALO=%d -- the halo exchange is switched OFF, results are wrong (timing experiments only)\n", v); }
+   }
    return v;
 }
 
@@ -552,6 +557,24 @@ static int dist_halo(rmh_ctx *c, const double *u, cudaStream_t s)
    return 0;
 }
 
+static int dist_traces(rmh_ctx *c, const double *vec, double *dst, cudaStream_t s)
+{
+   rmh_dist *d = c->dist;
+   if (!d || !d->connected) { set_error("dist_traces: no connected rmh_dist"); return 1; }
+   if (c->sent_epoch == c->epoch + 1) { c->epoch += 2; }
+   c->sent_ptr = nullptr;
+   const unsigned long long ep = ++c->epoch;
+   if (d->npeers > 0)
+   {
+      if (dist_put(d, vec, ep, false, s)) { return 1; }
+      if (dist_wait(d, ep, false, s)) { return 1; }
+   }
+   CUDA_OK(cudaMemcpyAsync(dst, c->gtr[ep & 1], (size_t)c->n_gslots * c->NFD * sizeof(double), cudaMemcpyDeviceToDevice, s));
+   c->ughost = c->gtr[ep & 1];
+   c->halo_ptr = nullptr;
+   return 0;
+}
+
 extern "C" int rmh_dist_rk_stage(rmh_dist *d, int lo_type, double dt, double a, double b, const double *x0,
                                  const double *y, double *out, void *stream)
 {
@@ -611,6 +634,7 @@ extern "C" int rmh_dist_rk_step_host(rmh_dist *d, int ode, int lo_type, double *
 {
    rmh_ctx *c = d->c;
    const size_t bytes = (size_t)c->N * sizeof(double);
+   if (rmh_host_sync(c)) { return 1; }      // queued steps share the stage intermediates with this call
    CUDA_OK(cudaMemcpyAsync(c->w3, u_host, bytes, cudaMemcpyHostToDevice, 0));
    c->xe_ptr = nullptr;
    if (rmh_dist_rk_step(d, ode, lo_type, t, dt, c->w3, nullptr)) { return 1; }

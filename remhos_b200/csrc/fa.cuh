@@ -177,6 +177,9 @@ struct FaArgs
    const int16_t *pat_idx;    // [npat][NFD] natural index, on the neighbour's face, of pat[id][j]
    const uint8_t *pat_face;   // [npat] the neighbour's local face
    const double *K, *KH, *M, *BI, *BL, *ml, *inflow;
+   // decomposed meshes, FluxBasedFCT: the neighbour-side face block of every ghost face [n_gslots][NFD][NFD]
+   // (k_fa_ghost_blocks) and the ghost traces of the flux coefficients R+ / R- (remhos_fct.cpp:406-409)
+   const double *BIg = nullptr, *gcp = nullptr, *gcn = nullptr;
    // product remap (FluxBasedFCT::CalcFCTProduct, remhos_fct.cpp:214-246): element-local fluxes
    // beta_j fel_i - beta_i fel_j added to the in-element couplings (null: none)
    const double *pbeta = nullptr, *pfel = nullptr;
@@ -937,7 +940,10 @@ __global__ void k_si_gather(int64_t n, const int32_t *d2c, const double *si, dou
 
 // ---- FluxBasedFCT (Zalesak), gather form: every DOF visits all its couplings of K_HO
 // (in-element via KH / M, across faces via BI of both sides); each flux is evaluated from both
-// ends with the same operands in the same order, so f_ji = -f_ij bit for bit.
+// ends with the same operands in the same order, so f_ji = -f_ij bit for bit.  Across a rank
+// boundary the neighbour's trace comes from the ghost array, its face block from BIg (formed on
+// this side from the same quadrature points: equal to the owner's up to the summation order, so
+// f_ji = -f_ij holds to round-off there) and the visit gets the index -1 - (slot * NFD + b).
 template <typename Visit>
 __device__ __forceinline__ void flux_visit(const FaArgs &A, const double *u, const double *du_ho,
                                            double dt, int64_t e, int i, const double *ue,
@@ -973,10 +979,22 @@ __device__ __forceinline__ void flux_visit(const FaArgs &A, const double *u, con
          const int64_t nb = A.fn.nbr_elem[e * NF + f];
          if (nb < 0) { continue; }
          const int a = face_nat_index(A.dim, A.D1, l, ax);
+         const double *BIe = A.BI + ((size_t)e * NF + f) * NFD * NFD;
+         if (nb >= A.fn.ne_owned)
+         {
+            const int64_t slot = nb - A.fn.ne_owned;
+            const double *BIn = A.BIg + (size_t)slot * NFD * NFD;
+            for (int b = 0; b < NFD; b++)
+            {
+               const double kij = BIe[a * NFD + b], kji = BIn[b * NFD + a];
+               const double dij = fmax(fmax(0.0, -kij), -kji);
+               visit(-1 - (slot * NFD + b), dt * dij * (ui - A.fn.ughost[slot * NFD + b]));
+            }
+            continue;
+         }
          const int pid = A.fn.nbr_pat[e * NF + f];
          const int f2 = A.pat_face[pid];
          const int a2 = A.pat_idx[pid * NFD + a];
-         const double *BIe = A.BI + ((size_t)e * NF + f) * NFD * NFD;
          const double *BIn = A.BI + ((size_t)nb * NF + f2) * NFD * NFD;
          for (int b = 0; b < NFD; b++)
          {
@@ -1035,7 +1053,8 @@ __global__ void k_flux_apply(FaArgs A, double dt, const double *u, const double 
       double s = 0.0;
       flux_visit(A, u, du_ho, dt, e, i, ue, dhe, [&](int64_t gj, double f)
       {
-         const double a = (f >= 0.0) ? fmin(cpi, cn[gj]) : fmin(cni, cp[gj]);
+         const double cnj = (gj < 0) ? A.gcn[-1 - gj] : cn[gj], cpj = (gj < 0) ? A.gcp[-1 - gj] : cp[gj];
+         const double a = (f >= 0.0) ? fmin(cpi, cnj) : fmin(cni, cpj);
          s += f * a;
       });
       du[g] = du_lo[g] + s / A.ml[g] / dt;

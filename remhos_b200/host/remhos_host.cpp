@@ -919,11 +919,12 @@ int remhos(int argc, char *argv[], double &final_mass_u)
    if (comm.world > 1)
    {
       // fused stage path for -ho 3 -lo 5 -fct 2 -s 1/2/3; every other combination runs solver by solver with
-      // one halo exchange per operator evaluation.  Not decomposed: the flux-based FCT (needs the neighbours'
-      // matrix blocks and the R+- exchanges, remhos_fct.cpp:406-409), the monolithic solver (serial in the
-      // reference too), smoothness indicators, product remap, the per-stage -vb checks.
-      Verify(o.fct != 1 && o.mono == 0 && o.si == 0 && !o.ps && !o.vb,
-             "decomposed runs (WORLD_SIZE > 1) do not cover -fct 1, -mono, -si, -ps and -vb");
+      // one halo exchange per operator evaluation (the flux-based FCT: two more, for R+ and R-,
+      // remhos_fct.cpp:406-409).  Not decomposed: the monolithic solver (serial in the reference too),
+      // smoothness indicators, product remap, the per-stage -vb checks.
+      Verify(o.mono == 0 && o.si == 0 && !o.ps && !o.vb,
+             "decomposed runs (WORLD_SIZE > 1) do not cover -mono, -si, -ps and -vb");
+      Verify(!(o.fct == 1 && o.problem >= 10), "decomposed remap runs do not cover -fct 1");
    }
    // ---- combinations the reference rejects (Appendix A of SURVEY.md) or this build lacks
    if (!ODESolver::Known(o.ode))

@@ -382,6 +382,11 @@ DECOMP_GENERAL = [
     ('cube01_hex.mesh', ['-p', 10, '-rs', 2, '-o', 2, '-dt', -1, '-tf', 0.5, '-ho', 3, '-lo', 5, '-fct', 2, '-ms', 6, '-pa']),
     ('inline-quad.mesh', ['-p', 14, '-rs', 2, '-o', 3, '-dt', -1, '-tf', 0.5, '-ho', 3, '-lo', 3, '-fct', 2, '-ms', 8]),
     ('inline-quad.mesh', ['-p', 14, '-rs', 2, '-o', 2, '-dt', 0.004, '-tf', 0.04, '-ho', 3, '-lo', 5, '-fct', 4, '-s', 12]),
+    # FluxBasedFCT across rank boundaries: ghost-face blocks formed locally, R+ / R- exchanged (remhos_fct.cpp:406-409)
+    ('periodic-square.mesh', ['-p', 5, '-rs', 3, '-o', 2, '-dt', 0.004, '-tf', 0.04, '-ho', 3, '-lo', 1, '-fct', 1]),
+    ('periodic-hexagon.mesh', ['-p', 0, '-rs', 2, '-o', 3, '-dt', 0.005, '-tf', 0.05, '-ho', 1, '-lo', 2, '-fct', 1, '-s', 2]),
+    ('periodic-cube.mesh', ['-p', 1, '-rs', 1, '-o', 2, '-dt', 0.01, '-tf', 0.05, '-ho', 3, '-lo', 1, '-fct', 1]),
+    ('inline-quad.mesh', ['-p', 4, '-rs', 2, '-o', 2, '-dt', 0.002, '-tf', 0.02, '-ho', 3, '-lo', 2, '-fct', 1]),
 ]
 
 
@@ -389,7 +394,8 @@ DECOMP_GENERAL = [
 @pytest.mark.parametrize('mesh_name,flags', DECOMP_GENERAL,
                          ids=['RD-clipscale', 'DU-clipscale-rk2', 'hexagon-Neumann-DUprec', 'cube-RDsub', 'idp3-fctproject',
                               'cube-rk4-rotation', 'dtc', 'LO-only', 'inline-quad-boundary', 'remap-3d-fused',
-                              'remap-2d-RD', 'remap-2d-idp2-fctproject'])
+                              'remap-2d-RD', 'remap-2d-idp2-fctproject', 'fluxfct-DU', 'fluxfct-hexagon-Neumann-rk2',
+                              'fluxfct-cube-rotation', 'fluxfct-inline-quad-boundary'])
 def test_cli_decomposed_solver_by_solver(mesh_name, flags):
     """Decomposed runs of the matrix-based / unfused solver combinations (DU, RD, subcell RD, Neumann,
     FCTProject, IDP and RK4 time stepping, automatic dt): `remhos -gpus 2` against the single-GPU run.
@@ -416,5 +422,7 @@ def test_cli_decomposed_rejections():
     torch = pytest.importorskip('torch')
     if torch.cuda.device_count() < 2:
         pytest.skip('needs >= 2 GPUs')
-    rc, out, err = run_cli('-no-vis', '-m', mesh('periodic-square.mesh'), '-p', 5, '-ho', 3, '-lo', 1, '-fct', 1, '-gpus', 2)
+    rc, out, err = run_cli('-no-vis', '-m', mesh('periodic-square.mesh'), '-p', 5, '-ho', 3, '-lo', 1, '-fct', 2, '-mono', 1, '-gpus', 2)
     assert rc == 134 and 'decomposed runs' in err
+    rc, out, err = run_cli('-no-vis', '-m', mesh('inline-quad.mesh'), '-p', 14, '-ho', 3, '-lo', 1, '-fct', 1, '-gpus', 2)
+    assert rc == 134 and 'decomposed remap runs' in err
