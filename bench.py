@@ -212,7 +212,7 @@ def dist_parity_check(rank, world, local_rank):
 def extra_runs(order, rs, local_rank, steps=20):
     """The general paths, same metric, driver-visible: problem 1 (rotation: velocity varies inside an
     element -> FP64 tensor-core kernel k_stage3w) on the bench mesh, and remap (problem 10 on the
-    refined unit cube: quadrature data rebuilt every stage, non-affine mass solve)."""
+    refined unit cube: quadrature data rebuilt for every new stage time, non-affine mass solve)."""
     import torch
     import remhos_b200 as rb
     from remhos_b200.setup_problem import Problem
@@ -264,7 +264,7 @@ def extra_runs(order, rs, local_rank, steps=20):
         n = prob.ctx.ndofs
         out['remap'] = {
             'workload': 'remap -p 10 (Taylor-Green mesh motion), unit cube -rs %d, order %d, operators '
-                        'rebuilt every stage' % (min(rs, 5), order),
+                        'rebuilt for every new stage time (2 of the 3 stage times per RK3 step; t + dt is reused by the next step)' % (min(rs, 5), order),
             'value': n * STAGES * nst / (ms * 1e-3), 'unit': 'DOF*stage/s', 'ms_per_step': ms / nst,
             'steps': nst, 'dofs': n, 'stage_kernel_ms': kms}
         prob.close()

@@ -51,6 +51,13 @@ static std::atomic<int64_t> g_launches{0};
 
 // ============================================================================ context
 struct HostPipe;
+// remap mode: the time-dependent operator data of ONE other time (see rmh_set_time)
+struct GeomSet
+{
+   double *Dvol = nullptr, *detJw = nullptr, *Dface = nullptr, *ml = nullptr, *einv = nullptr, *BL = nullptr;
+   double t = 0.0;
+   bool valid = false;
+};
 struct rmh_ctx
 {
    int dim, p, mo, exec_mode, bounds_type, device;
@@ -131,6 +138,9 @@ struct rmh_ctx
    const double *ughost = nullptr;
    const double *halo_ptr = nullptr;    // state whose ghost traces / (min,max) the window holds (unfused path)
    struct HostPipe *pipe = nullptr;      // rmh_rk_step_host_async
+   GeomSet gspare;                       // remap: second set of operator data (rmh_set_time)
+   size_t n_dvol = 0, n_dface = 0;
+   bool geom_ok = false;                 // the active set holds the operators of t_cur
    // fused halo send (dist.cuh): the stage kernel that wrote sent_ptr has already stored its halo for epoch sent_epoch
    bool send_next = false;
    const double *sent_ptr = nullptr;
@@ -1907,6 +1917,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    const size_t rq = (size_t)((c->Q + 1) & ~1);
    const size_t n_dvol = (c->dim == 3) ? (size_t)c->ne * c->Q * c->Q * rq * 3 : (size_t)c->ne * c->dim * c->NQ;
    const size_t n_dface = (c->dim == 3) ? (size_t)c->ne * c->NF * c->Q * rq : (size_t)c->ne * c->NF * c->NQF;
+   c->n_dvol = n_dvol; c->n_dface = n_dface;
    if (dev_alloc(c, &c->Dvol, n_dvol)) { return fail(); }
    if (dev_alloc(c, &c->detJw, (size_t)c->ne * c->NQ)) { return fail(); }
    if (dev_alloc(c, &c->Dface, n_dface)) { return fail(); }
@@ -1922,6 +1933,7 @@ extern "C" int rmh_ctx_create(const rmh_desc *d, rmh_ctx **out)
    if (d->inflow) { if (dev_upload(c, &c->inflow, d->inflow, (size_t)c->N)) { return fail(); } }
    if (run_geom(c, 0.0, 0)) { return fail(); }
    CUDA_OK(cudaDeviceSynchronize());
+   c->geom_ok = true;
    if (c->exec_mode == 0)
    {
       std::vector<double> ei((size_t)c->ne);
@@ -2008,10 +2020,51 @@ extern "C" int rmh_ctx_quad_points_1d(const rmh_ctx *c, double *q1d, double *w1d
    return 0;
 }
 
+static void swap_geom_sets(rmh_ctx *c)
+{
+   GeomSet &g = c->gspare;
+   std::swap(c->Dvol, g.Dvol); std::swap(c->detJw, g.detJw); std::swap(c->Dface, g.Dface);
+   std::swap(c->ml, g.ml); std::swap(c->einv, g.einv); std::swap(c->BL, g.BL);
+   const double t = c->t_cur; const bool ok = c->geom_ok;
+   c->t_cur = g.t; c->geom_ok = g.valid;
+   g.t = t; g.valid = ok;
+}
+
+// Remap: the operators are functions of t only (mesh position x0 + t v, remhos.cpp:1598-1677).  The context
+// keeps the data of the last TWO distinct times: an RK3-SSP step asks for t, t + dt, t + dt/2 and the next
+// step starts at t + dt again, so one rebuild in three is a pointer swap; asking for the current time again
+// (rmh_mult_unlimited followed by rmh_limit_mult) costs nothing.  Matrix-based solvers and subcell weights
+// keep their data outside the sets: with them every call rebuilds, as before.  RMH_NO_GEOM_CACHE=1: ditto.
 extern "C" int rmh_set_time(rmh_ctx *c, double t, void *stream)
 {
    if (c->exec_mode != 1) { c->t_cur = t; return 0; }
-   return run_geom(c, t, (cudaStream_t)stream);
+   static int no_cache = -1;
+   if (no_cache < 0) { const char *ev = getenv("RMH_NO_GEOM_CACHE"); no_cache = (ev && ev[0] == '1') ? 1 : 0; }
+   if (no_cache || c->fa_on || c->sub_on)
+   {
+      c->gspare.valid = false;
+      c->geom_ok = false;
+      const int rc = run_geom(c, t, (cudaStream_t)stream);
+      c->geom_ok = (rc == 0);
+      return rc;
+   }
+   if (c->geom_ok && c->t_cur == t) { return 0; }
+   GeomSet &g = c->gspare;
+   if (!g.Dvol)
+   {
+      if (dev_alloc(c, &g.Dvol, c->n_dvol) || dev_alloc(c, &g.detJw, (size_t)c->ne * c->NQ) ||
+          dev_alloc(c, &g.Dface, c->n_dface) || dev_alloc(c, &g.ml, (size_t)c->N) ||
+          dev_alloc(c, &g.einv, (size_t)c->ne) || dev_alloc(c, &g.BL, (size_t)c->ne * c->NF * c->NFD)) { return 1; }
+      CUDA_OK(cudaMemsetAsync(g.Dvol, 0, c->n_dvol * sizeof(double), (cudaStream_t)stream));     // padding rows
+      CUDA_OK(cudaMemsetAsync(g.Dface, 0, c->n_dface * sizeof(double), (cudaStream_t)stream));
+      g.valid = false;
+   }
+   swap_geom_sets(c);                                  // the set of the previous time stays around
+   if (c->geom_ok && c->t_cur == t) { return 0; }      // ... and this one was built for t
+   c->geom_ok = false;
+   const int rc = run_geom(c, t, (cudaStream_t)stream);
+   c->geom_ok = (rc == 0);
+   return rc;
 }
 
 extern "C" int rmh_lumped_mass(rmh_ctx *c, double *m_dev, void *stream)
