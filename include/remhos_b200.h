@@ -186,7 +186,11 @@ int rmh_ctx_quad_points_1d(const rmh_ctx *ctx, double *q1d, double *w1d);
 
 /* Remap: move the mesh to x0 + t*v and rebuild all quadrature data, mass inverse data and
  * the lumped mass (AdvectionOperator::MultUnlimited, remhos.cpp:1598-1677). No-op cost in
- * transport mode. */
+ * transport mode.  The operators depend on t only: the context keeps the data of the last two
+ * distinct times, so asking for the current time again is free and an RK3 step (t, t + dt,
+ * t + dt/2, next step t + dt again) rebuilds twice instead of three times.  With the
+ * matrix-based solvers or subcell weights switched on, and with RMH_NO_GEOM_CACHE=1, every
+ * call rebuilds. */
 int rmh_set_time(rmh_ctx *ctx, double t, void *stream);
 
 /* lumpedM (remhos.cpp:705-727; remap refresh :1625-1632) */
