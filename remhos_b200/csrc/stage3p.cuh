@@ -262,7 +262,7 @@ k_stage3p(StagePArgs a, const Tab<D1, Q> tab)
 {
    using S = SmemP<D1, Q, E>;
    using P3 = Smem3<D1, Q, E>;
-   constexpr int ND = S::ND, NQ = S::NQ, QQ = S::QQ, NF = S::NF, NFD = S::NFD, T = S::T, N3 = S::N3;
+   constexpr int ND = S::ND, QQ = S::QQ, NF = S::NF, NFD = S::NFD, T = S::T, N3 = S::N3;
    constexpr int NL = S::NL, NY = S::NY, NT1 = S::NT1, NT2 = S::NT2;
    constexpr int K2 = (NT2 + T - 1) / T;
    constexpr int NK = (ND + 31) / 32;

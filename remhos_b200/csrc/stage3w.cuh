@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 k_stage3w(StagePArgs a, const Tab<D1, Q> tab)
 {
    using S = SmemW<D1, Q>;
-   constexpr int ND = S::ND, QQ = S::QQ, NF = S::NF, NFD = S::NFD, N3 = S::N3, RQ = S::RQ;
+   constexpr int ND = S::ND, NF = S::NF, NFD = S::NFD, RQ = S::RQ;
    constexpr int KF = S::KF, KB = S::KB, NL = S::NL, NY = S::NY, NC = S::NC, NT1 = S::NT1, NT2 = S::NT2;
    constexpr int PZ = S::PZ, PA = S::PA;
    constexpr int NK = (ND + 31) / 32;
