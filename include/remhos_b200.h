@@ -60,6 +60,11 @@ const double *rmh_mesh_nodes(const rmh_mesh *m);
 const int64_t *rmh_mesh_elem_vertices(const rmh_mesh *m);
 /* Keep only the listed elements (used by the domain decomposition); ids are global. */
 int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *elem_ids, rmh_mesh **out);
+/* Mesh::MakeRefined(mesh, factor, BasisType::ClosedUniform) (remhos.cpp:801): every element split into
+ * factor^dim linear sub-elements on the uniform lattice; shared lattice points become shared vertices
+ * (periodic meshes stay periodic).  nodes == NULL: the mesh's own nodes, else [ne][(g+1)^dim][dim].
+ * This is the subcell mesh -save writes as meshLO_*.mesh (remhos.cpp:1021-1026,1371-1376). */
+int rmh_mesh_make_refined(const rmh_mesh *m, int factor, const double *nodes, rmh_mesh **out);
 
 /* On-disk formats (-save, -visit: remhos.cpp:1016-1043,1366-1380).  rmh_mesh_save = Mesh::Print in
  * "MFEM mesh v1.0" with the nodes as the element-wise Gauss-Lobatto field L2_T1_<dim>D_P<g> (nodes ==

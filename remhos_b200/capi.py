@@ -143,6 +143,22 @@ class Mesh:
         check(lib().rmh_mesh_extract(self.h, C.c_int64(ids.size), _ptr(ids), C.byref(h)))
         return Mesh(h)
 
+    def elem_sizes(self):
+        """Mesh::GetElementSize(e) = |det J(centre)|^(1/dim) per element"""
+        h = np.empty(self.ne, dtype=np.float64)
+        check(lib().rmh_mesh_elem_sizes(self.h, _ptr(h)))
+        return h
+
+    def make_refined(self, factor, nodes=None):
+        """Mesh::MakeRefined(mesh, factor, ClosedUniform): factor^dim linear sub-elements per element
+        (the subcell mesh, meshLO_*.mesh); nodes: moved nodes like Mesh.nodes(), default the mesh's own"""
+        h = C.c_void_p()
+        if nodes is not None:
+            nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        check(lib().rmh_mesh_make_refined(self.h, int(factor), _ptr(nodes) if nodes is not None else None,
+                                          C.byref(h)))
+        return Mesh(h)
+
     def partition(self, nparts):
         part = np.zeros(self.ne, dtype=np.int32)
         check(lib().rmh_mesh_partition(self.h, int(nparts), _ptr(part)))

@@ -963,6 +963,95 @@ extern "C" int rmh_mesh_extract(const rmh_mesh *m, int64_t n, const int64_t *ids
    return 0;
 }
 
+// Mesh::MakeRefined(mesh, factor, BasisType::ClosedUniform) (remhos.cpp:801): every element split into
+// factor^dim linear sub-elements on the uniform lattice i / factor -- the subcell mesh of the subcell
+// residual-distribution schemes, written as meshLO_*.mesh by -save (remhos.cpp:1021-1026, 1371-1376).
+// Vertices = distinct lattice points: the order-`factor` DG lattice points united through the face
+// coincidences of the neighbour-DOF map (the same identification the H1 numbering of the smoothness
+// indicator uses), so periodic meshes stay periodic.  nodes == NULL: the mesh's own nodes; else
+// [ne][(g+1)^dim][dim] (the moved mesh of a remap run).  The result has geometry order 1 with
+// element-wise (discontinuous) nodes, as SetCurvature(1, disc_nodes) gives for periodic meshes (:822).
+extern "C" int rmh_mesh_make_refined(const rmh_mesh *mm, int factor, const double *nodes, rmh_mesh **out)
+{
+   const Mesh &M = mm->m;
+   if (factor < 1) { set_error("make_refined: factor must be >= 1"); return 1; }
+   const int dim = M.dim, p = factor, n = p + 1, nf = 2 * dim, nvx = M.nvert();
+   int nd = 1, nfd = 1, ns = 1;
+   for (int a = 0; a < dim; a++) { nd *= n; ns *= p; }
+   for (int a = 0; a < dim - 1; a++) { nfd *= n; }
+   if ((double)M.ne * nd >= 2147483647.0) { set_error("make_refined: int32 overflow"); return 1; }
+   // ---- distinct lattice points
+   std::vector<int32_t> bd((size_t)nf * nfd), nbr((size_t)M.ne * nf * nfd);
+   if (rmh_mesh_dof_maps(mm, p, bd.data(), nbr.data(), nullptr, nullptr, nullptr, nullptr)) { return 1; }
+   const int64_t N = M.ne * nd;
+   std::vector<int64_t> par((size_t)N);
+   for (int64_t i = 0; i < N; i++) { par[i] = i; }
+   auto find = [&](int64_t i)
+   {
+      while (par[i] != i) { par[i] = par[par[i]]; i = par[i]; }
+      return i;
+   };
+   for (int64_t e = 0; e < M.ne; e++)
+      for (int f = 0; f < nf; f++)
+         for (int j = 0; j < nfd; j++)
+         {
+            const int64_t g = nbr[((size_t)e * nf + f) * nfd + j];
+            if (g < 0) { continue; }
+            const int64_t a = find(e * nd + bd[j * nf + f]), b = find(g);       // bd is [nfd][nf]
+            if (a != b) { par[std::max(a, b)] = std::min(a, b); }
+         }
+   std::vector<int64_t> vid((size_t)N, -1);
+   int64_t nv = 0;
+   for (int64_t i = 0; i < N; i++) { const int64_t r = find(i); if (vid[r] < 0) { vid[r] = nv++; } vid[i] = vid[r]; }
+   // ---- positions of the lattice points
+   const int g = M.g, n1 = g + 1;
+   int nn = 1;
+   for (int a = 0; a < dim; a++) { nn *= n1; }
+   std::vector<double> pts((size_t)n);
+   for (int i = 0; i < n; i++) { pts[i] = (double)i / p; }
+   const std::vector<double> L = lagrange(gauss_lobatto_01(n1), pts);      // [n][n1]
+   const double *X = nodes ? nodes : M.X.data();
+   rmh_mesh *r = new rmh_mesh;
+   Mesh &S = r->m;
+   S.dim = dim; S.g = 1; S.nv = nv; S.ne = M.ne * ns;
+   S.ev.resize((size_t)S.ne * nvx);
+   S.X.resize((size_t)S.ne * nvx * dim);
+   std::vector<double> xl((size_t)nd * dim);
+   for (int64_t e = 0; e < M.ne; e++)
+   {
+      const double *Xe = X + (size_t)e * nn * dim;
+      for (int q = 0; q < nd; q++)
+      {
+         int l[3] = {0, 0, 0}, mq = q;
+         for (int a = 0; a < dim; a++) { l[a] = mq % n; mq /= n; }
+         double x[3] = {0, 0, 0};
+         for (int k = 0; k < nn; k++)
+         {
+            int mk = k;
+            double w = 1.0;
+            for (int a = 0; a < dim; a++) { w *= L[(size_t)l[a] * n1 + mk % n1]; mk /= n1; }
+            for (int i = 0; i < dim; i++) { x[i] += w * Xe[k * dim + i]; }
+         }
+         for (int i = 0; i < dim; i++) { xl[(size_t)q * dim + i] = x[i]; }
+      }
+      for (int sc = 0; sc < ns; sc++)
+      {
+         int c[3] = {0, 0, 0}, ms = sc;
+         for (int a = 0; a < dim; a++) { c[a] = ms % p; ms /= p; }
+         const int64_t se = e * ns + sc;
+         for (int k = 0; k < nvx; k++)
+         {
+            int q = 0, mul = 1;
+            for (int a = 0; a < dim; a++) { q += (c[a] + ((k >> a) & 1)) * mul; mul *= n; }
+            S.ev[se * nvx + k] = vid[e * nd + q];
+            for (int i = 0; i < dim; i++) { S.X[((size_t)se * nvx + k) * dim + i] = xl[(size_t)q * dim + i]; }
+         }
+      }
+   }
+   *out = r;
+   return 0;
+}
+
 // ------------------------------------------------------------------- on-disk formats
 // Mesh::Print in "MFEM mesh v1.0" (what pmesh.PrintAsOne writes for -save, remhos.cpp:1016-1030,
 // 1366-1380, and VisItDataCollection for -visit, :1034-1043): elements in MFEM's vertex order,

@@ -347,17 +347,28 @@ void ParFiniteElementSpace::SetupDistributed(double &dt, double &t_final_, int d
    nbr_elem.assign(nbe.begin(), nbe.begin() + (size_t)no * nf);
 }
 
-void ParFiniteElementSpace::SaveMesh(const std::string &path, double t, int precision) const
+void ParFiniteElementSpace::SaveMesh(const std::string &path, double t, int precision, int refine_factor) const
 {
+   std::vector<double> x;
    if (exec_mode == 1 && !vel_nodes_host.empty())
    {
       const double *x0 = rmh_mesh_nodes(mesh);
-      std::vector<double> x(vel_nodes_host.size());
+      x.resize(vel_nodes_host.size());
       for (size_t i = 0; i < x.size(); i++) { x[i] = x0[i] + t * vel_nodes_host[i]; }   // remhos.cpp:1602
-      Check(rmh_mesh_save(mesh, path.c_str(), x.data(), precision));
+   }
+   const double *nodes = x.empty() ? nullptr : x.data();
+   if (refine_factor > 1)
+   {
+      // the subcell mesh: ParMesh::MakeRefined(pmesh, order, ClosedUniform), moved with the HO mesh
+      // (remhos.cpp:801, 1021-1026, 1371-1376)
+      rmh_mesh *sub = nullptr;
+      Check(rmh_mesh_make_refined(mesh, refine_factor, nodes, &sub));
+      const int rc = rmh_mesh_save(sub, path.c_str(), nullptr, precision);
+      rmh_mesh_free(sub);
+      Check(rc);
       return;
    }
-   Check(rmh_mesh_save(mesh, path.c_str(), nullptr, precision));
+   Check(rmh_mesh_save(mesh, path.c_str(), nodes, precision));
 }
 
 void ParFiniteElementSpace::SaveGridFunction(const std::string &path, const std::vector<double> &vals,
@@ -1058,10 +1069,12 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       if (o.ps) { Check(rmh_reduce(pfes.ctx, 0, u.Block(1), lumpedM.Read(), &mass0_us, nullptr)); }   // :1079-1083
       // Print the starting mesh and initial condition (remhos.cpp:1015-1030); VisIt collection (:1032-1043)
       const int precision = 8;
+      const int lo_factor = (o.lo == 4 || o.mono == 2) ? o.order : 1;     // use_subcell_RD (remhos.cpp:610-612)
       if (o.save)
       {
          Verify(comm.world == 1, "-save writes one rank's files (PrintAsOne): run it on one GPU");
          pfes.SaveMesh("meshHO_init.mesh", 0.0, precision);
+         pfes.SaveMesh("meshLO_init.mesh", 0.0, precision, lo_factor);   // the HO mesh itself without a subcell scheme (:870)
          std::vector<double> h = u.HostRead();
          h.resize((size_t)NV);
          pfes.SaveGridFunction("sltn_init.gf", h, precision);
@@ -1190,6 +1203,7 @@ int remhos(int argc, char *argv[], double &final_mass_u)
       if (o.save)                                                        // remhos.cpp:1365-1380,1472-1482
       {
          pfes.SaveMesh("meshHO_final.mesh", t, precision);
+         pfes.SaveMesh("meshLO_final.mesh", t, precision, lo_factor);
          std::vector<double> h = u.HostRead();
          h.resize((size_t)NV);
          pfes.SaveGridFunction("sltn_final.gf", h, precision);

@@ -100,7 +100,7 @@ public:
    bool subcells_ready = false;
    bool dt_control_on = false;      // -dtc 1: the LO rate must stay visible to the dt estimate (unfused path)
    // pmesh.Print of the mesh at time t (remap: moved nodes) / u.Save, in MFEM's formats (remhos.cpp:1016-1030)
-   void SaveMesh(const std::string &path, double t, int precision = 8) const;
+   void SaveMesh(const std::string &path, double t, int precision = 8, int refine_factor = 1) const;
    void SaveGridFunction(const std::string &path, const std::vector<double> &vals, int precision = 8) const;
    // decomposed runs (comm.world > 1): `mesh` is this rank's owned part, the members below hold the rest
    Communicator *comm = nullptr;

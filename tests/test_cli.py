@@ -348,9 +348,11 @@ def test_cli_save_and_visit_write_mfem_files(tmp_path):
     p = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=180, cwd=str(tmp_path))
     assert p.returncode == 0, p.stderr
     names = sorted(os.listdir(tmp_path))
-    for f in ('meshHO_init.mesh', 'meshHO_final.mesh', 'sltn_init.gf', 'sltn_final.gf', 'Remhos_000000.mfem_root',
-              'Remhos_000005.mfem_root', 'Remhos_000010.mfem_root'):
+    for f in ('meshHO_init.mesh', 'meshHO_final.mesh', 'meshLO_init.mesh', 'meshLO_final.mesh', 'sltn_init.gf',
+              'sltn_final.gf', 'Remhos_000000.mfem_root', 'Remhos_000005.mfem_root', 'Remhos_000010.mfem_root'):
         assert f in names, names
+    # no subcell scheme: subcell_mesh = &pmesh (remhos.cpp:870), the LO files repeat the HO ones
+    assert open(tmp_path / 'meshLO_final.mesh').read() == open(tmp_path / 'meshHO_final.mesh').read()
     m0 = rb.Mesh.load(str(tmp_path / 'meshHO_init.mesh'))
     m1 = rb.Mesh.load(str(tmp_path / 'meshHO_final.mesh'))
     assert m0.ne == m1.ne == 64 and m0.geom_order == 2
@@ -366,6 +368,24 @@ def test_cli_save_and_visit_write_mfem_files(tmp_path):
     assert root['cycle'] == 10 and root['domains'] == 1 and 'solution' in root['fields']
     assert os.path.exists(tmp_path / (root['mesh']['path'] % 0)) and os.path.exists(tmp_path / (root['fields']['solution']['path'] % 0))
     assert rb.Mesh.load(str(tmp_path / (root['mesh']['path'] % 0))).ne == 64
+
+
+@pytest.mark.gpu
+def test_cli_save_writes_the_subcell_mesh(tmp_path):
+    """-save with a subcell scheme (-lo 4): meshLO_*.mesh is ParMesh::MakeRefined(pmesh, order, ClosedUniform),
+    moved with the HO mesh in remap mode (remhos.cpp:801, 1021-1026, 1371-1376)"""
+    import remhos_b200 as rb
+    args = ['-no-vis', '-m', mesh('inline-quad.mesh'), '-p', 14, '-rs', 1, '-o', 3, '-dt', 0.01, '-tf', 0.05, '-ho', 3,
+            '-lo', 4, '-fct', 2, '-save']
+    p = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=180, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    ho0, ho1 = rb.Mesh.load(str(tmp_path / 'meshHO_init.mesh')), rb.Mesh.load(str(tmp_path / 'meshHO_final.mesh'))
+    lo0, lo1 = rb.Mesh.load(str(tmp_path / 'meshLO_init.mesh')), rb.Mesh.load(str(tmp_path / 'meshLO_final.mesh'))
+    assert ho0.ne == 64 and lo0.ne == lo1.ne == 64 * 9 and lo0.geom_order == 1
+    assert lo0.nv == (8 * 3 + 1) ** 2
+    assert np.abs(lo0.nodes() - ho0.make_refined(3).nodes()).max() < 1e-7        # 8 digits written
+    assert np.abs(lo1.nodes() - ho1.make_refined(3).nodes()).max() < 1e-7
+    assert np.abs(lo1.nodes() - lo0.nodes()).max() > 1e-3                       # moved
 
 
 DECOMP_GENERAL = [

@@ -173,3 +173,62 @@ def test_mesh_save_round_trip(name, rs, g, tmp_path):
     assert lines[0] == 'FiniteElementSpace' and lines[1] == 'FiniteElementCollection: L2_T2_%dD_P3' % m.dim
     assert lines[2] == 'VDim: 1' and lines[3] == 'Ordering: 0'
     assert np.array_equal(np.array([float(v) for v in lines[5:5 + vals.size]]), vals)
+
+
+@pytest.mark.parametrize('name,rs,g,periodic', [('periodic-square.mesh', 1, 2, True), ('periodic-hexagon.mesh', 0, 2, True),
+                                                ('periodic-cube.mesh', 0, 2, True), ('inline-quad.mesh', 1, 2, False),
+                                                ('cube01_hex.mesh', 1, 3, False)])
+@pytest.mark.parametrize('factor', [1, 2, 3])
+def test_make_refined_is_the_subcell_mesh(name, rs, g, periodic, factor, tmp_path):
+    """rmh_mesh_make_refined = Mesh::MakeRefined(mesh, order, ClosedUniform) (remhos.cpp:801), the mesh -save
+    writes as meshLO_*.mesh: factor^dim linear sub-elements per element on the uniform lattice, shared lattice
+    points are shared vertices (periodic identification kept), positions = the geometry evaluated at i / factor,
+    and the result is a valid mesh for every other function of the module (topology, writer, reader)."""
+    from remhos_b200.capi import lib, check
+    m = rb.Mesh.load(os.path.join(DATA, name)).refine(rs)
+    m.set_curvature(g)
+    dim, ne = m.dim, m.ne
+    r = m.make_refined(factor)
+    assert r.dim == dim and r.ne == ne * factor ** dim and r.geom_order == 1
+    # vertex count: on a torus (all-quad / all-hex periodic mesh) #vertices = #elements; on the box meshes
+    # (n sub-elements per direction) (n + 1)^dim
+    if periodic:
+        assert r.nv == r.ne
+    else:
+        n1 = round(ne ** (1.0 / dim)) * factor
+        assert r.nv == (n1 + 1) ** dim
+    # positions: corner k of sub-element (a, b, c) is the lattice point (a + k_x, b + k_y, c + k_z) / factor
+    pts = np.arange(factor + 1) / factor
+    from remhos_b200.setup_problem import mesh_eval
+    xl = mesh_eval(m, pts).reshape(ne, *([factor + 1] * dim)[::-1], dim)       # [e][z][y][x][dim]
+    X = r.nodes().reshape(ne, factor ** dim, 2 ** dim, dim)
+    for sc in range(factor ** dim):
+        c = [(sc // factor ** a) % factor for a in range(dim)]
+        for k in range(2 ** dim):
+            idx = tuple(c[a] + ((k >> a) & 1) for a in range(dim))[::-1]
+            assert np.abs(X[:, sc, k] - xl[(slice(None),) + idx]).max() < 1e-14
+    # the same vertex id <=> the same point (up to the periodic shift); every vertex id is used
+    ev = r.elem_vertices()
+    assert np.array_equal(np.unique(ev), np.arange(r.nv))
+    if not periodic:
+        pos = np.full((r.nv, dim), np.nan)
+        flat_v, flat_x = ev.reshape(-1), r.nodes().reshape(-1, dim)
+        pos[flat_v] = flat_x
+        assert np.abs(pos[flat_v] - flat_x).max() < 1e-13
+        assert np.unique(np.round(pos, 9), axis=0).shape[0] == r.nv
+    # a valid mesh: neighbour maps, boundary faces, round trip through the writer and the reader
+    maps = r.dof_maps(1)
+    nb = int((maps['nbr_elem'] < 0).sum())
+    nb0 = int((m.dof_maps(1)['nbr_elem'] < 0).sum())
+    assert nb == nb0 * factor ** (dim - 1)
+    p = str(tmp_path / 'lo.mesh')
+    check(lib().rmh_mesh_save(r.h, p.encode(), None, 17))
+    r2 = rb.Mesh.load(p)
+    assert r2.ne == r.ne and np.array_equal(r2.nodes(), r.nodes()) and np.array_equal(r2.elem_vertices(), ev)
+    # moved nodes (remap): linear in the nodes
+    x = m.nodes() * 1.5 + 0.25
+    rm = m.make_refined(factor, x)
+    assert np.abs(rm.nodes() - (r.nodes() * 1.5 + 0.25)).max() < 1e-13
+    # total volume is kept when the geometry is (multi)linear
+    if g == 1 or name in ('periodic-square.mesh', 'periodic-cube.mesh', 'inline-quad.mesh', 'cube01_hex.mesh'):
+        assert abs((r.elem_sizes() ** dim).sum() - (m.elem_sizes() ** dim).sum()) < 1e-12 * ne
